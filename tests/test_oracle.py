@@ -1,0 +1,193 @@
+"""CPU: pin the oracle (oracle/restate.py) against numpy, the reference's own
+doctest pins, and the golden vectors captured from the unmodified reference."""
+
+import json
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from tests.helpers import bits, dataset_from_arrays, load_json, load_npz, panels, same_bits, same_float
+
+PA_GROUPS = {  # CS/fast/constants.py:36-41, row order CS/fast/plotting.py:26-31
+    "all": [(0.0, 360.0)],
+    "down": [(0.0, 30.0), (330.0, 360.0)],
+    "up": [(150.0, 210.0)],
+    "perp": [(40.0, 140.0), (210.0, 330.0)],
+}
+
+
+def group_mask(pa, ranges):
+    m = np.zeros_like(pa, dtype=bool)
+    with np.errstate(invalid="ignore"):
+        for lo, hi in ranges:
+            m |= (pa >= lo) & (pa <= hi)
+    return m
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(7, 64, 96), (5, 10, 12), (3, 1, 4), (4, 129, 6), (2, 200, 8), (3, 96, 64), (2, 5, 7)])
+def test_nansum_orders_match_numpy(dtype, shape):
+    rng = np.random.default_rng(1)
+    c = rng.gamma(2.0, 3.0, shape).astype(dtype)
+    c[rng.random(shape) < 0.05] = np.nan
+    c[0, 0, 0] = -0.0
+    assert np.array_equal(bits(R.nansum_layout_a(c)), bits(np.nansum(c, axis=1)))
+    sel = rng.random(shape[1]) < 0.5
+    assert np.array_equal(bits(R.nansum_layout_a(c, sel)), bits(np.nansum(c[:, sel, :], axis=1)))
+    stored = np.ascontiguousarray(np.transpose(c, (0, 2, 1)))
+    view = np.transpose(stored, (0, 2, 1))
+    assert np.array_equal(bits(R.nansum_layout_b(stored)), bits(np.nansum(view, axis=1)))
+    if 8 <= shape[1] <= 128:
+        assert np.array_equal(bits(R.nansum_layout_b_vec(stored)), bits(np.nansum(view, axis=1)))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_nanpercentile_matches_numpy(dtype):
+    rng = np.random.default_rng(2)
+    for n in [1, 2, 3, 5, 10, 100, 1001, 59200, 300000]:
+        for p in [0, 1, 5, 50, 95, 99, 99.5, 100, 33.3]:
+            v = rng.gamma(2.0, 30.0, n).astype(dtype)
+            if n > 3:
+                v[rng.random(n) < 0.1] = np.nan
+            with np.errstate(invalid="ignore"):
+                assert same_float(np.nanpercentile(v, p), R.nanpercentile(v, p)), (n, p)
+    v = rng.poisson(3.0, 59200).astype(dtype)
+    v[5], v[6] = np.inf, -np.inf
+    for p in [0, 1, 99, 100]:
+        with np.errstate(invalid="ignore"):
+            assert same_float(np.nanpercentile(v, p), R.nanpercentile(v, p))
+    assert np.isnan(R.nanpercentile(np.array([np.nan], dtype=dtype), 50))
+
+
+def test_nanpercentile_float32_index_at_large_n():
+    """At n ~ 3e7 the float32 virtual index is several positions off the float64 one."""
+    rng = np.random.default_rng(3)
+    v = rng.gamma(2.0, 30.0, 20_000_000).astype(np.float32)
+    for p in (95, 99):
+        assert float(np.nanpercentile(v, p)) == R.nanpercentile(v, p)
+
+
+def test_reference_doctest_pins():
+    pins = load_json("doctests.json")
+    assert R.round_extrema(1234, "up") == pins["round_extrema(1234,'up')"] == 1300.0
+    assert R.round_extrema(0.0123, "down") == pins["round_extrema(0.0123,'down')"] == 0.012
+    assert list(R.compute_percentile_bounds(np.array([[1.0, 2.0, 3.0, 100.0]]), 0, 100)) == [1.0, 100.0]
+    assert pins["compute_percentile_bounds([[1,2,3,100]],0,100)"] == [1.0, 100.0]
+    assert list(R.compute_percentile_bounds(np.array([1.0, 2.0, 3.0]), z_min=-5.0, z_max=5.0)) == [-5.0, 5.0]
+    got = R.extrema_overrides({"ees_linear_linear_y_max": 1234, "ees_linear_linear_z_min": 0.0123}, "ees", "linear", "linear")
+    assert list(got) == pins["_extrema_overrides"] == [None, 1300.0, 0.012, None]
+    assert R.extrema_overrides(None, "ees", "linear", "linear") == (None, None, None, None)
+
+
+def _zoom_from_lines(lines, zoom_minutes=6.25):
+    """CS/plotting.py:586-596."""
+    if len(lines) == 1:
+        return lines[0], zoom_minutes * 60
+    c = 0.5 * (lines[0] + lines[1])
+    return c, max(zoom_minutes * 60, abs(lines[1] - lines[0]) * 1.5)
+
+
+def test_panel_restatement_matches_reference_pa_grid():
+    g = load_npz("pa_grid.npz")
+    ds = dataset_from_arrays({k[3:]: v for k, v in g.items() if k.startswith("in_")})
+    lo, hi = g["cusp_idx"]
+    lines = [float(ds["times"][lo]), float(ds["times"][hi])]
+    center, dur = _zoom_from_lines(lines)
+    for zs in ("linear", "log"):
+        for variant, zb in (("raw", (None, None)), ("given", (0.0, 460.0))):
+            ref = panels(g, f"{variant}_{zs}")
+            assert len(ref) == 8
+            k = 0
+            for name in ("all", "down", "up", "perp"):
+                sel = group_mask(ds["pitch_angle"], PA_GROUPS[name])
+                pa_data = ds["data"][:, sel, :]
+                y_hi = 4000 if variant == "raw" else 2900.0
+                emask = (ds["energy"] >= 0) & (ds["energy"] <= y_hi)
+                with np.errstate(invalid="ignore", over="ignore"):
+                    full = np.nansum(pa_data, axis=1)[:, emask].T
+                    vmin, vmax = R.compute_percentile_bounds(full, 1, 99, *zb)
+                for zoom in (False, True):
+                    kw = dict(center=center, window=dur) if zoom else dict(x_min=ds["times"][0], x_max=ds["times"][-1])
+                    got = R.panel(ds["times"], ds["energy"], pa_data, z_scale=zs, z_min=vmin, z_max=vmax, **kw)
+                    assert got["mode"] == ref[k]["mode"]
+                    assert same_float(got["vmin"], ref[k]["vmin"]) and same_float(got["vmax"], ref[k]["vmax"])
+                    assert same_bits(got["matrix"], ref[k]["matrix"])
+                    k += 1
+
+
+def test_panel_restatement_matches_reference_generic():
+    g = load_npz("generic_set.npz")
+    for name in ("f32", "f64", "tep"):
+        ds = dataset_from_arrays({k[len(name) + 4 :]: v for k, v in g.items() if k.startswith(f"in_{name}_")})
+        for zs in ("linear", "log"):
+            ref = panels(g, f"{name}_{zs}")
+            assert len(ref) == 1
+            got = R.panel(ds["times"], ds["energy"], ds["data"], y_max=ds["energy"].max(), z_scale=zs)
+            assert same_bits(got["matrix"], ref[0]["matrix"])
+            assert same_float(got["vmin"], ref[0]["vmin"]) and same_float(got["vmax"], ref[0]["vmax"])
+
+
+def _tree_files():
+    tree = load_npz("extrema_tree.npz")
+    orbits = sorted({int(k.split("_")[0]) for k in tree if k[0].isdigit()})
+    order = ("ees", "eeb", "ies", "ieb")
+    files = []
+    for o in orbits:
+        per = {}
+        for inst in order:
+            if f"{o}_{inst}_data" in tree:
+                ds = dataset_from_arrays({v: tree[f"{o}_{inst}_{v}"] for v in ("time_unix", "data", "energy", "pitch_angle")})
+                per[inst] = (ds["energy"], ds["data"])
+        files.append((o, per))
+    return files, order
+
+
+def test_global_extrema_restatement_matches_reference():
+    files, order = _tree_files()
+    gold = load_json("extrema_tree.json")
+    state = {}
+    for combo in gold["combos"]:  # CLI order: one shared cache (batch_multi_plot_FAST_spectrograms.py:88-93)
+        state = R.global_extrema(files, order, combo["y"], combo["z"], state=state, max_percentile=99.0)
+        assert state == combo["extrema"], (combo["y"], combo["z"])
+    st = R.global_extrema(files, order, "linear", "linear", max_percentile=95.0, compute_mins=True)
+    assert st == gold["pool95_mins"]
+    # fresh cache, linear/log: every orbit is scanned with the running max
+    st = R.global_extrema(files, order, "linear", "log", max_percentile=99.0)
+    assert st == gold["batch_extrema"]
+
+
+def test_running_max_differs_from_final_pool():
+    """The storm orbit makes the prefix running max exceed the final-pool percentile."""
+    files, _ = _tree_files()
+    gold = load_json("extrema_tree.json")["batch_extrema"]
+    pool = []
+    for _o, per in files:
+        if "ees" in per:
+            with np.errstate(invalid="ignore", over="ignore"):
+                c = np.nansum(per["ees"][1], axis=1)
+            pool.append(c[np.isfinite(c) & (c > 0)])
+    final = np.ceil(np.nanpercentile(np.concatenate(pool), 99.0))
+    assert gold["ees_linear_log_z_max"] > final
+
+
+def test_norm_and_colormap_index_semantics():
+    m = np.array([[0.0, 0.5, 1.0, 2.0, -1.0, np.nan]], dtype=np.float32)
+    idx = R.colormap_index(R.normalize(m, 0.0, 1.0))
+    assert idx.tolist() == [[0, 128, 255, R.I_OVER, R.I_UNDER, R.I_BAD]]
+    lg = np.array([[1.0, 10.0, 100.0, 1000.0, 0.5]], dtype=np.float32)
+    idx = R.colormap_index(R.lognorm(lg, 1.0, 100.0))
+    assert idx.tolist() == [[0, 128, 255, R.I_OVER, R.I_UNDER]]
+    with pytest.raises(ValueError):
+        R.lognorm(lg, 10.0, 1.0)
+    with pytest.raises(ValueError):
+        R.lognorm(lg, float("nan"), 1.0)
+
+
+def test_native_float32_log10_flip_rate_is_tiny():
+    """Informational bound: the correctly rounded log10 the product defines vs this machine's np.log10."""
+    rng = np.random.default_rng(5)
+    m = rng.gamma(2.0, 80.0, (96, 4000)).astype(np.float32) + np.float32(0.5)
+    a = R.colormap_index(R.lognorm(m, 1.0, 2000.0))
+    b = R.colormap_index(R.lognorm(m, 1.0, 2000.0, native_log=True))
+    assert np.mean(a != b) < 1e-3
