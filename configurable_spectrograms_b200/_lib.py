@@ -1,0 +1,331 @@
+"""ctypes binding of ``libcsgpu.so`` (C ABI in ``include/csgpu.h``).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+usable, :class:`CsgError` is raised -- the product path never computes on the host.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcsgpu.so")
+
+F32, F64 = 0, 1
+LAYOUT_TPE, LAYOUT_TEP = 0, 1
+MAX_GROUPS = 7
+I_UNDER, I_OVER, I_BAD = 256, 257, 258
+NORM_OK, NORM_VMIN_GT_VMAX, NORM_INVALID = 0, 1, 2
+
+
+class CsgError(RuntimeError):
+    """A libcsgpu call failed (message from ``csg_last_error``)."""
+
+
+# numpy mirrors of the C structs (sizes asserted against the header comments)
+FILE_DESC = np.dtype(
+    [
+        ("d_cube", "<u8"),
+        ("sums_off", "<i8"),
+        ("flags_off", "<i8"),
+        ("T", "<i4"),
+        ("P", "<i4"),
+        ("E", "<i4"),
+        ("bits_off", "<i4"),
+        ("first_block", "<i4"),
+        ("reserved", "<i4", (3,)),
+    ],
+    align=True,
+)
+REGION = np.dtype(
+    [
+        ("mat_off", "<i8"),
+        ("ld", "<i4"),
+        ("t0", "<i4"),
+        ("nt", "<i4"),
+        ("rows_off", "<i4"),
+        ("cols_off", "<i4"),
+        ("ne", "<i4"),
+        ("want_pct", "<i4"),
+        ("reserved", "<i4"),
+        ("p_lo", "<f8"),
+        ("p_hi", "<f8"),
+    ],
+    align=True,
+)
+REGION_STATS = np.dtype(
+    [
+        ("p_lo", "<f8"),
+        ("p_hi", "<f8"),
+        ("min_pos", "<f8"),
+        ("fin_min", "<f8"),
+        ("fin_max", "<f8"),
+        ("n_valid", "<i8"),
+        ("n_nan", "<i4"),
+        ("n_neginf", "<i4"),
+        ("n_posinf", "<i4"),
+        ("n_pos", "<i4"),
+    ],
+    align=True,
+)
+PANEL = np.dtype(
+    [
+        ("region", "<i4"),
+        ("pct_region", "<i4"),
+        ("log_scale", "<i4"),
+        ("first_block", "<i4"),
+        ("z_min", "<f8"),
+        ("z_max", "<f8"),
+        ("out_off", "<i8"),
+    ],
+    align=True,
+)
+PANEL_NORM = np.dtype(
+    [
+        ("vmin", "<f8"),
+        ("vmax", "<f8"),
+        ("fill_lo", "<f8"),
+        ("fill_hi", "<f8"),
+        ("t_vmin", "<f8"),
+        ("t_range", "<f8"),
+        ("status", "<i4"),
+        ("degenerate", "<i4"),
+    ],
+    align=True,
+)
+POOL_ITEM = np.dtype(
+    [("mat_off", "<i8"), ("n_cells", "<i4"), ("E", "<i4"), ("inst", "<i4"), ("pos", "<i4")], align=True
+)
+POOL_QUERY = np.dtype(
+    [("inst", "<i4"), ("pos", "<i4"), ("slot", "<i4"), ("bin", "<i4"), ("rank", "<i8"), ("row_total", "<i8")],
+    align=True,
+)
+assert FILE_DESC.itemsize == 56 and REGION.itemsize == 56 and REGION_STATS.itemsize == 64
+assert PANEL.itemsize == 40 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
+
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+#: every symbol include/csgpu.h declares: (restype, argtypes)
+SIGNATURES = {
+    "csg_abi_version": (_i, []),
+    "csg_device_count": (_i, []),
+    "csg_create": (_vp, [_i, _vp]),
+    "csg_destroy": (None, [_vp]),
+    "csg_last_error": (C.c_char_p, [_vp]),
+    "csg_sync": (_i, [_vp]),
+    "csg_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_sz)]),
+    "csg_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "csg_dev_free": (_i, [_vp, _vp]),
+    "csg_host_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "csg_host_free": (_i, [_vp, _vp]),
+    "csg_host_register": (_i, [_vp, _vp, _sz]),
+    "csg_host_unregister": (_i, [_vp, _vp]),
+    "csg_h2d": (_i, [_vp, _vp, _vp, _sz]),
+    "csg_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "csg_memset": (_i, [_vp, _vp, _i, _sz]),
+    "csg_timer_start": (_i, [_vp, _i]),
+    "csg_timer_stop": (_i, [_vp, _i]),
+    "csg_timer_ms": (_i, [_vp, _i, C.POINTER(C.c_float)]),
+    "csg_launch_count": (_i64, [_vp]),
+    "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i]),
+    "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
+    "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
+    "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "csg_pool_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),
+}
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen ``libcsgpu.so`` and bind every declared symbol (no compute, no GPU needed)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise CsgError(
+            f"{p} not found: build it with `python -m configurable_spectrograms_b200.build` "
+            "(there is no CPU fallback for this path)"
+        )
+    lib = C.CDLL(p, mode=C.RTLD_LOCAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.csg_abi_version() != 1:
+        raise CsgError(f"libcsgpu ABI version {lib.csg_abi_version()} != 1")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def np_dtype_code(dtype) -> int:
+    dt = np.dtype(dtype)
+    if dt == np.float32:
+        return F32
+    if dt == np.float64:
+        return F64
+    raise TypeError(f"unsupported cube dtype {dt}: libcsgpu computes in float32 or float64")
+
+
+class DevBuf:
+    """A device allocation owned by a :class:`Context`."""
+
+    __slots__ = ("ctx", "ptr", "nbytes")
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        out = _vp()
+        ctx._check(ctx.lib.csg_dev_alloc(ctx.handle, max(self.nbytes, 1), C.byref(out)))
+        self.ptr = out.value
+
+    def free(self):
+        if self.ptr and self.ctx.handle:
+            self.ctx.lib.csg_dev_free(self.ctx.handle, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, arr: np.ndarray, offset: int = 0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes, (offset, arr.nbytes, self.nbytes)
+        self.ctx._check(self.ctx.lib.csg_h2d(self.ctx.handle, self.ptr + offset, arr.ctypes.data, arr.nbytes))
+        self.ctx._keep(arr)
+
+    def download(self, dtype, count: int, offset: int = 0, sync: bool = True) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes, (offset, out.nbytes, self.nbytes)
+        self.ctx._check(self.ctx.lib.csg_d2h(self.ctx.handle, out.ctypes.data, self.ptr + offset, out.nbytes))
+        if sync:
+            self.ctx.sync()
+        return out
+
+    def zero(self):
+        self.ctx._check(self.ctx.lib.csg_memset(self.ctx.handle, self.ptr, 0, self.nbytes))
+
+
+class PinnedBuf:
+    """Page-locked host memory exposed as a numpy byte array."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        out = _vp()
+        ctx._check(ctx.lib.csg_host_alloc(ctx.handle, max(self.nbytes, 1), C.byref(out)))
+        self.ptr = out.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr))
+
+    def view(self, dtype, count: int, offset: int = 0) -> np.ndarray:
+        dt = np.dtype(dtype)
+        return self.array[offset : offset + count * dt.itemsize].view(dt)
+
+    def free(self):
+        if self.ptr and self.ctx.handle:
+            self.array = None
+            self.ctx.lib.csg_host_free(self.ctx.handle, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context (``csg_ctx``); all work runs on its stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self.handle = None
+        if self.lib.csg_device_count() <= 0:
+            raise CsgError("no CUDA device available: libcsgpu has no CPU fallback")
+        h = self.lib.csg_create(int(device), _vp(stream) if stream else None)
+        if not h:
+            raise CsgError(self.lib.csg_last_error(None).decode())
+        self.handle = h
+        self.device = int(device)
+        self._alive: list = []
+
+    # -- helpers
+    def _check(self, status: int):
+        if status != 0:
+            raise CsgError(self.lib.csg_last_error(self.handle).decode())
+
+    def _keep(self, obj):
+        """Hold a host array until the next sync (async H2D source)."""
+        self._alive.append(obj)
+
+    def sync(self):
+        self._check(self.lib.csg_sync(self.handle))
+        self._alive.clear()
+
+    def close(self):
+        if self.handle:
+            self.lib.csg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def alloc(self, nbytes: int) -> DevBuf:
+        return DevBuf(self, nbytes)
+
+    def pinned(self, nbytes: int) -> PinnedBuf:
+        return PinnedBuf(self, nbytes)
+
+    def to_device(self, arr: np.ndarray) -> DevBuf:
+        arr = np.ascontiguousarray(arr)
+        buf = DevBuf(self, arr.nbytes)
+        buf.upload(arr)
+        return buf
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sm, mem = _i(), _sz()
+        self._check(self.lib.csg_device_info(self.handle, name, 128, C.byref(sm), C.byref(mem)))
+        return name.value.decode(), sm.value, mem.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.csg_launch_count(self.handle))
+
+    def timer_start(self, slot: int):
+        self._check(self.lib.csg_timer_start(self.handle, slot))
+
+    def timer_stop(self, slot: int):
+        self._check(self.lib.csg_timer_stop(self.handle, slot))
+
+    def timer_ms(self, slot: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.csg_timer_ms(self.handle, slot, C.byref(ms)))
+        return float(ms.value)
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device (created on first use)."""
+    ctx = _default_ctx.get(device)
+    if ctx is None or ctx.handle is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx

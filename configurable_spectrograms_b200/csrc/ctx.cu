@@ -1,0 +1,171 @@
+// Context, memory, timing: the plumbing half of the C ABI (include/csgpu.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+char g_csg_err[512] = "";
+
+int csg_fail(csg_ctx* ctx, int status, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_csg_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  if (ctx) memcpy(g_csg_err, ctx->err, 512);
+  return status;
+}
+
+extern "C" {
+
+int csg_abi_version(void) { return CSG_ABI_VERSION; }
+
+int csg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+csg_ctx* csg_create(int device, void* external_stream) {
+  int n = csg_device_count();
+  if (n <= 0) {
+    csg_fail(nullptr, CSG_ERR_NODEV, "no CUDA device available: libcsgpu has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    csg_fail(nullptr, CSG_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    csg_fail(nullptr, CSG_ERR_CUDA, "cudaSetDevice(%d) failed: %s", device,
+             cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  csg_ctx* ctx = (csg_ctx*)calloc(1, sizeof(csg_ctx));
+  if (!ctx) return nullptr;
+  ctx->device = device;
+  if (external_stream) {
+    ctx->stream = (cudaStream_t)external_stream;
+    ctx->own_stream = false;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      csg_fail(nullptr, CSG_ERR_CUDA, "cudaStreamCreate failed: %s",
+               cudaGetErrorString(cudaGetLastError()));
+      free(ctx);
+      return nullptr;
+    }
+    ctx->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (int i = 0; i < 32; ++i) {
+    cudaEventCreate(&ctx->ev_start[i]);
+    cudaEventCreate(&ctx->ev_stop[i]);
+  }
+  return ctx;
+}
+
+void csg_destroy(csg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 32; ++i) {
+    cudaEventDestroy(ctx->ev_start[i]);
+    cudaEventDestroy(ctx->ev_stop[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  free(ctx);
+}
+
+const char* csg_last_error(csg_ctx* ctx) { return ctx ? ctx->err : g_csg_err; }
+
+int csg_sync(csg_ctx* ctx) {
+  CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CSG_OK;
+}
+
+int csg_device_info(csg_ctx* ctx, char* name, int name_len, int* sm_count, size_t* total_mem) {
+  cudaDeviceProp prop;
+  CSG_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  if (name && name_len > 0) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  return CSG_OK;
+}
+
+int csg_dev_alloc(csg_ctx* ctx, size_t bytes, void** d_ptr) {
+  CSG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return csg_fail(ctx, CSG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return CSG_OK;
+}
+int csg_dev_free(csg_ctx* ctx, void* d_ptr) {
+  CSG_CUDA(ctx, cudaSetDevice(ctx->device));
+  CSG_CUDA(ctx, cudaFree(d_ptr));
+  return CSG_OK;
+}
+int csg_host_alloc(csg_ctx* ctx, size_t bytes, void** h_ptr) {
+  cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return csg_fail(ctx, CSG_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return CSG_OK;
+}
+int csg_host_free(csg_ctx* ctx, void* h_ptr) {
+  CSG_CUDA(ctx, cudaFreeHost(h_ptr));
+  return CSG_OK;
+}
+int csg_host_register(csg_ctx* ctx, void* h_ptr, size_t bytes) {
+  CSG_CUDA(ctx, cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+  return CSG_OK;
+}
+int csg_host_unregister(csg_ctx* ctx, void* h_ptr) {
+  CSG_CUDA(ctx, cudaHostUnregister(h_ptr));
+  return CSG_OK;
+}
+int csg_h2d(csg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return CSG_OK;
+  CSG_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return CSG_OK;
+}
+int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return CSG_OK;
+  CSG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return CSG_OK;
+}
+int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes) {
+  if (bytes == 0) return CSG_OK;
+  CSG_CUDA(ctx, cudaMemsetAsync(d_dst, byte_value, bytes, ctx->stream));
+  return CSG_OK;
+}
+
+int csg_timer_start(csg_ctx* ctx, int slot) {
+  if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "timer slot %d out of range", slot);
+  CSG_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
+  return CSG_OK;
+}
+int csg_timer_stop(csg_ctx* ctx, int slot) {
+  if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "timer slot %d out of range", slot);
+  CSG_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
+  return CSG_OK;
+}
+int csg_timer_ms(csg_ctx* ctx, int slot, float* ms) {
+  if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "timer slot %d out of range", slot);
+  CSG_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop[slot]));
+  CSG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start[slot], ctx->ev_stop[slot]));
+  return CSG_OK;
+}
+int64_t csg_launch_count(csg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// K3 -- fused clamp + normalise + colormap-LUT rasteriser.
+//
+// csg_panel_prepare restates make_spectrogram's z handling (CS/plotting.py:259-279 log branch,
+// :307-315 linear branch) per panel on the device, from the region stats of K2a.
+// csg_rasterise restates what imshow(matrix, cmap=, norm=LogNorm(..) | vmin=,vmax=) colours at
+// cell resolution (CS/plotting.py:280-287,316-324): matplotlib 3.11 Normalize.__call__ /
+// LogNorm (make_norm_from_scale(LogScale, nonpositive="mask")) and Colormap._get_rgba_and_mask.
+// matplotlib is not installable in the build image, so this boundary is restated from the
+// published algorithm (parity unpinned):
+//   x  = D(f64(v) - vmin);  x = D(f64(x) / (vmax - vmin))          [in-place ops, f64 scalars]
+//   log: v -> log10_D(v) first, vmin/vmax -> log10 in f64
+//   xa = x * 256 (in D); xa == 256 -> 255; xa < 0 -> under(256); xa >= 256 -> over(257);
+//   NaN / masked -> bad(258); else trunc(xa).
+// log10_D for float32 is defined as the correctly rounded float32 of the float64 logarithm
+// (numpy's own float32 log10 is libm/SVML dependent).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 32;
+constexpr int I_UNDER = 256, I_OVER = 257, I_BAD = 258;
+
+template <typename T>
+__device__ __forceinline__ T round_to(double v) {
+  return (T)v;
+}
+
+template <typename T>
+__device__ __forceinline__ T log10_d(T v);
+template <>
+__device__ __forceinline__ float log10_d<float>(float v) {
+  return (float)log10((double)v);
+}
+template <>
+__device__ __forceinline__ double log10_d<double>(double v) {
+  return log10(v);
+}
+
+template <typename T>
+__device__ __forceinline__ int cmap_index(T v, const csg_panel_norm& nm, bool log_scale) {
+  if (log_scale) {
+    // np.where(~isfinite(m) | (m <= 0), z_axis_min, m)   CS/plotting.py:278
+    if (!is_finite(v) || v <= T(0)) v = (T)nm.fill_lo;
+  } else {
+    // CS/plotting.py:310-312
+    if (is_nan(v)) v = (T)nm.fill_lo;
+    if (v == (T)(-CUDART_INF)) v = (T)nm.fill_lo;
+    if (v == (T)CUDART_INF) v = (T)nm.fill_hi;
+  }
+  if (nm.degenerate) return 0;  // vmin == vmax: result.fill(0) / np.full_like(value, 0)
+  T x;
+  if (log_scale) {
+    const T t = log10_d<T>(v);
+    x = (T)((double)t - nm.t_vmin);
+    x = (T)((double)x / nm.t_range);
+    if (!is_finite(x)) return I_BAD;  // np.ma.masked_invalid
+  } else {
+    x = (T)((double)v - nm.t_vmin);
+    x = (T)((double)x / nm.t_range);
+  }
+  T xa = mul_rn(x, T(256));
+  if (xa == T(256)) xa = T(255);
+  if (is_nan(xa)) return I_BAD;
+  if (xa < T(0)) return I_UNDER;
+  if (xa >= T(256)) return I_OVER;
+  return (int)xa;
+}
+
+template <typename T>
+__global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n_panels,
+                                     const csg_region_stats* __restrict__ stats,
+                                     csg_panel_norm* __restrict__ norms) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_panels) return;
+  const csg_panel p = panels[i];
+  const csg_region_stats own = stats[p.region];
+  const csg_region_stats pct = stats[p.pct_region >= 0 ? p.pct_region : p.region];
+  // compute_percentile_bounds(matrix, 1, 99, z_min, z_max)   CS/plotting.py:259
+  double zmin = is_nan(p.z_min) ? pct.p_lo : p.z_min;
+  double zmax = is_nan(p.z_max) ? pct.p_hi : p.z_max;
+  csg_panel_norm nm;
+  nm.status = CSG_NORM_OK;
+  nm.degenerate = 0;
+  if (p.log_scale) {
+    // safe_vmin = nanmin(finite positive) or 1e-10; z_min = float(max(z_min, safe_vmin, 1e-10))  :261-276
+    const double safe = own.n_pos > 0 ? own.min_pos : 1e-10;
+    double m = zmin;  // Python max(): keep the first unless a later one compares greater
+    if (safe > m) m = safe;
+    if (1e-10 > m) m = 1e-10;
+    zmin = m;
+    nm.vmin = zmin, nm.vmax = zmax;
+    nm.fill_lo = (double)(T)zmin;
+    nm.fill_hi = (double)(T)zmax;
+    // LogNorm.__call__ checks, in matplotlib's order
+    if (zmin > zmax) {
+      nm.status = CSG_NORM_VMIN_GT_VMAX;
+    } else if (zmin == zmax) {
+      nm.degenerate = 1;
+    }
+    const double tlo = log10(zmin), thi = log10(zmax);
+    nm.t_vmin = tlo;
+    nm.t_range = thi - tlo;
+    if (nm.status == CSG_NORM_OK && !nm.degenerate && !(is_finite(tlo) && is_finite(thi)))
+      nm.status = CSG_NORM_INVALID;
+  } else {
+    nm.fill_lo = (double)(T)zmin;
+    nm.fill_hi = (double)(T)zmax;
+    if (!(is_finite(zmin) && is_finite(zmax) && zmax > zmin)) {
+      // z_min = nanmin(matrix), z_max = nanmax(matrix) over the substituted matrix   :313-315
+      double lo = CUDART_INF, hi = -CUDART_INF;
+      bool any = false;
+      if (own.fin_min <= own.fin_max) {
+        lo = own.fin_min, hi = own.fin_max, any = true;
+      }
+      if ((own.n_nan > 0 || own.n_neginf > 0) && !is_nan(nm.fill_lo)) {
+        lo = fmin(lo, nm.fill_lo), hi = fmax(hi, nm.fill_lo), any = true;
+      }
+      if (own.n_posinf > 0 && !is_nan(nm.fill_hi)) {
+        lo = fmin(lo, nm.fill_hi), hi = fmax(hi, nm.fill_hi), any = true;
+      }
+      zmin = any ? lo : CUDART_NAN;
+      zmax = any ? hi : CUDART_NAN;
+    }
+    nm.vmin = zmin, nm.vmax = zmax;
+    nm.t_vmin = zmin;
+    nm.t_range = zmax - zmin;
+    if (zmin == zmax)
+      nm.degenerate = 1;
+    else if (zmin > zmax)
+      nm.status = CSG_NORM_VMIN_GT_VMAX;
+  }
+  norms[i] = nm;
+}
+
+// One block = one 32x32 (energy x time) tile of one panel.  Cells are read along the energy
+// axis (contiguous in the collapsed (T,E) matrix), coloured, transposed through shared
+// memory and written along the time axis (contiguous in the (E',T') image).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
+                     const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
+                     const csg_panel_norm* __restrict__ norms, int n_panels,
+                     const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
+                     uint16_t* __restrict__ index) {
+  __shared__ uint32_t s_lut[259];
+  __shared__ uint16_t s_idx[kTile][kTile + 2];
+  __shared__ csg_panel_norm s_nm;
+  __shared__ csg_region s_rg;
+  __shared__ int s_panel;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int lo = 0, hi = n_panels - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    s_panel = lo;
+    s_nm = norms[lo];
+    s_rg = regions[panels[lo].region];
+  }
+  for (int i = tid; i < 259; i += 256) s_lut[i] = lut ? lut[i] : 0u;
+  __syncthreads();
+  const csg_panel pn = panels[s_panel];
+  const csg_region& rg = s_rg;
+  if (s_nm.status != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
+
+  const int tiles_t = (rg.nt + kTile - 1) / kTile;
+  const int tile = (int)blockIdx.x - pn.first_block;
+  const int e0 = (tile / tiles_t) * kTile, t0 = (tile % tiles_t) * kTile;
+  const int tx = tid & 31, ty = tid >> 5;
+  const bool log_scale = pn.log_scale != 0;
+
+  const int e = e0 + tx;
+  const int col = e < rg.ne ? __ldg(pool + rg.cols_off + e) : 0;
+#pragma unroll
+  for (int k = 0; k < kTile; k += 8) {
+    const int tt = t0 + ty + k;
+    int idx = 0;
+    if (e < rg.ne && tt < rg.nt) {
+      const int row = rg.rows_off < 0 ? rg.t0 + tt : __ldg(pool + rg.rows_off + tt);
+      const T v = __ldg(mats + rg.mat_off + (long long)row * rg.ld + col);
+      idx = cmap_index<T>(v, s_nm, log_scale);
+    }
+    s_idx[ty + k][tx] = (uint16_t)idx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kTile; k += 8) {
+    const int ee = e0 + ty + k, tt = t0 + tx;
+    if (ee < rg.ne && tt < rg.nt) {
+      const uint16_t idx = s_idx[tx][ty + k];
+      const long long o = pn.out_off + (long long)ee * rg.nt + tt;
+      if (rgba) rgba[o] = s_lut[idx];
+      if (index) index[o] = idx;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t csg_raster_blocks(int32_t ne, int32_t nt) {
+  if (ne <= 0 || nt <= 0) return 0;
+  return ((ne + kTile - 1) / kTile) * ((nt + kTile - 1) / kTile);
+}
+
+int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels, const csg_region* d_regions,
+                      const csg_region_stats* d_stats, int dtype, csg_panel_norm* d_norms) {
+  (void)d_regions;
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_panels <= 0) return CSG_OK;
+  if (!d_panels || !d_stats || !d_norms) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  const int blocks = (n_panels + 127) / 128;
+  if (dtype == CSG_F32)
+    panel_prepare_kernel<float><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
+  else if (dtype == CSG_F64)
+    panel_prepare_kernel<double><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
+  else
+    return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
+  CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
+  return CSG_OK;
+}
+
+int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
+                  const int32_t* d_index_pool, const csg_panel* d_panels, const csg_panel_norm* d_norms,
+                  int n_panels, int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_panels <= 0 || total_blocks <= 0) return CSG_OK;
+  if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
+  if (dtype == CSG_F32)
+    rasterise_kernel<float><<<total_blocks, 256, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
+                                                                   d_norms, n_panels, (const uint32_t*)d_lut,
+                                                                   (uint32_t*)d_rgba, d_index);
+  else if (dtype == CSG_F64)
+    rasterise_kernel<double><<<total_blocks, 256, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
+                                                                    d_panels, d_norms, n_panels, (const uint32_t*)d_lut,
+                                                                    (uint32_t*)d_rgba, d_index);
+  else
+    return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
+  CSG_LAUNCH_CHECK(ctx, "rasterise_kernel");
+  return CSG_OK;
+}
+
+}  // extern "C"

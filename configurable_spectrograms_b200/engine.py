@@ -1,0 +1,405 @@
+"""Batched device engine over libcsgpu: cubes -> sums -> stats -> norms -> rasters.
+
+A :class:`Batch` holds every counts cube of one dtype resident in HBM together with
+the descriptor tables the kernels walk (files, regions, panels, index pool).  The
+reference-shaped host functions (``plotting.make_spectrogram`` ...) build batches of
+one file; the FAST batch driver builds one batch per GPU shard.
+
+Data layout in HBM:
+  cubes   one allocation, each file 256-byte aligned, dtype D
+  sums    per file [(G+1)][T][E] dtype D (group 0 = every pitch bin)
+  flags   per file [T] uint8 (bit g: a non-NaN cell exists in row t of group g)
+  pool    int32 column / row index lists shared by regions
+  rgba / index   per panel [E'][T'] uint32 / uint16, row 0 = lowest energy
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (
+    FILE_DESC,
+    PANEL,
+    PANEL_NORM,
+    REGION,
+    REGION_STATS,
+    Context,
+    CsgError,
+    DevBuf,
+    np_dtype_code,
+)
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+def classify_cube(cube: np.ndarray):
+    """(array to upload, layout, (T,P,E)) for a (time, pitch, energy) cube or view.
+
+    ``load_fast_cdf_dataset`` hands out either a C-contiguous (T,P,E) array or the
+    transposed *view* of a stored (T,E,P) array (reference ``cdf_utils.py:254-255``);
+    numpy's ``nansum(axis=1)`` adds in a different order for the two, so the storage
+    order is part of the input.
+    """
+    if cube.ndim != 3:
+        raise ValueError(f"expected a 3-D (time, pitch, energy) cube, got shape {cube.shape}")
+    T, P, E = cube.shape
+    if cube.flags.c_contiguous:
+        return cube, _lib.LAYOUT_TPE, (T, P, E)
+    stored = cube.transpose(0, 2, 1)
+    if stored.flags.c_contiguous:
+        return stored, _lib.LAYOUT_TEP, (T, P, E)
+    return np.ascontiguousarray(cube), _lib.LAYOUT_TPE, (T, P, E)
+
+
+class Batch:
+    """Cubes of one dtype on one GPU plus the tables of everything to compute from them."""
+
+    def __init__(self, ctx: Context, dtype, n_groups: int = 0):
+        if not 0 <= n_groups <= _lib.MAX_GROUPS:
+            raise ValueError(f"n_groups must be 0..{_lib.MAX_GROUPS}")
+        self.ctx = ctx
+        self.dtype = np.dtype(dtype)
+        self.code = np_dtype_code(dtype)
+        self.G = int(n_groups)
+        self.files: list[dict] = []
+        self._regions: list[tuple] = []
+        self._panels: list[tuple] = []
+        self._pool: list[np.ndarray] = []
+        self._pool_len = 0
+        self._pool_cache: dict[bytes, int] = {}
+        self._sums_elems = 0
+        self._flags_bytes = 0
+        self._bits: list[np.ndarray] = []
+        self._bits_len = 0
+        self._cube_bytes = 0
+        self._pixels = 0
+        # device state
+        self.d_cubes: DevBuf | None = None
+        self.d_sums: DevBuf | None = None
+        self.d_flags: DevBuf | None = None
+        self.d_bits: DevBuf | None = None
+        self.d_files: dict[int, tuple[DevBuf, int, int, int]] = {}
+        self.d_regions: DevBuf | None = None
+        self.d_pool: DevBuf | None = None
+        self.d_stats: DevBuf | None = None
+        self.d_panels: DevBuf | None = None
+        self.d_norms: DevBuf | None = None
+        self.d_rgba: DevBuf | None = None
+        self.d_index: DevBuf | None = None
+        self.d_lut: DevBuf | None = None
+        self._raster_blocks = 0
+        self._tables_dirty = True
+
+    # ------------------------------------------------------------------ files
+    def add_file(self, cube: np.ndarray | None, pa_bits: np.ndarray | None = None, *, shape=None, layout=None, device_ptr=None) -> int:
+        """Register one cube (host array, or a device pointer with ``shape``/``layout``)."""
+        if cube is not None:
+            if cube.dtype != self.dtype:
+                raise TypeError(f"cube dtype {cube.dtype} != batch dtype {self.dtype}")
+            host, layout, (T, P, E) = classify_cube(cube)
+        else:
+            host = None
+            T, P, E = shape
+            layout = _lib.LAYOUT_TPE if layout is None else layout
+        if self.G > 0:
+            if pa_bits is None or len(pa_bits) != P:
+                raise ValueError("pa_bits (uint8[P]) is required when the batch has pitch-angle groups")
+            bits = np.ascontiguousarray(pa_bits, dtype=np.uint8)
+        else:
+            bits = np.zeros(P, dtype=np.uint8)
+        f = {
+            "T": T,
+            "P": P,
+            "E": E,
+            "layout": layout,
+            "host": host,
+            "device_ptr": device_ptr,
+            "cube_off": self._cube_bytes,
+            "sums_off": self._sums_elems,
+            "flags_off": self._flags_bytes,
+            "bits_off": self._bits_len,
+        }
+        self._cube_bytes += _align(T * P * E * self.dtype.itemsize)
+        self._sums_elems += _align((self.G + 1) * T * E * self.dtype.itemsize) // self.dtype.itemsize
+        self._flags_bytes += _align(T, 4)
+        self._bits.append(bits)
+        self._bits_len += P
+        self.files.append(f)
+        self._tables_dirty = True
+        return len(self.files) - 1
+
+    @property
+    def cube_bytes(self) -> int:
+        return sum(f["T"] * f["P"] * f["E"] for f in self.files) * self.dtype.itemsize
+
+    def upload_cubes(self):
+        """H2D of every host cube into one device allocation (async on the ctx stream)."""
+        need = any(f["host"] is not None for f in self.files)
+        if need and (self.d_cubes is None or self.d_cubes.nbytes < self._cube_bytes):
+            self.d_cubes = self.ctx.alloc(self._cube_bytes)
+        for f in self.files:
+            if f["host"] is not None:
+                self.d_cubes.upload(f["host"], f["cube_off"])
+                f["device_ptr"] = self.d_cubes.ptr + f["cube_off"]
+        self._tables_dirty = True
+
+    def _build_file_tables(self):
+        lib = self.ctx.lib
+        self.d_files = {}
+        for layout in (_lib.LAYOUT_TPE, _lib.LAYOUT_TEP):
+            idx = [i for i, f in enumerate(self.files) if f["layout"] == layout and f["T"] > 0]
+            if not idx:
+                continue
+            tab = np.zeros(len(idx), dtype=FILE_DESC)
+            blocks = 0
+            max_p = 1
+            for j, i in enumerate(idx):
+                f = self.files[i]
+                if f["device_ptr"] is None:
+                    raise CsgError("cube not on the device: call upload_cubes() first")
+                tab[j]["d_cube"] = f["device_ptr"]
+                tab[j]["sums_off"] = f["sums_off"]
+                tab[j]["flags_off"] = f["flags_off"]
+                tab[j]["T"], tab[j]["P"], tab[j]["E"] = f["T"], f["P"], f["E"]
+                tab[j]["bits_off"] = f["bits_off"]
+                tab[j]["first_block"] = blocks
+                blocks += lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout)
+                max_p = max(max_p, f["P"])
+            self.d_files[layout] = (self.ctx.to_device(tab), len(idx), blocks, max_p)
+        self.d_bits = self.ctx.to_device(np.concatenate(self._bits) if self._bits else np.zeros(1, np.uint8))
+        if self.d_sums is None or self.d_sums.nbytes < self._sums_elems * self.dtype.itemsize:
+            self.d_sums = self.ctx.alloc(max(self._sums_elems, 1) * self.dtype.itemsize)
+        if self.d_flags is None or self.d_flags.nbytes < self._flags_bytes:
+            self.d_flags = self.ctx.alloc(max(self._flags_bytes, 4))
+        self._tables_dirty = False
+
+    def collapse(self):
+        """K1 over every file (one launch per storage layout present)."""
+        if self._tables_dirty:
+            self._build_file_tables()
+        self.d_flags.zero()
+        for layout, (tab, n, blocks, max_p) in self.d_files.items():
+            self.ctx._check(
+                self.ctx.lib.csg_collapse(
+                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr, self.G, max_p, self.code, layout,
+                    self.d_sums.ptr, self.d_flags.ptr,
+                )
+            )
+
+    def mat_off(self, file: int, group: int) -> int:
+        f = self.files[file]
+        return f["sums_off"] + group * f["T"] * f["E"]
+
+    def sums(self, file: int, group: int = 0) -> np.ndarray:
+        """Download one collapsed (T,E) matrix."""
+        f = self.files[file]
+        if f["T"] == 0:
+            return np.zeros((0, f["E"]), dtype=self.dtype)
+        n = f["T"] * f["E"]
+        a = self.d_sums.download(self.dtype, n, self.mat_off(file, group) * self.dtype.itemsize)
+        return a.reshape(f["T"], f["E"])
+
+    def all_flags(self) -> np.ndarray:
+        return self.d_flags.download(np.uint8, self._flags_bytes)
+
+    def flags(self, file: int, flags_host: np.ndarray | None = None) -> np.ndarray:
+        f = self.files[file]
+        if flags_host is None:
+            return self.d_flags.download(np.uint8, f["T"], f["flags_off"]) if f["T"] else np.zeros(0, np.uint8)
+        return flags_host[f["flags_off"] : f["flags_off"] + f["T"]]
+
+    # ---------------------------------------------------------------- regions
+    def _pool_add(self, idx: np.ndarray) -> int:
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        key = idx.tobytes()
+        off = self._pool_cache.get(key)
+        if off is None:
+            off = self._pool_len
+            self._pool.append(idx)
+            self._pool_len += len(idx)
+            self._pool_cache[key] = off
+        return off
+
+    def add_region(self, file: int, group: int, cols, *, t0: int = 0, nt: int | None = None, rows=None,
+                   want_pct: bool = False, p_lo: float = 1.0, p_hi: float = 99.0) -> int:
+        f = self.files[file]
+        cols = np.asarray(cols, dtype=np.int32)
+        if rows is not None:
+            rows = np.asarray(rows, dtype=np.int32)
+            # contiguous runs need no list
+            if len(rows) > 0 and np.array_equal(rows, np.arange(rows[0], rows[0] + len(rows), dtype=np.int32)):
+                t0, nt, rows = int(rows[0]), len(rows), None
+            elif len(rows) == 0:
+                t0, nt, rows = 0, 0, None
+        if rows is None:
+            nt = f["T"] - t0 if nt is None else nt
+            rows_off = -1
+        else:
+            rows_off = self._pool_add(rows)
+            t0, nt = 0, len(rows)
+        cols_off = self._pool_add(cols) if len(cols) else 0
+        self._regions.append(
+            (self.mat_off(file, group), f["E"], t0, nt, rows_off, cols_off, len(cols), int(want_pct), 0, float(p_lo), float(p_hi))
+        )
+        return len(self._regions) - 1
+
+    def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None) -> int:
+        r = self._regions[region]
+        ne, nt = r[6], r[3]
+        self._panels.append(
+            (region, pct_region, int(bool(log_scale)), self._raster_blocks,
+             np.nan if z_min is None else float(z_min), np.nan if z_max is None else float(z_max), self._pixels)
+        )
+        self._raster_blocks += self.ctx.lib.csg_raster_blocks(ne, nt)
+        self._pixels += ne * nt
+        return len(self._panels) - 1
+
+    def panel_shape(self, panel: int) -> tuple[int, int]:
+        r = self._regions[self._panels[panel][0]]
+        return r[6], r[3]
+
+    def upload_tables(self):
+        """Region / panel / index tables -> device (call after the last add_*)."""
+        regions = np.array(self._regions, dtype=REGION) if self._regions else np.zeros(0, REGION)
+        self.d_regions = self.ctx.to_device(regions) if len(regions) else None
+        pool = np.concatenate(self._pool) if self._pool else np.zeros(1, np.int32)
+        self.d_pool = self.ctx.to_device(pool)
+        self.d_stats = self.ctx.alloc(max(len(regions), 1) * REGION_STATS.itemsize)
+        self.upload_panels()
+
+    def upload_panels(self):
+        panels = np.array(self._panels, dtype=PANEL) if self._panels else np.zeros(0, PANEL)
+        self.d_panels = self.ctx.to_device(panels) if len(panels) else None
+        if len(panels):
+            if self.d_norms is None or self.d_norms.nbytes < len(panels) * PANEL_NORM.itemsize:
+                self.d_norms = self.ctx.alloc(len(panels) * PANEL_NORM.itemsize)
+
+    def set_panel_bounds(self, panel: int, z_min=None, z_max=None):
+        p = list(self._panels[panel])
+        p[4] = np.nan if z_min is None else float(z_min)
+        p[5] = np.nan if z_max is None else float(z_max)
+        self._panels[panel] = tuple(p)
+
+    # ------------------------------------------------------------------ stages
+    def run_stats(self):
+        """K2a over every region."""
+        if not self._regions:
+            return
+        self.ctx._check(
+            self.ctx.lib.csg_region_stats_run(
+                self.ctx.handle, self.d_sums.ptr, self.code, self.d_regions.ptr, len(self._regions),
+                self.d_pool.ptr, self.d_stats.ptr,
+            )
+        )
+
+    def stats(self) -> np.ndarray:
+        if not self._regions:
+            return np.zeros(0, REGION_STATS)
+        return self.d_stats.download(REGION_STATS, len(self._regions))
+
+    def prepare(self):
+        """Resolve every panel's normalisation on the device."""
+        if not self._panels:
+            return
+        self.ctx._check(
+            self.ctx.lib.csg_panel_prepare(
+                self.ctx.handle, self.d_panels.ptr, len(self._panels), self.d_regions.ptr, self.d_stats.ptr,
+                self.code, self.d_norms.ptr,
+            )
+        )
+
+    def norms(self) -> np.ndarray:
+        if not self._panels:
+            return np.zeros(0, PANEL_NORM)
+        return self.d_norms.download(PANEL_NORM, len(self._panels))
+
+    def set_lut(self, lut259: np.ndarray):
+        lut = np.ascontiguousarray(lut259, dtype=np.uint8)
+        if lut.shape != (259, 4):
+            raise ValueError("LUT must be (259, 4) uint8: 256 colours + under + over + bad")
+        self.d_lut = self.ctx.to_device(lut)
+
+    def rasterise(self, want_rgba: bool = True, want_index: bool = True):
+        """K3 over every panel."""
+        if not self._panels:
+            return
+        if want_rgba and self.d_lut is None:
+            raise CsgError("set_lut() before rasterise(want_rgba=True)")
+        if want_rgba and (self.d_rgba is None or self.d_rgba.nbytes < self._pixels * 4):
+            self.d_rgba = self.ctx.alloc(max(self._pixels, 1) * 4)
+        if want_index and (self.d_index is None or self.d_index.nbytes < self._pixels * 2):
+            self.d_index = self.ctx.alloc(max(self._pixels, 1) * 2)
+        self.ctx._check(
+            self.ctx.lib.csg_rasterise(
+                self.ctx.handle, self.d_sums.ptr, self.code, self.d_regions.ptr, self.d_pool.ptr, self.d_panels.ptr,
+                self.d_norms.ptr, len(self._panels), self._raster_blocks,
+                self.d_lut.ptr if self.d_lut is not None else None,
+                self.d_rgba.ptr if want_rgba else None, self.d_index.ptr if want_index else None,
+            )
+        )
+
+    def panel_index(self, panel: int) -> np.ndarray:
+        ne, nt = self.panel_shape(panel)
+        off = self._panels[panel][6]
+        return self.d_index.download(np.uint16, ne * nt, off * 2).reshape(ne, nt)
+
+    def panel_rgba(self, panel: int) -> np.ndarray:
+        ne, nt = self.panel_shape(panel)
+        off = self._panels[panel][6]
+        return self.d_rgba.download(np.uint8, ne * nt * 4, off * 4).reshape(ne, nt, 4)
+
+    def all_rgba(self) -> np.ndarray:
+        return self.d_rgba.download(np.uint8, self._pixels * 4)
+
+    def all_index(self) -> np.ndarray:
+        return self.d_index.download(np.uint16, self._pixels)
+
+    @property
+    def n_regions(self) -> int:
+        return len(self._regions)
+
+    @property
+    def n_panels(self) -> int:
+        return len(self._panels)
+
+    @property
+    def n_pixels(self) -> int:
+        return self._pixels
+
+
+def collapse_host(cube: np.ndarray, pa_bits: np.ndarray | None = None, n_groups: int = 0, ctx: Context | None = None):
+    """``csg_collapse_host``: the drop-in for ``COLLAPSE_FUNCTION(cube, axis=1)``.
+
+    Returns ``(sums[(G+1), T, E], row_flags[T])``.
+    """
+    ctx = ctx or _lib.default_context()
+    host, layout, (T, P, E) = classify_cube(np.asarray(cube))
+    host = np.ascontiguousarray(host)
+    code = np_dtype_code(host.dtype)
+    sums = np.zeros((n_groups + 1, T, E), dtype=host.dtype)
+    flags = np.zeros(T, dtype=np.uint8)
+    bits = np.ascontiguousarray(pa_bits, dtype=np.uint8) if n_groups else None
+    ctx._check(
+        ctx.lib.csg_collapse_host(
+            ctx.handle, host.ctypes.data, T, P, E, code, layout, bits.ctypes.data if bits is not None else None,
+            n_groups, sums.ctypes.data, flags.ctypes.data,
+        )
+    )
+    return sums, flags
+
+
+def nansum(cube, axis: int = 1):
+    """GPU ``np.nansum(cube, axis=1)`` with numpy's exact summation order (the
+    reference's pluggable ``COLLAPSE_FUNCTION``, ``constants.py:12``)."""
+    cube = np.asarray(cube)
+    if cube.ndim != 3:
+        raise ValueError("nansum: expected a 3-D cube")
+    if axis != 1:
+        cube = np.moveaxis(cube, axis, 1)
+    sums, _ = collapse_host(cube)
+    return sums[0]

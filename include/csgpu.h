@@ -1,0 +1,241 @@
+/* csgpu.h -- C ABI of libcsgpu.so, the B200 (sm_100a) implementation of the
+ * Configurable-Spectrograms data-parallel batch path.
+ *
+ * The reference (ev-hansen/Configurable-Spectrograms) has no FFI of its own; its
+ * operator surface on this path is a set of numpy / matplotlib call sites inside
+ * Python functions.  Every entry point below names the
+ * reference call site(s) it replaces ("CS/" = src/configurable_spectrograms/).
+ * INTEGRATION.md shows the ctypes stubs a maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns a csg_status (0 = OK)
+ *     except constructors/accessors; csg_last_error() returns the message.
+ *   - all pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *   - one csg_ctx per GPU, not thread-safe; all work is enqueued on the context's
+ *     stream (own stream, or an external cudaStream_t handed to csg_create()).
+ *   - dtype: CSG_F32 / CSG_F64 is the dtype D of the counts cube; sums,
+ *     percentiles and normalisation are computed in D exactly like numpy /
+ *     matplotlib do.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef CSGPU_H
+#define CSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CSG_API __attribute__((visibility("default")))
+#else
+#define CSG_API
+#endif
+
+typedef enum {
+  CSG_OK = 0,
+  CSG_ERR_CUDA = 1,   /* a CUDA runtime call failed (message has the CUDA error) */
+  CSG_ERR_ARG = 2,    /* invalid argument */
+  CSG_ERR_NOMEM = 3,  /* allocation failed */
+  CSG_ERR_NODEV = 4   /* no usable CUDA device */
+} csg_status;
+
+enum { CSG_F32 = 0, CSG_F64 = 1 };
+/* memory order of a counts cube */
+enum {
+  CSG_LAYOUT_TPE = 0, /* C-contiguous (time, pitch, energy): np.nansum(axis=1) is an ascending-p chain  */
+  CSG_LAYOUT_TEP = 1  /* stored (time, energy, pitch), collapsed through the transposed view of
+                         CS/cdf_utils.py:254-255: numpy's 8-accumulator pairwise order                 */
+};
+#define CSG_MAX_GROUPS 7 /* pitch-angle groups per file besides the unmasked total */
+
+typedef struct csg_ctx csg_ctx;
+
+/* ------------------------------------------------------------------ context */
+CSG_API int csg_abi_version(void);
+CSG_API int csg_device_count(void);
+/* external_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for an own stream */
+CSG_API csg_ctx* csg_create(int device, void* external_stream);
+CSG_API void csg_destroy(csg_ctx* ctx);
+CSG_API const char* csg_last_error(csg_ctx* ctx); /* ctx may be NULL: error of a failed csg_create() */
+CSG_API int csg_sync(csg_ctx* ctx);
+/* "NVIDIA B200", SM count, total memory bytes */
+CSG_API int csg_device_info(csg_ctx* ctx, char* name, int name_len, int* sm_count, size_t* total_mem);
+
+/* ------------------------------------------------------------------- memory */
+CSG_API int csg_dev_alloc(csg_ctx* ctx, size_t bytes, void** d_ptr);
+CSG_API int csg_dev_free(csg_ctx* ctx, void* d_ptr);
+CSG_API int csg_host_alloc(csg_ctx* ctx, size_t bytes, void** h_ptr); /* pinned */
+CSG_API int csg_host_free(csg_ctx* ctx, void* h_ptr);
+CSG_API int csg_host_register(csg_ctx* ctx, void* h_ptr, size_t bytes); /* pin caller memory (cdflib arrays) */
+CSG_API int csg_host_unregister(csg_ctx* ctx, void* h_ptr);
+CSG_API int csg_h2d(csg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
+CSG_API int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
+CSG_API int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes);
+
+/* ------------------------------------------------------------------- timing */
+/* CUDA-event stopwatch slots (0..31) on the ctx stream. */
+CSG_API int csg_timer_start(csg_ctx* ctx, int slot);
+CSG_API int csg_timer_stop(csg_ctx* ctx, int slot);
+CSG_API int csg_timer_ms(csg_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
+/* number of kernels this context has launched since creation */
+CSG_API int64_t csg_launch_count(csg_ctx* ctx);
+
+/* ------------------------------------------------------------- K1: collapse */
+/* One counts cube.  Replaces COLLAPSE_FUNCTION = np.nansum(cube, axis=1)
+ * (CS/constants.py:12) at CS/plotting.py:188, CS/fast/plotting.py:128,278,
+ * CS/fast/extrema.py:259, together with the pitch-angle gather
+ * data[:, mask, :] (CS/fast/plotting.py:121-127) and the zoom test
+ * np.any(~np.isnan(cube[window])) (CS/plotting.py:597-603). */
+typedef struct {
+  const void* d_cube; /* device cube, dtype D, layout as given to csg_collapse()         */
+  int64_t sums_off;   /* element offset in d_sums of this file's [(G+1)][T][E] block    */
+  int64_t flags_off;  /* byte offset in d_row_flags of this file's [T] flag bytes       */
+  int32_t T, P, E;
+  int32_t bits_off;    /* byte offset in d_pa_bits of this file's [P] membership bytes   */
+  int32_t first_block; /* exclusive prefix sum of csg_collapse_blocks() over the files   */
+  int32_t reserved[3];
+} csg_file_desc; /* 56 bytes */
+
+/* thread blocks csg_collapse() uses for one (T,P,E) file (for first_block) */
+CSG_API int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout);
+
+/* sums[file][0] = sum over every pitch bin; sums[file][1+g] = sum over bins p with
+ * (d_pa_bits[bits_off+p] >> g) & 1.  NaN counts as +0, fill values and +-inf are
+ * summed as-is, result dtype = D, summation order bit-identical to numpy's
+ * (SURVEY.md Appendix B).  d_row_flags[flags_off+t] bit 0 / bit 1+g: some non-NaN
+ * cell exists in row t among all / group-g pitch bins (any energy).
+ * All files of one call share dtype, layout and n_groups. */
+CSG_API int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
+                 const uint8_t* d_pa_bits, int n_groups, int max_P, int dtype, int layout,
+                 void* d_sums, uint8_t* d_row_flags);
+
+/* Host-buffer convenience for one cube: the drop-in for COLLAPSE_FUNCTION(array, axis=1).
+ * h_pa_bits may be NULL when n_groups == 0.  h_sums receives [(G+1)][T][E] of dtype D,
+ * h_row_flags (may be NULL) [T]. */
+CSG_API int csg_collapse_host(csg_ctx* ctx, const void* h_cube, int32_t T, int32_t P, int32_t E, int dtype,
+                      int layout, const uint8_t* h_pa_bits, int n_groups, void* h_sums,
+                      uint8_t* h_row_flags);
+
+/* ------------------------------------------- K2a: region stats + percentiles */
+/* A region is the cell set of one energy-time matrix slice after the reference's
+ * masks (CS/plotting.py:191-219, CS/fast/plotting.py:116-118,129-130,279-281):
+ * output row j (energy, after the descending flip) = column d_index_pool[cols_off+j]
+ * of the collapsed (T,E) matrix, output column i = row t0+i (rows_off < 0) or row
+ * d_index_pool[rows_off+i]. */
+typedef struct {
+  int64_t mat_off; /* element offset of the (T,E) matrix in d_mats                */
+  int32_t ld;      /* elements between consecutive time rows (= E)                */
+  int32_t t0, nt;
+  int32_t rows_off; /* -1: contiguous rows [t0, t0+nt)                             */
+  int32_t cols_off;
+  int32_t ne;
+  int32_t want_pct; /* 0: min/max/counts only                                      */
+  int32_t reserved;
+  double p_lo, p_hi; /* percentiles (0..100), e.g. 1 and 99                         */
+} csg_region;        /* 56 bytes */
+
+/* np.nanpercentile(matrix, p) twice (CS/percentile_utils.py:87-88), plus the
+ * reductions of CS/plotting.py:261-262 (safe_vmin) and :313-315 (nanmin/nanmax). */
+typedef struct {
+  double p_lo, p_hi;       /* linear-interpolation percentiles in D arithmetic; NaN if no valid cell */
+  double min_pos;          /* min over finite cells > 0; +inf when none                               */
+  double fin_min, fin_max; /* min / max over finite cells; +inf / -inf when none                      */
+  int64_t n_valid;         /* non-NaN cells                                                           */
+  int32_t n_nan, n_neginf, n_posinf, n_pos; /* n_pos = finite cells > 0                               */
+} csg_region_stats;                         /* 64 bytes */
+
+CSG_API int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
+                         int n_regions, const int32_t* d_index_pool, csg_region_stats* d_out);
+
+/* ------------------------------------------------------ K3: norm + colormap */
+/* One imshow panel (CS/plotting.py:276-287 log, :308-324 linear). */
+typedef struct {
+  int32_t region;     /* cells to draw; its stats give safe_vmin and the linear fallback  */
+  int32_t pct_region; /* stats entry whose p_lo/p_hi stand in for z bounds that are NaN   */
+  int32_t log_scale;  /* 1: LogNorm branch, 0: linear branch                              */
+  int32_t first_block; /* exclusive prefix sum of csg_raster_blocks(ne, nt)               */
+  double z_min, z_max; /* explicit bounds (reference z_axis_min / z_axis_max); NaN = None */
+  int64_t out_off;     /* pixel offset of this panel in d_rgba / d_index (ne rows x nt)   */
+} csg_panel;           /* 40 bytes */
+
+enum {
+  CSG_NORM_OK = 0,
+  CSG_NORM_VMIN_GT_VMAX = 1, /* matplotlib: ValueError("vmin must be less or equal to vmax") */
+  CSG_NORM_INVALID = 2       /* matplotlib LogNorm: ValueError("Invalid vmin or vmax")       */
+};
+typedef struct {
+  double vmin, vmax;       /* bounds handed to LogNorm(vmin,vmax) / imshow(vmin=,vmax=)            */
+  double fill_lo, fill_hi; /* substitutes written into the matrix (already rounded to D)          */
+  double t_vmin, t_range;  /* log: log10(vmin), log10(vmax)-log10(vmin); linear: vmin, vmax-vmin  */
+  int32_t status;          /* CSG_NORM_*                                                          */
+  int32_t degenerate;      /* 1: vmin == vmax -> every cell maps to index 0                       */
+} csg_panel_norm;          /* 56 bytes */
+
+CSG_API int32_t csg_raster_blocks(int32_t ne, int32_t nt);
+
+/* Resolve every panel's normalisation on the device from the region stats. */
+CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels,
+                      const csg_region* d_regions, const csg_region_stats* d_stats, int dtype,
+                      csg_panel_norm* d_norms);
+
+/* Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
+ * under, over, bad).  d_index (uint16, may be NULL) receives Colormap indices 0..255 and
+ * 256/257/258 for under/over/bad; d_rgba (may be NULL) the colours.  Row 0 of a panel is
+ * the lowest energy (imshow origin="lower"). */
+CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
+                  const int32_t* d_index_pool, const csg_panel* d_panels,
+                  const csg_panel_norm* d_norms, int n_panels, int total_blocks,
+                  const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index);
+
+/* ---------------------------------------------- K2b: global extrema (pooled) */
+/* The pooled finite-positive samples of CS/fast/extrema.py:259-267 are never
+ * materialised: each file's collapsed total matrix is histogrammed by radix digit
+ * of the float key, the histograms are prefix-scanned along the ascending-orbit
+ * file sequence of each instrument, and order statistics of every prefix pool
+ * (the reference recomputes nanpercentile(concat(blocks so far)) per step,
+ * :280-285) are located digit by digit. */
+typedef struct {
+  int64_t mat_off; /* element offset of the file's total (T,E) matrix in d_mats (contiguous T*E) */
+  int32_t n_cells; /* T*E                                                                        */
+  int32_t E;
+  int32_t inst; /* instrument slot 0..n_inst-1                                                 */
+  int32_t pos;  /* position of this file in its instrument's ascending-orbit sequence          */
+} csg_pool_item; /* 24 bytes */
+
+/* Level-0 pass: d_hist[inst][pos][0][bin] (uint32, bins = 1<<bits, top `bits` bits of the
+ * positive-float key), d_counts[item][E] (int32: finite-positive cells per energy column,
+ * CS/fast/extrema.py:260-264), d_npos[item] (int32).  hist_stride_pos = slots*bins. */
+CSG_API int csg_pool_hist_first(csg_ctx* ctx, const void* d_mats, int dtype, const csg_pool_item* d_items,
+                        int n_items, int max_pos, int bits, int max_E, uint32_t* d_hist,
+                        int32_t* d_counts, int32_t* d_npos);
+/* Refinement pass: cells whose key >> prefix_shift equals d_slot_prefix[inst][s] are counted
+ * in d_hist[inst][pos][s][(key >> shift) & (bins-1)].  d_slot_prefix is sorted ascending per
+ * instrument, padded with UINT64_MAX, n_slots entries per instrument. */
+CSG_API int csg_pool_hist_refine(csg_ctx* ctx, const void* d_mats, int dtype, const csg_pool_item* d_items,
+                         int n_items, int max_pos, int n_slots, const uint64_t* d_slot_prefix,
+                         int prefix_shift, int shift, int bits, uint32_t* d_hist);
+/* In-place inclusive scan of d_hist along pos for every (inst, slot, bin); d_totals (may be
+ * NULL) receives the last row [inst][slot][bin] (this rank's bucket totals, the payload of
+ * the histogram-merge all-gather). */
+CSG_API int csg_pool_scan(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len,
+                  int n_slots, int bits, uint32_t* d_totals);
+/* One query = (inst, pos, slot, rank): find the bin of the scanned row where the cumulative
+ * count first exceeds rank; writes bin and the residual rank inside that bin.  d_base (may be
+ * NULL) [inst][slot][bin]: counts held by lower ranks, added to every row on the fly. */
+typedef struct {
+  int32_t inst, pos, slot, bin; /* bin: output */
+  int64_t rank;                 /* in: rank within the slot's population; out: residual */
+  int64_t row_total;            /* out: population of the slot row (level 0: pool size n_k) */
+} csg_pool_query;               /* 32 bytes */
+CSG_API int csg_pool_locate(csg_ctx* ctx, const uint32_t* d_hist, int max_pos, int n_slots, int bits,
+                    const uint32_t* d_base, csg_pool_query* d_queries, int n_queries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSGPU_H */

@@ -1,0 +1,325 @@
+"""GPU parity tests of the kernels, called through the C ABI (ctypes), against numpy /
+the oracle restatement on the same seeded inputs.  Bit-exact unless stated."""
+
+import numpy as np
+import pytest
+
+from tests.helpers import bits, same_bits, same_float
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from configurable_spectrograms_b200 import _lib
+
+    return _lib.Context(0)
+
+
+def _rand_cube(rng, shape, dtype, nan=0.05, integer=False):
+    c = rng.poisson(3.0, shape).astype(dtype) if integer else rng.gamma(2.0, 3.0, shape).astype(dtype)
+    if nan:
+        c[rng.random(shape) < nan] = np.nan
+    return c
+
+
+def _bits_from_masks(masks):
+    b = np.zeros(len(masks[0]), dtype=np.uint8)
+    for g, m in enumerate(masks):
+        b |= (m.astype(np.uint8) << g).astype(np.uint8)
+    return b
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize(
+    "shape", [(50, 64, 96), (7, 10, 12), (3, 1, 4), (5, 129, 6), (9, 64, 95), (4, 33, 7), (1, 64, 96), (300, 64, 96)]
+)
+def test_collapse_tpe_bit_exact(ctx, dtype, shape):
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(hash((shape, np.dtype(dtype).itemsize)) % 2**31)
+    cube = _rand_cube(rng, shape, dtype)
+    cube[0, 0, 0] = -0.0
+    if shape[0] > 4:
+        cube[2] = np.nan
+        cube[3, :, :] = np.nan
+        cube[3, 0, 1] = 1.0
+        cube[4, 0, 0] = np.inf
+        cube[4, 1, 0] = -np.inf
+        cube[1, 0, 2] = -1e31
+    masks = [rng.random(shape[1]) < f for f in (0.9, 0.3, 0.2, 0.5)]
+    masks[2][:] = False  # an empty group sums to +0.0
+    b = Batch(ctx, dtype, n_groups=4)
+    f = b.add_file(cube, _bits_from_masks(masks))
+    b.upload_cubes()
+    b.collapse()
+    with np.errstate(invalid="ignore", over="ignore"):
+        assert np.array_equal(bits(b.sums(f, 0)), bits(np.nansum(cube, axis=1)))
+        for g, m in enumerate(masks):
+            ref = np.nansum(cube[:, m, :], axis=1)
+            assert same_bits(b.sums(f, g + 1), ref, zero_sign_insensitive=False), g
+    fl = b.flags(f)
+    nn = ~np.isnan(cube)
+    assert np.array_equal((fl & 1).astype(bool), nn.any(axis=(1, 2)))
+    for g, m in enumerate(masks):
+        assert np.array_equal(((fl >> (g + 1)) & 1).astype(bool), nn[:, m, :].any(axis=(1, 2)))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(20, 64, 96), (7, 10, 12), (3, 5, 4), (5, 128, 6), (2, 8, 3), (6, 96, 64)])
+def test_collapse_tep_view_bit_exact(ctx, dtype, shape):
+    """The transposed view of a stored (T,E,P) array: numpy's pairwise order for the total,
+    the gathered copy's ascending chain for the groups."""
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(11)
+    T, P, E = shape
+    stored = _rand_cube(rng, (T, E, P), dtype)
+    view = np.transpose(stored, (0, 2, 1))
+    masks = [rng.random(P) < f for f in (0.9, 0.3)]
+    b = Batch(ctx, dtype, n_groups=2)
+    f = b.add_file(view, _bits_from_masks(masks))
+    b.upload_cubes()
+    b.collapse()
+    assert np.array_equal(bits(b.sums(f, 0)), bits(np.nansum(view, axis=1)))
+    for g, m in enumerate(masks):
+        assert same_bits(b.sums(f, g + 1), np.nansum(view[:, m, :], axis=1), zero_sign_insensitive=False)
+    nn = ~np.isnan(view)
+    assert np.array_equal((b.flags(f) & 1).astype(bool), nn.any(axis=(1, 2)))
+
+
+def test_collapse_ragged_batch_and_host_entry(ctx):
+    from configurable_spectrograms_b200.engine import Batch, collapse_host, nansum
+
+    rng = np.random.default_rng(12)
+    cubes = [_rand_cube(rng, (T, 64, 96), np.float32, integer=True) for T in (5, 130, 1, 77, 64)]
+    b = Batch(ctx, np.float32, n_groups=0)
+    ids = [b.add_file(c) for c in cubes]
+    b.add_file(np.zeros((0, 64, 96), np.float32))  # an empty file is legal
+    b.upload_cubes()
+    b.collapse()
+    for i, c in zip(ids, cubes):
+        assert np.array_equal(bits(b.sums(i)), bits(np.nansum(c, axis=1)))
+    s, fl = collapse_host(cubes[1], ctx=ctx)
+    assert np.array_equal(bits(s[0]), bits(np.nansum(cubes[1], axis=1)))
+    assert np.array_equal(bits(nansum(cubes[3])), bits(np.nansum(cubes[3], axis=1)))
+
+
+def _region_ref(m, cols, rows):
+    return m[np.ix_(rows, cols)].T
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("integer", [True, False])
+def test_region_stats_match_numpy(ctx, dtype, integer):
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(13)
+    cube = _rand_cube(rng, (400, 8, 96), dtype, integer=integer)
+    cube[5, :, 10] = np.nan
+    cube[6, 0, 11] = np.inf
+    cube[7, 0, 12] = -np.inf
+    cube[8, 0, 13] = -5.0
+    b = Batch(ctx, dtype, 0)
+    f = b.add_file(cube)
+    b.upload_cubes()
+    b.collapse()
+    with np.errstate(invalid="ignore"):
+        m = np.nansum(cube, axis=1)
+        m[5, 10] = np.nan  # nansum never yields NaN from NaN inputs; inject via inf-inf below instead
+    cube2 = cube.copy()
+    cube2[9, 0, 14], cube2[9, 1, 14] = np.inf, -np.inf  # inf + -inf -> NaN cell
+    b2 = Batch(ctx, dtype, 0)
+    f2 = b2.add_file(cube2)
+    b2.upload_cubes()
+    b2.collapse()
+    with np.errstate(invalid="ignore"):
+        m = np.nansum(cube2, axis=1)
+    cases = [
+        (np.arange(96)[::-1][10:84], np.arange(400), (1, 99)),
+        (np.arange(5, 60), np.arange(100, 180), (1, 99)),
+        (np.arange(96), np.arange(400), (0, 100)),
+        (np.arange(0, 96, 3), np.array([3, 9, 10, 11, 200, 399]), (5, 95)),
+        (np.arange(14, 15), np.arange(9, 10), (1, 99)),  # single NaN cell
+        (np.arange(20, 21), np.arange(30, 31), (50, 50.5)),  # single cell
+        (np.arange(96), np.arange(400), (33.3, 99.9)),
+    ]
+    regs = []
+    for cols, rows, (pl, ph) in cases:
+        regs.append(b2.add_region(f2, 0, cols, rows=rows, want_pct=True, p_lo=pl, p_hi=ph))
+    b2.upload_tables()
+    b2.run_stats()
+    st = b2.stats()
+    for r, (cols, rows, (pl, ph)) in zip(regs, cases):
+        ref = _region_ref(m, cols, rows)
+        with np.errstate(invalid="ignore"), np.testing.suppress_warnings() as sup:
+            sup.filter(RuntimeWarning)
+            elo = float(np.nanpercentile(ref, pl)) if (~np.isnan(ref)).any() else np.nan
+            ehi = float(np.nanpercentile(ref, ph)) if (~np.isnan(ref)).any() else np.nan
+        assert same_float(st[r]["p_lo"], elo), (r, st[r]["p_lo"], elo)
+        assert same_float(st[r]["p_hi"], ehi), (r, st[r]["p_hi"], ehi)
+        fp = ref[np.isfinite(ref) & (ref > 0)]
+        assert st[r]["n_pos"] == fp.size
+        assert st[r]["min_pos"] == (fp.min() if fp.size else np.inf)
+        fin = ref[np.isfinite(ref)]
+        assert st[r]["fin_min"] == (fin.min() if fin.size else np.inf)
+        assert st[r]["fin_max"] == (fin.max() if fin.size else -np.inf)
+        assert st[r]["n_valid"] == (~np.isnan(ref)).sum()
+        assert st[r]["n_nan"] == np.isnan(ref).sum()
+        assert st[r]["n_posinf"] == np.isposinf(ref).sum() and st[r]["n_neginf"] == np.isneginf(ref).sum()
+
+
+def _lut():
+    rng = np.random.default_rng(99)
+    from oracle import restate as R
+
+    return R.lut_with_extremes(rng.integers(0, 256, (256, 4), dtype=np.uint8))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_prepare_and_rasterise_match_oracle(ctx, dtype):
+    """Every branch of make_spectrogram's z handling + the restated norm/LUT index."""
+    from configurable_spectrograms_b200.engine import Batch
+    from oracle import restate as R
+
+    rng = np.random.default_rng(14)
+    T, P, E = 260, 6, 96
+    cube = _rand_cube(rng, (T, P, E), dtype, integer=False) * dtype(40)
+    cube[10, 0, 5], cube[10, 1, 5] = np.inf, -np.inf
+    cube[11, 0, 6] = np.inf
+    cube[12, 0, 7] = -np.inf
+    cube[13, :, 8] = 0.0
+    cube[14, :, 9] = -3.0
+    cube[20:25] = np.nan
+    flat = np.full((T, P, E), 2.0, dtype=dtype)  # flat data: percentiles equal -> fallback/degenerate
+    energy = np.geomspace(4.0, 30000.0, E)[::-1].astype(np.float32)
+    times = 1000.0 + 2.5 * np.arange(T)
+    lut = _lut()
+    b = Batch(ctx, dtype, 0)
+    fa, fb = b.add_file(cube), b.add_file(flat)
+    b.upload_cubes()
+    b.collapse()
+    keep = np.flatnonzero((energy >= 0) & (energy <= 4000))
+    cols = keep[::-1]  # descending energies: flip
+    zoom_rows = np.flatnonzero((times >= times[100] - 60) & (times <= times[100] + 60))
+    specs = []
+    for f, src in ((fa, cube), (fb, flat)):
+        for rows, kw in ((np.arange(T), dict(x_min=times[0], x_max=times[-1])), (zoom_rows, dict(center=times[100], window=120.0))):
+            for zs in ("linear", "log"):
+                for zb in ((None, None), (0.0, 460.0), (5.0, None), (None, 3.0), (50.0, 10.0), (0.0, 0.0)):
+                    specs.append((f, src, rows, kw, zs, zb))
+    panels = []
+    for f, src, rows, kw, zs, zb in specs:
+        r = b.add_region(f, 0, cols, rows=rows, want_pct=True)
+        panels.append(b.add_panel(r, -1, zs == "log", zb[0], zb[1]))
+    b.upload_tables()
+    b.run_stats()
+    b.prepare()
+    b.set_lut(lut)
+    b.rasterise()
+    norms = b.norms()
+    n_checked = 0
+    for p, (f, src, rows, kw, zs, zb) in zip(panels, specs):
+        with np.testing.suppress_warnings() as sup:
+            sup.filter(RuntimeWarning)
+            ref = R.panel(times, energy, src, z_scale=zs, z_min=zb[0], z_max=zb[1], **kw)
+        nm = norms[p]
+        assert same_float(nm["vmin"], ref["vmin"]), (zs, zb, nm["vmin"], ref["vmin"])
+        assert same_float(nm["vmax"], ref["vmax"]), (zs, zb, nm["vmax"], ref["vmax"])
+        try:
+            with np.errstate(all="ignore"):
+                idx_ref, rgba_ref = R.rasterise(ref, lut)
+        except ValueError as exc:
+            assert nm["status"] != 0, (zs, zb, str(exc))
+            continue
+        assert nm["status"] == 0, (zs, zb)
+        assert np.array_equal(b.panel_index(p), idx_ref), (zs, zb)
+        assert np.array_equal(b.panel_rgba(p), rgba_ref), (zs, zb)
+        n_checked += 1
+    assert n_checked > len(specs) // 2
+
+
+def test_rasterise_large_panel_index_exact(ctx):
+    """One full-size panel (74 x 800 cells, log) against the oracle."""
+    from configurable_spectrograms_b200.engine import Batch
+    from oracle import restate as R
+
+    rng = np.random.default_rng(15)
+    cube = _rand_cube(rng, (800, 64, 96), np.float32, integer=True)
+    energy = np.geomspace(4.0, 30000.0, 96)[::-1].astype(np.float32)
+    times = 2.5 * np.arange(800)
+    b = Batch(ctx, np.float32, 0)
+    f = b.add_file(cube)
+    b.upload_cubes()
+    b.collapse()
+    keep = np.flatnonzero(energy <= 4000)[::-1]
+    r = b.add_region(f, 0, keep, want_pct=True)
+    p = b.add_panel(r, -1, True)
+    b.upload_tables()
+    b.run_stats()
+    b.prepare()
+    b.set_lut(_lut())
+    b.rasterise()
+    ref = R.panel(times, energy, cube, x_min=times[0], x_max=times[-1], z_scale="log")
+    idx_ref, _ = R.rasterise(ref, _lut())
+    assert np.array_equal(b.panel_index(p), idx_ref)
+
+
+def _pool_reference(mats_by_inst, p, dtype):
+    """Brute force: running max over prefixes of nanpercentile(pool so far)."""
+    best, last = None, None
+    pool = []
+    for m in mats_by_inst:
+        pos = m[np.isfinite(m) & (m > 0)]
+        if pos.size:
+            pool.append(pos)
+        if pool:
+            v = float(np.nanpercentile(np.concatenate(pool), p))
+            best = v if best is None else max(best, v)
+            last = v
+    return best, last
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("integer", [True, False])
+def test_pool_prefix_percentiles_exact(ctx, dtype, integer):
+    from configurable_spectrograms_b200._lib import POOL_ITEM
+    from configurable_spectrograms_b200.engine import Batch
+    from configurable_spectrograms_b200.pool_select import GpuPoolBackend, prefix_percentiles
+
+    rng = np.random.default_rng(16)
+    n_inst, n_files = 3, 9
+    b = Batch(ctx, dtype, 0)
+    cubes = {}
+    for i in range(n_inst):
+        for k in range(n_files - i):
+            T = int(rng.integers(20, 60))
+            scale = 8.0 if k == 1 else 1.0  # an early storm: running max != final pool
+            c = (_rand_cube(rng, (T, 4, 96), dtype, integer=integer) * dtype(scale)).astype(dtype)
+            if k == 3:
+                c[:] = np.nan  # a file with no positive sample at all
+            cubes[(i, k)] = (b.add_file(c), c)
+    b.upload_cubes()
+    b.collapse()
+    items = np.zeros(len(cubes), dtype=POOL_ITEM)
+    for j, ((i, k), (f, c)) in enumerate(cubes.items()):
+        items[j] = (b.mat_off(f, 0), c.shape[0] * 96, 96, i, k)
+    inst_len = np.array([n_files - i for i in range(n_inst)], dtype=np.int32)
+    reqs = [{"inst": i, "p": 99.0, "mode": "running_max"} for i in range(n_inst)]
+    reqs += [{"inst": i, "p": 1, "mode": "last"} for i in range(n_inst)]
+    reqs += [{"inst": 0, "p": 50.0, "mode": "running_max"}]
+    vals, counts, npos = prefix_percentiles(GpuPoolBackend(b), dtype, items, n_inst, inst_len, 96, reqs)
+    for r, req in enumerate(reqs):
+        i = req["inst"]
+        with np.errstate(invalid="ignore"):
+            mats = [np.nansum(cubes[(i, k)][1], axis=1) for k in range(n_files - i)]
+        best, last = _pool_reference(mats, req["p"], dtype)
+        exp = best if req["mode"] == "running_max" else last
+        assert vals[r] == exp, (r, req, vals[r], exp)
+    # per-energy positive counts (CS/fast/extrema.py:260-264)
+    for j, ((i, k), (f, c)) in enumerate(cubes.items()):
+        with np.errstate(invalid="ignore"):
+            m = np.nansum(c, axis=1)
+        ok = np.isfinite(m) & (m > 0)
+        assert np.array_equal(counts[j], ok.sum(axis=0))
+        assert npos[j] == ok.sum()
