@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- orbits/sec of the FAST batch path (BASELINE.json metric) on N B200s.
+
+One step = one pass of the hot path over this rank's shard of synthetic FAST orbits
+(linear y / log z, turbo, max_processing_percentile=99, fresh extrema cache):
+
+  K1  collapse every cube once (all pitch-angle groups + total + row flags)
+  K2b pooled extrema: radix histograms, prefix scan, exact prefix percentiles (+ all-gather
+      of bucket totals across ranks)
+  K2a 1/99 percentiles + safe_vmin of every figure row
+  K3  normalise + LUT rasterise every panel of every figure (pitch-angle grids given/raw for
+      4 instruments + instrument grids given/raw, full + cusp-zoom columns)
+
+``value``  : whole-job orbits/s, cubes resident in HBM, CUDA-event timed, max over ranks.
+``e2e``    : same metric through the host-buffer path: H2D of the cubes from pinned memory,
+             the same stages, D2H of every RGBA raster into pinned memory, inside the timed
+             region.
+Workload (weak scaling): 125 orbits per GPU = config 4 (1000 orbits) at 8 GPUs.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ORDER = ("ees", "eeb", "ies", "ieb")
+NOMINAL_T = {"ees": 800, "ies": 800, "eeb": 903, "ieb": 903}
+P, E = 64, 96
+METRIC = "orbits/sec (whole box, device-timed)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--orbits-per-gpu", type=int, default=125)
+    ap.add_argument("--cpu-sample-orbits", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=4)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic workload (shapes of `FAST CDF variables.txt`; generated on the GPU with torch --
+# plumbing only -- so a 10 GB shard does not take minutes of host RNG)
+# ----------------------------------------------------------------------------------------
+def orbit_layout(n_orbits, first_orbit, seed):
+    """Host-side description of the shard: per file shape, times, cusp lines, intensity."""
+    from configurable_spectrograms_b200 import synth
+
+    rng = np.random.default_rng(seed + 7919 * first_orbit)
+    energy = synth.energy_bins()
+    pitch = synth.pitch_angle_bins()
+    files, orbits = [], []
+    offset = 0
+    for k in range(n_orbits):
+        g = first_orbit + k
+        start = 946684800.0 + 7980.0 * g
+        has_cusp = g % 3 == 0
+        storm = g in (1, 2, 5)
+        entry = {"orbit": 13000 + g, "files": {}, "lines": {}}
+        for inst in ORDER:
+            T = NOMINAL_T[inst]
+            cadence = 2.5 if inst.endswith("s") else 0.6
+            times = start + cadence * np.arange(T, dtype=np.float64)
+            lines = []
+            win = None
+            if has_cusp:
+                lo = int(T * 0.4) + int(rng.integers(0, 20))
+                hi = lo + (47 if inst.endswith("s") else 259)
+                win = (lo, hi)
+                lines = [float(times[lo]), float(times[hi])]
+            files.append({"inst": inst, "T": T, "offset": offset, "intensity": (8.0 if storm else 1.0) * (3.0 if inst[0] == "e" else 0.3), "win": win, "seed": seed * 100003 + g * 4 + ORDER.index(inst)})
+            entry["files"][inst] = {"index": len(files) - 1, "times": times, "energy": energy, "pitch_angle": pitch}
+            entry["lines"][inst] = lines
+            offset += T * P * E
+        orbits.append(entry)
+    return files, orbits, offset
+
+
+def generate_cubes(torch, files, total_elems, device):
+    """Poisson counts with the structure of synth.make_cube, 1 % NaN; one flat float32 tensor."""
+    cubes = torch.empty(total_elems, dtype=torch.float32, device=device)
+    p = torch.arange(P, device=device, dtype=torch.float32)[None, :, None]
+    e = torch.arange(E, device=device, dtype=torch.float32)[None, None, :]
+    cutoff = 1e-4 + 1.0 / (1.0 + torch.exp(-(e - 0.30 * E) / 0.8))
+    peak = torch.exp(-(((e - 0.55 * E) / (0.22 * E)) ** 2)) * (1.0 + 0.6 * torch.cos(2 * torch.pi * p / P))
+    bump_e = torch.exp(-(((e - 0.7 * E) / (0.1 * E)) ** 2))
+    gen = torch.Generator(device=device)
+    for f in files:
+        T = f["T"]
+        gen.manual_seed(f["seed"])
+        t = torch.arange(T, device=device, dtype=torch.float32)[:, None, None]
+        lam = f["intensity"] * cutoff * (0.15 + peak * (1.0 + 0.5 * torch.sin(2 * torch.pi * t / T * 3.0)))
+        if f["win"] is not None:
+            bump = torch.zeros(T, 1, 1, device=device)
+            bump[f["win"][0] : f["win"][1]] = 4.0
+            lam = lam * (1.0 + bump * bump_e)
+        cube = torch.poisson(lam, generator=gen)
+        cube[torch.rand(cube.shape, device=device, generator=gen) < 0.01] = float("nan")
+        cubes[f["offset"] : f["offset"] + T * P * E] = cube.reshape(-1)
+    return cubes
+
+
+def turbo_like_lut():
+    """A deterministic 259 x 4 uint8 table (matplotlib's tables are not on the box; indices, not
+    colours, are what parity grades)."""
+    from configurable_spectrograms_b200.colormaps import get_lut
+
+    return get_lut("turbo")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port of the reference's numeric path
+# ----------------------------------------------------------------------------------------
+def cpu_sample_orbits(n, seed):
+    from configurable_spectrograms_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    out = []
+    energy, pitch = synth.energy_bins(), synth.pitch_angle_bins()
+    for k in range(n):
+        dsets, lines = {}, {}
+        for inst in ORDER:
+            T = NOMINAL_T[inst]
+            win = (int(T * 0.4), int(T * 0.4) + (47 if inst.endswith("s") else 259)) if k % 3 == 0 else None
+            cube = synth.make_cube(rng, T, intensity=(8.0 if k == 1 else 1.0) * (3.0 if inst[0] == "e" else 0.3), cusp_window=win)
+            times = synth.make_times(T, start=946684800.0 + 7980.0 * k, cadence=2.5 if inst.endswith("s") else 0.6)
+            dsets[inst] = {"times": times, "data": cube, "energy": energy, "pitch_angle": pitch}
+            lines[inst] = [float(times[win[0]]), float(times[win[1]])] if win else []
+        out.append((13000 + k, dsets, lines))
+    return out
+
+
+def run_cpu_port(orbits, steps, warmup):
+    from oracle import cpu_pipeline as CP
+
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(warmup + steps):
+        t, _state, _n = CP.run_step(orbits, "linear", "log", 99.0, workers=cores)
+        if i >= warmup:
+            times.append(t)
+    return float(np.mean(times)), cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_sample_orbits
+    orbits = cpu_sample_orbits(n, args.seed)
+    sec, cores = run_cpu_port(orbits, args.steps, min(args.warmup, 1))
+    value = n / sec
+    sample = f"{n} synthetic FAST orbits (4 instruments, nominal shapes), both submissions, numeric path only (no Agg/PNG)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "orbits/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config4 shard: FAST batch step, linear y / log z, max_processing_percentile=99", "sample_orbits": n},
+        "cpu_baseline": {"value": value, "unit": "orbits/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+
+    from configurable_spectrograms_b200 import _lib
+    from configurable_spectrograms_b200.fast.extrema import _extrema_overrides, extrema_from_shard
+    from configurable_spectrograms_b200.fast.pipeline import ShardPlan
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+
+        from configurable_spectrograms_b200.comm import TorchComm
+
+        dist.init_process_group("nccl", device_id=dev)
+        comm = TorchComm(dist, dev)
+
+    n_local = args.orbits_per_gpu
+    first = rank * n_local
+    files, orbits, total_elems = orbit_layout(n_local, first, args.seed)
+    cubes = generate_cubes(torch, files, total_elems, dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = _lib.Context(local, stream=stream)
+    lut = turbo_like_lut()
+
+    # global ascending orbit sequence (every rank knows every orbit number; files all present)
+    sequence = [(13000 + g, {i: True for i in ORDER}) for g in range(world * n_local)]
+
+    def build_shard(base_ptr):
+        shard = ShardPlan(ctx, "linear", "log", zoom_duration_minutes=6, instrument_order=ORDER)
+        shard.first_orbit_index = first
+        for ob in orbits:
+            dsets = {}
+            for inst, fd in ob["files"].items():
+                f = files[fd["index"]]
+                dsets[inst] = {"times": fd["times"], "energy": fd["energy"], "pitch_angle": fd["pitch_angle"],
+                               "shape": (f["T"], P, E), "device_ptr": base_ptr + 4 * f["offset"]}
+            shard.add_orbit(ob["orbit"], dsets, ob["lines"])
+        return shard
+
+    def plan_figures(shard, state):
+        """Both submissions of every orbit (extrema=None, extrema=state); identical panels are shared."""
+        shard.fetch_flags()
+        for ob in shard.orbits:
+            for ge in (None, state):
+                for inst in ORDER:
+                    if inst not in ob["files"]:
+                        continue
+                    ov = _extrema_overrides(ge, inst, "linear", "log")
+                    shard.plan_pitch_angle_grid(ob, inst, "given", *ov)
+                    shard.plan_pitch_angle_grid(ob, inst, "raw")
+                shard.plan_instrument_grid(ob, "given", global_extrema=ge)
+                shard.plan_instrument_grid(ob, "raw", global_extrema=None)
+        shard.upload_tables()
+        shard.batch.set_lut(lut)
+
+    def device_stages(shard, timers=True):
+        if timers:
+            ctx.timer_start(0)
+        shard.collapse()
+        if timers:
+            ctx.timer_stop(0)
+        state = extrema_from_shard(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm)
+        if shard.batch.n_panels == 0:
+            plan_figures(shard, state)
+        if timers:
+            ctx.timer_start(1)
+        shard.run_panels(None, want_index=False)
+        if timers:
+            ctx.timer_stop(1)
+        return state
+
+    # ------------------------------------------------------------ device-resident arm
+    shard = build_shard(cubes.data_ptr())
+    state0 = device_stages(shard, timers=False)  # plans the panels on the first pass
+    ctx.sync()
+    for _ in range(args.warmup):
+        device_stages(shard)
+    ctx.sync()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    collapse_ms, panel_ms = [], []
+    ev0.record()
+    for _ in range(args.steps):
+        state = device_stages(shard)
+        collapse_ms.append(None)
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    # per-stage timers hold the last step; re-measure collapse alone for the roofline average
+    k1 = []
+    for _ in range(max(args.steps, 3)):
+        ctx.timer_start(0)
+        shard.collapse()
+        ctx.timer_stop(0)
+        k1.append(ctx.timer_ms(0))
+    assert state == state0, "extrema changed between steps"
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_orbits = world * n_local
+    value = total_orbits / (ms_step / 1e3)
+
+    cube_bytes = 4 * total_elems
+    sums_bytes = sum(5 * f["T"] * E * 4 for f in files)
+    k1_ms = float(np.mean(k1))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (cube_bytes + sums_bytes) / (k1_ms / 1e3) / 1e9
+
+    # ------------------------------------------------------------------- e2e arm
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(total_elems, dtype=torch.float32, pin_memory=True)
+        host.copy_(cubes)
+        torch.cuda.synchronize()
+        n_px = shard.batch.n_pixels
+        rgba_host = torch.empty(n_px, dtype=torch.int32, pin_memory=True)
+        rgba_view = None
+
+        def e2e_step():
+            cubes.copy_(host, non_blocking=True)  # H2D of this step's inputs (pinned -> HBM)
+            device_stages(shard, timers=False)
+            ctx._check(ctx.lib.csg_d2h(ctx.handle, rgba_host.data_ptr(), shard.batch.d_rgba.ptr, n_px * 4))
+            ctx.sync()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+        e2e = {"value": total_orbits / (float(dt.item()) / n_e2e), "unit": "orbits/s",
+               "h2d_bytes_per_step": int(cube_bytes), "d2h_bytes_per_step": int(n_px * 4), "steps": n_e2e}
+
+    # ----------------------------------------------------------- CPU baseline beside it
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_sample_orbits
+        sec, cores = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
+        cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "port",
+               "sample": f"{n} synthetic FAST orbits of the same workload, both submissions, numeric path only (no Agg/PNG), {sec:.1f} s wall"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "orbits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"config4 shard: {n_local} orbits/GPU ({world * n_local} orbits total; 1000 at 8 GPUs), "
+                            "4 instruments, FAST batch step linear y / log z, turbo, max_processing_percentile=99",
+                "orbits_per_gpu": n_local, "bytes_per_orbit": int(cube_bytes // n_local),
+                "panels_per_gpu": shard.batch.n_panels, "regions_per_gpu": shard.batch.n_regions,
+                "pixels_per_gpu": shard.batch.n_pixels,
+                "l2_policy": f"inputs larger than L2 ({cube_bytes / 1e9:.1f} GB of cubes streamed per step)",
+            },
+            "roofline": {"bound": "hbm", "kernel": "collapse_tpe_kernel<float,4>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": k1_ms,
+                         "algorithmic_bytes": int(cube_bytes + sums_bytes),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+            "stage_ms": {"collapse": k1_ms, "panels_last": ctx.timer_ms(1)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+"""CDF access and cusp-boundary lookup (reference ``cdf_utils.py``).
+
+CDF *decoding* is out of scope for the GPU path: with
+``cdflib`` installed real files are read through it; otherwise a ``<file>.npz`` side-car
+holding the four variables is used (synthetic data, ``synth.py``).
+"""
+
+from __future__ import annotations
+
+import os
+from pathlib import Path
+
+import numpy as np
+
+from .constants import CDF_DATA_DIRECTORY, CDF_VARIABLE_NAMES, FILTERED_ORBITS_CSV_PATH
+from .logging_utils import log_error, log_message
+
+filtered_orbits_cache: dict = {}
+orbit_column_cache: dict = {}
+cdf_type_cache: dict = {}
+
+INSTRUMENT_TAGS = ("ees", "eeb", "ies", "ieb")
+
+
+def _read_variables(cdf_path: str, names) -> list[np.ndarray]:
+    side_car = str(cdf_path) + ".npz"
+    if os.path.exists(side_car):
+        with np.load(side_car) as z:
+            return [np.asarray(z[n]) for n in names]
+    try:
+        import cdflib
+    except ImportError as exc:
+        raise ImportError(
+            f"cdflib is not installed and no side-car '{side_car}' exists: cannot read {cdf_path}"
+        ) from exc
+    with cdflib.CDF(cdf_path) as cdf:
+        return [np.asarray(cdf.varget(n)) for n in names]
+
+
+def load_filtered_orbits(csv_path: str = FILTERED_ORBITS_CSV_PATH):
+    """Tab-separated cusp-index table, cached per path; ``None`` when unreadable (``:26-52``)."""
+    if csv_path in filtered_orbits_cache:
+        return filtered_orbits_cache[csv_path]
+    import pandas as pd
+
+    try:
+        frame = pd.read_csv(csv_path, sep="\t")
+    except OSError as exc:
+        log_error(f"Error loading CSV {csv_path}: {exc}")
+        return None
+    filtered_orbits_cache[csv_path] = frame
+    return frame
+
+
+def get_timestamps_for_orbit(filtered_orbits_dataframe, orbit_number, instrument_type, time_unix_array) -> list[float]:
+    """Cusp boundary timestamps of an orbit: one value for a degenerate index pair, two
+    otherwise, ``[]`` when anything is missing (``:55-123``).
+
+    >>> import pandas as pd, numpy as np
+    >>> orbits = pd.DataFrame({"orbit": [42], "ees min index": [1], "ees max index": [3]})
+    >>> get_timestamps_for_orbit(orbits, 42, "ees", np.array([100.0, 200.0, 300.0, 400.0]))
+    [200.0, 400.0]
+    >>> get_timestamps_for_orbit(orbits, 99, "ees", np.array([100.0, 200.0, 300.0, 400.0]))
+    []
+    """
+    frame = filtered_orbits_dataframe
+    if frame is None or instrument_type is None or time_unix_array is None:
+        return []
+    key = (id(frame), instrument_type)
+    if key not in orbit_column_cache:
+        lowered = {c: c.lower() for c in frame.columns}
+        orbit_col = next(c for c, l in lowered.items() if "orbit" in l)
+        lo_col = next(c for c, l in lowered.items() if instrument_type in l and "min index" in l)
+        hi_col = next(c for c, l in lowered.items() if instrument_type in l and "max index" in l)
+        orbit_column_cache[key] = (orbit_col, lo_col, hi_col)
+    orbit_col, lo_col, hi_col = orbit_column_cache[key]
+    hit = frame[frame[orbit_col] == orbit_number]
+    if hit.empty:
+        return []
+    try:
+        lo = int(hit.iloc[0][lo_col])
+        hi = int(hit.iloc[0][hi_col])
+    except (TypeError, ValueError):
+        log_message("[WARN] Non-integer indices found in orbit row, using 0.")
+        return []
+    last = len(time_unix_array) - 1
+    lo = max(0, min(lo, last))
+    hi = max(0, min(hi, last))
+    if lo == hi:
+        return [float(time_unix_array[lo])]
+    return [float(time_unix_array[lo]), float(time_unix_array[hi])]
+
+
+def get_cdf_file_type(cdf_file_path: str) -> str | None:
+    """``'ees'|'eeb'|'ies'|'ieb'``, ``'orb'`` for ephemeris files, else ``None`` (``:126-154``).
+
+    >>> get_cdf_file_type("fa_esa_l2_eeb_20000101001737_13312_v02.cdf")
+    'eeb'
+    >>> get_cdf_file_type("fa_k0_orb_13312_v01.cdf")
+    'orb'
+    """
+    lowered = cdf_file_path.lower()
+    if "_orb_" in lowered:
+        return "orb"
+    for tag in INSTRUMENT_TAGS:
+        if f"_{tag}_" in lowered:
+            return tag
+    log_error(f"Unknown CDF file type for path: {cdf_file_path}")
+    return None
+
+
+def get_variable_shape(cdf_path: str, variable_name: str):
+    kind = cdf_type_cache.get(cdf_path)
+    if kind is None:
+        kind = cdf_type_cache[cdf_path] = get_cdf_file_type(cdf_path)
+    if kind is None or kind == "orb":
+        return None
+    try:
+        (value,) = _read_variables(cdf_path, [variable_name])
+        return value.shape if isinstance(value, np.ndarray) else None
+    except Exception as exc:
+        log_error(f"Error reading {cdf_path} for variable {variable_name}: {exc}")
+        return None
+
+
+def get_cdf_var_shapes(cdf_folder_path: str = CDF_DATA_DIRECTORY, variable_names=CDF_VARIABLE_NAMES):
+    paths = [str(p) for p in Path(cdf_folder_path).rglob("*.[cC][dD][fF]")]
+    return {name: [get_variable_shape(p, name) for p in paths] for name in variable_names}
+
+
+def load_fast_cdf_dataset(cdf_path: str, variable_names=tuple(CDF_VARIABLE_NAMES)) -> dict[str, np.ndarray]:
+    """``{'times','data','energy','pitch_angle'}`` with 1-D bin arrays and ``data`` as a
+    (time, pitch, energy) array or transposed *view* (``:222-256``) -- the view is kept
+    un-copied because numpy's summation order, reproduced on the GPU, depends on it."""
+    times, data, energy_full, pitch_full = _read_variables(cdf_path, variable_names)
+    energy = energy_full[0, 0, :] if energy_full.ndim == 3 else energy_full
+    pitch = pitch_full[0, :, 0] if pitch_full.ndim == 3 else pitch_full
+    if data.shape[1] == len(energy) and data.shape[2] == len(pitch):
+        data = np.transpose(data, (0, 2, 1))
+    return {"times": times, "data": data, "energy": energy, "pitch_angle": pitch}

@@ -40,7 +40,7 @@ __device__ __forceinline__ void load_chunk(Chunk<float, 4>& c, const float* p, b
     c.v[0] = r.x, c.v[1] = r.y, c.v[2] = r.z, c.v[3] = r.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c.v[i] = i < valid ? ld_stream1(p + i) : 0.f;
+    for (int i = 0; i < 4; ++i) c.v[i] = i < valid ? ld_stream1(p + i) : CUDART_NAN_F;  // padding lanes: ignored like NaN
   }
 }
 __device__ __forceinline__ void load_chunk(Chunk<double, 2>& c, const double* p, bool aligned, int valid) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_chunk(Chunk<double, 2>& c, const double* p,
     c.v[0] = r.x, c.v[1] = r.y;
   } else {
     c.v[0] = ld_stream1(p);
-    c.v[1] = valid > 1 ? ld_stream1(p + 1) : 0.0;
+    c.v[1] = valid > 1 ? ld_stream1(p + 1) : CUDART_NAN;
   }
 }
 

@@ -403,3 +403,25 @@ def nansum(cube, axis: int = 1):
         cube = np.moveaxis(cube, axis, 1)
     sums, _ = collapse_host(cube)
     return sums[0]
+
+
+def matrix_percentiles(matrix: np.ndarray, p_lo, p_hi, ctx: Context | None = None) -> tuple[float, float]:
+    """``(np.nanpercentile(matrix, p_lo), np.nanpercentile(matrix, p_hi))`` of the flattened
+    matrix, selected exactly on the GPU (K2a) in the matrix dtype's arithmetic."""
+    ctx = ctx or _lib.default_context()
+    m = np.asarray(matrix)
+    if m.dtype not in (np.float32, np.float64):
+        m = m.astype(np.float64)  # numpy computes integer input in float64
+    flat = np.ascontiguousarray(m).reshape(1, -1)
+    n = flat.shape[1]
+    if n == 0:
+        return float("nan"), float("nan")
+    d_m = ctx.to_device(flat)
+    reg = np.zeros(1, dtype=REGION)
+    reg[0] = (0, n, 0, 1, -1, 0, n, 1, 0, float(p_lo), float(p_hi))
+    d_r = ctx.to_device(reg)
+    d_pool = ctx.to_device(np.arange(n, dtype=np.int32))
+    d_out = ctx.alloc(REGION_STATS.itemsize)
+    ctx._check(ctx.lib.csg_region_stats_run(ctx.handle, d_m.ptr, np_dtype_code(flat.dtype), d_r.ptr, 1, d_pool.ptr, d_out.ptr))
+    st = d_out.download(REGION_STATS, 1)[0]
+    return float(st["p_lo"]), float(st["p_hi"])

@@ -1,0 +1,316 @@
+"""Global per-instrument axis extrema (reference ``fast/extrema.py``).
+
+Same call signature, JSON cache schema and control flow as the reference's
+``compute_global_extrema`` -- including its quirks, which are results: the
+linear/linear combo re-uses its own keys from the second orbit on (``:208-243``), the
+``complete`` flag compares an orbit index with a file count (``:315-319``), log-scale
+combos only transform cached linear/linear values (``:201-220``).
+
+The arithmetic is different: the reference re-concatenates every positive sample seen so
+far and calls ``np.nanpercentile`` after each (orbit, instrument) step (quadratic); here
+all files are collapsed once on the GPU (K1) and the running maximum over every prefix
+pool is selected exactly from scanned radix histograms (K2b, ``pool_select.py``).
+"""
+
+from __future__ import annotations
+
+import copy
+import json
+import math
+import os
+from collections.abc import Iterable
+from typing import Any
+
+import numpy as np
+
+from ..logging_utils import log_exception
+from ..percentile_utils import round_extrema
+from .constants import FAST_EXTREMA_JSON_PATH
+
+
+def _extrema_overrides(global_extrema, inst, y_scale, z_scale):
+    """Rounded ``(y_min, y_max, z_min, z_max)`` for one instrument (``:26-70``).
+
+    >>> extrema = {"ees_linear_linear_y_max": 1234, "ees_linear_linear_z_min": 0.0123}
+    >>> _extrema_overrides(extrema, "ees", "linear", "linear")
+    (None, 1300.0, 0.012, None)
+    >>> _extrema_overrides(None, "ees", "linear", "linear")
+    (None, None, None, None)
+    """
+    if not isinstance(global_extrema, dict):
+        return None, None, None, None
+    stem = f"{inst}_{y_scale}_{z_scale}"
+    out = []
+    for axis, how in (("y_min", "down"), ("y_max", "up"), ("z_min", "down"), ("z_max", "up")):
+        value = global_extrema.get(f"{stem}_{axis}")
+        out.append(None if value is None else round_extrema(value, how))
+    return tuple(out)
+
+
+def _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor_cutoff, log_floor_value,
+          on_scan, on_step_done=None):
+    """The reference's orbit x instrument loop (``:183-331``) with the scan abstracted.
+
+    ``sequence``: [(orbit, {inst: handle})] ascending.  ``on_scan(inst, orbit_index, handle)``
+    is called where the reference loads a file and updates its pools, and must return
+    ``(candidate_energy_max, candidate_intensity_max, intensity_min_store)``.
+    """
+
+    def safe_log(value):  # :151-161
+        if value is None:
+            return float(log_floor_value)
+        try:
+            value = float(value)
+        except (TypeError, ValueError):
+            return float(log_floor_value)
+        if not np.isfinite(value) or value <= log_floor_cutoff:
+            return float(log_floor_value)
+        return float(np.log10(value))
+
+    orbit_numbers = [o for o, _ in sequence]
+    last_key = f"{y_scale}_{z_scale}_last_orbit"
+    stored = state.get(last_key, -1)
+    last_done = int(stored) if isinstance(stored, (int, float)) else -1
+    y_log, z_log = y_scale == "log", z_scale == "log"
+    for orbit_index, (orbit, handles) in enumerate(sequence):
+        if orbit <= last_done:
+            continue
+        for inst in instrument_order:
+            stem = f"{inst}_{y_scale}_{z_scale}"
+            progress_key = f"{stem}_extrema_progress"
+            entry = state.get(progress_key)
+            if isinstance(entry, dict) and entry.get("complete"):
+                continue
+            ll = f"{inst}_linear_linear"
+            have_y, have_z = f"{ll}_y_max" in state, f"{ll}_z_max" in state
+            if have_y:
+                state[f"{stem}_y_max"] = safe_log(state[f"{ll}_y_max"]) if y_log else state[f"{ll}_y_max"]
+                state[f"{stem}_y_min"] = log_floor_value if y_log else state.get(f"{ll}_y_min", 0)
+            if have_z:
+                state[f"{stem}_z_max"] = safe_log(state[f"{ll}_z_max"]) if z_log else state[f"{ll}_z_max"]
+                state[f"{stem}_z_min"] = log_floor_value if z_log else state.get(f"{ll}_z_min", 0)
+            if have_y and have_z:
+                state[progress_key] = {"processed_index": max(totals[inst] - 1, -1), "total": totals[inst], "complete": True}
+                for other in instrument_order:
+                    state.pop(f"{other}_{y_scale}_{z_scale}_last_orbit", None)
+                state[last_key] = max(orbit_numbers) if orbit_numbers else -1
+                if on_step_done:
+                    on_step_done(reuse=True)
+                continue
+            cand_e, cand_z, z_min_store = on_scan(inst, orbit_index, handles.get(inst))
+            prev_e, prev_z = state.get(f"{stem}_y_max"), state.get(f"{stem}_z_max")
+            merged_e = max(float(prev_e), cand_e) if isinstance(prev_e, (int, float)) else cand_e
+            merged_z = max(float(prev_z), cand_z) if isinstance(prev_z, (int, float)) else cand_z
+            state[f"{stem}_y_min"] = 0
+            state[f"{stem}_y_max"] = int(min(4000, math.ceil(merged_e)))
+            state[f"{stem}_z_min"] = z_min_store
+            state[f"{stem}_z_max"] = float(math.ceil(merged_z))
+            state[progress_key] = {
+                "processed_index": orbit_index,
+                "total": totals[inst],
+                "complete": orbit_index + 1 >= totals[inst],
+            }
+            for other in instrument_order:
+                state.pop(f"{other}_{y_scale}_{z_scale}_last_orbit", None)
+            state[last_key] = orbit
+            if on_step_done:
+                on_step_done(reuse=False)
+    return state
+
+
+def plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff=0.1, log_floor_value=-1.0):
+    """Dry run: which (instrument -> [orbit_index]) steps reach the scan with this cache state."""
+    steps: dict[str, list[int]] = {i: [] for i in instrument_order}
+    totals = {i: sum(1 for _, h in sequence if i in h) for i in instrument_order}
+
+    def record(inst, orbit_index, handle):
+        steps[inst].append(orbit_index)
+        return 0.0, 0.0, 0
+
+    _walk(sequence, instrument_order, y_scale, z_scale, copy.deepcopy(state), totals, log_floor_cutoff,
+          log_floor_value, record)
+    return steps, totals
+
+
+def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
+    """Per-step 99 %-coverage energy (``:270-278``) from per-file per-energy positive counts.
+
+    ``energies[k]`` / ``counts[k]`` belong to the k-th scanned file of one instrument.  The
+    reference keeps a dict keyed by ``float(energy_value)`` holding only energies that have
+    seen a positive count; zero-count keys do not move the cumulative sum, so searching the
+    union of all keys finds the same energy.
+    """
+    n = len(energies)
+    if n == 0:
+        return []
+    keys = np.unique(np.concatenate([np.asarray(e, dtype=np.float64) for e in energies]))
+    per_file = np.zeros((n, len(keys)), dtype=np.int64)
+    for k, (e, c) in enumerate(zip(energies, counts)):
+        e = np.asarray(e, dtype=np.float64)
+        np.add.at(per_file[k], np.searchsorted(keys, e), np.asarray(c[: len(e)], dtype=np.int64))
+    running = np.cumsum(per_file, axis=0)  # counts per key after each step
+    along = np.cumsum(running, axis=1)
+    total = along[:, -1]
+    target = 0.99 * total
+    first = (along > target[:, None]).argmax(axis=1)
+    return [float(keys[first[k]]) if total[k] > 0 else 0.0 for k in range(n)]
+
+
+def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
+                       max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None,
+                       on_step_done=None):
+    """Update ``state`` from an already collapsed :class:`pipeline.ShardPlan`.
+
+    ``sequence[k] = (orbit, {inst: True})`` must list the GLOBAL ascending orbit sequence
+    (all ranks); ``shard.orbits`` holds this rank's contiguous slice starting at
+    ``shard.first_orbit_index``.
+    """
+    from ..pool_select import GpuPoolBackend, SingleRank, prefix_percentiles
+
+    comm = comm or SingleRank()
+    instrument_order = tuple(instrument_order)
+    steps, totals = plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
+    first = getattr(shard, "first_orbit_index", 0)
+    local_steps = {
+        inst: [oi - first for oi in steps[inst] if first <= oi < first + len(shard.orbits)] for inst in instrument_order
+    }
+    items, inst_len, owners = shard.pool_items(local_steps)
+    requests = [{"inst": ii, "p": max_percentile, "mode": "running_max"} for ii in range(len(instrument_order))]
+    if compute_mins:
+        requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
+    max_E = max((shard.batch.files[f]["E"] for _, _, f in owners), default=1)
+    values, counts, npos = prefix_percentiles(
+        GpuPoolBackend(shard.batch), shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm
+    )
+    # ---- per-step energy candidates need every rank's per-file counts in sequence order
+    local_rows = {}
+    for row, (inst, oi, file) in enumerate(owners):
+        local_rows[(inst, oi + first)] = (shard.file_meta[file]["energy"], counts[row])
+    merged_rows = {}
+    for part in comm.allgather_object(local_rows):
+        merged_rows.update(part)
+    cand_e: dict[tuple[str, int], float] = {}
+    for inst in instrument_order:
+        present = [oi for oi in steps[inst] if (inst, oi) in merged_rows]
+        ce = energy_candidates([merged_rows[(inst, oi)][0] for oi in present], [merged_rows[(inst, oi)][1] for oi in present])
+        by_step = dict(zip(present, ce))
+        running = 0.0
+        for oi in steps[inst]:  # steps without a file repeat the previous candidate
+            running = by_step.get(oi, running)
+            cand_e[(inst, oi)] = running
+    n_inst = len(instrument_order)
+
+    def scan(inst, orbit_index, handle):
+        ii = instrument_order.index(inst)
+        z = values[ii]
+        z_min = 0
+        if compute_mins:
+            zm = values[n_inst + ii]
+            z_min = float(zm) if zm is not None else 0
+        return cand_e.get((inst, orbit_index), 0.0), (float(z) if z is not None else 0.0), z_min
+
+    return _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor_cutoff, log_floor_value,
+                 scan, on_step_done)
+
+
+def compute_global_extrema(
+    directory_path: str,
+    y_scale: str,
+    z_scale: str,
+    instrument_order: Iterable[str],
+    extrema_json_path: str = FAST_EXTREMA_JSON_PATH,
+    compute_mins: bool = False,
+    max_percentile: float = 95.0,
+    log_floor_cutoff: float = 0.1,
+    log_floor_value: float = -1.0,
+    flush_batch_size: int = 10,
+    _shard=None,
+    _comm=None,
+) -> dict[str, Any]:
+    """Compute or resume the cached per-instrument extrema (reference ``:73-366``).
+
+    ``_shard`` (internal) re-uses cubes a batch driver already holds on the GPU.
+    """
+    from ..cdf_utils import load_fast_cdf_dataset
+    from .orbit_discovery import discover_orbit_files
+
+    instrument_order = tuple(instrument_order)
+    state: dict[str, Any] = {}
+    if os.path.exists(extrema_json_path):
+        try:
+            with open(extrema_json_path) as handle:
+                state = json.load(handle)
+        except (OSError, json.JSONDecodeError) as exc:
+            log_exception(f"[EXTREMA] Failed to read existing extrema JSON '{extrema_json_path}' (starting fresh)", exc, level="message")
+            state = {}
+
+    orbit_files = discover_orbit_files(directory_path, instrument_order)
+    orbits = sorted(orbit_files)
+    sequence = [(o, {i: True for i in orbit_files[o]}) for o in orbits]
+    last_key = f"{y_scale}_{z_scale}_last_orbit"
+    flush_state = {"since": 0}
+
+    def dump(ordered_first: bool):
+        payload = state
+        if ordered_first and last_key in state:
+            payload = {last_key: state[last_key], **{k: v for k, v in state.items() if k != last_key}}
+        try:
+            with open(extrema_json_path, "w") as handle:
+                json.dump(payload, handle, indent=2)
+            return True
+        except OSError as exc:
+            log_exception("[EXTREMA] flush failure", exc, level="message")
+            return False
+
+    def step_done(reuse: bool):
+        if reuse:
+            dump(False)  # the reference rewrites the cache right after a re-use (:234-236)
+            return
+        flush_state["since"] += 1
+        if flush_state["since"] >= flush_batch_size and dump(False):
+            flush_state["since"] = 0
+
+    shard = _shard
+    if shard is None:
+        steps, _ = plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
+        needed = sorted({oi for lst in steps.values() for oi in lst})
+        if needed:
+            from .. import _lib
+            from .pipeline import ShardPlan
+
+            shard = ShardPlan(_lib.default_context(), y_scale, z_scale, instrument_order=instrument_order)
+            shard.first_orbit_index = 0
+            wanted = {oi: {i for i in instrument_order if oi in steps[i]} for oi in needed}
+            for oi, orbit in enumerate(orbits):
+                datasets = {}
+                for inst in wanted.get(oi, ()):
+                    path = orbit_files[orbit].get(inst)
+                    if path is None:
+                        continue
+                    try:
+                        datasets[inst] = load_fast_cdf_dataset(path)
+                    except Exception as exc:
+                        log_exception(f"[EXTREMA] Ingest failure inst={inst} orbit={orbit} file={path}", exc, level="message")
+                shard.add_orbit(orbit, datasets)
+            shard.upload()
+            shard.collapse()
+    if shard is None:
+        # nothing reaches the scan (everything re-used or complete): only the bookkeeping runs
+        totals = {i: sum(1 for _, h in sequence if i in h) for i in instrument_order}
+
+        def unreachable(inst, orbit_index, handle):
+            raise AssertionError("scan step without a planned shard")
+
+        _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor_cutoff, log_floor_value,
+              unreachable, step_done)
+    else:
+        extrema_from_shard(
+            shard, sequence, instrument_order, y_scale, z_scale, state, compute_mins=compute_mins,
+            max_percentile=max_percentile, log_floor_cutoff=log_floor_cutoff, log_floor_value=log_floor_value,
+            comm=_comm, on_step_done=step_done,
+        )
+    if flush_state["since"] > 0:
+        dump(True)
+    if last_key in state:
+        return {last_key: state[last_key], **{k: v for k, v in state.items() if k != last_key}}
+    return state

@@ -1,0 +1,318 @@
+"""One GPU shard of the FAST batch path: cubes -> sums -> extrema -> panels -> rasters.
+
+This is the B200 re-design of what the reference does per worker process
+(``fast/process_orbit.py`` -> ``fast/plotting.py`` -> ``plotting.py``): instead of one
+orbit per process and twelve ``np.nansum`` per figure, every cube of the shard is
+reduced once (K1), every percentile the figure builders need is selected in one launch
+(K2a), the pooled extrema come from the same collapsed matrices (K2b) and every panel
+of every figure is rasterised in one launch (K3).  Host Python only plans descriptor
+tables and composes figures.
+
+The planner restates the reference's masks and bound selection verbatim (citations
+inline) so that panels, bounds and figure/file naming are identical.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .. import _lib
+from ..engine import Batch
+from ..logging_utils import log_exception
+from .constants import DEFAULT_INSTRUMENT_ORDER, DEFAULT_PITCH_ANGLE_CATEGORIES, PITCH_ANGLE_ROW_KEYS
+
+
+def pitch_angle_bits(pitch_angle: np.ndarray, categories: dict, row_keys=PITCH_ANGLE_ROW_KEYS):
+    """(uint8[P] membership bits, row keys present) -- ``fast/plotting.py:121-127``.
+
+    Closed intervals, NaN bins match nothing; bit g belongs to the g-th present row key.
+    """
+    keys = [k for k in row_keys if k in categories]
+    bits = np.zeros(len(pitch_angle), dtype=np.uint8)
+    with np.errstate(invalid="ignore"):
+        for g, key in enumerate(keys):
+            member = np.zeros(len(pitch_angle), dtype=bool)
+            for lo, hi in categories[key]:
+                member |= (pitch_angle >= lo) & (pitch_angle <= hi)
+            bits |= (member.astype(np.uint8) << g).astype(np.uint8)
+    return bits, keys
+
+
+def zoom_window(vertical_lines, zoom_duration_minutes):
+    """(center, duration) of the zoom column -- ``plotting.py:586-596``; None without lines."""
+    if not vertical_lines:
+        return None
+    if len(vertical_lines) == 1:
+        return vertical_lines[0], zoom_duration_minutes * 60
+    center = 0.5 * (vertical_lines[0] + vertical_lines[1])
+    return center, max(zoom_duration_minutes * 60, abs(vertical_lines[1] - vertical_lines[0]) * 1.5)
+
+
+@dataclass
+class RowSpec:
+    label: str
+    file: int
+    group: int
+    full_panel: int | None
+    zoom_panel: int | None
+    times: np.ndarray
+    energy: np.ndarray  # the y axis handed to make_spectrogram (unfiltered)
+    vmin: float | None = None
+    vmax: float | None = None
+
+
+@dataclass
+class FigureSpec:
+    kind: str  # "pitch-angle" | "instrument-grid"
+    orbit: int
+    variant: str  # "given" | "raw"
+    instrument: str | None
+    title: str
+    rows: list[RowSpec] = field(default_factory=list)
+    vertical_lines: list[float] | None = None
+    zoom: tuple[float, float] | None = None
+    zoom_needed: bool = False
+    error: str | None = None
+
+
+class ShardPlan:
+    """Plans and runs the batch path for a list of orbits on one GPU."""
+
+    def __init__(self, ctx, y_scale="linear", z_scale="linear", zoom_duration_minutes=6.25,
+                 instrument_order=DEFAULT_INSTRUMENT_ORDER, pitch_angle_categories=None, dtype=np.float32):
+        self.ctx = ctx
+        self.y_scale, self.z_scale = y_scale, z_scale
+        self.zoom_minutes = zoom_duration_minutes
+        self.instrument_order = tuple(instrument_order)
+        self.categories = pitch_angle_categories or DEFAULT_PITCH_ANGLE_CATEGORIES
+        self.n_groups = len([k for k in PITCH_ANGLE_ROW_KEYS if k in self.categories])
+        self.batch = Batch(ctx, dtype, n_groups=self.n_groups)
+        self.orbits: list[dict] = []  # {"orbit", "files": {inst: file_id}, "lines": {inst: [..]}}
+        self.file_meta: list[dict] = []
+        self.figures: list[FigureSpec] = []
+        self._panel_cache: dict = {}
+        self._region_cache: dict = {}
+        self._cols_cache: dict = {}
+        self._flags_host = None
+
+    # ------------------------------------------------------------- phase 1: files
+    def add_orbit(self, orbit: int, datasets: dict, lines: dict | None = None):
+        """``datasets``: {inst: load_fast_cdf_dataset(...) dict}; ``lines``: {inst: cusp timestamps}."""
+        entry = {"orbit": orbit, "files": {}, "lines": lines or {}}
+        for inst, ds in datasets.items():
+            energy = np.asarray(ds["energy"])
+            pitch = np.asarray(ds["pitch_angle"])
+            bits, keys = pitch_angle_bits(pitch, self.categories)
+            if "device_ptr" in ds:  # cube already resident in HBM (T,P,E C-order unless "layout" says otherwise)
+                fid = self.batch.add_file(None, bits, shape=ds["shape"], layout=ds.get("layout"), device_ptr=ds["device_ptr"])
+            else:
+                data = np.asarray(ds["data"])
+                if data.dtype != self.batch.dtype:
+                    data = data.astype(self.batch.dtype)
+                fid = self.batch.add_file(data, bits)
+            self.file_meta.append({"times": np.asarray(ds["times"]), "energy": energy, "keys": keys, "inst": inst, "orbit": orbit})
+            entry["files"][inst] = fid
+        self.orbits.append(entry)
+
+    def upload(self):
+        self.batch.upload_cubes()
+
+    def collapse(self):
+        self.batch.collapse()
+
+    def fetch_flags(self):
+        self._flags_host = self.batch.all_flags()
+
+    # ------------------------------------------------------------ phase 2: panels
+    def _energy_cols(self, file: int, lo, hi):
+        """Columns kept by ``(E >= lo) & (E <= hi)`` (builder order, no flip) and the same
+        after make_spectrogram's descending flip (``plotting.py:192-202``)."""
+        energy = self.file_meta[file]["energy"]
+        key = (energy.ctypes.data, len(energy), float(lo), float(hi))
+        hit = self._cols_cache.get(key)
+        if hit is None:
+            with np.errstate(invalid="ignore"):
+                keep = np.flatnonzero((energy >= lo) & (energy <= hi)).astype(np.int32)
+            flipped = keep
+            if len(keep) and energy[keep[0]] > energy[keep[-1]]:
+                flipped = keep[::-1].copy()
+            hit = self._cols_cache[key] = (keep, flipped)
+        return hit
+
+    def _region(self, file, group, cols, rows_key, rows, want_pct):
+        key = (file, group, cols.ctypes.data, len(cols), rows_key)
+        rid = self._region_cache.get(key)
+        if rid is None:
+            if isinstance(rows, tuple):
+                rid = self.batch.add_region(file, group, cols, t0=rows[0], nt=rows[1], want_pct=want_pct)
+            else:
+                rid = self.batch.add_region(file, group, cols, rows=rows, want_pct=want_pct)
+            self._region_cache[key] = rid
+        elif want_pct:
+            r = list(self.batch._regions[rid])
+            if not r[7]:
+                r[7] = 1
+                self.batch._regions[rid] = tuple(r)
+        return rid
+
+    def _panel(self, region, pct_region, z_min, z_max):
+        key = (region, pct_region, z_min, z_max)
+        pid = self._panel_cache.get(key)
+        if pid is None:
+            pid = self.batch.add_panel(region, pct_region, self.z_scale == "log", z_min, z_max)
+            self._panel_cache[key] = pid
+        return pid
+
+    def _rows_full(self, file):
+        """Row mask of the full panel: ``x >= x[0]`` and ``x <= x[-1]`` (``plotting.py:212-219``)."""
+        t = self.file_meta[file]["times"]
+        with np.errstate(invalid="ignore"):
+            m = (t >= t[0]) & (t <= t[-1])
+        if m.all():
+            return "full", (0, len(t))
+        return "full", np.flatnonzero(m)
+
+    def _rows_zoom(self, file, zoom):
+        t = self.file_meta[file]["times"]
+        center, duration = zoom
+        half = duration / 2
+        with np.errstate(invalid="ignore"):
+            m = (t >= center - half) & (t <= center + half)  # plotting.py:204-210
+        return ("zoom", float(center), float(duration)), np.flatnonzero(m)
+
+    def _window_has_data(self, file, group_bit, zoom):
+        """``np.any(~np.isnan(d[mask_zoom]))`` from the K1 row flags (``plotting.py:597-603``)."""
+        t = self.file_meta[file]["times"]
+        center, duration = zoom
+        with np.errstate(invalid="ignore"):
+            m = (t >= center - duration / 2) & (t <= center + duration / 2)
+        fl = self.batch.flags(file, self._flags_host)
+        return bool(np.any((fl[m] >> group_bit) & 1))
+
+    def _rows_for_dataset(self, fig, label, file, group, builder_cols, z_given, zoom):
+        """One dataset dict of the figure builders + its make_spectrogram panels."""
+        meta = self.file_meta[file]
+        if len(builder_cols) == 0 or len(meta["times"]) == 0:
+            return  # matrix_full_plot.size == 0 -> dataset skipped (fast/plotting.py:132-133,283-284)
+        z_lo, z_hi = z_given
+        pct = -1
+        if z_lo is None or z_hi is None:
+            # compute_percentile_bounds(matrix_full_plot, 1, 99, z_min, z_max) on the builder matrix
+            pct = self._region(file, group, builder_cols, "full", (0, len(meta["times"])), True)
+        # make_spectrogram always clips energy to [0, 4000] here: y_axis_min/max are not
+        # forwarded by generic_plot_multirow_optional_zoom (plotting.py:618-636 vs :104-105)
+        _, cols = self._energy_cols(file, 0, 4000)
+        row = RowSpec(label=label, file=file, group=group, full_panel=None, zoom_panel=None,
+                      times=meta["times"], energy=meta["energy"])
+        if len(cols):
+            rk, rows = self._rows_full(file)
+            n_rows = rows[1] if isinstance(rows, tuple) else len(rows)
+            if n_rows:
+                reg = self._region(file, group, cols, rk, rows, False)
+                row.full_panel = self._panel(reg, pct, z_lo, z_hi)
+            if zoom is not None:
+                rk, rows = self._rows_zoom(file, zoom)
+                if len(rows):
+                    reg = self._region(file, group, cols, rk, rows, False)
+                    row.zoom_panel = self._panel(reg, pct, z_lo, z_hi)
+        row.vmin, row.vmax = z_lo, z_hi
+        fig.rows.append(row)
+
+    def plan_pitch_angle_grid(self, orbit_entry, inst, variant, y_min=None, y_max=None, z_min=None, z_max=None):
+        """``FAST_plot_pitch_angle_grid`` (``fast/plotting.py:34-174``) for one file."""
+        file = orbit_entry["files"][inst]
+        meta = self.file_meta[file]
+        lines = orbit_entry["lines"].get(inst) or None
+        fig = FigureSpec("pitch-angle", orbit_entry["orbit"], variant, inst,
+                         f"Orbit {orbit_entry['orbit']} - Pitch Angle {inst} ESA Spectrograms",
+                         vertical_lines=lines)
+        y_lo = 0 if y_min is None else y_min
+        y_hi = 4000 if y_max is None else y_max
+        builder_cols, _ = self._energy_cols(file, y_lo, y_hi)
+        fig.zoom = zoom_window(lines, self.zoom_minutes)
+        for g, key in enumerate(meta["keys"]):
+            self._rows_for_dataset(fig, key.title(), file, g + 1, builder_cols, (z_min, z_max), fig.zoom)
+        if fig.zoom is not None:
+            fig.zoom_needed = any(self._window_has_data(r.file, r.group, fig.zoom) for r in fig.rows)
+        self.figures.append(fig)
+        return fig
+
+    def plan_instrument_grid(self, orbit_entry, variant, global_extrema=None, y_min=None, y_max=None, z_min=None, z_max=None):
+        """``FAST_plot_instrument_grid`` (``fast/plotting.py:177-328``) for one orbit."""
+        fig = FigureSpec("instrument-grid", orbit_entry["orbit"], variant, None,
+                         f"Orbit {orbit_entry['orbit']} -  ESA Spectrograms")
+        lines = None
+        pending = []
+        for inst in self.instrument_order:
+            file = orbit_entry["files"].get(inst)
+            if file is None:
+                continue
+            if lines is None and orbit_entry["lines"] is not None and inst in orbit_entry["lines"]:
+                lines = orbit_entry["lines"][inst]  # first instrument decides, even when empty (:258-265)
+            if isinstance(global_extrema, dict):
+                kp = f"{inst}_{self.y_scale}_{self.z_scale}"
+                y_lo = global_extrema.get(f"{kp}_y_min", 0 if y_min is None else y_min)
+                y_hi = global_extrema.get(f"{kp}_y_max", 4000 if y_max is None else y_max)
+                row_z = (global_extrema.get(f"{kp}_z_min"), global_extrema.get(f"{kp}_z_max"))
+            else:
+                y_lo = 0 if y_min is None else y_min
+                y_hi = 4000 if y_max is None else y_max
+                row_z = (None, None)
+            pending.append((inst, file, y_lo, y_hi, row_z))
+        fig.vertical_lines = lines if lines else None
+        fig.zoom = zoom_window(lines, self.zoom_minutes) if lines else None
+        for inst, file, y_lo, y_hi, row_z in pending:
+            builder_cols, _ = self._energy_cols(file, y_lo, y_hi)
+            # vmin/vmax = percentiles or the per-instrument extrema; a figure-level z_min/z_max
+            # argument overrides them inside generic_plot_multirow_optional_zoom (plotting.py:632-633)
+            z_lo = row_z[0] if z_min is None else z_min
+            z_hi = row_z[1] if z_max is None else z_max
+            self._rows_for_dataset(fig, inst.upper(), file, 0, builder_cols, (z_lo, z_hi), fig.zoom)
+        if fig.zoom is not None:
+            fig.zoom_needed = any(self._window_has_data(r.file, 0, fig.zoom) for r in fig.rows)
+        self.figures.append(fig)
+        return fig
+
+    # ------------------------------------------------------------------ execution
+    def upload_tables(self):
+        self.batch.upload_tables()
+
+    def run_panels(self, lut259=None, want_index=True):
+        b = self.batch
+        b.run_stats()
+        b.prepare()
+        if lut259 is not None:
+            b.set_lut(lut259)
+        b.rasterise(want_rgba=lut259 is not None or b.d_lut is not None, want_index=want_index)
+
+    def pool_items(self, steps_by_inst: dict[str, list[int]]):
+        """POOL_ITEM table for the scanned (orbit index) steps of every instrument."""
+        from .._lib import POOL_ITEM
+
+        rows = []
+        inst_len = np.zeros(len(self.instrument_order), dtype=np.int32)
+        owners = []
+        for ii, inst in enumerate(self.instrument_order):
+            pos = 0
+            for oi in steps_by_inst.get(inst, []):
+                file = self.orbits[oi]["files"].get(inst)
+                if file is None:
+                    continue
+                f = self.batch.files[file]
+                rows.append((self.batch.mat_off(file, 0), f["T"] * f["E"], f["E"], ii, pos))
+                owners.append((inst, oi, file))
+                pos += 1
+            inst_len[ii] = pos
+        items = np.array(rows, dtype=POOL_ITEM) if rows else np.zeros(0, POOL_ITEM)
+        return items, inst_len, owners
+
+
+def check_norm_status(norm_row, what: str):
+    """Raise what matplotlib would raise at draw time for an invalid panel normalisation."""
+    st = int(norm_row["status"])
+    if st == _lib.NORM_VMIN_GT_VMAX:
+        raise ValueError(f"vmin must be less or equal to vmax ({what}: vmin={norm_row['vmin']}, vmax={norm_row['vmax']})")
+    if st == _lib.NORM_INVALID:
+        raise ValueError(f"Invalid vmin or vmax ({what}: vmin={norm_row['vmin']}, vmax={norm_row['vmax']})")

@@ -54,7 +54,7 @@ def test_collapse_tpe_bit_exact(ctx, dtype, shape):
     b.upload_cubes()
     b.collapse()
     with np.errstate(invalid="ignore", over="ignore"):
-        assert np.array_equal(bits(b.sums(f, 0)), bits(np.nansum(cube, axis=1)))
+        assert same_bits(b.sums(f, 0), np.nansum(cube, axis=1), zero_sign_insensitive=False)
         for g, m in enumerate(masks):
             ref = np.nansum(cube[:, m, :], axis=1)
             assert same_bits(b.sums(f, g + 1), ref, zero_sign_insensitive=False), g
@@ -81,7 +81,7 @@ def test_collapse_tep_view_bit_exact(ctx, dtype, shape):
     f = b.add_file(view, _bits_from_masks(masks))
     b.upload_cubes()
     b.collapse()
-    assert np.array_equal(bits(b.sums(f, 0)), bits(np.nansum(view, axis=1)))
+    assert same_bits(b.sums(f, 0), np.nansum(view, axis=1), zero_sign_insensitive=False)
     for g, m in enumerate(masks):
         assert same_bits(b.sums(f, g + 1), np.nansum(view[:, m, :], axis=1), zero_sign_insensitive=False)
     nn = ~np.isnan(view)
