@@ -135,8 +135,9 @@ SIGNATURES = {
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
-    "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
-    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "csg_threshold_bytes": (_sz, [_i, _i]),
+    "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),

@@ -36,18 +36,23 @@ __device__ __forceinline__ double log10_d<double>(double v) {
   return log10(v);
 }
 
+// the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
 template <typename T>
-__device__ __forceinline__ int cmap_index(T v, const csg_panel_norm& nm, bool log_scale) {
+__device__ __forceinline__ T substitute(T v, const csg_panel_norm& nm, bool log_scale) {
   if (log_scale) {
-    // np.where(~isfinite(m) | (m <= 0), z_axis_min, m)   CS/plotting.py:278
-    if (!is_finite(v) || v <= T(0)) v = (T)nm.fill_lo;
+    if (!is_finite(v) || v <= T(0)) v = (T)nm.fill_lo;  // np.where(~isfinite(m) | (m <= 0), z_axis_min, m)
   } else {
-    // CS/plotting.py:310-312
     if (is_nan(v)) v = (T)nm.fill_lo;
     if (v == (T)(-CUDART_INF)) v = (T)nm.fill_lo;
     if (v == (T)CUDART_INF) v = (T)nm.fill_hi;
   }
-  if (nm.degenerate) return 0;  // vmin == vmax: result.fill(0) / np.full_like(value, 0)
+  return v;
+}
+
+// matplotlib's index for an (already substituted) value, evaluated directly
+template <typename T>
+__device__ __forceinline__ int cmap_index_direct(T v, const csg_panel_norm& nm, bool log_scale) {
+  if (nm.degenerate == 1) return 0;  // vmin == vmax: result.fill(0) / np.full_like(value, 0)
   T x;
   if (log_scale) {
     const T t = log10_d<T>(v);
@@ -64,6 +69,88 @@ __device__ __forceinline__ int cmap_index(T v, const csg_panel_norm& nm, bool lo
   if (xa < T(0)) return I_UNDER;
   if (xa >= T(256)) return I_OVER;
   return (int)xa;
+}
+
+// The index is a monotone step function of the value, so a panel needs at most 257
+// thresholds: thr[k] = smallest value whose "monotone code" (under = -1, 0..255, over = 256)
+// is >= k.  The rasteriser then only counts thresholds <= value -- exact by construction
+// (the thresholds come from the direct formula) and free of per-pixel float64 log10.
+template <typename T>
+__device__ __forceinline__ int monotone_code(T v, const csg_panel_norm& nm, bool log_scale) {
+  const int idx = cmap_index_direct<T>(v, nm, log_scale);
+  return idx == I_UNDER ? -1 : (idx == I_OVER ? 256 : idx);  // I_BAD cannot occur for ordered finite input
+}
+
+constexpr int kThr = 257;
+constexpr int kThrPitch = 264;  // padded row length of the threshold table
+
+template <typename T>
+__global__ void __launch_bounds__(288)
+    panel_threshold_kernel(const csg_panel* __restrict__ panels, const csg_panel_norm* __restrict__ norms, int n_panels,
+                           T* __restrict__ thresholds) {
+  typedef typename Key<T>::U U;
+  const int pi = blockIdx.x;
+  const int k = threadIdx.x;
+  if (k >= kThr) return;
+  const csg_panel_norm nm = norms[pi];
+  T* out = thresholds + (size_t)pi * kThrPitch;
+  if (nm.status != CSG_NORM_OK || nm.degenerate != 0) {
+    out[k] = (T)CUDART_INF;
+    return;
+  }
+  const bool log_scale = panels[pi].log_scale != 0;
+  // ordered domain of substituted values: finite positives (log) or [-inf, +inf] (linear)
+  const U dom_lo = log_scale ? Key<T>::key((T)0) + 1 : Key<T>::key((T)(-CUDART_INF));
+  const U dom_hi = log_scale ? Key<T>::key((T)CUDART_INF) - 1 : Key<T>::key((T)CUDART_INF);
+  auto code = [&](U key) { return monotone_code<T>(Key<T>::val(key), nm, log_scale); };
+  // start from the analytic inverse, then gallop to a bracket and bisect
+  const double frac = (double)k / 256.0;
+  double guess = log_scale ? exp10(nm.t_vmin + frac * nm.t_range) : nm.t_vmin + frac * nm.t_range;
+  T gT = (T)guess;
+  if (is_nan(gT)) gT = T(1);
+  U g = Key<T>::key(gT);
+  if (g < dom_lo) g = dom_lo;
+  if (g > dom_hi) g = dom_hi;
+  U lo, hi;  // invariant once bracketed: code(lo) < k <= code(hi)
+  U step = 2;
+  bool found = true;
+  if (code(g) >= k) {
+    hi = g;
+    while (true) {
+      if (hi == dom_lo) {  // even the smallest value reaches k
+        lo = hi;
+        break;
+      }
+      lo = (hi - dom_lo > step) ? hi - step : dom_lo;
+      if (code(lo) < k) break;
+      hi = lo;
+      step <<= 2;
+    }
+  } else {
+    lo = g;
+    while (true) {
+      if (lo == dom_hi) {  // no value reaches k
+        found = false;
+        break;
+      }
+      hi = (dom_hi - lo > step) ? lo + step : dom_hi;
+      if (code(hi) >= k) break;
+      lo = hi;
+      step <<= 2;
+    }
+  }
+  if (!found) {
+    out[k] = (T)CUDART_INF;
+    return;
+  }
+  while (hi - lo > 1) {
+    const U mid = lo + ((hi - lo) >> 1);
+    if (code(mid) >= k)
+      hi = mid;
+    else
+      lo = mid;
+  }
+  out[k] = Key<T>::val(hi);
 }
 
 template <typename T>
@@ -128,6 +215,8 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
       nm.degenerate = 1;
     else if (zmin > zmax)
       nm.status = CSG_NORM_VMIN_GT_VMAX;
+    else if (is_nan(zmin) || is_nan(zmax))
+      nm.degenerate = 2;  // every normalised value is NaN -> "bad" colour
   }
   norms[i] = nm;
 }
@@ -139,10 +228,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                      const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
-                     const csg_panel_norm* __restrict__ norms, int n_panels,
+                     const csg_panel_norm* __restrict__ norms, int n_panels, const T* __restrict__ thresholds,
                      const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
                      uint16_t* __restrict__ index) {
   __shared__ uint32_t s_lut[259];
+  __shared__ T s_thr[kThrPitch];
   __shared__ uint16_t s_idx[kTile][kTile + 2];
   __shared__ csg_panel_norm s_nm;
   __shared__ csg_region s_rg;
@@ -164,6 +254,8 @@ __global__ void __launch_bounds__(256)
   }
   for (int i = tid; i < 259; i += 256) s_lut[i] = lut ? lut[i] : 0u;
   __syncthreads();
+  for (int i = tid; i < kThr; i += 256) s_thr[i] = thresholds[(size_t)s_panel * kThrPitch + i];
+  __syncthreads();
   const csg_panel pn = panels[s_panel];
   const csg_region& rg = s_rg;
   if (s_nm.status != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
@@ -182,8 +274,18 @@ __global__ void __launch_bounds__(256)
     int idx = 0;
     if (e < rg.ne && tt < rg.nt) {
       const int row = rg.rows_off < 0 ? rg.t0 + tt : __ldg(pool + rg.rows_off + tt);
-      const T v = __ldg(mats + rg.mat_off + (long long)row * rg.ld + col);
-      idx = cmap_index<T>(v, s_nm, log_scale);
+      const T v = substitute<T>(__ldg(mats + rg.mat_off + (long long)row * rg.ld + col), s_nm, log_scale);
+      if (s_nm.degenerate == 1) {
+        idx = 0;
+      } else if (s_nm.degenerate == 2 || is_nan(v)) {
+        idx = I_BAD;
+      } else {
+        int n = 0;  // thresholds <= v (upper bound over 257 sorted entries)
+#pragma unroll
+        for (int step = 256; step >= 1; step >>= 1)
+          if (n + step <= kThr && s_thr[n + step - 1] <= v) n += step;
+        idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
+      }
     }
     s_idx[ty + k][tx] = (uint16_t)idx;
   }
@@ -209,37 +311,49 @@ int32_t csg_raster_blocks(int32_t ne, int32_t nt) {
   return ((ne + kTile - 1) / kTile) * ((nt + kTile - 1) / kTile);
 }
 
+size_t csg_threshold_bytes(int n_panels, int dtype) {
+  return (size_t)(n_panels > 0 ? n_panels : 0) * kThrPitch * (dtype == CSG_F64 ? 8 : 4);
+}
+
 int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels, const csg_region* d_regions,
-                      const csg_region_stats* d_stats, int dtype, csg_panel_norm* d_norms) {
+                      const csg_region_stats* d_stats, int dtype, csg_panel_norm* d_norms, void* d_thresholds) {
   (void)d_regions;
   if (!ctx) return CSG_ERR_ARG;
   if (n_panels <= 0) return CSG_OK;
-  if (!d_panels || !d_stats || !d_norms) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  if (!d_panels || !d_stats || !d_norms || !d_thresholds) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   const int blocks = (n_panels + 127) / 128;
-  if (dtype == CSG_F32)
+  if (dtype == CSG_F32) {
     panel_prepare_kernel<float><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
-  else if (dtype == CSG_F64)
+    CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
+    panel_threshold_kernel<float><<<n_panels, 288, 0, ctx->stream>>>(d_panels, d_norms, n_panels, (float*)d_thresholds);
+  } else if (dtype == CSG_F64) {
     panel_prepare_kernel<double><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
-  else
+    CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
+    panel_threshold_kernel<double><<<n_panels, 288, 0, ctx->stream>>>(d_panels, d_norms, n_panels, (double*)d_thresholds);
+  } else {
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
-  CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
+  }
+  CSG_LAUNCH_CHECK(ctx, "panel_threshold_kernel");
   return CSG_OK;
 }
 
 int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels, const csg_panel_norm* d_norms,
-                  int n_panels, int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index) {
+                  const void* d_thresholds, int n_panels, int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba,
+                  uint16_t* d_index) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_panels <= 0 || total_blocks <= 0) return CSG_OK;
-  if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms || !d_thresholds)
+    return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
   if (dtype == CSG_F32)
     rasterise_kernel<float><<<total_blocks, 256, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
-                                                                   d_norms, n_panels, (const uint32_t*)d_lut,
-                                                                   (uint32_t*)d_rgba, d_index);
+                                                                   d_norms, n_panels, (const float*)d_thresholds,
+                                                                   (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else if (dtype == CSG_F64)
     rasterise_kernel<double><<<total_blocks, 256, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
-                                                                    d_panels, d_norms, n_panels, (const uint32_t*)d_lut,
+                                                                    d_panels, d_norms, n_panels,
+                                                                    (const double*)d_thresholds, (const uint32_t*)d_lut,
                                                                     (uint32_t*)d_rgba, d_index);
   else
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);

@@ -19,14 +19,16 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kTargets = 4;  // (lo, hi) neighbours of two percentiles
 
-template <typename T>
-__device__ __forceinline__ T region_cell(const T* __restrict__ mats, const csg_region& rg,
-                                         const int32_t* __restrict__ pool, long long i) {
-  const int r = (int)(i / rg.ne);
-  const int c = (int)(i - (long long)r * rg.ne);
-  const int row = rg.rows_off < 0 ? rg.t0 + r : __ldg(pool + rg.rows_off + r);
-  const int col = __ldg(pool + rg.cols_off + c);
-  return __ldg(mats + rg.mat_off + (long long)row * rg.ld + col);
+constexpr int kMaxCols = 1024;  // column lists up to this length are staged in shared memory
+
+// one atomic per distinct bin per warp: spectrogram counts repeat heavily, so a plain
+// shared-memory atomic per lane serialises on a handful of addresses
+__device__ __forceinline__ void hist_add(unsigned* h, unsigned bin, bool valid) {
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+  }
 }
 
 // numpy _get_indexes/_get_gamma for one percentile over n valid samples, arithmetic in T
@@ -47,6 +49,7 @@ __device__ void percentile_ranks(long long n, double p, long long& lo, long long
   } else {
     const T fl = floor(v);
     lo = (long long)fl;
+    if (lo > n - 1) lo = n - 1;
     hi = lo + 1;
     if (hi > n - 1) hi = n - 1;
     gamma = sub_rn(v, fl);
@@ -67,46 +70,70 @@ __global__ void __launch_bounds__(kThreads)
                         const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out) {
   typedef typename Key<T>::U U;
   __shared__ unsigned s_hist[kTargets][kBins];
+  __shared__ int s_cols[kMaxCols];
   __shared__ long long s_ll[32];
   __shared__ double s_d[32];
   __shared__ unsigned s_u[32];
   __shared__ U s_prefix[kTargets];
   __shared__ long long s_rank[kTargets];
+  __shared__ int s_hidx[kTargets];
 
   const csg_region rg = regions[blockIdx.x];
-  const long long n_cells = (long long)rg.nt * rg.ne;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const bool cols_in_smem = rg.ne <= kMaxCols;
 
   for (int i = tid; i < kBins; i += kThreads) s_hist[0][i] = 0;
+  if (cols_in_smem)
+    for (int i = tid; i < rg.ne; i += kThreads) s_cols[i] = __ldg(pool + rg.cols_off + i);
   __syncthreads();
+
+  // Walk the region warp-per-time-row: lanes stride over the energy columns, which are
+  // (nearly) contiguous in the collapsed (T,E) matrix -> coalesced, division-free.
+  auto for_each_cell = [&](auto&& fn) {
+    for (int r = warp; r < rg.nt; r += kWarps) {
+      const int row = rg.rows_off < 0 ? rg.t0 + r : __ldg(pool + rg.rows_off + r);
+      const T* rp = mats + rg.mat_off + (long long)row * rg.ld;
+      for (int c0 = 0; c0 < rg.ne; c0 += 32) {
+        const int c = c0 + lane;
+        const bool in = c < rg.ne;
+        T v = T(0);
+        if (in) v = __ldg(rp + (cols_in_smem ? s_cols[c] : __ldg(pool + rg.cols_off + c)));
+        fn(v, in);
+      }
+    }
+  };
 
   // ---- pass 0: classification + first digit
   long long n_valid = 0;
   unsigned n_nan = 0, n_ninf = 0, n_pinf = 0, n_pos = 0;
   double min_pos = CUDART_INF, fin_min = CUDART_INF, fin_max = -CUDART_INF;
   constexpr int kTopShift = Key<T>::BITS - kDigitBits;
-  for (long long i = tid; i < n_cells; i += kThreads) {
-    const T v = region_cell(mats, rg, pool, i);
-    if (is_nan(v)) {
-      ++n_nan;
-      continue;
-    }
-    ++n_valid;
-    if (is_finite(v)) {
-      const double dv = (double)v;
-      fin_min = fmin(fin_min, dv);
-      fin_max = fmax(fin_max, dv);
-      if (v > T(0)) {
-        ++n_pos;
-        min_pos = fmin(min_pos, dv);
+  const bool want = rg.want_pct != 0;
+  for_each_cell([&](T v, bool in) {
+    const bool valid = in && !is_nan(v);
+    if (in) {
+      if (!valid) {
+        ++n_nan;
+      } else {
+        ++n_valid;
+        if (is_finite(v)) {
+          const double dv = (double)v;
+          fin_min = fmin(fin_min, dv);
+          fin_max = fmax(fin_max, dv);
+          if (v > T(0)) {
+            ++n_pos;
+            min_pos = fmin(min_pos, dv);
+          }
+        } else if (v > T(0)) {
+          ++n_pinf;
+        } else {
+          ++n_ninf;
+        }
       }
-    } else if (v > T(0)) {
-      ++n_pinf;
-    } else {
-      ++n_ninf;
     }
-    if (rg.want_pct) atomicAdd(&s_hist[0][(unsigned)(Key<T>::key(v) >> kTopShift)], 1u);
-  }
+    if (want) hist_add(s_hist[0], valid ? (unsigned)(Key<T>::key(v) >> kTopShift) : 0u, valid);
+  });
   auto addll = [](long long a, long long b) { return a + b; };
   auto addu = [](unsigned a, unsigned b) { return a + b; };
   auto mind = [](double a, double b) { return fmin(a, b); };
@@ -128,7 +155,7 @@ __global__ void __launch_bounds__(kThreads)
   st.n_valid = n_valid;
   st.n_nan = (int)n_nan, st.n_neginf = (int)n_ninf, st.n_posinf = (int)n_pinf, st.n_pos = (int)n_pos;
 
-  if (!rg.want_pct || n_valid == 0) {
+  if (!want || n_valid == 0) {
     if (tid == 0) out[blockIdx.x] = st;
     return;
   }
@@ -141,26 +168,23 @@ __global__ void __launch_bounds__(kThreads)
   if (tid < kTargets) {
     s_prefix[tid] = 0;
     s_rank[tid] = rank[tid];
+    s_hidx[tid] = 0;
   }
   __syncthreads();
 
   // ---- digit loop
   int shift = kTopShift;
   int bits = kDigitBits;
-  bool first = true;
   while (true) {
     const int nb = 1 << bits;
-    // locate each target's bucket in its histogram (level 0: all share histogram 0)
+    // locate each target's bucket in the histogram of its prefix
     for (int j = 0; j < kTargets; ++j) {
-      const unsigned* h = s_hist[first ? 0 : j];
-      const long long want = s_rank[j];
-      // each thread owns nb/kThreads consecutive bins (nb >= kThreads is not required)
+      const unsigned* h = s_hist[s_hidx[j]];
+      const long long want_rank = s_rank[j];
       const int per = (nb + kThreads - 1) / kThreads;
       const int b0 = tid * per;
       long long mine = 0;
       for (int b = b0; b < b0 + per && b < nb; ++b) mine += h[b];
-      // exclusive scan of `mine` over threads
-      const int lane = tid & 31, warp = tid >> 5;
       long long inc = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -173,13 +197,13 @@ __global__ void __launch_bounds__(kThreads)
       long long warp_off = 0;
       for (int w = 0; w < warp; ++w) warp_off += s_ll[w];
       const long long excl = warp_off + inc - mine;
-      if (want >= excl && want < excl + mine) {
+      if (want_rank >= excl && want_rank < excl + mine) {
         long long run = excl;
         for (int b = b0; b < b0 + per && b < nb; ++b) {
           const long long c = h[b];
-          if (want < run + c) {
+          if (want_rank < run + c) {
             s_prefix[j] = (s_prefix[j] << bits) | (U)b;
-            s_rank[j] = want - run;
+            s_rank[j] = want_rank - run;
             break;
           }
           run += c;
@@ -188,27 +212,37 @@ __global__ void __launch_bounds__(kThreads)
       __syncthreads();
     }
     if (shift == 0) break;
-    // next digit
+    // next digit: one histogram per DISTINCT prefix (lo/hi neighbours usually share theirs)
     const int prev_shift = shift;
     bits = shift < kDigitBits ? shift : kDigitBits;
     shift -= bits;
     const int nb2 = 1 << bits;
+    if (tid == 0) {
+      for (int j = 0; j < kTargets; ++j) {
+        int h = j;
+        for (int i = 0; i < j; ++i)
+          if (s_prefix[i] == s_prefix[j]) {
+            h = s_hidx[i];
+            break;
+          }
+        s_hidx[j] = h;
+      }
+    }
     for (int i = tid; i < kTargets * kBins; i += kThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const U p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
-    for (long long i = tid; i < n_cells; i += kThreads) {
-      const T v = region_cell(mats, rg, pool, i);
-      if (is_nan(v)) continue;
+    const bool u1 = s_hidx[1] == 1, u2 = s_hidx[2] == 2, u3 = s_hidx[3] == 3;
+    for_each_cell([&](T v, bool in) {
+      const bool valid = in && !is_nan(v);
       const U k = Key<T>::key(v);
       const U hi = k >> prev_shift;
       const unsigned b = (unsigned)(k >> shift) & (unsigned)(nb2 - 1);
-      if (hi == p0) atomicAdd(&s_hist[0][b], 1u);
-      if (hi == p1) atomicAdd(&s_hist[1][b], 1u);
-      if (hi == p2) atomicAdd(&s_hist[2][b], 1u);
-      if (hi == p3) atomicAdd(&s_hist[3][b], 1u);
-    }
+      hist_add(s_hist[0], b, valid && hi == p0);
+      if (u1) hist_add(s_hist[1], b, valid && hi == p1);
+      if (u2) hist_add(s_hist[2], b, valid && hi == p2);
+      if (u3) hist_add(s_hist[3], b, valid && hi == p3);
+    });
     __syncthreads();
-    first = false;
   }
 
   if (tid == 0) {

@@ -92,6 +92,7 @@ class Batch:
         self.d_rgba: DevBuf | None = None
         self.d_index: DevBuf | None = None
         self.d_lut: DevBuf | None = None
+        self.d_thr: DevBuf | None = None
         self._raster_blocks = 0
         self._tables_dirty = True
 
@@ -278,6 +279,9 @@ class Batch:
         if len(panels):
             if self.d_norms is None or self.d_norms.nbytes < len(panels) * PANEL_NORM.itemsize:
                 self.d_norms = self.ctx.alloc(len(panels) * PANEL_NORM.itemsize)
+            thr_bytes = self.ctx.lib.csg_threshold_bytes(len(panels), self.code)
+            if self.d_thr is None or self.d_thr.nbytes < thr_bytes:
+                self.d_thr = self.ctx.alloc(thr_bytes)
 
     def set_panel_bounds(self, panel: int, z_min=None, z_max=None):
         p = list(self._panels[panel])
@@ -309,7 +313,7 @@ class Batch:
         self.ctx._check(
             self.ctx.lib.csg_panel_prepare(
                 self.ctx.handle, self.d_panels.ptr, len(self._panels), self.d_regions.ptr, self.d_stats.ptr,
-                self.code, self.d_norms.ptr,
+                self.code, self.d_norms.ptr, self.d_thr.ptr,
             )
         )
 
@@ -337,7 +341,7 @@ class Batch:
         self.ctx._check(
             self.ctx.lib.csg_rasterise(
                 self.ctx.handle, self.d_sums.ptr, self.code, self.d_regions.ptr, self.d_pool.ptr, self.d_panels.ptr,
-                self.d_norms.ptr, len(self._panels), self._raster_blocks,
+                self.d_norms.ptr, self.d_thr.ptr, len(self._panels), self._raster_blocks,
                 self.d_lut.ptr if self.d_lut is not None else None,
                 self.d_rgba.ptr if want_rgba else None, self.d_index.ptr if want_index else None,
             )

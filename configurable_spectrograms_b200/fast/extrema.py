@@ -179,8 +179,11 @@ def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, stat
     if compute_mins:
         requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
     max_E = max((shard.batch.files[f]["E"] for _, _, f in owners), default=1)
+    backend = getattr(shard, "_pool_backend", None)
+    if backend is None:
+        backend = shard._pool_backend = GpuPoolBackend(shard.batch)  # persistent scratch across steps
     values, counts, npos = prefix_percentiles(
-        GpuPoolBackend(shard.batch), shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm
+        backend, shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm
     )
     # ---- per-step energy candidates need every rank's per-file counts in sequence order
     local_rows = {}

@@ -11,8 +11,9 @@ handful of buckets.
 
 Multi-GPU: ranks hold contiguous blocks of the ascending-orbit sequence.  Per digit one
 all-gather of each rank's bucket totals gives every rank the counts held by lower
-ranks (added by ``csg_pool_scan``); one all-gather of the surviving (instrument,
-prefix) pairs and their lower bounds keeps the slot tables identical everywhere.
+ranks (added on the fly by ``csg_pool_locate``); one all-gather of the surviving
+(instrument, prefix) pairs and their lower bounds keeps the slot tables identical
+everywhere.
 """
 
 from __future__ import annotations
@@ -25,6 +26,7 @@ from ._lib import POOL_ITEM, POOL_QUERY
 FIRST_BITS = 11
 NEXT_BITS = 10
 MAX_SLOTS = 64
+_U64MAX = np.iinfo(np.uint64).max
 
 
 def key_bits(dtype) -> int:
@@ -70,41 +72,83 @@ def percentile_ranks(n: np.ndarray, p, dtype):
     return lo, hi, gamma
 
 
-def lerp(a, b, g, dtype):
-    """numpy ``_lerp`` rounded after every operation in D."""
-    D = np.dtype(dtype).type
+def lerp_vec(a, b, g, dtype):
+    """numpy ``_lerp`` rounded after every operation in D (vectorised)."""
+    dt = np.dtype(dtype)
     with np.errstate(invalid="ignore", over="ignore"):
-        a, b, g = D(a), D(b), D(g)
-        d = D(b - a)
-        r = D(a + D(d * g))
-        if g >= 0.5:
-            r = D(b - D(d * D(D(1) - g)))
-    return r
+        a, b, g = a.astype(dt), b.astype(dt), g.astype(dt)
+        d = (b - a).astype(dt)
+        r = (a + (d * g).astype(dt)).astype(dt)
+        alt = (b - (d * (dt.type(1) - g).astype(dt)).astype(dt)).astype(dt)
+    return np.where(g >= 0.5, alt, r)
+
+
+class _Grow:
+    """Grow-only device / pinned scratch so a steady-state step allocates nothing."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.dev: dict[str, _lib.DevBuf] = {}
+        self.pin: dict[str, _lib.PinnedBuf] = {}
+
+    def device(self, name: str, nbytes: int) -> _lib.DevBuf:
+        buf = self.dev.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            buf = self.dev[name] = self.ctx.alloc(max(int(nbytes * 1.25), 256))
+        return buf
+
+    def pinned(self, name: str, nbytes: int) -> _lib.PinnedBuf:
+        buf = self.pin.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            buf = self.pin[name] = self.ctx.pinned(max(int(nbytes * 1.25), 256))
+        return buf
 
 
 class GpuPoolBackend:
-    """The four pool kernels over a :class:`engine.Batch`'s sums buffer."""
+    """The four pool kernels over a :class:`engine.Batch`'s sums buffer (persistent scratch)."""
 
     def __init__(self, batch):
         self.batch = batch
         self.ctx = batch.ctx
-        self.d_items = None
+        self.mem = _Grow(batch.ctx)
+        self._items_key = None
         self.n_items = 0
 
+    # -- small transfers through pinned staging
+    def _put(self, name: str, arr: np.ndarray) -> _lib.DevBuf:
+        arr = np.ascontiguousarray(arr)
+        pin = self.mem.pinned(name, arr.nbytes)
+        pin.array[: arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        dev = self.mem.device(name, arr.nbytes)
+        self.ctx._check(self.ctx.lib.csg_h2d(self.ctx.handle, dev.ptr, pin.ptr, arr.nbytes))
+        return dev
+
+    def _get(self, name: str, dev: _lib.DevBuf, dtype, count: int, sync=True) -> np.ndarray:
+        nbytes = np.dtype(dtype).itemsize * count
+        pin = self.mem.pinned("get_" + name, nbytes)
+        self.ctx._check(self.ctx.lib.csg_d2h(self.ctx.handle, pin.ptr, dev.ptr, nbytes))
+        if sync:
+            self.ctx.sync()
+        return pin.view(dtype, count)
+
     def set_items(self, items: np.ndarray, n_inst: int, max_pos: int, inst_len: np.ndarray, max_E: int):
+        key = (items.tobytes(), n_inst, max_pos, inst_len.tobytes(), max_E)
         self.items = items
         self.n_items = len(items)
         self.n_inst, self.max_pos, self.max_E = n_inst, max(max_pos, 1), max(max_E, 1)
-        self.d_items = self.ctx.to_device(items) if len(items) else None
-        self.d_inst_len = self.ctx.to_device(np.ascontiguousarray(inst_len, dtype=np.int32))
+        if key != self._items_key:
+            self.d_items = self._put("items", items) if len(items) else None
+            self.d_inst_len = self._put("inst_len", np.ascontiguousarray(inst_len, dtype=np.int32))
+            self._items_key = key
 
     def hist_first(self, bits: int):
         nb = 1 << bits
         self.n_slots, self.bits = 1, bits
-        self.d_hist = self.ctx.alloc(self.n_inst * self.max_pos * nb * 4)
-        self.d_hist.zero()
-        d_counts = self.ctx.alloc(max(self.n_items, 1) * self.max_E * 4)
-        d_npos = self.ctx.alloc(max(self.n_items, 1) * 4)
+        nbytes = self.n_inst * self.max_pos * nb * 4
+        self.d_hist = self.mem.device("hist0", nbytes)
+        self.ctx._check(self.ctx.lib.csg_memset(self.ctx.handle, self.d_hist.ptr, 0, nbytes))
+        d_counts = self.mem.device("counts", max(self.n_items, 1) * self.max_E * 4)
+        d_npos = self.mem.device("npos", max(self.n_items, 1) * 4)
         if self.n_items:
             self.ctx._check(
                 self.ctx.lib.csg_pool_hist_first(
@@ -112,17 +156,18 @@ class GpuPoolBackend:
                     self.max_pos, bits, self.max_E, self.d_hist.ptr, d_counts.ptr, d_npos.ptr,
                 )
             )
-        counts = d_counts.download(np.int32, self.n_items * self.max_E, sync=False).reshape(self.n_items, self.max_E)
-        npos = d_npos.download(np.int32, self.n_items)
-        return counts, npos
+        counts = self._get("counts", d_counts, np.int32, self.n_items * self.max_E, sync=False)
+        npos = self._get("npos", d_npos, np.int32, self.n_items)
+        return counts.reshape(self.n_items, self.max_E).copy(), npos.copy()
 
     def hist_refine(self, slot_prefix: np.ndarray, prefix_shift: int, shift: int, bits: int):
         n_slots = slot_prefix.shape[1]
         nb = 1 << bits
         self.n_slots, self.bits = n_slots, bits
-        self.d_hist = self.ctx.alloc(self.n_inst * self.max_pos * n_slots * nb * 4)
-        self.d_hist.zero()
-        d_pref = self.ctx.to_device(np.ascontiguousarray(slot_prefix, dtype=np.uint64))
+        nbytes = self.n_inst * self.max_pos * n_slots * nb * 4
+        self.d_hist = self.mem.device("hist1", nbytes)
+        self.ctx._check(self.ctx.lib.csg_memset(self.ctx.handle, self.d_hist.ptr, 0, nbytes))
+        d_pref = self._put("pref", np.ascontiguousarray(slot_prefix, dtype=np.uint64))
         if self.n_items:
             self.ctx._check(
                 self.ctx.lib.csg_pool_hist_refine(
@@ -135,7 +180,7 @@ class GpuPoolBackend:
         """Inclusive scan along the file sequence; returns this rank's bucket totals when asked."""
         nb = 1 << self.bits
         n = self.n_inst * self.n_slots * nb
-        d_tot = self.ctx.alloc(n * 4) if want_totals else None
+        d_tot = self.mem.device("totals", n * 4) if want_totals else None
         self.ctx._check(
             self.ctx.lib.csg_pool_scan(
                 self.ctx.handle, self.d_hist.ptr, self.n_inst, self.max_pos, self.d_inst_len.ptr, self.n_slots,
@@ -143,21 +188,21 @@ class GpuPoolBackend:
             )
         )
         if want_totals:
-            return d_tot.download(np.uint32, n).reshape(self.n_inst, self.n_slots, nb)
+            return self._get("totals", d_tot, np.uint32, n).reshape(self.n_inst, self.n_slots, nb).copy()
         return None
 
     def locate(self, queries: np.ndarray, base: np.ndarray | None) -> np.ndarray:
         if len(queries) == 0:
             return queries
-        d_q = self.ctx.to_device(queries)
-        d_base = self.ctx.to_device(np.ascontiguousarray(base, dtype=np.uint32)) if base is not None else None
+        d_q = self._put("queries", queries)
+        d_base = self._put("base", np.ascontiguousarray(base, dtype=np.uint32)) if base is not None else None
         self.ctx._check(
             self.ctx.lib.csg_pool_locate(
                 self.ctx.handle, self.d_hist.ptr, self.max_pos, self.n_slots, self.bits,
                 d_base.ptr if d_base is not None else None, d_q.ptr, len(queries),
             )
         )
-        return d_q.download(POOL_QUERY, len(queries))
+        return self._get("queries", d_q, POOL_QUERY, len(queries)).copy()
 
 
 class SingleRank:
@@ -194,47 +239,47 @@ def prefix_percentiles(backend, dtype, items: np.ndarray, n_inst: int, inst_len:
     # ---- digit 0: histograms, positive counts
     shift0, bits0 = plan[0]
     counts, npos = backend.hist_first(bits0)
-    # pool size after each local prefix, plus what lower ranks hold
-    local_tot = np.zeros(n_inst, dtype=np.int64)
     n_after = np.zeros((n_inst, max(max_pos, 1)), dtype=np.int64)
-    for i in range(n_inst):
-        sel = np.flatnonzero(items["inst"] == i)
-        order = sel[np.argsort(items["pos"][sel])]
-        c = np.cumsum(npos[order].astype(np.int64))
-        n_after[i, : len(c)] = c
-        local_tot[i] = c[-1] if len(c) else 0
+    if len(items):
+        per = np.zeros((n_inst, max(max_pos, 1)), dtype=np.int64)
+        per[items["inst"], items["pos"]] = npos
+        n_after = np.cumsum(per, axis=1)
+    local_tot = n_after[:, -1].copy() if max_pos else np.zeros(n_inst, np.int64)
     all_tot = comm.allgather(local_tot)
     below = np.sum(all_tot[: comm.rank], axis=0).astype(np.int64) if comm.rank > 0 else np.zeros(n_inst, np.int64)
     grand = np.sum(all_tot, axis=0).astype(np.int64)
-    n_after += below[:, None]
+    n_after = n_after + below[:, None]
 
     # ---- queries: (request, pos) pairs -> two rank targets each
-    q_req, q_pos, q_lo, q_hi, q_gamma = [], [], [], [], []
+    qr, qp, qlo, qhi, qg = [], [], [], [], []
     for r, req in enumerate(requests):
         i = req["inst"]
         L = int(inst_len[i])
+        if L == 0:
+            continue
+        n = n_after[i, :L]
         if req["mode"] == "last":
-            # the pool after the globally last file: owned by the highest rank holding files of inst
             holders = [rk for rk in range(comm.size) if all_tot[rk][i] > 0]
-            if not holders or holders[-1] != comm.rank or L == 0:
+            if not holders or holders[-1] != comm.rank:
                 continue
-            # last local position with a non-empty cumulative pool
-            pos_list = [L - 1]
+            ks = np.array([L - 1])
         else:
-            pos_list = list(range(L))
-        for k in pos_list:
-            n = int(n_after[i, k])
-            if n <= 0:
-                continue
-            if req["mode"] == "running_max" and k > 0 and n == int(n_after[i, k - 1]):
-                continue  # file added no positive sample: same pool, same candidate
-            lo, hi, g = percentile_ranks(np.array([n]), req["p"], D)
-            q_req.append(r), q_pos.append(k), q_lo.append(int(lo[0])), q_hi.append(int(hi[0])), q_gamma.append(g[0])
+            prev = np.concatenate([[below[i]], n[:-1]])
+            ks = np.flatnonzero((n > 0) & (n != prev))  # a file without positives repeats the candidate
+        if len(ks) == 0:
+            continue
+        lo, hi, g = percentile_ranks(n[ks], req["p"], D)
+        qr.append(np.full(len(ks), r)), qp.append(ks), qlo.append(lo), qhi.append(hi), qg.append(g)
+    if qr:
+        q_req, q_pos = np.concatenate(qr), np.concatenate(qp)
+        q_lo, q_hi, q_gamma = np.concatenate(qlo), np.concatenate(qhi), np.concatenate(qg)
+    else:
+        q_req = q_pos = q_lo = q_hi = np.zeros(0, np.int64)
+        q_gamma = np.zeros(0, D)
     nq = len(q_req)
-    q_req = np.array(q_req, dtype=np.int64)
-    q_pos = np.array(q_pos, dtype=np.int64)
-    q_inst = np.array([requests[r]["inst"] for r in q_req], dtype=np.int64) if nq else np.zeros(0, np.int64)
-    # targets: index 2*j (lo) and 2*j+1 (hi)
+    req_inst = np.array([r["inst"] for r in requests], dtype=np.int64)
+    req_runmax = np.array([r["mode"] == "running_max" for r in requests], dtype=bool)
+    q_inst = req_inst[q_req] if nq else np.zeros(0, np.int64)
     t_rank = np.empty(2 * nq, dtype=np.int64)
     t_rank[0::2], t_rank[1::2] = q_lo, q_hi
     t_prefix = np.zeros(2 * nq, dtype=np.uint64)
@@ -255,74 +300,74 @@ def prefix_percentiles(backend, dtype, items: np.ndarray, n_inst: int, inst_len:
     for level, (shift, bits) in enumerate(plan):
         if level == 0:
             base = exchange_base(backend.scan(comm.size > 1))
-            t_slot = np.zeros(2 * nq, dtype=np.int64)
-            pending = np.repeat(active, 2)
-            _locate(backend, base, t_inst, t_pos, t_slot, t_rank, t_prefix, pending, bits)
+            _locate(backend, base, t_inst, t_pos, np.zeros(2 * nq, np.int64), t_rank, t_prefix, np.repeat(active, 2), bits)
         else:
-            # distinct (inst, prefix) among active targets, agreed across ranks
             act_t = np.repeat(active, 2)
-            mine = sorted({(int(i), int(p)) for i, p in zip(t_inst[act_t], t_prefix[act_t])})
-            union = sorted(set().union(*[set(x) for x in comm.allgather_object(mine)]))
-            todo = {i: [p for (ii, p) in union if ii == i] for i in range(n_inst)}
-            done_t = ~act_t  # inactive targets need no refinement
+            mine = [np.unique(t_prefix[act_t & (t_inst == i)]) for i in range(n_inst)]
+            if comm.size > 1:
+                parts = comm.allgather_object(mine)
+                mine = [np.unique(np.concatenate([p[i] for p in parts])) for i in range(n_inst)]
+            todo = [m for m in mine]
+            done_t = ~act_t
             while True:
-                n_slots = min(MAX_SLOTS, max((len(v) for v in todo.values()), default=0))
+                n_slots = min(MAX_SLOTS, max((len(v) for v in todo), default=0))
                 if n_slots == 0:
                     break
-                table = np.full((n_inst, n_slots), np.iinfo(np.uint64).max, dtype=np.uint64)
-                taken = {}
+                table = np.full((n_inst, n_slots), _U64MAX, dtype=np.uint64)
                 for i in range(n_inst):
                     chunk = todo[i][:n_slots]
                     todo[i] = todo[i][n_slots:]
-                    table[i, : len(chunk)] = np.array(chunk, dtype=np.uint64)
-                    taken[i] = {p: s for s, p in enumerate(chunk)}
+                    table[i, : len(chunk)] = chunk
                 backend.hist_refine(table, prev_shift, shift, bits)
                 base = exchange_base(backend.scan(comm.size > 1))
+                # slot of every pending target = position of its prefix in its instrument's row
                 t_slot = np.full(2 * nq, -1, dtype=np.int64)
-                for j in np.flatnonzero(~done_t):
-                    s = taken[int(t_inst[j])].get(int(t_prefix[j]))
-                    if s is not None:
-                        t_slot[j] = s
+                for i in range(n_inst):
+                    sel = np.flatnonzero(~done_t & (t_inst == i))
+                    if len(sel) == 0:
+                        continue
+                    row = table[i]
+                    s = np.searchsorted(row, t_prefix[sel])
+                    s = np.minimum(s, n_slots - 1)
+                    hit = row[s] == t_prefix[sel]
+                    t_slot[sel[hit]] = s[hit]
                 pending = t_slot >= 0
                 _locate(backend, base, t_inst, t_pos, t_slot, t_rank, t_prefix, pending, bits)
                 done_t |= pending
         prev_shift = shift
         # ---- prune prefixes that cannot hold the running maximum
-        lo_bound = bits_to_value(t_prefix[0::2] << np.uint64(shift), D).astype(np.float64)
-        hi_bound = bits_to_value(((t_prefix[1::2] + np.uint64(1)) << np.uint64(shift)) - np.uint64(1), D).astype(np.float64)
-        best_local = {}
-        for r, req in enumerate(requests):
-            if req["mode"] != "running_max":
-                continue
-            sel = active & (q_req == r)
-            best_local[r] = float(lo_bound[sel].max()) if sel.any() else -np.inf
-        best = {}
-        for d in comm.allgather_object(best_local):
-            for r, v in d.items():
-                best[r] = max(best.get(r, -np.inf), v)
-        for r, req in enumerate(requests):
-            if req["mode"] != "running_max":
-                continue
-            sel = active & (q_req == r)
-            active[sel & (hi_bound < best[r])] = False
+        if nq:
+            sh = np.uint64(shift)
+            lo_bound = bits_to_value(t_prefix[0::2] << sh, D).astype(np.float64)
+            hi_bound = bits_to_value(((t_prefix[1::2] + np.uint64(1)) << sh) - np.uint64(1), D).astype(np.float64)
+        else:
+            lo_bound = hi_bound = np.zeros(0)
+        best_local = np.full(len(requests), -np.inf)
+        if nq:
+            sel = active & req_runmax[q_req]
+            np.maximum.at(best_local, q_req[sel], lo_bound[sel])
+        best = best_local
+        if comm.size > 1:
+            best = np.max(np.stack(comm.allgather(best_local)), axis=0)
+        if nq:
+            drop = req_runmax[q_req] & (hi_bound < best[q_req])
+            active &= ~drop
 
     # ---- exact neighbours -> numpy's lerp -> per-request reduction
-    vals = bits_to_value(t_prefix, D)
-    local = {}
-    for j in np.flatnonzero(active):
-        r = int(q_req[j])
-        v = float(lerp(vals[2 * j], vals[2 * j + 1], q_gamma[j], D))
-        if requests[r]["mode"] == "running_max":
-            local[r] = max(local.get(r, -np.inf), v)
-        else:
-            local[r] = v
-    merged: dict[int, float] = {}
-    for d in comm.allgather_object(local):
-        for r, v in d.items():
-            merged[r] = max(merged[r], v) if (r in merged and requests[r]["mode"] == "running_max") else v
-    out = []
-    for r, req in enumerate(requests):
-        out.append(merged.get(r) if grand[req["inst"]] > 0 else None)
+    local_val = np.full(len(requests), -np.inf)
+    local_has = np.zeros(len(requests), dtype=bool)
+    if nq and active.any():
+        vals = bits_to_value(t_prefix, D)
+        sel = np.flatnonzero(active)
+        v = lerp_vec(vals[2 * sel], vals[2 * sel + 1], q_gamma[sel], D).astype(np.float64)
+        np.maximum.at(local_val, q_req[sel], v)  # "last" requests hold a single query
+        local_has[q_req[sel]] = True
+    if comm.size > 1:
+        parts = comm.allgather(np.concatenate([local_val, local_has.astype(np.float64)]))
+        stack = np.stack(parts)
+        local_val = stack[:, : len(requests)].max(axis=0)
+        local_has = stack[:, len(requests) :].max(axis=0) > 0
+    out = [float(local_val[r]) if (local_has[r] and grand[requests[r]["inst"]] > 0) else None for r in range(len(requests))]
     return out, counts, npos
 
 

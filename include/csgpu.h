@@ -173,15 +173,21 @@ typedef struct {
   double fill_lo, fill_hi; /* substitutes written into the matrix (already rounded to D)          */
   double t_vmin, t_range;  /* log: log10(vmin), log10(vmax)-log10(vmin); linear: vmin, vmax-vmin  */
   int32_t status;          /* CSG_NORM_*                                                          */
-  int32_t degenerate;      /* 1: vmin == vmax -> every cell maps to index 0                       */
+  int32_t degenerate;      /* 1: vmin == vmax -> every cell maps to index 0; 2: NaN bound -> all "bad" */
 } csg_panel_norm;          /* 56 bytes */
 
 CSG_API int32_t csg_raster_blocks(int32_t ne, int32_t nt);
 
-/* Resolve every panel's normalisation on the device from the region stats. */
+/* bytes of the per-panel threshold table csg_panel_prepare() fills (257 values of dtype D
+ * per panel, padded): value -> index is a monotone step function, so the rasteriser only
+ * counts thresholds <= value; the thresholds themselves come from the direct formula. */
+CSG_API size_t csg_threshold_bytes(int n_panels, int dtype);
+
+/* Resolve every panel's normalisation (and its index thresholds) on the device from the
+ * region stats. */
 CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels,
                       const csg_region* d_regions, const csg_region_stats* d_stats, int dtype,
-                      csg_panel_norm* d_norms);
+                      csg_panel_norm* d_norms, void* d_thresholds);
 
 /* Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
  * under, over, bad).  d_index (uint16, may be NULL) receives Colormap indices 0..255 and
@@ -189,8 +195,8 @@ CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_pan
  * the lowest energy (imshow origin="lower"). */
 CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels,
-                  const csg_panel_norm* d_norms, int n_panels, int total_blocks,
-                  const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index);
+                  const csg_panel_norm* d_norms, const void* d_thresholds, int n_panels,
+                  int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index);
 
 /* ---------------------------------------------- K2b: global extrema (pooled) */
 /* The pooled finite-positive samples of CS/fast/extrema.py:259-267 are never
