@@ -80,6 +80,8 @@ PANEL = np.dtype(
         ("z_min", "<f8"),
         ("z_max", "<f8"),
         ("out_off", "<i8"),
+        ("stat_region", "<i4"),
+        ("reserved", "<i4"),
     ],
     align=True,
 )
@@ -104,7 +106,7 @@ POOL_QUERY = np.dtype(
     align=True,
 )
 assert FILE_DESC.itemsize == 56 and REGION.itemsize == 56 and REGION_STATS.itemsize == 64
-assert PANEL.itemsize == 40 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
+assert PANEL.itemsize == 48 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 

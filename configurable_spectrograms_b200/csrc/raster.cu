@@ -17,7 +17,6 @@
 
 namespace {
 
-constexpr int kTile = 32;
 constexpr int I_UNDER = 256, I_OVER = 257, I_BAD = 258;
 
 template <typename T>
@@ -160,7 +159,7 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_panels) return;
   const csg_panel p = panels[i];
-  const csg_region_stats own = stats[p.region];
+  const csg_region_stats own = stats[p.stat_region >= 0 ? p.stat_region : p.region];
   const csg_region_stats pct = stats[p.pct_region >= 0 ? p.pct_region : p.region];
   // compute_percentile_bounds(matrix, 1, 99, z_min, z_max)   CS/plotting.py:259
   double zmin = is_nan(p.z_min) ? pct.p_lo : p.z_min;
@@ -221,9 +220,16 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   norms[i] = nm;
 }
 
-// One block = one 32x32 (energy x time) tile of one panel.  Cells are read along the energy
-// axis (contiguous in the collapsed (T,E) matrix), coloured, transposed through shared
-// memory and written along the time axis (contiguous in the (E',T') image).
+// One block = one (<=128 energies) x (32 time steps) tile of one panel.  Cells are read along the
+// energy axis (contiguous in the collapsed (T,E) matrix), mapped to their LUT index through the
+// panel's threshold table, transposed through shared memory and written along the time axis
+// (contiguous in the (E',T') image).  Work inside the tile is flattened so no lane idles on
+// the ragged energy count (74 of 96 channels survive the 0-4000 eV mask).
+constexpr int kTileT = 32;
+constexpr int kTileE = 128;
+
+constexpr int kPad = 4;  // sentinels on both sides of the threshold row in shared memory
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
@@ -231,74 +237,100 @@ __global__ void __launch_bounds__(256)
                      const csg_panel_norm* __restrict__ norms, int n_panels, const T* __restrict__ thresholds,
                      const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
                      uint16_t* __restrict__ index) {
-  __shared__ uint32_t s_lut[259];
-  __shared__ T s_thr[kThrPitch];
-  __shared__ uint16_t s_idx[kTile][kTile + 2];
-  __shared__ csg_panel_norm s_nm;
-  __shared__ csg_region s_rg;
-  __shared__ int s_panel;
+  __shared__ uint32_t s_lut[260];
+  __shared__ T s_thr[kThr + 2 * kPad];  // [kPad + k] = thr[k]; -inf below, +inf above
+  __shared__ uint16_t s_idx[kTileE * (kTileT + 2)];
+  __shared__ int s_cols[kTileE];
+  __shared__ int s_rows[kTileT];
 
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    int lo = 0, hi = n_panels - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    s_panel = lo;
-    s_nm = norms[lo];
-    s_rg = regions[panels[lo].region];
+  // ---- which panel owns this block: 256-ary search over first_block, all threads probing
+  int lo = 0, len = n_panels;
+  while (len > 1) {
+    const int chunk = (len + 255) >> 8;
+    const int i = lo + tid * chunk;
+    const bool le = i < lo + len && __ldg(&panels[i].first_block) <= (int)blockIdx.x;
+    const int cnt = __syncthreads_count(le);  // probes are monotone: the first cnt are true
+    const int nlo = lo + (cnt - 1) * chunk;
+    len = min(chunk, lo + len - nlo);
+    lo = nlo;
   }
-  for (int i = tid; i < 259; i += 256) s_lut[i] = lut ? lut[i] : 0u;
-  __syncthreads();
-  for (int i = tid; i < kThr; i += 256) s_thr[i] = thresholds[(size_t)s_panel * kThrPitch + i];
-  __syncthreads();
-  const csg_panel pn = panels[s_panel];
-  const csg_region& rg = s_rg;
-  if (s_nm.status != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
-
-  const int tiles_t = (rg.nt + kTile - 1) / kTile;
-  const int tile = (int)blockIdx.x - pn.first_block;
-  const int e0 = (tile / tiles_t) * kTile, t0 = (tile % tiles_t) * kTile;
-  const int tx = tid & 31, ty = tid >> 5;
+  const int pi = lo;
+  // every thread keeps its own copy of the few scalars it needs (broadcast loads)
+  const csg_panel pn = panels[pi];
+  const csg_region rg = regions[pn.region];
+  const int status = __ldg(&norms[pi].status);
+  const int degenerate = __ldg(&norms[pi].degenerate);
+  if (status != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
+  const T fill_lo = (T)__ldg(&norms[pi].fill_lo), fill_hi = (T)__ldg(&norms[pi].fill_hi);
+  const double t_vmin = __ldg(&norms[pi].t_vmin), t_range = __ldg(&norms[pi].t_range);
   const bool log_scale = pn.log_scale != 0;
 
-  const int e = e0 + tx;
-  const int col = e < rg.ne ? __ldg(pool + rg.cols_off + e) : 0;
-#pragma unroll
-  for (int k = 0; k < kTile; k += 8) {
-    const int tt = t0 + ty + k;
-    int idx = 0;
-    if (e < rg.ne && tt < rg.nt) {
-      const int row = rg.rows_off < 0 ? rg.t0 + tt : __ldg(pool + rg.rows_off + tt);
-      const T v = substitute<T>(__ldg(mats + rg.mat_off + (long long)row * rg.ld + col), s_nm, log_scale);
-      if (s_nm.degenerate == 1) {
-        idx = 0;
-      } else if (s_nm.degenerate == 2 || is_nan(v)) {
-        idx = I_BAD;
-      } else {
-        int n = 0;  // thresholds <= v (upper bound over 257 sorted entries)
-#pragma unroll
-        for (int step = 256; step >= 1; step >>= 1)
-          if (n + step <= kThr && s_thr[n + step - 1] <= v) n += step;
-        idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
-      }
+  const int tiles_t = (rg.nt + kTileT - 1) / kTileT;
+  const int tile = (int)blockIdx.x - pn.first_block;
+  const int e0 = (tile / tiles_t) * kTileE, t0 = (tile % tiles_t) * kTileT;
+  const int ne_t = min(kTileE, rg.ne - e0), nt_t = min(kTileT, rg.nt - t0);
+  for (int i = tid; i < 259; i += 256) s_lut[i] = lut ? lut[i] : 0u;
+  for (int i = tid; i < kThr + 2 * kPad; i += 256) {
+    const int k = i - kPad;
+    s_thr[i] = k < 0 ? (T)(-CUDART_INF) : (k >= kThr ? (T)CUDART_INF : thresholds[(size_t)pi * kThrPitch + k]);
+  }
+  for (int i = tid; i < ne_t; i += 256) s_cols[i] = __ldg(pool + rg.cols_off + e0 + i);
+  for (int i = tid; i < nt_t; i += 256) s_rows[i] = rg.rows_off < 0 ? rg.t0 + t0 + i : __ldg(pool + rg.rows_off + t0 + i);
+  __syncthreads();
+
+  // first guess of n = #{thresholds <= v} from fast float math; verified against the table
+  const float c1 = log_scale ? (float)(256.0 * 0.30102999566398120 / t_range) : (float)(256.0 / t_range);
+  const float c0 = (float)(-256.0 * t_vmin / t_range) + 1.0f;
+
+  const int n_cells = ne_t * nt_t;
+  int tt = tid / ne_t, e = tid - tt * ne_t;
+  const int dt = 256 / ne_t, de = 256 - dt * ne_t;
+  const T* base = mats + rg.mat_off;
+  const int ld = rg.ld;
+  for (int i = tid; i < n_cells; i += 256) {
+    T v = __ldg(base + (long long)s_rows[tt] * ld + s_cols[e]);
+    // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
+    if (log_scale) {
+      v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+    } else {
+      v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
+      v = (v == (T)CUDART_INF) ? fill_hi : v;
     }
-    s_idx[ty + k][tx] = (uint16_t)idx;
+    const float fv = (float)v;
+    float gf = (log_scale ? __log2f(fv) : fv) * c1 + c0;
+    gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
+    int n = (int)gf;
+    // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
+    const T* w = s_thr + (kPad - 2) + n;
+    const T a = w[0], b = w[1], c = w[2], d = w[3];
+    if (a <= v && !(d <= v)) {
+      n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
+    } else {  // rare: the float guess was off by more than one
+#pragma unroll 1
+      while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
+#pragma unroll 1
+      while (n < kThr && s_thr[kPad + n] <= v) ++n;
+    }
+    int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
+    idx = is_nan(v) ? I_BAD : idx;
+    idx = degenerate == 1 ? 0 : (degenerate == 2 ? I_BAD : idx);
+    s_idx[e * (kTileT + 2) + tt] = (uint16_t)idx;
+    e += de, tt += dt;
+    if (e >= ne_t) e -= ne_t, ++tt;
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kTile; k += 8) {
-    const int ee = e0 + ty + k, tt = t0 + tx;
-    if (ee < rg.ne && tt < rg.nt) {
-      const uint16_t idx = s_idx[tx][ty + k];
-      const long long o = pn.out_off + (long long)ee * rg.nt + tt;
-      if (rgba) rgba[o] = s_lut[idx];
-      if (index) index[o] = idx;
-    }
+  // ---- transposed write: consecutive lanes -> consecutive time steps of one energy row
+  int ee = tid / nt_t, t2 = tid - ee * nt_t;
+  const int dee = 256 / nt_t, dt2 = 256 - dee * nt_t;
+  const long long obase = pn.out_off + (long long)e0 * rg.nt + t0;
+  for (int i = tid; i < n_cells; i += 256) {
+    const uint16_t idx = s_idx[ee * (kTileT + 2) + t2];
+    const long long o = obase + (long long)ee * rg.nt + t2;
+    if (rgba) rgba[o] = s_lut[idx];
+    if (index) index[o] = idx;
+    t2 += dt2, ee += dee;
+    if (t2 >= nt_t) t2 -= nt_t, ++ee;
   }
 }
 
@@ -308,7 +340,7 @@ extern "C" {
 
 int32_t csg_raster_blocks(int32_t ne, int32_t nt) {
   if (ne <= 0 || nt <= 0) return 0;
-  return ((ne + kTile - 1) / kTile) * ((nt + kTile - 1) / kTile);
+  return ((ne + kTileE - 1) / kTileE) * ((nt + kTileT - 1) / kTileT);
 }
 
 size_t csg_threshold_bytes(int n_panels, int dtype) {

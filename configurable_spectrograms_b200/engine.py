@@ -227,7 +227,8 @@ class Batch:
         return off
 
     def add_region(self, file: int, group: int, cols, *, t0: int = 0, nt: int | None = None, rows=None,
-                   want_pct: bool = False, p_lo: float = 1.0, p_hi: float = 99.0) -> int:
+                   want_pct: bool | int = False, p_lo: float = 1.0, p_hi: float = 99.0) -> int:
+        """``want_pct``: 0/False reductions only, 1/True + percentiles, 2 geometry only (no stats)."""
         f = self.files[file]
         cols = np.asarray(cols, dtype=np.int32)
         if rows is not None:
@@ -249,12 +250,14 @@ class Batch:
         )
         return len(self._regions) - 1
 
-    def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None) -> int:
+    def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None,
+                  stat_region: int = -1) -> int:
         r = self._regions[region]
         ne, nt = r[6], r[3]
         self._panels.append(
             (region, pct_region, int(bool(log_scale)), self._raster_blocks,
-             np.nan if z_min is None else float(z_min), np.nan if z_max is None else float(z_max), self._pixels)
+             np.nan if z_min is None else float(z_min), np.nan if z_max is None else float(z_max), self._pixels,
+             stat_region, 0)
         )
         self._raster_blocks += self.ctx.lib.csg_raster_blocks(ne, nt)
         self._pixels += ne * nt

@@ -95,6 +95,7 @@ class ShardPlan:
         self._panel_cache: dict = {}
         self._region_cache: dict = {}
         self._cols_cache: dict = {}
+        self._full_stats: dict = {}  # (file, group) -> percentile region over the [0,4000] eV cells, every row
         self._flags_host = None
 
     # ------------------------------------------------------------- phase 1: files
@@ -150,18 +151,20 @@ class ShardPlan:
             else:
                 rid = self.batch.add_region(file, group, cols, rows=rows, want_pct=want_pct)
             self._region_cache[key] = rid
-        elif want_pct:
+        else:
             r = list(self.batch._regions[rid])
-            if not r[7]:
-                r[7] = 1
+            # 2 = geometry only < 0 = reductions < 1 = reductions + percentiles
+            order = {2: 0, 0: 1, 1: 2}
+            if order[int(want_pct)] > order[r[7]]:
+                r[7] = int(want_pct)
                 self.batch._regions[rid] = tuple(r)
         return rid
 
-    def _panel(self, region, pct_region, z_min, z_max):
-        key = (region, pct_region, z_min, z_max)
+    def _panel(self, region, pct_region, z_min, z_max, stat_region=-1):
+        key = (region, pct_region, z_min, z_max, stat_region)
         pid = self._panel_cache.get(key)
         if pid is None:
-            pid = self.batch.add_panel(region, pct_region, self.z_scale == "log", z_min, z_max)
+            pid = self.batch.add_panel(region, pct_region, self.z_scale == "log", z_min, z_max, stat_region)
             self._panel_cache[key] = pid
         return pid
 
@@ -203,15 +206,18 @@ class ShardPlan:
             pct = self._region(file, group, builder_cols, "full", (0, len(meta["times"])), True)
         # make_spectrogram always clips energy to [0, 4000] here: y_axis_min/max are not
         # forwarded by generic_plot_multirow_optional_zoom (plotting.py:618-636 vs :104-105)
-        _, cols = self._energy_cols(file, 0, 4000)
+        plain, cols = self._energy_cols(file, 0, 4000)
+        if pct >= 0 and builder_cols is plain:
+            self._full_stats[(file, group)] = pct  # same cell set as the full panel (stats are order-free)
         row = RowSpec(label=label, file=file, group=group, full_panel=None, zoom_panel=None,
                       times=meta["times"], energy=meta["energy"])
         if len(cols):
             rk, rows = self._rows_full(file)
             n_rows = rows[1] if isinstance(rows, tuple) else len(rows)
             if n_rows:
-                reg = self._region(file, group, cols, rk, rows, False)
-                row.full_panel = self._panel(reg, pct, z_lo, z_hi)
+                shared = self._full_stats.get((file, group), -1) if isinstance(rows, tuple) else -1
+                reg = self._region(file, group, cols, rk, rows, 2 if shared >= 0 else 0)
+                row.full_panel = self._panel(reg, pct, z_lo, z_hi, shared)
             if zoom is not None:
                 rk, rows = self._rows_zoom(file, zoom)
                 if len(rows):

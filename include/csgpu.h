@@ -134,7 +134,7 @@ typedef struct {
   int32_t rows_off; /* -1: contiguous rows [t0, t0+nt)                             */
   int32_t cols_off;
   int32_t ne;
-  int32_t want_pct; /* 0: min/max/counts only                                      */
+  int32_t want_pct; /* 0: reductions only, 1: reductions + percentiles, 2: geometry only (no stats) */
   int32_t reserved;
   double p_lo, p_hi; /* percentiles (0..100), e.g. 1 and 99                         */
 } csg_region;        /* 56 bytes */
@@ -155,13 +155,16 @@ CSG_API int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype, co
 /* ------------------------------------------------------ K3: norm + colormap */
 /* One imshow panel (CS/plotting.py:276-287 log, :308-324 linear). */
 typedef struct {
-  int32_t region;     /* cells to draw; its stats give safe_vmin and the linear fallback  */
-  int32_t pct_region; /* stats entry whose p_lo/p_hi stand in for z bounds that are NaN   */
-  int32_t log_scale;  /* 1: LogNorm branch, 0: linear branch                              */
-  int32_t first_block; /* exclusive prefix sum of csg_raster_blocks(ne, nt)               */
-  double z_min, z_max; /* explicit bounds (reference z_axis_min / z_axis_max); NaN = None */
-  int64_t out_off;     /* pixel offset of this panel in d_rgba / d_index (ne rows x nt)   */
-} csg_panel;           /* 40 bytes */
+  int32_t region;      /* cells to draw (geometry)                                         */
+  int32_t pct_region;  /* stats entry whose p_lo/p_hi stand in for z bounds that are NaN   */
+  int32_t log_scale;   /* 1: LogNorm branch, 0: linear branch                              */
+  int32_t first_block; /* exclusive prefix sum of csg_raster_blocks(ne, nt)                */
+  double z_min, z_max; /* explicit bounds (reference z_axis_min / z_axis_max); NaN = None  */
+  int64_t out_off;     /* pixel offset of this panel in d_rgba / d_index (ne rows x nt)    */
+  int32_t stat_region; /* stats entry giving safe_vmin / the linear fallback: a region with
+                          the same cell SET as `region` (order-independent), or -1 = region */
+  int32_t reserved;
+} csg_panel;           /* 48 bytes */
 
 enum {
   CSG_NORM_OK = 0,
