@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=4)
+    ap.add_argument("--profile-host", default=None, help="write a cProfile of the timed step loop to this path")
     return ap.parse_args()
 
 
@@ -221,8 +222,8 @@ def main():
     import torch
 
     from configurable_spectrograms_b200 import _lib
-    from configurable_spectrograms_b200.fast.extrema import _extrema_overrides, extrema_from_shard
-    from configurable_spectrograms_b200.fast.pipeline import ShardPlan
+    from configurable_spectrograms_b200.fast.extrema import extrema_enqueue, extrema_finish
+    from configurable_spectrograms_b200.fast.pipeline import BatchStep, ShardPlan
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,8 +246,10 @@ def main():
     files, orbits, total_elems = orbit_layout(n_local, first, args.seed)
     cubes = generate_cubes(torch, files, total_elems, dev)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = _lib.Context(local, stream=stream)
+    # one explicit stream for everything: libcsgpu kernels, torch events and the NCCL exchanges
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    ctx = _lib.Context(local, stream=tstream.cuda_stream)
     lut = turbo_like_lut()
 
     # global ascending orbit sequence (every rank knows every orbit number; files all present)
@@ -264,45 +267,16 @@ def main():
             shard.add_orbit(ob["orbit"], dsets, ob["lines"])
         return shard
 
-    def plan_figures(shard, state):
-        """Both submissions of every orbit (extrema=None, extrema=state); identical panels are shared."""
-        shard.fetch_flags()
-        for ob in shard.orbits:
-            for ge in (None, state):
-                for inst in ORDER:
-                    if inst not in ob["files"]:
-                        continue
-                    ov = _extrema_overrides(ge, inst, "linear", "log")
-                    shard.plan_pitch_angle_grid(ob, inst, "given", *ov)
-                    shard.plan_pitch_angle_grid(ob, inst, "raw")
-                shard.plan_instrument_grid(ob, "given", global_extrema=ge)
-                shard.plan_instrument_grid(ob, "raw", global_extrema=None)
-        shard.upload_tables()
-        shard.batch.set_lut(lut)
-
-    def device_stages(shard, timers=True):
-        if timers:
-            ctx.timer_start(0)
-        shard.collapse()
-        if timers:
-            ctx.timer_stop(0)
-        state = extrema_from_shard(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm)
-        if shard.batch.n_panels == 0:
-            plan_figures(shard, state)
-        if timers:
-            ctx.timer_start(1)
-        shard.run_panels(None, want_index=False)
-        if timers:
-            ctx.timer_stop(1)
-        return state
-
     # ------------------------------------------------------------ device-resident arm
     shard = build_shard(cubes.data_ptr())
-    state0 = device_stages(shard, timers=False)  # plans the panels on the first pass
-    ctx.sync()
+    step = BatchStep(shard, sequence, max_percentile=99.0, comm=comm, lut259=lut, want_index=False)
+    t_plan = time.perf_counter()
+    state0 = step.run({})  # plans the panels on the first pass
+    step.finish()
+    t_plan = time.perf_counter() - t_plan
     for _ in range(args.warmup):
-        device_stages(shard)
-    ctx.sync()
+        step.run({})
+    step.finish()
 
     def barrier():
         if world > 1:
@@ -315,24 +289,55 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    collapse_ms, panel_ms = [], []
-    ev0.record()
+    host_t0 = time.perf_counter()
+    prof = None
+    if args.profile_host:
+        import cProfile
+
+        prof = cProfile.Profile()
+        prof.enable()
+    ev0.record(tstream)
     for _ in range(args.steps):
-        state = device_stages(shard)
-        collapse_ms.append(None)
-    ev1.record()
+        state = step.run({})
+    ev1.record(tstream)
+    if prof is not None:
+        prof.disable()
+        import io
+        import pstats
+
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        open(args.profile_host, "w").write(buf.getvalue())
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
+    step.finish()
     barrier()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
-    # per-stage timers hold the last step; re-measure collapse alone for the roofline average
-    k1 = []
-    for _ in range(max(args.steps, 3)):
-        ctx.timer_start(0)
-        shard.collapse()
-        ctx.timer_stop(0)
-        k1.append(ctx.timer_ms(0))
     assert state == state0, "extrema changed between steps"
+    # per-kernel stage times (separate passes, CUDA events on the same stream)
+    def timed(fn, n=max(args.steps, 3)):
+        out = []
+        for _ in range(n):
+            ctx.timer_start(0)
+            fn()
+            ctx.timer_stop(0)
+            out.append(ctx.timer_ms(0))
+        return float(np.mean(out))
+
+    k1_ms = timed(shard.collapse)
+    stats_ms = timed(shard.batch.run_stats)
+    prep_ms = timed(shard.batch.prepare)
+    raster_ms = timed(lambda: shard.batch.rasterise(want_rgba=True, want_index=False))
+
+    pool = []
+    for _ in range(max(args.steps, 3)):  # device time of the K2b launches alone (host bookkeeping excluded)
+        ctx.timer_start(0)
+        pending = extrema_enqueue(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm)
+        ctx.timer_stop(0)
+        extrema_finish(pending)
+        pool.append(ctx.timer_ms(0))
+    pool_ms = float(np.mean(pool))
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -342,7 +347,6 @@ def main():
 
     cube_bytes = 4 * total_elems
     sums_bytes = sum(5 * f["T"] * E * 4 for f in files)
-    k1_ms = float(np.mean(k1))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -363,9 +367,9 @@ def main():
 
         def e2e_step():
             cubes.copy_(host, non_blocking=True)  # H2D of this step's inputs (pinned -> HBM)
-            device_stages(shard, timers=False)
+            step.run({})
             ctx._check(ctx.lib.csg_d2h(ctx.handle, rgba_host.data_ptr(), shard.batch.d_rgba.ptr, n_px * 4))
-            ctx.sync()
+            step.finish()
 
         e2e_step()
         barrier()
@@ -406,7 +410,8 @@ def main():
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
-            "stage_ms": {"collapse": k1_ms, "panels_last": ctx.timer_ms(1)},
+            "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
+                         "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3},
         }
         print(json.dumps(line))
     if world > 1:

@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
+ABI_VERSION = 2
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 MAX_GROUPS = 7
@@ -82,6 +83,8 @@ PANEL = np.dtype(
         ("out_off", "<i8"),
         ("stat_region", "<i4"),
         ("reserved", "<i4"),
+        ("zmin_slot", "<i4"),
+        ("zmax_slot", "<i4"),
     ],
     align=True,
 )
@@ -105,8 +108,19 @@ POOL_QUERY = np.dtype(
     [("inst", "<i4"), ("pos", "<i4"), ("slot", "<i4"), ("bin", "<i4"), ("rank", "<i8"), ("row_total", "<i8")],
     align=True,
 )
+FLAG_WINDOW = np.dtype(
+    [("flags_off", "<i8"), ("t0", "<i4"), ("nt", "<i4"), ("rows_off", "<i4"), ("bit", "<i4")], align=True
+)
+assert FLAG_WINDOW.itemsize == 24
+POOL_REQUEST = np.dtype([("inst", "<i4"), ("mode", "<i4"), ("p", "<f8")], align=True)
+POOL_SEL = np.dtype(
+    [("inst", "<i4"), ("pos", "<i4"), ("req", "<i4"), ("active", "<i4"), ("slot", "<i4", (2,)), ("rank", "<i8", (2,)),
+     ("prefix", "<u8", (2,)), ("gamma", "<f8")],
+    align=True,
+)
+assert POOL_REQUEST.itemsize == 16 and POOL_SEL.itemsize == 64
 assert FILE_DESC.itemsize == 56 and REGION.itemsize == 56 and REGION_STATS.itemsize == 64
-assert PANEL.itemsize == 48 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
+assert PANEL.itemsize == 56 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
@@ -132,18 +146,29 @@ SIGNATURES = {
     "csg_timer_stop": (_i, [_vp, _i]),
     "csg_timer_ms": (_i, [_vp, _i, C.POINTER(C.c_float)]),
     "csg_launch_count": (_i64, [_vp]),
+    "csg_event_record": (_i, [_vp, _i]),
+    "csg_event_sync": (_i, [_vp, _i]),
     "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i]),
     "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "csg_window_any": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_threshold_bytes": (_sz, [_i, _i]),
-    "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "csg_pool_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),
+    "csg_pool_row_totals": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "csg_pool_sel_init": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "csg_pool_sel_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "csg_pool_sel_bounds": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "csg_pool_sel_slots": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "csg_pool_sel_assign": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "csg_pool_sel_finish": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "csg_pool_base": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp]),
 }
 
 _lib = None
@@ -165,8 +190,8 @@ def load_library(path: str | None = None):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.csg_abi_version() != 1:
-        raise CsgError(f"libcsgpu ABI version {lib.csg_abi_version()} != 1")
+    if lib.csg_abi_version() != ABI_VERSION:
+        raise CsgError(f"libcsgpu ABI version {lib.csg_abi_version()} != {ABI_VERSION}: rebuild the library")
     if path is None:
         _lib = lib
     return lib
@@ -258,6 +283,7 @@ class Context:
         self.handle = None
         if self.lib.csg_device_count() <= 0:
             raise CsgError("no CUDA device available: libcsgpu has no CPU fallback")
+        # stream: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream); None/0 = own stream
         h = self.lib.csg_create(int(device), _vp(stream) if stream else None)
         if not h:
             raise CsgError(self.lib.csg_last_error(None).decode())
@@ -271,8 +297,11 @@ class Context:
             raise CsgError(self.lib.csg_last_error(self.handle).decode())
 
     def _keep(self, obj):
-        """Hold a host array until the next sync (async H2D source)."""
+        """Hold a host array until the next sync (async H2D source).  Pageable sources are staged
+        before cudaMemcpyAsync returns, so the list only has to bridge the call itself."""
         self._alive.append(obj)
+        if len(self._alive) > 1024:
+            del self._alive[:512]
 
     def sync(self):
         self._check(self.lib.csg_sync(self.handle))
@@ -309,6 +338,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.csg_launch_count(self.handle))
+
+    def event_record(self, slot: int):
+        self._check(self.lib.csg_event_record(self.handle, slot))
+
+    def event_sync(self, slot: int):
+        self._check(self.lib.csg_event_sync(self.handle, slot))
 
     def timer_start(self, slot: int):
         self._check(self.lib.csg_timer_start(self.handle, slot))

@@ -37,3 +37,24 @@ class TorchComm:
 
     def barrier(self):
         self.dist.barrier()
+
+    # ---- device-pointer collectives (NCCL): the payload never leaves HBM, nothing blocks the host
+    def _tensor(self, ptr: int, nbytes: int):
+        key = (ptr, nbytes)
+        cache = self.__dict__.setdefault("_tensors", {})
+        t = cache.get(key)
+        if t is None:
+            holder = type("CudaPtr", (), {})()
+            holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            t = cache[key] = self.torch.as_tensor(holder, device=self.device)
+        return t
+
+    def allgather_dev(self, src_ptr: int, dst_ptr: int, nbytes: int):
+        """dst[rank][nbytes] <- every rank's src[nbytes] (enqueued behind the current stream's work)."""
+        self.dist.all_gather_into_tensor(self._tensor(dst_ptr, nbytes * self.size), self._tensor(src_ptr, nbytes))
+
+    def allreduce_max_dev(self, ptr: int, count: int, kind: str):
+        torch = self.torch
+        dt = {"i8": torch.int64, "f8": torch.float64, "i4": torch.int32}[kind]
+        t = self._tensor(ptr, count * dt.itemsize).view(dt)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)

@@ -304,6 +304,22 @@ __global__ void collapse_tep_kernel(const csg_file_desc* __restrict__ files, int
   }
 }
 
+// warp = one zoom window: any row with the group's bit set?
+__global__ void window_any_kernel(const uint8_t* __restrict__ row_flags, const csg_flag_window* __restrict__ windows,
+                                  int n_windows, const int32_t* __restrict__ pool, uint8_t* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_windows) return;
+  const csg_flag_window win = windows[w];
+  const uint8_t* fl = row_flags + win.flags_off;
+  bool any = false;
+  for (int i = lane; i < win.nt; i += 32) {
+    const int row = win.rows_off < 0 ? win.t0 + i : __ldg(pool + win.rows_off + i);
+    any |= ((fl[row] >> win.bit) & 1u) != 0;
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) out[w] = any ? 1 : 0;
+}
+
 inline int tep_rows_per_block(int P, int dtype) {
   const size_t es = dtype == CSG_F64 ? 8 : 4;
   int rows = 256;
@@ -384,6 +400,17 @@ int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int to
   if (dtype == CSG_F32)
     return launch_tep<float>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (float*)d_sums, d_row_flags);
   return launch_tep<double>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (double*)d_sums, d_row_flags);
+}
+
+int csg_window_any(csg_ctx* ctx, const uint8_t* d_row_flags, const csg_flag_window* d_windows, int n_windows,
+                   const int32_t* d_index_pool, uint8_t* d_out) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_windows <= 0) return CSG_OK;
+  if (!d_row_flags || !d_windows || !d_out) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  const int blocks = (n_windows * 32 + 255) / 256;
+  window_any_kernel<<<blocks, 256, 0, ctx->stream>>>(d_row_flags, d_windows, n_windows, d_index_pool, d_out);
+  CSG_LAUNCH_CHECK(ctx, "window_any_kernel");
+  return CSG_OK;
 }
 
 int csg_collapse_host(csg_ctx* ctx, const void* h_cube, int32_t T, int32_t P, int32_t E, int dtype, int layout,

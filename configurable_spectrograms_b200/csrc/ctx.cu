@@ -65,6 +65,7 @@ csg_ctx* csg_create(int device, void* external_stream) {
   for (int i = 0; i < 32; ++i) {
     cudaEventCreate(&ctx->ev_start[i]);
     cudaEventCreate(&ctx->ev_stop[i]);
+    cudaEventCreateWithFlags(&ctx->ev_user[i], cudaEventDisableTiming);
   }
   return ctx;
 }
@@ -76,6 +77,7 @@ void csg_destroy(csg_ctx* ctx) {
   for (int i = 0; i < 32; ++i) {
     cudaEventDestroy(ctx->ev_start[i]);
     cudaEventDestroy(ctx->ev_stop[i]);
+    cudaEventDestroy(ctx->ev_user[i]);
   }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
@@ -167,5 +169,16 @@ int csg_timer_ms(csg_ctx* ctx, int slot, float* ms) {
   return CSG_OK;
 }
 int64_t csg_launch_count(csg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int csg_event_record(csg_ctx* ctx, int slot) {
+  if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "event slot %d out of range", slot);
+  CSG_CUDA(ctx, cudaEventRecord(ctx->ev_user[slot], ctx->stream));
+  return CSG_OK;
+}
+int csg_event_sync(csg_ctx* ctx, int slot) {
+  if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "event slot %d out of range", slot);
+  CSG_CUDA(ctx, cudaEventSynchronize(ctx->ev_user[slot]));
+  return CSG_OK;
+}
 
 }  // extern "C"

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(288)
 
 template <typename T>
 __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n_panels,
-                                     const csg_region_stats* __restrict__ stats,
+                                     const csg_region_stats* __restrict__ stats, const double* __restrict__ zvals,
                                      csg_panel_norm* __restrict__ norms) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_panels) return;
@@ -162,8 +162,10 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   const csg_region_stats own = stats[p.stat_region >= 0 ? p.stat_region : p.region];
   const csg_region_stats pct = stats[p.pct_region >= 0 ? p.pct_region : p.region];
   // compute_percentile_bounds(matrix, 1, 99, z_min, z_max)   CS/plotting.py:259
-  double zmin = is_nan(p.z_min) ? pct.p_lo : p.z_min;
-  double zmax = is_nan(p.z_max) ? pct.p_hi : p.z_max;
+  const double given_lo = (p.zmin_slot >= 0 && zvals) ? zvals[p.zmin_slot] : p.z_min;
+  const double given_hi = (p.zmax_slot >= 0 && zvals) ? zvals[p.zmax_slot] : p.z_max;
+  double zmin = is_nan(given_lo) ? pct.p_lo : given_lo;
+  double zmax = is_nan(given_hi) ? pct.p_hi : given_hi;
   csg_panel_norm nm;
   nm.status = CSG_NORM_OK;
   nm.degenerate = 0;
@@ -348,18 +350,19 @@ size_t csg_threshold_bytes(int n_panels, int dtype) {
 }
 
 int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels, const csg_region* d_regions,
-                      const csg_region_stats* d_stats, int dtype, csg_panel_norm* d_norms, void* d_thresholds) {
+                      const csg_region_stats* d_stats, int dtype, const double* d_zvals, csg_panel_norm* d_norms,
+                      void* d_thresholds) {
   (void)d_regions;
   if (!ctx) return CSG_ERR_ARG;
   if (n_panels <= 0) return CSG_OK;
   if (!d_panels || !d_stats || !d_norms || !d_thresholds) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   const int blocks = (n_panels + 127) / 128;
   if (dtype == CSG_F32) {
-    panel_prepare_kernel<float><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
+    panel_prepare_kernel<float><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_zvals, d_norms);
     CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
     panel_threshold_kernel<float><<<n_panels, 288, 0, ctx->stream>>>(d_panels, d_norms, n_panels, (float*)d_thresholds);
   } else if (dtype == CSG_F64) {
-    panel_prepare_kernel<double><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_norms);
+    panel_prepare_kernel<double><<<blocks, 128, 0, ctx->stream>>>(d_panels, n_panels, d_stats, d_zvals, d_norms);
     CSG_LAUNCH_CHECK(ctx, "panel_prepare_kernel");
     panel_threshold_kernel<double><<<n_panels, 288, 0, ctx->stream>>>(d_panels, d_norms, n_panels, (double*)d_thresholds);
   } else {

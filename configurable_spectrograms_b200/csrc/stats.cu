@@ -35,39 +35,6 @@ __device__ __forceinline__ void hist_add_private(unsigned* wh, unsigned bin, boo
   __syncwarp();
 }
 
-// numpy _get_indexes/_get_gamma for one percentile over n valid samples, arithmetic in T
-template <typename T>
-__device__ void percentile_ranks(long long n, double p, long long& lo, long long& hi, T& gamma) {
-  const T q = div_rn((T)p, (T)100);
-  const T nm1 = (T)(n - 1);
-  const T v = mul_rn(nm1, q);
-  if (v >= nm1) {  // above bounds: both neighbours are the last element
-    lo = hi = n - 1;
-    gamma = T(0);
-  } else if (v < T(0)) {
-    lo = hi = 0;
-    gamma = T(0);
-  } else if (is_nan(v)) {
-    lo = hi = n - 1;
-    gamma = T(0);
-  } else {
-    const T fl = floor(v);
-    lo = (long long)fl;
-    if (lo > n - 1) lo = n - 1;
-    hi = lo + 1;
-    if (hi > n - 1) hi = n - 1;
-    gamma = sub_rn(v, fl);
-  }
-}
-
-template <typename T>
-__device__ T numpy_lerp(T a, T b, T g) {
-  const T d = sub_rn(b, a);
-  T r = add_rn(a, mul_rn(d, g));
-  if (g >= T(0.5)) r = sub_rn(b, mul_rn(d, sub_rn(T(1), g)));
-  return r;
-}
-
 template <typename T, bool HEAVY>
 __global__ void __launch_bounds__(kThreads)
     region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,

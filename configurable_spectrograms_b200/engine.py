@@ -22,6 +22,7 @@ import numpy as np
 from . import _lib
 from ._lib import (
     FILE_DESC,
+    FLAG_WINDOW,
     PANEL,
     PANEL_NORM,
     REGION,
@@ -54,6 +55,31 @@ def classify_cube(cube: np.ndarray):
     if stored.flags.c_contiguous:
         return stored, _lib.LAYOUT_TEP, (T, P, E)
     return np.ascontiguousarray(cube), _lib.LAYOUT_TPE, (T, P, E)
+
+
+class ZSlot(float):
+    """A z bound that lives in the batch's device table ``d_zvals`` instead of in the panel.
+
+    Behaves like the float it currently holds; panels built from it reference ``slot``, so the
+    bound can change every step (global extrema of this step) without re-planning the panels.
+    Two slots never compare equal, even when they hold the same value right now.
+    """
+
+    __slots__ = ("slot",)
+
+    def __new__(cls, value, slot: int):
+        obj = super().__new__(cls, np.nan if value is None else value)
+        obj.slot = int(slot)
+        return obj
+
+    def __eq__(self, other):
+        return isinstance(other, ZSlot) and other.slot == self.slot
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash(("ZSlot", self.slot))
 
 
 class Batch:
@@ -93,6 +119,12 @@ class Batch:
         self.d_index: DevBuf | None = None
         self.d_lut: DevBuf | None = None
         self.d_thr: DevBuf | None = None
+        self.d_zvals: DevBuf | None = None
+        self._windows: list[tuple] = []
+        self.d_windows: DevBuf | None = None
+        self.d_window_any: DevBuf | None = None
+        self._zvals: list[float] = []
+        self._zvals_dirty = False
         self._raster_blocks = 0
         self._tables_dirty = True
 
@@ -226,6 +258,14 @@ class Batch:
             self._pool_cache[key] = off
         return off
 
+    def reset_tables(self):
+        """Forget every region / panel / window / z slot (the cubes and their sums stay)."""
+        self._regions, self._panels, self._pool, self._windows, self._zvals = [], [], [], [], []
+        self._pool_len, self._pool_cache = 0, {}
+        self._raster_blocks = self._pixels = 0
+        self._zvals_dirty = False
+        self.d_regions = self.d_panels = self.d_windows = self.d_window_any = None
+
     def add_region(self, file: int, group: int, cols, *, t0: int = 0, nt: int | None = None, rows=None,
                    want_pct: bool | int = False, p_lo: float = 1.0, p_hi: float = 99.0) -> int:
         """``want_pct``: 0/False reductions only, 1/True + percentiles, 2 geometry only (no stats)."""
@@ -250,6 +290,44 @@ class Batch:
         )
         return len(self._regions) - 1
 
+    def zslot(self, value=None) -> ZSlot:
+        """A new slot of the per-step z-bound table (``None`` = not given -> percentile bound)."""
+        self._zvals.append(np.nan if value is None else float(value))
+        self._zvals_dirty = True
+        return ZSlot(value, len(self._zvals) - 1)
+
+    def set_zslot(self, slot: int, value):
+        value = np.nan if value is None else float(value)
+        old = self._zvals[slot]
+        if not (old == value or (old != old and value != value)):
+            self._zvals[slot] = value
+            self._zvals_dirty = True
+
+    def add_window(self, file: int, bit: int, rows) -> int:
+        """A zoom window over the K1 row flags: ``rows`` = (t0, nt) or an index array."""
+        f = self.files[file]
+        if isinstance(rows, tuple):
+            t0, nt, rows_off = int(rows[0]), int(rows[1]), -1
+        else:
+            rows = np.asarray(rows, dtype=np.int32)
+            if len(rows) and np.array_equal(rows, np.arange(rows[0], rows[0] + len(rows), dtype=np.int32)):
+                t0, nt, rows_off = int(rows[0]), len(rows), -1
+            else:
+                t0, nt, rows_off = 0, len(rows), (self._pool_add(rows) if len(rows) else -1)
+        self._windows.append((f["flags_off"], t0, nt, rows_off, int(bit)))
+        return len(self._windows) - 1
+
+    def run_windows(self):
+        """d_window_any[w] = any row of window w holds a non-NaN cell of its group (K1 flags)."""
+        if not self._windows:
+            return
+        self.ctx._check(
+            self.ctx.lib.csg_window_any(
+                self.ctx.handle, self.d_flags.ptr, self.d_windows.ptr, len(self._windows), self.d_pool.ptr,
+                self.d_window_any.ptr,
+            )
+        )
+
     def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None,
                   stat_region: int = -1) -> int:
         r = self._regions[region]
@@ -257,7 +335,7 @@ class Batch:
         self._panels.append(
             (region, pct_region, int(bool(log_scale)), self._raster_blocks,
              np.nan if z_min is None else float(z_min), np.nan if z_max is None else float(z_max), self._pixels,
-             stat_region, 0)
+             stat_region, 0, z_min.slot if isinstance(z_min, ZSlot) else -1, z_max.slot if isinstance(z_max, ZSlot) else -1)
         )
         self._raster_blocks += self.ctx.lib.csg_raster_blocks(ne, nt)
         self._pixels += ne * nt
@@ -274,6 +352,9 @@ class Batch:
         pool = np.concatenate(self._pool) if self._pool else np.zeros(1, np.int32)
         self.d_pool = self.ctx.to_device(pool)
         self.d_stats = self.ctx.alloc(max(len(regions), 1) * REGION_STATS.itemsize)
+        if self._windows:
+            self.d_windows = self.ctx.to_device(np.array(self._windows, dtype=FLAG_WINDOW))
+            self.d_window_any = self.ctx.alloc(len(self._windows))
         self.upload_panels()
 
     def upload_panels(self):
@@ -313,10 +394,16 @@ class Batch:
         """Resolve every panel's normalisation on the device."""
         if not self._panels:
             return
+        if self._zvals and (self._zvals_dirty or self.d_zvals is None):
+            vals = np.asarray(self._zvals, dtype=np.float64)
+            if self.d_zvals is None or self.d_zvals.nbytes < vals.nbytes:
+                self.d_zvals = self.ctx.alloc(max(vals.nbytes * 2, 256))
+            self.d_zvals.upload(vals)
+            self._zvals_dirty = False
         self.ctx._check(
             self.ctx.lib.csg_panel_prepare(
                 self.ctx.handle, self.d_panels.ptr, len(self._panels), self.d_regions.ptr, self.d_stats.ptr,
-                self.code, self.d_norms.ptr, self.d_thr.ptr,
+                self.code, self.d_zvals.ptr if self.d_zvals is not None else None, self.d_norms.ptr, self.d_thr.ptr,
             )
         )
 

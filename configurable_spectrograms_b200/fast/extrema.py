@@ -156,35 +156,73 @@ def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
     return [float(keys[first[k]]) if total[k] > 0 else 0.0 for k in range(n)]
 
 
-def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
-                       max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None,
-                       on_step_done=None):
-    """Update ``state`` from an already collapsed :class:`pipeline.ShardPlan`.
+def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
+                    max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None):
+    """Enqueue the pooled-extrema selection (K2b) for an already collapsed :class:`pipeline.ShardPlan`.
+
+    Everything runs asynchronously on the context's stream (``pool_select.DevicePoolSelector``);
+    the returned token is redeemed by :func:`extrema_finish`, so the caller can enqueue more GPU
+    work (K2a) in between and hide the host bookkeeping behind it.
 
     ``sequence[k] = (orbit, {inst: True})`` must list the GLOBAL ascending orbit sequence
     (all ranks); ``shard.orbits`` holds this rank's contiguous slice starting at
     ``shard.first_orbit_index``.
     """
-    from ..pool_select import GpuPoolBackend, SingleRank, prefix_percentiles
+    from ..pool_select import DevicePoolSelector, SingleRank
 
     comm = comm or SingleRank()
     instrument_order = tuple(instrument_order)
-    steps, totals = plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
     first = getattr(shard, "first_orbit_index", 0)
-    local_steps = {
-        inst: [oi - first for oi in steps[inst] if first <= oi < first + len(shard.orbits)] for inst in instrument_order
-    }
-    items, inst_len, owners = shard.pool_items(local_steps)
+    # which steps reach the scan depends only on the orbit sequence and the cache state: plan once
+    cache = shard.__dict__.setdefault("_extrema_plan_cache", {})
+    key = (id(sequence), len(sequence), instrument_order, y_scale, z_scale, json.dumps(state, sort_keys=True, default=str),
+           log_floor_cutoff, log_floor_value, first, len(shard.orbits))
+    hit = cache.get(key)
+    if hit is None:
+        steps, totals = plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff,
+                                           log_floor_value)
+        local_steps = {
+            inst: [oi - first for oi in steps[inst] if first <= oi < first + len(shard.orbits)]
+            for inst in instrument_order
+        }
+        if len(cache) > 8:
+            cache.clear()
+        hit = cache[key] = (sequence, steps, totals, *shard.pool_items(local_steps))  # holds `sequence`: id stays unique
+    _, steps, totals, items, inst_len, owners = hit
     requests = [{"inst": ii, "p": max_percentile, "mode": "running_max"} for ii in range(len(instrument_order))]
     if compute_mins:
         requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
     max_E = max((shard.batch.files[f]["E"] for _, _, f in owners), default=1)
-    backend = getattr(shard, "_pool_backend", None)
-    if backend is None:
-        backend = shard._pool_backend = GpuPoolBackend(shard.batch)  # persistent scratch across steps
-    values, counts, npos = prefix_percentiles(
-        backend, shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm
-    )
+    selector = getattr(shard, "_pool_selector", None)
+    if selector is None:
+        selector = shard._pool_selector = DevicePoolSelector(shard.batch)  # persistent scratch across steps
+    selector.enqueue(shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm)
+    return {
+        "shard": shard, "sequence": sequence, "instrument_order": instrument_order, "y_scale": y_scale, "z_scale": z_scale,
+        "state": state, "compute_mins": compute_mins, "log_floor_cutoff": log_floor_cutoff,
+        "log_floor_value": log_floor_value, "comm": comm, "steps": steps, "totals": totals, "first": first,
+        "items": items, "inst_len": inst_len, "owners": owners, "requests": requests, "max_E": max_E, "selector": selector,
+    }
+
+
+def extrema_finish(pending, on_step_done=None):
+    """Wait for the selection's read-back and run the reference's bookkeeping walk on the results."""
+    from ..pool_select import GpuPoolBackend, prefix_percentiles
+
+    shard, comm = pending["shard"], pending["comm"]
+    instrument_order, steps, first = pending["instrument_order"], pending["steps"], pending["first"]
+    owners, requests, compute_mins = pending["owners"], pending["requests"], pending["compute_mins"]
+    values, counts, npos = pending["selector"].result()
+    if values is None:
+        # more distinct candidate buckets survived than the device table holds: same kernels,
+        # digit loop driven from the host (arbitrary candidate counts)
+        backend = getattr(shard, "_pool_backend", None)
+        if backend is None:
+            backend = shard._pool_backend = GpuPoolBackend(shard.batch)
+        values, counts, npos = prefix_percentiles(
+            backend, shard.batch.dtype, pending["items"], len(instrument_order), pending["inst_len"], pending["max_E"],
+            requests, comm=comm,
+        )
     # ---- per-step energy candidates need every rank's per-file counts in sequence order
     local_rows = {}
     for row, (inst, oi, file) in enumerate(owners):
@@ -212,8 +250,18 @@ def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, stat
             z_min = float(zm) if zm is not None else 0
         return cand_e.get((inst, orbit_index), 0.0), (float(z) if z is not None else 0.0), z_min
 
-    return _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor_cutoff, log_floor_value,
-                 scan, on_step_done)
+    return _walk(pending["sequence"], instrument_order, pending["y_scale"], pending["z_scale"], pending["state"],
+                 pending["totals"], pending["log_floor_cutoff"], pending["log_floor_value"], scan, on_step_done)
+
+
+def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
+                       max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None,
+                       on_step_done=None):
+    """Update ``state`` from an already collapsed :class:`pipeline.ShardPlan` (enqueue + finish)."""
+    pending = extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, compute_mins=compute_mins,
+                              max_percentile=max_percentile, log_floor_cutoff=log_floor_cutoff,
+                              log_floor_value=log_floor_value, comm=comm)
+    return extrema_finish(pending, on_step_done)
 
 
 def compute_global_extrema(

@@ -73,7 +73,8 @@ class FigureSpec:
     rows: list[RowSpec] = field(default_factory=list)
     vertical_lines: list[float] | None = None
     zoom: tuple[float, float] | None = None
-    zoom_needed: bool = False
+    zoom_needed: bool = False  # filled per step from the K1 row flags (resolve_zoom_flags)
+    zoom_windows: list[int] = field(default_factory=list)
     error: str | None = None
 
 
@@ -97,6 +98,7 @@ class ShardPlan:
         self._cols_cache: dict = {}
         self._full_stats: dict = {}  # (file, group) -> percentile region over the [0,4000] eV cells, every row
         self._flags_host = None
+        self._window_cache: dict = {}
 
     # ------------------------------------------------------------- phase 1: files
     def add_orbit(self, orbit: int, datasets: dict, lines: dict | None = None):
@@ -185,14 +187,36 @@ class ShardPlan:
             m = (t >= center - half) & (t <= center + half)  # plotting.py:204-210
         return ("zoom", float(center), float(duration)), np.flatnonzero(m)
 
-    def _window_has_data(self, file, group_bit, zoom):
-        """``np.any(~np.isnan(d[mask_zoom]))`` from the K1 row flags (``plotting.py:597-603``)."""
-        t = self.file_meta[file]["times"]
-        center, duration = zoom
-        with np.errstate(invalid="ignore"):
-            m = (t >= center - duration / 2) & (t <= center + duration / 2)
-        fl = self.batch.flags(file, self._flags_host)
-        return bool(np.any((fl[m] >> group_bit) & 1))
+    def _zoom_window(self, file, group_bit, zoom) -> int:
+        """Window id for ``np.any(~np.isnan(d[mask_zoom]))`` (``plotting.py:597-603``), answered on
+        the device from the K1 row flags (``csg_window_any``)."""
+        key = (file, group_bit, float(zoom[0]), float(zoom[1]))
+        wid = self._window_cache.get(key)
+        if wid is None:
+            t = self.file_meta[file]["times"]
+            center, duration = zoom
+            with np.errstate(invalid="ignore"):
+                m = (t >= center - duration / 2) & (t <= center + duration / 2)
+            wid = self._window_cache[key] = self.batch.add_window(file, group_bit, np.flatnonzero(m))
+        return wid
+
+    def resolve_zoom_flags(self, window_any: np.ndarray):
+        """Fill every figure's ``zoom_needed`` from the downloaded ``csg_window_any`` result."""
+        if not hasattr(self, "_zoom_index") or self._zoom_index[0] != len(self.figures):
+            ids, starts, figs = [], [], []
+            for fig in self.figures:
+                fig.zoom_needed = False
+                if fig.zoom_windows:
+                    starts.append(len(ids))
+                    ids.extend(fig.zoom_windows)
+                    figs.append(fig)
+            self._zoom_index = (len(self.figures), np.asarray(ids, dtype=np.int64), np.asarray(starts, dtype=np.int64), figs)
+        _, ids, starts, figs = self._zoom_index
+        if len(figs) == 0:
+            return
+        hit = np.maximum.reduceat(window_any[ids], starts)
+        for fig, h in zip(figs, hit.tolist()):
+            fig.zoom_needed = bool(h)
 
     def _rows_for_dataset(self, fig, label, file, group, builder_cols, z_given, zoom):
         """One dataset dict of the figure builders + its make_spectrogram panels."""
@@ -241,7 +265,7 @@ class ShardPlan:
         for g, key in enumerate(meta["keys"]):
             self._rows_for_dataset(fig, key.title(), file, g + 1, builder_cols, (z_min, z_max), fig.zoom)
         if fig.zoom is not None:
-            fig.zoom_needed = any(self._window_has_data(r.file, r.group, fig.zoom) for r in fig.rows)
+            fig.zoom_windows = [self._zoom_window(r.file, r.group, fig.zoom) for r in fig.rows]
         self.figures.append(fig)
         return fig
 
@@ -277,9 +301,17 @@ class ShardPlan:
             z_hi = row_z[1] if z_max is None else z_max
             self._rows_for_dataset(fig, inst.upper(), file, 0, builder_cols, (z_lo, z_hi), fig.zoom)
         if fig.zoom is not None:
-            fig.zoom_needed = any(self._window_has_data(r.file, 0, fig.zoom) for r in fig.rows)
+            fig.zoom_windows = [self._zoom_window(r.file, 0, fig.zoom) for r in fig.rows]
         self.figures.append(fig)
         return fig
+
+    def reset_plan(self):
+        """Drop every planned figure / panel (files and their collapsed sums stay valid)."""
+        self.batch.reset_tables()
+        self.figures = []
+        self._panel_cache, self._region_cache, self._full_stats, self._window_cache = {}, {}, {}, {}
+        if hasattr(self, "_zoom_index"):
+            del self._zoom_index
 
     # ------------------------------------------------------------------ execution
     def upload_tables(self):
@@ -313,6 +345,137 @@ class ShardPlan:
             inst_len[ii] = pos
         items = np.array(rows, dtype=POOL_ITEM) if rows else np.zeros(0, POOL_ITEM)
         return items, inst_len, owners
+
+
+class BatchStep:
+    """One batch step of the reference's directory driver for this rank's shard of orbits.
+
+    ``fast/batch_directory.py:159-171`` runs the global-extrema pre-pass, then ``:237-243``
+    submits every orbit twice (without and with the extrema) to ``FAST_process_single_orbit``,
+    which draws {given, raw} pitch-angle grids per instrument and {given, raw} instrument grids
+    (``fast/process_orbit.py:148-253``).  Here the whole shard goes through K1 -> K2b -> K2a ->
+    K3 as a handful of launches.  The panel tables are planned once from metadata (times,
+    energies, pitch angles, cusp rows); the z bounds that depend on this step's extrema live in
+    the batch's slot table, so a step re-plans only if the extrema change the *geometry*
+    (y bounds / missing keys).
+    """
+
+    def __init__(self, shard: ShardPlan, sequence, max_percentile=95.0, comm=None, lut259=None, want_index=False,
+                 compute_mins=False):
+        self.shard = shard
+        self.sequence = sequence
+        self.max_percentile = max_percentile
+        self.comm = comm
+        self.want_index = want_index
+        self.compute_mins = compute_mins
+        self.lut = lut259
+        self._sig = None
+        self._slots: dict = {}
+        self._win_pin = None
+        self.state: dict | None = None
+
+    # -- what of the extrema state shapes the plan (everything else flows through z slots)
+    def _bounds(self, state):
+        from .extrema import _extrema_overrides
+
+        sh = self.shard
+        out = {}
+        for inst in sh.instrument_order:
+            stem = f"{inst}_{sh.y_scale}_{sh.z_scale}"
+            ov = _extrema_overrides(state, inst, sh.y_scale, sh.z_scale)
+            raw = tuple(state.get(f"{stem}_{k}") for k in ("y_min", "y_max", "z_min", "z_max"))
+            out[inst] = (ov, raw)
+        return out
+
+    @staticmethod
+    def _signature(bounds):
+        return tuple(
+            (inst, ov[0], ov[1], ov[2] is None, ov[3] is None, raw[0], raw[1], raw[2] is None, raw[3] is None)
+            for inst, (ov, raw) in bounds.items()
+        )
+
+    def _plan(self, state, bounds):
+        sh, b = self.shard, self.shard.batch
+        sh.reset_plan()
+        self._slots = {}
+        slotted = dict(state)
+        given = {}
+        for inst, (ov, raw) in bounds.items():
+            stem = f"{inst}_{sh.y_scale}_{sh.z_scale}"
+            zr = []
+            for name, v in (("zr_min", ov[2]), ("zr_max", ov[3])):
+                if v is None:
+                    zr.append(None)
+                else:
+                    zr.append(b.zslot(v))
+                    self._slots[(inst, name)] = zr[-1]
+            given[inst] = (ov[0], ov[1], zr[0], zr[1])
+            for name, key, v in (("z_min", f"{stem}_z_min", raw[2]), ("z_max", f"{stem}_z_max", raw[3])):
+                if v is not None:
+                    slotted[key] = self._slots[(inst, name)] = b.zslot(v)
+        for ob in sh.orbits:
+            for with_extrema in (False, True):  # batch_directory.py:237-243
+                for inst in sh.instrument_order:
+                    if inst not in ob["files"]:
+                        continue
+                    if with_extrema:
+                        sh.plan_pitch_angle_grid(ob, inst, "given", *given[inst])
+                    else:
+                        sh.plan_pitch_angle_grid(ob, inst, "given")
+                    sh.plan_pitch_angle_grid(ob, inst, "raw")
+                sh.plan_instrument_grid(ob, "given", global_extrema=slotted if with_extrema else None)
+                sh.plan_instrument_grid(ob, "raw", global_extrema=None)
+        sh.upload_tables()
+        if self.lut is not None:
+            b.set_lut(self.lut)
+        n_win = len(b._windows)
+        self._win_pin = b.ctx.pinned(max(n_win, 1))
+
+    def _update_slots(self, bounds):
+        b = self.shard.batch
+        for inst, (ov, raw) in bounds.items():
+            for name, v in (("zr_min", ov[2]), ("zr_max", ov[3]), ("z_min", raw[2]), ("z_max", raw[3])):
+                slot = self._slots.get((inst, name))
+                if slot is not None:
+                    b.set_zslot(slot.slot, v)
+
+    def run(self, cache_state: dict | None = None) -> dict:
+        """Enqueue one whole step; returns the extrema state (rasters stay on the device)."""
+        from .extrema import extrema_enqueue, extrema_finish
+
+        sh, b = self.shard, self.shard.batch
+        sh.collapse()
+        pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
+                                  dict(cache_state or {}), compute_mins=self.compute_mins,
+                                  max_percentile=self.max_percentile, comm=self.comm)
+        planned = self._sig is not None
+        if planned:  # K2a does not depend on the extrema: it overlaps the host bookkeeping below
+            b.run_windows()
+            b.run_stats()
+        state = extrema_finish(pending)
+        bounds = self._bounds(state)
+        sig = self._signature(bounds)
+        if sig != self._sig:
+            self._plan(state, bounds)
+            self._sig = sig
+            b.run_windows()
+            b.run_stats()
+        else:
+            self._update_slots(bounds)
+        b.prepare()
+        b.rasterise(want_rgba=b.d_lut is not None, want_index=self.want_index)
+        if b._windows:
+            b.ctx._check(b.ctx.lib.csg_d2h(b.ctx.handle, self._win_pin.ptr, b.d_window_any.ptr, len(b._windows)))
+        self.state = state
+        return state
+
+    def finish(self):
+        """Wait for the step and fill the figures' ``zoom_needed`` flags."""
+        b = self.shard.batch
+        b.ctx.sync()
+        if b._windows:
+            self.shard.resolve_zoom_flags(self._win_pin.view(np.uint8, len(b._windows)))
+        return self.state
 
 
 def check_norm_status(norm_row, what: str):

@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from ._lib import POOL_ITEM, POOL_QUERY
+from ._lib import POOL_ITEM, POOL_QUERY, POOL_REQUEST, POOL_SEL
 
 FIRST_BITS = 11
 NEXT_BITS = 10
@@ -203,6 +203,155 @@ class GpuPoolBackend:
             )
         )
         return self._get("queries", d_q, POOL_QUERY, len(queries)).copy()
+
+
+class DevicePoolSelector:
+    """The whole digit loop enqueued on the context's stream: no host round trip per digit.
+
+    ``enqueue`` launches histograms, scans, the selection-table kernels of ``csrc/poolsel.cu`` and
+    (multi-rank) the NCCL exchanges on device buffers, then an asynchronous read-back of the
+    few results; ``result`` waits for that read-back only, so kernels enqueued afterwards (K2a)
+    overlap the host bookkeeping.  When more than ``N_SLOTS`` distinct key prefixes survive a
+    digit the device flags it and the caller falls back to the host-driven ``prefix_percentiles``.
+    """
+
+    N_SLOTS = 16
+    EVENT_SLOT = 31
+
+    def __init__(self, batch):
+        self.batch = batch
+        self.ctx = batch.ctx
+        self.mem = _Grow(batch.ctx)
+        self._static_key = None
+        self._pending = None
+
+    def _put(self, name: str, arr: np.ndarray) -> _lib.DevBuf:
+        arr = np.ascontiguousarray(arr)
+        pin = self.mem.pinned(name, arr.nbytes)
+        pin.array[: arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        dev = self.mem.device(name, arr.nbytes)
+        self.ctx._check(self.ctx.lib.csg_h2d(self.ctx.handle, dev.ptr, pin.ptr, arr.nbytes))
+        return dev
+
+    def enqueue(self, dtype, items: np.ndarray, n_inst: int, inst_len: np.ndarray, max_E: int, requests: list[dict],
+                comm=None):
+        comm = comm or SingleRank()
+        ctx, lib, mem = self.ctx, self.ctx.lib, self.mem
+        h, chk = ctx.handle, ctx._check
+        D = np.dtype(dtype)
+        code = _lib.np_dtype_code(D)
+        plan = digit_plan(D)
+        R, S = comm.size, self.N_SLOTS
+        n_items, n_req = len(items), len(requests)
+        max_pos = max(int(inst_len.max()) if len(inst_len) else 0, 1)
+        if R > 1:  # the table shape must agree across ranks only per rank; exchanged buffers are per (inst, slot, bin)
+            pass
+        max_E = max(int(max_E), 1)
+        # ---- static tables (re-uploaded only when they change)
+        key = (items.tobytes(), n_inst, inst_len.tobytes(), max_E, repr(requests), D.str)
+        if key != self._static_key:
+            reqs = np.zeros(max(n_req, 1), dtype=POOL_REQUEST)
+            for r, rq in enumerate(requests):
+                reqs[r] = (rq["inst"], 0 if rq["mode"] == "running_max" else 1, float(rq["p"]))
+            self.d_items = self._put("items", items) if n_items else None
+            self.d_inst_len = self._put("inst_len", np.ascontiguousarray(inst_len, dtype=np.int32))
+            self.d_reqs = self._put("reqs", reqs)
+            self._static_key = key
+        shift0, bits0 = plan[0]
+        nb0 = 1 << bits0
+        hist0 = mem.device("hist0", n_inst * max_pos * nb0 * 4)
+        chk(lib.csg_memset(h, hist0.ptr, 0, n_inst * max_pos * nb0 * 4))
+        d_counts = mem.device("counts", max(n_items, 1) * max_E * 4)
+        d_npos = mem.device("npos", max(n_items, 1) * 4)
+        sums = self.batch.d_sums.ptr
+        if n_items:
+            chk(lib.csg_pool_hist_first(h, sums, code, self.d_items.ptr, n_items, max_pos, bits0, max_E, hist0.ptr,
+                                        d_counts.ptr, d_npos.ptr))
+        d_tot = mem.device("totals", n_inst * S * 1024 * 4) if R > 1 else None
+        d_gath = mem.device("gath", R * n_inst * S * 1024 * 4) if R > 1 else None
+        d_base = mem.device("base", n_inst * S * 1024 * 4) if R > 1 else None
+        d_above = mem.device("above", n_inst * 8) if R > 1 else None
+        chk(lib.csg_pool_scan(h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, d_tot.ptr if R > 1 else None))
+        if R > 1:
+            comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * nb0 * 4)
+            chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, nb0, d_base.ptr, d_above.ptr))
+        d_n_after = mem.device("n_after", n_inst * max_pos * 8)
+        d_below = mem.device("below", n_inst * 8)
+        d_flags = mem.device("flags", 16)
+        d_sel = mem.device("sel", max(n_req, 1) * max_pos * POOL_SEL.itemsize)
+        d_best = mem.device("best", 64 * 8)
+        d_local = mem.device("local_slots", n_inst * S * 8)
+        d_gslots = mem.device("gath_slots", R * n_inst * S * 8) if R > 1 else d_local
+        d_table = mem.device("table", n_inst * S * 8)
+        d_values = mem.device("values", 64 * 8)
+        d_has = mem.device("has", 64 * 4)
+        base_ptr = d_base.ptr if R > 1 else None
+        chk(lib.csg_memset(h, d_flags.ptr, 0, 16))
+        chk(lib.csg_pool_row_totals(h, hist0.ptr, n_inst, max_pos, bits0, base_ptr, d_n_after.ptr, d_below.ptr))
+        chk(lib.csg_pool_sel_init(h, code, self.d_reqs.ptr, n_req, self.d_inst_len.ptr, max_pos, d_n_after.ptr,
+                                  d_below.ptr, d_above.ptr if R > 1 else None, d_sel.ptr))
+        chk(lib.csg_pool_sel_locate(h, hist0.ptr, max_pos, 1, bits0, base_ptr, d_sel.ptr, n_req, d_flags.ptr))
+        prev_shift = shift0
+        hist1 = None
+        for shift, bits in plan[1:]:
+            nb = 1 << bits
+            chk(lib.csg_pool_sel_bounds(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr))
+            if R > 1:
+                comm.allreduce_max_dev(d_best.ptr, n_req, "i8")
+            chk(lib.csg_pool_sel_slots(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr, n_inst, S,
+                                       d_local.ptr, d_flags.ptr))
+            if R > 1:
+                comm.allgather_dev(d_local.ptr, d_gslots.ptr, n_inst * S * 8)
+            chk(lib.csg_pool_sel_assign(h, d_sel.ptr, n_req, max_pos, d_gslots.ptr, R, n_inst, S, d_table.ptr, d_flags.ptr))
+            nbytes = n_inst * max_pos * S * nb * 4
+            hist1 = mem.device("hist1", nbytes)
+            chk(lib.csg_memset(h, hist1.ptr, 0, nbytes))
+            if n_items:
+                chk(lib.csg_pool_hist_refine(h, sums, code, self.d_items.ptr, n_items, max_pos, S, d_table.ptr, prev_shift,
+                                             shift, bits, hist1.ptr))
+            chk(lib.csg_pool_scan(h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_tot.ptr if R > 1 else None))
+            if R > 1:
+                comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * S * nb * 4)
+                chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, S * nb, d_base.ptr, None))
+            chk(lib.csg_pool_sel_locate(h, hist1.ptr, max_pos, S, bits, base_ptr, d_sel.ptr, n_req, d_flags.ptr))
+            prev_shift = shift
+        chk(lib.csg_pool_sel_finish(h, code, d_sel.ptr, n_req, max_pos, d_values.ptr, d_has.ptr))
+        if R > 1:
+            comm.allreduce_max_dev(d_values.ptr, n_req, "f8")
+            comm.allreduce_max_dev(d_has.ptr, n_req, "i4")
+            comm.allreduce_max_dev(d_flags.ptr, 4, "i4")
+        # ---- asynchronous read-back into one pinned block
+        sizes = [("values", d_values, 64 * 8), ("has", d_has, 64 * 4), ("flags", d_flags, 16),
+                 ("counts", d_counts, n_items * max_E * 4), ("npos", d_npos, n_items * 4)]
+        total = sum(_al(n) for _, _, n in sizes)
+        pin = mem.pinned("readback", total)
+        off, views = 0, {}
+        for name, dev, n in sizes:
+            if n:
+                chk(lib.csg_d2h(h, pin.ptr + off, dev.ptr, n))
+            views[name] = (off, n)
+            off += _al(n)
+        ctx.event_record(self.EVENT_SLOT)
+        self._pending = (pin, views, n_req, n_items, max_E)
+
+    def result(self):
+        """(values | None on slot overflow, counts[n_items][max_E], npos[n_items]); waits for the read-back only."""
+        pin, views, n_req, n_items, max_E = self._pending
+        self.ctx.event_sync(self.EVENT_SLOT)
+        get = lambda name, dt: pin.view(dt, views[name][1] // np.dtype(dt).itemsize, views[name][0])
+        flags = get("flags", np.int32)
+        counts = get("counts", np.int32).reshape(n_items, max_E).copy()
+        npos = get("npos", np.int32).copy()
+        if flags[1]:  # slot overflow: later digits ran on a truncated table, their flags mean nothing
+            return None, counts, npos
+        if flags[0] or flags[2]:
+            raise _lib.CsgError("device pool selection: a rank fell outside its bucket (histogram / scan mismatch)")
+        vals, has = get("values", np.float64)[:n_req], get("has", np.int32)[:n_req]
+        return [float(v) if ok else None for v, ok in zip(vals, has)], counts, npos
+
+
+def _al(n: int, a: int = 64) -> int:
+    return (int(n) + a - 1) // a * a
 
 
 class SingleRank:

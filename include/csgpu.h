@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 1
+#define CSG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -84,6 +84,10 @@ CSG_API int csg_timer_stop(csg_ctx* ctx, int slot);
 CSG_API int csg_timer_ms(csg_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
 /* number of kernels this context has launched since creation */
 CSG_API int64_t csg_launch_count(csg_ctx* ctx);
+/* Event slots (0..31): record on the ctx stream, wait on the host for that point only (later
+ * work keeps running) -- used to read small results back while the next kernels execute. */
+CSG_API int csg_event_record(csg_ctx* ctx, int slot);
+CSG_API int csg_event_sync(csg_ctx* ctx, int slot);
 
 /* ------------------------------------------------------------- K1: collapse */
 /* One counts cube.  Replaces COLLAPSE_FUNCTION = np.nansum(cube, axis=1)
@@ -113,6 +117,16 @@ CSG_API int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, 
 CSG_API int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
                  const uint8_t* d_pa_bits, int n_groups, int max_P, int dtype, int layout,
                  void* d_sums, uint8_t* d_row_flags);
+
+/* zoom_needed = np.any(~np.isnan(cube[window])) (CS/plotting.py:597-603) from the row flags:
+ * d_out[w] = 1 iff some row of window w has bit `bit` set.  Rows are [t0, t0+nt) when
+ * rows_off < 0, else d_index_pool[rows_off .. rows_off+nt). */
+typedef struct {
+  int64_t flags_off; /* byte offset of the file's flags in d_row_flags */
+  int32_t t0, nt, rows_off, bit;
+} csg_flag_window; /* 24 bytes */
+CSG_API int csg_window_any(csg_ctx* ctx, const uint8_t* d_row_flags, const csg_flag_window* d_windows, int n_windows,
+                   const int32_t* d_index_pool, uint8_t* d_out);
 
 /* Host-buffer convenience for one cube: the drop-in for COLLAPSE_FUNCTION(array, axis=1).
  * h_pa_bits may be NULL when n_groups == 0.  h_sums receives [(G+1)][T][E] of dtype D,
@@ -164,7 +178,9 @@ typedef struct {
   int32_t stat_region; /* stats entry giving safe_vmin / the linear fallback: a region with
                           the same cell SET as `region` (order-independent), or -1 = region */
   int32_t reserved;
-} csg_panel;           /* 48 bytes */
+  int32_t zmin_slot, zmax_slot; /* >= 0: take the bound from d_zvals[slot] instead of z_min / z_max
+                                   (bounds that depend on this step's global extrema); -1: literal */
+} csg_panel;           /* 56 bytes */
 
 enum {
   CSG_NORM_OK = 0,
@@ -187,10 +203,10 @@ CSG_API int32_t csg_raster_blocks(int32_t ne, int32_t nt);
 CSG_API size_t csg_threshold_bytes(int n_panels, int dtype);
 
 /* Resolve every panel's normalisation (and its index thresholds) on the device from the
- * region stats. */
+ * region stats.  d_zvals (may be NULL when no panel uses a slot): double[], NaN = None. */
 CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels,
                       const csg_region* d_regions, const csg_region_stats* d_stats, int dtype,
-                      csg_panel_norm* d_norms, void* d_thresholds);
+                      const double* d_zvals, csg_panel_norm* d_norms, void* d_thresholds);
 
 /* Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
  * under, over, bad).  d_index (uint16, may be NULL) receives Colormap indices 0..255 and
@@ -243,6 +259,60 @@ typedef struct {
 } csg_pool_query;               /* 32 bytes */
 CSG_API int csg_pool_locate(csg_ctx* ctx, const uint32_t* d_hist, int max_pos, int n_slots, int bits,
                     const uint32_t* d_base, csg_pool_query* d_queries, int n_queries);
+
+/* ------------------------------- K2b, device-resident selection (no host round trips) */
+/* The digit loop above driven on the GPU: one dense table entry per (request, pos) follows the
+ * two neighbour ranks of numpy's linear interpolation through the digits; prefixes that cannot
+ * hold the running maximum (CS/fast/extrema.py:287-300) are dropped between digits and the
+ * distinct surviving key prefixes form the slot table of the next csg_pool_hist_refine(). */
+typedef struct {
+  int32_t inst;
+  int32_t mode; /* 0: max over every prefix pool of its percentile (the reference's max-merge);
+                   1: percentile of the whole pool (compute_mins, CS/fast/extrema.py:302-309) */
+  double p;     /* percentile 0..100 */
+} csg_pool_request; /* 16 bytes */
+typedef struct {
+  int32_t inst, pos, req, active;
+  int32_t slot[2];    /* slot of the lo / hi neighbour's prefix in the current refine table   */
+  int64_t rank[2];    /* rank inside the current bucket                                       */
+  uint64_t prefix[2]; /* key bits resolved so far                                             */
+  double gamma;       /* numpy's interpolation weight, computed in D                          */
+} csg_pool_sel;       /* 64 bytes */
+/* d_flags: int32[4], zeroed by the caller; bit set on: [0] a rank fell outside its row,
+ * [1] more than n_slots distinct prefixes survived (fall back to the host-driven loop),
+ * [2] a target's prefix is missing from the slot table. */
+
+/* n_after[inst][pos] = population of prefix pool pos (scanned level-0 row + lower ranks' d_base,
+ * may be NULL); d_below[inst] = population held by lower ranks. */
+CSG_API int csg_pool_row_totals(csg_ctx* ctx, const uint32_t* d_hist, int n_inst, int max_pos, int bits,
+                        const uint32_t* d_base, int64_t* d_n_after, int64_t* d_below);
+/* Fill d_sel[n_req][max_pos]: active entries + numpy's (n-1)*q rank arithmetic in D.
+ * d_above[inst] (may be NULL): positives held by higher ranks. */
+CSG_API int csg_pool_sel_init(csg_ctx* ctx, int dtype, const csg_pool_request* d_requests, int n_req,
+                      const int32_t* d_inst_len, int max_pos, const int64_t* d_n_after,
+                      const int64_t* d_below, const int64_t* d_above, csg_pool_sel* d_sel);
+CSG_API int csg_pool_sel_locate(csg_ctx* ctx, const uint32_t* d_hist, int max_pos, int n_slots, int bits,
+                        const uint32_t* d_base, csg_pool_sel* d_sel, int n_req, int32_t* d_flags);
+/* d_best[n_req] (int64 key bits, -1 = none): this rank's best lower bound per running-max request;
+ * all-reduce(max) it across ranks before csg_pool_sel_slots(). */
+CSG_API int csg_pool_sel_bounds(csg_ctx* ctx, const csg_pool_sel* d_sel, const csg_pool_request* d_requests,
+                        int n_req, int max_pos, int shift, int64_t* d_best);
+/* Prune against d_best, then d_local_slots[inst][n_slots] = ascending distinct prefixes still
+ * followed on this rank (padded with UINT64_MAX); all-gather it before csg_pool_sel_assign(). */
+CSG_API int csg_pool_sel_slots(csg_ctx* ctx, csg_pool_sel* d_sel, const csg_pool_request* d_requests, int n_req,
+                       int max_pos, int shift, const int64_t* d_best, int n_inst, int n_slots,
+                       uint64_t* d_local_slots, int32_t* d_flags);
+/* d_gathered[n_ranks][inst][n_slots] -> d_table[inst][n_slots] (merged) + every target's slot. */
+CSG_API int csg_pool_sel_assign(csg_ctx* ctx, csg_pool_sel* d_sel, int n_req, int max_pos,
+                        const uint64_t* d_gathered, int n_ranks, int n_inst, int n_slots,
+                        uint64_t* d_table, int32_t* d_flags);
+/* d_values[n_req] (double; -inf when no entry survived on this rank), d_has[n_req]. */
+CSG_API int csg_pool_sel_finish(csg_ctx* ctx, int dtype, const csg_pool_sel* d_sel, int n_req, int max_pos,
+                        double* d_values, int32_t* d_has);
+/* From the all-gathered bucket totals d_gathered[n_ranks][inst][cols_per_inst]:
+ * d_base = sum over lower ranks; d_above[inst] (may be NULL) = cells held by higher ranks. */
+CSG_API int csg_pool_base(csg_ctx* ctx, const uint32_t* d_gathered, int n_ranks, int rank, int n_inst,
+                  size_t cols_per_inst, uint32_t* d_base, int64_t* d_above);
 
 #ifdef __cplusplus
 }

@@ -282,10 +282,11 @@ def _pool_reference(mats_by_inst, p, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("integer", [True, False])
-def test_pool_prefix_percentiles_exact(ctx, dtype, integer):
+@pytest.mark.parametrize("selector", ["host_driven", "device"])
+def test_pool_prefix_percentiles_exact(ctx, dtype, integer, selector):
     from configurable_spectrograms_b200._lib import POOL_ITEM
     from configurable_spectrograms_b200.engine import Batch
-    from configurable_spectrograms_b200.pool_select import GpuPoolBackend, prefix_percentiles
+    from configurable_spectrograms_b200.pool_select import DevicePoolSelector, GpuPoolBackend, prefix_percentiles
 
     rng = np.random.default_rng(16)
     n_inst, n_files = 3, 9
@@ -308,7 +309,14 @@ def test_pool_prefix_percentiles_exact(ctx, dtype, integer):
     reqs = [{"inst": i, "p": 99.0, "mode": "running_max"} for i in range(n_inst)]
     reqs += [{"inst": i, "p": 1, "mode": "last"} for i in range(n_inst)]
     reqs += [{"inst": 0, "p": 50.0, "mode": "running_max"}]
-    vals, counts, npos = prefix_percentiles(GpuPoolBackend(b), dtype, items, n_inst, inst_len, 96, reqs)
+    if selector == "device":
+        sel = DevicePoolSelector(b)
+        for _ in range(2):  # the second run re-uses every scratch buffer and static table
+            sel.enqueue(dtype, items, n_inst, inst_len, 96, reqs)
+            vals, counts, npos = sel.result()
+        assert vals is not None, "slot overflow on a tiny pool"
+    else:
+        vals, counts, npos = prefix_percentiles(GpuPoolBackend(b), dtype, items, n_inst, inst_len, 96, reqs)
     for r, req in enumerate(reqs):
         i = req["inst"]
         with np.errstate(invalid="ignore"):
@@ -323,3 +331,39 @@ def test_pool_prefix_percentiles_exact(ctx, dtype, integer):
         ok = np.isfinite(m) & (m > 0)
         assert np.array_equal(counts[j], ok.sum(axis=0))
         assert npos[j] == ok.sum()
+
+
+def test_device_selector_slot_overflow_falls_back(ctx):
+    """More distinct surviving prefixes than the device slot table holds -> flagged, never wrong."""
+    from configurable_spectrograms_b200._lib import POOL_ITEM
+    from configurable_spectrograms_b200.engine import Batch
+    from configurable_spectrograms_b200.pool_select import DevicePoolSelector, GpuPoolBackend, prefix_percentiles
+
+    rng = np.random.default_rng(5)
+    b = Batch(ctx, np.float32, 0)
+    n_files = 12
+    files = []
+    for k in range(n_files):
+        c = np.exp(rng.uniform(0.0, 9.0, (16, 2, 8))).astype(np.float32)  # spread over many coarse buckets
+        files.append((b.add_file(c), c))
+    b.upload_cubes()
+    b.collapse()
+    items = np.zeros(n_files, dtype=POOL_ITEM)
+    for k, (f, c) in enumerate(files):
+        items[k] = (b.mat_off(f, 0), c.shape[0] * 8, 8, 0, k)
+    inst_len = np.array([n_files], dtype=np.int32)
+    ps = (10.0, 30.0, 50.0, 70.0, 90.0)
+    reqs = [{"inst": 0, "p": p, "mode": "last"} for p in ps]  # whole-pool requests are never pruned
+    mats = [np.nansum(c, axis=1) for _, c in files]
+    expected = [_pool_reference(mats, p, np.float32)[1] for p in ps]
+    sel = DevicePoolSelector(b)
+    sel.N_SLOTS = 2
+    sel.enqueue(np.float32, items, 1, inst_len, 8, reqs)
+    vals, counts, npos = sel.result()
+    assert vals is None, "five spread-out percentiles cannot share two slots"
+    vals2, _, _ = prefix_percentiles(GpuPoolBackend(b), np.float32, items, 1, inst_len, 8, reqs)
+    assert vals2 == expected
+    sel.N_SLOTS = 16
+    sel.enqueue(np.float32, items, 1, inst_len, 8, reqs)
+    vals3, _, _ = sel.result()
+    assert vals3 == expected
