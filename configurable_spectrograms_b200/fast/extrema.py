@@ -72,46 +72,51 @@ def _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor
     stored = state.get(last_key, -1)
     last_done = int(stored) if isinstance(stored, (int, float)) else -1
     y_log, z_log = y_scale == "log", z_scale == "log"
+    # key strings of every instrument, built once (the loop below runs orbits x instruments times)
+    keys = []
+    for inst in instrument_order:
+        stem, ll = f"{inst}_{y_scale}_{z_scale}", f"{inst}_linear_linear"
+        keys.append((inst, f"{stem}_extrema_progress", f"{ll}_y_max", f"{ll}_z_max", f"{ll}_y_min", f"{ll}_z_min",
+                     f"{stem}_y_max", f"{stem}_y_min", f"{stem}_z_max", f"{stem}_z_min"))
+    other_last = [f"{other}_{y_scale}_{z_scale}_last_orbit" for other in instrument_order]
+    max_orbit = max(orbit_numbers) if orbit_numbers else -1
     for orbit_index, (orbit, handles) in enumerate(sequence):
         if orbit <= last_done:
             continue
-        for inst in instrument_order:
-            stem = f"{inst}_{y_scale}_{z_scale}"
-            progress_key = f"{stem}_extrema_progress"
+        for inst, progress_key, ll_y, ll_z, ll_ymin, ll_zmin, k_ymax, k_ymin, k_zmax, k_zmin in keys:
             entry = state.get(progress_key)
             if isinstance(entry, dict) and entry.get("complete"):
                 continue
-            ll = f"{inst}_linear_linear"
-            have_y, have_z = f"{ll}_y_max" in state, f"{ll}_z_max" in state
+            have_y, have_z = ll_y in state, ll_z in state
             if have_y:
-                state[f"{stem}_y_max"] = safe_log(state[f"{ll}_y_max"]) if y_log else state[f"{ll}_y_max"]
-                state[f"{stem}_y_min"] = log_floor_value if y_log else state.get(f"{ll}_y_min", 0)
+                state[k_ymax] = safe_log(state[ll_y]) if y_log else state[ll_y]
+                state[k_ymin] = log_floor_value if y_log else state.get(ll_ymin, 0)
             if have_z:
-                state[f"{stem}_z_max"] = safe_log(state[f"{ll}_z_max"]) if z_log else state[f"{ll}_z_max"]
-                state[f"{stem}_z_min"] = log_floor_value if z_log else state.get(f"{ll}_z_min", 0)
+                state[k_zmax] = safe_log(state[ll_z]) if z_log else state[ll_z]
+                state[k_zmin] = log_floor_value if z_log else state.get(ll_zmin, 0)
             if have_y and have_z:
                 state[progress_key] = {"processed_index": max(totals[inst] - 1, -1), "total": totals[inst], "complete": True}
-                for other in instrument_order:
-                    state.pop(f"{other}_{y_scale}_{z_scale}_last_orbit", None)
-                state[last_key] = max(orbit_numbers) if orbit_numbers else -1
+                for other in other_last:
+                    state.pop(other, None)
+                state[last_key] = max_orbit
                 if on_step_done:
                     on_step_done(reuse=True)
                 continue
             cand_e, cand_z, z_min_store = on_scan(inst, orbit_index, handles.get(inst))
-            prev_e, prev_z = state.get(f"{stem}_y_max"), state.get(f"{stem}_z_max")
+            prev_e, prev_z = state.get(k_ymax), state.get(k_zmax)
             merged_e = max(float(prev_e), cand_e) if isinstance(prev_e, (int, float)) else cand_e
             merged_z = max(float(prev_z), cand_z) if isinstance(prev_z, (int, float)) else cand_z
-            state[f"{stem}_y_min"] = 0
-            state[f"{stem}_y_max"] = int(min(4000, math.ceil(merged_e)))
-            state[f"{stem}_z_min"] = z_min_store
-            state[f"{stem}_z_max"] = float(math.ceil(merged_z))
+            state[k_ymin] = 0
+            state[k_ymax] = int(min(4000, math.ceil(merged_e)))
+            state[k_zmin] = z_min_store
+            state[k_zmax] = float(math.ceil(merged_z))
             state[progress_key] = {
                 "processed_index": orbit_index,
                 "total": totals[inst],
                 "complete": orbit_index + 1 >= totals[inst],
             }
-            for other in instrument_order:
-                state.pop(f"{other}_{y_scale}_{z_scale}_last_orbit", None)
+            for other in other_last:
+                state.pop(other, None)
             state[last_key] = orbit
             if on_step_done:
                 on_step_done(reuse=False)
@@ -143,17 +148,59 @@ def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
     n = len(energies)
     if n == 0:
         return []
-    keys = np.unique(np.concatenate([np.asarray(e, dtype=np.float64) for e in energies]))
-    per_file = np.zeros((n, len(keys)), dtype=np.int64)
-    for k, (e, c) in enumerate(zip(energies, counts)):
-        e = np.asarray(e, dtype=np.float64)
-        np.add.at(per_file[k], np.searchsorted(keys, e), np.asarray(c[: len(e)], dtype=np.int64))
+    shared = all(e is energies[0] for e in energies)
+    if shared:  # the usual case: every file of the instrument carries the same energy table
+        e0 = np.asarray(energies[0], dtype=np.float64)
+        keys, idx = np.unique(e0, return_inverse=True)
+        c = np.asarray(counts, dtype=np.int64)[:, : len(e0)]
+        if len(keys) == len(e0):
+            per_file = np.empty((n, len(keys)), dtype=np.int64)
+            per_file[:, idx] = c
+        else:
+            per_file = np.zeros((len(keys), n), dtype=np.int64)
+            np.add.at(per_file, idx, c.T)
+            per_file = per_file.T
+    else:
+        keys = np.unique(np.concatenate([np.asarray(e, dtype=np.float64) for e in energies]))
+        per_file = np.zeros((n, len(keys)), dtype=np.int64)
+        for k, (e, c) in enumerate(zip(energies, counts)):
+            e = np.asarray(e, dtype=np.float64)
+            np.add.at(per_file[k], np.searchsorted(keys, e), np.asarray(c[: len(e)], dtype=np.int64))
     running = np.cumsum(per_file, axis=0)  # counts per key after each step
     along = np.cumsum(running, axis=1)
     total = along[:, -1]
     target = 0.99 * total
     first = (along > target[:, None]).argmax(axis=1)
-    return [float(keys[first[k]]) if total[k] > 0 else 0.0 for k in range(n)]
+    out = keys[first]
+    return [float(v) if t > 0 else 0.0 for v, t in zip(out.tolist(), total.tolist())]
+
+
+def _energy_plan(shard, comm, instrument_order, steps, owners, first):
+    """Who holds the per-energy counts of every scanned step (static per plan; exchanged once)."""
+    local = [(inst, oi + first, shard.file_meta[file]["energy"]) for inst, oi, file in owners]
+    parts = comm.allgather_object(local) if comm.size > 1 else [local]
+    n_max = max((len(p) for p in parts), default=0)
+    max_E = max((len(e) for p in parts for _, _, e in p), default=1)  # same on every rank: shapes of the exchange
+    where, energies = {}, {}
+    for rk, part in enumerate(parts):
+        for row, (inst, oi, energy) in enumerate(part):
+            where[(inst, oi)] = rk * n_max + row
+            energies[(inst, oi)] = energy
+    plan = {}
+    for inst in instrument_order:
+        present = [oi for oi in steps[inst] if (inst, oi) in where]
+        en = [energies[(inst, oi)] for oi in present]
+        # after a pickle round trip equal tables are distinct objects: fold them back together
+        uniq: list[np.ndarray] = []
+        for k, e in enumerate(en):
+            for u in uniq:
+                if u is e or (u.shape == np.shape(e) and np.array_equal(u, e, equal_nan=True)):
+                    en[k] = u
+                    break
+            else:
+                uniq.append(e)
+        plan[inst] = (present, np.asarray([where[(inst, oi)] for oi in present], dtype=np.int64), en)
+    return plan, n_max, max_E
 
 
 def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
@@ -185,14 +232,16 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
             inst: [oi - first for oi in steps[inst] if first <= oi < first + len(shard.orbits)]
             for inst in instrument_order
         }
+        items, inst_len, owners = shard.pool_items(local_steps)
+        eplan, n_max, max_E = _energy_plan(shard, comm, instrument_order, steps, owners, first)
         if len(cache) > 8:
             cache.clear()
-        hit = cache[key] = (sequence, steps, totals, *shard.pool_items(local_steps))  # holds `sequence`: id stays unique
-    _, steps, totals, items, inst_len, owners = hit
+        # the entry holds `sequence` itself, so its id() cannot be recycled while the entry lives
+        hit = cache[key] = (sequence, steps, totals, items, inst_len, owners, eplan, n_max, max_E)
+    _, steps, totals, items, inst_len, owners, eplan, n_max, max_E = hit
     requests = [{"inst": ii, "p": max_percentile, "mode": "running_max"} for ii in range(len(instrument_order))]
     if compute_mins:
         requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
-    max_E = max((shard.batch.files[f]["E"] for _, _, f in owners), default=1)
     selector = getattr(shard, "_pool_selector", None)
     if selector is None:
         selector = shard._pool_selector = DevicePoolSelector(shard.batch)  # persistent scratch across steps
@@ -202,53 +251,62 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
         "state": state, "compute_mins": compute_mins, "log_floor_cutoff": log_floor_cutoff,
         "log_floor_value": log_floor_value, "comm": comm, "steps": steps, "totals": totals, "first": first,
         "items": items, "inst_len": inst_len, "owners": owners, "requests": requests, "max_E": max_E, "selector": selector,
+        "eplan": eplan, "n_max": n_max,
     }
 
 
 def extrema_finish(pending, on_step_done=None):
-    """Wait for the selection's read-back and run the reference's bookkeeping walk on the results."""
+    """Wait for the selection's read-backs and run the reference's bookkeeping walk on the results."""
     from ..pool_select import GpuPoolBackend, prefix_percentiles
 
     shard, comm = pending["shard"], pending["comm"]
-    instrument_order, steps, first = pending["instrument_order"], pending["steps"], pending["first"]
-    owners, requests, compute_mins = pending["owners"], pending["requests"], pending["compute_mins"]
-    values, counts, npos = pending["selector"].result()
+    instrument_order, steps = pending["instrument_order"], pending["steps"]
+    requests, compute_mins = pending["requests"], pending["compute_mins"]
+    selector = pending["selector"]
+    # ---- y extrema: per-step energy candidates from every rank's per-file positive counts
+    # (available after the first histogram pass; this overlaps the digit loop on the GPU)
+    counts, npos = selector.result_counts()
+    if comm.size > 1:
+        padded = np.zeros((pending["n_max"], pending["max_E"]), dtype=np.int32)
+        padded[: len(counts)] = counts
+        all_counts = np.concatenate(comm.allgather(padded), axis=0)
+    else:
+        all_counts = counts
+    cand_e: dict[str, dict[int, float]] = {}
+    for inst in instrument_order:
+        present, rows, energies = pending["eplan"][inst]
+        ce = energy_candidates(energies, all_counts[rows]) if present else []
+        by_step = dict(zip(present, ce))
+        running, per = 0.0, {}
+        for oi in steps[inst]:  # steps without a file repeat the previous candidate
+            running = by_step.get(oi, running)
+            per[oi] = running
+        cand_e[inst] = per
+    # ---- z extrema: the device selection
+    values = selector.result_values()
     if values is None:
         # more distinct candidate buckets survived than the device table holds: same kernels,
         # digit loop driven from the host (arbitrary candidate counts)
         backend = getattr(shard, "_pool_backend", None)
         if backend is None:
             backend = shard._pool_backend = GpuPoolBackend(shard.batch)
-        values, counts, npos = prefix_percentiles(
+        values, _, _ = prefix_percentiles(
             backend, shard.batch.dtype, pending["items"], len(instrument_order), pending["inst_len"], pending["max_E"],
             requests, comm=comm,
         )
-    # ---- per-step energy candidates need every rank's per-file counts in sequence order
-    local_rows = {}
-    for row, (inst, oi, file) in enumerate(owners):
-        local_rows[(inst, oi + first)] = (shard.file_meta[file]["energy"], counts[row])
-    merged_rows = {}
-    for part in comm.allgather_object(local_rows):
-        merged_rows.update(part)
-    cand_e: dict[tuple[str, int], float] = {}
-    for inst in instrument_order:
-        present = [oi for oi in steps[inst] if (inst, oi) in merged_rows]
-        ce = energy_candidates([merged_rows[(inst, oi)][0] for oi in present], [merged_rows[(inst, oi)][1] for oi in present])
-        by_step = dict(zip(present, ce))
-        running = 0.0
-        for oi in steps[inst]:  # steps without a file repeat the previous candidate
-            running = by_step.get(oi, running)
-            cand_e[(inst, oi)] = running
     n_inst = len(instrument_order)
-
-    def scan(inst, orbit_index, handle):
-        ii = instrument_order.index(inst)
+    per_inst = {}
+    for ii, inst in enumerate(instrument_order):
         z = values[ii]
         z_min = 0
         if compute_mins:
             zm = values[n_inst + ii]
             z_min = float(zm) if zm is not None else 0
-        return cand_e.get((inst, orbit_index), 0.0), (float(z) if z is not None else 0.0), z_min
+        per_inst[inst] = (cand_e[inst], float(z) if z is not None else 0.0, z_min)
+
+    def scan(inst, orbit_index, handle):
+        ce, z, z_min = per_inst[inst]
+        return ce.get(orbit_index, 0.0), z, z_min
 
     return _walk(pending["sequence"], instrument_order, pending["y_scale"], pending["z_scale"], pending["state"],
                  pending["totals"], pending["log_floor_cutoff"], pending["log_floor_value"], scan, on_step_done)

@@ -267,6 +267,18 @@ class DevicePoolSelector:
         if n_items:
             chk(lib.csg_pool_hist_first(h, sums, code, self.d_items.ptr, n_items, max_pos, bits0, max_E, hist0.ptr,
                                         d_counts.ptr, d_npos.ptr))
+        # the per-energy positive counts are final here: read them back now so the host can work
+        # on the y extrema while the digit loop runs
+        sizes = [("values", 64 * 8), ("has", 64 * 4), ("flags", 16), ("counts", n_items * max_E * 4), ("npos", n_items * 4)]
+        pin = mem.pinned("readback", sum(_al(n) for _, n in sizes))
+        views, off = {}, 0
+        for name, n in sizes:
+            views[name] = (off, n)
+            off += _al(n)
+        if n_items:
+            chk(lib.csg_d2h(h, pin.ptr + views["counts"][0], d_counts.ptr, n_items * max_E * 4))
+            chk(lib.csg_d2h(h, pin.ptr + views["npos"][0], d_npos.ptr, n_items * 4))
+        ctx.event_record(self.EVENT_SLOT - 1)
         d_tot = mem.device("totals", n_inst * S * 1024 * 4) if R > 1 else None
         d_gath = mem.device("gath", R * n_inst * S * 1024 * 4) if R > 1 else None
         d_base = mem.device("base", n_inst * S * 1024 * 4) if R > 1 else None
@@ -320,34 +332,38 @@ class DevicePoolSelector:
             comm.allreduce_max_dev(d_values.ptr, n_req, "f8")
             comm.allreduce_max_dev(d_has.ptr, n_req, "i4")
             comm.allreduce_max_dev(d_flags.ptr, 4, "i4")
-        # ---- asynchronous read-back into one pinned block
-        sizes = [("values", d_values, 64 * 8), ("has", d_has, 64 * 4), ("flags", d_flags, 16),
-                 ("counts", d_counts, n_items * max_E * 4), ("npos", d_npos, n_items * 4)]
-        total = sum(_al(n) for _, _, n in sizes)
-        pin = mem.pinned("readback", total)
-        off, views = 0, {}
-        for name, dev, n in sizes:
-            if n:
-                chk(lib.csg_d2h(h, pin.ptr + off, dev.ptr, n))
-            views[name] = (off, n)
-            off += _al(n)
+        # ---- asynchronous read-back of the few results
+        for name, dev in (("values", d_values), ("has", d_has), ("flags", d_flags)):
+            chk(lib.csg_d2h(h, pin.ptr + views[name][0], dev.ptr, views[name][1]))
         ctx.event_record(self.EVENT_SLOT)
         self._pending = (pin, views, n_req, n_items, max_E)
 
-    def result(self):
-        """(values | None on slot overflow, counts[n_items][max_E], npos[n_items]); waits for the read-back only."""
-        pin, views, n_req, n_items, max_E = self._pending
+    def _view(self, name, dt):
+        pin, views = self._pending[0], self._pending[1]
+        return pin.view(dt, views[name][1] // np.dtype(dt).itemsize, views[name][0])
+
+    def result_counts(self):
+        """(counts[n_items][max_E], npos[n_items]) -- available right after the first histogram pass."""
+        _, _, _, n_items, max_E = self._pending
+        self.ctx.event_sync(self.EVENT_SLOT - 1)
+        return self._view("counts", np.int32).reshape(n_items, max_E).copy(), self._view("npos", np.int32).copy()
+
+    def result_values(self):
+        """One float per request (None: empty pool), or None when the slot table overflowed."""
+        n_req = self._pending[2]
         self.ctx.event_sync(self.EVENT_SLOT)
-        get = lambda name, dt: pin.view(dt, views[name][1] // np.dtype(dt).itemsize, views[name][0])
-        flags = get("flags", np.int32)
-        counts = get("counts", np.int32).reshape(n_items, max_E).copy()
-        npos = get("npos", np.int32).copy()
+        flags = self._view("flags", np.int32)
         if flags[1]:  # slot overflow: later digits ran on a truncated table, their flags mean nothing
-            return None, counts, npos
+            return None
         if flags[0] or flags[2]:
             raise _lib.CsgError("device pool selection: a rank fell outside its bucket (histogram / scan mismatch)")
-        vals, has = get("values", np.float64)[:n_req], get("has", np.int32)[:n_req]
-        return [float(v) if ok else None for v, ok in zip(vals, has)], counts, npos
+        vals, has = self._view("values", np.float64)[:n_req], self._view("has", np.int32)[:n_req]
+        return [float(v) if ok else None for v, ok in zip(vals, has)]
+
+    def result(self):
+        """(values | None on slot overflow, counts, npos); waits for the read-backs only."""
+        counts, npos = self.result_counts()
+        return self.result_values(), counts, npos
 
 
 def _al(n: int, a: int = 64) -> int:

@@ -1,0 +1,130 @@
+"""CPU tests of the product's host-side bookkeeping (no GPU, no libcsgpu compute): the extrema
+walk, the per-step energy candidates and the shard planner's masks, checked against the
+reference's own results (tests/golden) with numpy standing in for the device selection."""
+
+import numpy as np
+
+from configurable_spectrograms_b200.fast import extrema as X
+from tests.helpers import load_json
+from tests.test_oracle import _tree_files
+
+
+def _brute_energy_candidates(energies, counts):
+    """CS/fast/extrema.py:261-278 literally: dict keyed by float(energy), sorted, cumsum, searchsorted."""
+    acc, out = {}, []
+    for e, c in zip(energies, counts):
+        for ev, cnt in zip(e, c):
+            if cnt:
+                acc[float(ev)] = acc.get(float(ev), 0) + int(cnt)
+        if not acc:
+            out.append(0.0)
+            continue
+        ks = np.array(sorted(acc))
+        cum = np.cumsum([acc[k] for k in ks])
+        idx = min(int(np.searchsorted(cum, 0.99 * cum[-1], side="right")), len(ks) - 1)
+        out.append(float(ks[idx]))
+    return out
+
+
+def test_energy_candidates_paths_agree():
+    rng = np.random.default_rng(0)
+    for dup in (False, True):
+        energy = np.sort(rng.uniform(4, 30000, 96))[::-1].copy()
+        if dup:
+            energy[10:14] = energy[10]
+            energy[50] = energy[51]
+        n = 17
+        counts = rng.integers(0, 40, (n, 96)) * (rng.random((n, 96)) < 0.7)
+        counts[3] = 0
+        counts[0, 60:] = 0
+        shared = X.energy_candidates([energy] * n, counts)
+        separate = X.energy_candidates([energy.copy() for _ in range(n)], counts)
+        brute = _brute_energy_candidates([energy] * n, counts)
+        assert shared == separate == brute
+    # files with different tables, and an empty leading pool
+    e1, e2 = np.linspace(10, 1000, 12), np.linspace(5, 3000, 9)
+    cs = [np.zeros(12, int), rng.integers(0, 9, 12), rng.integers(0, 9, 9), rng.integers(0, 9, 12)]
+    es = [e1, e1, e2, e1]
+    padded = [np.pad(c, (0, 12 - len(c))) for c in cs]
+    assert X.energy_candidates(es, padded) == _brute_energy_candidates(es, cs)
+
+
+def _numpy_scan(files, order, max_percentile, compute_mins):
+    """on_scan for X._walk with numpy standing in for K1/K2b (same semantics as the device path:
+    one call per (instrument, orbit index) in sequence order)."""
+    pools = {i: [] for i in order}
+    counts = {i: ([], []) for i in order}
+
+    def scan(inst, orbit_index, handle):
+        _o, per = files[orbit_index]
+        if inst in per:
+            energy, cube = per[inst]
+            with np.errstate(invalid="ignore", over="ignore"):
+                c = np.nansum(cube, axis=1)
+            m = np.isfinite(c) & (c > 0)
+            counts[inst][0].append(energy)
+            counts[inst][1].append(m.sum(axis=0))
+            if m.any():
+                pools[inst].append(c[m])
+        ce = X.energy_candidates(*counts[inst])
+        cand_e = ce[-1] if ce else 0.0
+        cand_z, z_min = 0.0, 0
+        if pools[inst]:
+            pool = np.concatenate(pools[inst])
+            cand_z = float(np.nanpercentile(pool, max_percentile))
+            if compute_mins:
+                z_min = float(np.nanpercentile(pool, 1))
+        return cand_e, cand_z, z_min
+
+    return scan
+
+
+def test_walk_reproduces_reference_extrema_json():
+    files, order = _tree_files()
+    gold = load_json("extrema_tree.json")
+    sequence = [(o, {i: True for i in per}) for o, per in files]
+    totals = {i: sum(1 for _, h in sequence if i in h) for i in order}
+    state = {}
+    for combo in gold["combos"]:  # CLI order, one shared cache
+        steps, totals2 = X.plan_scanned_steps(sequence, order, combo["y"], combo["z"], state)
+        assert totals2 == totals
+        before = json_copy(state)
+        state = X._walk(sequence, order, combo["y"], combo["z"], state, totals, 0.1, -1.0, _numpy_scan(files, order, 99.0, False))
+        assert state == combo["extrema"], (combo["y"], combo["z"])
+        # the dry run predicted exactly the steps that reached the scan
+        seen = {i: [] for i in order}
+
+        def record(inst, oi, handle):
+            seen[inst].append(oi)
+            return 0.0, 0.0, 0
+
+        X._walk(sequence, order, combo["y"], combo["z"], before, totals, 0.1, -1.0, record)
+        assert seen == steps
+    st = X._walk(sequence, order, "linear", "linear", {}, totals, 0.1, -1.0, _numpy_scan(files, order, 95.0, True))
+    assert st == gold["pool95_mins"]
+    st = X._walk(sequence, order, "linear", "log", {}, totals, 0.1, -1.0, _numpy_scan(files, order, 99.0, False))
+    assert st == gold["batch_extrema"]
+
+
+def json_copy(obj):
+    import json
+
+    return json.loads(json.dumps(obj))
+
+
+def test_pitch_angle_bits_closed_intervals():
+    from configurable_spectrograms_b200.fast.constants import DEFAULT_PITCH_ANGLE_CATEGORIES
+    from configurable_spectrograms_b200.fast.pipeline import pitch_angle_bits, zoom_window
+
+    pa = np.array([0.0, 30.0, 35.0, 40.0, 145.0, 150.0, 210.0, 330.0, 360.0, 365.0, np.nan, -3.0])
+    bits, keys = pitch_angle_bits(pa, DEFAULT_PITCH_ANGLE_CATEGORIES)
+    assert keys == ["all", "downgoing", "upgoing", "perpendicular"] or len(keys) == 4
+    g = {k: (bits >> i) & 1 for i, k in enumerate(keys)}
+    all_k, down, up, perp = (g[k] for k in keys)
+    assert list(all_k) == [1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0]
+    assert list(down) == [1, 1, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0]
+    assert list(up) == [0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0]
+    assert list(perp) == [0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0]  # 210 and 330 sit in two groups; 35 and 145 in none
+    assert zoom_window([], 6.25) is None
+    assert zoom_window([100.0], 6.25) == (100.0, 375.0)
+    assert zoom_window([100.0, 1100.0], 6.25) == (600.0, 1500.0)
