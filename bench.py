@@ -346,7 +346,8 @@ def main():
     value = total_orbits / (ms_step / 1e3)
 
     cube_bytes = 4 * total_elems
-    sums_bytes = sum(5 * f["T"] * E * 4 for f in files)
+    sums_bytes = sum(5 * f["T"] * E * 4 for f in files)  # algorithmic: (G+1)*T*E*s per file
+    fallbacks = shard.batch.stats_fallbacks()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -405,13 +406,14 @@ def main():
                 "pixels_per_gpu": shard.batch.n_pixels,
                 "l2_policy": f"inputs larger than L2 ({cube_bytes / 1e9:.1f} GB of cubes streamed per step)",
             },
-            "roofline": {"bound": "hbm", "kernel": "collapse_tpe_kernel<float,4>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "collapse_slab_kernel<float,4,1>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": k1_ms,
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
             "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
-                         "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3},
+                         "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,
+                         "percentile_regions_needing_radix_fallback": fallbacks},
         }
         print(json.dumps(line))
     if world > 1:

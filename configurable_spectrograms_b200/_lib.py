@@ -14,9 +14,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
+K1_GENERIC, K1_SLAB = 0, 1
 MAX_GROUPS = 7
 I_UNDER, I_OVER, I_BAD = 256, 257, 258
 NORM_OK, NORM_VMIN_GT_VMAX, NORM_INVALID = 0, 1, 2
@@ -102,7 +103,7 @@ PANEL_NORM = np.dtype(
     align=True,
 )
 POOL_ITEM = np.dtype(
-    [("mat_off", "<i8"), ("n_cells", "<i4"), ("E", "<i4"), ("inst", "<i4"), ("pos", "<i4")], align=True
+    [("mat_off", "<i8"), ("T", "<i4"), ("E", "<i4"), ("inst", "<i4"), ("pos", "<i4")], align=True
 )
 POOL_QUERY = np.dtype(
     [("inst", "<i4"), ("pos", "<i4"), ("slot", "<i4"), ("bin", "<i4"), ("rank", "<i8"), ("row_total", "<i8")],
@@ -148,11 +149,15 @@ SIGNATURES = {
     "csg_launch_count": (_i64, [_vp]),
     "csg_event_record": (_i, [_vp, _i]),
     "csg_event_sync": (_i, [_vp, _i]),
-    "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i]),
-    "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "csg_collapse_kernel": (_i, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp]),
+    "csg_slab_supported": (_i, [_i, _i, _i, _i]),
+    "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _i]),
+    "csg_sums_elems": (_i64, [C.c_int32, C.c_int32, _i]),
+    "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "csg_window_any": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "csg_region_stats_fallbacks": (_i, [_vp, _i, C.POINTER(_i)]),
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),

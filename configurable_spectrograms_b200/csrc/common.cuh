@@ -15,11 +15,14 @@ struct csg_ctx {
   cudaEvent_t ev_stop[32];
   cudaEvent_t ev_user[32];
   int64_t launches;
+  void* scratch;  // device scratch owned by the context (grow-only)
+  size_t scratch_bytes;
   char err[512];
 };
 
 extern char g_csg_err[512];
 int csg_fail(csg_ctx* ctx, int status, const char* fmt, ...);
+int csg_scratch(csg_ctx* ctx, size_t bytes, void** out);  // stats.cu
 
 #define CSG_CUDA(ctx, call)                                                                  \
   do {                                                                                       \

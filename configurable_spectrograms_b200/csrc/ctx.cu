@@ -79,6 +79,7 @@ void csg_destroy(csg_ctx* ctx) {
     cudaEventDestroy(ctx->ev_stop[i]);
     cudaEventDestroy(ctx->ev_user[i]);
   }
+  if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
 }

@@ -18,39 +18,92 @@ namespace {
 
 constexpr int kThreads = 256;
 
+constexpr int kSplit = 4;  // blocks per file: each takes a contiguous band of energy rows
+
+// Walk rows [e0, e1) of an energy-major [E][ld] matrix, warp per row, 128-bit loads (two in
+// flight); fn(v, in, e) is called with warp-uniform control flow, row_done(e) once per row.
+template <typename T, typename Fn, typename RowDone>
+__device__ __forceinline__ void walk_rows(const T* __restrict__ m, int ld, int nt, int e0, int e1, Fn&& fn,
+                                          RowDone&& row_done) {
+  constexpr int V = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int e = e0 + warp; e < e1; e += nw) {
+    const T* p = m + (long long)e * ld;  // 16-byte aligned: mat_off and ld are multiples of 4 elements
+    const int nvec = nt / V;
+    for (int i0 = 0; i0 < nvec; i0 += 64) {
+      const int ia = i0 + lane, ib = i0 + 32 + lane;
+      const bool ina = ia < nvec, inb = ib < nvec;
+      T a[V], b[V];
+      if constexpr (sizeof(T) == 4) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ra = ina ? __ldg(reinterpret_cast<const float4*>(p) + ia) : z;
+        const float4 rb = inb ? __ldg(reinterpret_cast<const float4*>(p) + ib) : z;
+        a[0] = ra.x, a[1] = ra.y, a[2] = ra.z, a[3] = ra.w;
+        b[0] = rb.x, b[1] = rb.y, b[2] = rb.z, b[3] = rb.w;
+      } else {
+        const double2 z = make_double2(0.0, 0.0);
+        const double2 ra = ina ? __ldg(reinterpret_cast<const double2*>(p) + ia) : z;
+        const double2 rb = inb ? __ldg(reinterpret_cast<const double2*>(p) + ib) : z;
+        a[0] = ra.x, a[1] = ra.y;
+        b[0] = rb.x, b[1] = rb.y;
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) fn(a[v], ina, e);
+      if (i0 + 32 < nvec) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) fn(b[v], inb, e);
+      }
+    }
+    const int done = nvec * V;
+    if (done < nt) {
+      const bool in = done + lane < nt;
+      fn(in ? __ldg(p + done + lane) : T(0), in, e);
+    }
+    row_done(e);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     pool_hist_first_kernel(const T* __restrict__ mats, const csg_pool_item* __restrict__ items, int max_pos,
                            int bits, int max_E, uint32_t* __restrict__ hist, int32_t* __restrict__ counts,
                            int32_t* __restrict__ npos) {
-  extern __shared__ unsigned s_mem[];
-  const int nb = 1 << bits;
-  unsigned* s_hist = s_mem;        // [nb]
-  unsigned* s_cnt = s_mem + nb;    // [E]
+  extern __shared__ unsigned s_hist[];  // [1 << bits]
   __shared__ unsigned s_red[32];
-  const csg_pool_item it = items[blockIdx.x];
-  for (int i = threadIdx.x; i < nb + it.E; i += kThreads) s_mem[i] = 0;
+  const int nb = 1 << bits;
+  const csg_pool_item it = items[blockIdx.x / kSplit];
+  const int part = blockIdx.x % kSplit;
+  const int per = (it.E + kSplit - 1) / kSplit;
+  const int e0 = part * per, e1 = min(it.E, e0 + per);
+  for (int i = threadIdx.x; i < nb; i += kThreads) s_hist[i] = 0;
   __syncthreads();
-  const T* m = mats + it.mat_off;
-  constexpr int kShiftBase = Key<T>::POS_BITS;
-  const int shift = kShiftBase - bits;
-  unsigned mine = 0;
-  for (int i = threadIdx.x; i < it.n_cells; i += kThreads) {
-    const T v = __ldg(m + i);
-    if (is_finite(v) && v > T(0)) {
-      ++mine;
-      atomicAdd(&s_hist[(unsigned)(Key<T>::bits(v) >> shift)], 1u);
-      atomicAdd(&s_cnt[i % it.E], 1u);
-    }
-  }
+  const int shift = Key<T>::POS_BITS - bits;
+  const int lane = threadIdx.x & 31;
+  unsigned mine = 0, row_count = 0;
+  int32_t* c = counts + (size_t)(blockIdx.x / kSplit) * max_E;
+  walk_rows<T>(
+      mats + it.mat_off, (it.T + 3) & ~3, it.T, e0, e1,
+      [&](T v, bool in, int) {
+        if (in && is_finite(v) && v > T(0)) {
+          ++row_count;
+          atomicAdd(&s_hist[(unsigned)(Key<T>::bits(v) >> shift)], 1u);
+        }
+      },
+      [&](int e) {  // per-energy positive count (CS/fast/extrema.py:260-264): the row belongs to this warp
+        const unsigned total = __reduce_add_sync(0xffffffffu, row_count);
+        if (lane == 0) c[e] = (int32_t)total;
+        mine += row_count;
+        row_count = 0;
+      });
   auto addu = [](unsigned a, unsigned b) { return a + b; };
   mine = block_reduce(mine, addu, 0u, s_red);
   __syncthreads();
   uint32_t* h = hist + ((size_t)it.inst * max_pos + it.pos) * nb;  // slot stride = 1 slot at level 0
-  for (int i = threadIdx.x; i < nb; i += kThreads) h[i] = s_hist[i];
-  int32_t* c = counts + (size_t)blockIdx.x * max_E;
-  for (int i = threadIdx.x; i < it.E; i += kThreads) c[i] = (int32_t)s_cnt[i];
-  if (threadIdx.x == 0) npos[blockIdx.x] = (int32_t)mine;
+  for (int i = threadIdx.x; i < nb; i += kThreads) {
+    const unsigned n = s_hist[i];
+    if (n) atomicAdd(&h[i], n);
+  }
+  if (threadIdx.x == 0 && mine) atomicAdd(&npos[blockIdx.x / kSplit], (int32_t)mine);
 }
 
 template <typename T>
@@ -60,29 +113,33 @@ __global__ void __launch_bounds__(kThreads)
                             int bits, uint32_t* __restrict__ hist) {
   typedef typename Key<T>::U U;
   __shared__ uint64_t s_pref[64];
-  const csg_pool_item it = items[blockIdx.x];
+  const csg_pool_item it = items[blockIdx.x / kSplit];
+  const int part = blockIdx.x % kSplit;
+  const int per = (it.E + kSplit - 1) / kSplit;
+  const int e0 = part * per, e1 = min(it.E, e0 + per);
   for (int i = threadIdx.x; i < n_slots; i += kThreads) s_pref[i] = slot_prefix[(size_t)it.inst * n_slots + i];
   __syncthreads();
-  const T* m = mats + it.mat_off;
+  // sorted ascending, padded with UINT64_MAX: the live prefixes span [first, last]
+  int live = 0;
+  while (live < n_slots && s_pref[live] != ~0ull) ++live;
+  if (live == 0) return;
+  const uint64_t first = s_pref[0], last = s_pref[live - 1];
   const int nb = 1 << bits;
   uint32_t* h = hist + ((size_t)it.inst * max_pos + it.pos) * (size_t)n_slots * nb;
-  for (int i = threadIdx.x; i < it.n_cells; i += kThreads) {
-    const T v = __ldg(m + i);
-    if (is_finite(v) && v > T(0)) {
-      const U k = Key<T>::bits(v);
-      const uint64_t hi = (uint64_t)(k >> prefix_shift);
-      // sorted ascending, padded with UINT64_MAX: binary search
-      int lo = 0, up = n_slots - 1;
-      while (lo < up) {
-        const int mid = (lo + up) >> 1;
-        if (s_pref[mid] < hi)
-          lo = mid + 1;
-        else
-          up = mid;
-      }
-      if (s_pref[lo] == hi) atomicAdd(&h[(size_t)lo * nb + ((unsigned)(k >> shift) & (unsigned)(nb - 1))], 1u);
-    }
-  }
+  walk_rows<T>(
+      mats + it.mat_off, (it.T + 3) & ~3, it.T, e0, e1,
+      [&](T v, bool in, int) {
+        if (!(in && is_finite(v) && v > T(0))) return;
+        const U k = Key<T>::bits(v);
+        const uint64_t hi = (uint64_t)(k >> prefix_shift);
+        if (hi < first || hi > last) return;  // almost every cell
+        for (int s = 0; s < live; ++s)
+          if (s_pref[s] == hi) {
+            atomicAdd(&h[(size_t)s * nb + ((unsigned)(k >> shift) & (unsigned)(nb - 1))], 1u);
+            break;
+          }
+      },
+      [](int) {});
 }
 
 // thread = one (inst, slot, bin) column; walk the instrument's files in orbit order
@@ -160,12 +217,14 @@ int csg_pool_hist_first(csg_ctx* ctx, const void* d_mats, int dtype, const csg_p
   if (n_items <= 0) return CSG_OK;
   if (bits < 1 || bits > 12) return csg_fail(ctx, CSG_ERR_ARG, "bits %d out of range (1..12)", bits);
   if (max_E <= 0 || max_E > 8192) return csg_fail(ctx, CSG_ERR_ARG, "max_E %d out of range", max_E);
-  const size_t smem = ((size_t)(1 << bits) + max_E) * sizeof(unsigned);
+  const size_t smem = (size_t)(1 << bits) * sizeof(unsigned);
+  CSG_CUDA(ctx, cudaMemsetAsync(d_npos, 0, (size_t)n_items * sizeof(int32_t), ctx->stream));
+  CSG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)n_items * max_E * sizeof(int32_t), ctx->stream));
   if (dtype == CSG_F32)
-    pool_hist_first_kernel<float><<<n_items, kThreads, smem, ctx->stream>>>((const float*)d_mats, d_items, max_pos, bits,
+    pool_hist_first_kernel<float><<<n_items * kSplit, kThreads, smem, ctx->stream>>>((const float*)d_mats, d_items, max_pos, bits,
                                                                             max_E, d_hist, d_counts, d_npos);
   else if (dtype == CSG_F64)
-    pool_hist_first_kernel<double><<<n_items, kThreads, smem, ctx->stream>>>((const double*)d_mats, d_items, max_pos,
+    pool_hist_first_kernel<double><<<n_items * kSplit, kThreads, smem, ctx->stream>>>((const double*)d_mats, d_items, max_pos,
                                                                              bits, max_E, d_hist, d_counts, d_npos);
   else
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
@@ -181,10 +240,10 @@ int csg_pool_hist_refine(csg_ctx* ctx, const void* d_mats, int dtype, const csg_
   if (n_slots < 1 || n_slots > 64) return csg_fail(ctx, CSG_ERR_ARG, "n_slots %d out of range (1..64)", n_slots);
   if (bits < 1 || bits > 12) return csg_fail(ctx, CSG_ERR_ARG, "bits %d out of range (1..12)", bits);
   if (dtype == CSG_F32)
-    pool_hist_refine_kernel<float><<<n_items, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_items, max_pos, n_slots,
+    pool_hist_refine_kernel<float><<<n_items * kSplit, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_items, max_pos, n_slots,
                                                                           d_slot_prefix, prefix_shift, shift, bits, d_hist);
   else if (dtype == CSG_F64)
-    pool_hist_refine_kernel<double><<<n_items, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_items, max_pos,
+    pool_hist_refine_kernel<double><<<n_items * kSplit, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_items, max_pos,
                                                                            n_slots, d_slot_prefix, prefix_shift, shift,
                                                                            bits, d_hist);
   else

@@ -222,18 +222,30 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   norms[i] = nm;
 }
 
-// One block = one (<=128 energies) x (32 time steps) tile of one panel.  Cells are read along the
-// energy axis (contiguous in the collapsed (T,E) matrix), mapped to their LUT index through the
-// panel's threshold table, transposed through shared memory and written along the time axis
-// (contiguous in the (E',T') image).  Work inside the tile is flattened so no lane idles on
-// the ragged energy count (74 of 96 channels survive the 0-4000 eV mask).
-constexpr int kTileT = 32;
-constexpr int kTileE = 128;
+// One block = kPixPerBlock consecutive pixels of one panel's (E', T') image.  The collapsed matrices
+// are energy-major, so consecutive pixels of an image row are consecutive cells of one matrix row:
+// reads and writes are both fully coalesced and there is no transpose.  Each cell is mapped to its
+// LUT index through the panel's threshold table: a fast float guess of the count, verified
+// against a 4-entry window of the exact thresholds (exact by construction).
+constexpr int kRasterThreads = 256;
+constexpr int kPixPerThread = 32;
+constexpr int kPixPerBlock = kRasterThreads * kPixPerThread;
 
 constexpr int kPad = 4;  // sentinels on both sides of the threshold row in shared memory
 
+__device__ __forceinline__ float fast_log2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // only a first guess: verified against the table
+  return r;
+}
+
+template <bool B>
+struct Flag {
+  static constexpr bool value = B;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRasterThreads, 4)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                      const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
                      const csg_panel_norm* __restrict__ norms, int n_panels, const T* __restrict__ thresholds,
@@ -241,98 +253,112 @@ __global__ void __launch_bounds__(256)
                      uint16_t* __restrict__ index) {
   __shared__ uint32_t s_lut[260];
   __shared__ T s_thr[kThr + 2 * kPad];  // [kPad + k] = thr[k]; -inf below, +inf above
-  __shared__ uint16_t s_idx[kTileE * (kTileT + 2)];
-  __shared__ int s_cols[kTileE];
-  __shared__ int s_rows[kTileT];
 
   const int tid = threadIdx.x;
-  // ---- which panel owns this block: 256-ary search over first_block, all threads probing
-  int lo = 0, len = n_panels;
-  while (len > 1) {
-    const int chunk = (len + 255) >> 8;
-    const int i = lo + tid * chunk;
-    const bool le = i < lo + len && __ldg(&panels[i].first_block) <= (int)blockIdx.x;
-    const int cnt = __syncthreads_count(le);  // probes are monotone: the first cnt are true
-    const int nlo = lo + (cnt - 1) * chunk;
-    len = min(chunk, lo + len - nlo);
-    lo = nlo;
+  // ---- which panel owns this block (every thread runs the same cached binary search)
+  int lo = 0, hi = n_panels - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
   const int pi = lo;
-  // every thread keeps its own copy of the few scalars it needs (broadcast loads)
-  const csg_panel pn = panels[pi];
-  const csg_region rg = regions[pn.region];
-  const int status = __ldg(&norms[pi].status);
-  const int degenerate = __ldg(&norms[pi].degenerate);
-  if (status != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
-  const T fill_lo = (T)__ldg(&norms[pi].fill_lo), fill_hi = (T)__ldg(&norms[pi].fill_hi);
-  const double t_vmin = __ldg(&norms[pi].t_vmin), t_range = __ldg(&norms[pi].t_range);
-  const bool log_scale = pn.log_scale != 0;
+  const csg_panel* pn = panels + pi;
+  const csg_region* rg = regions + __ldg(&pn->region);
+  const csg_panel_norm* nm = norms + pi;
+  if (__ldg(&nm->status) != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
+  const int degenerate = __ldg(&nm->degenerate);
+  const bool log_scale = __ldg(&pn->log_scale) != 0;
+  const unsigned nt = (unsigned)__ldg(&rg->nt);
+  const unsigned n_pix = (unsigned)__ldg(&rg->ne) * nt;
+  const unsigned first = (unsigned)((int)blockIdx.x - __ldg(&pn->first_block)) * kPixPerBlock;
+  const unsigned last = first + kPixPerBlock < n_pix ? first + kPixPerBlock : n_pix;
+  const long long out_off = __ldg(&pn->out_off);
+  uint32_t* out_rgba = rgba ? rgba + out_off : nullptr;
+  uint16_t* out_idx = index ? index + out_off : nullptr;
 
-  const int tiles_t = (rg.nt + kTileT - 1) / kTileT;
-  const int tile = (int)blockIdx.x - pn.first_block;
-  const int e0 = (tile / tiles_t) * kTileE, t0 = (tile % tiles_t) * kTileT;
-  const int ne_t = min(kTileE, rg.ne - e0), nt_t = min(kTileT, rg.nt - t0);
-  for (int i = tid; i < 259; i += 256) s_lut[i] = lut ? lut[i] : 0u;
-  for (int i = tid; i < kThr + 2 * kPad; i += 256) {
+  for (int i = tid; i < 259; i += kRasterThreads) s_lut[i] = lut ? lut[i] : 0u;
+  if (degenerate != 0) {
+    // vmin == vmax: every cell maps to index 0; NaN bound: every cell is "bad"
+    __syncthreads();
+    const int idx = degenerate == 1 ? 0 : I_BAD;
+    for (unsigned i = first + tid; i < last; i += kRasterThreads) {
+      if (out_rgba) out_rgba[i] = s_lut[idx];
+      if (out_idx) out_idx[i] = (uint16_t)idx;
+    }
+    return;
+  }
+  for (int i = tid; i < kThr + 2 * kPad; i += kRasterThreads) {
     const int k = i - kPad;
     s_thr[i] = k < 0 ? (T)(-CUDART_INF) : (k >= kThr ? (T)CUDART_INF : thresholds[(size_t)pi * kThrPitch + k]);
   }
-  for (int i = tid; i < ne_t; i += 256) s_cols[i] = __ldg(pool + rg.cols_off + e0 + i);
-  for (int i = tid; i < nt_t; i += 256) s_rows[i] = rg.rows_off < 0 ? rg.t0 + t0 + i : __ldg(pool + rg.rows_off + t0 + i);
   __syncthreads();
 
   // first guess of n = #{thresholds <= v} from fast float math; verified against the table
+  const double t_vmin = __ldg(&nm->t_vmin), t_range = __ldg(&nm->t_range);
   const float c1 = log_scale ? (float)(256.0 * 0.30102999566398120 / t_range) : (float)(256.0 / t_range);
   const float c0 = (float)(-256.0 * t_vmin / t_range) + 1.0f;
-
-  const int n_cells = ne_t * nt_t;
-  int tt = tid / ne_t, e = tid - tt * ne_t;
-  const int dt = 256 / ne_t, de = 256 - dt * ne_t;
-  const T* base = mats + rg.mat_off;
-  const int ld = rg.ld;
-  for (int i = tid; i < n_cells; i += 256) {
-    T v = __ldg(base + (long long)s_rows[tt] * ld + s_cols[e]);
-    // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
-    if (log_scale) {
-      v = (is_finite(v) && v > T(0)) ? v : fill_lo;
-    } else {
-      v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
-      v = (v == (T)CUDART_INF) ? fill_hi : v;
-    }
-    const float fv = (float)v;
-    float gf = (log_scale ? __log2f(fv) : fv) * c1 + c0;
-    gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
-    int n = (int)gf;
-    // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
-    const T* w = s_thr + (kPad - 2) + n;
-    const T a = w[0], b = w[1], c = w[2], d = w[3];
-    if (a <= v && !(d <= v)) {
-      n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
-    } else {  // rare: the float guess was off by more than one
+  const T fill_lo = (T)__ldg(&nm->fill_lo), fill_hi = (T)__ldg(&nm->fill_hi);
+  const T* mat = mats + __ldg(&rg->mat_off);
+  const int32_t* cols = pool + __ldg(&rg->cols_off);
+  const int rows_off = __ldg(&rg->rows_off);
+  const int32_t* rows = pool + (rows_off < 0 ? 0 : rows_off);
+  const int ld = __ldg(&rg->ld), t0 = __ldg(&rg->t0);
+  // the pixel loop, specialised on the scale and on how time steps are addressed (32-bit index math)
+  auto pixels = [&](auto log_c, auto rowlist_c) {
+    constexpr bool LOG = decltype(log_c)::value, ROWLIST = decltype(rowlist_c)::value;
+    unsigned i = first + tid;
+    unsigned j = i / nt, tt = i - j * nt;
+    const unsigned dq = kRasterThreads / nt, dr = kRasterThreads - dq * nt;
+    unsigned j_cached = ~0u, row_base = 0;
+#pragma unroll 2
+    for (; i < last; i += kRasterThreads) {
+      if (j != j_cached) {  // a new image row: its energy channel's matrix row
+        row_base = (unsigned)(__ldg(cols + j) * ld + (ROWLIST ? 0 : t0));
+        j_cached = j;
+      }
+      T v = __ldg(mat + (row_base + (ROWLIST ? (unsigned)__ldg(rows + tt) : tt)));
+      // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
+      if (LOG) {
+        v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+      } else {
+        v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
+        v = (v == (T)CUDART_INF) ? fill_hi : v;
+      }
+      const float fv = (float)v;
+      float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
+      gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
+      int n = (int)gf;
+      // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
+      const T a = s_thr[kPad - 2 + n], b = s_thr[kPad - 1 + n], c = s_thr[kPad + n], d = s_thr[kPad + 1 + n];
+      if (a <= v && !(d <= v)) {
+        n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
+      } else {  // rare: the float guess was off by more than one
 #pragma unroll 1
-      while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
+        while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
 #pragma unroll 1
-      while (n < kThr && s_thr[kPad + n] <= v) ++n;
+        while (n < kThr && s_thr[kPad + n] <= v) ++n;
+      }
+      int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
+      idx = is_nan(v) ? I_BAD : idx;
+      if (out_rgba) out_rgba[i] = s_lut[idx];
+      if (out_idx) out_idx[i] = (uint16_t)idx;
+      j += dq, tt += dr;
+      if (tt >= nt) tt -= nt, ++j;
     }
-    int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
-    idx = is_nan(v) ? I_BAD : idx;
-    idx = degenerate == 1 ? 0 : (degenerate == 2 ? I_BAD : idx);
-    s_idx[e * (kTileT + 2) + tt] = (uint16_t)idx;
-    e += de, tt += dt;
-    if (e >= ne_t) e -= ne_t, ++tt;
-  }
-  __syncthreads();
-  // ---- transposed write: consecutive lanes -> consecutive time steps of one energy row
-  int ee = tid / nt_t, t2 = tid - ee * nt_t;
-  const int dee = 256 / nt_t, dt2 = 256 - dee * nt_t;
-  const long long obase = pn.out_off + (long long)e0 * rg.nt + t0;
-  for (int i = tid; i < n_cells; i += 256) {
-    const uint16_t idx = s_idx[ee * (kTileT + 2) + t2];
-    const long long o = obase + (long long)ee * rg.nt + t2;
-    if (rgba) rgba[o] = s_lut[idx];
-    if (index) index[o] = idx;
-    t2 += dt2, ee += dee;
-    if (t2 >= nt_t) t2 -= nt_t, ++ee;
+  };
+  if (log_scale) {
+    if (rows_off < 0)
+      pixels(Flag<true>{}, Flag<false>{});
+    else
+      pixels(Flag<true>{}, Flag<true>{});
+  } else {
+    if (rows_off < 0)
+      pixels(Flag<false>{}, Flag<false>{});
+    else
+      pixels(Flag<false>{}, Flag<true>{});
   }
 }
 
@@ -342,7 +368,7 @@ extern "C" {
 
 int32_t csg_raster_blocks(int32_t ne, int32_t nt) {
   if (ne <= 0 || nt <= 0) return 0;
-  return ((ne + kTileE - 1) / kTileE) * ((nt + kTileT - 1) / kTileT);
+  return (int32_t)(((long long)ne * nt + kPixPerBlock - 1) / kPixPerBlock);
 }
 
 size_t csg_threshold_bytes(int n_panels, int dtype) {
@@ -382,11 +408,11 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
     return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
   if (dtype == CSG_F32)
-    rasterise_kernel<float><<<total_blocks, 256, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
+    rasterise_kernel<float><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
                                                                    d_norms, n_panels, (const float*)d_thresholds,
                                                                    (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else if (dtype == CSG_F64)
-    rasterise_kernel<double><<<total_blocks, 256, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
+    rasterise_kernel<double><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
                                                                     d_panels, d_norms, n_panels,
                                                                     (const double*)d_thresholds, (const uint32_t*)d_lut,
                                                                     (uint32_t*)d_rgba, d_index);

@@ -4,134 +4,246 @@
 // called at CS/fast/plotting.py:134,286 and CS/plotting.py:259) and the reductions
 // safe_vmin = nanmin(matrix[isfinite & > 0]) (CS/plotting.py:261-262), nanmin/nanmax (:314-315).
 //
-// One thread block per region.  Selection is an MSD radix select on the order-preserving key of
-// the dtype: a histogram pass per digit (11 bits), the bucket holding each wanted rank is
-// followed into the next digit; after the last digit the key IS the order statistic, so the
-// result is exact.  The two neighbours are then interpolated with numpy's float arithmetic
-// (q = D(p)/D(100); v = D(n-1)*q; lerp rounded after every operation -- SURVEY.md Appendix B).
+// A region is a set of energy rows x a time range of one energy-major collapsed matrix, so its
+// cells are contiguous runs.  One thread block per region, ONE pass over the cells:
 //
-// The first digit sees every cell: each warp owns a private histogram copy and the elected
-// lane of every distinct bin updates it with a plain read-modify-write (spectrogram counts
-// repeat heavily; shared-memory atomics on a handful of hot bins serialise).  Later digits
-// only touch the few cells inside the followed buckets and skip whole warps otherwise.
+//   sample   1024 strided cells are sorted in shared memory; for each wanted percentile two
+//            pivots bracket its quantile with a 4.5-sigma margin (pivots are sample VALUES, so
+//            heavy ties -- spectrogram counts repeat massively -- collapse a bracket onto the
+//            tied value instead of widening it)
+//   pass     every cell is classified (NaN / inf / positive, min / max reductions) and compared
+//            with the pivots: counts below / equal to each pivot; cells strictly inside a bracket
+//            are appended to a small shared-memory candidate list (warp-aggregated append)
+//   resolve  n is known now: numpy's rank arithmetic in D gives the two neighbour ranks of each
+//            percentile; a rank is answered by a pivot (tie counts) or by the sorted candidates.
+//
+// No per-cell atomics, no histogram.  The rare region whose rank escapes its bracket (or whose
+// candidates overflow) is flagged and redone by the multi-pass MSD radix select below, which is
+// exact for any input.  Interpolation is numpy's lerp rounded after every operation
+// (SURVEY.md Appendix B).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kSample = 4096;   // two-sided brackets at the 1st / 99th percentile need m*(1-q) > 4.5 sigma
+constexpr int kCand = 2048;     // candidate capacity per bracket (the lists reuse the sample's storage)
+static_assert(2 * kCand == kSample, "candidate lists alias the sample buffer");
+constexpr int kMaxCols = 1024;  // energy-row lists up to this length are staged in shared memory
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
-constexpr int kTargets = 4;     // (lo, hi) neighbours of two percentiles
-constexpr int kMaxCols = 1024;  // column lists up to this length are staged in shared memory
-static_assert(kWarps >= kTargets, "private copies are reused as target histograms");
+constexpr int kTargets = 4;  // (lo, hi) neighbours of two percentiles
 
-__device__ __forceinline__ void hist_add_private(unsigned* wh, unsigned bin, bool valid) {
-  const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (valid) {
-    const unsigned peers = __match_any_sync(act, bin);
-    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) wh[bin] += (unsigned)__popc(peers);
-  }
-  __syncwarp();
-}
-
-template <typename T, bool HEAVY>
-__global__ void __launch_bounds__(kThreads)
-    region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
-                        const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out) {
-  typedef typename Key<T>::U U;
-  extern __shared__ unsigned s_dyn[];  // HEAVY: [kWarps][kBins] private copies, later [kTargets][kBins]
-  __shared__ int s_cols[kMaxCols];
-  __shared__ long long s_ll[32];
-  __shared__ T s_t[32];
-  __shared__ unsigned s_u[32];
-  __shared__ U s_prefix[kTargets];
-  __shared__ long long s_rank[kTargets];
-  __shared__ int s_hidx[kTargets];
-
-  const csg_region rg = regions[blockIdx.x];
-  if (rg.want_pct != (HEAVY ? 1 : 0)) return;  // the other specialisation handles it / geometry only
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool cols_in_smem = rg.ne <= kMaxCols;
-  const int ne = rg.ne, nt = rg.nt;
-
-  if (HEAVY)
-    for (int i = tid; i < kWarps * kBins; i += kThreads) s_dyn[i] = 0;
-  if (cols_in_smem)
-    for (int i = tid; i < ne; i += kThreads) s_cols[i] = __ldg(pool + rg.cols_off + i);
-  __syncthreads();
-
-  // Walk the region warp-per-time-row (two rows in flight): lanes stride over the energy
-  // columns, which are (nearly) contiguous in the collapsed (T,E) matrix -> coalesced and
-  // division-free.  fn(v, in) is called with warp-uniform control flow.
-  auto for_each_cell = [&](auto&& fn) {
-    for (int r = warp; r < nt; r += 2 * kWarps) {
-      const int r2 = r + kWarps;
-      const bool two = r2 < nt;
-      const int rowa = rg.rows_off < 0 ? rg.t0 + r : __ldg(pool + rg.rows_off + r);
-      const int rowb = two ? (rg.rows_off < 0 ? rg.t0 + r2 : __ldg(pool + rg.rows_off + r2)) : rowa;
-      const T* pa = mats + rg.mat_off + (long long)rowa * rg.ld;
-      const T* pb = mats + rg.mat_off + (long long)rowb * rg.ld;
-      for (int c0 = 0; c0 < ne; c0 += 96) {
-        T va[3], vb[3];
-        bool in[3];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int c = c0 + u * 32 + lane;
-          in[u] = c < ne;
-          va[u] = vb[u] = T(0);
-          if (in[u]) {
-            const int col = cols_in_smem ? s_cols[c] : __ldg(pool + rg.cols_off + c);
-            va[u] = __ldg(pa + col);
-            vb[u] = __ldg(pb + col);
-          }
+template <typename U>
+__device__ void bitonic_sort(U* a, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_pow2; i += kThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const U x = a[i], y = a[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) a[i] = y, a[l] = x;
         }
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-          if (c0 + u * 32 < ne) {
-            fn(va[u], in[u]);
-            if (two) fn(vb[u], in[u]);
-          }
       }
     }
-  };
+  __syncthreads();
+}
 
-  // ---- pass 0: classification (+ first digit into the warp-private copy)
-  unsigned n_valid_w = 0, n_nan_w = 0, n_pos_w = 0, n_pinf_w = 0, n_ninf_w = 0;  // warp-uniform counters
+// Walk the region warp-per-energy-row.  fn(v, in) is called with warp-uniform control flow
+// (`in` = this lane holds a real cell), so it may use full-mask warp primitives.
+template <typename T, typename Fn>
+__device__ __forceinline__ void for_each_cell(const T* __restrict__ mats, const csg_region& rg,
+                                              const int32_t* __restrict__ pool, const int* s_cols, bool cols_in_smem,
+                                              Fn&& fn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* base = mats + rg.mat_off;
+  constexpr int V = 16 / sizeof(T);
+  for (int j = warp; j < rg.ne; j += kWarps) {
+    const int col = cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j);
+    const T* row = base + (long long)col * rg.ld;
+    const int nt = rg.nt;
+    if (rg.rows_off < 0) {
+      const T* p = row + rg.t0;
+      // peel to 16-byte alignment, vector body (two loads in flight), scalar tail
+      int head = (int)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(T));
+      if (head > nt) head = nt;
+      if (head > 0) {
+        const bool in = lane < head;
+        fn(in ? __ldg(p + lane) : T(0), in);
+      }
+      const int nvec = (nt - head) / V;
+      const T* pv = p + head;
+      for (int i0 = 0; i0 < nvec; i0 += 64) {
+        const int ia = i0 + lane, ib = i0 + 32 + lane;
+        const bool ina = ia < nvec, inb = ib < nvec;
+        T a[V], b[V];
+        if constexpr (sizeof(T) == 4) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 ra = ina ? __ldg(reinterpret_cast<const float4*>(pv) + ia) : z;
+          const float4 rb = inb ? __ldg(reinterpret_cast<const float4*>(pv) + ib) : z;
+          a[0] = (T)ra.x, a[1] = (T)ra.y, a[V - 2] = (T)ra.z, a[V - 1] = (T)ra.w;
+          b[0] = (T)rb.x, b[1] = (T)rb.y, b[V - 2] = (T)rb.z, b[V - 1] = (T)rb.w;
+        } else {
+          const double2 z = make_double2(0.0, 0.0);
+          const double2 ra = ina ? __ldg(reinterpret_cast<const double2*>(pv) + ia) : z;
+          const double2 rb = inb ? __ldg(reinterpret_cast<const double2*>(pv) + ib) : z;
+          a[0] = (T)ra.x, a[V - 1] = (T)ra.y;
+          b[0] = (T)rb.x, b[V - 1] = (T)rb.y;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) fn(a[v], ina);
+        if (i0 + 32 < nvec) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) fn(b[v], inb);
+        }
+      }
+      const int done = head + nvec * V;
+      if (done < nt) {  // fewer than V cells
+        const bool in = done + lane < nt;
+        fn(in ? __ldg(p + done + lane) : T(0), in);
+      }
+    } else {
+      for (int k0 = 0; k0 < nt; k0 += 32) {
+        const bool in = k0 + lane < nt;
+        fn(in ? __ldg(row + __ldg(pool + rg.rows_off + k0 + lane)) : T(0), in);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
+                        const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out,
+                        uint8_t* __restrict__ todo) {
+  typedef typename Key<T>::U U;
+  constexpr U KEY_MIN = 0;       // below the key of every non-NaN value (-inf maps above 0)
+  constexpr U KEY_MAX = ~(U)0;   // above the key of +inf
+  __shared__ U s_buf[kSample];  // the sorted sample, then (pivots taken) the two candidate lists
+  U* s_keys = s_buf;
+  U(*s_cand)[kCand] = reinterpret_cast<U(*)[kCand]>(s_buf);
+  __shared__ int s_ncand[2];
+  __shared__ int s_cols[kMaxCols];
+  __shared__ unsigned s_u[32];
+  __shared__ T s_t[32];
+  __shared__ U s_pivot[2][2];
+
+  const csg_region rg = regions[blockIdx.x];
+  if (threadIdx.x == 0) todo[blockIdx.x] = 0;
+  if (rg.want_pct == 2) return;  // geometry only
+  const bool pct = rg.want_pct == 1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool cols_in_smem = rg.ne <= kMaxCols;
+  const long long n_cells = (long long)rg.ne * rg.nt;
+
+  if (cols_in_smem)
+    for (int i = tid; i < rg.ne; i += kThreads) s_cols[i] = __ldg(pool + rg.cols_off + i);
+  if (tid < 2) s_ncand[tid] = 0;
+  __syncthreads();
+
+  // ---- brackets
+  const bool small = n_cells <= kCand;  // everything fits the candidate list: no sampling
+  if (pct && !small) {
+    // evenly spread sample positions (n_cells > kSample / 2, so neighbours may repeat a cell for
+    // regions below kSample cells: harmless, the sample only places the pivots)
+    for (int s = tid; s < kSample; s += kThreads) {
+      const long long cell = ((2 * (long long)s + 1) * n_cells) / (2 * kSample);
+      const int j = (int)(cell / rg.nt), k = (int)(cell - (long long)j * rg.nt);
+      const int col = cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j);
+      const int t = rg.rows_off < 0 ? rg.t0 + k : __ldg(pool + rg.rows_off + k);
+      const T v = __ldg(mats + rg.mat_off + (long long)col * rg.ld + t);
+      s_keys[s] = is_nan(v) ? KEY_MAX : Key<T>::key(v);  // NaN sorts to the end
+    }
+    bitonic_sort(s_keys, kSample);
+    if (tid < 2) {
+      int lo = 0, hi = kSample;  // valid sample size m: the NaN sentinels sit at the end
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_keys[mid] == KEY_MAX)
+          hi = mid;
+        else
+          lo = mid + 1;
+      }
+      const int m = lo;
+      const double q = (tid == 0 ? rg.p_lo : rg.p_hi) / 100.0;
+      U plo = KEY_MIN, phi = KEY_MAX;
+      if (m >= 16 && q >= 0.0 && q <= 1.0) {
+        const double centre = q * (m - 1);
+        const double delta = 4.5 * sqrt(m * q * (1.0 - q)) + 3.0;
+        const int a = (int)floor(centre - delta), b = (int)ceil(centre + delta);
+        if (a >= 0) plo = s_keys[a];
+        if (b < m) phi = s_keys[b];
+      }
+      s_pivot[tid][0] = plo, s_pivot[tid][1] = phi;
+    }
+    __syncthreads();  // pivots are out: the buffer becomes the candidate lists
+  } else if (tid < 2) {
+    s_pivot[tid][0] = KEY_MIN, s_pivot[tid][1] = KEY_MAX;
+  }
+  __syncthreads();
+  const U plo0 = s_pivot[0][0], phi0 = s_pivot[0][1], plo1 = s_pivot[1][0], phi1 = s_pivot[1][1];
+  const bool share = small;  // both percentiles read list 0
+
+  // ---- the pass
+  unsigned n_valid = 0, n_nan = 0, n_pos = 0, n_pinf = 0, n_ninf = 0;
+  unsigned lt0 = 0, eqlo0 = 0, eqhi0 = 0, lt1 = 0, eqlo1 = 0, eqhi1 = 0;
   const T kInf = (T)CUDART_INF;
   T min_pos = kInf, fin_min = kInf, fin_max = -kInf;
-  constexpr int kTopShift = Key<T>::BITS - kDigitBits;
-  unsigned* my_hist = HEAVY ? s_dyn + warp * kBins : nullptr;
-  for_each_cell([&](T v, bool in) {
+  auto append = [&](int b, U key, bool want) {  // warp-uniform call
+    const unsigned peers = __ballot_sync(0xffffffffu, want);
+    if (peers == 0u) return;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&s_ncand[b], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+      const int pos = base + __popc(peers & ((1u << lane) - 1u));
+      if (pos < kCand) s_cand[b][pos] = key;
+    }
+  };
+  for_each_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v, bool in) {
     const bool valid = in && !is_nan(v);
     const bool fin = valid && is_finite(v);
     const bool pos = v > T(0);
-    n_valid_w += __popc(__ballot_sync(0xffffffffu, valid));
-    n_nan_w += __popc(__ballot_sync(0xffffffffu, in && !valid));
-    n_pos_w += __popc(__ballot_sync(0xffffffffu, fin && pos));
-    const unsigned infs = __ballot_sync(0xffffffffu, valid && !fin);
-    if (infs) {  // rare
-      n_pinf_w += __popc(__ballot_sync(0xffffffffu, valid && !fin && pos));
-      n_ninf_w += __popc(__ballot_sync(0xffffffffu, valid && !fin && !pos));
-    }
+    n_valid += valid ? 1u : 0u;
+    n_nan += (in && !valid) ? 1u : 0u;
+    n_pos += (fin && pos) ? 1u : 0u;
+    n_pinf += (valid && !fin && pos) ? 1u : 0u;
+    n_ninf += (valid && !fin && !pos) ? 1u : 0u;
     const T f = fin ? v : kInf;
     fin_min = f < fin_min ? f : fin_min;
     const T g = fin ? v : -kInf;
     fin_max = g > fin_max ? g : fin_max;
     const T h = (fin && pos) ? v : kInf;
     min_pos = h < min_pos ? h : min_pos;
-    if (HEAVY) hist_add_private(my_hist, valid ? (unsigned)(Key<T>::key(v) >> kTopShift) : 0u, valid);
+    if (pct) {
+      const U k = Key<T>::key(v);
+      lt0 += (valid && k < plo0) ? 1u : 0u;
+      eqlo0 += (valid && k == plo0) ? 1u : 0u;
+      eqhi0 += (valid && k == phi0 && phi0 != plo0) ? 1u : 0u;
+      append(0, k, valid && k > plo0 && k < phi0);
+      if (!share) {
+        lt1 += (valid && k < plo1) ? 1u : 0u;
+        eqlo1 += (valid && k == plo1) ? 1u : 0u;
+        eqhi1 += (valid && k == phi1 && phi1 != plo1) ? 1u : 0u;
+        append(1, k, valid && k > plo1 && k < phi1);
+      }
+    }
   });
-  auto addll = [](long long a, long long b) { return a + b; };
+
   auto addu = [](unsigned a, unsigned b) { return a + b; };
   auto mint = [](T a, T b) { return a < b ? a : b; };
   auto maxt = [](T a, T b) { return a > b ? a : b; };
-  const bool lead = lane == 0;
-  const long long n_valid = block_reduce((long long)(lead ? n_valid_w : 0u), addll, 0ll, s_ll);
-  const unsigned n_nan = block_reduce(lead ? n_nan_w : 0u, addu, 0u, s_u);
-  const unsigned n_pos = block_reduce(lead ? n_pos_w : 0u, addu, 0u, s_u);
-  const unsigned n_pinf = block_reduce(lead ? n_pinf_w : 0u, addu, 0u, s_u);
-  const unsigned n_ninf = block_reduce(lead ? n_ninf_w : 0u, addu, 0u, s_u);
+  n_valid = block_reduce(n_valid, addu, 0u, s_u);
+  n_nan = block_reduce(n_nan, addu, 0u, s_u);
+  n_pos = block_reduce(n_pos, addu, 0u, s_u);
+  n_pinf = block_reduce(n_pinf, addu, 0u, s_u);
+  n_ninf = block_reduce(n_ninf, addu, 0u, s_u);
   min_pos = block_reduce(min_pos, mint, kInf, s_t);
   fin_min = block_reduce(fin_min, mint, kInf, s_t);
   fin_max = block_reduce(fin_max, maxt, (T)(-kInf), s_t);
@@ -141,24 +253,94 @@ __global__ void __launch_bounds__(kThreads)
   st.min_pos = (double)min_pos;
   st.fin_min = (double)fin_min;
   st.fin_max = (double)fin_max;
-  st.n_valid = n_valid;
+  st.n_valid = (long long)n_valid;
   st.n_nan = (int)n_nan, st.n_neginf = (int)n_ninf, st.n_posinf = (int)n_pinf, st.n_pos = (int)n_pos;
-
-  if (!HEAVY || n_valid == 0) {
+  if (!pct || n_valid == 0) {
     if (tid == 0) out[blockIdx.x] = st;
     return;
   }
-  unsigned(*s_hist)[kBins] = reinterpret_cast<unsigned(*)[kBins]>(s_dyn);
-  // fold the warp-private copies into histogram 0
-  __syncthreads();
-  for (int b = tid; b < kBins; b += kThreads) {
-    unsigned sum = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) sum += s_dyn[w * kBins + b];
-    s_dyn[b] = sum;  // thread b only ever touches column b of every copy
+  lt0 = block_reduce(lt0, addu, 0u, s_u);
+  eqlo0 = block_reduce(eqlo0, addu, 0u, s_u);
+  eqhi0 = block_reduce(eqhi0, addu, 0u, s_u);
+  if (!share) {
+    lt1 = block_reduce(lt1, addu, 0u, s_u);
+    eqlo1 = block_reduce(eqlo1, addu, 0u, s_u);
+    eqhi1 = block_reduce(eqhi1, addu, 0u, s_u);
   }
+  __syncthreads();
+  const int n0 = s_ncand[0], n1 = share ? n0 : s_ncand[1];
+  bool fail = n0 > kCand || n1 > kCand;
+  if (!fail) {
+    // sort the candidate lists (padded to a power of two with KEY_MAX, which is no value's key)
+    for (int b = 0; b < (share ? 1 : 2); ++b) {
+      const int n = b == 0 ? n0 : n1;
+      int np2 = 1;
+      while (np2 < n) np2 <<= 1;
+      for (int i = n + tid; i < np2; i += kThreads) s_cand[b][i] = KEY_MAX;
+      bitonic_sort(s_cand[b], np2);
+    }
+  }
+  if (tid == 0) {
+    long long rank[kTargets];
+    T gamma[2];
+    percentile_ranks<T>((long long)n_valid, rg.p_lo, rank[0], rank[1], gamma[0]);
+    percentile_ranks<T>((long long)n_valid, rg.p_hi, rank[2], rank[3], gamma[1]);
+    T val[kTargets];
+    for (int j = 0; j < kTargets && !fail; ++j) {
+      const int b = share ? 0 : (j >> 1);
+      const U plo = b == 0 ? plo0 : plo1, phi = b == 0 ? phi0 : phi1;
+      const long long below = b == 0 ? lt0 : lt1, at_lo = b == 0 ? eqlo0 : eqlo1, at_hi = b == 0 ? eqhi0 : eqhi1;
+      const long long inside = b == 0 ? n0 : n1;
+      long long r = rank[j];
+      U key = 0;
+      if (r < below) {
+        fail = true;
+      } else if ((r -= below) < at_lo) {
+        key = plo;
+      } else if ((r -= at_lo) < inside) {
+        key = s_cand[b][r];
+      } else if ((r -= inside) < at_hi) {
+        key = phi;
+      } else {
+        fail = true;
+      }
+      val[j] = Key<T>::val(key);
+    }
+    if (!fail) {
+      st.p_lo = (double)numpy_lerp<T>(val[0], val[1], gamma[0]);
+      st.p_hi = (double)numpy_lerp<T>(val[2], val[3], gamma[1]);
+    } else {
+      todo[blockIdx.x] = 1;  // redone exactly by region_select_kernel
+    }
+    out[blockIdx.x] = st;
+  }
+}
 
-  // ---- wanted ranks
+// ---------------------------------------------------------------------------------------------
+// Exact fallback: MSD radix select on the order-preserving key (a histogram pass per 11-bit digit,
+// the bucket holding each wanted rank is followed into the next digit).  Runs only for regions
+// flagged by region_stats_kernel (n_valid is already in `out`).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    region_select_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
+                         const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out,
+                         const uint8_t* __restrict__ todo) {
+  typedef typename Key<T>::U U;
+  if (!todo[blockIdx.x]) return;
+  __shared__ unsigned s_hist[kTargets][kBins];
+  __shared__ int s_cols[kMaxCols];
+  __shared__ long long s_ll[32];
+  __shared__ U s_prefix[kTargets];
+  __shared__ long long s_rank[kTargets];
+  __shared__ int s_hidx[kTargets];
+
+  const csg_region rg = regions[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool cols_in_smem = rg.ne <= kMaxCols;
+  if (cols_in_smem)
+    for (int i = tid; i < rg.ne; i += kThreads) s_cols[i] = __ldg(pool + rg.cols_off + i);
+  const long long n_valid = out[blockIdx.x].n_valid;
   long long rank[kTargets];
   T gamma[2];
   percentile_ranks<T>(n_valid, rg.p_lo, rank[0], rank[1], gamma[0]);
@@ -168,13 +350,41 @@ __global__ void __launch_bounds__(kThreads)
     s_rank[tid] = rank[tid];
     s_hidx[tid] = 0;
   }
-  __syncthreads();
-
-  // ---- digit loop
-  int shift = kTopShift;
-  int bits = kDigitBits;
-  while (true) {
+  int shift = Key<T>::BITS;
+  while (shift > 0) {
+    const int bits = shift < kDigitBits ? shift : kDigitBits;
+    const int prev_shift = shift;
+    shift -= bits;
+    const unsigned mask = (1u << bits) - 1u;
     const int nb = 1 << bits;
+    __syncthreads();
+    if (tid == 0) {  // one histogram per DISTINCT prefix (lo/hi neighbours usually share theirs)
+      for (int j = 0; j < kTargets; ++j) {
+        int h = j;
+        for (int i = 0; i < j; ++i)
+          if (s_prefix[i] == s_prefix[j]) {
+            h = s_hidx[i];
+            break;
+          }
+        s_hidx[j] = h;
+      }
+    }
+    for (int i = tid; i < kTargets * kBins; i += kThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const U p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
+    const bool u1 = s_hidx[1] == 1, u2 = s_hidx[2] == 2, u3 = s_hidx[3] == 3;
+    const bool first = prev_shift == Key<T>::BITS;
+    for_each_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v, bool in) {
+      if (!in || is_nan(v)) return;
+      const U k = Key<T>::key(v);
+      const U hi = first ? (U)0 : (U)(k >> (prev_shift & (Key<T>::BITS - 1)));
+      const unsigned b = (unsigned)(k >> shift) & mask;
+      if (hi == p0) atomicAdd(&s_hist[0][b], 1u);
+      if (u1 && hi == p1) atomicAdd(&s_hist[1][b], 1u);
+      if (u2 && hi == p2) atomicAdd(&s_hist[2][b], 1u);
+      if (u3 && hi == p3) atomicAdd(&s_hist[3][b], 1u);
+    });
+    __syncthreads();
     // locate each target's bucket in the histogram of its prefix
     for (int j = 0; j < kTargets; ++j) {
       const unsigned* h = s_hist[s_hidx[j]];
@@ -198,64 +408,46 @@ __global__ void __launch_bounds__(kThreads)
       if (want_rank >= excl && want_rank < excl + mine) {
         long long run = excl;
         for (int b = b0; b < b0 + per && b < nb; ++b) {
-          const long long c = h[b];
-          if (want_rank < run + c) {
+          const long long cnt = h[b];
+          if (want_rank < run + cnt) {
             s_prefix[j] = (s_prefix[j] << bits) | (U)b;
             s_rank[j] = want_rank - run;
             break;
           }
-          run += c;
+          run += cnt;
         }
       }
       __syncthreads();
     }
-    if (shift == 0) break;
-    // next digit: one histogram per DISTINCT prefix (lo/hi neighbours usually share theirs)
-    const int prev_shift = shift;
-    bits = shift < kDigitBits ? shift : kDigitBits;
-    shift -= bits;
-    const unsigned mask = (1u << bits) - 1u;
-    if (tid == 0) {
-      for (int j = 0; j < kTargets; ++j) {
-        int h = j;
-        for (int i = 0; i < j; ++i)
-          if (s_prefix[i] == s_prefix[j]) {
-            h = s_hidx[i];
-            break;
-          }
-        s_hidx[j] = h;
-      }
-    }
-    for (int i = tid; i < kTargets * kBins; i += kThreads) s_dyn[i] = 0;
-    __syncthreads();
-    const U p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
-    const bool u1 = s_hidx[1] == 1, u2 = s_hidx[2] == 2, u3 = s_hidx[3] == 3;
-    for_each_cell([&](T v, bool in) {
-      const U k = Key<T>::key(v);
-      const U hi = k >> prev_shift;
-      const bool valid = in && !is_nan(v);
-      const bool m0 = valid && hi == p0, m1 = u1 && valid && hi == p1, m2 = u2 && valid && hi == p2,
-                 m3 = u3 && valid && hi == p3;
-      if (__ballot_sync(0xffffffffu, m0 | m1 | m2 | m3) == 0u) return;  // nothing of this warp in a followed bucket
-      const unsigned b = (unsigned)(k >> shift) & mask;
-      if (m0) atomicAdd(&s_hist[0][b], 1u);
-      if (m1) atomicAdd(&s_hist[1][b], 1u);
-      if (m2) atomicAdd(&s_hist[2][b], 1u);
-      if (m3) atomicAdd(&s_hist[3][b], 1u);
-    });
-    __syncthreads();
   }
-
   if (tid == 0) {
     const T a0 = Key<T>::val(s_prefix[0]), b0 = Key<T>::val(s_prefix[1]);
     const T a1 = Key<T>::val(s_prefix[2]), b1 = Key<T>::val(s_prefix[3]);
-    st.p_lo = (double)numpy_lerp<T>(a0, b0, gamma[0]);
-    st.p_hi = (double)numpy_lerp<T>(a1, b1, gamma[1]);
-    out[blockIdx.x] = st;
+    out[blockIdx.x].p_lo = (double)numpy_lerp<T>(a0, b0, gamma[0]);
+    out[blockIdx.x].p_hi = (double)numpy_lerp<T>(a1, b1, gamma[1]);
   }
 }
 
 }  // namespace
+
+int csg_scratch(csg_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->scratch_bytes < bytes) {
+    if (ctx->scratch) {
+      CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      CSG_CUDA(ctx, cudaFree(ctx->scratch));
+      ctx->scratch = nullptr, ctx->scratch_bytes = 0;
+    }
+    const size_t want = bytes + bytes / 2 + 4096;
+    cudaError_t e = cudaMalloc(&ctx->scratch, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return csg_fail(ctx, CSG_ERR_NOMEM, "cudaMalloc(%zu) for scratch failed: %s", want, cudaGetErrorString(e));
+    }
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return CSG_OK;
+}
 
 extern "C" int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                                     int n_regions, const int32_t* d_index_pool, csg_region_stats* d_out) {
@@ -263,22 +455,42 @@ extern "C" int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype,
   if (n_regions <= 0) return CSG_OK;
   if (!d_mats || !d_regions || !d_index_pool || !d_out) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   if (dtype != CSG_F32 && dtype != CSG_F64) return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
-  // two specialisations over the same table (a block whose region belongs to the other one
-  // exits at once): percentile regions need the histogram machinery, the rest only reductions
-  const size_t heavy_smem = (size_t)kWarps * kBins * sizeof(unsigned);
+  void* todo = nullptr;
+  int st = csg_scratch(ctx, (size_t)n_regions, &todo);
+  if (st != CSG_OK) return st;
   if (dtype == CSG_F32) {
-    auto heavy = region_stats_kernel<float, true>;
-    cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem);
-    heavy<<<n_regions, kThreads, heavy_smem, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out);
-    CSG_LAUNCH_CHECK(ctx, "region_stats_kernel<heavy>");
-    region_stats_kernel<float, false><<<n_regions, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out);
+    region_stats_kernel<float><<<n_regions, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out,
+                                                                        (uint8_t*)todo);
+    CSG_LAUNCH_CHECK(ctx, "region_stats_kernel");
+    region_select_kernel<float><<<n_regions, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out,
+                                                                         (const uint8_t*)todo);
   } else {
-    auto heavy = region_stats_kernel<double, true>;
-    cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem);
-    heavy<<<n_regions, kThreads, heavy_smem, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool, d_out);
-    CSG_LAUNCH_CHECK(ctx, "region_stats_kernel<heavy>");
-    region_stats_kernel<double, false><<<n_regions, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool, d_out);
+    region_stats_kernel<double><<<n_regions, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
+                                                                         d_out, (uint8_t*)todo);
+    CSG_LAUNCH_CHECK(ctx, "region_stats_kernel");
+    region_select_kernel<double><<<n_regions, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
+                                                                          d_out, (const uint8_t*)todo);
   }
-  CSG_LAUNCH_CHECK(ctx, "region_stats_kernel<light>");
+  CSG_LAUNCH_CHECK(ctx, "region_select_kernel");
+  return CSG_OK;
+}
+
+// how many regions of the last csg_region_stats_run() needed the radix-select fallback (synchronises)
+extern "C" int csg_region_stats_fallbacks(csg_ctx* ctx, int n_regions, int* count) {
+  if (!ctx || !count) return CSG_ERR_ARG;
+  *count = 0;
+  if (n_regions <= 0 || !ctx->scratch || ctx->scratch_bytes < (size_t)n_regions) return CSG_OK;
+  unsigned char* h = (unsigned char*)malloc((size_t)n_regions);
+  if (!h) return csg_fail(ctx, CSG_ERR_NOMEM, "malloc(%d) failed", n_regions);
+  cudaError_t e = cudaMemcpyAsync(h, ctx->scratch, (size_t)n_regions, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    free(h);
+    return csg_fail(ctx, CSG_ERR_CUDA, "reading fallback flags failed: %s", cudaGetErrorString(e));
+  }
+  int n = 0;
+  for (int i = 0; i < n_regions; ++i) n += h[i] ? 1 : 0;
+  free(h);
+  *count = n;
   return CSG_OK;
 }

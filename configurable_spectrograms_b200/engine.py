@@ -7,7 +7,8 @@ one file; the FAST batch driver builds one batch per GPU shard.
 
 Data layout in HBM:
   cubes   one allocation, each file 256-byte aligned, dtype D
-  sums    per file [(G+1)][T][E] dtype D (group 0 = every pitch bin)
+  sums    per file [(G+1)][E][Tp] dtype D, energy-major (group 0 = every pitch bin; Tp = T
+          rounded up to a multiple of 4) -- the orientation imshow draws (matrix_plot = collapsed.T)
   flags   per file [T] uint8 (bit g: a non-NaN cell exists in row t of group g)
   pool    int32 column / row index lists shared by regions
   rgba / index   per panel [E'][T'] uint32 / uint16, row 0 = lowest energy
@@ -157,8 +158,9 @@ class Batch:
             "flags_off": self._flags_bytes,
             "bits_off": self._bits_len,
         }
+        f["Tp"] = (T + 3) // 4 * 4
         self._cube_bytes += _align(T * P * E * self.dtype.itemsize)
-        self._sums_elems += _align((self.G + 1) * T * E * self.dtype.itemsize) // self.dtype.itemsize
+        self._sums_elems += _align((self.G + 1) * E * f["Tp"] * self.dtype.itemsize) // self.dtype.itemsize
         self._flags_bytes += _align(T, 4)
         self._bits.append(bits)
         self._bits_len += P
@@ -182,28 +184,39 @@ class Batch:
         self._tables_dirty = True
 
     def _build_file_tables(self):
+        """One descriptor table per (storage layout, K1 kernel): a launch handles files of one kind."""
         lib = self.ctx.lib
         self.d_files = {}
-        for layout in (_lib.LAYOUT_TPE, _lib.LAYOUT_TEP):
-            idx = [i for i, f in enumerate(self.files) if f["layout"] == layout and f["T"] > 0]
-            if not idx:
+        groups: dict[tuple[int, int], list[int]] = {}
+        for i, f in enumerate(self.files):
+            if f["T"] <= 0:
                 continue
+            if f["device_ptr"] is None:
+                raise CsgError("cube not on the device: call upload_cubes() first")
+            kern = lib.csg_collapse_kernel(f["T"], f["P"], f["E"], self.code, f["layout"], f["device_ptr"])
+            groups.setdefault((f["layout"], kern), []).append(i)
+        # a slab table whose maxima cannot be staged falls back to the generic kernel as a whole
+        key = (_lib.LAYOUT_TPE, _lib.K1_SLAB)
+        if key in groups:
+            mp = max(self.files[i]["P"] for i in groups[key])
+            me = max(self.files[i]["E"] for i in groups[key])
+            if not lib.csg_slab_supported(mp, me, self.G, self.code):
+                groups.setdefault((_lib.LAYOUT_TPE, _lib.K1_GENERIC), []).extend(groups.pop(key))
+        for (layout, kern), idx in groups.items():
+            idx.sort()
             tab = np.zeros(len(idx), dtype=FILE_DESC)
-            blocks = 0
-            max_p = 1
+            blocks, max_p, max_e = 0, 1, 1
             for j, i in enumerate(idx):
                 f = self.files[i]
-                if f["device_ptr"] is None:
-                    raise CsgError("cube not on the device: call upload_cubes() first")
                 tab[j]["d_cube"] = f["device_ptr"]
                 tab[j]["sums_off"] = f["sums_off"]
                 tab[j]["flags_off"] = f["flags_off"]
                 tab[j]["T"], tab[j]["P"], tab[j]["E"] = f["T"], f["P"], f["E"]
                 tab[j]["bits_off"] = f["bits_off"]
                 tab[j]["first_block"] = blocks
-                blocks += lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout)
-                max_p = max(max_p, f["P"])
-            self.d_files[layout] = (self.ctx.to_device(tab), len(idx), blocks, max_p)
+                blocks += lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout, kern)
+                max_p, max_e = max(max_p, f["P"]), max(max_e, f["E"])
+            self.d_files[(layout, kern)] = (self.ctx.to_device(tab), len(idx), blocks, max_p, max_e)
         self.d_bits = self.ctx.to_device(np.concatenate(self._bits) if self._bits else np.zeros(1, np.uint8))
         if self.d_sums is None or self.d_sums.nbytes < self._sums_elems * self.dtype.itemsize:
             self.d_sums = self.ctx.alloc(max(self._sums_elems, 1) * self.dtype.itemsize)
@@ -212,30 +225,31 @@ class Batch:
         self._tables_dirty = False
 
     def collapse(self):
-        """K1 over every file (one launch per storage layout present)."""
+        """K1 over every file (one launch per storage layout / kernel present)."""
         if self._tables_dirty:
             self._build_file_tables()
         self.d_flags.zero()
-        for layout, (tab, n, blocks, max_p) in self.d_files.items():
+        for (layout, kern), (tab, n, blocks, max_p, max_e) in self.d_files.items():
             self.ctx._check(
                 self.ctx.lib.csg_collapse(
-                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr, self.G, max_p, self.code, layout,
+                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr, self.G, max_p, max_e, self.code, layout, kern,
                     self.d_sums.ptr, self.d_flags.ptr,
                 )
             )
 
     def mat_off(self, file: int, group: int) -> int:
+        """Element offset of the file's energy-major [E][Tp] matrix of one group in the sums buffer."""
         f = self.files[file]
-        return f["sums_off"] + group * f["T"] * f["E"]
+        return f["sums_off"] + group * f["E"] * f["Tp"]
 
     def sums(self, file: int, group: int = 0) -> np.ndarray:
-        """Download one collapsed (T,E) matrix."""
+        """Download one collapsed matrix in numpy's (T, E) orientation (``np.nansum(cube, axis=1)``)."""
         f = self.files[file]
         if f["T"] == 0:
             return np.zeros((0, f["E"]), dtype=self.dtype)
-        n = f["T"] * f["E"]
+        n = f["E"] * f["Tp"]
         a = self.d_sums.download(self.dtype, n, self.mat_off(file, group) * self.dtype.itemsize)
-        return a.reshape(f["T"], f["E"])
+        return np.ascontiguousarray(a.reshape(f["E"], f["Tp"])[:, : f["T"]].T)
 
     def all_flags(self) -> np.ndarray:
         return self.d_flags.download(np.uint8, self._flags_bytes)
@@ -286,7 +300,7 @@ class Batch:
             t0, nt = 0, len(rows)
         cols_off = self._pool_add(cols) if len(cols) else 0
         self._regions.append(
-            (self.mat_off(file, group), f["E"], t0, nt, rows_off, cols_off, len(cols), int(want_pct), 0, float(p_lo), float(p_hi))
+            (self.mat_off(file, group), f["Tp"], t0, nt, rows_off, cols_off, len(cols), int(want_pct), 0, float(p_lo), float(p_hi))
         )
         return len(self._regions) - 1
 
@@ -384,6 +398,12 @@ class Batch:
                 self.d_pool.ptr, self.d_stats.ptr,
             )
         )
+
+    def stats_fallbacks(self) -> int:
+        """Regions of the last run_stats() that needed the exact radix-select fallback."""
+        n = C.c_int(0)
+        self.ctx._check(self.ctx.lib.csg_region_stats_fallbacks(self.ctx.handle, len(self._regions), C.byref(n)))
+        return int(n.value)
 
     def stats(self) -> np.ndarray:
         if not self._regions:
@@ -512,9 +532,9 @@ def matrix_percentiles(matrix: np.ndarray, p_lo, p_hi, ctx: Context | None = Non
         return float("nan"), float("nan")
     d_m = ctx.to_device(flat)
     reg = np.zeros(1, dtype=REGION)
-    reg[0] = (0, n, 0, 1, -1, 0, n, 1, 0, float(p_lo), float(p_hi))
+    reg[0] = (0, n, 0, n, -1, 0, 1, 1, 0, float(p_lo), float(p_hi))  # one energy row holding every cell
     d_r = ctx.to_device(reg)
-    d_pool = ctx.to_device(np.arange(n, dtype=np.int32))
+    d_pool = ctx.to_device(np.zeros(1, dtype=np.int32))
     d_out = ctx.alloc(REGION_STATS.itemsize)
     ctx._check(ctx.lib.csg_region_stats_run(ctx.handle, d_m.ptr, np_dtype_code(flat.dtype), d_r.ptr, 1, d_pool.ptr, d_out.ptr))
     st = d_out.download(REGION_STATS, 1)[0]

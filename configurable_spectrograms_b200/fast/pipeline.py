@@ -339,7 +339,7 @@ class ShardPlan:
                 if file is None:
                     continue
                 f = self.batch.files[file]
-                rows.append((self.batch.mat_off(file, 0), f["T"] * f["E"], f["E"], ii, pos))
+                rows.append((self.batch.mat_off(file, 0), f["T"], f["E"], ii, pos))
                 owners.append((inst, oi, file))
                 pos += 1
             inst_len[ii] = pos

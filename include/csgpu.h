@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 2
+#define CSG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -97,7 +97,7 @@ CSG_API int csg_event_sync(csg_ctx* ctx, int slot);
  * np.any(~np.isnan(cube[window])) (CS/plotting.py:597-603). */
 typedef struct {
   const void* d_cube; /* device cube, dtype D, layout as given to csg_collapse()         */
-  int64_t sums_off;   /* element offset in d_sums of this file's [(G+1)][T][E] block    */
+  int64_t sums_off;   /* element offset in d_sums of this file's [(G+1)][E][Tp] block (multiple of 4) */
   int64_t flags_off;  /* byte offset in d_row_flags of this file's [T] flag bytes       */
   int32_t T, P, E;
   int32_t bits_off;    /* byte offset in d_pa_bits of this file's [P] membership bytes   */
@@ -105,18 +105,30 @@ typedef struct {
   int32_t reserved[3];
 } csg_file_desc; /* 56 bytes */
 
+/* Which kernel collapses a file: the slab kernel streams whole time steps of a C-contiguous
+ * (T,P,E) cube through shared memory with bulk asynchronous copies (TMA) and needs a 16-byte
+ * aligned cube whose energy rows are a multiple of 16 bytes; everything else takes the generic
+ * kernel.  A csg_collapse() call handles files of ONE kernel. */
+enum { CSG_K1_GENERIC = 0, CSG_K1_SLAB = 1 };
+CSG_API int csg_collapse_kernel(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube);
+/* 1 when the slab kernel can stage tables with these maxima (else route the table to GENERIC) */
+CSG_API int csg_slab_supported(int max_P, int max_E, int n_groups, int dtype);
 /* thread blocks csg_collapse() uses for one (T,P,E) file (for first_block) */
-CSG_API int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout);
+CSG_API int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout, int kernel);
+/* elements of one file's sums block: (n_groups+1) * E * Tp, Tp = T rounded up to a multiple of 4 */
+CSG_API int64_t csg_sums_elems(int32_t T, int32_t E, int n_groups);
 
-/* sums[file][0] = sum over every pitch bin; sums[file][1+g] = sum over bins p with
- * (d_pa_bits[bits_off+p] >> g) & 1.  NaN counts as +0, fill values and +-inf are
- * summed as-is, result dtype = D, summation order bit-identical to numpy's
- * (SURVEY.md Appendix B).  d_row_flags[flags_off+t] bit 0 / bit 1+g: some non-NaN
- * cell exists in row t among all / group-g pitch bins (any energy).
- * All files of one call share dtype, layout and n_groups. */
+/* sums are ENERGY-MAJOR -- the orientation of matrix_plot = collapsed.T (CS/plotting.py:236):
+ * sums[file][g][e][t] at sums_off + (g*E + e)*Tp + t; g = 0 is the sum over every pitch bin,
+ * g = 1+k the sum over bins p with (d_pa_bits[bits_off+p] >> k) & 1 (cells t >= T of a row
+ * are padding and never read).  NaN counts as +0, fill values and +-inf are summed as-is,
+ * result dtype = D, summation order bit-identical to numpy's.
+ * d_row_flags[flags_off+t] bit 0 / bit 1+k: some non-NaN cell exists in time row t among
+ * all / group-k pitch bins (any energy); zero it before the call.
+ * All files of one call share dtype, layout, kernel and n_groups. */
 CSG_API int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
-                 const uint8_t* d_pa_bits, int n_groups, int max_P, int dtype, int layout,
-                 void* d_sums, uint8_t* d_row_flags);
+                 const uint8_t* d_pa_bits, int n_groups, int max_P, int max_E, int dtype, int layout,
+                 int kernel, void* d_sums, uint8_t* d_row_flags);
 
 /* zoom_needed = np.any(~np.isnan(cube[window])) (CS/plotting.py:597-603) from the row flags:
  * d_out[w] = 1 iff some row of window w has bit `bit` set.  Rows are [t0, t0+nt) when
@@ -138,12 +150,12 @@ CSG_API int csg_collapse_host(csg_ctx* ctx, const void* h_cube, int32_t T, int32
 /* ------------------------------------------- K2a: region stats + percentiles */
 /* A region is the cell set of one energy-time matrix slice after the reference's
  * masks (CS/plotting.py:191-219, CS/fast/plotting.py:116-118,129-130,279-281):
- * output row j (energy, after the descending flip) = column d_index_pool[cols_off+j]
- * of the collapsed (T,E) matrix, output column i = row t0+i (rows_off < 0) or row
+ * output row j (energy, after the descending flip) = energy row d_index_pool[cols_off+j]
+ * of the energy-major [E][ld] matrix, output column i = time step t0+i (rows_off < 0) or
  * d_index_pool[rows_off+i]. */
 typedef struct {
-  int64_t mat_off; /* element offset of the (T,E) matrix in d_mats                */
-  int32_t ld;      /* elements between consecutive time rows (= E)                */
+  int64_t mat_off; /* element offset of the [E][ld] matrix in d_mats              */
+  int32_t ld;      /* elements between consecutive energy rows (= Tp)             */
   int32_t t0, nt;
   int32_t rows_off; /* -1: contiguous rows [t0, t0+nt)                             */
   int32_t cols_off;
@@ -165,6 +177,9 @@ typedef struct {
 
 CSG_API int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                          int n_regions, const int32_t* d_index_pool, csg_region_stats* d_out);
+/* Diagnostics: regions of the last run whose percentile ranks escaped the sampled brackets and
+ * were redone by the exact radix select (synchronises the stream). */
+CSG_API int csg_region_stats_fallbacks(csg_ctx* ctx, int n_regions, int* count);
 
 /* ------------------------------------------------------ K3: norm + colormap */
 /* One imshow panel (CS/plotting.py:276-287 log, :308-324 linear). */
@@ -225,8 +240,8 @@ CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg
  * (the reference recomputes nanpercentile(concat(blocks so far)) per step,
  * :280-285) are located digit by digit. */
 typedef struct {
-  int64_t mat_off; /* element offset of the file's total (T,E) matrix in d_mats (contiguous T*E) */
-  int32_t n_cells; /* T*E                                                                        */
+  int64_t mat_off; /* element offset of the file's total [E][Tp] matrix in d_mats (group 0)     */
+  int32_t T;       /* time steps; row pitch Tp = T rounded up to a multiple of 4                 */
   int32_t E;
   int32_t inst; /* instrument slot 0..n_inst-1                                                 */
   int32_t pos;  /* position of this file in its instrument's ascending-orbit sequence          */

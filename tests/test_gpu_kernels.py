@@ -169,6 +169,39 @@ def test_region_stats_match_numpy(ctx, dtype, integer):
         assert st[r]["n_posinf"] == np.isposinf(ref).sum() and st[r]["n_neginf"] == np.isneginf(ref).sum()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["counts", "continuous", "sparse"])
+def test_region_stats_tail_percentiles_take_the_single_pass(ctx, dtype, kind):
+    """FAST-sized panels at the default (1, 99): exact, and resolved inside the sampled brackets."""
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(21)
+    shape = (800, 4, 96)
+    if kind == "counts":
+        cube = rng.poisson(2.0, shape).astype(dtype)
+    elif kind == "continuous":
+        cube = rng.gamma(2.0, 50.0, shape).astype(dtype)
+    else:  # mostly zero counts: the 1st percentile sits on a massive tie
+        cube = (rng.poisson(0.02, shape) * rng.integers(1, 50, shape)).astype(dtype)
+    cube[rng.random(shape) < 0.01] = np.nan
+    b = Batch(ctx, dtype, 0)
+    f = b.add_file(cube)
+    b.upload_cubes()
+    b.collapse()
+    with np.errstate(invalid="ignore"):
+        m = np.nansum(cube, axis=1)
+    cases = [(np.arange(96)[::-1][11:85], 0, 800), (np.arange(96), 3, 797), (np.arange(10, 40), 100, 259)]
+    regs = [b.add_region(f, 0, cols, t0=t0, nt=nt, want_pct=True) for cols, t0, nt in cases]
+    b.upload_tables()
+    b.run_stats()
+    assert b.stats_fallbacks() == 0
+    st = b.stats()
+    for r, (cols, t0, nt) in zip(regs, cases):
+        ref = m[t0 : t0 + nt][:, cols].T
+        assert same_float(st[r]["p_lo"], float(np.nanpercentile(ref, 1)))
+        assert same_float(st[r]["p_hi"], float(np.nanpercentile(ref, 99)))
+
+
 def _lut():
     rng = np.random.default_rng(99)
     from oracle import restate as R
@@ -304,7 +337,7 @@ def test_pool_prefix_percentiles_exact(ctx, dtype, integer, selector):
     b.collapse()
     items = np.zeros(len(cubes), dtype=POOL_ITEM)
     for j, ((i, k), (f, c)) in enumerate(cubes.items()):
-        items[j] = (b.mat_off(f, 0), c.shape[0] * 96, 96, i, k)
+        items[j] = (b.mat_off(f, 0), c.shape[0], 96, i, k)
     inst_len = np.array([n_files - i for i in range(n_inst)], dtype=np.int32)
     reqs = [{"inst": i, "p": 99.0, "mode": "running_max"} for i in range(n_inst)]
     reqs += [{"inst": i, "p": 1, "mode": "last"} for i in range(n_inst)]
@@ -350,7 +383,7 @@ def test_device_selector_slot_overflow_falls_back(ctx):
     b.collapse()
     items = np.zeros(n_files, dtype=POOL_ITEM)
     for k, (f, c) in enumerate(files):
-        items[k] = (b.mat_off(f, 0), c.shape[0] * 8, 8, 0, k)
+        items[k] = (b.mat_off(f, 0), c.shape[0], 8, 0, k)
     inst_len = np.array([n_files], dtype=np.int32)
     ps = (10.0, 30.0, 50.0, 70.0, 90.0)
     reqs = [{"inst": 0, "p": p, "mode": "last"} for p in ps]  # whole-pool requests are never pruned
