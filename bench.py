@@ -406,7 +406,7 @@ def main():
                 "pixels_per_gpu": shard.batch.n_pixels,
                 "l2_policy": f"inputs larger than L2 ({cube_bytes / 1e9:.1f} GB of cubes streamed per step)",
             },
-            "roofline": {"bound": "hbm", "kernel": "collapse_slab_kernel<float,4,1>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "collapse_stream_kernel<float,4,384>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": k1_ms,
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},

@@ -14,10 +14,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
-K1_GENERIC, K1_SLAB = 0, 1
+K1_GENERIC, K1_STREAM = 0, 1
 MAX_GROUPS = 7
 I_UNDER, I_OVER, I_BAD = 256, 257, 258
 NORM_OK, NORM_VMIN_GT_VMAX, NORM_INVALID = 0, 1, 2
@@ -150,10 +150,10 @@ SIGNATURES = {
     "csg_event_record": (_i, [_vp, _i]),
     "csg_event_sync": (_i, [_vp, _i]),
     "csg_collapse_kernel": (_i, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp]),
-    "csg_slab_supported": (_i, [_i, _i, _i, _i]),
+    "csg_pitch_runs": (_i, [_vp, _i, _i, _vp, _vp]),
     "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _i]),
     "csg_sums_elems": (_i64, [C.c_int32, C.c_int32, _i]),
-    "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "csg_window_any": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),

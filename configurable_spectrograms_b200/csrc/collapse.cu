@@ -17,12 +17,13 @@
 //                (groups) the gather copies to C order, so the ascending-p chain again.
 //
 // Kernels
-//   collapse_slab_kernel   (TPE, the FAST shapes) one time step of a (T,P,E) cube is one contiguous
-//       P*E slab: every warp streams its time rows through a private ring of shared-memory
-//       stages filled by cp.async.bulk (TMA, mbarrier complete_tx) -- bytes in flight do not
-//       cost registers -- and walks the pitch axis in runs of constant group membership with a
-//       loop body specialised per membership mask; a CTA covers 16 time rows so the transposed
-//       result leaves as 64-byte row segments.
+//   collapse_stream_kernel (TPE, the FAST shapes) block = 16 time rows x all energy chunks; the pitch
+//       axis is walked in host-built runs of constant group membership with a loop body
+//       specialised per membership mask, eight 128-bit streaming loads in flight per thread;
+//       the transposed 16-row tile leaves through shared memory as 64-byte row segments.
+//       (A TMA variant -- per-warp rings of cp.async.bulk stages -- was measured slower: with
+//       24 of 32 lanes per energy row and per-stage bookkeeping it was issue-bound at 8-16
+//       warps per SM; see DESIGN.md.)
 //   collapse_tpe_kernel    (TPE, any shape/alignment) register-staged generic path.
 //   collapse_tep_kernel    (stored (T,E,P) view).
 #include <stdlib.h>
@@ -92,103 +93,61 @@ __device__ __forceinline__ void or_flag_byte(uint8_t* dst, unsigned fl) {
 }
 
 // ---------------------------------------------------------------------------------
-// TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS)
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy, completion counted in bytes on the mbarrier; the cube is read
-// exactly once, so it is marked evict-first in L2 (the sums written next should stay there)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-
-// ---------------------------------------------------------------------------------
-// slab kernel: persistent CTAs, one per SM, each owning a contiguous range of 16-row tiles.
-// Every warp streams ITS time rows (row w, w+W, ... of each tile) through a private ring of
-// shared-memory stages; lane 0 keeps the ring full with bulk copies that run ahead across
-// tile boundaries, all lanes consume.  A tile's transposed result is staged in shared
-// memory and leaves as 64-byte row segments.
+// stream kernel (TPE, the FAST shapes): block = 16 consecutive time rows x every energy chunk,
+// thread = (time row, VEC consecutive energies), all lanes busy.  The pitch axis is walked in
+// RUNS of constant group membership (host-built table: a handful per file) with a loop body
+// specialised per membership mask -- no per-bin predicate work, only the adds a bin needs --
+// eight 128-bit streaming loads in flight per thread.  Groups that contain every pitch bin are
+// not summed at all: they equal the unmasked total (same elements, same order) and are copied.
+// The transposed 16-row tile is staged in shared memory and leaves as 64-byte row segments.
 // ---------------------------------------------------------------------------------
 constexpr int kTileRows = 16;
 constexpr int kOutPitch = kTileRows + 1;
-constexpr int kSlabMaxWarps = 8;
 
-template <typename T, int V>
-struct LdsVec;
-template <>
-struct LdsVec<float, 4> {
-  static __device__ __forceinline__ void load(const float* p, float (&x)[4]) {
-    const float4 r = *reinterpret_cast<const float4*>(p);
-    x[0] = r.x, x[1] = r.y, x[2] = r.z, x[3] = r.w;
-  }
-};
-template <>
-struct LdsVec<double, 2> {
-  static __device__ __forceinline__ void load(const double* p, double (&x)[2]) {
-    const double2 r = *reinterpret_cast<const double2*>(p);
-    x[0] = r.x, x[1] = r.y;
-  }
-};
-
-// one run of pitch bins [p0, p1) of a staged chunk (row pitch E), constant membership MASK
-// (MASK < 0: membership read per bin from s_bits -- the generic body for more than 4 groups)
-template <typename T, int NG, int NJ, int MASK>
-__device__ __forceinline__ void slab_run(const T* __restrict__ stage, int p0, int p1, int E, int EV, int lane,
-                                         const uint8_t* __restrict__ s_bits, int p_base, unsigned keep,
-                                         T (&acc)[NJ][NG + 1][VecOf<T>::N], unsigned& flag) {
+template <typename T, int NG, int MASK>
+__device__ __forceinline__ void stream_run(const T* __restrict__ ptr, long long E, int p0, int p1,
+                                           const uint8_t* __restrict__ bits_p, unsigned keep,
+                                           T (&acc)[NG + 1][VecOf<T>::N], unsigned& flag) {
   constexpr int V = VecOf<T>::N;
+  constexpr int U = 8;
   bool any = false;
   unsigned any_bits = 0;
-#pragma unroll 4
-  for (int p = p0; p < p1; ++p) {
-    const unsigned bits = MASK < 0 ? (s_bits[p_base + p] & keep) : (unsigned)MASK;
-    bool row_ok = false;
+  auto one = [&](const Chunk<T, V>& x, int p) {
+    const unsigned bits = MASK < 0 ? (__ldg(bits_p + p) & keep) : (unsigned)MASK;
+    bool ok_any = false;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      // lanes past the last energy chunk redo the last one (results discarded): no divergence
-      const int c = min(lane + 32 * j, EV - 1);
-      T x[V];
-      LdsVec<T, V>::load(stage + (size_t)p * E + c * V, x);
+    for (int v = 0; v < V; ++v) {
+      const bool ok = !is_nan(x.v[v]);
+      const T z = ok ? x.v[v] : T(0);
+      ok_any |= ok;
+      acc[0][v] = add_rn(acc[0][v], z);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const bool ok = !is_nan(x[v]);
-        const T z = ok ? x[v] : T(0);
-        row_ok |= ok;
-        acc[j][0][v] = add_rn(acc[j][0][v], z);
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-          if ((bits >> g) & 1u) acc[j][g + 1][v] = add_rn(acc[j][g + 1][v], z);
-      }
+      for (int g = 0; g < NG; ++g)
+        if ((bits >> g) & 1u) acc[g + 1][v] = add_rn(acc[g + 1][v], z);
     }
-    any |= row_ok;
-    if (MASK < 0) any_bits |= row_ok ? ((bits << 1) | 1u) : 0u;
+    any |= ok_any;
+    if (MASK < 0) any_bits |= ok_any ? ((bits << 1) | 1u) : 0u;
+  };
+  int p = p0;
+  for (; p + U <= p1; p += U) {
+    Chunk<T, V> x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) load_chunk(x[u], ptr + (long long)(p + u) * E, true, V);
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(x[u], p + u);
+  }
+  if (p + 4 <= p1) {
+    Chunk<T, V> x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_chunk(x[u], ptr + (long long)(p + u) * E, true, V);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(x[u], p + u);
+    p += 4;
+  }
+  for (; p < p1; ++p) {
+    Chunk<T, V> x;
+    load_chunk(x, ptr + (long long)p * E, true, V);
+    one(x, p);
   }
   if (MASK < 0)
     flag |= any_bits;
@@ -196,194 +155,95 @@ __device__ __forceinline__ void slab_run(const T* __restrict__ stage, int p0, in
     flag |= any ? (((unsigned)MASK << 1) | 1u) : 0u;
 }
 
-template <typename T, int NG, int NJ>
-__global__ void __launch_bounds__(kSlabMaxWarps * 32, 1)
-    collapse_slab_kernel(const csg_file_desc* __restrict__ files, int n_files, int total_tiles,
-                         const uint8_t* __restrict__ pa_bits, int n_groups, T* __restrict__ sums,
-                         uint8_t* __restrict__ row_flags, int pc, int ns, int stage_elems, int max_P, int max_E) {
+template <typename T, int NG, int TPB>
+__global__ void __launch_bounds__(TPB, (TPB <= 512 ? 2 : 1))
+    collapse_stream_kernel(const csg_file_desc* __restrict__ files, int n_files, const int32_t* __restrict__ runs,
+                           const uint8_t* __restrict__ pa_bits, int n_groups, T* __restrict__ sums,
+                           uint8_t* __restrict__ row_flags) {
   constexpr int V = VecOf<T>::N;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int W = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EV = TPB / kTileRows;  // energy chunks per row
+  constexpr int E = EV * V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_out = reinterpret_cast<T*>(smem_raw);  // [(NG+1)][E][kOutPitch]
+  __shared__ unsigned s_flags[kTileRows];
 
-  // carve shared memory: stages | output tile | barriers | runs | membership bytes
-  T* s_stage = reinterpret_cast<T*>(smem_raw);
-  size_t off = (size_t)W * ns * stage_elems * sizeof(T);
-  T* s_out = reinterpret_cast<T*>(smem_raw + off);
-  off += (size_t)(NG + 1) * max_E * kOutPitch * sizeof(T);
-  off = (off + 7) & ~size_t(7);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + off);
-  off += (size_t)W * ns * sizeof(uint64_t);
-  int* s_runs = reinterpret_cast<int*>(smem_raw + off);  // {p0, p1, mask} triples; [3*max_P] = count, [+1] = alias
-  off += (size_t)(3 * max_P + 2) * sizeof(int);
-  uint8_t* s_bits = smem_raw + off;
-
-  if (threadIdx.x < W * ns) mbar_init(&s_bar[threadIdx.x], 1);
-  if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const int fi = find_file(files, n_files, blockIdx.x);
+  const csg_file_desc f = files[fi];
+  const int t0 = (blockIdx.x - f.first_block) * kTileRows;
+  const int rows_here = min(kTileRows, f.T - t0);
+  const int r = threadIdx.x / EV, c = threadIdx.x - r * EV;
+  if (threadIdx.x < kTileRows) s_flags[threadIdx.x] = 0;
   __syncthreads();
 
-  T* my_stage = s_stage + (size_t)warp * ns * stage_elems;
-  uint64_t* my_bar = s_bar + warp * ns;
-  uint64_t policy = 0;
-  if (lane == 0) policy = policy_evict_first();
-  unsigned ring = 0;  // stages this warp has consumed since the kernel started (slot / parity of the ring)
-
-  // this CTA's contiguous range of tiles
-  const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-  int tile = blockIdx.x * per_cta;
-  const int tile_end = min(total_tiles, tile + per_cta);
-
-  while (tile < tile_end) {
-    const int fi = find_file(files, n_files, tile);
-    const csg_file_desc f = files[fi];
-    const int P = f.P, E = f.E, EV = E / V;
-    const int file_tile0 = tile - f.first_block;
-    const int file_tiles = (f.T + kTileRows - 1) / kTileRows;
-    const int n_seg = min(tile_end - tile, file_tiles - file_tile0);  // tiles of this file in this CTA
-
-    // ---- per-file tables: membership bytes, runs of constant membership, groups that hold every bin
-    __syncthreads();
-    for (int p = threadIdx.x; p < P; p += blockDim.x) s_bits[p] = NG ? pa_bits[f.bits_off + p] : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned all = 0xffu;
-      for (int p = 0; p < P; ++p) all &= s_bits[p];
-      int n = 0, start = 0;
-      for (int p = 1; p <= P; ++p)
-        if (p == P || s_bits[p] != s_bits[start]) {
-          s_runs[3 * n] = start, s_runs[3 * n + 1] = p, s_runs[3 * n + 2] = s_bits[start] & ~all;
-          ++n, start = p;
-        }
-      s_runs[3 * max_P] = n;
-      s_runs[3 * max_P + 1] = (int)all;  // these groups equal the unmasked total: copied, not summed
-    }
-    __syncthreads();
-    const int n_runs = s_runs[3 * max_P];
-    const unsigned alias = (unsigned)s_runs[3 * max_P + 1];
-    const unsigned keep = ~alias;
-
-    const int n_ch = (P + pc - 1) / pc;  // stages per time row
-    const int nfull = (kTileRows - warp + W - 1) / W;  // this warp's rows in a full tile
-    auto rows_in = [&](int kk) {  // this warp's rows in tile kk of the segment (only a file's last tile is short)
-      const int here = min(kTileRows, f.T - (file_tile0 + kk) * kTileRows);
-      return warp < here ? (here - warp + W - 1) / W : 0;
-    };
-    const int total = (nfull * (n_seg - 1) + rows_in(n_seg - 1)) * n_ch;
-    const T* cube = static_cast<const T*>(f.d_cube);
-
-    auto issue = [&](int q) {  // lane 0: arm the stage's barrier and start its bulk copy
-      const int ri = q / n_ch, ch = q - ri * n_ch;
-      const int kk = ri / nfull, i = ri - kk * nfull;
-      const int t = (file_tile0 + kk) * kTileRows + warp + W * i;
-      const int pcn = min(pc, P - ch * pc);
-      const unsigned bytes = (unsigned)((size_t)pcn * E * sizeof(T));
-      const unsigned slot = (ring + (unsigned)q) % (unsigned)ns;
-      mbar_expect_tx(&my_bar[slot], bytes);
-      bulk_g2s(my_stage + (size_t)slot * stage_elems, cube + ((size_t)t * P + (size_t)ch * pc) * E, bytes, &my_bar[slot],
-               policy);
-    };
-    if (lane == 0)
-      for (int q = 0; q < ns - 1 && q < total; ++q) issue(q);
-
-    int s = 0;  // stages consumed in this segment
-    for (int kk = 0; kk < n_seg; ++kk) {
-      const int t_base = (file_tile0 + kk) * kTileRows;
-      const int rows_here = min(kTileRows, f.T - t_base);
-      const int n_i = rows_in(kk);
-      for (int i = 0; i < n_i; ++i) {
-        T acc[NJ][NG + 1][V];
+  const unsigned alias = (unsigned)f.reserved[2];  // groups holding every pitch bin
+  if (r < rows_here) {
+    const T* ptr = static_cast<const T*>(f.d_cube) + ((long long)(t0 + r) * f.P) * E + c * V;
+    const int32_t* run = runs + 3 * (long long)f.reserved[0];
+    const int n_runs = f.reserved[1];
+    const uint8_t* bits_p = pa_bits + f.bits_off;
+    T acc[NG + 1][V];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j)
+    for (int g = 0; g <= NG; ++g)
 #pragma unroll
-          for (int g = 0; g <= NG; ++g)
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[j][g][v] = T(0);
-        unsigned flag = 0;
-        for (int ch = 0; ch < n_ch; ++ch, ++s) {
-          if (lane == 0 && s + ns - 1 < total) issue(s + ns - 1);  // its slot was drained in the previous iteration
-          const unsigned g = ring + (unsigned)s;
-          const unsigned slot = g % (unsigned)ns;
-          mbar_wait(&my_bar[slot], (g / (unsigned)ns) & 1u);
-          const T* stage = my_stage + (size_t)slot * stage_elems;
-          const int p_lo = ch * pc, p_hi = min(P, p_lo + pc);
-          for (int r = 0; r < n_runs; ++r) {
-            const int a = max(s_runs[3 * r], p_lo), b = min(s_runs[3 * r + 1], p_hi);
-            if (a >= b) continue;
-            const int mask = s_runs[3 * r + 2];
-            const int a0 = a - p_lo, b0 = b - p_lo;
-            if (NG == 4) {
-              switch (mask & 15) {
-#define CSG_RUN(M)                                                                      \
-  case M:                                                                               \
-    slab_run<T, NG, NJ, M>(stage, a0, b0, E, EV, lane, s_bits, p_lo, keep, acc, flag);  \
+      for (int v = 0; v < V; ++v) acc[g][v] = T(0);
+    unsigned flag = 0;
+    for (int k = 0; k < n_runs; ++k) {
+      const int p0 = __ldg(run + 3 * k), p1 = __ldg(run + 3 * k + 1), mask = __ldg(run + 3 * k + 2);
+      if (NG == 4) {
+        switch (mask & 15) {
+#define CSG_RUN(M)                                                         \
+  case M:                                                                  \
+    stream_run<T, NG, M>(ptr, E, p0, p1, bits_p, ~alias, acc, flag);       \
     break;
-                CSG_RUN(0)
-                CSG_RUN(1)
-                CSG_RUN(2)
-                CSG_RUN(3)
-                CSG_RUN(4)
-                CSG_RUN(5)
-                CSG_RUN(6)
-                CSG_RUN(7)
-                CSG_RUN(8)
-                CSG_RUN(9)
-                CSG_RUN(10)
-                CSG_RUN(11)
-                CSG_RUN(12)
-                CSG_RUN(13)
-                CSG_RUN(14)
-                CSG_RUN(15)
+          CSG_RUN(0)
+          CSG_RUN(1)
+          CSG_RUN(2)
+          CSG_RUN(3)
+          CSG_RUN(4)
+          CSG_RUN(5)
+          CSG_RUN(6)
+          CSG_RUN(7)
+          CSG_RUN(8)
+          CSG_RUN(9)
+          CSG_RUN(10)
+          CSG_RUN(11)
+          CSG_RUN(12)
+          CSG_RUN(13)
+          CSG_RUN(14)
+          CSG_RUN(15)
 #undef CSG_RUN
-              }
-            } else if (NG == 0) {
-              slab_run<T, NG, NJ, 0>(stage, a0, b0, E, EV, lane, s_bits, p_lo, keep, acc, flag);
-            } else {
-              slab_run<T, NG, NJ, -1>(stage, a0, b0, E, EV, lane, s_bits, p_lo, keep, acc, flag);
-            }
-          }
-          __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
         }
-        // ---- the row is complete: groups that hold every bin copy the total
-        const int row = warp + W * i;
-        if (flag & 1u) flag |= alias << 1;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int c = lane + 32 * j;
-          if (c < EV) {
-#pragma unroll
-            for (int g = 0; g <= NG; ++g) {
-              const bool copy = g > 0 && ((alias >> (g - 1)) & 1u);
-#pragma unroll
-              for (int v = 0; v < V; ++v)
-                s_out[((size_t)g * E + c * V + v) * kOutPitch + row] = copy ? acc[j][0][v] : acc[j][g][v];
-            }
-          }
-        }
-        const unsigned fl = __reduce_or_sync(0xffffffffu, flag);
-        if (lane == 0 && row_flags != nullptr) row_flags[f.flags_off + t_base + row] = (uint8_t)fl;  // sole owner
+      } else if (NG == 0) {
+        stream_run<T, NG, 0>(ptr, E, p0, p1, bits_p, ~alias, acc, flag);
+      } else {
+        stream_run<T, NG, -1>(ptr, E, p0, p1, bits_p, ~alias, acc, flag);
       }
-      __syncthreads();
-      // ---- transposed tile -> sums[g][e][t_base .. t_base+rows_here): 64-byte segments
-      {
-        const int Tp = pitch_of(f.T);
-        const long long plane = (long long)E * Tp;
-        T* out = sums + f.sums_off + t_base;
-        const int r = threadIdx.x & (kTileRows - 1);
-        const int step = blockDim.x / kTileRows;
-        const int n_ge = (n_groups + 1) * E;
-        int ge = threadIdx.x / kTileRows;
-        int g = ge / E, e = ge - g * E;
-        for (; ge < n_ge; ge += step) {
-          if (r < rows_here) out[g * plane + (long long)e * Tp + r] = s_out[(size_t)ge * kOutPitch + r];
-          e += step;
-          while (e >= E) e -= E, ++g;
-        }
-      }
-      __syncthreads();
     }
-    ring += (unsigned)total;
-    tile += n_seg;
+    if (flag & 1u) flag |= alias << 1;
+#pragma unroll
+    for (int g = 0; g <= NG; ++g) {
+      const bool copy = g > 0 && ((alias >> (g - 1)) & 1u);
+#pragma unroll
+      for (int v = 0; v < V; ++v) s_out[((size_t)g * E + c * V + v) * kOutPitch + r] = copy ? acc[0][v] : acc[g][v];
+    }
+    if (flag) atomicOr(&s_flags[r], flag);
   }
+  __syncthreads();
+  // ---- transposed tile -> sums[g][e][t0 .. t0+rows_here): 64-byte segments
+  const int Tp = pitch_of(f.T);
+  const long long plane = (long long)E * Tp;
+  T* out = sums + f.sums_off + t0;
+  const int rr = threadIdx.x & (kTileRows - 1);
+  constexpr int step = TPB / kTileRows;
+  const int n_ge = (n_groups + 1) * E;
+  if (rr < rows_here) {
+    for (int ge = threadIdx.x / kTileRows; ge < n_ge; ge += step) {
+      const int g = ge / E, e = ge - g * E;  // E is a compile-time constant
+      out[g * plane + (long long)e * Tp + rr] = s_out[(size_t)ge * kOutPitch + rr];
+    }
+  }
+  if (row_flags != nullptr && threadIdx.x < rows_here)
+    row_flags[f.flags_off + t0 + threadIdx.x] = (uint8_t)s_flags[threadIdx.x];  // the block owns these rows
 }
 
 // ---------------------------------------------------------------------------------
@@ -470,7 +330,7 @@ __global__ void __launch_bounds__(kBlock)
       }
     }
 
-    // energy-major output: element (e, t) at e*Tp + t (uncoalesced here; the slab kernel is the fast path)
+    // energy-major output: element (e, t) at e*Tp + t (uncoalesced here; the stream kernel is the fast path)
     const int Tp = pitch_of(f.T);
     const long long plane = (long long)E * Tp;
     T* out = sums + f.sums_off + t;
@@ -631,47 +491,20 @@ inline int tep_rows_per_block(int P, int dtype) {
   return rows;
 }
 
-// ---- slab kernel configuration: warps per CTA, pitch bins per stage, stages per warp, shared memory
-struct SlabCfg {
-  int warps, pc, ns, stage_elems, nj;
-  size_t smem;
-  bool ok;
-};
-inline SlabCfg slab_config(int max_P, int max_E, int n_groups, int dtype) {
-  SlabCfg c{};
-  const size_t es = dtype == CSG_F64 ? 8 : 4;
-  const int V = (int)(16 / es);
-  c.ok = false;
-  if (max_E % V != 0 || max_P <= 0 || max_E <= 0) return c;
-  c.nj = (max_E / V + 31) / 32;
-  if (c.nj > 3) return c;
-  const int NG = n_groups == 0 ? 0 : (n_groups <= 4 ? 4 : CSG_MAX_GROUPS);
-  const size_t fixed = (size_t)(NG + 1) * max_E * kOutPitch * es + 16 + (size_t)(3 * max_P + 2) * 4 + max_P + 64;
-  const size_t budget = 224 * 1024;  // one persistent CTA per SM
-  const size_t row = (size_t)max_E * es;
-  int warps = 8, ns = 3;
-  int pc = (int)(6144 / row);  // about 6 KB per stage
-  if (pc < 1) pc = 1;
-  if (pc > max_P) pc = max_P;
-  // tuning overrides (scripts/k1_sweep.py)
-  if (const char* e = getenv("CSG_SLAB_W")) warps = atoi(e) >= 1 && atoi(e) <= kSlabMaxWarps ? atoi(e) : warps;
-  if (const char* e = getenv("CSG_SLAB_PC")) pc = atoi(e) > 0 ? (atoi(e) < max_P ? atoi(e) : max_P) : pc;
-  if (const char* e = getenv("CSG_SLAB_NS")) ns = atoi(e) >= 2 ? atoi(e) : ns;
-  auto total = [&](int pc_, int ns_) { return fixed + (size_t)warps * ns_ * (pc_ * row + 8); };
-  while (total(pc, ns) > budget && pc > 1) pc = (pc + 1) / 2;
-  if (total(pc, ns) > budget) ns = 2;
-  if (total(pc, ns) > budget) return c;
-  c.warps = warps, c.pc = pc, c.ns = ns, c.stage_elems = (int)(pc * (size_t)max_E), c.smem = total(pc, ns), c.ok = true;
-  return c;
+// ---- stream kernel eligibility: 16 x (E / VEC) threads per block must be a supported block size
+inline int stream_tpb(int E, int dtype) {
+  const int V = dtype == CSG_F64 ? 2 : 4;
+  if (E <= 0 || E % V != 0) return 0;
+  const int tpb = kTileRows * (E / V);
+  return (tpb == 256 || tpb == 384 || tpb == 512 || tpb == 768 || tpb == 1024) ? tpb : 0;
 }
-
-inline bool slab_file_ok(int32_t T, int32_t P, int32_t E, int dtype, const void* d_cube) {
-  const size_t es = dtype == CSG_F64 ? 8 : 4;
-  const int V = (int)(16 / es);
-  if (T <= 0 || P <= 0 || E % V != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(d_cube) & 15) != 0) return false;
-  if ((E / V + 31) / 32 > 3) return false;
-  return true;
+inline size_t stream_smem(int E, int n_groups, int dtype) {
+  const int NG = n_groups == 0 ? 0 : (n_groups <= 4 ? 4 : CSG_MAX_GROUPS);
+  return (size_t)(NG + 1) * E * kOutPitch * (dtype == CSG_F64 ? 8 : 4);
+}
+inline bool stream_file_ok(int32_t T, int32_t P, int32_t E, int dtype, const void* d_cube) {
+  if (T <= 0 || P <= 0 || stream_tpb(E, dtype) == 0) return false;
+  return (reinterpret_cast<uintptr_t>(d_cube) & 15) == 0;
 }
 
 template <typename T>
@@ -691,39 +524,49 @@ int launch_tpe(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int tota
   return CSG_OK;
 }
 
-template <typename T, int NG>
-int launch_slab_nj(csg_ctx* ctx, const SlabCfg& c, const csg_file_desc* d_files, int n_files, int total_blocks,
-                   const uint8_t* d_pa_bits, int n_groups, int max_P, int max_E, T* d_sums, uint8_t* d_row_flags) {
-  auto go = [&](auto kern) -> int {
-    CSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    const int grid = total_blocks < ctx->sm_count ? total_blocks : ctx->sm_count;  // persistent: one CTA per SM
-    kern<<<grid, c.warps * 32, c.smem, ctx->stream>>>(d_files, n_files, total_blocks, d_pa_bits, n_groups, d_sums,
-                                                       d_row_flags, c.pc, c.ns, c.stage_elems, max_P, max_E);
-    return CSG_OK;
-  };
-  int st;
-  if (c.nj == 1)
-    st = go(collapse_slab_kernel<T, NG, 1>);
-  else if (c.nj == 2)
-    st = go(collapse_slab_kernel<T, NG, 2>);
-  else
-    st = go(collapse_slab_kernel<T, NG, 3>);
-  if (st != CSG_OK) return st;
-  CSG_LAUNCH_CHECK(ctx, "collapse_slab_kernel");
+template <typename T, int NG, int TPB>
+int launch_stream_one(csg_ctx* ctx, size_t smem, const csg_file_desc* d_files, int n_files, int total_blocks,
+                      const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+  auto kern = collapse_stream_kernel<T, NG, TPB>;
+  CSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<total_blocks, TPB, smem, ctx->stream>>>(d_files, n_files, d_runs, d_pa_bits, n_groups, d_sums, d_row_flags);
+  CSG_LAUNCH_CHECK(ctx, "collapse_stream_kernel");
   return CSG_OK;
 }
 
+template <typename T, int NG>
+int launch_stream_ng(csg_ctx* ctx, int tpb, size_t smem, const csg_file_desc* d_files, int n_files, int total_blocks,
+                     const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+#define CSG_GO(TPB)                                                                                                   \
+  case TPB:                                                                                                           \
+    return launch_stream_one<T, NG, TPB>(ctx, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums, \
+                                         d_row_flags);
+  switch (tpb) {
+    CSG_GO(256)
+    CSG_GO(384)
+    CSG_GO(512)
+    CSG_GO(768)
+    CSG_GO(1024)
+  }
+#undef CSG_GO
+  return csg_fail(ctx, CSG_ERR_ARG, "stream kernel: unsupported block size %d", tpb);
+}
+
 template <typename T>
-int launch_slab(csg_ctx* ctx, const SlabCfg& c, const csg_file_desc* d_files, int n_files, int total_blocks,
-                const uint8_t* d_pa_bits, int n_groups, int max_P, int max_E, T* d_sums, uint8_t* d_row_flags) {
+int launch_stream(csg_ctx* ctx, int E, int dtype, const csg_file_desc* d_files, int n_files, int total_blocks,
+                  const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+  const int tpb = stream_tpb(E, dtype);
+  const size_t smem = stream_smem(E, n_groups, dtype);
+  if (tpb == 0 || smem > 200 * 1024)
+    return csg_fail(ctx, CSG_ERR_ARG, "stream kernel cannot handle E=%d: use CSG_K1_GENERIC for this table", E);
   if (n_groups == 0)
-    return launch_slab_nj<T, 0>(ctx, c, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, max_E, d_sums,
-                                d_row_flags);
+    return launch_stream_ng<T, 0>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums,
+                                  d_row_flags);
   if (n_groups <= 4)
-    return launch_slab_nj<T, 4>(ctx, c, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, max_E, d_sums,
-                                d_row_flags);
-  return launch_slab_nj<T, CSG_MAX_GROUPS>(ctx, c, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, max_E, d_sums,
-                                           d_row_flags);
+    return launch_stream_ng<T, 4>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums,
+                                  d_row_flags);
+  return launch_stream_ng<T, CSG_MAX_GROUPS>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
+                                             d_sums, d_row_flags);
 }
 
 template <typename T>
@@ -754,11 +597,23 @@ extern "C" {
 
 int csg_collapse_kernel(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube) {
   if (layout == CSG_LAYOUT_TEP) return CSG_K1_GENERIC;
-  return slab_file_ok(T, P, E, dtype, d_cube) ? CSG_K1_SLAB : CSG_K1_GENERIC;
+  return stream_file_ok(T, P, E, dtype, d_cube) ? CSG_K1_STREAM : CSG_K1_GENERIC;
 }
 
-int csg_slab_supported(int max_P, int max_E, int n_groups, int dtype) {
-  return slab_config(max_P, max_E, n_groups, dtype).ok ? 1 : 0;
+// runs of constant group membership along the pitch axis: {p0, p1, mask} triples with the
+// groups that hold every bin (returned in *alias) cleared from the masks
+int csg_pitch_runs(const uint8_t* h_pa_bits, int P, int n_groups, int32_t* h_runs, int32_t* alias) {
+  unsigned all = n_groups > 0 ? ((1u << n_groups) - 1u) : 0u;
+  for (int p = 0; p < P; ++p) all &= h_pa_bits ? h_pa_bits[p] : 0u;
+  auto bits = [&](int p) { return (unsigned)((h_pa_bits && n_groups > 0) ? h_pa_bits[p] : 0u) & ((1u << n_groups) - 1u); };
+  int n = 0, start = 0;
+  for (int p = 1; p <= P; ++p)
+    if (p == P || bits(p) != bits(start)) {
+      h_runs[3 * n] = start, h_runs[3 * n + 1] = p, h_runs[3 * n + 2] = (int32_t)(bits(start) & ~all);
+      ++n, start = p;
+    }
+  if (alias) *alias = (int32_t)all;
+  return n;
 }
 
 int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout, int kernel) {
@@ -767,7 +622,7 @@ int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layo
     const int rows = tep_rows_per_block(P, dtype);
     return (int32_t)(((long long)T * E + rows - 1) / rows);
   }
-  if (kernel == CSG_K1_SLAB) return (T + kTileRows - 1) / kTileRows;
+  if (kernel == CSG_K1_STREAM) return (T + kTileRows - 1) / kTileRows;
   const int vec = dtype == CSG_F64 ? 2 : 4;
   const long long items = (long long)T * ((E + vec - 1) / vec);
   return (int32_t)((items + kBlock - 1) / kBlock);
@@ -779,8 +634,8 @@ int64_t csg_sums_elems(int32_t T, int32_t E, int n_groups) {
 }
 
 int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
-                 const uint8_t* d_pa_bits, int n_groups, int max_P, int max_E, int dtype, int layout, int kernel,
-                 void* d_sums, uint8_t* d_row_flags) {
+                 const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E, int dtype,
+                 int layout, int kernel, void* d_sums, uint8_t* d_row_flags) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_groups < 0 || n_groups > CSG_MAX_GROUPS) return csg_fail(ctx, CSG_ERR_ARG, "n_groups %d out of range", n_groups);
   if (n_groups > 0 && !d_pa_bits) return csg_fail(ctx, CSG_ERR_ARG, "d_pa_bits is NULL with n_groups > 0");
@@ -790,16 +645,13 @@ int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int to
   if (!d_files || !d_sums) return csg_fail(ctx, CSG_ERR_ARG, "NULL table or output");
   if (max_P <= 0 || max_P > 32768) return csg_fail(ctx, CSG_ERR_ARG, "max_P %d out of range (1..32768)", max_P);
   if (layout == CSG_LAYOUT_TPE) {
-    if (kernel == CSG_K1_SLAB) {
-      const SlabCfg c = slab_config(max_P, max_E, n_groups, dtype);
-      if (!c.ok)
-        return csg_fail(ctx, CSG_ERR_ARG, "slab kernel cannot stage (P=%d, E=%d): use CSG_K1_GENERIC for this table", max_P,
-                        max_E);
+    if (kernel == CSG_K1_STREAM) {
+      if (!d_runs) return csg_fail(ctx, CSG_ERR_ARG, "d_runs is NULL for the stream kernel");
       if (dtype == CSG_F32)
-        return launch_slab<float>(ctx, c, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, max_E, (float*)d_sums,
-                                  d_row_flags);
-      return launch_slab<double>(ctx, c, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, max_E, (double*)d_sums,
-                                 d_row_flags);
+        return launch_stream<float>(ctx, max_E, dtype, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
+                                    (float*)d_sums, d_row_flags);
+      return launch_stream<double>(ctx, max_E, dtype, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
+                                   (double*)d_sums, d_row_flags);
     }
     if (dtype == CSG_F32)
       return launch_tpe<float>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, (float*)d_sums, d_row_flags);
@@ -832,11 +684,11 @@ int csg_collapse_host(csg_ctx* ctx, const void* h_cube, int32_t T, int32_t P, in
   const int Tp = (T + 3) & ~3;
   const size_t sums_bytes = (size_t)csg_sums_elems(T, E, n_groups) * es;
   const size_t flag_bytes = ((size_t)T + 3) & ~size_t(3);
-  void *d_cube = nullptr, *d_sums = nullptr, *d_flags = nullptr, *d_bits = nullptr, *d_desc = nullptr;
+  void *d_cube = nullptr, *d_sums = nullptr, *d_flags = nullptr, *d_bits = nullptr, *d_desc = nullptr, *d_runs = nullptr;
   int st = CSG_OK;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_cube), cudaFree(d_sums), cudaFree(d_flags), cudaFree(d_bits), cudaFree(d_desc);
+    cudaFree(d_cube), cudaFree(d_sums), cudaFree(d_flags), cudaFree(d_bits), cudaFree(d_desc), cudaFree(d_runs);
   };
 #define CSG_TRY(x)            \
   if ((st = (x)) != CSG_OK) { \
@@ -848,19 +700,25 @@ int csg_collapse_host(csg_ctx* ctx, const void* h_cube, int32_t T, int32_t P, in
   CSG_TRY(csg_dev_alloc(ctx, flag_bytes, &d_flags));
   CSG_TRY(csg_dev_alloc(ctx, (size_t)P, &d_bits));
   CSG_TRY(csg_dev_alloc(ctx, sizeof(csg_file_desc), &d_desc));
+  CSG_TRY(csg_dev_alloc(ctx, (size_t)(3 * P + 3) * sizeof(int32_t), &d_runs));
   csg_file_desc desc;
   memset(&desc, 0, sizeof(desc));
   desc.d_cube = d_cube;
   desc.T = T, desc.P = P, desc.E = E;
-  int kernel = csg_collapse_kernel(T, P, E, dtype, layout, d_cube);
-  if (kernel == CSG_K1_SLAB && !csg_slab_supported(P, E, n_groups, dtype)) kernel = CSG_K1_GENERIC;
+  std::vector<int32_t> h_runs((size_t)3 * P + 3);
+  int32_t alias = 0;
+  desc.reserved[0] = 0;
+  desc.reserved[1] = csg_pitch_runs(h_pa_bits, P, n_groups, h_runs.data(), &alias);
+  desc.reserved[2] = alias;
+  CSG_TRY(csg_h2d(ctx, d_runs, h_runs.data(), h_runs.size() * sizeof(int32_t)));
+  const int kernel = csg_collapse_kernel(T, P, E, dtype, layout, d_cube);
   const int blocks = csg_collapse_blocks(T, P, E, dtype, layout, kernel);
   CSG_TRY(csg_h2d(ctx, d_cube, h_cube, cube_bytes));
   CSG_TRY(csg_h2d(ctx, d_desc, &desc, sizeof(desc)));
   if (n_groups > 0) CSG_TRY(csg_h2d(ctx, d_bits, h_pa_bits, (size_t)P));
   CSG_TRY(csg_memset(ctx, d_flags, 0, flag_bytes));
-  CSG_TRY(csg_collapse(ctx, (const csg_file_desc*)d_desc, 1, blocks, (const uint8_t*)d_bits, n_groups, P, E, dtype, layout,
-                       kernel, d_sums, (uint8_t*)d_flags));
+  CSG_TRY(csg_collapse(ctx, (const csg_file_desc*)d_desc, 1, blocks, (const uint8_t*)d_bits, (const int32_t*)d_runs,
+                       n_groups, P, E, dtype, layout, kernel, d_sums, (uint8_t*)d_flags));
   // the device keeps sums energy-major [g][e][Tp]; the host entry hands back numpy's (T, E)
   std::vector<unsigned char> tmp(sums_bytes);
   CSG_TRY(csg_d2h(ctx, tmp.data(), d_sums, sums_bytes));

@@ -110,6 +110,7 @@ class Batch:
         self.d_sums: DevBuf | None = None
         self.d_flags: DevBuf | None = None
         self.d_bits: DevBuf | None = None
+        self.d_runs: DevBuf | None = None
         self.d_files: dict[int, tuple[DevBuf, int, int, int]] = {}
         self.d_regions: DevBuf | None = None
         self.d_pool: DevBuf | None = None
@@ -184,26 +185,37 @@ class Batch:
         self._tables_dirty = True
 
     def _build_file_tables(self):
-        """One descriptor table per (storage layout, K1 kernel): a launch handles files of one kind."""
+        """One descriptor table per (storage layout, K1 kernel, E): a launch handles files of one kind."""
         lib = self.ctx.lib
         self.d_files = {}
-        groups: dict[tuple[int, int], list[int]] = {}
+        groups: dict[tuple[int, int, int], list[int]] = {}
         for i, f in enumerate(self.files):
             if f["T"] <= 0:
                 continue
             if f["device_ptr"] is None:
                 raise CsgError("cube not on the device: call upload_cubes() first")
             kern = lib.csg_collapse_kernel(f["T"], f["P"], f["E"], self.code, f["layout"], f["device_ptr"])
-            groups.setdefault((f["layout"], kern), []).append(i)
-        # a slab table whose maxima cannot be staged falls back to the generic kernel as a whole
-        key = (_lib.LAYOUT_TPE, _lib.K1_SLAB)
-        if key in groups:
-            mp = max(self.files[i]["P"] for i in groups[key])
-            me = max(self.files[i]["E"] for i in groups[key])
-            if not lib.csg_slab_supported(mp, me, self.G, self.code):
-                groups.setdefault((_lib.LAYOUT_TPE, _lib.K1_GENERIC), []).extend(groups.pop(key))
-        for (layout, kern), idx in groups.items():
-            idx.sort()
+            # every file of a stream-kernel table shares one energy count (it fixes the block shape)
+            groups.setdefault((f["layout"], kern, f["E"] if kern == _lib.K1_STREAM else 0), []).append(i)
+        # runs of constant pitch-angle group membership (stream kernel), one entry per distinct table
+        runs_tab: list[np.ndarray] = []
+        runs_len = 0
+        runs_of: dict[bytes, tuple[int, int, int]] = {}
+        for (layout, kern, _e), idx in groups.items():
+            if kern != _lib.K1_STREAM:
+                continue
+            for i in idx:
+                bits = self._bits[i]
+                key = bits.tobytes()
+                if key not in runs_of:
+                    buf = np.zeros(3 * len(bits) + 3, dtype=np.int32)
+                    alias = C.c_int32(0)
+                    n = lib.csg_pitch_runs(bits.ctypes.data, len(bits), self.G, buf.ctypes.data, C.byref(alias))
+                    runs_of[key] = (runs_len, n, int(alias.value))
+                    runs_tab.append(buf[: 3 * n])
+                    runs_len += n
+        self.d_runs = self.ctx.to_device(np.concatenate(runs_tab)) if runs_tab else None
+        for (layout, kern, _e), idx in groups.items():
             tab = np.zeros(len(idx), dtype=FILE_DESC)
             blocks, max_p, max_e = 0, 1, 1
             for j, i in enumerate(idx):
@@ -214,9 +226,11 @@ class Batch:
                 tab[j]["T"], tab[j]["P"], tab[j]["E"] = f["T"], f["P"], f["E"]
                 tab[j]["bits_off"] = f["bits_off"]
                 tab[j]["first_block"] = blocks
+                if kern == _lib.K1_STREAM:
+                    tab[j]["reserved"] = runs_of[self._bits[i].tobytes()]
                 blocks += lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout, kern)
                 max_p, max_e = max(max_p, f["P"]), max(max_e, f["E"])
-            self.d_files[(layout, kern)] = (self.ctx.to_device(tab), len(idx), blocks, max_p, max_e)
+            self.d_files[(layout, kern, _e)] = (self.ctx.to_device(tab), len(idx), blocks, max_p, max_e)
         self.d_bits = self.ctx.to_device(np.concatenate(self._bits) if self._bits else np.zeros(1, np.uint8))
         if self.d_sums is None or self.d_sums.nbytes < self._sums_elems * self.dtype.itemsize:
             self.d_sums = self.ctx.alloc(max(self._sums_elems, 1) * self.dtype.itemsize)
@@ -225,14 +239,15 @@ class Batch:
         self._tables_dirty = False
 
     def collapse(self):
-        """K1 over every file (one launch per storage layout / kernel present)."""
+        """K1 over every file (one launch per storage layout / kernel / block shape present)."""
         if self._tables_dirty:
             self._build_file_tables()
         self.d_flags.zero()
-        for (layout, kern), (tab, n, blocks, max_p, max_e) in self.d_files.items():
+        for (layout, kern, _e), (tab, n, blocks, max_p, max_e) in self.d_files.items():
             self.ctx._check(
                 self.ctx.lib.csg_collapse(
-                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr, self.G, max_p, max_e, self.code, layout, kern,
+                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr,
+                    self.d_runs.ptr if self.d_runs is not None else None, self.G, max_p, max_e, self.code, layout, kern,
                     self.d_sums.ptr, self.d_flags.ptr,
                 )
             )

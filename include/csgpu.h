@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 3
+#define CSG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -102,17 +102,21 @@ typedef struct {
   int32_t T, P, E;
   int32_t bits_off;    /* byte offset in d_pa_bits of this file's [P] membership bytes   */
   int32_t first_block; /* exclusive prefix sum of csg_collapse_blocks() over the files   */
-  int32_t reserved[3];
+  int32_t reserved[3]; /* STREAM kernel: [0] index of the file's first triple in d_runs, [1] number of
+                          runs, [2] alias mask (csg_pitch_runs); ignored by the other kernels      */
 } csg_file_desc; /* 56 bytes */
 
-/* Which kernel collapses a file: the slab kernel streams whole time steps of a C-contiguous
- * (T,P,E) cube through shared memory with bulk asynchronous copies (TMA) and needs a 16-byte
- * aligned cube whose energy rows are a multiple of 16 bytes; everything else takes the generic
- * kernel.  A csg_collapse() call handles files of ONE kernel. */
-enum { CSG_K1_GENERIC = 0, CSG_K1_SLAB = 1 };
+/* Which kernel collapses a file: the stream kernel (16-row tiles, loop bodies specialised per
+ * run of constant group membership, coalesced transposed output) needs a 16-byte aligned
+ * C-contiguous (T,P,E) cube with E / (16 bytes / sizeof D) in {16,24,32,48,64}; everything else
+ * takes the generic kernel.  A csg_collapse() call handles files of ONE kernel, and every file of
+ * a STREAM table has the same E (= max_E). */
+enum { CSG_K1_GENERIC = 0, CSG_K1_STREAM = 1 };
 CSG_API int csg_collapse_kernel(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube);
-/* 1 when the slab kernel can stage tables with these maxima (else route the table to GENERIC) */
-CSG_API int csg_slab_supported(int max_P, int max_E, int n_groups, int dtype);
+/* Host helper: runs of constant group membership along the pitch axis as {p0, p1, mask} int32
+ * triples (at most P of them) for csg_file_desc.reserved[0..1]; *alias (-> reserved[2]) = groups
+ * that contain every bin -- their bits are cleared from the masks, the kernel copies the total. */
+CSG_API int csg_pitch_runs(const uint8_t* h_pa_bits, int P, int n_groups, int32_t* h_runs, int32_t* alias);
 /* thread blocks csg_collapse() uses for one (T,P,E) file (for first_block) */
 CSG_API int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout, int kernel);
 /* elements of one file's sums block: (n_groups+1) * E * Tp, Tp = T rounded up to a multiple of 4 */
@@ -127,8 +131,8 @@ CSG_API int64_t csg_sums_elems(int32_t T, int32_t E, int n_groups);
  * all / group-k pitch bins (any energy); zero it before the call.
  * All files of one call share dtype, layout, kernel and n_groups. */
 CSG_API int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
-                 const uint8_t* d_pa_bits, int n_groups, int max_P, int max_E, int dtype, int layout,
-                 int kernel, void* d_sums, uint8_t* d_row_flags);
+                 const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E,
+                 int dtype, int layout, int kernel, void* d_sums, uint8_t* d_row_flags);
 
 /* zoom_needed = np.any(~np.isnan(cube[window])) (CS/plotting.py:597-603) from the row flags:
  * d_out[w] = 1 iff some row of window w has bit `bit` set.  Rows are [t0, t0+nt) when

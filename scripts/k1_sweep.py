@@ -53,8 +53,5 @@ def run(env_extra, n_orb):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     configs = [{}]
-    for w, pc, ns in ((8, 16, 2), (8, 16, 3), (8, 24, 2), (8, 8, 4), (8, 8, 6), (6, 32, 2), (7, 32, 2), (4, 32, 3), (4, 32, 4),
-                      (4, 16, 6), (6, 16, 4), (5, 32, 3)):
-        configs.append({"CSG_SLAB_W": str(w), "CSG_SLAB_PC": str(pc), "CSG_SLAB_NS": str(ns)})
     for c in configs:
         run(c, n)
