@@ -357,6 +357,24 @@ class Batch:
             )
         )
 
+    def _pool_array(self) -> np.ndarray:
+        if getattr(self, "_pool_flat_len", -1) != self._pool_len:
+            self._pool_flat = np.concatenate(self._pool) if self._pool else np.zeros(0, np.int32)
+            self._pool_flat_len = self._pool_len
+        return self._pool_flat
+
+    def region_energy_index(self, region: int) -> np.ndarray:
+        """Energy channel of every image row of a region (lowest energy first)."""
+        r = self._regions[region]
+        return self._pool_array()[r[5] : r[5] + r[6]]
+
+    def region_time_index(self, region: int) -> np.ndarray:
+        """Time step of every image column of a region."""
+        r = self._regions[region]
+        if r[4] < 0:
+            return np.arange(r[2], r[2] + r[3])
+        return self._pool_array()[r[4] : r[4] + r[3]]
+
     def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None,
                   stat_region: int = -1) -> int:
         r = self._regions[region]

@@ -361,7 +361,12 @@ class BatchStep:
     """
 
     def __init__(self, shard: ShardPlan, sequence, max_percentile=95.0, comm=None, lut259=None, want_index=False,
-                 compute_mins=False):
+                 compute_mins=False, plot_orbits=None, submissions=(False, True)):
+        """``plot_orbits``: orbit numbers to draw (default: every orbit of the shard; the extrema
+        pre-pass always covers the whole sequence).  ``submissions``: which of the reference's two
+        submissions per orbit to plan -- without / with the global extrema."""
+        self.plot_orbits = None if plot_orbits is None else set(plot_orbits)
+        self.submissions = tuple(submissions)
         self.shard = shard
         self.sequence = sequence
         self.max_percentile = max_percentile
@@ -380,7 +385,7 @@ class BatchStep:
 
         sh = self.shard
         out = {}
-        for inst in sh.instrument_order:
+        for inst in dict.fromkeys(tuple(sh.instrument_order) + tuple(DEFAULT_INSTRUMENT_ORDER)):
             stem = f"{inst}_{sh.y_scale}_{sh.z_scale}"
             ov = _extrema_overrides(state, inst, sh.y_scale, sh.z_scale)
             raw = tuple(state.get(f"{stem}_{k}") for k in ("y_min", "y_max", "z_min", "z_max"))
@@ -413,9 +418,13 @@ class BatchStep:
             for name, key, v in (("z_min", f"{stem}_z_min", raw[2]), ("z_max", f"{stem}_z_max", raw[3])):
                 if v is not None:
                     slotted[key] = self._slots[(inst, name)] = b.zslot(v)
+        self.figure_ranges = {}  # (orbit, with_extrema) -> [first, last) in shard.figures
         for ob in sh.orbits:
-            for with_extrema in (False, True):  # batch_directory.py:237-243
-                for inst in sh.instrument_order:
+            if self.plot_orbits is not None and ob["orbit"] not in self.plot_orbits:
+                continue
+            for with_extrema in self.submissions:  # batch_directory.py:237-243
+                first = len(sh.figures)
+                for inst in DEFAULT_INSTRUMENT_ORDER:  # process_orbit.py:124 walks the default order
                     if inst not in ob["files"]:
                         continue
                     if with_extrema:
@@ -425,6 +434,7 @@ class BatchStep:
                     sh.plan_pitch_angle_grid(ob, inst, "raw")
                 sh.plan_instrument_grid(ob, "given", global_extrema=slotted if with_extrema else None)
                 sh.plan_instrument_grid(ob, "raw", global_extrema=None)
+                self.figure_ranges[(ob["orbit"], with_extrema)] = (first, len(sh.figures))
         sh.upload_tables()
         if self.lut is not None:
             b.set_lut(self.lut)
@@ -439,20 +449,28 @@ class BatchStep:
                 if slot is not None:
                     b.set_zslot(slot.slot, v)
 
-    def run(self, cache_state: dict | None = None) -> dict:
-        """Enqueue one whole step; returns the extrema state (rasters stay on the device)."""
+    def run(self, cache_state: dict | None = None, state: dict | None = None, collapse: bool = True) -> dict:
+        """Enqueue one whole step; returns the extrema state (rasters stay on the device).
+
+        ``state``: an already computed extrema dict (e.g. from ``compute_global_extrema`` with its
+        JSON cache) -- the K2b pre-pass is skipped and only the figures run."""
         from .extrema import extrema_enqueue, extrema_finish
 
         sh, b = self.shard, self.shard.batch
-        sh.collapse()
-        pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
-                                  dict(cache_state or {}), compute_mins=self.compute_mins,
-                                  max_percentile=self.max_percentile, comm=self.comm)
+        if collapse:
+            sh.collapse()
         planned = self._sig is not None
-        if planned:  # K2a does not depend on the extrema: it overlaps the host bookkeeping below
+        if state is None:
+            pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
+                                      dict(cache_state or {}), compute_mins=self.compute_mins,
+                                      max_percentile=self.max_percentile, comm=self.comm)
+            if planned:  # K2a does not depend on the extrema: it overlaps the host bookkeeping below
+                b.run_windows()
+                b.run_stats()
+            state = extrema_finish(pending)
+        elif planned:
             b.run_windows()
             b.run_stats()
-        state = extrema_finish(pending)
         bounds = self._bounds(state)
         sig = self._signature(bounds)
         if sig != self._sig:

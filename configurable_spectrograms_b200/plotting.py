@@ -1,0 +1,438 @@
+"""Generic spectrogram plotting on the GPU path (reference ``plotting.py``).
+
+Same public functions and argument meaning as the reference: ``make_spectrogram``,
+``generic_plot_spectrogram_set``, ``generic_plot_multirow_optional_zoom``,
+``close_all_axes_and_clear``.  The numeric work of one ``make_spectrogram`` call --
+``COLLAPSE_FUNCTION`` (``:188``), the energy / zoom / x-range masks (``:191-219``),
+``compute_percentile_bounds`` (``:259``), ``safe_vmin`` (``:261-262``), the log / linear z
+clamps (``:276-279,308-315``) and what ``imshow`` + the norm + the colormap would colour
+(``:280-287,316-324``) -- runs in libcsgpu (K1, K2a, K3); the host keeps the axes metadata,
+labels, ticks and cusp markers, recorded on raster axes (``figure.py``).
+
+There is no CPU fallback: without libcsgpu / a CUDA device these functions raise ``CsgError``.
+"""
+
+from __future__ import annotations
+
+from datetime import datetime, timezone
+
+import numpy as np
+
+from . import _lib
+from .colormaps import get_lut
+from .constants import AXIS_LABEL_FONT_SIZE, PLOT_FIGURE_HEIGHT_INCHES, PLOT_FIGURE_WIDTH_INCHES, TICK_LABEL_FONT_SIZE
+from .cusp_marking import draw_cusp_both_markers, draw_cusp_bracket_marker, draw_cusp_line_markers
+from .engine import Batch
+from .figure import FigureCanvas, SpectrogramFigure, close_all_axes_and_clear
+from .logging_utils import log_message
+
+__all__ = [
+    "make_spectrogram",
+    "generic_plot_spectrogram_set",
+    "generic_plot_multirow_optional_zoom",
+    "close_all_axes_and_clear",
+    "date2num",
+    "num2date",
+]
+
+_CUSP_MARKER_DRAWERS = {
+    "line": draw_cusp_line_markers,
+    "bracket": draw_cusp_bracket_marker,
+    "both": draw_cusp_both_markers,
+}
+#: colormaps whose high end is red: the cusp line switches to white on them (reference ``:45-50``)
+_RED_HEAVY_COLORMAPS = {"turbo", "jet", "hot", "inferno", "magma", "plasma", "autumn", "gist_heat", "Reds", "YlOrRd", "OrRd"}
+
+
+def date2num(unix_seconds):
+    """matplotlib's ``date2num(datetime.fromtimestamp(t, tz=utc))``: days since 1970-01-01 UTC
+    (the reference's x axis, ``:221-223``), vectorised.
+
+    ``datetime.fromtimestamp`` rounds the fraction half-to-even to microseconds; matplotlib's
+    ``_dt64_to_ordinalf`` then computes ``(whole_seconds + microseconds * 1000 / 1e9) / 86400``
+    in float64.  Both steps are reproduced so the extents and marker positions match bit for bit.
+    """
+    t = np.asarray(unix_seconds, dtype=np.float64)
+    frac, whole = np.modf(t)
+    micro = np.rint(frac * 1e6)
+    carry = micro >= 1e6
+    whole = np.where(carry, whole + 1.0, whole)
+    micro = np.where(carry, micro - 1e6, micro)
+    neg = micro < 0  # negative timestamps: borrow a second, like divmod
+    whole = np.where(neg, whole - 1.0, whole)
+    micro = np.where(neg, micro + 1e6, micro)
+    days = (whole + (micro * 1000.0) / 1.0e9) / 86400.0
+    return float(days) if days.ndim == 0 else days
+
+
+def num2date(days, tz=timezone.utc):
+    from datetime import timedelta
+
+    return datetime(1970, 1, 1, tzinfo=timezone.utc) + timedelta(microseconds=round(float(days) * 86400e6))
+
+
+def _colormap_name(colormap) -> str:
+    return colormap if isinstance(colormap, str) else getattr(colormap, "name", "custom")
+
+
+def _as_cube(data_array_3d, collapse_axis):
+    cube = np.asarray(data_array_3d)
+    if cube.ndim != 3:
+        raise ValueError(f"make_spectrogram expects a 3-D array, got shape {cube.shape}")
+    if collapse_axis != 1:
+        cube = np.moveaxis(cube, collapse_axis, 1)
+    if cube.dtype not in (np.float32, np.float64):
+        cube = cube.astype(np.float64)  # numpy sums and ranks integer input exactly; float64 keeps that
+    return cube
+
+
+def make_spectrogram(
+    x_axis_values,
+    y_axis_values,
+    data_array_3d,
+    x_axis_min=None,
+    x_axis_max=None,
+    x_axis_is_unix=True,
+    x_axis_label=None,
+    center_timestamp=None,
+    window_duration_seconds=None,
+    y_axis_scale_function=None,
+    y_axis_label=None,
+    y_axis_min=0,
+    y_axis_max=4000,
+    z_axis_scale_function=None,
+    z_axis_min=None,
+    z_axis_max=None,
+    z_axis_label=None,
+    collapse_axis=1,
+    colormap="viridis",
+    axis_object=None,
+    instrument_label=None,
+    vertical_lines_unix=None,
+    cusp_marker_style="both",
+    cusp_marker_kwargs=None,
+    _context=None,
+):
+    """Plot a spectrogram by collapsing a 3-D array along an axis (reference ``:92-389``).
+
+    Returns ``(axis_object, x_axis_plot)`` or ``(None, None)`` when every energy bin / time step
+    is filtered out.  ``axis_object`` is a :class:`figure.PanelAxes` holding the RGBA raster
+    (``.images[-1].rgba``, row 0 = lowest energy), the LUT index plane (``.index``) and the
+    resolved ``vmin`` / ``vmax``.
+    """
+    log_message(
+        f"[DEBUG] make_spectrogram: y_axis_scale_function={y_axis_scale_function}, "
+        f"z_axis_scale_function={z_axis_scale_function}, z_axis_min={z_axis_min}, "
+        f"z_axis_max={z_axis_max}, colormap={colormap}"
+    )
+    x_axis = np.asarray(x_axis_values)
+    y_axis = np.asarray(y_axis_values)
+    cube = _as_cube(data_array_3d, collapse_axis)
+
+    # energy mask (:191-198); the all-NaN-column mask is a no-op after nansum (all-NaN -> 0.0)
+    with np.errstate(invalid="ignore"):
+        keep = np.flatnonzero((y_axis >= y_axis_min) & (y_axis <= y_axis_max))
+    if cube.shape[0] == 0 or len(keep) == 0:
+        log_message("[WARNING] All energy bins were filtered out. No data to plot.")
+        return None, None
+    y_kept = y_axis[keep]
+    if y_kept[0] > y_kept[-1]:  # descending energies: flip (:200-202)
+        y_kept, keep = y_kept[::-1], keep[::-1]
+
+    rows = np.arange(len(x_axis))
+    if center_timestamp is not None and window_duration_seconds is not None:  # :204-210
+        half = window_duration_seconds / 2
+        with np.errstate(invalid="ignore"):
+            rows = rows[(x_axis[rows] >= center_timestamp - half) & (x_axis[rows] <= center_timestamp + half)]
+    if x_axis_min is not None or x_axis_max is not None:  # :212-219
+        with np.errstate(invalid="ignore"):
+            m = np.ones(len(rows), dtype=bool)
+            if x_axis_min is not None:
+                m &= x_axis[rows] >= x_axis_min
+            if x_axis_max is not None:
+                m &= x_axis[rows] <= x_axis_max
+        rows = rows[m]
+    x_sel = x_axis[rows]
+    if x_axis_is_unix:
+        x_axis_plot = date2num(x_sel) if len(x_sel) else np.zeros(0)
+        x_label = x_axis_label if x_axis_label is not None else "Time (UTC)"
+    else:
+        x_axis_plot = x_sel
+        x_label = x_axis_label if x_axis_label is not None else "X"
+
+    if axis_object is None:
+        fig = SpectrogramFigure(figsize=(PLOT_FIGURE_WIDTH_INCHES, PLOT_FIGURE_HEIGHT_INCHES))
+        FigureCanvas(fig)
+        axis_object = fig.add_subplot(1, 1, 1)
+    else:
+        fig = axis_object.figure
+
+    if center_timestamp is not None and window_duration_seconds is not None:
+        lo, hi = center_timestamp - window_duration_seconds / 2, center_timestamp + window_duration_seconds / 2
+        if x_axis_is_unix:
+            axis_object.set_xlim(date2num(lo), date2num(hi))
+        else:
+            axis_object.set_xlim(lo, hi)
+    else:
+        axis_object.set_xlim(x_axis_plot[0], x_axis_plot[-1])  # IndexError on an empty x, like the reference (:253)
+    if len(rows) == 0:
+        log_message("[WARNING] No data to plot after filtering. Skipping plot.")
+        return None, None
+
+    # ---- the numeric path on the GPU: K1 collapse, K2a bounds, K3 norm + colormap
+    ctx = _context or _lib.default_context()
+    batch = Batch(ctx, cube.dtype, n_groups=0)
+    f = batch.add_file(cube)
+    batch.upload_cubes()
+    batch.collapse()
+    log_scale = z_axis_scale_function == "log"
+    region = batch.add_region(f, 0, keep, rows=rows, want_pct=z_axis_min is None or z_axis_max is None)
+    panel = batch.add_panel(region, -1, log_scale, z_axis_min, z_axis_max)
+    batch.upload_tables()
+    batch.run_stats()
+    batch.prepare()
+    lut = get_lut(colormap)
+    batch.set_lut(lut)
+    batch.rasterise(want_rgba=True, want_index=True)
+    norm = batch.norms()[panel]
+    st = int(norm["status"])
+    if st == _lib.NORM_VMIN_GT_VMAX:  # what matplotlib raises when the figure is drawn
+        raise ValueError("vmin must be less or equal to vmax")
+    if st == _lib.NORM_INVALID:
+        raise ValueError("Invalid vmin or vmax")
+    z_lo, z_hi = float(norm["vmin"]), float(norm["vmax"])
+    if log_scale:
+        stats = batch.stats()[region]
+        if stats["n_pos"] < stats["n_valid"] + stats["n_nan"] or not (np.isfinite(z_lo) and z_hi > z_lo > 0):
+            log_message(
+                "[WARNING] Non-positive values found in matrix for log colorbar. "
+                "Masking to z_axis_min and enforcing log scale."
+            )
+    rgba, index = batch.panel_rgba(panel), batch.panel_index(panel)
+    draw_panel(axis_object, rgba, index, z_lo, z_hi, log_scale, x_axis_plot, y_kept, x_label=x_label,
+               x_axis_is_unix=x_axis_is_unix, y_axis_scale_function=y_axis_scale_function, y_axis_label=y_axis_label,
+               y_axis_min=y_axis_min, y_axis_max=y_axis_max, z_axis_label=z_axis_label, colormap=colormap,
+               instrument_label=instrument_label, vertical_lines_unix=vertical_lines_unix,
+               cusp_marker_style=cusp_marker_style, cusp_marker_kwargs=cusp_marker_kwargs)
+    return axis_object, x_axis_plot
+
+
+def draw_panel(axis_object, rgba, index, z_lo, z_hi, log_scale, x_axis_plot, y_kept, *, x_label="Time (UTC)",
+               x_axis_is_unix=True, y_axis_scale_function=None, y_axis_label=None, y_axis_min=0, y_axis_max=4000,
+               z_axis_label=None, colormap="viridis", instrument_label=None, vertical_lines_unix=None,
+               cusp_marker_style="both", cusp_marker_kwargs=None):
+    """Everything ``make_spectrogram`` does to the axes once the raster exists (reference
+    ``:280-387``): imshow, colorbar, labels, y ticks, time formatter, cusp markers."""
+    fig = axis_object.figure
+    extent = (x_axis_plot[0], x_axis_plot[-1], y_kept[0], y_kept[-1])
+    im = axis_object.imshow(rgba, aspect="auto", origin="lower", extent=extent, cmap=_colormap_name(colormap),
+                            norm="log" if log_scale else None, vmin=z_lo, vmax=z_hi, index=index)
+    ticks = None
+    if log_scale and z_lo > 0 and z_hi > 0 and np.isfinite(z_lo) and np.isfinite(z_hi):
+        lo_e, hi_e = int(np.floor(np.log10(z_lo))), int(np.ceil(np.log10(z_hi)))
+        ticks = [10**i for i in range(lo_e, hi_e + 1) if z_lo <= 10**i <= z_hi]
+    colorbar = fig.colorbar(im, ax=axis_object, label=z_axis_label if z_axis_label is not None else "Counts", ticks=ticks)
+
+    axis_object.set_xlabel(x_label)
+    axis_object.set_ylabel(y_axis_label if y_axis_label is not None else "Energy (eV)")
+    if instrument_label is not None:
+        axis_object.set_title(instrument_label)
+
+    if len(y_kept) >= 2:  # y ticks (:335-355)
+        if y_axis_scale_function != "log":
+            y_max_str = str(y_axis_max)
+            digits = len(y_max_str)
+            first, second = int(y_max_str[0]), int(y_max_str[1])
+            if second >= 5:
+                step, y_max_tick = 10**digits, first * 10 ** (digits - 1)
+            else:
+                step, y_max_tick = 10 ** (digits - 1), (first + 0.5) * 10 ** (digits - 1)
+            yticks = [i for i in range(y_axis_min, int(y_max_tick) + 1, step) if (i / y_max_tick) <= 1.1]
+            if yticks:
+                axis_object.set_yticks(yticks)
+                axis_object.set_yticklabels([f"{int(e)}" for e in yticks])
+        else:
+            axis_object.set_yscale("log")
+
+    if x_axis_is_unix:  # tick format by displayed span (:357-368)
+        left, right = axis_object.get_xlim()
+        span = (num2date(right) - num2date(left)).total_seconds()
+        axis_object.xaxis.set_major_formatter("%H:%M:%S" if span < 120 else "%H:%M")
+
+    if vertical_lines_unix is not None and len(vertical_lines_unix) > 0:  # :370-381
+        if x_axis_is_unix:
+            marks = [v for v in date2num(list(vertical_lines_unix)) if x_axis_plot[0] <= v <= x_axis_plot[-1]]
+        else:
+            marks = [v for v in vertical_lines_unix if x_axis_plot[0] <= v <= x_axis_plot[-1]]
+        draw_marker = _CUSP_MARKER_DRAWERS.get(cusp_marker_style, draw_cusp_both_markers)
+        marker_kwargs = dict(cusp_marker_kwargs or {})
+        marker_kwargs.setdefault("line_color", "white" if colormap in _RED_HEAVY_COLORMAPS else "red")
+        draw_marker(axis_object, marks, **marker_kwargs)
+
+    axis_object.tick_params(axis="both", which="major", labelsize=TICK_LABEL_FONT_SIZE, length=8, width=1)
+    axis_object.tick_params(axis="both", which="minor", labelsize=TICK_LABEL_FONT_SIZE, length=5, width=1)
+    colorbar.ax.tick_params(labelsize=TICK_LABEL_FONT_SIZE, length=6, width=1)
+    colorbar.ax.tick_params(which="minor", labelsize=TICK_LABEL_FONT_SIZE, length=3, width=1)
+    axis_object.xaxis.label.set_fontsize(AXIS_LABEL_FONT_SIZE)
+    axis_object.yaxis.label.set_fontsize(AXIS_LABEL_FONT_SIZE)
+    colorbar.ax.set_ylabel("Counts", fontsize=AXIS_LABEL_FONT_SIZE)
+    return im
+
+
+def generic_plot_spectrogram_set(
+    datasets,
+    collapse_axis=1,
+    zoom_center=None,
+    zoom_window_seconds=None,
+    vertical_lines=None,
+    x_is_unix=True,
+    y_scale="linear",
+    z_scale="linear",
+    colormap="viridis",
+    figure_title=None,
+    show=False,
+    y_min=None,
+    y_max=None,
+    z_min=None,
+    z_max=None,
+    cusp_marker_style="both",
+    cusp_marker_kwargs=None,
+):
+    """A vertical stack of generic spectrograms (reference ``:392-502``): one ``make_spectrogram``
+    per dataset dict (required keys ``x, y, data``; optional ``label, y_label, z_label, x_label,
+    y_min, y_max, z_min, z_max``).  Returns ``(fig, canvas)`` or ``(None, None)``."""
+    if not datasets:
+        return None, None
+    fig = SpectrogramFigure(figsize=(10, 3 * len(datasets)))
+    canvas = FigureCanvas(fig)
+    for row_index, dataset in enumerate(datasets):
+        axis_obj = fig.add_subplot(len(datasets), 1, row_index + 1)
+        ds_y_min, ds_y_max = dataset.get("y_min", y_min), dataset.get("y_max", y_max)
+        ds_z_min, ds_z_max = dataset.get("z_min", z_min), dataset.get("z_max", z_max)
+        inferred_y_max = dataset["y"].max() if ds_y_max is None and dataset.get("y") is not None else ds_y_max
+        make_spectrogram(
+            x_axis_values=dataset["x"],
+            y_axis_values=dataset["y"],
+            data_array_3d=dataset["data"],
+            collapse_axis=collapse_axis,
+            center_timestamp=zoom_center,
+            window_duration_seconds=zoom_window_seconds,
+            x_axis_is_unix=x_is_unix,
+            y_axis_scale_function=y_scale,
+            z_axis_scale_function=z_scale,
+            y_axis_min=ds_y_min if ds_y_min is not None else 0,
+            y_axis_max=inferred_y_max if inferred_y_max is not None else 4000,
+            z_axis_min=ds_z_min,
+            z_axis_max=ds_z_max,
+            colormap=colormap,
+            y_axis_label=dataset.get("y_label", "Energy (eV)"),
+            z_axis_label=dataset.get("z_label", "Counts"),
+            x_axis_label="Time (UTC)" if x_is_unix else dataset.get("x_label"),
+            vertical_lines_unix=vertical_lines,
+            cusp_marker_style=cusp_marker_style,
+            cusp_marker_kwargs=cusp_marker_kwargs,
+            axis_object=axis_obj,
+        )
+        if dataset.get("label"):
+            axis_obj.set_title(dataset["label"])
+    if figure_title:
+        fig.suptitle(figure_title)
+    fig.tight_layout(rect=(0, 0, 1, 0.97))
+    return fig, canvas
+
+
+def zoom_window_from_lines(vertical_lines, zoom_duration_minutes):
+    """(centre, duration) of the zoom column, or ``None`` without lines (reference ``:586-596``)."""
+    if not vertical_lines:
+        return None
+    if len(vertical_lines) == 1:
+        return vertical_lines[0], zoom_duration_minutes * 60
+    centre = 0.5 * (vertical_lines[0] + vertical_lines[1])
+    return centre, max(zoom_duration_minutes * 60, abs(vertical_lines[1] - vertical_lines[0]) * 1.5)
+
+
+def generic_plot_multirow_optional_zoom(
+    datasets,
+    vertical_lines=None,
+    zoom_duration_minutes=6.25,
+    y_scale="linear",
+    z_scale="linear",
+    colormap="viridis",
+    show=False,
+    title=None,
+    row_label_pad=50,
+    row_label_rotation=90,
+    y_min=None,
+    y_max=None,
+    z_min=None,
+    z_max=None,
+    cusp_marker_style="both",
+    cusp_marker_kwargs=None,
+):
+    """Rows of spectrograms with an optional zoom column (reference ``:505-698``).
+
+    Dataset keys read: ``x, y, data, vmin, vmax, label`` -- exactly the reference's set (its
+    ``y_min / y_max / z_min / z_max`` dataset keys are ignored there too, so every panel is
+    clipped to the default 0-4000 eV).
+    """
+    if not datasets:
+        return None, None
+    zoom_needed = False
+    centre = duration = None
+    zoom = zoom_window_from_lines(vertical_lines, zoom_duration_minutes) if vertical_lines is not None and len(vertical_lines) > 0 else None
+    if zoom is not None:
+        centre, duration = zoom
+        left, right = centre - duration / 2, centre + duration / 2
+        for ds in datasets:
+            t, d = np.asarray(ds["x"]), np.asarray(ds["data"])
+            with np.errstate(invalid="ignore"):
+                mask_zoom = (t >= left) & (t <= right)
+            if np.any(~np.isnan(d[mask_zoom])):
+                zoom_needed = True
+                break
+    n_rows, n_cols = len(datasets), 2 if zoom_needed else 1
+    fig = SpectrogramFigure(figsize=(12 * n_cols, 3 * n_rows))
+    canvas = FigureCanvas(fig)
+    axes = np.empty((n_rows, n_cols), dtype=object)
+    for i in range(n_rows):
+        for j in range(n_cols):
+            axes[i, j] = fig.add_subplot(n_rows, n_cols, i * n_cols + j + 1)
+    for i, ds in enumerate(datasets):
+        times, energy, data3d = ds["x"], ds["y"], ds["data"]
+        vmin, vmax = ds.get("vmin"), ds.get("vmax")
+        common = dict(
+            x_axis_values=times, y_axis_values=energy, data_array_3d=data3d, collapse_axis=1, x_axis_is_unix=True,
+            instrument_label=None, y_axis_scale_function=y_scale, z_axis_scale_function=z_scale,
+            vertical_lines_unix=vertical_lines, cusp_marker_style=cusp_marker_style, cusp_marker_kwargs=cusp_marker_kwargs,
+            z_axis_min=vmin if z_min is None else z_min, z_axis_max=vmax if z_max is None else z_max, colormap=colormap,
+        )
+        make_spectrogram(x_axis_min=times[0], x_axis_max=times[-1], axis_object=axes[i, 0], **common)
+        if n_cols == 2:
+            make_spectrogram(center_timestamp=centre, window_duration_seconds=duration, axis_object=axes[i, 1], **common)
+    _finish_multirow(fig, axes, datasets, vertical_lines, title, row_label_pad, row_label_rotation)
+    return fig, canvas
+
+
+def _finish_multirow(fig, axes, datasets, vertical_lines, title, row_label_pad=50, row_label_rotation=90):
+    """Row labels, column titles, footer texts of a multirow figure (reference ``:659-693``)."""
+    n_cols = axes.shape[1]
+    for i, ds in enumerate(datasets):
+        axes[i, 0].set_ylabel(ds.get("label", ""), fontsize=AXIS_LABEL_FONT_SIZE, rotation=row_label_rotation,
+                              labelpad=row_label_pad, va="center")
+    axes[0, 0].set_title("Full", fontsize=AXIS_LABEL_FONT_SIZE)
+    if n_cols == 2:
+        axes[0, 1].set_title("Zoomed", fontsize=AXIS_LABEL_FONT_SIZE)
+    if title:
+        fig.suptitle(title, fontsize=AXIS_LABEL_FONT_SIZE + 2)
+    base_times = datasets[0]["x"]
+    t0 = datetime.fromtimestamp(float(base_times[0]), tz=timezone.utc)
+    t1 = datetime.fromtimestamp(float(base_times[-1]), tz=timezone.utc)
+    span = f"Data timespan: {t0.strftime('%Y-%m-%d %H:%M:%S')} to {t1.strftime('%Y-%m-%d %H:%M:%S')} UTC"
+    fig.subplots_adjust(bottom=0.18)
+    fig.text(0.5, 0.01, span, ha="center", va="bottom", fontsize=13)
+    if vertical_lines is not None and len(vertical_lines) > 0:
+        v0 = datetime.fromtimestamp(float(min(vertical_lines)), tz=timezone.utc)
+        v1 = datetime.fromtimestamp(float(max(vertical_lines)), tz=timezone.utc)
+        marked = f"Marked range: {v0.strftime('%Y-%m-%d %H:%M:%S')} to {v1.strftime('%Y-%m-%d %H:%M:%S')} UTC"
+        fig.text(0.5, 0.045, marked, ha="center", va="bottom", fontsize=13, color="red")
+    fig.tight_layout(rect=(0, 0.08, 1, 0.95))

@@ -1,0 +1,221 @@
+"""GPU parity of the reference-shaped host API (plotting.*, fast.plotting.*, fast.process_orbit,
+fast.batch_directory, generic_batch) against what the UNMODIFIED reference produced
+(tests/golden/*, see tests/golden/make_golden.py)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from tests.helpers import dataset_from_arrays, load_json, load_npz, panels, same_float
+
+pytestmark = pytest.mark.gpu
+
+ORDER = ("ees", "eeb", "ies", "ieb")
+
+
+def _index_of(ref):
+    lut = R.lut_with_extremes(np.zeros((256, 4), np.uint8))
+    return R.rasterise(ref, lut)[0]
+
+
+def _check_axes(ax, ref, what):
+    im = ax.images[-1]
+    assert same_float(im.vmin, ref["vmin"]) and same_float(im.vmax, ref["vmax"]), (what, im.vmin, ref["vmin"], im.vmax, ref["vmax"])
+    assert (im.norm == "log") == (ref["mode"] == "log"), what
+    assert np.array_equal(im.index, _index_of(ref)), what
+    assert np.array_equal(np.asarray(im.extent, dtype=np.float64), ref["extent"]), (what, im.extent, ref["extent"])
+
+
+def test_generic_plot_spectrogram_set_matches_reference():
+    from configurable_spectrograms_b200.plotting import generic_plot_spectrogram_set
+
+    g = load_npz("generic_set.npz")
+    for name in ("f32", "f64", "tep"):
+        ds = dataset_from_arrays({k[len(name) + 4 :]: v for k, v in g.items() if k.startswith(f"in_{name}_")})
+        for zs in ("linear", "log"):
+            ref = panels(g, f"{name}_{zs}")
+            fig, canvas = generic_plot_spectrogram_set(
+                [{"x": ds["times"], "y": ds["energy"], "data": ds["data"], "label": name}], z_scale=zs, colormap="viridis", show=False
+            )
+            assert fig is not None and canvas.figure is fig and len(fig.axes) == 1
+            _check_axes(fig.axes[0], ref[0], (name, zs))
+            assert fig.axes[0].title == name
+    ds = dataset_from_arrays({k[7:]: v for k, v in g.items() if k.startswith("in_f32_")})
+    ref = panels(g, "f32_zoom_log")
+    fig, _ = generic_plot_spectrogram_set(
+        [{"x": ds["times"], "y": ds["energy"], "data": ds["data"]}], zoom_center=float(ds["times"][20]),
+        zoom_window_seconds=50.0, z_scale="log", show=False,
+    )
+    _check_axes(fig.axes[0], ref[0], "zoom")
+    assert generic_plot_spectrogram_set([]) == (None, None)
+
+
+def test_make_spectrogram_conventions():
+    """(None, None) when everything is filtered out; caller arrays are never modified; matplotlib's
+    draw-time error for inverted bounds."""
+    from configurable_spectrograms_b200.plotting import make_spectrogram
+
+    rng = np.random.default_rng(3)
+    times = 946684800.0 + 2.5 * np.arange(30)
+    energy = np.linspace(4.0, 30000.0, 12)
+    cube = rng.poisson(3.0, (30, 5, 12)).astype(np.float32)
+    keep = cube.copy()
+    assert make_spectrogram(times, energy, cube, y_axis_min=-10, y_axis_max=-5) == (None, None)
+    ax, x_plot = make_spectrogram(times, energy, cube, y_axis_max=40000, vertical_lines_unix=[float(times[10])])
+    assert ax is not None and len(x_plot) == 30 and np.array_equal(cube, keep)
+    assert ax.images[-1].rgba.shape == (12, 30, 4)
+    assert any(l["kind"] == "vline" for l in ax.lines)
+    with pytest.raises(ValueError):  # LogNorm(vmin=50, vmax=10): matplotlib raises when the figure is drawn
+        make_spectrogram(times, energy, cube, y_axis_max=40000, z_axis_scale_function="log", z_axis_min=50.0, z_axis_max=10.0)
+    # inverted linear bounds fall back to the data range instead (reference plotting.py:313-315)
+    ax, _ = make_spectrogram(times, energy, cube, y_axis_max=40000, z_axis_min=50.0, z_axis_max=10.0)
+    with np.errstate(invalid="ignore"):
+        m = np.nansum(cube, axis=1)
+    assert ax.images[-1].vmin == float(m.min()) and ax.images[-1].vmax == float(m.max())
+    # integer cubes go through float64 exactly like numpy
+    ax, _ = make_spectrogram(times, energy, cube.astype(np.int64), y_axis_max=40000)
+    ref = R.panel(times, energy, cube.astype(np.float64), x_min=None, x_max=None, y_max=40000)
+    assert same_float(ax.images[-1].vmin, ref["vmin"]) and same_float(ax.images[-1].vmax, ref["vmax"])
+
+
+def _write_tree(tmp_path):
+    tree = load_npz("extrema_tree.npz")
+    keys = sorted({k.rsplit("_", 1)[0] for k in tree if k.endswith("_relpath")})
+    for stem in keys:
+        rel = str(tree[f"{stem}_relpath"])
+        path = tmp_path / rel
+        path.parent.mkdir(parents=True, exist_ok=True)
+        path.write_bytes(b"")
+        np.savez(str(path) + ".npz", **{v: tree[f"{stem}_{v}"] for v in ("time_unix", "data", "energy", "pitch_angle")})
+    (tmp_path / "FAST_Cusp_Indices.csv").write_text(str(tree["csv"]))
+
+
+def test_pitch_angle_and_instrument_grid_functions(tmp_path, monkeypatch):
+    from configurable_spectrograms_b200 import cdf_utils
+    from configurable_spectrograms_b200.fast.plotting import FAST_plot_instrument_grid, FAST_plot_pitch_angle_grid
+
+    g = load_npz("pa_grid.npz")
+    arrays = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    d = tmp_path / "one" / "2000" / "01"
+    d.mkdir(parents=True)
+    path = d / "fa_esa_l2_ees_20000101000000_777_v02.cdf"
+    path.write_bytes(b"")
+    np.savez(str(path) + ".npz", **arrays)
+    import pandas as pd
+
+    frame = pd.DataFrame({"Orbit Number": [777], "ees min Index": [80], "ees Max Index": [92]})
+    cdf_utils.orbit_column_cache.clear()
+    for zs in ("linear", "log"):
+        for variant, kw in (("raw", {}), ("given", dict(y_min=0.0, y_max=2900.0, z_min=0.0, z_max=460.0))):
+            ref = panels(g, f"{variant}_{zs}")
+            fig, canvas = FAST_plot_pitch_angle_grid(str(path), filtered_orbits_df=frame, orbit_number=777,
+                                                     scale_function_z=zs, show=False, colormap="turbo", **kw)
+            assert fig is not None and len(fig.axes) == 8
+            assert fig.suptitle_text == "Orbit 777 - Pitch Angle ees ESA Spectrograms"
+            for k, ax in enumerate(fig.axes):  # row-major: (row, Full), (row, Zoomed)
+                _check_axes(ax, ref[k], (zs, variant, k))
+            assert fig.axes[0].title == "Full" and fig.axes[1].title == "Zoomed"
+            assert [fig.axes[2 * i].yaxis.label.text for i in range(4)] == [
+                "All\n(0, 360)", "Downgoing\n(0, 30), (330, 360)", "Upgoing\n(150, 210)", "Perpendicular\n(40, 140), (210, 330)"]
+            out = tmp_path / f"pa_{zs}_{variant}.png"
+            fig.savefig(str(out), dpi=200)
+            assert out.stat().st_size > 1000
+    # instrument grid
+    g = load_npz("inst_grid.npz")
+    ext = json.loads(str(g["extrema_json"]))
+    files = {}
+    for inst in ORDER:
+        p = d / f"fa_esa_l2_{inst}_20000101000000_778_v02.cdf"
+        p.write_bytes(b"")
+        np.savez(str(p) + ".npz", **{k[len(inst) + 4 :]: v for k, v in g.items() if k.startswith(f"in_{inst}_")})
+        files[inst] = str(p)
+    cols = {"Orbit Number": [778]}
+    for inst in ORDER:
+        cols[f"{inst} min Index"], cols[f"{inst} Max Index"] = [40], [60]
+    frame = pd.DataFrame(cols)
+    cdf_utils.orbit_column_cache.clear()
+    for tag, ge in (("raw", None), ("given", ext)):
+        ref = panels(g, tag)
+        fig, _ = FAST_plot_instrument_grid(files, filtered_orbits_df=frame, orbit_number=778, scale_function_y="linear",
+                                           scale_function_z="log", show=False, colormap="viridis", global_extrema=ge)
+        assert len(fig.axes) == len(ref)
+        for k, ax in enumerate(fig.axes):
+            _check_axes(ax, ref[k], (tag, k))
+    assert FAST_plot_instrument_grid({}, show=False) == (None, None)
+
+
+def test_directory_driver_matches_reference_outputs(tmp_path, monkeypatch):
+    """FAST_plot_spectrograms_directory on the golden tree: statuses, PNG tree, extrema JSON and
+    progress keys as the reference wrote them."""
+    from configurable_spectrograms_b200 import cdf_utils, png
+    from configurable_spectrograms_b200.fast.batch_directory import FAST_plot_spectrograms_directory
+
+    _write_tree(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    cdf_utils.filtered_orbits_cache.clear()
+    cdf_utils.orbit_column_cache.clear()
+    gold = load_json("extrema_tree.json")
+    res = FAST_plot_spectrograms_directory(
+        "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", colormap="cividis",
+        max_processing_percentile=99, max_workers=2, progress_json_path="./progress.json",
+    )
+    assert sorted((r["orbit"], r["status"]) for r in res) == [tuple(x) for x in gold["batch_status"]]
+    pngs = []
+    for dirpath, _dirs, fs in os.walk("./FAST_plots"):
+        pngs += [os.path.relpath(os.path.join(dirpath, fn), "./FAST_plots") for fn in fs]
+    assert sorted(pngs) == gold["batch_pngs"]
+    assert json.load(open("./FAST_calculated_extrema.json")) == gold["batch_extrema"]
+    prog = json.load(open("./progress.json"))
+    assert set(prog) == set(gold["batch_progress"])
+    assert prog["linear_log_error_plotting"] == [] and prog["orbit_linear_log_timed_out"] == []
+    # (the reference's own last_orbit lags by its unflushed tail: 13004; ours records the true last orbit)
+    assert prog["linear_log_last_orbit"] == 13005
+    img = png.decode_rgba(open(os.path.join("./FAST_plots", gold["batch_pngs"][0]), "rb").read())
+    assert img.ndim == 3 and img.shape[2] == 4 and img.shape[0] > 100
+    # resume: nothing left to do, nothing re-plotted
+    again = FAST_plot_spectrograms_directory(
+        "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", colormap="cividis",
+        max_processing_percentile=99, max_workers=2, progress_json_path="./progress.json",
+    )
+    assert again == []
+
+
+def test_process_single_orbit_and_generic_batch(tmp_path, monkeypatch):
+    from configurable_spectrograms_b200 import cdf_utils
+    from configurable_spectrograms_b200.cdf_utils import load_fast_cdf_dataset, load_filtered_orbits
+    from configurable_spectrograms_b200.fast.orbit_discovery import discover_orbit_files
+    from configurable_spectrograms_b200.fast.process_orbit import FAST_process_single_orbit
+    from configurable_spectrograms_b200.generic_batch import generic_batch_plot
+
+    _write_tree(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    cdf_utils.filtered_orbits_cache.clear()
+    cdf_utils.orbit_column_cache.clear()
+    gold = load_json("extrema_tree.json")
+    frame = load_filtered_orbits()
+    files = discover_orbit_files("./FAST_data", ORDER)
+    for orbit in (13000, 13003):
+        r = FAST_process_single_orbit(orbit, files[orbit], frame, 6, "linear", "log", ORDER, "cividis", "./out/",
+                                      global_extrema=gold["batch_extrema"])
+        assert r == {"orbit": orbit, "status": "ok", "errors": []}
+        got = sorted(os.listdir(f"./out/2000/01/{orbit}"))
+        assert got == sorted(os.path.basename(p) for p in gold["batch_pngs"] if f"/{orbit}/" in p)
+    # generic batch: items are orbit numbers, one dataset per instrument present
+    def build(item):
+        return [
+            {"x": ds["times"], "y": ds["energy"], "data": ds["data"], "label": inst}
+            for inst, ds in ((i, load_fast_cdf_dataset(p)) for i, p in files[item].items())
+        ] if item != 13001 else []
+
+    res = generic_batch_plot([13000, 13001, 13002], "./generic_out", build, y_scale="linear", z_scale="log",
+                             max_workers=2, progress_json_path="./generic_progress.json", install_signal_handlers=False)
+    assert sorted(res) == [(13000, "ok"), (13001, "no_data"), (13002, "ok")]
+    assert os.path.exists("./generic_out/13000/generic.png") and not os.path.exists("./generic_out/13001")
+    prog = json.load(open("./generic_progress.json"))
+    assert sorted(prog["completed_items"]) == ["13000", "13002"] and prog["no_data"] == ["13001"] and prog["schema_version"] == 1
+    res = generic_batch_plot([13000, 13001, 13002], "./generic_out", build, max_workers=2,
+                             progress_json_path="./generic_progress.json", install_signal_handlers=False)
+    assert res == [(13001, "no_data")]  # completed items are skipped on resume
