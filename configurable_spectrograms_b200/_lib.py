@@ -133,6 +133,7 @@ SIGNATURES = {
     "csg_destroy": (None, [_vp]),
     "csg_last_error": (C.c_char_p, [_vp]),
     "csg_sync": (_i, [_vp]),
+    "csg_stream_handle": (_vp, [_vp]),
     "csg_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_sz)]),
     "csg_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "csg_dev_free": (_i, [_vp, _vp]),
@@ -311,6 +312,11 @@ class Context:
     def sync(self):
         self._check(self.lib.csg_sync(self.handle))
         self._alive.clear()
+
+    @property
+    def stream_handle(self) -> int:
+        """The cudaStream_t (as an integer) all of this context's work is enqueued on."""
+        return int(self.lib.csg_stream_handle(self.handle) or 0)
 
     def close(self):
         if self.handle:

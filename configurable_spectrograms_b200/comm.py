@@ -49,12 +49,26 @@ class TorchComm:
             t = cache[key] = self.torch.as_tensor(holder, device=self.device)
         return t
 
-    def allgather_dev(self, src_ptr: int, dst_ptr: int, nbytes: int):
-        """dst[rank][nbytes] <- every rank's src[nbytes] (enqueued behind the current stream's work)."""
-        self.dist.all_gather_into_tensor(self._tensor(dst_ptr, nbytes * self.size), self._tensor(src_ptr, nbytes))
+    def _on(self, stream_handle: int):
+        """Order the collective behind (and the following work after) the given cudaStream_t --
+        the libcsgpu context's stream -- whatever torch's current stream happens to be."""
+        torch = self.torch
+        if not stream_handle:
+            return torch.cuda.stream(torch.cuda.current_stream(self.device))
+        cache = self.__dict__.setdefault("_streams", {})
+        ext = cache.get(stream_handle)
+        if ext is None:
+            ext = cache[stream_handle] = torch.cuda.ExternalStream(stream_handle, device=self.device)
+        return torch.cuda.stream(ext)
 
-    def allreduce_max_dev(self, ptr: int, count: int, kind: str):
+    def allgather_dev(self, src_ptr: int, dst_ptr: int, nbytes: int, stream_handle: int = 0):
+        """dst[rank][nbytes] <- every rank's src[nbytes], enqueued behind the context stream's work."""
+        with self._on(stream_handle):
+            self.dist.all_gather_into_tensor(self._tensor(dst_ptr, nbytes * self.size), self._tensor(src_ptr, nbytes))
+
+    def allreduce_max_dev(self, ptr: int, count: int, kind: str, stream_handle: int = 0):
         torch = self.torch
         dt = {"i8": torch.int64, "f8": torch.float64, "i4": torch.int32}[kind]
         t = self._tensor(ptr, count * dt.itemsize).view(dt)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        with self._on(stream_handle):
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)

@@ -86,6 +86,8 @@ void csg_destroy(csg_ctx* ctx) {
 
 const char* csg_last_error(csg_ctx* ctx) { return ctx ? ctx->err : g_csg_err; }
 
+void* csg_stream_handle(csg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int csg_sync(csg_ctx* ctx) {
   CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CSG_OK;

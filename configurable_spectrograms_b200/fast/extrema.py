@@ -245,7 +245,8 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
     selector = getattr(shard, "_pool_selector", None)
     if selector is None:
         selector = shard._pool_selector = DevicePoolSelector(shard.batch)  # persistent scratch across steps
-    selector.enqueue(shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm)
+    selector.enqueue(shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm,
+                     count_rows=n_max)
     return {
         "shard": shard, "sequence": sequence, "instrument_order": instrument_order, "y_scale": y_scale, "z_scale": z_scale,
         "state": state, "compute_mins": compute_mins, "log_floor_cutoff": log_floor_cutoff,
@@ -265,13 +266,7 @@ def extrema_finish(pending, on_step_done=None):
     selector = pending["selector"]
     # ---- y extrema: per-step energy candidates from every rank's per-file positive counts
     # (available after the first histogram pass; this overlaps the digit loop on the GPU)
-    counts, npos = selector.result_counts()
-    if comm.size > 1:
-        padded = np.zeros((pending["n_max"], pending["max_E"]), dtype=np.int32)
-        padded[: len(counts)] = counts
-        all_counts = np.concatenate(comm.allgather(padded), axis=0)
-    else:
-        all_counts = counts
+    all_counts, npos = selector.result_counts()  # multi-rank: every rank's rows (device all-gather)
     cand_e: dict[str, dict[int, float]] = {}
     for inst in instrument_order:
         present, rows, energies = pending["eplan"][inst]
@@ -360,6 +355,8 @@ def compute_global_extrema(
     flush_state = {"since": 0}
 
     def dump(ordered_first: bool):
+        if _comm is not None and getattr(_comm, "rank", 0) != 0:
+            return True  # every rank holds the same state; rank 0 owns the cache file
         payload = state
         if ordered_first and last_key in state:
             payload = {last_key: state[last_key], **{k: v for k, v in state.items() if k != last_key}}

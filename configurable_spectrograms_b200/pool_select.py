@@ -234,7 +234,10 @@ class DevicePoolSelector:
         return dev
 
     def enqueue(self, dtype, items: np.ndarray, n_inst: int, inst_len: np.ndarray, max_E: int, requests: list[dict],
-                comm=None):
+                comm=None, count_rows: int | None = None):
+        """``count_rows`` (multi-rank): rows of the per-file count table every rank contributes to the
+        device all-gather (the largest item count over the ranks); ``result_counts`` then returns
+        every rank's rows, rank after rank."""
         comm = comm or SingleRank()
         ctx, lib, mem = self.ctx, self.ctx.lib, self.mem
         h, chk = ctx.handle, ctx._check
@@ -242,6 +245,7 @@ class DevicePoolSelector:
         code = _lib.np_dtype_code(D)
         plan = digit_plan(D)
         R, S = comm.size, self.N_SLOTS
+        sh = ctx.stream_handle if R > 1 else 0  # NCCL is ordered against THIS context's stream
         n_items, n_req = len(items), len(requests)
         max_pos = max(int(inst_len.max()) if len(inst_len) else 0, 1)
         if R > 1:  # the table shape must agree across ranks only per rank; exchanged buffers are per (inst, slot, bin)
@@ -261,22 +265,31 @@ class DevicePoolSelector:
         nb0 = 1 << bits0
         hist0 = mem.device("hist0", n_inst * max_pos * nb0 * 4)
         chk(lib.csg_memset(h, hist0.ptr, 0, n_inst * max_pos * nb0 * 4))
-        d_counts = mem.device("counts", max(n_items, 1) * max_E * 4)
+        rows = max(n_items, 1) if (R == 1 or count_rows is None) else max(int(count_rows), n_items, 1)
+        d_counts = mem.device("counts", rows * max_E * 4)
         d_npos = mem.device("npos", max(n_items, 1) * 4)
+        if R > 1:
+            chk(lib.csg_memset(h, d_counts.ptr, 0, rows * max_E * 4))
         sums = self.batch.d_sums.ptr
         if n_items:
             chk(lib.csg_pool_hist_first(h, sums, code, self.d_items.ptr, n_items, max_pos, bits0, max_E, hist0.ptr,
                                         d_counts.ptr, d_npos.ptr))
         # the per-energy positive counts are final here: read them back now so the host can work
         # on the y extrema while the digit loop runs
-        sizes = [("values", 64 * 8), ("has", 64 * 4), ("flags", 16), ("counts", n_items * max_E * 4), ("npos", n_items * 4)]
+        n_count_rows = n_items if R == 1 else R * rows
+        sizes = [("values", 64 * 8), ("has", 64 * 4), ("flags", 16), ("counts", n_count_rows * max_E * 4), ("npos", n_items * 4)]
         pin = mem.pinned("readback", sum(_al(n) for _, n in sizes))
         views, off = {}, 0
         for name, n in sizes:
             views[name] = (off, n)
             off += _al(n)
-        if n_items:
+        if R > 1:  # every rank's per-file counts, gathered on the device
+            d_counts_all = mem.device("counts_all", R * rows * max_E * 4)
+            comm.allgather_dev(d_counts.ptr, d_counts_all.ptr, rows * max_E * 4, sh)
+            chk(lib.csg_d2h(h, pin.ptr + views["counts"][0], d_counts_all.ptr, R * rows * max_E * 4))
+        elif n_items:
             chk(lib.csg_d2h(h, pin.ptr + views["counts"][0], d_counts.ptr, n_items * max_E * 4))
+        if n_items:
             chk(lib.csg_d2h(h, pin.ptr + views["npos"][0], d_npos.ptr, n_items * 4))
         ctx.event_record(self.EVENT_SLOT - 1)
         d_tot = mem.device("totals", n_inst * S * 1024 * 4) if R > 1 else None
@@ -285,7 +298,7 @@ class DevicePoolSelector:
         d_above = mem.device("above", n_inst * 8) if R > 1 else None
         chk(lib.csg_pool_scan(h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, d_tot.ptr if R > 1 else None))
         if R > 1:
-            comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * nb0 * 4)
+            comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * nb0 * 4, sh)
             chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, nb0, d_base.ptr, d_above.ptr))
         d_n_after = mem.device("n_after", n_inst * max_pos * 8)
         d_below = mem.device("below", n_inst * 8)
@@ -309,11 +322,11 @@ class DevicePoolSelector:
             nb = 1 << bits
             chk(lib.csg_pool_sel_bounds(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr))
             if R > 1:
-                comm.allreduce_max_dev(d_best.ptr, n_req, "i8")
+                comm.allreduce_max_dev(d_best.ptr, n_req, "i8", sh)
             chk(lib.csg_pool_sel_slots(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr, n_inst, S,
                                        d_local.ptr, d_flags.ptr))
             if R > 1:
-                comm.allgather_dev(d_local.ptr, d_gslots.ptr, n_inst * S * 8)
+                comm.allgather_dev(d_local.ptr, d_gslots.ptr, n_inst * S * 8, sh)
             chk(lib.csg_pool_sel_assign(h, d_sel.ptr, n_req, max_pos, d_gslots.ptr, R, n_inst, S, d_table.ptr, d_flags.ptr))
             nbytes = n_inst * max_pos * S * nb * 4
             hist1 = mem.device("hist1", nbytes)
@@ -323,20 +336,19 @@ class DevicePoolSelector:
                                              shift, bits, hist1.ptr))
             chk(lib.csg_pool_scan(h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_tot.ptr if R > 1 else None))
             if R > 1:
-                comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * S * nb * 4)
+                comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * S * nb * 4, sh)
                 chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, S * nb, d_base.ptr, None))
             chk(lib.csg_pool_sel_locate(h, hist1.ptr, max_pos, S, bits, base_ptr, d_sel.ptr, n_req, d_flags.ptr))
             prev_shift = shift
         chk(lib.csg_pool_sel_finish(h, code, d_sel.ptr, n_req, max_pos, d_values.ptr, d_has.ptr))
-        if R > 1:
-            comm.allreduce_max_dev(d_values.ptr, n_req, "f8")
-            comm.allreduce_max_dev(d_has.ptr, n_req, "i4")
-            comm.allreduce_max_dev(d_flags.ptr, 4, "i4")
+        if R > 1:  # "has" follows from the reduced value (-inf = no rank held an entry)
+            comm.allreduce_max_dev(d_values.ptr, n_req, "f8", sh)
+            comm.allreduce_max_dev(d_flags.ptr, 4, "i4", sh)
         # ---- asynchronous read-back of the few results
         for name, dev in (("values", d_values), ("has", d_has), ("flags", d_flags)):
             chk(lib.csg_d2h(h, pin.ptr + views[name][0], dev.ptr, views[name][1]))
         ctx.event_record(self.EVENT_SLOT)
-        self._pending = (pin, views, n_req, n_items, max_E)
+        self._pending = (pin, views, n_req, n_items, max_E, n_count_rows)
 
     def _view(self, name, dt):
         pin, views = self._pending[0], self._pending[1]
@@ -344,9 +356,9 @@ class DevicePoolSelector:
 
     def result_counts(self):
         """(counts[n_items][max_E], npos[n_items]) -- available right after the first histogram pass."""
-        _, _, _, n_items, max_E = self._pending
+        _, _, _, n_items, max_E, n_count_rows = self._pending
         self.ctx.event_sync(self.EVENT_SLOT - 1)
-        return self._view("counts", np.int32).reshape(n_items, max_E).copy(), self._view("npos", np.int32).copy()
+        return self._view("counts", np.int32).reshape(n_count_rows, max_E).copy(), self._view("npos", np.int32).copy()
 
     def result_values(self):
         """One float per request (None: empty pool), or None when the slot table overflowed."""
@@ -357,8 +369,8 @@ class DevicePoolSelector:
             return None
         if flags[0] or flags[2]:
             raise _lib.CsgError("device pool selection: a rank fell outside its bucket (histogram / scan mismatch)")
-        vals, has = self._view("values", np.float64)[:n_req], self._view("has", np.int32)[:n_req]
-        return [float(v) if ok else None for v, ok in zip(vals, has)]
+        vals = self._view("values", np.float64)[:n_req]
+        return [float(v) if np.isfinite(v) else None for v in vals]
 
     def result(self):
         """(values | None on slot overflow, counts, npos); waits for the read-backs only."""

@@ -63,6 +63,8 @@ CSG_API csg_ctx* csg_create(int device, void* external_stream);
 CSG_API void csg_destroy(csg_ctx* ctx);
 CSG_API const char* csg_last_error(csg_ctx* ctx); /* ctx may be NULL: error of a failed csg_create() */
 CSG_API int csg_sync(csg_ctx* ctx);
+/* the cudaStream_t every call of this context is enqueued on (for ordering external work, e.g. NCCL) */
+CSG_API void* csg_stream_handle(csg_ctx* ctx);
 /* "NVIDIA B200", SM count, total memory bytes */
 CSG_API int csg_device_info(csg_ctx* ctx, char* name, int name_len, int* sm_count, size_t* total_mem);
 

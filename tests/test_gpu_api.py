@@ -219,3 +219,25 @@ def test_process_single_orbit_and_generic_batch(tmp_path, monkeypatch):
     res = generic_batch_plot([13000, 13001, 13002], "./generic_out", build, max_workers=2,
                              progress_json_path="./generic_progress.json", install_signal_handlers=False)
     assert res == [(13001, "no_data")]  # completed items are skipped on resume
+
+
+def test_two_gpu_extrema_and_directory_driver(tmp_path):
+    """Ranks own contiguous orbit blocks; the NCCL exchange of bucket totals / surviving prefixes
+    must reproduce the reference's extrema JSON and PNG tree (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _write_tree(tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "multigpu_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    if r.returncode != 0:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "multigpu_worker_failure.log"), "w") as f:
+            f.write(r.stdout + "\n=====\n" + r.stderr)
+    assert r.returncode == 0 and "MULTIGPU_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
