@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -99,6 +99,8 @@ PANEL_NORM = np.dtype(
         ("t_range", "<f8"),
         ("status", "<i4"),
         ("degenerate", "<i4"),
+        ("c0", "<f4"),
+        ("c1", "<f4"),
     ],
     align=True,
 )
@@ -121,7 +123,7 @@ POOL_SEL = np.dtype(
 )
 assert POOL_REQUEST.itemsize == 16 and POOL_SEL.itemsize == 64
 assert FILE_DESC.itemsize == 56 and REGION.itemsize == 56 and REGION_STATS.itemsize == 64
-assert PANEL.itemsize == 56 and PANEL_NORM.itemsize == 56 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
+assert PANEL.itemsize == 56 and PANEL_NORM.itemsize == 64 and POOL_ITEM.itemsize == 24 and POOL_QUERY.itemsize == 32
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
@@ -162,7 +164,7 @@ SIGNATURES = {
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
-    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),

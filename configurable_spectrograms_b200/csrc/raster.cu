@@ -169,6 +169,7 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   csg_panel_norm nm;
   nm.status = CSG_NORM_OK;
   nm.degenerate = 0;
+  nm.c0 = nm.c1 = 0.f;
   if (p.log_scale) {
     // safe_vmin = nanmin(finite positive) or 1e-10; z_min = float(max(z_min, safe_vmin, 1e-10))  :261-276
     const double safe = own.n_pos > 0 ? own.min_pos : 1e-10;
@@ -219,6 +220,9 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
     else if (is_nan(zmin) || is_nan(zmax))
       nm.degenerate = 2;  // every normalised value is NaN -> "bad" colour
   }
+  // first-guess coefficients of the rasteriser: #{thresholds <= v} ~ c1 * (log2 v | v) + c0
+  nm.c1 = p.log_scale ? (float)(256.0 * 0.30102999566398120 / nm.t_range) : (float)(256.0 / nm.t_range);
+  nm.c0 = (float)(-256.0 * nm.t_vmin / nm.t_range) + 1.0f;
   norms[i] = nm;
 }
 
@@ -248,23 +252,28 @@ template <typename T>
 __global__ void __launch_bounds__(kRasterThreads, 4)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                      const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
-                     const csg_panel_norm* __restrict__ norms, int n_panels, const T* __restrict__ thresholds,
-                     const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
+                     const csg_panel_norm* __restrict__ norms, int n_panels, const int32_t* __restrict__ block_panel,
+                     const T* __restrict__ thresholds, const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
                      uint16_t* __restrict__ index) {
   __shared__ uint32_t s_lut[260];
   __shared__ T s_thr[kThr + 2 * kPad];  // [kPad + k] = thr[k]; -inf below, +inf above
 
   const int tid = threadIdx.x;
-  // ---- which panel owns this block (every thread runs the same cached binary search)
-  int lo = 0, hi = n_panels - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
-      lo = mid;
-    else
-      hi = mid - 1;
+  // ---- which panel owns this block: host-built table, else a cached binary search
+  int pi;
+  if (block_panel != nullptr) {
+    pi = __ldg(block_panel + blockIdx.x);
+  } else {
+    int lo = 0, hi = n_panels - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    pi = lo;
   }
-  const int pi = lo;
   const csg_panel* pn = panels + pi;
   const csg_region* rg = regions + __ldg(&pn->region);
   const csg_panel_norm* nm = norms + pi;
@@ -296,53 +305,70 @@ __global__ void __launch_bounds__(kRasterThreads, 4)
   }
   __syncthreads();
 
-  // first guess of n = #{thresholds <= v} from fast float math; verified against the table
-  const double t_vmin = __ldg(&nm->t_vmin), t_range = __ldg(&nm->t_range);
-  const float c1 = log_scale ? (float)(256.0 * 0.30102999566398120 / t_range) : (float)(256.0 / t_range);
-  const float c0 = (float)(-256.0 * t_vmin / t_range) + 1.0f;
+  const float c1 = __ldg(&nm->c1), c0 = __ldg(&nm->c0);
   const T fill_lo = (T)__ldg(&nm->fill_lo), fill_hi = (T)__ldg(&nm->fill_hi);
   const T* mat = mats + __ldg(&rg->mat_off);
   const int32_t* cols = pool + __ldg(&rg->cols_off);
   const int rows_off = __ldg(&rg->rows_off);
   const int32_t* rows = pool + (rows_off < 0 ? 0 : rows_off);
   const int ld = __ldg(&rg->ld), t0 = __ldg(&rg->t0);
-  // the pixel loop, specialised on the scale and on how time steps are addressed (32-bit index math)
+
+  // value -> LUT index: fast float guess of the threshold count, verified against the exact table
+  auto to_index = [&](T v, auto log_c) -> int {
+    constexpr bool LOG = decltype(log_c)::value;
+    // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
+    if (LOG) {
+      v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+    } else {
+      v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
+      v = (v == (T)CUDART_INF) ? fill_hi : v;
+    }
+    const float fv = (float)v;
+    float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
+    gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
+    int n = (int)gf;
+    // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
+    const T a = s_thr[kPad - 2 + n], b = s_thr[kPad - 1 + n], c = s_thr[kPad + n], d = s_thr[kPad + 1 + n];
+    if (a <= v && !(d <= v)) {
+      n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
+    } else {  // rare: the float guess was off by more than one
+#pragma unroll 1
+      while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
+#pragma unroll 1
+      while (n < kThr && s_thr[kPad + n] <= v) ++n;
+    }
+    int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
+    return is_nan(v) ? I_BAD : idx;
+  };
+
+  // the pixel loop, specialised on the scale and on how time steps are addressed; 32-bit index
+  // math, four independent cells in flight per thread
   auto pixels = [&](auto log_c, auto rowlist_c) {
-    constexpr bool LOG = decltype(log_c)::value, ROWLIST = decltype(rowlist_c)::value;
+    constexpr bool ROWLIST = decltype(rowlist_c)::value;
+    constexpr int U = 4;
     unsigned i = first + tid;
     unsigned j = i / nt, tt = i - j * nt;
     const unsigned dq = kRasterThreads / nt, dr = kRasterThreads - dq * nt;
-    unsigned j_cached = ~0u, row_base = 0;
-#pragma unroll 2
+    auto address = [&](unsigned jj, unsigned t) -> unsigned {
+      return (unsigned)(__ldg(cols + jj) * ld + (ROWLIST ? __ldg(rows + t) : t0 + (int)t));
+    };
+    for (; i + (U - 1) * kRasterThreads < last; i += U * kRasterThreads) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = __ldg(mat + address(j, tt));
+        j += dq, tt += dr;
+        if (tt >= nt) tt -= nt, ++j;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = to_index(v[u], log_c);
+        if (out_rgba) out_rgba[i + u * kRasterThreads] = s_lut[idx];
+        if (out_idx) out_idx[i + u * kRasterThreads] = (uint16_t)idx;
+      }
+    }
     for (; i < last; i += kRasterThreads) {
-      if (j != j_cached) {  // a new image row: its energy channel's matrix row
-        row_base = (unsigned)(__ldg(cols + j) * ld + (ROWLIST ? 0 : t0));
-        j_cached = j;
-      }
-      T v = __ldg(mat + (row_base + (ROWLIST ? (unsigned)__ldg(rows + tt) : tt)));
-      // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
-      if (LOG) {
-        v = (is_finite(v) && v > T(0)) ? v : fill_lo;
-      } else {
-        v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
-        v = (v == (T)CUDART_INF) ? fill_hi : v;
-      }
-      const float fv = (float)v;
-      float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
-      gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
-      int n = (int)gf;
-      // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
-      const T a = s_thr[kPad - 2 + n], b = s_thr[kPad - 1 + n], c = s_thr[kPad + n], d = s_thr[kPad + 1 + n];
-      if (a <= v && !(d <= v)) {
-        n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
-      } else {  // rare: the float guess was off by more than one
-#pragma unroll 1
-        while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
-#pragma unroll 1
-        while (n < kThr && s_thr[kPad + n] <= v) ++n;
-      }
-      int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
-      idx = is_nan(v) ? I_BAD : idx;
+      const int idx = to_index(__ldg(mat + address(j, tt)), log_c);
       if (out_rgba) out_rgba[i] = s_lut[idx];
       if (out_idx) out_idx[i] = (uint16_t)idx;
       j += dq, tt += dr;
@@ -400,8 +426,8 @@ int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels, con
 
 int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels, const csg_panel_norm* d_norms,
-                  const void* d_thresholds, int n_panels, int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba,
-                  uint16_t* d_index) {
+                  const void* d_thresholds, int n_panels, int total_blocks, const int32_t* d_block_panel,
+                  const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_panels <= 0 || total_blocks <= 0) return CSG_OK;
   if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms || !d_thresholds)
@@ -409,11 +435,11 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
   if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
   if (dtype == CSG_F32)
     rasterise_kernel<float><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
-                                                                   d_norms, n_panels, (const float*)d_thresholds,
+                                                                   d_norms, n_panels, d_block_panel, (const float*)d_thresholds,
                                                                    (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else if (dtype == CSG_F64)
     rasterise_kernel<double><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
-                                                                    d_panels, d_norms, n_panels,
+                                                                    d_panels, d_norms, n_panels, d_block_panel,
                                                                     (const double*)d_thresholds, (const uint32_t*)d_lut,
                                                                     (uint32_t*)d_rgba, d_index);
   else

@@ -407,7 +407,11 @@ class Batch:
     def upload_panels(self):
         panels = np.array(self._panels, dtype=PANEL) if self._panels else np.zeros(0, PANEL)
         self.d_panels = self.ctx.to_device(panels) if len(panels) else None
+        self.d_block_panel = None
         if len(panels):
+            first = panels["first_block"].astype(np.int64)
+            counts = np.diff(np.append(first, self._raster_blocks))
+            self.d_block_panel = self.ctx.to_device(np.repeat(np.arange(len(panels), dtype=np.int32), counts))
             if self.d_norms is None or self.d_norms.nbytes < len(panels) * PANEL_NORM.itemsize:
                 self.d_norms = self.ctx.alloc(len(panels) * PANEL_NORM.itemsize)
             thr_bytes = self.ctx.lib.csg_threshold_bytes(len(panels), self.code)
@@ -485,6 +489,7 @@ class Batch:
             self.ctx.lib.csg_rasterise(
                 self.ctx.handle, self.d_sums.ptr, self.code, self.d_regions.ptr, self.d_pool.ptr, self.d_panels.ptr,
                 self.d_norms.ptr, self.d_thr.ptr, len(self._panels), self._raster_blocks,
+                self.d_block_panel.ptr if getattr(self, "d_block_panel", None) is not None else None,
                 self.d_lut.ptr if self.d_lut is not None else None,
                 self.d_rgba.ptr if want_rgba else None, self.d_index.ptr if want_index else None,
             )

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 4
+#define CSG_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -214,7 +214,8 @@ typedef struct {
   double t_vmin, t_range;  /* log: log10(vmin), log10(vmax)-log10(vmin); linear: vmin, vmax-vmin  */
   int32_t status;          /* CSG_NORM_*                                                          */
   int32_t degenerate;      /* 1: vmin == vmax -> every cell maps to index 0; 2: NaN bound -> all "bad" */
-} csg_panel_norm;          /* 56 bytes */
+  float c0, c1;            /* rasteriser's first-guess coefficients (internal)                    */
+} csg_panel_norm;          /* 64 bytes */
 
 CSG_API int32_t csg_raster_blocks(int32_t ne, int32_t nt);
 
@@ -229,14 +230,17 @@ CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_pan
                       const csg_region* d_regions, const csg_region_stats* d_stats, int dtype,
                       const double* d_zvals, csg_panel_norm* d_norms, void* d_thresholds);
 
-/* Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
+/* d_block_panel (may be NULL): panel index of every thread block, i.e. panel p repeated
+ * csg_raster_blocks(ne_p, nt_p) times; without it every block binary-searches first_block.
+ * Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
  * under, over, bad).  d_index (uint16, may be NULL) receives Colormap indices 0..255 and
  * 256/257/258 for under/over/bad; d_rgba (may be NULL) the colours.  Row 0 of a panel is
  * the lowest energy (imshow origin="lower"). */
 CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels,
                   const csg_panel_norm* d_norms, const void* d_thresholds, int n_panels,
-                  int total_blocks, const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index);
+                  int total_blocks, const int32_t* d_block_panel, const uint8_t* d_lut, uint8_t* d_rgba,
+                  uint16_t* d_index);
 
 /* ---------------------------------------------- K2b: global extrema (pooled) */
 /* The pooled finite-positive samples of CS/fast/extrema.py:259-267 are never
