@@ -7,8 +7,8 @@
 // A region is a set of energy rows x a time range of one energy-major collapsed matrix, so its
 // cells are contiguous runs.  One thread block per region, ONE pass over the cells:
 //
-//   sample   1024 strided cells are sorted in shared memory; for each wanted percentile two
-//            pivots bracket its quantile with a 4.5-sigma margin (pivots are sample VALUES, so
+//   sample   2048 evenly spread cells are sorted in shared memory; for each wanted percentile two
+//            pivots bracket its quantile with a 3.5-sigma margin (pivots are sample VALUES, so
 //            heavy ties -- spectrogram counts repeat massively -- collapse a bracket onto the
 //            tied value instead of widening it)
 //   pass     every cell is classified (NaN / inf / positive, min / max reductions) and compared
@@ -29,7 +29,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSample = 4096;   // two-sided brackets at the 1st / 99th percentile need m*(1-q) > 4.5 sigma
+constexpr int kSample = 4096;   // storage shared by the sample and the candidate lists
+constexpr int kDraw = 2048;     // sample size: two-sided brackets at the 1st / 99th percentile need m*(1-q) > margin
 constexpr int kCand = 2048;     // candidate capacity per bracket (the lists reuse the sample's storage)
 static_assert(2 * kCand == kSample, "candidate lists alias the sample buffer");
 constexpr int kMaxCols = 1024;  // energy-row lists up to this length are staged in shared memory
@@ -37,8 +38,9 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kTargets = 4;  // (lo, hi) neighbours of two percentiles
 
+// Bitonic sort of n_pow2 keys in shared memory (any power of two; used for short lists).
 template <typename U>
-__device__ void bitonic_sort(U* a, int n_pow2) {
+__device__ void bitonic_sort_small(U* a, int n_pow2) {
   for (int k = 2; k <= n_pow2; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       __syncthreads();
@@ -54,64 +56,142 @@ __device__ void bitonic_sort(U* a, int n_pow2) {
   __syncthreads();
 }
 
-// Walk the region warp-per-energy-row.  fn(v, in) is called with warp-uniform control flow
-// (`in` = this lane holds a real cell), so it may use full-mask warp primitives.
+// Bitonic sort of kThreads * C keys: every thread keeps C consecutive keys in registers.  Compare-
+// exchange distances below C stay inside the thread, distances below 32 * C are warp shuffles, and
+// only the few largest distances go through shared memory (two barriers each).
+template <typename U, int C>
+__device__ void bitonic_sort_regs(U* a) {
+  constexpr int N = kThreads * C;
+  const int t = threadIdx.x, base = t * C;
+  U r[C];
+  __syncthreads();  // the keys were just written by other threads
+#pragma unroll
+  for (int e = 0; e < C; ++e) r[e] = a[base + e];
+  auto keep = [](U mine, U other, bool want_min) { return want_min == (mine < other) ? mine : other; };
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32 * C) {  // partner in another warp: through shared memory
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < C; ++e) a[base + e] = r[e];
+        __syncthreads();
+        const bool up = (base & k) == 0, low = (base & j) == 0;
+#pragma unroll
+        for (int e = 0; e < C; ++e) r[e] = keep(r[e], a[(base + e) ^ j], low == up);
+      } else if (j >= C) {  // partner in another lane, same element slot
+        const bool up = (base & k) == 0, low = (base & j) == 0;
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+          const U other = __shfl_xor_sync(0xffffffffu, r[e], j / C);
+          r[e] = keep(r[e], other, low == up);
+        }
+      } else {  // both keys in this thread
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+          const int l = e ^ j;
+          if (l > e) {
+            const bool up = ((base + e) & k) == 0;
+            const U x = r[e], y = r[l];
+            const bool swap = (x > y) == up;
+            r[e] = swap ? y : x;
+            r[l] = swap ? x : y;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < C; ++e) a[base + e] = r[e];
+  __syncthreads();
+}
+
+template <typename U>
+__device__ void block_sort(U* a, int n_pow2) {
+  switch (n_pow2) {
+    case kThreads * 2: bitonic_sort_regs<U, 2>(a); break;
+    case kThreads * 4: bitonic_sort_regs<U, 4>(a); break;
+    case kThreads * 8: bitonic_sort_regs<U, 8>(a); break;
+    default: bitonic_sort_small(a, n_pow2);
+  }
+}
+
+// Walk every cell of a region with all lanes busy: the (energy row, 16-byte vector) items of a
+// contiguous-time region are flattened over the block (two vector loads in flight per thread);
+// the few unaligned head / tail cells of every row and row-list regions take a scalar loop.
+// fn(v, in) is called with block-uniform control flow (`in` = this lane holds a real cell), so
+// it may use full-mask warp primitives.
 template <typename T, typename Fn>
 __device__ __forceinline__ void for_each_cell(const T* __restrict__ mats, const csg_region& rg,
                                               const int32_t* __restrict__ pool, const int* s_cols, bool cols_in_smem,
                                               Fn&& fn) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const T* base = mats + rg.mat_off;
   constexpr int V = 16 / sizeof(T);
-  for (int j = warp; j < rg.ne; j += kWarps) {
-    const int col = cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j);
-    const T* row = base + (long long)col * rg.ld;
-    const int nt = rg.nt;
-    if (rg.rows_off < 0) {
-      const T* p = row + rg.t0;
-      // peel to 16-byte alignment, vector body (two loads in flight), scalar tail
-      int head = (int)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(T));
-      if (head > nt) head = nt;
-      if (head > 0) {
-        const bool in = lane < head;
-        fn(in ? __ldg(p + lane) : T(0), in);
+  const int tid = threadIdx.x;
+  const T* base = mats + rg.mat_off;
+  const int ne = rg.ne, nt = rg.nt;
+  auto col_of = [&](int j) { return cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j); };
+  const bool vec_ok = rg.rows_off < 0 && (rg.ld % V) == 0 && ((reinterpret_cast<uintptr_t>(mats) & 15) == 0);
+  int head = 0, nvec = 0;
+  if (vec_ok) {
+    const int mis = (int)((rg.mat_off + rg.t0) % V);
+    head = (V - mis) % V;
+    if (head > nt) head = nt;
+    nvec = (nt - head) / V;
+  }
+  if (nvec > 0) {
+    const long long total = (long long)ne * nvec;
+    // item -> (row, vector) advanced incrementally: no division in the loop
+    const int stride = 2 * kThreads;
+    const int dq = stride / nvec, dr = stride - dq * nvec;
+    int ra = tid / nvec, va = tid - ra * nvec;
+    int rb = (tid + kThreads) / nvec, vb = (tid + kThreads) - rb * nvec;
+    for (long long it0 = 0; it0 < total; it0 += stride) {
+      const bool ina = it0 + tid < total, inb = it0 + tid + kThreads < total;
+      T a[V], b[V];
+      if constexpr (sizeof(T) == 4) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 qa = ina ? __ldg(reinterpret_cast<const float4*>(base + (long long)col_of(ra) * rg.ld + rg.t0 + head) + va) : z;
+        const float4 qb = inb ? __ldg(reinterpret_cast<const float4*>(base + (long long)col_of(rb) * rg.ld + rg.t0 + head) + vb) : z;
+        a[0] = (T)qa.x, a[1] = (T)qa.y, a[V - 2] = (T)qa.z, a[V - 1] = (T)qa.w;
+        b[0] = (T)qb.x, b[1] = (T)qb.y, b[V - 2] = (T)qb.z, b[V - 1] = (T)qb.w;
+      } else {
+        const double2 z = make_double2(0.0, 0.0);
+        const double2 qa = ina ? __ldg(reinterpret_cast<const double2*>(base + (long long)col_of(ra) * rg.ld + rg.t0 + head) + va) : z;
+        const double2 qb = inb ? __ldg(reinterpret_cast<const double2*>(base + (long long)col_of(rb) * rg.ld + rg.t0 + head) + vb) : z;
+        a[0] = (T)qa.x, a[V - 1] = (T)qa.y;
+        b[0] = (T)qb.x, b[V - 1] = (T)qb.y;
       }
-      const int nvec = (nt - head) / V;
-      const T* pv = p + head;
-      for (int i0 = 0; i0 < nvec; i0 += 64) {
-        const int ia = i0 + lane, ib = i0 + 32 + lane;
-        const bool ina = ia < nvec, inb = ib < nvec;
-        T a[V], b[V];
-        if constexpr (sizeof(T) == 4) {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 ra = ina ? __ldg(reinterpret_cast<const float4*>(pv) + ia) : z;
-          const float4 rb = inb ? __ldg(reinterpret_cast<const float4*>(pv) + ib) : z;
-          a[0] = (T)ra.x, a[1] = (T)ra.y, a[V - 2] = (T)ra.z, a[V - 1] = (T)ra.w;
-          b[0] = (T)rb.x, b[1] = (T)rb.y, b[V - 2] = (T)rb.z, b[V - 1] = (T)rb.w;
-        } else {
-          const double2 z = make_double2(0.0, 0.0);
-          const double2 ra = ina ? __ldg(reinterpret_cast<const double2*>(pv) + ia) : z;
-          const double2 rb = inb ? __ldg(reinterpret_cast<const double2*>(pv) + ib) : z;
-          a[0] = (T)ra.x, a[V - 1] = (T)ra.y;
-          b[0] = (T)rb.x, b[V - 1] = (T)rb.y;
-        }
 #pragma unroll
-        for (int v = 0; v < V; ++v) fn(a[v], ina);
-        if (i0 + 32 < nvec) {
+      for (int v = 0; v < V; ++v) fn(a[v], ina);
+      if (it0 + kThreads < total) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) fn(b[v], inb);
-        }
+        for (int v = 0; v < V; ++v) fn(b[v], inb);
       }
-      const int done = head + nvec * V;
-      if (done < nt) {  // fewer than V cells
-        const bool in = done + lane < nt;
-        fn(in ? __ldg(p + done + lane) : T(0), in);
+      ra += dq, va += dr;
+      if (va >= nvec) va -= nvec, ++ra;
+      rb += dq, vb += dr;
+      if (vb >= nvec) vb -= nvec, ++rb;
+    }
+  }
+  // scalar cells: the head and tail of every row (vector path), or every cell otherwise
+  const int done = head + nvec * V;          // cells [head, done) of a row went through the vector loop
+  const int per_row = nvec > 0 ? nt - (done - head) : nt;
+  if (per_row > 0) {
+    const long long total = (long long)ne * per_row;
+    for (long long it0 = 0; it0 < total; it0 += kThreads) {
+      const long long it = it0 + tid;
+      const bool in = it < total;
+      T v = T(0);
+      if (in) {
+        const int j = (int)(it / per_row);
+        int k = (int)(it - (long long)j * per_row);
+        if (nvec > 0 && k >= head) k += done - head;  // skip the vectorised middle
+        const int t = rg.rows_off < 0 ? rg.t0 + k : __ldg(pool + rg.rows_off + k);
+        v = __ldg(base + (long long)col_of(j) * rg.ld + t);
       }
-    } else {
-      for (int k0 = 0; k0 < nt; k0 += 32) {
-        const bool in = k0 + lane < nt;
-        fn(in ? __ldg(row + __ldg(pool + rg.rows_off + k0 + lane)) : T(0), in);
-      }
+      fn(v, in);
     }
   }
 }
@@ -151,17 +231,17 @@ __global__ void __launch_bounds__(kThreads)
   if (pct && !small) {
     // evenly spread sample positions (n_cells > kSample / 2, so neighbours may repeat a cell for
     // regions below kSample cells: harmless, the sample only places the pivots)
-    for (int s = tid; s < kSample; s += kThreads) {
-      const long long cell = ((2 * (long long)s + 1) * n_cells) / (2 * kSample);
+    for (int s = tid; s < kDraw; s += kThreads) {
+      const long long cell = ((2 * (long long)s + 1) * n_cells) / (2 * kDraw);
       const int j = (int)(cell / rg.nt), k = (int)(cell - (long long)j * rg.nt);
       const int col = cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j);
       const int t = rg.rows_off < 0 ? rg.t0 + k : __ldg(pool + rg.rows_off + k);
       const T v = __ldg(mats + rg.mat_off + (long long)col * rg.ld + t);
       s_keys[s] = is_nan(v) ? KEY_MAX : Key<T>::key(v);  // NaN sorts to the end
     }
-    bitonic_sort(s_keys, kSample);
+    block_sort(s_keys, kDraw);
     if (tid < 2) {
-      int lo = 0, hi = kSample;  // valid sample size m: the NaN sentinels sit at the end
+      int lo = 0, hi = kDraw;  // valid sample size m: the NaN sentinels sit at the end
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (s_keys[mid] == KEY_MAX)
@@ -174,7 +254,8 @@ __global__ void __launch_bounds__(kThreads)
       U plo = KEY_MIN, phi = KEY_MAX;
       if (m >= 16 && q >= 0.0 && q <= 1.0) {
         const double centre = q * (m - 1);
-        const double delta = 4.5 * sqrt(m * q * (1.0 - q)) + 3.0;
+        // 3.5 sigma + 2: a rank escapes its bracket about once in a thousand regions (-> exact fallback)
+        const double delta = 3.5 * sqrt(m * q * (1.0 - q)) + 2.0;
         const int a = (int)floor(centre - delta), b = (int)ceil(centre + delta);
         if (a >= 0) plo = s_keys[a];
         if (b < m) phi = s_keys[b];
@@ -277,7 +358,7 @@ __global__ void __launch_bounds__(kThreads)
       int np2 = 1;
       while (np2 < n) np2 <<= 1;
       for (int i = n + tid; i < np2; i += kThreads) s_cand[b][i] = KEY_MAX;
-      bitonic_sort(s_cand[b], np2);
+      block_sort(s_cand[b], np2);
     }
   }
   if (tid == 0) {
