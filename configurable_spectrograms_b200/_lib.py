@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 7
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -164,10 +164,10 @@ SIGNATURES = {
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
-    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
-    "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "csg_pool_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),
     "csg_pool_row_totals": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "csg_pool_sel_init": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),

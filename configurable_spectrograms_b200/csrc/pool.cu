@@ -142,23 +142,46 @@ __global__ void __launch_bounds__(kThreads)
       [](int) {});
 }
 
-// thread = one (inst, slot, bin) column; walk the instrument's files in orbit order
-__global__ void pool_scan_kernel(uint32_t* __restrict__ hist, int n_inst, int max_pos,
-                                 const int32_t* __restrict__ inst_len, int n_slots, int nb,
-                                 uint32_t* __restrict__ totals) {
+// Inclusive scan along the file sequence.  Block = 32 consecutive (slot, bin) columns of one
+// instrument x 8 segments of the sequence: every thread sums its segment, the segment totals
+// are scanned in shared memory, a second walk writes the running sums (coalesced 128-byte rows).
+// Slots whose table entry is the UINT64_MAX padding hold no data and are skipped.
+constexpr int kScanCols = 32;
+constexpr int kScanSegs = 8;
+
+__global__ void __launch_bounds__(kScanCols* kScanSegs)
+    pool_scan_kernel(uint32_t* __restrict__ hist, int n_inst, int max_pos, const int32_t* __restrict__ inst_len,
+                     int n_slots, int nb, const uint64_t* __restrict__ slot_table, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_seg[kScanSegs][kScanCols + 1];
   const size_t cols = (size_t)n_slots * nb;
-  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (size_t)n_inst * cols) return;
-  const int inst = (int)(gid / cols);
-  const size_t col = gid - (size_t)inst * cols;
+  const int blocks_per_inst = (int)((cols + kScanCols - 1) / kScanCols);
+  const int inst = blockIdx.x / blocks_per_inst;
+  const size_t col = (size_t)(blockIdx.x - inst * blocks_per_inst) * kScanCols + (threadIdx.x % kScanCols);
+  const int seg = threadIdx.x / kScanCols;
+  const bool in = col < cols;
+  const int slot = in ? (int)(col / nb) : 0;
+  const bool live = in && (slot_table == nullptr || slot_table[(size_t)inst * n_slots + slot] != ~0ull);
   const int len = inst_len[inst];
+  const int per = (len + kScanSegs - 1) / kScanSegs;
+  const int k0 = seg * per, k1 = min(len, k0 + per);
   uint32_t* p = hist + (size_t)inst * max_pos * cols + col;
+  uint32_t sum = 0;
+  if (live)
+    for (int k = k0; k < k1; ++k) sum += p[(size_t)k * cols];
+  s_seg[seg][threadIdx.x % kScanCols] = sum;
+  __syncthreads();
   uint32_t run = 0;
-  for (int k = 0; k < len; ++k) {
-    run += p[(size_t)k * cols];
-    p[(size_t)k * cols] = run;
+  for (int g = 0; g < seg; ++g) run += s_seg[g][threadIdx.x % kScanCols];
+  if (live)
+    for (int k = k0; k < k1; ++k) {
+      run += p[(size_t)k * cols];
+      p[(size_t)k * cols] = run;
+    }
+  if (totals && in && seg == kScanSegs - 1) {
+    uint32_t total = 0;
+    for (int g = 0; g < kScanSegs; ++g) total += s_seg[g][threadIdx.x % kScanCols];
+    totals[(size_t)inst * cols + col] = live ? total : 0u;
   }
-  if (totals) totals[gid] = run;
 }
 
 // block = one query: find the bin where the cumulative count of row (inst,pos,slot) crosses rank
@@ -253,12 +276,13 @@ int csg_pool_hist_refine(csg_ctx* ctx, const void* d_mats, int dtype, const csg_
 }
 
 int csg_pool_scan(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len, int n_slots,
-                  int bits, uint32_t* d_totals) {
+                  int bits, const uint64_t* d_slot_table, uint32_t* d_totals) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_inst <= 0 || max_pos <= 0) return CSG_OK;
-  const size_t n = (size_t)n_inst * n_slots * ((size_t)1 << bits);
-  const int blocks = (int)((n + 255) / 256);
-  pool_scan_kernel<<<blocks, 256, 0, ctx->stream>>>(d_hist, n_inst, max_pos, d_inst_len, n_slots, 1 << bits, d_totals);
+  const size_t cols = (size_t)n_slots * ((size_t)1 << bits);
+  const int blocks = n_inst * (int)((cols + kScanCols - 1) / kScanCols);
+  pool_scan_kernel<<<blocks, kScanCols * kScanSegs, 0, ctx->stream>>>(d_hist, n_inst, max_pos, d_inst_len, n_slots, 1 << bits,
+                                                                       d_slot_table, d_totals);
   CSG_LAUNCH_CHECK(ctx, "pool_scan_kernel");
   return CSG_OK;
 }

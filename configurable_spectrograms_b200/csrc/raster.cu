@@ -252,22 +252,23 @@ template <typename T>
 __global__ void __launch_bounds__(kRasterThreads, 4)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                      const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
-                     const csg_panel_norm* __restrict__ norms, int n_panels, const int32_t* __restrict__ block_panel,
-                     const T* __restrict__ thresholds, const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba,
-                     uint16_t* __restrict__ index) {
+                     const csg_panel_norm* __restrict__ norms, int n_panels, int block_offset,
+                     const int32_t* __restrict__ block_panel, const T* __restrict__ thresholds,
+                     const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba, uint16_t* __restrict__ index) {
   __shared__ uint32_t s_lut[260];
   __shared__ T s_thr[kThr + 2 * kPad];  // [kPad + k] = thr[k]; -inf below, +inf above
 
   const int tid = threadIdx.x;
+  const int blk = (int)blockIdx.x + block_offset;
   // ---- which panel owns this block: host-built table, else a cached binary search
   int pi;
   if (block_panel != nullptr) {
-    pi = __ldg(block_panel + blockIdx.x);
+    pi = __ldg(block_panel + blk);
   } else {
     int lo = 0, hi = n_panels - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&panels[mid].first_block) <= (int)blockIdx.x)
+      if (__ldg(&panels[mid].first_block) <= blk)
         lo = mid;
       else
         hi = mid - 1;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kRasterThreads, 4)
   const bool log_scale = __ldg(&pn->log_scale) != 0;
   const unsigned nt = (unsigned)__ldg(&rg->nt);
   const unsigned n_pix = (unsigned)__ldg(&rg->ne) * nt;
-  const unsigned first = (unsigned)((int)blockIdx.x - __ldg(&pn->first_block)) * kPixPerBlock;
+  const unsigned first = (unsigned)(blk - __ldg(&pn->first_block)) * kPixPerBlock;
   const unsigned last = first + kPixPerBlock < n_pix ? first + kPixPerBlock : n_pix;
   const long long out_off = __ldg(&pn->out_off);
   uint32_t* out_rgba = rgba ? rgba + out_off : nullptr;
@@ -426,8 +427,8 @@ int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_panels, con
 
 int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels, const csg_panel_norm* d_norms,
-                  const void* d_thresholds, int n_panels, int total_blocks, const int32_t* d_block_panel,
-                  const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index) {
+                  const void* d_thresholds, int n_panels, int total_blocks, int block_offset,
+                  const int32_t* d_block_panel, const uint8_t* d_lut, uint8_t* d_rgba, uint16_t* d_index) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_panels <= 0 || total_blocks <= 0) return CSG_OK;
   if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms || !d_thresholds)
@@ -435,11 +436,11 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
   if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
   if (dtype == CSG_F32)
     rasterise_kernel<float><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
-                                                                   d_norms, n_panels, d_block_panel, (const float*)d_thresholds,
+                                                                   d_norms, n_panels, block_offset, d_block_panel, (const float*)d_thresholds,
                                                                    (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else if (dtype == CSG_F64)
     rasterise_kernel<double><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
-                                                                    d_panels, d_norms, n_panels, d_block_panel,
+                                                                    d_panels, d_norms, n_panels, block_offset, d_block_panel,
                                                                     (const double*)d_thresholds, (const uint32_t*)d_lut,
                                                                     (uint32_t*)d_rgba, d_index);
   else

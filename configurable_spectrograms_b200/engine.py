@@ -405,18 +405,33 @@ class Batch:
         self.upload_panels()
 
     def upload_panels(self):
-        panels = np.array(self._panels, dtype=PANEL) if self._panels else np.zeros(0, PANEL)
-        self.d_panels = self.ctx.to_device(panels) if len(panels) else None
-        self.d_block_panel = None
-        if len(panels):
-            first = panels["first_block"].astype(np.int64)
-            counts = np.diff(np.append(first, self._raster_blocks))
-            self.d_block_panel = self.ctx.to_device(np.repeat(np.arange(len(panels), dtype=np.int32), counts))
-            if self.d_norms is None or self.d_norms.nbytes < len(panels) * PANEL_NORM.itemsize:
-                self.d_norms = self.ctx.alloc(len(panels) * PANEL_NORM.itemsize)
-            thr_bytes = self.ctx.lib.csg_threshold_bytes(len(panels), self.code)
-            if self.d_thr is None or self.d_thr.nbytes < thr_bytes:
-                self.d_thr = self.ctx.alloc(thr_bytes)
+        """Panel table -> device.  Panels whose bounds do not depend on the per-step z slots come
+        first, so they can be resolved and rasterised before the slot values are known."""
+        self.d_panels = self.d_block_panel = None
+        self._dev_order = np.zeros(0, np.int64)
+        self._n_free = self._blocks_free = 0
+        if not self._panels:
+            return
+        logical = np.array(self._panels, dtype=PANEL)
+        free = (logical["zmin_slot"] < 0) & (logical["zmax_slot"] < 0)
+        order = np.concatenate([np.flatnonzero(free), np.flatnonzero(~free)])
+        dev = logical[order]
+        blocks = np.array([self.ctx.lib.csg_raster_blocks(self._regions[p["region"]][6], self._regions[p["region"]][3])
+                           for p in dev], dtype=np.int64)
+        first = np.concatenate([[0], np.cumsum(blocks)[:-1]])
+        dev["first_block"] = first
+        # region-stat references stay valid (they index regions, not panels)
+        self._dev_order = order
+        self._n_free = int(free.sum())
+        self._blocks_free = int(blocks[: self._n_free].sum())
+        self.d_panels = self.ctx.to_device(dev)
+        self.d_block_panel = self.ctx.to_device(np.repeat(np.arange(len(dev), dtype=np.int32), blocks))
+        n = len(dev)
+        if self.d_norms is None or self.d_norms.nbytes < n * PANEL_NORM.itemsize:
+            self.d_norms = self.ctx.alloc(n * PANEL_NORM.itemsize)
+        thr_bytes = self.ctx.lib.csg_threshold_bytes(n, self.code)
+        if self.d_thr is None or self.d_thr.nbytes < thr_bytes:
+            self.d_thr = self.ctx.alloc(thr_bytes)
 
     def set_panel_bounds(self, panel: int, z_min=None, z_max=None):
         p = list(self._panels[panel])
@@ -447,27 +462,46 @@ class Batch:
             return np.zeros(0, REGION_STATS)
         return self.d_stats.download(REGION_STATS, len(self._regions))
 
-    def prepare(self):
-        """Resolve every panel's normalisation on the device."""
+    def _panel_range(self, part):
+        """(first panel, count, first block, block count) in device order: part None = every panel,
+        0 = panels free of z slots, 1 = panels that read z slots."""
+        n = len(self._panels)
+        if part is None:
+            return 0, n, 0, self._raster_blocks
+        if part == 0:
+            return 0, self._n_free, 0, self._blocks_free
+        return self._n_free, n - self._n_free, self._blocks_free, self._raster_blocks - self._blocks_free
+
+    def prepare(self, part=None):
+        """Resolve panel normalisations on the device (``part``: see :meth:`_panel_range`)."""
         if not self._panels:
             return
-        if self._zvals and (self._zvals_dirty or self.d_zvals is None):
+        p0, n, _, _ = self._panel_range(part)
+        if n == 0:
+            return
+        if self._zvals and (self._zvals_dirty or self.d_zvals is None) and part != 0:
             vals = np.asarray(self._zvals, dtype=np.float64)
             if self.d_zvals is None or self.d_zvals.nbytes < vals.nbytes:
                 self.d_zvals = self.ctx.alloc(max(vals.nbytes * 2, 256))
             self.d_zvals.upload(vals)
             self._zvals_dirty = False
+        thr_one = self.ctx.lib.csg_threshold_bytes(1, self.code)
         self.ctx._check(
             self.ctx.lib.csg_panel_prepare(
-                self.ctx.handle, self.d_panels.ptr, len(self._panels), self.d_regions.ptr, self.d_stats.ptr,
-                self.code, self.d_zvals.ptr if self.d_zvals is not None else None, self.d_norms.ptr, self.d_thr.ptr,
+                self.ctx.handle, self.d_panels.ptr + p0 * PANEL.itemsize, n, self.d_regions.ptr, self.d_stats.ptr,
+                self.code, self.d_zvals.ptr if self.d_zvals is not None else None,
+                self.d_norms.ptr + p0 * PANEL_NORM.itemsize, self.d_thr.ptr + p0 * thr_one,
             )
         )
 
     def norms(self) -> np.ndarray:
+        """Resolved normalisation of every panel, indexed by panel id."""
         if not self._panels:
             return np.zeros(0, PANEL_NORM)
-        return self.d_norms.download(PANEL_NORM, len(self._panels))
+        dev = self.d_norms.download(PANEL_NORM, len(self._panels))
+        out = np.empty_like(dev)
+        out[self._dev_order] = dev
+        return out
 
     def set_lut(self, lut259: np.ndarray):
         lut = np.ascontiguousarray(lut259, dtype=np.uint8)
@@ -475,8 +509,8 @@ class Batch:
             raise ValueError("LUT must be (259, 4) uint8: 256 colours + under + over + bad")
         self.d_lut = self.ctx.to_device(lut)
 
-    def rasterise(self, want_rgba: bool = True, want_index: bool = True):
-        """K3 over every panel."""
+    def rasterise(self, want_rgba: bool = True, want_index: bool = True, part=None):
+        """K3 over the panels of ``part`` (see :meth:`_panel_range`)."""
         if not self._panels:
             return
         if want_rgba and self.d_lut is None:
@@ -485,11 +519,13 @@ class Batch:
             self.d_rgba = self.ctx.alloc(max(self._pixels, 1) * 4)
         if want_index and (self.d_index is None or self.d_index.nbytes < self._pixels * 2):
             self.d_index = self.ctx.alloc(max(self._pixels, 1) * 2)
+        _, n, b0, nb = self._panel_range(part)
+        if n == 0 or nb == 0:
+            return
         self.ctx._check(
             self.ctx.lib.csg_rasterise(
                 self.ctx.handle, self.d_sums.ptr, self.code, self.d_regions.ptr, self.d_pool.ptr, self.d_panels.ptr,
-                self.d_norms.ptr, self.d_thr.ptr, len(self._panels), self._raster_blocks,
-                self.d_block_panel.ptr if getattr(self, "d_block_panel", None) is not None else None,
+                self.d_norms.ptr, self.d_thr.ptr, len(self._panels), nb, b0, self.d_block_panel.ptr,
                 self.d_lut.ptr if self.d_lut is not None else None,
                 self.d_rgba.ptr if want_rgba else None, self.d_index.ptr if want_index else None,
             )

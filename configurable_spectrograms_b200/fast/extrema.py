@@ -72,6 +72,8 @@ def _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor
     stored = state.get(last_key, -1)
     last_done = int(stored) if isinstance(stored, (int, float)) else -1
     y_log, z_log = y_scale == "log", z_scale == "log"
+    if on_step_done is None and _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, last_done, on_scan):
+        return state
     # key strings of every instrument, built once (the loop below runs orbits x instruments times)
     keys = []
     for inst in instrument_order:
@@ -121,6 +123,63 @@ def _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor
             if on_step_done:
                 on_step_done(reuse=False)
     return state
+
+
+def _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, last_done, on_scan) -> bool:
+    """The loop of :func:`_walk` when every (orbit, instrument) step is a plain scan step: nothing
+    is re-used from the linear/linear keys, nothing is complete, nobody watches the intermediate
+    states.  Then the instruments are independent max-merge chains and only their last writes
+    survive, so each chain runs on local variables and ``state`` is written once -- the same
+    arithmetic in the same order per instrument, without ~25 dict operations per step.
+    Returns False (state untouched) when the preconditions do not hold."""
+    if not sequence or not instrument_order or (y_scale == "linear" and z_scale == "linear"):
+        return False
+    for inst in instrument_order:
+        entry = state.get(f"{inst}_{y_scale}_{z_scale}_extrema_progress")
+        if isinstance(entry, dict) and entry.get("complete"):
+            return False
+        if f"{inst}_linear_linear_y_max" in state or f"{inst}_linear_linear_z_max" in state:
+            return False
+    first = next((k for k, (orbit, _h) in enumerate(sequence) if orbit > last_done), None)
+    if first is None:
+        return False
+    last_index = len(sequence) - 1
+    # every later orbit must pass the `orbit <= last_done` gate too (ascending sequences always do)
+    if any(orbit <= last_done for orbit, _h in sequence[first:]):
+        return False
+    results = {}
+    last_executed = first
+    for inst in instrument_order:
+        stem = f"{inst}_{y_scale}_{z_scale}"
+        prev_e, prev_z = state.get(f"{stem}_y_max"), state.get(f"{stem}_z_max")
+        z_min_store, stop = 0, first
+        for orbit_index in range(first, last_index + 1):
+            cand_e, cand_z, z_min_store = on_scan(inst, orbit_index, sequence[orbit_index][1].get(inst))
+            merged_e = max(float(prev_e), cand_e) if isinstance(prev_e, (int, float)) else cand_e
+            merged_z = max(float(prev_z), cand_z) if isinstance(prev_z, (int, float)) else cand_z
+            prev_e = int(min(4000, math.ceil(merged_e)))
+            prev_z = float(math.ceil(merged_z))
+            stop = orbit_index
+            if orbit_index + 1 >= totals[inst]:  # "complete": the instrument is skipped from here on (:315-319)
+                break
+        results[inst] = (stem, prev_e, prev_z, z_min_store, stop)
+        last_executed = max(last_executed, stop)
+    # the writes of the last step of every chain
+    for inst in instrument_order:
+        stem, y_max, z_max, z_min_store, stop = results[inst]
+        state[f"{stem}_y_min"] = 0
+        state[f"{stem}_y_max"] = y_max
+        state[f"{stem}_z_min"] = z_min_store
+        state[f"{stem}_z_max"] = z_max
+        state[f"{stem}_extrema_progress"] = {
+            "processed_index": stop,
+            "total": totals[inst],
+            "complete": stop + 1 >= totals[inst],
+        }
+        state.pop(f"{inst}_{y_scale}_{z_scale}_last_orbit", None)
+    state.pop(f"{y_scale}_{z_scale}_last_orbit", None)
+    state[f"{y_scale}_{z_scale}_last_orbit"] = sequence[last_executed][0]
+    return True
 
 
 def plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff=0.1, log_floor_value=-1.0):

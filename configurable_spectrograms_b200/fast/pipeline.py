@@ -460,17 +460,29 @@ class BatchStep:
         if collapse:
             sh.collapse()
         planned = self._sig is not None
+        want_rgba = b.d_lut is not None
+        early = False
+
+        def independent_stages():
+            # nothing here depends on this step's extrema: K2a for every region, and K3 for the
+            # panels that read no z slot (the raw variants) -- the GPU stays busy while the host
+            # turns the pooled results into bounds
+            b.run_windows()
+            b.run_stats()
+            b.prepare(part=0)
+            b.rasterise(want_rgba=want_rgba, want_index=self.want_index, part=0)
+
         if state is None:
             pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
                                       dict(cache_state or {}), compute_mins=self.compute_mins,
                                       max_percentile=self.max_percentile, comm=self.comm)
-            if planned:  # K2a does not depend on the extrema: it overlaps the host bookkeeping below
-                b.run_windows()
-                b.run_stats()
+            if planned:
+                independent_stages()
+                early = True
             state = extrema_finish(pending)
         elif planned:
-            b.run_windows()
-            b.run_stats()
+            independent_stages()
+            early = True
         bounds = self._bounds(state)
         sig = self._signature(bounds)
         if sig != self._sig:
@@ -478,10 +490,16 @@ class BatchStep:
             self._sig = sig
             b.run_windows()
             b.run_stats()
+            early = False
         else:
             self._update_slots(bounds)
-        b.prepare()
-        b.rasterise(want_rgba=b.d_lut is not None, want_index=self.want_index)
+        want_rgba = b.d_lut is not None
+        if early:
+            b.prepare(part=1)
+            b.rasterise(want_rgba=want_rgba, want_index=self.want_index, part=1)
+        else:
+            b.prepare()
+            b.rasterise(want_rgba=want_rgba, want_index=self.want_index)
         if b._windows:
             b.ctx._check(b.ctx.lib.csg_d2h(b.ctx.handle, self._win_pin.ptr, b.d_window_any.ptr, len(b._windows)))
         self.state = state

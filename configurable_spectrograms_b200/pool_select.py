@@ -184,7 +184,7 @@ class GpuPoolBackend:
         self.ctx._check(
             self.ctx.lib.csg_pool_scan(
                 self.ctx.handle, self.d_hist.ptr, self.n_inst, self.max_pos, self.d_inst_len.ptr, self.n_slots,
-                self.bits, d_tot.ptr if d_tot is not None else None,
+                self.bits, None, d_tot.ptr if d_tot is not None else None,
             )
         )
         if want_totals:
@@ -296,7 +296,7 @@ class DevicePoolSelector:
         d_gath = mem.device("gath", R * n_inst * S * 1024 * 4) if R > 1 else None
         d_base = mem.device("base", n_inst * S * 1024 * 4) if R > 1 else None
         d_above = mem.device("above", n_inst * 8) if R > 1 else None
-        chk(lib.csg_pool_scan(h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, d_tot.ptr if R > 1 else None))
+        chk(lib.csg_pool_scan(h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, None, d_tot.ptr if R > 1 else None))
         if R > 1:
             comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * nb0 * 4, sh)
             chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, nb0, d_base.ptr, d_above.ptr))
@@ -334,7 +334,8 @@ class DevicePoolSelector:
             if n_items:
                 chk(lib.csg_pool_hist_refine(h, sums, code, self.d_items.ptr, n_items, max_pos, S, d_table.ptr, prev_shift,
                                              shift, bits, hist1.ptr))
-            chk(lib.csg_pool_scan(h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_tot.ptr if R > 1 else None))
+            chk(lib.csg_pool_scan(h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_table.ptr,
+                                  d_tot.ptr if R > 1 else None))
             if R > 1:
                 comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * S * nb * 4, sh)
                 chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, S * nb, d_base.ptr, None))

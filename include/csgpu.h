@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 5
+#define CSG_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -230,7 +230,9 @@ CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_pan
                       const csg_region* d_regions, const csg_region_stats* d_stats, int dtype,
                       const double* d_zvals, csg_panel_norm* d_norms, void* d_thresholds);
 
-/* d_block_panel (may be NULL): panel index of every thread block, i.e. panel p repeated
+/* Launches blocks [block_offset, block_offset + total_blocks) of the panel table's block space
+ * (a table can be rasterised in several launches, e.g. the panels whose bounds are known first).
+ * d_block_panel (may be NULL): panel index of every thread block, i.e. panel p repeated
  * csg_raster_blocks(ne_p, nt_p) times; without it every block binary-searches first_block.
  * Clamp -> normalise -> 256-entry LUT index -> RGBA8.  d_lut: 259 x 4 bytes (256 colours,
  * under, over, bad).  d_index (uint16, may be NULL) receives Colormap indices 0..255 and
@@ -239,8 +241,8 @@ CSG_API int csg_panel_prepare(csg_ctx* ctx, const csg_panel* d_panels, int n_pan
 CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region* d_regions,
                   const int32_t* d_index_pool, const csg_panel* d_panels,
                   const csg_panel_norm* d_norms, const void* d_thresholds, int n_panels,
-                  int total_blocks, const int32_t* d_block_panel, const uint8_t* d_lut, uint8_t* d_rgba,
-                  uint16_t* d_index);
+                  int total_blocks, int block_offset, const int32_t* d_block_panel, const uint8_t* d_lut,
+                  uint8_t* d_rgba, uint16_t* d_index);
 
 /* ---------------------------------------------- K2b: global extrema (pooled) */
 /* The pooled finite-positive samples of CS/fast/extrema.py:259-267 are never
@@ -271,9 +273,10 @@ CSG_API int csg_pool_hist_refine(csg_ctx* ctx, const void* d_mats, int dtype, co
                          int prefix_shift, int shift, int bits, uint32_t* d_hist);
 /* In-place inclusive scan of d_hist along pos for every (inst, slot, bin); d_totals (may be
  * NULL) receives the last row [inst][slot][bin] (this rank's bucket totals, the payload of
- * the histogram-merge all-gather). */
+ * the histogram-merge all-gather).  d_slot_table (may be NULL) [inst][n_slots]: slots holding
+ * the UINT64_MAX padding are skipped (their totals are 0). */
 CSG_API int csg_pool_scan(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len,
-                  int n_slots, int bits, uint32_t* d_totals);
+                  int n_slots, int bits, const uint64_t* d_slot_table, uint32_t* d_totals);
 /* One query = (inst, pos, slot, rank): find the bin of the scanned row where the cumulative
  * count first exceeds rank; writes bin and the residual rank inside that bin.  d_base (may be
  * NULL) [inst][slot][bin]: counts held by lower ranks, added to every row on the fly. */

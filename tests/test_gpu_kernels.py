@@ -400,3 +400,33 @@ def test_device_selector_slot_overflow_falls_back(ctx):
     sel.enqueue(np.float32, items, 1, inst_len, 8, reqs)
     vals3, _, _ = sel.result()
     assert vals3 == expected
+
+
+def test_collapse_config5_generic_stress_cube(ctx):
+    """BASELINE config 5 shape class: a (T, 96, 64) float32 cube with T in the tens of thousands,
+    collapsed as layout A (stream kernel, E = 64) and through the transposed view (layout B):
+    bit-exact against numpy, plus size-independent properties on the full result."""
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(5)
+    T, P, E = 20000, 96, 64
+    cube = rng.uniform(0.0, 1000.0, (T, P, E)).astype(np.float32)
+    cube[rng.random((T, P, E)) < 0.005] = np.nan
+    b = Batch(ctx, np.float32, n_groups=0)
+    f = b.add_file(cube)
+    stored = np.ascontiguousarray(cube.transpose(0, 2, 1))  # (T, E, P): pitch contiguous
+    f2 = b.add_file(stored.transpose(0, 2, 1))
+    b.upload_cubes()
+    b.collapse()
+    assert any(k[1] == 1 for k in b.d_files), "the (T,96,64) cube must take the stream kernel"
+    with np.errstate(invalid="ignore"):
+        ref_a = np.nansum(cube, axis=1)
+        ref_b = np.nansum(stored.transpose(0, 2, 1), axis=1)
+    got_a, got_b = b.sums(f), b.sums(f2)
+    assert same_bits(got_a, ref_a, zero_sign_insensitive=False)
+    assert same_bits(got_b, ref_b, zero_sign_insensitive=False)
+    # the two summation orders differ in the last bits but agree to float32 accuracy
+    assert np.allclose(got_a, got_b, rtol=1e-5)
+    assert not np.array_equal(bits(got_a), bits(got_b))
+    fl = b.flags(f)
+    assert fl.all() and b.flags(f2).all()

@@ -128,3 +128,26 @@ def test_pitch_angle_bits_closed_intervals():
     assert zoom_window([], 6.25) is None
     assert zoom_window([100.0], 6.25) == (100.0, 375.0)
     assert zoom_window([100.0, 1100.0], 6.25) == (600.0, 1500.0)
+
+
+def test_walk_chain_fast_path_equals_step_loop():
+    """The per-instrument chain shortcut writes exactly what the step-by-step loop writes."""
+    rng = np.random.default_rng(9)
+    order = ("ees", "eeb", "ies", "ieb")
+    for trial in range(30):
+        n = int(rng.integers(1, 12))
+        sequence = []
+        for k in range(n):
+            present = {i: True for i in order if rng.random() < 0.8}
+            sequence.append((13000 + 3 * k, present))
+        totals = {i: sum(1 for _, h in sequence if i in h) for i in order}
+        table = {(i, k): (float(rng.uniform(0, 5000)), float(rng.uniform(0, 900)), 0) for i in order for k in range(n)}
+        scan = lambda inst, oi, h: table[(inst, oi)]
+        for ys, zs in (("linear", "log"), ("log", "log"), ("log", "linear"), ("linear", "linear")):
+            start = {} if trial % 3 else {"ees_%s_%s_y_max" % (ys, zs): 77, "ees_%s_%s_z_max" % (ys, zs): 12.5}
+            if trial % 5 == 0:
+                start[f"{ys}_{zs}_last_orbit"] = 13000  # resume: the first orbit is skipped
+            fast = X._walk(sequence, order, ys, zs, json_copy(start), totals, 0.1, -1.0, scan)
+            slow = X._walk(sequence, order, ys, zs, json_copy(start), totals, 0.1, -1.0, scan, on_step_done=lambda reuse: None)
+            assert fast == slow, (trial, ys, zs)
+            assert list(fast) and set(fast) == set(slow)
