@@ -43,7 +43,7 @@ METRIC = "orbits/sec (whole box, device-timed)"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--orbits-per-gpu", type=int, default=125)
@@ -132,6 +132,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.window = [None, None]  # host perf_counter interval of the GPU work being measured
+
+    def mark(self, which):
+        self.window[which] = time.perf_counter()
 
     def start(self):
         try:
@@ -145,18 +149,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0, t1 = self.window
+        rows = [r[1:] for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.15)]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "window": "warm-up + timed steps + per-stage passes (GPU busy throughout)"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -241,6 +248,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         comm = TorchComm(dist, dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~1 s before its first row: start it ahead of the GPU work
     n_local = args.orbits_per_gpu
     first = rank * n_local
     files, orbits, total_elems = orbit_layout(n_local, first, args.seed)
@@ -274,6 +284,7 @@ def main():
     state0 = step.run({})  # plans the panels on the first pass
     step.finish()
     t_plan = time.perf_counter() - t_plan
+    sampler.mark(0)
     for _ in range(args.warmup):
         step.run({})
     step.finish()
@@ -283,12 +294,10 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count()
+    torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` sees the timed steps only
     host_t0 = time.perf_counter()
     prof = None
     if args.profile_host:
@@ -300,6 +309,7 @@ def main():
     for _ in range(args.steps):
         state = step.run({})
     ev1.record(tstream)
+    torch.cuda.profiler.stop()
     if prof is not None:
         prof.disable()
         import io
@@ -312,17 +322,19 @@ def main():
     step.finish()
     barrier()
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     assert state == state0, "extrema changed between steps"
-    # per-kernel stage times (separate passes, CUDA events on the same stream)
-    def timed(fn, n=max(args.steps, 3)):
+    # per-kernel stage times: separate passes, CUDA events on the launching stream, `reps`
+    # back-to-back launches per event pair so the launch latency is not billed to the kernel
+    # (every stage streams far more than the 126 MB L2, so repeats do not hit cache)
+    def timed(fn, n=3, reps=5):
         out = []
         for _ in range(n):
             ctx.timer_start(0)
-            fn()
+            for _ in range(reps):
+                fn()
             ctx.timer_stop(0)
-            out.append(ctx.timer_ms(0))
+            out.append(ctx.timer_ms(0) / reps)
         return float(np.mean(out))
 
     k1_ms = timed(shard.collapse)
@@ -331,13 +343,15 @@ def main():
     raster_ms = timed(lambda: shard.batch.rasterise(want_rgba=True, want_index=False))
 
     pool = []
-    for _ in range(max(args.steps, 3)):  # device time of the K2b launches alone (host bookkeeping excluded)
+    for _ in range(5):  # device time of the K2b launches alone (host bookkeeping excluded)
         ctx.timer_start(0)
         pending = extrema_enqueue(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm)
         ctx.timer_stop(0)
         extrema_finish(pending)
         pool.append(ctx.timer_ms(0))
     pool_ms = float(np.mean(pool))
+    sampler.mark(1)
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -355,6 +369,21 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (cube_bytes + sums_bytes) / (k1_ms / 1e3) / 1e9
+    # DRAM bytes of one K1 launch from the committed `ncu --set full` capture of this same
+    # workload (profiles/r1_k1_traffic.json, written by scripts/ncu_summary.py --traffic)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
+        if tr.get("orbits_per_gpu") == n_local and tr.get("algorithmic_bytes") == int(cube_bytes + sums_bytes):
+            traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    # the whole step against the same roofline: SURVEY.md section 8(d)'s B_orbit, i.e. cube read +
+    # (G+1) sums written + one pass over the total for the pooled extrema + per panel pixel
+    # (stats read + raster read + RGBA write)
+    s_el = 4
+    step_bytes = cube_bytes + sums_bytes + sum(f["T"] * E * s_el for f in files) + shard.batch.n_pixels * (2 * s_el + 4)
+    step_gbs = step_bytes / ((float(ms_total) / args.steps) / 1e3) / 1e9
 
     # ------------------------------------------------------------------- e2e arm
     e2e = None
@@ -367,17 +396,27 @@ def main():
         rgba_view = None
 
         def e2e_step():
-            cubes.copy_(host, non_blocking=True)  # H2D of this step's inputs (pinned -> HBM)
+            # H2D of this step's inputs (pinned -> HBM) on the context stream, then the step; the
+            # rasters leave on the copy-out stream, so step k's read-back shares the (full duplex)
+            # link with step k+1's upload.  side_join: the next K3 must not overwrite rasters that
+            # are still being copied (enqueued after the upload, so the upload itself never waits).
+            ctx._check(ctx.lib.csg_h2d(ctx.handle, cubes.data_ptr(), host.data_ptr(), cube_bytes))
+            ctx.side_join()
             step.run({})
-            ctx._check(ctx.lib.csg_d2h(ctx.handle, rgba_host.data_ptr(), shard.batch.d_rgba.ptr, n_px * 4))
+            ctx.d2h_side(rgba_host.data_ptr(), shard.batch.d_rgba.ptr, n_px * 4)
             step.finish()
 
+        def e2e_drain():
+            ctx.side_sync()
+
         e2e_step()
+        e2e_drain()
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(2, min(args.steps, 3))
+        n_e2e = max(2, min(args.steps, 4))
         for _ in range(n_e2e):
             e2e_step()
+        e2e_drain()  # the last step's rasters are in host memory before the clock stops
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
@@ -407,9 +446,11 @@ def main():
                 "l2_policy": f"inputs larger than L2 ({cube_bytes / 1e9:.1f} GB of cubes streamed per step)",
             },
             "roofline": {"bound": "hbm", "kernel": "collapse_stream_kernel<float,4,384>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": k1_ms,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ms": k1_ms,
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+            "step_roofline": {"algorithmic_bytes": int(step_bytes), "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak, "note": "this rank's whole step (K1+K2b+K2a+K3), SURVEY 8(d) B_orbit x orbits / step time"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
             "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
                          "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,

@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -146,6 +146,9 @@ SIGNATURES = {
     "csg_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "csg_d2h": (_i, [_vp, _vp, _vp, _sz]),
     "csg_memset": (_i, [_vp, _vp, _i, _sz]),
+    "csg_d2h_side": (_i, [_vp, _vp, _vp, _sz]),
+    "csg_side_join": (_i, [_vp]),
+    "csg_side_sync": (_i, [_vp]),
     "csg_timer_start": (_i, [_vp, _i]),
     "csg_timer_stop": (_i, [_vp, _i]),
     "csg_timer_ms": (_i, [_vp, _i, C.POINTER(C.c_float)]),
@@ -351,6 +354,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.csg_launch_count(self.handle))
+
+    def d2h_side(self, host_ptr: int, dev_ptr: int, nbytes: int):
+        """Read a result back on the copy-out stream (overlaps later work on the main stream)."""
+        self._check(self.lib.csg_d2h_side(self.handle, host_ptr, dev_ptr, nbytes))
+
+    def side_join(self):
+        self._check(self.lib.csg_side_join(self.handle))
+
+    def side_sync(self):
+        self._check(self.lib.csg_side_sync(self.handle))
 
     def event_record(self, slot: int):
         self._check(self.lib.csg_event_record(self.handle, slot))

@@ -14,6 +14,9 @@ struct csg_ctx {
   cudaEvent_t ev_start[32];
   cudaEvent_t ev_stop[32];
   cudaEvent_t ev_user[32];
+  cudaStream_t side;      // copy-out stream: result read-backs that overlap the next step's uploads
+  cudaEvent_t ev_fork;    // ctx stream -> side stream
+  cudaEvent_t ev_side;    // last copy enqueued on the side stream
   int64_t launches;
   void* scratch;  // device scratch owned by the context (grow-only)
   size_t scratch_bytes;

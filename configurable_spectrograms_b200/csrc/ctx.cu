@@ -67,6 +67,9 @@ csg_ctx* csg_create(int device, void* external_stream) {
     cudaEventCreate(&ctx->ev_stop[i]);
     cudaEventCreateWithFlags(&ctx->ev_user[i], cudaEventDisableTiming);
   }
+  cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming);
   return ctx;
 }
 
@@ -79,6 +82,10 @@ void csg_destroy(csg_ctx* ctx) {
     cudaEventDestroy(ctx->ev_stop[i]);
     cudaEventDestroy(ctx->ev_user[i]);
   }
+  cudaStreamSynchronize(ctx->side);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_side);
+  cudaStreamDestroy(ctx->side);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
@@ -147,6 +154,25 @@ int csg_h2d(csg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
 int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   if (bytes == 0) return CSG_OK;
   CSG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return CSG_OK;
+}
+int csg_d2h_side(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (bytes == 0) return CSG_OK;
+  CSG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CSG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  CSG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->side));
+  CSG_CUDA(ctx, cudaEventRecord(ctx->ev_side, ctx->side));
+  return CSG_OK;
+}
+int csg_side_join(csg_ctx* ctx) {
+  if (!ctx) return CSG_ERR_ARG;
+  CSG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+  return CSG_OK;
+}
+int csg_side_sync(csg_ctx* ctx) {
+  if (!ctx) return CSG_ERR_ARG;
+  CSG_CUDA(ctx, cudaStreamSynchronize(ctx->side));
   return CSG_OK;
 }
 int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes) {

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 7
+#define CSG_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -78,6 +78,13 @@ CSG_API int csg_host_unregister(csg_ctx* ctx, void* h_ptr);
 CSG_API int csg_h2d(csg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
 CSG_API int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
 CSG_API int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes);
+/* Result read-back on the context's copy-out stream: ordered after everything enqueued on the
+ * ctx stream so far, but later ctx-stream work (the next shard's uploads and kernels) does not
+ * wait for it -- PCIe is full duplex.  csg_side_join makes the ctx stream wait for the copies
+ * (call it before the source buffer is overwritten); csg_side_sync makes the host wait. */
+CSG_API int csg_d2h_side(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+CSG_API int csg_side_join(csg_ctx* ctx);
+CSG_API int csg_side_sync(csg_ctx* ctx);
 
 /* ------------------------------------------------------------------- timing */
 /* CUDA-event stopwatch slots (0..31) on the ctx stream. */

@@ -2,6 +2,8 @@
 """Condense `ncu --set full` reports into the few numbers DESIGN.md / bench.py quote.
 
 usage: ncu_summary.py report.ncu-rep [...]  > profiles/xyz.txt
+       ncu_summary.py --traffic KERNEL_SUBSTRING ORBITS_PER_GPU ALGORITHMIC_BYTES report.ncu-rep > profiles/r1_k1_traffic.json
+         (DRAM bytes per launch of the matching kernel: what bench.py reports as roofline.traffic)
 Reads each report through `ncu -i <rep> --page raw --csv` (ncu must be on PATH).
 """
 import csv
@@ -39,7 +41,30 @@ METRICS = [
 ]
 
 
+def traffic(substr, orbits, algo_bytes, path):
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, data = rows[0], rows[2:]
+    ki, ri, wi, ti = (hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
+    hits = [r for r in data if substr in r[ki]]
+    if not hits:
+        raise SystemExit(f"no kernel matching {substr!r} in {path}")
+    rd = sum(float(r[ri]) for r in hits) / len(hits)
+    wr = sum(float(r[wi]) for r in hits) / len(hits)
+    print(json.dumps({
+        "kernel": hits[0][ki].replace("void <unnamed>::", "").split("(")[0], "launches_averaged": len(hits),
+        "orbits_per_gpu": int(orbits), "algorithmic_bytes": int(algo_bytes),
+        "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+        "ncu_duration_ns": sum(float(r[ti]) for r in hits) / len(hits),
+        "source": f"ncu --set full --clock-control none capture {path.split('/')[-1]} (python bench.py, default workload)",
+    }, indent=1))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--traffic":
+        return traffic(*sys.argv[2:6])
     for path in sys.argv[1:]:
         out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
