@@ -317,7 +317,7 @@ def main():
 
         buf = io.StringIO()
         pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
-        open(args.profile_host, "w").write(buf.getvalue())
+        open(f"{args.profile_host}.rank{rank}", "w").write(buf.getvalue())
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
     step.finish()
     barrier()

@@ -61,14 +61,30 @@ class TorchComm:
             ext = cache[stream_handle] = torch.cuda.ExternalStream(stream_handle, device=self.device)
         return torch.cuda.stream(ext)
 
-    def allgather_dev(self, src_ptr: int, dst_ptr: int, nbytes: int, stream_handle: int = 0):
-        """dst[rank][nbytes] <- every rank's src[nbytes], enqueued behind the context stream's work."""
-        with self._on(stream_handle):
-            self.dist.all_gather_into_tensor(self._tensor(dst_ptr, nbytes * self.size), self._tensor(src_ptr, nbytes))
+    def stream_scope(self, stream_handle: int):
+        """Context manager: inside it the device collectives may be called with
+        ``stream_handle=None`` (no per-call stream switch -- a dozen tiny collectives per step)."""
+        return self._on(stream_handle)
 
-    def allreduce_max_dev(self, ptr: int, count: int, kind: str, stream_handle: int = 0):
-        torch = self.torch
-        dt = {"i8": torch.int64, "f8": torch.float64, "i4": torch.int32}[kind]
-        t = self._tensor(ptr, count * dt.itemsize).view(dt)
+    def allgather_dev(self, src_ptr: int, dst_ptr: int, nbytes: int, stream_handle: int | None = 0):
+        """dst[rank][nbytes] <- every rank's src[nbytes], enqueued behind the context stream's work."""
+        dst, src = self._tensor(dst_ptr, nbytes * self.size), self._tensor(src_ptr, nbytes)
+        if stream_handle is None:
+            self.dist.all_gather_into_tensor(dst, src)
+            return
+        with self._on(stream_handle):
+            self.dist.all_gather_into_tensor(dst, src)
+
+    def allreduce_max_dev(self, ptr: int, count: int, kind: str, stream_handle: int | None = 0):
+        key = (ptr, count, kind)
+        cache = self.__dict__.setdefault("_typed", {})
+        t = cache.get(key)
+        if t is None:
+            torch = self.torch
+            dt = {"i8": torch.int64, "f8": torch.float64, "i4": torch.int32}[kind]
+            t = cache[key] = self._tensor(ptr, count * dt.itemsize).view(dt)
+        if stream_handle is None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return
         with self._on(stream_handle):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)

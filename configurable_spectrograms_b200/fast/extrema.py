@@ -149,19 +149,30 @@ def _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, la
         return False
     results = {}
     last_executed = first
+    range_max = getattr(on_scan, "range_max", None)
     for inst in instrument_order:
         stem = f"{inst}_{y_scale}_{z_scale}"
         prev_e, prev_z = state.get(f"{stem}_y_max"), state.get(f"{stem}_z_max")
-        z_min_store, stop = 0, first
-        for orbit_index in range(first, last_index + 1):
-            cand_e, cand_z, z_min_store = on_scan(inst, orbit_index, sequence[orbit_index][1].get(inst))
+        # the per-step loop below runs first..stop: it breaks after the step that makes the
+        # instrument "complete" (orbit_index + 1 >= total, :315-319), and always runs one step
+        stop = min(last_index, max(first, totals[inst] - 1))
+        folded = range_max(inst, first, stop) if range_max is not None else None
+        if folded is not None:
+            # ceil and min(4000, .) are monotone, so folding the max-merge over the steps equals
+            # one merge with the largest candidate: min(4000, ceil(max(prev, c_first..c_stop)))
+            cand_e, cand_z, z_min_store = folded
             merged_e = max(float(prev_e), cand_e) if isinstance(prev_e, (int, float)) else cand_e
             merged_z = max(float(prev_z), cand_z) if isinstance(prev_z, (int, float)) else cand_z
             prev_e = int(min(4000, math.ceil(merged_e)))
             prev_z = float(math.ceil(merged_z))
-            stop = orbit_index
-            if orbit_index + 1 >= totals[inst]:  # "complete": the instrument is skipped from here on (:315-319)
-                break
+        else:
+            z_min_store = 0
+            for orbit_index in range(first, stop + 1):
+                cand_e, cand_z, z_min_store = on_scan(inst, orbit_index, sequence[orbit_index][1].get(inst))
+                merged_e = max(float(prev_e), cand_e) if isinstance(prev_e, (int, float)) else cand_e
+                merged_z = max(float(prev_z), cand_z) if isinstance(prev_z, (int, float)) else cand_z
+                prev_e = int(min(4000, math.ceil(merged_e)))
+                prev_z = float(math.ceil(merged_z))
         results[inst] = (stem, prev_e, prev_z, z_min_store, stop)
         last_executed = max(last_executed, stop)
     # the writes of the last step of every chain
@@ -196,7 +207,7 @@ def plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_
     return steps, totals
 
 
-def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
+def energy_candidates(energies: list[np.ndarray], counts, as_array: bool = False, shared_table=None):
     """Per-step 99 %-coverage energy (``:270-278``) from per-file per-energy positive counts.
 
     ``energies[k]`` / ``counts[k]`` belong to the k-th scanned file of one instrument.  The
@@ -206,11 +217,10 @@ def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
     """
     n = len(energies)
     if n == 0:
-        return []
-    shared = all(e is energies[0] for e in energies)
+        return np.zeros(0) if as_array else []
+    shared = shared_table is not None or all(e is energies[0] for e in energies)
     if shared:  # the usual case: every file of the instrument carries the same energy table
-        e0 = np.asarray(energies[0], dtype=np.float64)
-        keys, idx = np.unique(e0, return_inverse=True)
+        e0, keys, idx = shared_table if shared_table is not None else shared_energy_table(energies[0])
         c = np.asarray(counts, dtype=np.int64)[:, : len(e0)]
         if len(keys) == len(e0):
             per_file = np.empty((n, len(keys)), dtype=np.int64)
@@ -230,8 +240,15 @@ def energy_candidates(energies: list[np.ndarray], counts) -> list[float]:
     total = along[:, -1]
     target = 0.99 * total
     first = (along > target[:, None]).argmax(axis=1)
-    out = keys[first]
-    return [float(v) if t > 0 else 0.0 for v, t in zip(out.tolist(), total.tolist())]
+    out = np.where(total > 0, keys[first], 0.0)
+    return out if as_array else out.tolist()
+
+
+def shared_energy_table(energy):
+    """(float64 energies, sorted unique keys, inverse index): the static part of :func:`energy_candidates`."""
+    e0 = np.asarray(energy, dtype=np.float64)
+    keys, idx = np.unique(e0, return_inverse=True)
+    return e0, keys, idx
 
 
 def _energy_plan(shard, comm, instrument_order, steps, owners, first):
@@ -258,7 +275,13 @@ def _energy_plan(shard, comm, instrument_order, steps, owners, first):
                     break
             else:
                 uniq.append(e)
-        plan[inst] = (present, np.asarray([where[(inst, oi)] for oi in present], dtype=np.int64), en)
+        # static index maps of the per-step candidate fill (extrema_finish): position of every
+        # present step inside steps[inst]
+        steps_arr = np.asarray(steps[inst], dtype=np.int64)
+        pos = np.searchsorted(steps_arr, np.asarray(present, dtype=np.int64)) if present else np.zeros(0, np.int64)
+        ascending = bool(np.all(np.diff(steps_arr) > 0)) if len(steps_arr) > 1 else True
+        table = shared_energy_table(en[0]) if en and all(e is en[0] for e in en) else None
+        plan[inst] = (present, np.asarray([where[(inst, oi)] for oi in present], dtype=np.int64), en, steps_arr, pos, ascending, table)
     return plan, n_max, max_E
 
 
@@ -326,16 +349,25 @@ def extrema_finish(pending, on_step_done=None):
     # ---- y extrema: per-step energy candidates from every rank's per-file positive counts
     # (available after the first histogram pass; this overlaps the digit loop on the GPU)
     all_counts, npos = selector.result_counts()  # multi-rank: every rank's rows (device all-gather)
-    cand_e: dict[str, dict[int, float]] = {}
+    n_seq = len(pending["sequence"])
+    cand_e: dict[str, np.ndarray] = {}  # per orbit index: the candidate the reference's step would see
     for inst in instrument_order:
-        present, rows, energies = pending["eplan"][inst]
-        ce = energy_candidates(energies, all_counts[rows]) if present else []
-        by_step = dict(zip(present, ce))
-        running, per = 0.0, {}
-        for oi in steps[inst]:  # steps without a file repeat the previous candidate
-            running = by_step.get(oi, running)
-            per[oi] = running
-        cand_e[inst] = per
+        present, rows, energies, steps_arr, pos, ascending, table = pending["eplan"][inst]
+        dense = np.zeros(n_seq, dtype=np.float64)
+        if present and ascending:
+            ce = energy_candidates(energies, all_counts[rows], as_array=True, shared_table=table)
+            # steps without a file repeat the previous candidate (0.0 before the first file)
+            idx = np.full(len(steps_arr), -1, dtype=np.int64)
+            idx[pos] = np.arange(len(present))
+            filled = np.maximum.accumulate(idx)
+            dense[steps_arr] = np.where(filled >= 0, ce[np.maximum(filled, 0)], 0.0)
+        elif present:
+            by_step = dict(zip(present, energy_candidates(energies, all_counts[rows])))
+            running = 0.0
+            for oi in steps[inst]:
+                running = by_step.get(oi, running)
+                dense[oi] = running
+        cand_e[inst] = dense
     # ---- z extrema: the device selection
     values = selector.result_values()
     if values is None:
@@ -360,8 +392,17 @@ def extrema_finish(pending, on_step_done=None):
 
     def scan(inst, orbit_index, handle):
         ce, z, z_min = per_inst[inst]
-        return ce.get(orbit_index, 0.0), z, z_min
+        return float(ce[orbit_index]), z, z_min
 
+    def range_max(inst, first, stop):
+        """Largest candidates over the steps first..stop (None: NaN candidates, walk step by step)."""
+        ce, z, z_min = per_inst[inst]
+        top = float(ce[first : stop + 1].max())
+        if top != top or z != z:
+            return None
+        return top, z, z_min
+
+    scan.range_max = range_max
     return _walk(pending["sequence"], instrument_order, pending["y_scale"], pending["z_scale"], pending["state"],
                  pending["totals"], pending["log_floor_cutoff"], pending["log_floor_value"], scan, on_step_done)
 

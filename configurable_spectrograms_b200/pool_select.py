@@ -239,13 +239,20 @@ class DevicePoolSelector:
         device all-gather (the largest item count over the ranks); ``result_counts`` then returns
         every rank's rows, rank after rank."""
         comm = comm or SingleRank()
+        if comm.size > 1 and hasattr(comm, "stream_scope"):
+            # NCCL is ordered against THIS context's stream: one stream switch for the whole digit loop
+            with comm.stream_scope(self.ctx.stream_handle):
+                return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, None)
+        sh = self.ctx.stream_handle if comm.size > 1 else 0
+        return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, sh)
+
+    def _enqueue(self, dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, sh):
         ctx, lib, mem = self.ctx, self.ctx.lib, self.mem
         h, chk = ctx.handle, ctx._check
         D = np.dtype(dtype)
         code = _lib.np_dtype_code(D)
         plan = digit_plan(D)
         R, S = comm.size, self.N_SLOTS
-        sh = ctx.stream_handle if R > 1 else 0  # NCCL is ordered against THIS context's stream
         n_items, n_req = len(items), len(requests)
         max_pos = max(int(inst_len.max()) if len(inst_len) else 0, 1)
         if R > 1:  # the table shape must agree across ranks only per rank; exchanged buffers are per (inst, slot, bin)

@@ -151,3 +151,15 @@ def test_walk_chain_fast_path_equals_step_loop():
             slow = X._walk(sequence, order, ys, zs, json_copy(start), totals, 0.1, -1.0, scan, on_step_done=lambda reuse: None)
             assert fast == slow, (trial, ys, zs)
             assert list(fast) and set(fast) == set(slow)
+
+            # the folded variant: one merge with the largest candidate of the chain's steps
+            def folded_scan(inst, oi, h):
+                return table[(inst, oi)]
+
+            def range_max(inst, a, b):
+                return (max(table[(inst, k)][0] for k in range(a, b + 1)), max(table[(inst, k)][1] for k in range(a, b + 1)),
+                        table[(inst, b)][2])
+
+            folded_scan.range_max = range_max
+            folded = X._walk(sequence, order, ys, zs, json_copy(start), totals, 0.1, -1.0, folded_scan)
+            assert folded == slow, (trial, ys, zs)
