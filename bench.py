@@ -345,7 +345,7 @@ def main():
     pool = []
     for _ in range(5):  # device time of the K2b launches alone (host bookkeeping excluded)
         ctx.timer_start(0)
-        pending = extrema_enqueue(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm)
+        pending = extrema_enqueue(shard, sequence, ORDER, "linear", "log", {}, max_percentile=99.0, comm=comm, per_step=False)
         ctx.timer_stop(0)
         extrema_finish(pending)
         pool.append(ctx.timer_ms(0))

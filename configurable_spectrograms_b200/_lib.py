@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -168,7 +168,20 @@ SIGNATURES = {
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "csg_pool_scan_cols": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    "csg_pool_slot_payload_bytes": (_sz, [_i, _i]),
+    "csg_pool_energy_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "csg_pool_pack_results": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]),
+    "csg_pool_reduce_max": (_i, [_vp, _vp, _i, _i, _vp]),
+    "csg_peer_create": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
+    "csg_peer_mailbox": (_vp, [_vp]),
+    "csg_peer_connect_ipc": (_i, [_vp, _vp, _vp]),
+    "csg_peer_connect_ptrs": (_i, [_vp, _vp, _vp]),
+    "csg_peer_allgather": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "csg_peer_error_word": (_vp, [_vp]),
+    "csg_peer_clear_error": (_i, [_vp, _vp]),
+    "csg_peer_destroy": (_i, [_vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "csg_pool_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),
@@ -177,9 +190,9 @@ SIGNATURES = {
     "csg_pool_sel_locate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "csg_pool_sel_bounds": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "csg_pool_sel_slots": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
-    "csg_pool_sel_assign": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "csg_pool_sel_assign": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _i, _i, _vp, _vp]),
     "csg_pool_sel_finish": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
-    "csg_pool_base": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _vp]),
+    "csg_pool_base": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _vp]),
 }
 
 _lib = None

@@ -88,3 +88,172 @@ class TorchComm:
             return
         with self._on(stream_handle):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+
+
+# ----------------------------------------------------------------------------------------
+# Exchanges: "every rank contributes nbytes, every rank sees all of them", on the context
+# stream, device memory in and out.  The pooled-extrema selection (pool_select.py) is written
+# against this one call.
+# ----------------------------------------------------------------------------------------
+class LocalExchange:
+    """One rank: the payload is its own gather."""
+
+    rank, size, kind = 0, 1, "local"
+    error_ptr = None
+
+    def ensure(self, slot_bytes: int):
+        pass
+
+    def allgather(self, src_ptr: int, nbytes: int) -> int:
+        return src_ptr
+
+
+class NcclExchange:
+    """NCCL all-gather (``torch.distributed``) into a persistent device buffer; everything is
+    stream-ordered, so one buffer serves every exchange of a step."""
+
+    kind = "nccl"
+    error_ptr = None
+
+    def __init__(self, comm: TorchComm, ctx):
+        self.comm, self.ctx = comm, ctx
+        self.rank, self.size = comm.rank, comm.size
+        self.buf = None
+
+    def ensure(self, slot_bytes: int):
+        if self.buf is None or self.buf.nbytes < slot_bytes * self.size:
+            self.buf = self.ctx.alloc(slot_bytes * self.size)
+
+    def allgather(self, src_ptr: int, nbytes: int) -> int:
+        self.comm.allgather_dev(src_ptr, self.buf.ptr, nbytes, None)  # inside TorchComm.stream_scope
+        return self.buf.ptr
+
+
+class PeerExchange:
+    """Mailboxes in every rank's HBM, written by the peers over NVLink (``csrc/peer.cu``)."""
+
+    kind = "peer"
+
+    def __init__(self, ctx, rank: int, size: int):
+        self.ctx, self.rank, self.size = ctx, rank, size
+        self.handle = None
+        self.slot_bytes = 0
+        self.error_ptr = None
+
+    def _create(self, slot_bytes: int) -> bytes:
+        import ctypes as C
+
+        self.destroy()
+        out, ipc = C.c_void_p(), (C.c_ubyte * 64)()
+        self.ctx._check(self.ctx.lib.csg_peer_create(self.ctx.handle, self.rank, self.size, slot_bytes, C.byref(out), ipc))
+        self.handle, self.slot_bytes = out.value, slot_bytes
+        self.error_ptr = self.ctx.lib.csg_peer_error_word(self.handle)
+        return bytes(ipc)
+
+    def mailbox(self) -> int:
+        return self.ctx.lib.csg_peer_mailbox(self.handle)
+
+    def connect_ipc(self, handles: list[bytes]):
+        import ctypes as C
+
+        blob = b"".join(handles)
+        self.ctx._check(self.ctx.lib.csg_peer_connect_ipc(self.ctx.handle, self.handle, C.c_char_p(blob)))
+
+    def connect_ptrs(self, mailboxes: list[int]):
+        import ctypes as C
+
+        arr = (C.c_void_p * len(mailboxes))(*mailboxes)
+        self.ctx._check(self.ctx.lib.csg_peer_connect_ptrs(self.ctx.handle, self.handle, arr))
+
+    def ensure(self, slot_bytes: int):
+        """Collective when the mailboxes must grow (every rank computes the same sizes)."""
+        if self.handle is not None and self.slot_bytes >= slot_bytes:
+            return
+        self._grow(slot_bytes)
+
+    def _grow(self, slot_bytes: int):
+        raise NotImplementedError
+
+    def allgather(self, src_ptr: int, nbytes: int) -> int:
+        import ctypes as C
+
+        out = C.c_void_p()
+        self.ctx._check(self.ctx.lib.csg_peer_allgather(self.ctx.handle, self.handle, src_ptr, nbytes, C.byref(out)))
+        return out.value
+
+    def clear_error(self):
+        self.ctx._check(self.ctx.lib.csg_peer_clear_error(self.ctx.handle, self.handle))
+
+    def destroy(self):
+        if self.handle is not None:
+            self.ctx.lib.csg_peer_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class IpcPeerExchange(PeerExchange):
+    """One process per GPU: mailboxes mapped through CUDA IPC handles exchanged once over
+    ``torch.distributed`` (plumbing); the data path never touches a library collective."""
+
+    def __init__(self, comm: TorchComm, ctx):
+        super().__init__(ctx, comm.rank, comm.size)
+        self.comm = comm
+
+    def _grow(self, slot_bytes: int):
+        self.ctx.sync()
+        self.comm.barrier()  # nobody may still be writing into a mailbox that is about to go away
+        mine = self._create(int(slot_bytes * 1.25))
+        handles = self.comm.allgather_object(mine)
+        if any(h == bytes(64) for h in handles):
+            raise RuntimeError("CUDA IPC is unavailable on at least one rank")
+        self.connect_ipc(handles)
+        self.comm.barrier()
+
+
+class SharedPeerGroup:
+    """Several ranks living in ONE process (one context / stream each): mailboxes wired by raw
+    device pointers.  Used by the single-GPU tests to run the multi-rank selection for real."""
+
+    def __init__(self, contexts):
+        self.members = [_SharedPeer(self, ctx, r, len(contexts)) for r, ctx in enumerate(contexts)]
+        self.slot_bytes = 0
+
+    def grow(self, slot_bytes: int):
+        if self.slot_bytes >= slot_bytes:
+            return
+        for m in self.members:
+            m.ctx.sync()
+        for m in self.members:
+            m._create(slot_bytes)
+        boxes = [m.mailbox() for m in self.members]
+        for m in self.members:
+            m.connect_ptrs(boxes)
+        self.slot_bytes = slot_bytes
+
+
+class _SharedPeer(PeerExchange):
+    def __init__(self, group, ctx, rank, size):
+        super().__init__(ctx, rank, size)
+        self.group = group
+
+    def ensure(self, slot_bytes: int):
+        self.group.grow(slot_bytes)
+
+
+def make_exchange(comm, ctx):
+    """The exchange a selection on ``ctx`` uses: peer mailboxes over NVLink by default,
+    ``CSG_EXCHANGE=nccl`` selects the library collectives (A/B measurements)."""
+    import os
+
+    if comm is None or getattr(comm, "size", 1) == 1:
+        return LocalExchange()
+    if not hasattr(comm, "allgather_dev"):
+        raise TypeError("multi-rank selection needs a TorchComm (device collectives)")
+    if os.environ.get("CSG_EXCHANGE", "peer").lower() == "nccl" or comm.device.type != "cuda":
+        return NcclExchange(comm, ctx)
+    return IpcPeerExchange(comm, ctx)

@@ -26,6 +26,9 @@ struct csg_ctx {
 extern char g_csg_err[512];
 int csg_fail(csg_ctx* ctx, int status, const char* fmt, ...);
 int csg_scratch(csg_ctx* ctx, size_t bytes, void** out);  // stats.cu
+// Fill on the ctx stream with a KERNEL (ctx.cu): unlike cudaMemsetAsync it never rides a copy-engine
+// queue, where a fill waiting behind a spinning peer-wait kernel would hold up other streams' copies.
+int csg_fill(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes);
 
 #define CSG_CUDA(ctx, call)                                                                  \
   do {                                                                                       \

@@ -18,6 +18,44 @@ int csg_fail(csg_ctx* ctx, int status, const char* fmt, ...) {
   return status;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) fill16_kernel(uint4* __restrict__ dst, size_t n16, unsigned word) {
+  const uint4 v = make_uint4(word, word, word, word);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+__global__ void __launch_bounds__(256) fill1_kernel(unsigned char* __restrict__ dst, size_t n, unsigned char b) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = b;
+}
+}  // namespace
+
+int csg_fill(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (bytes == 0) return CSG_OK;
+  if (!d_dst) return csg_fail(ctx, CSG_ERR_ARG, "csg_fill: NULL destination");
+  const unsigned b = (unsigned)byte_value & 0xffu;
+  unsigned char* p = (unsigned char*)d_dst;
+  const size_t head = (16 - ((uintptr_t)p & 15)) & 15;
+  const size_t h = head < bytes ? head : bytes;
+  if (h) {
+    fill1_kernel<<<1, 32, 0, ctx->stream>>>(p, h, (unsigned char)b);
+    CSG_LAUNCH_CHECK(ctx, "fill1_kernel");
+  }
+  const size_t n16 = (bytes - h) / 16;
+  if (n16) {
+    size_t blocks = (n16 + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    fill16_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((uint4*)(p + h), n16, b * 0x01010101u);
+    CSG_LAUNCH_CHECK(ctx, "fill16_kernel");
+  }
+  const size_t tail = bytes - h - n16 * 16;
+  if (tail) {
+    fill1_kernel<<<1, 32, 0, ctx->stream>>>(p + h + n16 * 16, tail, (unsigned char)b);
+    CSG_LAUNCH_CHECK(ctx, "fill1_kernel");
+  }
+  return CSG_OK;
+}
+
 extern "C" {
 
 int csg_abi_version(void) { return CSG_ABI_VERSION; }
@@ -67,7 +105,7 @@ csg_ctx* csg_create(int device, void* external_stream) {
     cudaEventCreate(&ctx->ev_stop[i]);
     cudaEventCreateWithFlags(&ctx->ev_user[i], cudaEventDisableTiming);
   }
-  cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+  ctx->side = nullptr;  // created on first use (csg_d2h_side)
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming);
   return ctx;
@@ -82,10 +120,12 @@ void csg_destroy(csg_ctx* ctx) {
     cudaEventDestroy(ctx->ev_stop[i]);
     cudaEventDestroy(ctx->ev_user[i]);
   }
-  cudaStreamSynchronize(ctx->side);
+  if (ctx->side) {
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamDestroy(ctx->side);
+  }
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_side);
-  cudaStreamDestroy(ctx->side);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
@@ -159,6 +199,7 @@ int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
 int csg_d2h_side(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   if (!ctx) return CSG_ERR_ARG;
   if (bytes == 0) return CSG_OK;
+  if (!ctx->side) CSG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
   CSG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   CSG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   CSG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->side));
@@ -167,19 +208,17 @@ int csg_d2h_side(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
 }
 int csg_side_join(csg_ctx* ctx) {
   if (!ctx) return CSG_ERR_ARG;
+  if (!ctx->side) return CSG_OK;  // nothing was ever copied out
   CSG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
   return CSG_OK;
 }
 int csg_side_sync(csg_ctx* ctx) {
   if (!ctx) return CSG_ERR_ARG;
+  if (!ctx->side) return CSG_OK;
   CSG_CUDA(ctx, cudaStreamSynchronize(ctx->side));
   return CSG_OK;
 }
-int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes) {
-  if (bytes == 0) return CSG_OK;
-  CSG_CUDA(ctx, cudaMemsetAsync(d_dst, byte_value, bytes, ctx->stream));
-  return CSG_OK;
-}
+int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes) { return csg_fill(ctx, d_dst, byte_value, bytes); }
 
 int csg_timer_start(csg_ctx* ctx, int slot) {
   if (slot < 0 || slot >= 32) return csg_fail(ctx, CSG_ERR_ARG, "timer slot %d out of range", slot);

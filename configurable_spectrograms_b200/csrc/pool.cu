@@ -67,7 +67,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
     pool_hist_first_kernel(const T* __restrict__ mats, const csg_pool_item* __restrict__ items, int max_pos,
                            int bits, int max_E, uint32_t* __restrict__ hist, int32_t* __restrict__ counts,
-                           int32_t* __restrict__ npos) {
+                           int32_t* __restrict__ npos, uint32_t* __restrict__ ehist) {
   extern __shared__ unsigned s_hist[];  // [1 << bits]
   __shared__ unsigned s_red[32];
   const int nb = 1 << bits;
@@ -81,6 +81,9 @@ __global__ void __launch_bounds__(kThreads)
   const int lane = threadIdx.x & 31;
   unsigned mine = 0, row_count = 0;
   int32_t* c = counts + (size_t)(blockIdx.x / kSplit) * max_E;
+  // the same counts keyed by (instrument, position): scanned along the sequence they give the
+  // per-energy totals of every prefix pool (csg_pool_energy_candidates)
+  uint32_t* ec = ehist ? ehist + ((size_t)it.inst * max_pos + it.pos) * max_E : nullptr;
   walk_rows<T>(
       mats + it.mat_off, (it.T + 3) & ~3, it.T, e0, e1,
       [&](T v, bool in, int) {
@@ -91,7 +94,10 @@ __global__ void __launch_bounds__(kThreads)
       },
       [&](int e) {  // per-energy positive count (CS/fast/extrema.py:260-264): the row belongs to this warp
         const unsigned total = __reduce_add_sync(0xffffffffu, row_count);
-        if (lane == 0) c[e] = (int32_t)total;
+        if (lane == 0) {
+          c[e] = (int32_t)total;
+          if (ec) ec[e] = total;
+        }
         mine += row_count;
         row_count = 0;
       });
@@ -235,20 +241,21 @@ __global__ void __launch_bounds__(kThreads)
 extern "C" {
 
 int csg_pool_hist_first(csg_ctx* ctx, const void* d_mats, int dtype, const csg_pool_item* d_items, int n_items,
-                        int max_pos, int bits, int max_E, uint32_t* d_hist, int32_t* d_counts, int32_t* d_npos) {
+                        int max_pos, int bits, int max_E, uint32_t* d_hist, int32_t* d_counts, int32_t* d_npos,
+                        uint32_t* d_ehist) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_items <= 0) return CSG_OK;
   if (bits < 1 || bits > 12) return csg_fail(ctx, CSG_ERR_ARG, "bits %d out of range (1..12)", bits);
   if (max_E <= 0 || max_E > 8192) return csg_fail(ctx, CSG_ERR_ARG, "max_E %d out of range", max_E);
   const size_t smem = (size_t)(1 << bits) * sizeof(unsigned);
-  CSG_CUDA(ctx, cudaMemsetAsync(d_npos, 0, (size_t)n_items * sizeof(int32_t), ctx->stream));
-  CSG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)n_items * max_E * sizeof(int32_t), ctx->stream));
+  if (int rc = csg_fill(ctx, d_npos, 0, (size_t)n_items * sizeof(int32_t))) return rc;
+  if (int rc = csg_fill(ctx, d_counts, 0, (size_t)n_items * max_E * sizeof(int32_t))) return rc;
   if (dtype == CSG_F32)
     pool_hist_first_kernel<float><<<n_items * kSplit, kThreads, smem, ctx->stream>>>((const float*)d_mats, d_items, max_pos, bits,
-                                                                            max_E, d_hist, d_counts, d_npos);
+                                                                            max_E, d_hist, d_counts, d_npos, d_ehist);
   else if (dtype == CSG_F64)
     pool_hist_first_kernel<double><<<n_items * kSplit, kThreads, smem, ctx->stream>>>((const double*)d_mats, d_items, max_pos,
-                                                                             bits, max_E, d_hist, d_counts, d_npos);
+                                                                             bits, max_E, d_hist, d_counts, d_npos, d_ehist);
   else
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
   CSG_LAUNCH_CHECK(ctx, "pool_hist_first_kernel");
@@ -283,6 +290,17 @@ int csg_pool_scan(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const
   const int blocks = n_inst * (int)((cols + kScanCols - 1) / kScanCols);
   pool_scan_kernel<<<blocks, kScanCols * kScanSegs, 0, ctx->stream>>>(d_hist, n_inst, max_pos, d_inst_len, n_slots, 1 << bits,
                                                                        d_slot_table, d_totals);
+  CSG_LAUNCH_CHECK(ctx, "pool_scan_kernel");
+  return CSG_OK;
+}
+
+int csg_pool_scan_cols(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len, int cols,
+                       uint32_t* d_totals) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_inst <= 0 || max_pos <= 0 || cols <= 0) return CSG_OK;
+  const int blocks = n_inst * ((cols + kScanCols - 1) / kScanCols);
+  pool_scan_kernel<<<blocks, kScanCols * kScanSegs, 0, ctx->stream>>>(d_hist, n_inst, max_pos, d_inst_len, 1, cols, nullptr,
+                                                                       d_totals);
   CSG_LAUNCH_CHECK(ctx, "pool_scan_kernel");
   return CSG_OK;
 }

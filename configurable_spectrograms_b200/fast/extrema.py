@@ -125,6 +125,33 @@ def _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor
     return state
 
 
+def chain_ranges(sequence, instrument_order, y_scale, z_scale, state, totals, last_done=None):
+    """``(first, {inst: stop})`` -- the orbit-index range every instrument's chain of scan steps
+    covers -- when the walk is nothing but independent max-merge chains (see
+    :func:`_walk_chains`); ``None`` when some step re-uses, skips or completes differently."""
+    if last_done is None:
+        stored = state.get(f"{y_scale}_{z_scale}_last_orbit", -1)
+        last_done = int(stored) if isinstance(stored, (int, float)) else -1
+    if not sequence or not instrument_order or (y_scale == "linear" and z_scale == "linear"):
+        return None
+    for inst in instrument_order:
+        entry = state.get(f"{inst}_{y_scale}_{z_scale}_extrema_progress")
+        if isinstance(entry, dict) and entry.get("complete"):
+            return None
+        if f"{inst}_linear_linear_y_max" in state or f"{inst}_linear_linear_z_max" in state:
+            return None
+    first = next((k for k, (orbit, _h) in enumerate(sequence) if orbit > last_done), None)
+    if first is None:
+        return None
+    last_index = len(sequence) - 1
+    # every later orbit must pass the `orbit <= last_done` gate too (ascending sequences always do)
+    if any(orbit <= last_done for orbit, _h in sequence[first:]):
+        return None
+    # the per-step loop runs first..stop: it breaks after the step that makes the instrument
+    # "complete" (orbit_index + 1 >= total, :315-319), and always runs one step
+    return first, {inst: min(last_index, max(first, totals[inst] - 1)) for inst in instrument_order}
+
+
 def _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, last_done, on_scan) -> bool:
     """The loop of :func:`_walk` when every (orbit, instrument) step is a plain scan step: nothing
     is re-used from the linear/linear keys, nothing is complete, nobody watches the intermediate
@@ -132,21 +159,10 @@ def _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, la
     survive, so each chain runs on local variables and ``state`` is written once -- the same
     arithmetic in the same order per instrument, without ~25 dict operations per step.
     Returns False (state untouched) when the preconditions do not hold."""
-    if not sequence or not instrument_order or (y_scale == "linear" and z_scale == "linear"):
+    ranges = chain_ranges(sequence, instrument_order, y_scale, z_scale, state, totals, last_done)
+    if ranges is None:
         return False
-    for inst in instrument_order:
-        entry = state.get(f"{inst}_{y_scale}_{z_scale}_extrema_progress")
-        if isinstance(entry, dict) and entry.get("complete"):
-            return False
-        if f"{inst}_linear_linear_y_max" in state or f"{inst}_linear_linear_z_max" in state:
-            return False
-    first = next((k for k, (orbit, _h) in enumerate(sequence) if orbit > last_done), None)
-    if first is None:
-        return False
-    last_index = len(sequence) - 1
-    # every later orbit must pass the `orbit <= last_done` gate too (ascending sequences always do)
-    if any(orbit <= last_done for orbit, _h in sequence[first:]):
-        return False
+    first, stops = ranges
     results = {}
     last_executed = first
     range_max = getattr(on_scan, "range_max", None)
@@ -155,7 +171,7 @@ def _walk_chains(sequence, instrument_order, y_scale, z_scale, state, totals, la
         prev_e, prev_z = state.get(f"{stem}_y_max"), state.get(f"{stem}_z_max")
         # the per-step loop below runs first..stop: it breaks after the step that makes the
         # instrument "complete" (orbit_index + 1 >= total, :315-319), and always runs one step
-        stop = min(last_index, max(first, totals[inst] - 1))
+        stop = stops[inst]
         folded = range_max(inst, first, stop) if range_max is not None else None
         if folded is not None:
             # ceil and min(4000, .) are monotone, so folding the max-merge over the steps equals
@@ -285,8 +301,36 @@ def _energy_plan(shard, comm, instrument_order, steps, owners, first):
     return plan, n_max, max_E
 
 
+def _device_y_tables(instrument_order, eplan, max_E):
+    """Static energy tables for ``csg_pool_energy_candidates`` -- or None when some instrument's
+    files do not share one table of distinct, NaN-free energies (the host path handles those)."""
+    n_inst = len(instrument_order)
+    order = np.zeros((n_inst, max_E), dtype=np.int32)
+    keys = np.zeros((n_inst, max_E), dtype=np.float64)
+    n_keys = np.zeros(n_inst, dtype=np.int32)
+    covered = {}
+    for ii, inst in enumerate(instrument_order):
+        present, _rows, _en, steps_arr, pos, ascending, table = eplan[inst]
+        if not ascending:
+            return None
+        cov = np.zeros(int(steps_arr.max()) + 1 if len(steps_arr) else 0, dtype=bool)
+        if present:
+            if table is None:
+                return None
+            e0, uniq, _idx = table
+            if len(uniq) != len(e0) or len(e0) > max_E or np.isnan(e0).any():
+                return None
+            o = np.argsort(e0, kind="stable")
+            order[ii, : len(e0)], keys[ii, : len(e0)], n_keys[ii] = o, e0[o], len(e0)
+            idx = np.full(len(steps_arr), -1, dtype=np.int64)
+            idx[pos] = 1
+            cov[steps_arr] = np.maximum.accumulate(idx) >= 0
+        covered[inst] = cov
+    return {"order": order, "keys": keys, "n_keys": n_keys, "covered": covered}
+
+
 def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
-                    max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None):
+                    max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None, per_step=True):
     """Enqueue the pooled-extrema selection (K2b) for an already collapsed :class:`pipeline.ShardPlan`.
 
     Everything runs asynchronously on the context's stream (``pool_select.DevicePoolSelector``);
@@ -296,6 +340,11 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
     ``sequence[k] = (orbit, {inst: True})`` must list the GLOBAL ascending orbit sequence
     (all ranks); ``shard.orbits`` holds this rank's contiguous slice starting at
     ``shard.first_orbit_index``.
+
+    ``per_step=False`` promises that :func:`extrema_finish` will not be asked for the state after
+    every step (no ``on_step_done``): when the walk then reduces to independent max-merge chains
+    (:func:`chain_ranges`) the y candidates are max-merged on the device too and the per-file
+    counts never travel to the host.
     """
     from ..pool_select import DevicePoolSelector, SingleRank
 
@@ -316,11 +365,28 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
         }
         items, inst_len, owners = shard.pool_items(local_steps)
         eplan, n_max, max_E = _energy_plan(shard, comm, instrument_order, steps, owners, first)
+        max_E = (max_E + 3) & ~3  # count rows pack to 16 bytes (exchange payloads)
+        ranges = chain_ranges(sequence, instrument_order, y_scale, z_scale, state, totals)
+        ytab = _device_y_tables(instrument_order, eplan, max_E) if ranges is not None else None
+        if ytab is not None:
+            first_step, stops = ranges
+            # positions of this rank that take part in each chain (global orbit index <= stop)
+            ytab["limit"] = np.array(
+                [sum(1 for i2, oi, _f in owners if i2 == inst and oi + first <= stops[inst]) for inst in instrument_order],
+                dtype=np.int32)
+            ytab["zero"] = {}
+            for inst in instrument_order:
+                cov = ytab["covered"][inst]
+                seg = np.zeros(stops[inst] + 1 - first_step, dtype=bool)
+                part = cov[first_step : stops[inst] + 1]
+                seg[: len(part)] = part
+                ytab["zero"][inst] = not bool(seg.all())  # some step of the chain sees the 0.0 candidate
         if len(cache) > 8:
             cache.clear()
         # the entry holds `sequence` itself, so its id() cannot be recycled while the entry lives
-        hit = cache[key] = (sequence, steps, totals, items, inst_len, owners, eplan, n_max, max_E)
-    _, steps, totals, items, inst_len, owners, eplan, n_max, max_E = hit
+        hit = cache[key] = (sequence, steps, totals, items, inst_len, owners, eplan, n_max, max_E, ytab)
+    _, steps, totals, items, inst_len, owners, eplan, n_max, max_E, ytab = hit
+    ydev = ytab if not per_step else None
     requests = [{"inst": ii, "p": max_percentile, "mode": "running_max"} for ii in range(len(instrument_order))]
     if compute_mins:
         requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
@@ -328,13 +394,13 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
     if selector is None:
         selector = shard._pool_selector = DevicePoolSelector(shard.batch)  # persistent scratch across steps
     selector.enqueue(shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm,
-                     count_rows=n_max)
+                     count_rows=n_max, ydev=ydev)
     return {
         "shard": shard, "sequence": sequence, "instrument_order": instrument_order, "y_scale": y_scale, "z_scale": z_scale,
         "state": state, "compute_mins": compute_mins, "log_floor_cutoff": log_floor_cutoff,
         "log_floor_value": log_floor_value, "comm": comm, "steps": steps, "totals": totals, "first": first,
         "items": items, "inst_len": inst_len, "owners": owners, "requests": requests, "max_E": max_E, "selector": selector,
-        "eplan": eplan, "n_max": n_max,
+        "eplan": eplan, "n_max": n_max, "ydev": ydev,
     }
 
 
@@ -346,6 +412,8 @@ def extrema_finish(pending, on_step_done=None):
     instrument_order, steps = pending["instrument_order"], pending["steps"]
     requests, compute_mins = pending["requests"], pending["compute_mins"]
     selector = pending["selector"]
+    if pending.get("ydev") is not None:
+        return _finish_device_y(pending, on_step_done)
     # ---- y extrema: per-step energy candidates from every rank's per-file positive counts
     # (available after the first histogram pass; this overlaps the digit loop on the GPU)
     all_counts, npos = selector.result_counts()  # multi-rank: every rank's rows (device all-gather)
@@ -407,13 +475,62 @@ def extrema_finish(pending, on_step_done=None):
                  pending["totals"], pending["log_floor_cutoff"], pending["log_floor_value"], scan, on_step_done)
 
 
+def _finish_device_y(pending, on_step_done):
+    """:func:`extrema_finish` when both extrema were max-merged on the device: one read-back of
+    ``n_requests + n_instruments`` numbers, then one merge per instrument."""
+    if on_step_done is not None:
+        raise ValueError("extrema_enqueue(per_step=False) cannot report the state after every step")
+    from ..pool_select import GpuPoolBackend, prefix_percentiles
+
+    shard, comm = pending["shard"], pending["comm"]
+    instrument_order, requests = pending["instrument_order"], pending["requests"]
+    selector, ydev = pending["selector"], pending["ydev"]
+    values = selector.result_values()
+    ycands = selector.result_y_candidates()
+    if values is None:  # slot-table overflow: same kernels, digit loop driven from the host
+        backend = getattr(shard, "_pool_backend", None)
+        if backend is None:
+            backend = shard._pool_backend = GpuPoolBackend(shard.batch)
+        values, _, _ = prefix_percentiles(
+            backend, shard.batch.dtype, pending["items"], len(instrument_order), pending["inst_len"], pending["max_E"],
+            requests, comm=comm,
+        )
+    n_inst = len(instrument_order)
+    per_inst = {}
+    for ii, inst in enumerate(instrument_order):
+        z = values[ii]
+        z_min = 0
+        if pending["compute_mins"]:
+            zm = values[n_inst + ii]
+            z_min = float(zm) if zm is not None else 0
+        top = ycands[ii]
+        if top is None:
+            top = 0.0  # no file took part: every step of the chain saw the empty-pool candidate
+        elif ydev["zero"][inst]:
+            top = max(top, 0.0)
+        per_inst[inst] = (top, float(z) if z is not None else 0.0, z_min)
+
+    def scan(inst, orbit_index, handle):
+        raise AssertionError("per-step scan requested from a device-merged selection")
+
+    scan.range_max = lambda inst, first, stop: per_inst[inst]
+    state = pending["state"]
+    totals = pending["totals"]
+    stored = state.get(f"{pending['y_scale']}_{pending['z_scale']}_last_orbit", -1)
+    last_done = int(stored) if isinstance(stored, (int, float)) else -1
+    if not _walk_chains(pending["sequence"], instrument_order, pending["y_scale"], pending["z_scale"], state, totals,
+                        last_done, scan):
+        raise AssertionError("chain preconditions changed between enqueue and finish")
+    return state
+
+
 def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
                        max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None,
                        on_step_done=None):
     """Update ``state`` from an already collapsed :class:`pipeline.ShardPlan` (enqueue + finish)."""
     pending = extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, compute_mins=compute_mins,
                               max_percentile=max_percentile, log_floor_cutoff=log_floor_cutoff,
-                              log_floor_value=log_floor_value, comm=comm)
+                              log_floor_value=log_floor_value, comm=comm, per_step=on_step_done is not None)
     return extrema_finish(pending, on_step_done)
 
 

@@ -153,7 +153,7 @@ class GpuPoolBackend:
             self.ctx._check(
                 self.ctx.lib.csg_pool_hist_first(
                     self.ctx.handle, self.batch.d_sums.ptr, self.batch.code, self.d_items.ptr, self.n_items,
-                    self.max_pos, bits, self.max_E, self.d_hist.ptr, d_counts.ptr, d_npos.ptr,
+                    self.max_pos, bits, self.max_E, self.d_hist.ptr, d_counts.ptr, d_npos.ptr, None,
                 )
             )
         counts = self._get("counts", d_counts, np.int32, self.n_items * self.max_E, sync=False)
@@ -234,32 +234,88 @@ class DevicePoolSelector:
         return dev
 
     def enqueue(self, dtype, items: np.ndarray, n_inst: int, inst_len: np.ndarray, max_E: int, requests: list[dict],
-                comm=None, count_rows: int | None = None):
+                comm=None, count_rows: int | None = None, exchange=None, ydev: dict | None = None, dry: bool = False):
         """``count_rows`` (multi-rank): rows of the per-file count table every rank contributes to the
-        device all-gather (the largest item count over the ranks); ``result_counts`` then returns
-        every rank's rows, rank after rank."""
+        gather (the largest item count over the ranks); ``result_counts`` then returns every
+        rank's rows, rank after rank.
+
+        ``exchange``: the all-gather the ranks meet through (``comm.make_exchange``; built from
+        ``comm`` when omitted).  ``ydev``: per-instrument energy tables for the on-device y
+        candidates -- ``{"order": int32[n_inst][max_E], "keys": float64[n_inst][max_E],
+        "n_keys": int32[n_inst], "limit": int32[n_inst]}`` -- in which case the per-file counts
+        are neither gathered nor read back (``result_counts`` is not available)."""
+        from .comm import LocalExchange, NcclExchange, make_exchange
+
         comm = comm or SingleRank()
-        if comm.size > 1 and hasattr(comm, "stream_scope"):
+        if exchange is None:
+            exchange = self.__dict__.get("_exchange")
+            if exchange is None or exchange.size != comm.size:
+                exchange = self._exchange = make_exchange(comm, self.ctx)
+        self._slot_bytes_needed = self._payload_bytes(np.dtype(dtype), n_inst, max_E, len(items), count_rows, len(requests),
+                                                      exchange.size, ydev is not None)
+        try:
+            exchange.ensure(self._slot_bytes_needed)
+        except RuntimeError:
+            if exchange.kind != "peer" or not hasattr(comm, "allgather_dev"):
+                raise
+            # no CUDA IPC here (every rank sees the same handle table, so every rank lands here)
+            exchange = self._exchange = NcclExchange(comm, self.ctx)
+            exchange.ensure(self._slot_bytes_needed)
+        if exchange.kind == "nccl":
             # NCCL is ordered against THIS context's stream: one stream switch for the whole digit loop
             with comm.stream_scope(self.ctx.stream_handle):
-                return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, None)
-        sh = self.ctx.stream_handle if comm.size > 1 else 0
-        return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, sh)
+                return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, exchange, count_rows, ydev, dry)
+        return self._enqueue(dtype, items, n_inst, inst_len, max_E, requests, exchange, count_rows, ydev, dry)
 
-    def _enqueue(self, dtype, items, n_inst, inst_len, max_E, requests, comm, count_rows, sh):
+    def reserve(self, *args, **kwargs):
+        """Same arguments as :meth:`enqueue`: allocate every scratch buffer, upload the static
+        tables, size the exchange mailboxes -- and launch nothing.  Device allocations order
+        kernels of different streams behind each other, so ranks that share ONE process (the
+        single-GPU tests) must all reserve before any of them enqueues; one process per GPU
+        never needs this."""
+        return self.enqueue(*args, dry=True, **kwargs)
+
+    def _payload_bytes(self, D, n_inst, max_E, n_items, count_rows, n_req, R, device_y):
+        S = self.N_SLOTS
+        bits0 = digit_plan(D)[0][1]
+        rows = max(n_items, 1) if (R == 1 or count_rows is None) else max(int(count_rows), n_items, 1)
+        sizes = [
+            _al(n_inst * ((1 << bits0) + max(int(max_E), 1)) * 4, 16),
+            n_inst * S * 1024 * 4,
+            int(self.ctx.lib.csg_pool_slot_payload_bytes(n_inst, S)),
+            _al((n_req + n_inst + 5) * 8, 16),
+        ]
+        if not device_y:
+            sizes.append(_al(rows * max(int(max_E), 1) * 4, 16))
+        return max(sizes)
+
+    def _enqueue(self, dtype, items, n_inst, inst_len, max_E, requests, ex, count_rows, ydev, dry=False):
+        """``dry``: allocate / upload every buffer the step needs and launch nothing (see ``reserve``)."""
         ctx, lib, mem = self.ctx, self.ctx.lib, self.mem
-        h, chk = ctx.handle, ctx._check
+        h = ctx.handle
+
+        def run(fn, *args):
+            if not dry:
+                ctx._check(fn(*args))
+
+        def gather(src_ptr, nbytes):
+            return src_ptr if dry else ex.allgather(src_ptr, nbytes)
+
+        def record(slot):
+            if not dry:
+                ctx.event_record(slot)
+
         D = np.dtype(dtype)
         code = _lib.np_dtype_code(D)
         plan = digit_plan(D)
-        R, S = comm.size, self.N_SLOTS
+        R, S = ex.size, self.N_SLOTS
         n_items, n_req = len(items), len(requests)
         max_pos = max(int(inst_len.max()) if len(inst_len) else 0, 1)
-        if R > 1:  # the table shape must agree across ranks only per rank; exchanged buffers are per (inst, slot, bin)
-            pass
         max_E = max(int(max_E), 1)
+        device_y = ydev is not None
         # ---- static tables (re-uploaded only when they change)
-        key = (items.tobytes(), n_inst, inst_len.tobytes(), max_E, repr(requests), D.str)
+        key = (items.tobytes(), n_inst, inst_len.tobytes(), max_E, repr(requests), D.str,
+               None if ydev is None else tuple(np.ascontiguousarray(ydev[k]).tobytes() for k in ("order", "keys", "n_keys", "limit")))
         if key != self._static_key:
             reqs = np.zeros(max(n_req, 1), dtype=POOL_REQUEST)
             for r, rq in enumerate(requests):
@@ -267,96 +323,125 @@ class DevicePoolSelector:
             self.d_items = self._put("items", items) if n_items else None
             self.d_inst_len = self._put("inst_len", np.ascontiguousarray(inst_len, dtype=np.int32))
             self.d_reqs = self._put("reqs", reqs)
+            if device_y:
+                self.d_order = self._put("y_order", np.ascontiguousarray(ydev["order"], dtype=np.int32))
+                self.d_keys = self._put("y_keys", np.ascontiguousarray(ydev["keys"], dtype=np.float64))
+                self.d_nkeys = self._put("y_nkeys", np.ascontiguousarray(ydev["n_keys"], dtype=np.int32))
+                self.d_limit = self._put("y_limit", np.ascontiguousarray(ydev["limit"], dtype=np.int32))
             self._static_key = key
         shift0, bits0 = plan[0]
         nb0 = 1 << bits0
         hist0 = mem.device("hist0", n_inst * max_pos * nb0 * 4)
-        chk(lib.csg_memset(h, hist0.ptr, 0, n_inst * max_pos * nb0 * 4))
+        run(lib.csg_memset, h, hist0.ptr, 0, n_inst * max_pos * nb0 * 4)
         rows = max(n_items, 1) if (R == 1 or count_rows is None) else max(int(count_rows), n_items, 1)
         d_counts = mem.device("counts", rows * max_E * 4)
         d_npos = mem.device("npos", max(n_items, 1) * 4)
-        if R > 1:
-            chk(lib.csg_memset(h, d_counts.ptr, 0, rows * max_E * 4))
+        d_ehist = None
+        if device_y:
+            d_ehist = mem.device("ehist", n_inst * max_pos * max_E * 4)
+            run(lib.csg_memset, h, d_ehist.ptr, 0, n_inst * max_pos * max_E * 4)
+        elif R > 1:
+            run(lib.csg_memset, h, d_counts.ptr, 0, rows * max_E * 4)
         sums = self.batch.d_sums.ptr
         if n_items:
-            chk(lib.csg_pool_hist_first(h, sums, code, self.d_items.ptr, n_items, max_pos, bits0, max_E, hist0.ptr,
-                                        d_counts.ptr, d_npos.ptr))
-        # the per-energy positive counts are final here: read them back now so the host can work
-        # on the y extrema while the digit loop runs
-        n_count_rows = n_items if R == 1 else R * rows
-        sizes = [("values", 64 * 8), ("has", 64 * 4), ("flags", 16), ("counts", n_count_rows * max_E * 4), ("npos", n_items * 4)]
-        pin = mem.pinned("readback", sum(_al(n) for _, n in sizes))
+            run(lib.csg_pool_hist_first, h, sums, code, self.d_items.ptr, n_items, max_pos, bits0, max_E, hist0.ptr,
+                                        d_counts.ptr, d_npos.ptr, d_ehist.ptr if device_y else None)
+        n_out = (n_req + n_inst + 5 + 1) & ~1  # doubles, 16-byte multiple
+        n_count_rows = 0 if device_y else (n_items if R == 1 else R * rows)
+        sizes = [("out", n_out * 8), ("counts", n_count_rows * max_E * 4), ("npos", n_items * 4)]
+        pin = mem.pinned("readback", sum(_al(n) for _, n in sizes) + 64)
         views, off = {}, 0
         for name, n in sizes:
             views[name] = (off, n)
             off += _al(n)
-        if R > 1:  # every rank's per-file counts, gathered on the device
-            d_counts_all = mem.device("counts_all", R * rows * max_E * 4)
-            comm.allgather_dev(d_counts.ptr, d_counts_all.ptr, rows * max_E * 4, sh)
-            chk(lib.csg_d2h(h, pin.ptr + views["counts"][0], d_counts_all.ptr, R * rows * max_E * 4))
-        elif n_items:
-            chk(lib.csg_d2h(h, pin.ptr + views["counts"][0], d_counts.ptr, n_items * max_E * 4))
-        if n_items:
-            chk(lib.csg_d2h(h, pin.ptr + views["npos"][0], d_npos.ptr, n_items * 4))
-        ctx.event_record(self.EVENT_SLOT - 1)
-        d_tot = mem.device("totals", n_inst * S * 1024 * 4) if R > 1 else None
-        d_gath = mem.device("gath", R * n_inst * S * 1024 * 4) if R > 1 else None
+        if not device_y:
+            # the per-energy positive counts are final here: read them back now so the host can
+            # work on the y extrema while the digit loop runs
+            if R > 1:  # every rank's per-file counts, gathered on the device
+                g = gather(d_counts.ptr, _al(rows * max_E * 4, 16))
+                run(lib.csg_d2h, h, pin.ptr + views["counts"][0], g, R * rows * max_E * 4)
+                assert _al(rows * max_E * 4, 16) == rows * max_E * 4 or R == 1, "count rows must pack to 16 bytes"
+            elif n_items:
+                run(lib.csg_d2h, h, pin.ptr + views["counts"][0], d_counts.ptr, n_items * max_E * 4)
+            if n_items:
+                run(lib.csg_d2h, h, pin.ptr + views["npos"][0], d_npos.ptr, n_items * 4)
+            record(self.EVENT_SLOT - 1)
+        # ---- level 0: scan, exchange [bucket totals | per-energy totals], lower ranks' base
+        e_cols = max_E if device_y else 0
+        pay0 = _al(n_inst * (nb0 + e_cols) * 4, 16)
+        d_tot = mem.device("totals", max(n_inst * S * 1024 * 4, pay0))
         d_base = mem.device("base", n_inst * S * 1024 * 4) if R > 1 else None
         d_above = mem.device("above", n_inst * 8) if R > 1 else None
-        chk(lib.csg_pool_scan(h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, None, d_tot.ptr if R > 1 else None))
+        run(lib.csg_pool_scan, h, hist0.ptr, n_inst, max_pos, self.d_inst_len.ptr, 1, bits0, None, d_tot.ptr if R > 1 else None)
+        etot_off = n_inst * nb0 * 4
+        if device_y:
+            run(lib.csg_pool_scan_cols, h, d_ehist.ptr, n_inst, max_pos, self.d_inst_len.ptr, max_E,
+                                       d_tot.ptr + etot_off if R > 1 else None)
+        g_etot, stride0 = None, pay0 // 4
         if R > 1:
-            comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * nb0 * 4, sh)
-            chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, nb0, d_base.ptr, d_above.ptr))
+            g0 = gather(d_tot.ptr, pay0)
+            run(lib.csg_pool_base, h, g0, stride0, R, ex.rank, n_inst, nb0, d_base.ptr, d_above.ptr)
+            g_etot = g0 + etot_off
+        d_ycand = None
+        if device_y:
+            d_ycand = mem.device("ycand", n_inst * 8)
+            run(lib.csg_pool_energy_candidates, h, d_ehist.ptr, n_inst, max_pos, max_E, self.d_order.ptr, self.d_keys.ptr,
+                                               self.d_nkeys.ptr, self.d_limit.ptr, g_etot, stride0, ex.rank, d_ycand.ptr)
         d_n_after = mem.device("n_after", n_inst * max_pos * 8)
         d_below = mem.device("below", n_inst * 8)
         d_flags = mem.device("flags", 16)
         d_sel = mem.device("sel", max(n_req, 1) * max_pos * POOL_SEL.itemsize)
-        d_best = mem.device("best", 64 * 8)
-        d_local = mem.device("local_slots", n_inst * S * 8)
-        d_gslots = mem.device("gath_slots", R * n_inst * S * 8) if R > 1 else d_local
+        slot_pay = int(lib.csg_pool_slot_payload_bytes(n_inst, S))
+        d_xbuf = mem.device("slot_payload", slot_pay)  # [64 x int64 bounds | n_inst x S slot lists]
+        d_best, d_local = d_xbuf.ptr, d_xbuf.ptr + 64 * 8
         d_table = mem.device("table", n_inst * S * 8)
         d_values = mem.device("values", 64 * 8)
         d_has = mem.device("has", 64 * 4)
+        d_out = mem.device("out", n_out * 8)
+        d_red = mem.device("out_reduced", n_out * 8)
         base_ptr = d_base.ptr if R > 1 else None
-        chk(lib.csg_memset(h, d_flags.ptr, 0, 16))
-        chk(lib.csg_pool_row_totals(h, hist0.ptr, n_inst, max_pos, bits0, base_ptr, d_n_after.ptr, d_below.ptr))
-        chk(lib.csg_pool_sel_init(h, code, self.d_reqs.ptr, n_req, self.d_inst_len.ptr, max_pos, d_n_after.ptr,
-                                  d_below.ptr, d_above.ptr if R > 1 else None, d_sel.ptr))
-        chk(lib.csg_pool_sel_locate(h, hist0.ptr, max_pos, 1, bits0, base_ptr, d_sel.ptr, n_req, d_flags.ptr))
+        run(lib.csg_memset, h, d_flags.ptr, 0, 16)
+        run(lib.csg_pool_row_totals, h, hist0.ptr, n_inst, max_pos, bits0, base_ptr, d_n_after.ptr, d_below.ptr)
+        run(lib.csg_pool_sel_init, h, code, self.d_reqs.ptr, n_req, self.d_inst_len.ptr, max_pos, d_n_after.ptr,
+                                  d_below.ptr, d_above.ptr if R > 1 else None, d_sel.ptr)
+        run(lib.csg_pool_sel_locate, h, hist0.ptr, max_pos, 1, bits0, base_ptr, d_sel.ptr, n_req, d_flags.ptr)
         prev_shift = shift0
-        hist1 = None
         for shift, bits in plan[1:]:
             nb = 1 << bits
-            chk(lib.csg_pool_sel_bounds(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr))
-            if R > 1:
-                comm.allreduce_max_dev(d_best.ptr, n_req, "i8", sh)
-            chk(lib.csg_pool_sel_slots(h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best.ptr, n_inst, S,
-                                       d_local.ptr, d_flags.ptr))
-            if R > 1:
-                comm.allgather_dev(d_local.ptr, d_gslots.ptr, n_inst * S * 8, sh)
-            chk(lib.csg_pool_sel_assign(h, d_sel.ptr, n_req, max_pos, d_gslots.ptr, R, n_inst, S, d_table.ptr, d_flags.ptr))
+            # bounds + locally pruned slot lists travel together; the global bound is applied after
+            run(lib.csg_pool_sel_bounds, h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best)
+            run(lib.csg_pool_sel_slots, h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, d_best, n_inst, S,
+                                       d_local, d_flags.ptr)
+            g = gather(d_xbuf.ptr, slot_pay) if R > 1 else d_xbuf.ptr
+            run(lib.csg_pool_sel_assign, h, d_sel.ptr, self.d_reqs.ptr, n_req, max_pos, prev_shift, g, slot_pay, R, n_inst, S,
+                                        d_table.ptr, d_flags.ptr)
             nbytes = n_inst * max_pos * S * nb * 4
             hist1 = mem.device("hist1", nbytes)
-            chk(lib.csg_memset(h, hist1.ptr, 0, nbytes))
+            run(lib.csg_memset, h, hist1.ptr, 0, nbytes)
             if n_items:
-                chk(lib.csg_pool_hist_refine(h, sums, code, self.d_items.ptr, n_items, max_pos, S, d_table.ptr, prev_shift,
-                                             shift, bits, hist1.ptr))
-            chk(lib.csg_pool_scan(h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_table.ptr,
-                                  d_tot.ptr if R > 1 else None))
+                run(lib.csg_pool_hist_refine, h, sums, code, self.d_items.ptr, n_items, max_pos, S, d_table.ptr, prev_shift,
+                                             shift, bits, hist1.ptr)
+            run(lib.csg_pool_scan, h, hist1.ptr, n_inst, max_pos, self.d_inst_len.ptr, S, bits, d_table.ptr,
+                                  d_tot.ptr if R > 1 else None)
             if R > 1:
-                comm.allgather_dev(d_tot.ptr, d_gath.ptr, n_inst * S * nb * 4, sh)
-                chk(lib.csg_pool_base(h, d_gath.ptr, R, comm.rank, n_inst, S * nb, d_base.ptr, None))
-            chk(lib.csg_pool_sel_locate(h, hist1.ptr, max_pos, S, bits, base_ptr, d_sel.ptr, n_req, d_flags.ptr))
+                g = gather(d_tot.ptr, n_inst * S * nb * 4)
+                run(lib.csg_pool_base, h, g, n_inst * S * nb, R, ex.rank, n_inst, S * nb, d_base.ptr, None)
+            run(lib.csg_pool_sel_locate, h, hist1.ptr, max_pos, S, bits, base_ptr, d_sel.ptr, n_req, d_flags.ptr)
             prev_shift = shift
-        chk(lib.csg_pool_sel_finish(h, code, d_sel.ptr, n_req, max_pos, d_values.ptr, d_has.ptr))
-        if R > 1:  # "has" follows from the reduced value (-inf = no rank held an entry)
-            comm.allreduce_max_dev(d_values.ptr, n_req, "f8", sh)
-            comm.allreduce_max_dev(d_flags.ptr, 4, "i4", sh)
-        # ---- asynchronous read-back of the few results
-        for name, dev in (("values", d_values), ("has", d_has), ("flags", d_flags)):
-            chk(lib.csg_d2h(h, pin.ptr + views[name][0], dev.ptr, views[name][1]))
-        ctx.event_record(self.EVENT_SLOT)
-        self._pending = (pin, views, n_req, n_items, max_E, n_count_rows)
+        run(lib.csg_pool_sel_finish, h, code, d_sel.ptr, n_req, max_pos, d_values.ptr, d_has.ptr)
+        # ---- one last payload: [values | y candidates | flags | exchange error], max over the ranks
+        run(lib.csg_pool_pack_results, h, d_values.ptr, n_req, d_ycand.ptr if device_y else None, n_inst, d_flags.ptr,
+                                      ex.error_ptr, d_out.ptr, n_out)
+        src = d_out.ptr
+        if R > 1:
+            g = gather(d_out.ptr, n_out * 8)
+            run(lib.csg_pool_reduce_max, h, g, R, n_out, d_red.ptr)
+            src = d_red.ptr
+        run(lib.csg_d2h, h, pin.ptr + views["out"][0], src, n_out * 8)
+        record(self.EVENT_SLOT)
+        if not dry:
+            self._last_exchange = ex
+            self._pending = (pin, views, n_req, n_items, max_E, n_count_rows, n_inst, device_y)
 
     def _view(self, name, dt):
         pin, views = self._pending[0], self._pending[1]
@@ -364,21 +449,41 @@ class DevicePoolSelector:
 
     def result_counts(self):
         """(counts[n_items][max_E], npos[n_items]) -- available right after the first histogram pass."""
-        _, _, _, n_items, max_E, n_count_rows = self._pending
+        _, _, _, n_items, max_E, n_count_rows, _, device_y = self._pending
+        if device_y:
+            raise _lib.CsgError("per-file counts are not read back when the y candidates are computed on the device")
         self.ctx.event_sync(self.EVENT_SLOT - 1)
         return self._view("counts", np.int32).reshape(n_count_rows, max_E).copy(), self._view("npos", np.int32).copy()
+
+    def _out(self):
+        n_req, n_inst = self._pending[2], self._pending[6]
+        self.ctx.event_sync(self.EVENT_SLOT)
+        out = self._view("out", np.float64)
+        flags = out[n_req + n_inst : n_req + n_inst + 4]
+        if out[n_req + n_inst + 4] != 0:
+            ex = self.__dict__.get("_last_exchange")
+            if ex is not None and hasattr(ex, "clear_error"):
+                ex.clear_error()
+            raise _lib.CsgError(f"peer exchange timed out waiting for rank {int(out[n_req + n_inst + 4]) - 1}")
+        return out, flags
 
     def result_values(self):
         """One float per request (None: empty pool), or None when the slot table overflowed."""
         n_req = self._pending[2]
-        self.ctx.event_sync(self.EVENT_SLOT)
-        flags = self._view("flags", np.int32)
+        out, flags = self._out()
         if flags[1]:  # slot overflow: later digits ran on a truncated table, their flags mean nothing
+            self.overflows = self.__dict__.get("overflows", 0) + 1
             return None
         if flags[0] or flags[2]:
             raise _lib.CsgError("device pool selection: a rank fell outside its bucket (histogram / scan mismatch)")
-        vals = self._view("values", np.float64)[:n_req]
-        return [float(v) if np.isfinite(v) else None for v in vals]
+        return [float(v) if np.isfinite(v) else None for v in out[:n_req]]
+
+    def result_y_candidates(self):
+        """Largest 99 %-coverage energy per instrument over the positions below ``limit`` (None:
+        no position took part on any rank).  Only with ``ydev``."""
+        n_req, n_inst = self._pending[2], self._pending[6]
+        out, _ = self._out()
+        return [float(v) if v != -np.inf else None for v in out[n_req : n_req + n_inst]]
 
     def result(self):
         """(values | None on slot overflow, counts, npos); waits for the read-backs only."""

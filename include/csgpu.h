@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 8
+#define CSG_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -271,7 +271,10 @@ typedef struct {
  * CS/fast/extrema.py:260-264), d_npos[item] (int32).  hist_stride_pos = slots*bins. */
 CSG_API int csg_pool_hist_first(csg_ctx* ctx, const void* d_mats, int dtype, const csg_pool_item* d_items,
                         int n_items, int max_pos, int bits, int max_E, uint32_t* d_hist,
-                        int32_t* d_counts, int32_t* d_npos);
+                        int32_t* d_counts, int32_t* d_npos, uint32_t* d_ehist);
+/* d_ehist (may be NULL; zeroed by the caller) [inst][pos][max_E]: the same per-energy counts keyed
+ * by (instrument, position) -- csg_pool_scan_cols() turns them into the per-energy totals of
+ * every prefix pool, the input of csg_pool_energy_candidates(). */
 /* Refinement pass: cells whose key >> prefix_shift equals d_slot_prefix[inst][s] are counted
  * in d_hist[inst][pos][s][(key >> shift) & (bins-1)].  d_slot_prefix is sorted ascending per
  * instrument, padded with UINT64_MAX, n_slots entries per instrument. */
@@ -284,6 +287,9 @@ CSG_API int csg_pool_hist_refine(csg_ctx* ctx, const void* d_mats, int dtype, co
  * the UINT64_MAX padding are skipped (their totals are 0). */
 CSG_API int csg_pool_scan(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len,
                   int n_slots, int bits, const uint64_t* d_slot_table, uint32_t* d_totals);
+/* The same scan over an arbitrary number of columns per (inst, pos) row (the per-energy counts). */
+CSG_API int csg_pool_scan_cols(csg_ctx* ctx, uint32_t* d_hist, int n_inst, int max_pos, const int32_t* d_inst_len,
+                       int cols, uint32_t* d_totals);
 /* One query = (inst, pos, slot, rank): find the bin of the scanned row where the cumulative
  * count first exceeds rank; writes bin and the residual rank inside that bin.  d_base (may be
  * NULL) [inst][slot][bin]: counts held by lower ranks, added to every row on the fly. */
@@ -337,17 +343,65 @@ CSG_API int csg_pool_sel_bounds(csg_ctx* ctx, const csg_pool_sel* d_sel, const c
 CSG_API int csg_pool_sel_slots(csg_ctx* ctx, csg_pool_sel* d_sel, const csg_pool_request* d_requests, int n_req,
                        int max_pos, int shift, const int64_t* d_best, int n_inst, int n_slots,
                        uint64_t* d_local_slots, int32_t* d_flags);
-/* d_gathered[n_ranks][inst][n_slots] -> d_table[inst][n_slots] (merged) + every target's slot. */
-CSG_API int csg_pool_sel_assign(csg_ctx* ctx, csg_pool_sel* d_sel, int n_req, int max_pos,
-                        const uint64_t* d_gathered, int n_ranks, int n_inst, int n_slots,
-                        uint64_t* d_table, int32_t* d_flags);
+/* One exchange per digit carries both the bounds and the slot lists: every rank's payload is
+ * [64 x int64 bounds (csg_pool_sel_bounds output, d_best) | n_inst x n_slots uint64 slot lists
+ * (csg_pool_sel_slots output, pruned with the LOCAL bounds)], csg_pool_slot_payload_bytes() in
+ * all.  d_gathered holds n_ranks payloads, rank_stride_bytes apart (n_ranks = 1: the local
+ * payload itself).  The kernel takes the maximum bound over the ranks, drops the prefixes
+ * below it, merges the lists into d_table[inst][n_slots] and gives every target its slot. */
+CSG_API int csg_pool_sel_assign(csg_ctx* ctx, csg_pool_sel* d_sel, const csg_pool_request* d_requests, int n_req,
+                        int max_pos, int shift, const void* d_gathered, size_t rank_stride_bytes, int n_ranks,
+                        int n_inst, int n_slots, uint64_t* d_table, int32_t* d_flags);
+CSG_API size_t csg_pool_slot_payload_bytes(int n_inst, int n_slots);
 /* d_values[n_req] (double; -inf when no entry survived on this rank), d_has[n_req]. */
 CSG_API int csg_pool_sel_finish(csg_ctx* ctx, int dtype, const csg_pool_sel* d_sel, int n_req, int max_pos,
                         double* d_values, int32_t* d_has);
-/* From the all-gathered bucket totals d_gathered[n_ranks][inst][cols_per_inst]:
- * d_base = sum over lower ranks; d_above[inst] (may be NULL) = cells held by higher ranks. */
-CSG_API int csg_pool_base(csg_ctx* ctx, const uint32_t* d_gathered, int n_ranks, int rank, int n_inst,
-                  size_t cols_per_inst, uint32_t* d_base, int64_t* d_above);
+/* From the all-gathered bucket totals (rank r's [inst][cols_per_inst] block starts at
+ * d_gathered + r * rank_stride uint32 elements): d_base = sum over lower ranks; d_above[inst]
+ * (may be NULL) = cells held by higher ranks. */
+CSG_API int csg_pool_base(csg_ctx* ctx, const uint32_t* d_gathered, size_t rank_stride, int n_ranks, int rank,
+                  int n_inst, size_t cols_per_inst, uint32_t* d_base, int64_t* d_above);
+
+/* y extrema on the device: the 99 %-coverage energy (CS/fast/extrema.py:270-278) of every prefix
+ * pool, max-merged per instrument.  d_ehist: scanned per-energy counts [inst][pos][max_E];
+ * d_order[inst][max_E]: energy columns in ascending-energy order; d_keys[inst][max_E]: those
+ * energies (float64, distinct, no NaN); d_n_keys[inst]; d_limit[inst]: positions < limit take
+ * part (the reference stops an instrument's chain at its `complete` step, :315-319);
+ * d_gathered_etot (+ r * rank_stride uint32 elements): rank r's per-energy totals [inst][max_E]
+ * (may be NULL on rank 0).  d_ycand[inst]: order-preserving int64 key of the largest candidate
+ * (decoded by csg_pool_pack_results; "none" when no position took part). */
+CSG_API int csg_pool_energy_candidates(csg_ctx* ctx, const uint32_t* d_ehist, int n_inst, int max_pos, int max_E,
+                               const int32_t* d_order, const double* d_keys, const int32_t* d_n_keys,
+                               const int32_t* d_limit, const uint32_t* d_gathered_etot, size_t rank_stride,
+                               int rank, int64_t* d_ycand);
+/* d_out[n_out >= n_req + n_inst + 5] (double) = [values | y candidates (-inf: none; d_ycand may be
+ * NULL) | the 4 selection flags | *d_peer_error (may be NULL) | zero padding]: one payload, so one
+ * last exchange + csg_pool_reduce_max() finishes the step on every rank. */
+CSG_API int csg_pool_pack_results(csg_ctx* ctx, const double* d_values, int n_req, const int64_t* d_ycand, int n_inst,
+                          const int32_t* d_flags, const void* d_peer_error, double* d_out, int n_out);
+CSG_API int csg_pool_reduce_max(csg_ctx* ctx, const double* d_gathered, int n_ranks, int n, double* d_out);
+
+/* ------------------------------------------- peer exchange (NVLink / NVSwitch stores) */
+/* The exchange step of the global extrema without library collectives:
+ * every rank owns a mailbox in its HBM; an all-gather is one kernel that stores the payload
+ * into every peer's mailbox and publishes an epoch flag (release, system scope), plus one
+ * kernel that waits for every rank's flag (acquire).  See csrc/peer.cu. */
+typedef struct csg_peer csg_peer;
+/* slot_bytes: largest payload of one rank.  ipc_handle_64 (may be NULL): receives the 64-byte
+ * cudaIpcMemHandle_t of this rank's mailbox (zeros when the platform has no IPC). */
+CSG_API int csg_peer_create(csg_ctx* ctx, int rank, int n_ranks, size_t slot_bytes, csg_peer** out, void* ipc_handle_64);
+CSG_API void* csg_peer_mailbox(csg_peer* peer);
+/* all_handles: n_ranks x 64 bytes, rank order (one process per GPU). */
+CSG_API int csg_peer_connect_ipc(csg_ctx* ctx, csg_peer* peer, const void* all_handles);
+/* mailboxes[n_ranks]: csg_peer_mailbox() of every rank (ranks living in one process). */
+CSG_API int csg_peer_connect_ptrs(csg_ctx* ctx, csg_peer* peer, void* const* mailboxes);
+/* nbytes: multiple of 16, <= slot_bytes; *d_gathered: n_ranks payloads, nbytes apart, valid until
+ * the third following exchange. */
+CSG_API int csg_peer_allgather(csg_ctx* ctx, csg_peer* peer, const void* d_src, size_t nbytes, void** d_gathered);
+/* int32 on the device: 0, or 1 + the rank whose flag did not arrive within ~2 s. */
+CSG_API void* csg_peer_error_word(csg_peer* peer);
+CSG_API int csg_peer_clear_error(csg_ctx* ctx, csg_peer* peer); /* on the ctx stream */
+CSG_API int csg_peer_destroy(csg_ctx* ctx, csg_peer* peer);
 
 #ifdef __cplusplus
 }

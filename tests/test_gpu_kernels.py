@@ -430,3 +430,135 @@ def test_collapse_config5_generic_stress_cube(ctx):
     assert not np.array_equal(bits(got_a), bits(got_b))
     fl = b.flags(f)
     assert fl.all() and b.flags(f2).all()
+
+
+def _sim_contexts(n):
+    """n contexts on device 0, each with its own stream: ranks living in one process."""
+    from configurable_spectrograms_b200 import _lib
+
+    return [_lib.Context(0) for _ in range(n)]
+
+
+def test_peer_exchange_allgather_in_process():
+    """csrc/peer.cu on one GPU: three ranks (three streams) store into each other's mailboxes;
+    more rounds than mailbox regions, changing payload sizes, one rank enqueued late."""
+    from configurable_spectrograms_b200.comm import SharedPeerGroup
+
+    R = 3
+    ctxs = _sim_contexts(R)
+    group = SharedPeerGroup(ctxs)
+    for m in group.members:
+        m.ensure(64 * 1024)
+    rng = np.random.default_rng(3)
+    sizes = [16, 4096, 64 * 1024, 48, 1024, 16 * 1024, 16, 32 * 1024, 64, 2048]
+    payloads = [[rng.integers(0, 255, n, dtype=np.uint8) for _ in range(R)] for n in sizes]
+    srcs = [[ctxs[r].to_device(payloads[k][r]) for r in range(R)] for k in range(len(sizes))]
+    # allocations order kernels of different streams behind each other: none while ranks wait
+    outs = [[ctxs[r].pinned(R * n) for r in range(R)] for n in sizes]
+    for c in ctxs:
+        c.sync()
+    for k, n in enumerate(sizes):
+        order = range(R) if k % 2 == 0 else reversed(range(R))  # nobody is always first
+        for r in order:
+            g = group.members[r].allgather(srcs[k][r].ptr, n)
+            ctxs[r]._check(ctxs[r].lib.csg_d2h(ctxs[r].handle, outs[k][r].ptr, g, R * n))
+    for c in ctxs:
+        c.sync()
+    for k, n in enumerate(sizes):
+        want = np.concatenate(payloads[k])
+        for r in range(R):
+            assert np.array_equal(outs[k][r].view(np.uint8, R * n), want), (k, r)
+    err = np.zeros(1, np.int32)
+    for r in range(R):
+        ctxs[r]._check(ctxs[r].lib.csg_d2h(ctxs[r].handle, err.ctypes.data, group.members[r].error_ptr, 4))
+        ctxs[r].sync()
+        assert err[0] == 0
+    del group, srcs, outs
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_ranks", [1, 2, 3])
+def test_device_selector_ranks_and_device_y_candidates(dtype, n_ranks):
+    """The device selection across ranks that meet through peer mailboxes (simulated in one
+    process), with the y candidates max-merged on the device: values, y candidates and chain
+    limits against numpy over the global sequence."""
+    from configurable_spectrograms_b200._lib import POOL_ITEM
+    from configurable_spectrograms_b200.comm import LocalExchange, SharedPeerGroup
+    from configurable_spectrograms_b200.engine import Batch
+    from configurable_spectrograms_b200.fast.extrema import energy_candidates
+    from configurable_spectrograms_b200.pool_select import DevicePoolSelector
+
+    rng = np.random.default_rng(21 + n_ranks)
+    n_inst, n_orbits, E = 3, 9, 24
+    energy = [np.geomspace(30000.0, 4.0, E), np.geomspace(5.0, 25000.0, E), rng.permutation(np.linspace(1.0, 4000.0, E))]
+    cubes = {}
+    for k in range(n_orbits):
+        for i in range(n_inst):
+            if (i, k) in ((1, 0), (2, 4)):
+                continue  # missing files: the chain of instrument 1 starts with the empty-pool candidate
+            T = int(rng.integers(10, 40))
+            c = (_rand_cube(rng, (T, 4, E), dtype, integer=(k % 2 == 0)) * dtype(9.0 if k == 1 else 1.0)).astype(dtype)
+            c[:, :, rng.integers(0, E)] = np.nan  # a dead energy channel
+            if k == 3:
+                c[:] = np.nan
+            cubes[(i, k)] = c
+    per = (n_orbits + n_ranks - 1) // n_ranks
+    ctxs = _sim_contexts(n_ranks)
+    exchanges = SharedPeerGroup(ctxs).members if n_ranks > 1 else [LocalExchange()]
+    stops = [n_orbits - 1, n_orbits - 3, 5]  # chains that end early (instrument "complete" quirk)
+    reqs = [{"inst": i, "p": 99.0, "mode": "running_max"} for i in range(n_inst)]
+    reqs += [{"inst": i, "p": 1, "mode": "last"} for i in range(n_inst)]
+    order = np.zeros((n_inst, E), np.int32)
+    keys = np.zeros((n_inst, E), np.float64)
+    for i in range(n_inst):
+        order[i] = np.argsort(energy[i], kind="stable")
+        keys[i] = energy[i][order[i]]
+    sels, keep = [], []
+    for r in range(n_ranks):
+        lo, hi = r * per, min(n_orbits, (r + 1) * per)
+        b = Batch(ctxs[r], dtype, 0)
+        mine = [(i, k, b.add_file(cubes[(i, k)])) for k in range(lo, hi) for i in range(n_inst) if (i, k) in cubes]
+        b.upload_cubes()
+        b.collapse()
+        pos = [0] * n_inst
+        rows, limit = [], np.zeros(n_inst, np.int32)
+        for i, k, f in mine:
+            rows.append((b.mat_off(f, 0), cubes[(i, k)].shape[0], E, i, pos[i]))
+            pos[i] += 1
+            if k <= stops[i]:
+                limit[i] += 1
+        items = np.array(rows, dtype=POOL_ITEM) if rows else np.zeros(0, POOL_ITEM)
+        sel = DevicePoolSelector(b)
+        ydev = {"order": order, "keys": keys, "n_keys": np.full(n_inst, E, np.int32), "limit": limit}
+        sels.append((sel, items, np.array(pos, np.int32), ydev))
+        keep.append(b)
+    for r in range(n_ranks):  # ranks sharing one process: every allocation happens before any launch
+        sel, items, inst_len, ydev = sels[r]
+        sel.reserve(dtype, items, n_inst, inst_len, E, reqs, exchange=exchanges[r], ydev=ydev)
+    for c in ctxs:
+        c.sync()
+    for rep in range(2):  # second pass: persistent scratch, mailbox regions wrap around
+        for r in (range(n_ranks) if rep == 0 else reversed(range(n_ranks))):
+            sel, items, inst_len, ydev = sels[r]
+            sel.enqueue(dtype, items, n_inst, inst_len, E, reqs, exchange=exchanges[r], ydev=ydev)
+        for r in range(n_ranks):
+            sel = sels[r][0]
+            vals, ycand = sel.result_values(), sel.result_y_candidates()
+            assert vals is not None
+            for q, req in enumerate(reqs):
+                i = req["inst"]
+                with np.errstate(invalid="ignore"):
+                    mats = [np.nansum(cubes[(i, k)], axis=1) for k in range(n_orbits) if (i, k) in cubes]
+                best, last = _pool_reference(mats, req["p"], dtype)
+                assert vals[q] == (best if req["mode"] == "running_max" else last), (r, q, vals[q], best, last)
+            for i in range(n_inst):
+                ks = [k for k in range(n_orbits) if (i, k) in cubes and k <= stops[i]]
+                with np.errstate(invalid="ignore"):
+                    counts = [(lambda m: (np.isfinite(m) & (m > 0)).sum(axis=0))(np.nansum(cubes[(i, k)], axis=1)) for k in ks]
+                want = max(energy_candidates([energy[i]] * len(ks), np.asarray(counts)))
+                assert ycand[i] == want, (r, i, ycand[i], want)
+    del sels, keep, exchanges
+    for c in ctxs:
+        c.close()
