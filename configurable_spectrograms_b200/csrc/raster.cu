@@ -226,16 +226,25 @@ __global__ void panel_prepare_kernel(const csg_panel* __restrict__ panels, int n
   norms[i] = nm;
 }
 
-// One block = kPixPerBlock consecutive pixels of one panel's (E', T') image.  The collapsed matrices
+// A chunk = kPixPerBlock consecutive pixels of one panel's (E', T') image.  The collapsed matrices
 // are energy-major, so consecutive pixels of an image row are consecutive cells of one matrix row:
-// reads and writes are both fully coalesced and there is no transpose.  Each cell is mapped to its
-// LUT index through the panel's threshold table: a fast float guess of the count, verified
-// against a 4-entry window of the exact thresholds (exact by construction).
-constexpr int kRasterThreads = 256;
-constexpr int kPixPerThread = 32;
+// reads and writes are both fully coalesced and there is no transpose.  A thread owns groups of four
+// consecutive pixels (one 128-bit RGBA store; one 128-bit load when the four cells are an aligned
+// run of one matrix row).  Each cell is mapped to its LUT index through the panel's threshold table:
+// a fast float guess of the count, verified against the two exact thresholds around it (exact by
+// construction).
+//
+// The per-pixel table lookups are random, and at one or two table reads plus one LUT read per
+// pixel the shared-memory pipe -- not HBM -- bounds the kernel when lanes collide on banks.  So
+// both tables are kept BANK-REPLICATED: row k of a table is 32 words, one per lane, and a lane
+// only ever reads its own column -- every lookup is a single conflict-free wavefront.  Blocks
+// are persistent (a contiguous range of chunks each), so the replicated LUT is built once per
+// block and the thresholds once per panel the block meets.
+constexpr int kRasterThreads = 512;
+constexpr int kPixPerThread = 16;
 constexpr int kPixPerBlock = kRasterThreads * kPixPerThread;
-
-constexpr int kPad = 4;  // sentinels on both sides of the threshold row in shared memory
+constexpr int kRows = kThr + 2;       // thr[-1] = -inf, thr[0..256], thr[257] = +inf
+constexpr int kLutRows = 260;
 
 __device__ __forceinline__ float fast_log2(float x) {
   float r;
@@ -249,143 +258,241 @@ struct Flag {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kRasterThreads, 4)
+constexpr size_t raster_smem_bytes() {
+  return (size_t)kLutRows * 32 * sizeof(uint32_t) + (size_t)kRows * 32 * sizeof(T);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
     rasterise_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                      const int32_t* __restrict__ pool, const csg_panel* __restrict__ panels,
-                     const csg_panel_norm* __restrict__ norms, int n_panels, int block_offset,
+                     const csg_panel_norm* __restrict__ norms, int n_panels, int chunk_offset, int n_chunks,
                      const int32_t* __restrict__ block_panel, const T* __restrict__ thresholds,
                      const uint32_t* __restrict__ lut, uint32_t* __restrict__ rgba, uint16_t* __restrict__ index) {
-  __shared__ uint32_t s_lut[260];
-  __shared__ T s_thr[kThr + 2 * kPad];  // [kPad + k] = thr[k]; -inf below, +inf above
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  T* s_thr = reinterpret_cast<T*>(s_raw);                                             // [kRows][32]
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_raw + (size_t)kRows * 32 * sizeof(T));  // [kLutRows][32]
 
-  const int tid = threadIdx.x;
-  const int blk = (int)blockIdx.x + block_offset;
-  // ---- which panel owns this block: host-built table, else a cached binary search
-  int pi;
-  if (block_panel != nullptr) {
-    pi = __ldg(block_panel + blk);
-  } else {
-    int lo = 0, hi = n_panels - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&panels[mid].first_block) <= blk)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    pi = lo;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // this block's contiguous range of chunks
+  const int per = (n_chunks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int c_begin = (int)blockIdx.x * per, c_end = min(n_chunks, c_begin + per);
+  if (c_begin >= c_end) return;
+  // LUT rows are keyed by the threshold COUNT n (what the lookup produces): 0 = under, 1..256 = colours
+  // 0..255, 257 = over, 258 = bad -- the colormap index itself is only formed for the index plane
+  for (int w = tid; w < kLutRows * 32; w += kRasterThreads) {
+    const int n = w >> 5;
+    const int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : (n <= 256 ? n - 1 : I_BAD));
+    s_lut[w] = (lut && n < 259) ? __ldg(lut + idx) : 0u;
   }
-  const csg_panel* pn = panels + pi;
-  const csg_region* rg = regions + __ldg(&pn->region);
-  const csg_panel_norm* nm = norms + pi;
-  if (__ldg(&nm->status) != CSG_NORM_OK) return;  // the host raises matplotlib's ValueError for this panel
-  const int degenerate = __ldg(&nm->degenerate);
-  const bool log_scale = __ldg(&pn->log_scale) != 0;
-  const unsigned nt = (unsigned)__ldg(&rg->nt);
-  const unsigned n_pix = (unsigned)__ldg(&rg->ne) * nt;
-  const unsigned first = (unsigned)(blk - __ldg(&pn->first_block)) * kPixPerBlock;
-  const unsigned last = first + kPixPerBlock < n_pix ? first + kPixPerBlock : n_pix;
-  const long long out_off = __ldg(&pn->out_off);
-  uint32_t* out_rgba = rgba ? rgba + out_off : nullptr;
-  uint16_t* out_idx = index ? index + out_off : nullptr;
+  const T* my_thr = s_thr + lane;        // row r (threshold k = r - 1) at my_thr[r * 32]
+  const uint32_t* my_lut = s_lut + lane;
 
-  for (int i = tid; i < 259; i += kRasterThreads) s_lut[i] = lut ? lut[i] : 0u;
-  if (degenerate != 0) {
-    // vmin == vmax: every cell maps to index 0; NaN bound: every cell is "bad"
-    __syncthreads();
-    const int idx = degenerate == 1 ? 0 : I_BAD;
-    for (unsigned i = first + tid; i < last; i += kRasterThreads) {
-      if (out_rgba) out_rgba[i] = s_lut[idx];
-      if (out_idx) out_idx[i] = (uint16_t)idx;
-    }
-    return;
-  }
-  for (int i = tid; i < kThr + 2 * kPad; i += kRasterThreads) {
-    const int k = i - kPad;
-    s_thr[i] = k < 0 ? (T)(-CUDART_INF) : (k >= kThr ? (T)CUDART_INF : thresholds[(size_t)pi * kThrPitch + k]);
-  }
-  __syncthreads();
+  int cur_panel = -1;
+  // panel state (reloaded when the block crosses into another panel)
+  bool skip = false, log_scale = false;
+  int degenerate = 0;
+  unsigned nt = 1, n_pix = 0;
+  int first_block = 0, ld = 0, t0 = 0, rows_off = -1;
+  long long out_off = 0;
+  float c1 = 0.f, c0 = 0.f;
+  T fill_lo = T(0), fill_hi = T(0);
+  const T* mat = mats;
+  const int32_t *cols = pool, *rows = pool;
+  bool in_vec = false;
 
-  const float c1 = __ldg(&nm->c1), c0 = __ldg(&nm->c0);
-  const T fill_lo = (T)__ldg(&nm->fill_lo), fill_hi = (T)__ldg(&nm->fill_hi);
-  const T* mat = mats + __ldg(&rg->mat_off);
-  const int32_t* cols = pool + __ldg(&rg->cols_off);
-  const int rows_off = __ldg(&rg->rows_off);
-  const int32_t* rows = pool + (rows_off < 0 ? 0 : rows_off);
-  const int ld = __ldg(&rg->ld), t0 = __ldg(&rg->t0);
-
-  // value -> LUT index: fast float guess of the threshold count, verified against the exact table
-  auto to_index = [&](T v, auto log_c) -> int {
-    constexpr bool LOG = decltype(log_c)::value;
-    // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
-    if (LOG) {
-      v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+  for (int chunk = c_begin; chunk < c_end; ++chunk) {
+    const int blk = chunk + chunk_offset;
+    int pi;
+    if (block_panel != nullptr) {
+      pi = __ldg(block_panel + blk);
     } else {
-      v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
-      v = (v == (T)CUDART_INF) ? fill_hi : v;
+      int lo = 0, hi = n_panels - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&panels[mid].first_block) <= blk)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      pi = lo;
     }
-    const float fv = (float)v;
-    float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
-    gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
-    int n = (int)gf;
-    // verified window: thr[n-2] <= v < thr[n+1]  =>  n* = n-1 + [thr[n-1] <= v] + [thr[n] <= v]
-    const T a = s_thr[kPad - 2 + n], b = s_thr[kPad - 1 + n], c = s_thr[kPad + n], d = s_thr[kPad + 1 + n];
-    if (a <= v && !(d <= v)) {
-      n = n - 1 + (b <= v ? 1 : 0) + (c <= v ? 1 : 0);
-    } else {  // rare: the float guess was off by more than one
-#pragma unroll 1
-      while (n > 0 && !(s_thr[kPad + n - 1] <= v)) --n;
-#pragma unroll 1
-      while (n < kThr && s_thr[kPad + n] <= v) ++n;
+    if (pi != cur_panel) {
+      cur_panel = pi;
+      const csg_panel* pn = panels + pi;
+      const csg_region* rg = regions + __ldg(&pn->region);
+      const csg_panel_norm* nm = norms + pi;
+      skip = __ldg(&nm->status) != CSG_NORM_OK;  // the host raises matplotlib's ValueError for this panel
+      degenerate = __ldg(&nm->degenerate);
+      log_scale = __ldg(&pn->log_scale) != 0;
+      nt = (unsigned)__ldg(&rg->nt);
+      n_pix = (unsigned)__ldg(&rg->ne) * nt;
+      first_block = __ldg(&pn->first_block);
+      out_off = __ldg(&pn->out_off);
+      c1 = __ldg(&nm->c1), c0 = __ldg(&nm->c0);
+      fill_lo = (T)__ldg(&nm->fill_lo), fill_hi = (T)__ldg(&nm->fill_hi);
+      mat = mats + __ldg(&rg->mat_off);
+      cols = pool + __ldg(&rg->cols_off);
+      rows_off = __ldg(&rg->rows_off);
+      rows = pool + (rows_off < 0 ? 0 : rows_off);
+      ld = __ldg(&rg->ld), t0 = __ldg(&rg->t0);
+      in_vec = sizeof(T) == 4 && rows_off < 0 && (ld & 3) == 0 && (__ldg(&rg->mat_off) & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(mats) & 15) == 0;
+      __syncthreads();  // every lane is done with the previous panel's thresholds
+      if (!skip && degenerate == 0) {
+        const T* thr = thresholds + (size_t)pi * kThrPitch;
+        for (int w = tid; w < kRows * 32; w += kRasterThreads) {
+          const int k = (w >> 5) - 1;
+          s_thr[w] = k < 0 ? (T)(-CUDART_INF) : (k >= kThr ? (T)CUDART_INF : __ldg(thr + k));
+        }
+      }
+      __syncthreads();
     }
-    int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : n - 1);
-    return is_nan(v) ? I_BAD : idx;
-  };
+    if (skip) continue;
+    const unsigned first = (unsigned)(blk - first_block) * kPixPerBlock;
+    const unsigned last = first + kPixPerBlock < n_pix ? first + kPixPerBlock : n_pix;
+    uint32_t* out_rgba = rgba ? rgba + out_off : nullptr;
+    uint16_t* out_idx = index ? index + out_off : nullptr;
+    if (degenerate != 0) {
+      // vmin == vmax: every cell maps to index 0; NaN bound: every cell is "bad"
+      const int idx = degenerate == 1 ? 0 : I_BAD;
+      const int row = degenerate == 1 ? 1 : 258;
+      for (unsigned i = first + tid; i < last; i += kRasterThreads) {
+        if (out_rgba) out_rgba[i] = my_lut[row * 32];
+        if (out_idx) out_idx[i] = (uint16_t)idx;
+      }
+      continue;
+    }
 
-  // the pixel loop, specialised on the scale and on how time steps are addressed; 32-bit index
-  // math, four independent cells in flight per thread
-  auto pixels = [&](auto log_c, auto rowlist_c) {
-    constexpr bool ROWLIST = decltype(rowlist_c)::value;
-    constexpr int U = 4;
-    unsigned i = first + tid;
-    unsigned j = i / nt, tt = i - j * nt;
-    const unsigned dq = kRasterThreads / nt, dr = kRasterThreads - dq * nt;
-    auto address = [&](unsigned jj, unsigned t) -> unsigned {
-      return (unsigned)(__ldg(cols + jj) * ld + (ROWLIST ? __ldg(rows + t) : t0 + (int)t));
+    // value -> number of thresholds <= value (258 for NaN): fast float guess, verified against the exact table
+    auto to_count = [&](T v, auto log_c) -> int {
+      constexpr bool LOG = decltype(log_c)::value;
+      // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
+      if (LOG) {
+        v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+      } else {
+        v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
+        v = (v == (T)CUDART_INF) ? fill_hi : v;
+      }
+      const float fv = (float)v;
+      float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
+      gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
+      int n = (int)gf;
+      // n thresholds are <= v  <=>  thr[n-1] <= v < thr[n]   (rows are offset by one: thr[k] = row k+1)
+      const T b = my_thr[n * 32], c = my_thr[(n + 1) * 32];
+      if (!(b <= v && !(c <= v))) {  // rare: the float guess was off
+#pragma unroll 1
+        while (n > 0 && !(my_thr[n * 32] <= v)) --n;
+#pragma unroll 1
+        while (n < kThr && my_thr[(n + 1) * 32] <= v) ++n;
+      }
+      return is_nan(v) ? 258 : n;
     };
-    for (; i + (U - 1) * kRasterThreads < last; i += U * kRasterThreads) {
-      T v[U];
+    auto count_to_index = [](int n) -> int { return n == 0 ? I_UNDER : (n == kThr ? I_OVER : (n == 258 ? I_BAD : n - 1)); };
+
+    // the pixel loop, specialised on the scale and on how time steps are addressed; 32-bit index
+    // math; a thread takes four consecutive pixels per step
+    const bool out_vec = (out_off & 3) == 0 && (!out_rgba || (reinterpret_cast<uintptr_t>(rgba) & 15) == 0) &&
+                         (!out_idx || (reinterpret_cast<uintptr_t>(index) & 7) == 0);
+    auto pixels = [&](auto log_c, auto rowlist_c) {
+      constexpr bool ROWLIST = decltype(rowlist_c)::value;
+      constexpr unsigned G = 4, STEP = G * kRasterThreads;
+      unsigned i = first + G * tid;
+      unsigned j = i / nt, tt = i - j * nt;
+      const unsigned dq = STEP / nt, dr = STEP - dq * nt;
+      auto address = [&](unsigned jj, unsigned t) -> unsigned {
+        return (unsigned)(__ldg(cols + jj) * ld + (ROWLIST ? __ldg(rows + t) : t0 + (int)t));
+      };
+      auto load4 = [&](unsigned jj, unsigned t, T* v) {  // cells of pixels i..i+3 (the caller checked i + 3 < last)
+        if (t + (G - 1) < nt) {
+          const unsigned a0 = address(jj, t);
+          if (!ROWLIST && in_vec && (a0 & 3u) == 0) {
+            if constexpr (sizeof(T) == 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(mat + a0));
+              v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+            }
+          } else if (!ROWLIST) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        v[u] = __ldg(mat + address(j, tt));
-        j += dq, tt += dr;
+            for (unsigned u = 0; u < G; ++u) v[u] = __ldg(mat + a0 + u);
+          } else {
+            const unsigned c = (unsigned)(__ldg(cols + jj) * ld);
+#pragma unroll
+            for (unsigned u = 0; u < G; ++u) v[u] = __ldg(mat + c + __ldg(rows + t + u));
+          }
+        } else {  // the group straddles two image rows
+#pragma unroll
+          for (unsigned u = 0; u < G; ++u) {
+            v[u] = __ldg(mat + address(jj, t));
+            if (++t == nt) t = 0, ++jj;
+          }
+        }
+      };
+      auto store4 = [&](unsigned at, const int* n) {
+        if (out_rgba) {
+          if (out_vec)
+            *reinterpret_cast<uint4*>(out_rgba + at) =
+                make_uint4(my_lut[n[0] * 32], my_lut[n[1] * 32], my_lut[n[2] * 32], my_lut[n[3] * 32]);
+          else {
+#pragma unroll
+            for (unsigned u = 0; u < G; ++u) out_rgba[at + u] = my_lut[n[u] * 32];
+          }
+        }
+        if (out_idx) {
+          int idx[G];
+#pragma unroll
+          for (unsigned u = 0; u < G; ++u) idx[u] = count_to_index(n[u]);
+          if (out_vec)
+            *reinterpret_cast<uint2*>(out_idx + at) =
+                make_uint2((unsigned)idx[0] | ((unsigned)idx[1] << 16), (unsigned)idx[2] | ((unsigned)idx[3] << 16));
+          else {
+#pragma unroll
+            for (unsigned u = 0; u < G; ++u) out_idx[at + u] = (uint16_t)idx[u];
+          }
+        }
+      };
+      auto advance = [&]() {
+        i += STEP, j += dq, tt += dr;
         if (tt >= nt) tt -= nt, ++j;
-      }
+      };
+      // full groups, software-pipelined by one: the next group's cells are requested before the
+      // current group is classified
+      T cur[G];
+      bool have = i + (G - 1) < last;
+      if (have) load4(j, tt, cur);
+      while (have) {
+        const unsigned at = i;
+        advance();
+        T nxt[G];
+        have = i + (G - 1) < last;
+        if (have) load4(j, tt, nxt);
+        int x[G];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = to_index(v[u], log_c);
-        if (out_rgba) out_rgba[i + u * kRasterThreads] = s_lut[idx];
-        if (out_idx) out_idx[i + u * kRasterThreads] = (uint16_t)idx;
+        for (unsigned u = 0; u < G; ++u) x[u] = to_count(cur[u], log_c);
+        store4(at, x);
+#pragma unroll
+        for (unsigned u = 0; u < G; ++u) cur[u] = nxt[u];
       }
+      if (i < last) {  // the last, partial group of the panel (i was advanced past every full group)
+        unsigned jj = j, t = tt;
+        for (unsigned p = i; p < last; ++p) {
+          const int n = to_count(__ldg(mat + address(jj, t)), log_c);
+          if (out_rgba) out_rgba[p] = my_lut[n * 32];
+          if (out_idx) out_idx[p] = (uint16_t)count_to_index(n);
+          if (++t == nt) t = 0, ++jj;
+        }
+      }
+    };
+    if (log_scale) {
+      if (rows_off < 0)
+        pixels(Flag<true>{}, Flag<false>{});
+      else
+        pixels(Flag<true>{}, Flag<true>{});
+    } else {
+      if (rows_off < 0)
+        pixels(Flag<false>{}, Flag<false>{});
+      else
+        pixels(Flag<false>{}, Flag<true>{});
     }
-    for (; i < last; i += kRasterThreads) {
-      const int idx = to_index(__ldg(mat + address(j, tt)), log_c);
-      if (out_rgba) out_rgba[i] = s_lut[idx];
-      if (out_idx) out_idx[i] = (uint16_t)idx;
-      j += dq, tt += dr;
-      if (tt >= nt) tt -= nt, ++j;
-    }
-  };
-  if (log_scale) {
-    if (rows_off < 0)
-      pixels(Flag<true>{}, Flag<false>{});
-    else
-      pixels(Flag<true>{}, Flag<true>{});
-  } else {
-    if (rows_off < 0)
-      pixels(Flag<false>{}, Flag<false>{});
-    else
-      pixels(Flag<false>{}, Flag<true>{});
   }
 }
 
@@ -434,15 +541,27 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
   if (!d_mats || !d_regions || !d_index_pool || !d_panels || !d_norms || !d_thresholds)
     return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   if (d_rgba && !d_lut) return csg_fail(ctx, CSG_ERR_ARG, "d_rgba requested without d_lut");
+  // persistent blocks: as many as fit the SMs at once (shared memory allows 2-3 per SM), each a contiguous chunk range
+  static bool configured_dev[64] = {false};
+  bool& configured = configured_dev[ctx->device & 63];
+  if (!configured) {
+    CSG_CUDA(ctx, cudaFuncSetAttribute(rasterise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)raster_smem_bytes<float>()));
+    CSG_CUDA(ctx, cudaFuncSetAttribute(rasterise_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)raster_smem_bytes<double>()));
+    configured = true;
+  }
+  const int per_sm = dtype == CSG_F32 ? 3 : 2;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > total_blocks) grid = total_blocks;
   if (dtype == CSG_F32)
-    rasterise_kernel<float><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_panels,
-                                                                   d_norms, n_panels, block_offset, d_block_panel, (const float*)d_thresholds,
-                                                                   (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
+    rasterise_kernel<float><<<grid, kRasterThreads, raster_smem_bytes<float>(), ctx->stream>>>(
+        (const float*)d_mats, d_regions, d_index_pool, d_panels, d_norms, n_panels, block_offset, total_blocks, d_block_panel,
+        (const float*)d_thresholds, (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else if (dtype == CSG_F64)
-    rasterise_kernel<double><<<total_blocks, kRasterThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
-                                                                    d_panels, d_norms, n_panels, block_offset, d_block_panel,
-                                                                    (const double*)d_thresholds, (const uint32_t*)d_lut,
-                                                                    (uint32_t*)d_rgba, d_index);
+    rasterise_kernel<double><<<grid, kRasterThreads, raster_smem_bytes<double>(), ctx->stream>>>(
+        (const double*)d_mats, d_regions, d_index_pool, d_panels, d_norms, n_panels, block_offset, total_blocks, d_block_panel,
+        (const double*)d_thresholds, (const uint32_t*)d_lut, (uint32_t*)d_rgba, d_index);
   else
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
   CSG_LAUNCH_CHECK(ctx, "rasterise_kernel");

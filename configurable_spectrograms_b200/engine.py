@@ -385,7 +385,7 @@ class Batch:
              stat_region, 0, z_min.slot if isinstance(z_min, ZSlot) else -1, z_max.slot if isinstance(z_max, ZSlot) else -1)
         )
         self._raster_blocks += self.ctx.lib.csg_raster_blocks(ne, nt)
-        self._pixels += ne * nt
+        self._pixels += (ne * nt + 3) & ~3  # every panel starts 16-byte aligned: 128-bit RGBA stores
         return len(self._panels) - 1
 
     def panel_shape(self, panel: int) -> tuple[int, int]:
