@@ -212,6 +212,11 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ unsigned s_u[32];
   __shared__ T s_t[32];
   __shared__ U s_pivot[2][2];
+  __shared__ unsigned s_hist8[kThreads];  // 256 bins of the candidate-list radix select
+  __shared__ unsigned long long s_sel_scratch[32];
+  __shared__ int s_sel_digit;
+  __shared__ long long s_sel_rank;
+  __shared__ unsigned s_sel_eq;
 
   const csg_region rg = regions[blockIdx.x];
   if (threadIdx.x == 0) todo[blockIdx.x] = 0;
@@ -287,7 +292,38 @@ __global__ void __launch_bounds__(kThreads)
       if (pos < kCand) s_cand[b][pos] = key;
     }
   };
+  // ge1 counts the cells at or above bracket 1's lower pivot (few), not the ones below it (nearly
+  // all): a cell strictly between the two brackets touches no bracket counter at all
+  unsigned ge1 = 0, n_fast = 0;
+  auto bracket0 = [&](U k, bool valid) {
+    lt0 += (valid && k < plo0) ? 1u : 0u;
+    eqlo0 += (valid && k == plo0) ? 1u : 0u;
+    eqhi0 += (valid && k == phi0 && phi0 != plo0) ? 1u : 0u;
+    append(0, k, valid && k > plo0 && k < phi0);
+  };
+  auto bracket1 = [&](U k, bool valid) {
+    ge1 += (valid && k >= plo1) ? 1u : 0u;
+    eqlo1 += (valid && k == plo1) ? 1u : 0u;
+    eqhi1 += (valid && k == phi1 && phi1 != plo1) ? 1u : 0u;
+    append(1, k, valid && k > plo1 && k < phi1);
+  };
   for_each_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v, bool in) {
+    if (__all_sync(0xffffffffu, in && is_finite(v))) {
+      // the common warp: 32 real, finite cells (the collapsed sums hold no NaN: nansum replaced them)
+      ++n_fast;
+      const bool pos = v > T(0);
+      n_pos += pos ? 1u : 0u;
+      fin_min = v < fin_min ? v : fin_min;
+      fin_max = v > fin_max ? v : fin_max;
+      const T h = pos ? v : kInf;
+      min_pos = h < min_pos ? h : min_pos;
+      if (pct) {
+        const U k = Key<T>::key(v);
+        if (__any_sync(0xffffffffu, k <= phi0)) bracket0(k, true);
+        if (!share && __any_sync(0xffffffffu, k >= plo1)) bracket1(k, true);
+      }
+      return;
+    }
     const bool valid = in && !is_nan(v);
     const bool fin = valid && is_finite(v);
     const bool pos = v > T(0);
@@ -304,18 +340,11 @@ __global__ void __launch_bounds__(kThreads)
     min_pos = h < min_pos ? h : min_pos;
     if (pct) {
       const U k = Key<T>::key(v);
-      lt0 += (valid && k < plo0) ? 1u : 0u;
-      eqlo0 += (valid && k == plo0) ? 1u : 0u;
-      eqhi0 += (valid && k == phi0 && phi0 != plo0) ? 1u : 0u;
-      append(0, k, valid && k > plo0 && k < phi0);
-      if (!share) {
-        lt1 += (valid && k < plo1) ? 1u : 0u;
-        eqlo1 += (valid && k == plo1) ? 1u : 0u;
-        eqhi1 += (valid && k == phi1 && phi1 != plo1) ? 1u : 0u;
-        append(1, k, valid && k > plo1 && k < phi1);
-      }
+      bracket0(k, valid);
+      if (!share) bracket1(k, valid);
     }
   });
+  n_valid += n_fast;
 
   auto addu = [](unsigned a, unsigned b) { return a + b; };
   auto mint = [](T a, T b) { return a < b ? a : b; };
@@ -344,49 +373,108 @@ __global__ void __launch_bounds__(kThreads)
   eqlo0 = block_reduce(eqlo0, addu, 0u, s_u);
   eqhi0 = block_reduce(eqhi0, addu, 0u, s_u);
   if (!share) {
-    lt1 = block_reduce(lt1, addu, 0u, s_u);
+    ge1 = block_reduce(ge1, addu, 0u, s_u);
+    lt1 = n_valid - ge1;
     eqlo1 = block_reduce(eqlo1, addu, 0u, s_u);
     eqhi1 = block_reduce(eqhi1, addu, 0u, s_u);
   }
   __syncthreads();
   const int n0 = s_ncand[0], n1 = share ? n0 : s_ncand[1];
   bool fail = n0 > kCand || n1 > kCand;
-  if (!fail) {
-    // sort the candidate lists (padded to a power of two with KEY_MAX, which is no value's key)
-    for (int b = 0; b < (share ? 1 : 2); ++b) {
-      const int n = b == 0 ? n0 : n1;
-      int np2 = 1;
-      while (np2 < n) np2 <<= 1;
-      for (int i = n + tid; i < np2; i += kThreads) s_cand[b][i] = KEY_MAX;
-      block_sort(s_cand[b], np2);
+  // every thread holds the same reduced counters: the rank arithmetic below is block-uniform
+  long long rank[kTargets];
+  T gamma[2];
+  percentile_ranks<T>((long long)n_valid, rg.p_lo, rank[0], rank[1], gamma[0]);
+  percentile_ranks<T>((long long)n_valid, rg.p_hi, rank[2], rank[3], gamma[1]);
+  T val[kTargets];
+  // the candidate lists are NOT sorted: the (at most four, pairwise adjacent) ranks that fall inside
+  // a list are answered by an 8-bit MSD radix select over the list in shared memory; a rank inside
+  // the run of equal keys found last re-uses it, the rank just after it is that key's successor
+  int prev_b = -1;
+  long long prev_first = 0, prev_last = -1;  // in-list rank range of prev_key
+  U prev_key = 0;
+  for (int j = 0; j < kTargets && !fail; ++j) {
+    const int b = share ? 0 : (j >> 1);
+    const U plo = b == 0 ? plo0 : plo1, phi = b == 0 ? phi0 : phi1;
+    const long long below = b == 0 ? lt0 : lt1, at_lo = b == 0 ? eqlo0 : eqlo1, at_hi = b == 0 ? eqhi0 : eqhi1;
+    const long long inside = b == 0 ? n0 : n1;
+    long long r = rank[j];
+    U key = 0;
+    if (r < below) {
+      fail = true;
+    } else if ((r -= below) < at_lo) {
+      key = plo;
+    } else if ((r -= at_lo) < inside) {
+      const U* list = s_cand[b];
+      const int n = (int)inside;
+      if (b == prev_b && r >= prev_first && r <= prev_last) {
+        key = prev_key;
+      } else if (b == prev_b && r == prev_last + 1) {
+        // successor: the smallest key above prev_key (exists: rank r is inside the list)
+        U m = KEY_MAX;
+        for (int i = tid; i < n; i += kThreads) {
+          const U k = list[i];
+          if (k > prev_key && k < m) m = k;
+        }
+        auto minu = [](U a, U c) { return a < c ? a : c; };
+        __syncthreads();
+        m = block_reduce(m, minu, KEY_MAX, reinterpret_cast<U*>(s_sel_scratch));
+        key = m;
+        prev_key = m, prev_first = r, prev_last = r;  // its run length is unknown: claim one rank only
+      } else {
+        U prefix = 0, mask = 0;
+        long long want = r;
+        unsigned eq = 0;
+        for (int shift = Key<T>::BITS - 8; shift >= 0; shift -= 8) {
+          __syncthreads();
+          s_hist8[tid] = 0;  // kThreads == 256 bins
+          __syncthreads();
+          for (int i = tid; i < n; i += kThreads) {
+            const U k = list[i];
+            if ((k & mask) == prefix) atomicAdd(&s_hist8[(unsigned)(k >> shift) & 255u], 1u);
+          }
+          __syncthreads();
+          if (tid < 32) {  // warp 0: lane l owns bins 8l..8l+7
+            unsigned c[8], mine = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c[q] = s_hist8[8 * tid + q], mine += c[q];
+            unsigned inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+              if (tid >= o) inc += t;
+            }
+            long long run = (long long)(inc - mine);
+            if (want >= run && want < run + (long long)mine) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (want >= run && want < run + (long long)c[q]) {
+                  s_sel_digit = 8 * tid + q;
+                  s_sel_rank = want - run;
+                  s_sel_eq = c[q];
+                }
+                run += c[q];
+              }
+            }
+          }
+          __syncthreads();
+          prefix |= (U)s_sel_digit << shift;
+          mask |= (U)255 << shift;
+          want = s_sel_rank;
+          eq = s_sel_eq;
+        }
+        key = prefix;
+        prev_key = key, prev_first = r - want, prev_last = r - want + (long long)eq - 1;
+      }
+      prev_b = b;
+    } else if ((r -= inside) < at_hi) {
+      key = phi;
+    } else {
+      fail = true;
     }
+    val[j] = Key<T>::val(key);
   }
   if (tid == 0) {
-    long long rank[kTargets];
-    T gamma[2];
-    percentile_ranks<T>((long long)n_valid, rg.p_lo, rank[0], rank[1], gamma[0]);
-    percentile_ranks<T>((long long)n_valid, rg.p_hi, rank[2], rank[3], gamma[1]);
-    T val[kTargets];
-    for (int j = 0; j < kTargets && !fail; ++j) {
-      const int b = share ? 0 : (j >> 1);
-      const U plo = b == 0 ? plo0 : plo1, phi = b == 0 ? phi0 : phi1;
-      const long long below = b == 0 ? lt0 : lt1, at_lo = b == 0 ? eqlo0 : eqlo1, at_hi = b == 0 ? eqhi0 : eqhi1;
-      const long long inside = b == 0 ? n0 : n1;
-      long long r = rank[j];
-      U key = 0;
-      if (r < below) {
-        fail = true;
-      } else if ((r -= below) < at_lo) {
-        key = plo;
-      } else if ((r -= at_lo) < inside) {
-        key = s_cand[b][r];
-      } else if ((r -= inside) < at_hi) {
-        key = phi;
-      } else {
-        fail = true;
-      }
-      val[j] = Key<T>::val(key);
-    }
     if (!fail) {
       st.p_lo = (double)numpy_lerp<T>(val[0], val[1], gamma[0]);
       st.p_hi = (double)numpy_lerp<T>(val[2], val[3], gamma[1]);
