@@ -197,7 +197,7 @@ __device__ __forceinline__ void for_each_cell(const T* __restrict__ mats, const 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
     region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                         const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out,
                         uint8_t* __restrict__ todo) {
