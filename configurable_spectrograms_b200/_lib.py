@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -115,6 +115,16 @@ FLAG_WINDOW = np.dtype(
     [("flags_off", "<i8"), ("t0", "<i4"), ("nt", "<i4"), ("rows_off", "<i4"), ("bit", "<i4")], align=True
 )
 assert FLAG_WINDOW.itemsize == 24
+PNG_TILE = np.dtype(
+    [("rgba_off", "<i8"), ("ne", "<i4"), ("nt", "<i4"), ("x", "<i4"), ("y", "<i4"), ("rep", "<i4"),
+     ("vline_first", "<i4"), ("vline_count", "<i4"), ("pad", "<i4")], align=True
+)
+PNG_VLINE = np.dtype([("col", "<i4"), ("half", "<i4"), ("rgba", "<u4"), ("pad", "<i4")], align=True)
+PNG_CANVAS = np.dtype(
+    [("W", "<i4"), ("H", "<i4"), ("tile_first", "<i4"), ("tile_count", "<i4"), ("background", "<u4"),
+     ("seg_first", "<i4"), ("segs_per_row", "<i4"), ("pad", "<i4")], align=True
+)
+assert PNG_TILE.itemsize == 40 and PNG_VLINE.itemsize == 16 and PNG_CANVAS.itemsize == 32
 POOL_REQUEST = np.dtype([("inst", "<i4"), ("mode", "<i4"), ("p", "<f8")], align=True)
 POOL_SEL = np.dtype(
     [("inst", "<i4"), ("pos", "<i4"), ("req", "<i4"), ("active", "<i4"), ("slot", "<i4", (2,)), ("rank", "<i8", (2,)),
@@ -174,6 +184,10 @@ SIGNATURES = {
     "csg_pool_energy_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "csg_pool_pack_results": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]),
     "csg_pool_reduce_max": (_i, [_vp, _vp, _i, _i, _vp]),
+    "csg_png_slot_bytes": (C.c_int32, []),
+    "csg_png_segments": (C.c_int32, [C.c_int32, C.c_int32]),
+    "csg_png_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "csg_png_compact": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "csg_peer_create": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
     "csg_peer_mailbox": (_vp, [_vp]),
     "csg_peer_connect_ipc": (_i, [_vp, _vp, _vp]),

@@ -1,0 +1,318 @@
+// K4 -- figure mosaics composed and DEFLATE-encoded on the device (the PNG hand-off of the path).
+//
+// The reference's product is one PNG per figure (CS/fast/process_orbit.py:98-117 ->
+// fig.savefig, CS/generic_batch.py:108-113); there nearly all wall time goes into Agg and zlib.
+// Here the colour-mapped panels (K3) already sit in HBM, so a figure never exists as raw pixels
+// anywhere: one kernel evaluates the mosaic (panels flipped to origin="lower", energy rows
+// repeated to the row height, cusp lines burnt in, background in the gaps -- the arithmetic of
+// figure.SpectrogramFigure.compose) for the scanline it encodes and for the one above it, applies
+// PNG filter 2 ("Up"), and writes finished DEFLATE blocks:
+//
+//   segment   = up to 1024 pixels of one scanline = one warp = one fixed-Huffman block that ends
+//               with an empty stored block (the zlib "sync flush": byte aligned, so segments
+//               concatenate bytewise into a valid stream in any quantity)
+//   tokens    = per pixel: identical to the previous pixel of the filtered line -> it extends a
+//               (distance 4) match, else four literals.  After the Up filter repeated rows,
+//               gaps and flat areas are runs of zero pixels, i.e. long matches.
+//   lanes     = 32 pixels each, encoded into private bit buffers; a warp prefix sum over the bit
+//               counts places them in the segment's stream (shared-memory atomicOr)
+//   adler32   = per segment (sum, weighted sum) of the filtered bytes, combined in order on the host
+//
+// The host adds the 2-byte zlib header, the final empty block, the Adler-32 and the PNG chunk
+// framing (png.py).  A decoder sees an ordinary 8-bit RGBA, non-interlaced PNG.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSegPixels = 1024;
+constexpr int kPieces = 32;          // lanes
+constexpr int kPiecePixels = 32;     // pixels per lane
+constexpr int kPixStride = 33;       // padded piece stride (words): conflict-free column reads
+constexpr int kTokWords = 37;        // per-lane token buffer: 32 pixels x 36 bits + header / trailer bits
+constexpr int kMergedWords = kPieces * kTokWords + 4;
+constexpr int kWarpsPerBlock = 4;
+
+struct HuffTables {
+  unsigned short lit_code[256];  // bit-reversed fixed-Huffman code of a literal byte
+  unsigned char lit_len[256];    // 8 or 9
+  unsigned int match_code[65];   // match of 4*n bytes at distance 4: length code + extra bits + distance code
+  unsigned char match_len[65];
+};
+__constant__ HuffTables c_huff;
+
+__device__ __forceinline__ unsigned sub4(unsigned a, unsigned b) { return __vsub4(a, b); }
+
+// One pixel of a figure's mosaic: the tiles whose rows contain y are listed in `mask`.
+__device__ __forceinline__ unsigned mosaic_pixel(const uint32_t* __restrict__ rgba, const csg_png_tile* __restrict__ tiles,
+                                                 const csg_png_vline* __restrict__ vlines, unsigned mask, int x, int y,
+                                                 unsigned background) {
+  while (mask) {
+    const int t = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const csg_png_tile& tl = tiles[t];
+    const int col = x - tl.x;
+    if (col < 0 || col >= tl.nt) continue;
+    const int r = (y - tl.y) / tl.rep;       // image row from the top
+    const int src = tl.ne - 1 - r;           // rasters are stored lowest energy first (origin="lower")
+    unsigned px = __ldg(rgba + tl.rgba_off + (long long)src * tl.nt + col);
+    for (int v = 0; v < tl.vline_count; ++v) {  // later lines overwrite earlier ones
+      const csg_png_vline ln = vlines[tl.vline_first + v];
+      if (col >= ln.col - ln.half && col <= ln.col + ln.half) px = ln.rgba;
+    }
+    return px;
+  }
+  return background;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    png_encode_kernel(const uint32_t* __restrict__ rgba, const csg_png_canvas* __restrict__ canvases, int n_canvases,
+                      const csg_png_tile* __restrict__ tiles, const csg_png_vline* __restrict__ vlines, int n_segments,
+                      unsigned char* __restrict__ slots, int slot_bytes, int32_t* __restrict__ sizes,
+                      uint32_t* __restrict__ adler) {
+  __shared__ unsigned s_pix[kWarpsPerBlock][kMergedWords];  // filtered pixels (padded pieces), then the merged stream
+  __shared__ unsigned s_tok[kWarpsPerBlock][kPieces * kTokWords];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kWarpsPerBlock + warp;
+  if (seg >= n_segments) return;
+  // ---- which canvas / scanline / chunk
+  int lo = 0, hi = n_canvases - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&canvases[mid].seg_first) <= seg)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const csg_png_canvas cv = canvases[lo];
+  const int local = seg - cv.seg_first;
+  const int row = local / cv.segs_per_row, chunk = local - row * cv.segs_per_row;
+  const int x0 = chunk * kSegPixels;
+  const int npx = min(kSegPixels, cv.W - x0);
+  const bool has_filter = chunk == 0;
+  const int n_raw = (has_filter ? 1 : 0) + 4 * npx;  // filtered bytes this segment feeds to DEFLATE
+  const csg_png_tile* tl = tiles + cv.tile_first;
+  // tiles crossing this scanline / the one above (at most 32 tiles per figure)
+  bool in_cur = false, in_up = false;
+  if (lane < cv.tile_count) {
+    const csg_png_tile t = tl[lane];
+    const int h = t.ne * t.rep;
+    in_cur = row >= t.y && row < t.y + h;
+    in_up = row - 1 >= t.y && row - 1 < t.y + h;
+  }
+  const unsigned mask_cur = __ballot_sync(0xffffffffu, in_cur), mask_up = __ballot_sync(0xffffffffu, in_up);
+
+  // ---- phase 1: compose + Up filter (coalesced), Adler partial sums
+  unsigned* pix = s_pix[warp];
+  unsigned long long sa = 0, sb = 0;
+  for (int p = lane; p < npx; p += 32) {
+    const unsigned cur = mosaic_pixel(rgba, tl, vlines, mask_cur, x0 + p, row, cv.background);
+    const unsigned up = row > 0 ? mosaic_pixel(rgba, tl, vlines, mask_up, x0 + p, row - 1, cv.background) : 0u;
+    const unsigned f = sub4(cur, up);
+    pix[(p >> 5) * kPixStride + (p & 31)] = f;
+    const unsigned b0 = f & 255u, b1 = (f >> 8) & 255u, b2 = (f >> 16) & 255u, b3 = f >> 24;
+    const unsigned t0 = (has_filter ? 1u : 0u) + 4u * (unsigned)p;  // position of b0 inside the segment
+    sa += b0 + b1 + b2 + b3;
+    sb += (unsigned long long)(n_raw - t0) * b0 + (unsigned long long)(n_raw - t0 - 1) * b1 +
+          (unsigned long long)(n_raw - t0 - 2) * b2 + (unsigned long long)(n_raw - t0 - 3) * b3;
+  }
+  if (lane == 0 && has_filter) sa += 2u, sb += 2ull * (unsigned long long)n_raw;  // the filter-type byte (2 = Up)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  __syncwarp();
+
+  // ---- phase 2: every lane turns its 32 pixels into tokens in a private bit buffer
+  unsigned* tok = s_tok[warp] + lane * kTokWords;
+  unsigned long long acc = 0;
+  int nacc = 0, nwords = 0;
+  auto put = [&](unsigned long long bits, int n) {  // n <= 32
+    acc |= bits << nacc;
+    nacc += n;
+    if (nacc >= 32) {
+      tok[nwords++] = (unsigned)acc;
+      acc >>= 32;
+      nacc -= 32;
+    }
+  };
+  if (lane == 0) {
+    put(2u, 3);  // BFINAL = 0, BTYPE = 01 (fixed Huffman)
+    if (has_filter) put(c_huff.lit_code[2], c_huff.lit_len[2]);
+  }
+  const int p_begin = lane * kPiecePixels, p_end = min(npx, p_begin + kPiecePixels);
+  if (p_begin < npx) {
+    // a run may start on the last pixel of the previous lane's piece (distance 4 reaches back into it)
+    unsigned prev = p_begin > 0 ? pix[((p_begin - 1) >> 5) * kPixStride + ((p_begin - 1) & 31)] : 0u;
+    bool have_prev = p_begin > 0;
+    int run = 0;
+    const unsigned* mine = pix + lane * kPixStride;
+    for (int p = p_begin; p < p_end; ++p) {
+      const unsigned x = mine[p - p_begin];
+      if (have_prev && x == prev) {
+        ++run;
+        continue;
+      }
+      if (run) {
+        put(c_huff.match_code[run], c_huff.match_len[run]);
+        run = 0;
+      }
+      const unsigned b0 = x & 255u, b1 = (x >> 8) & 255u, b2 = (x >> 16) & 255u, b3 = x >> 24;
+      // two puts of <= 18 bits: the 64-bit accumulator holds < 32 pending bits
+      put(c_huff.lit_code[b0] | ((unsigned)c_huff.lit_code[b1] << c_huff.lit_len[b0]), c_huff.lit_len[b0] + c_huff.lit_len[b1]);
+      put(c_huff.lit_code[b2] | ((unsigned)c_huff.lit_code[b3] << c_huff.lit_len[b2]), c_huff.lit_len[b2] + c_huff.lit_len[b3]);
+      prev = x, have_prev = true;
+    }
+    if (run) put(c_huff.match_code[run], c_huff.match_len[run]);  // run <= 32 pixels = 128 bytes
+  }
+  const bool last_lane = p_begin < npx && p_end == npx;
+  if (last_lane) put(0u, 7 + 3);  // end-of-block (7 zero bits) + header of the empty stored block (000)
+  if (nacc) tok[nwords] = (unsigned)acc;
+  const int my_bits = nwords * 32 + nacc;
+
+  // ---- phase 3: place the lanes' bit strings one after the other
+  int incl = my_bits;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total_bits = __shfl_sync(0xffffffffu, incl, 31);
+  const int off = incl - my_bits;
+  __syncwarp();  // every lane is done reading pixels: the buffer becomes the merged stream
+  unsigned* out = s_pix[warp];
+  const int total_bytes = (total_bits + 7) / 8 + 4;  // pad to a byte, then LEN = 0000, NLEN = FFFF
+  const int total_words = (total_bytes + 3) / 4;
+  for (int w = lane; w < total_words; w += 32) out[w] = 0u;
+  __syncwarp();
+  const int my_words = (my_bits + 31) / 32;
+  const int w0 = off >> 5, sh = off & 31;
+  for (int k = 0; k < my_words; ++k) {
+    const unsigned v = tok[k];
+    atomicOr(&out[w0 + k], v << sh);
+    if (sh) atomicOr(&out[w0 + k + 1], v >> (32 - sh));
+  }
+  __syncwarp();
+  if (lane == 0) {  // NLEN = 0xFFFF after the (zero) LEN
+    const int at = (total_bits + 7) / 8 + 2;
+    atomicOr(&out[at >> 2], 0xffu << (8 * (at & 3)));
+    atomicOr(&out[(at + 1) >> 2], 0xffu << (8 * ((at + 1) & 3)));
+  }
+  __syncwarp();
+  unsigned* dst = reinterpret_cast<unsigned*>(slots + (size_t)seg * slot_bytes);
+  for (int w = lane; w < total_words; w += 32) dst[w] = out[w];
+  if (lane == 0) {
+    sizes[seg] = total_bytes;
+    adler[2 * seg] = (unsigned)(sa % 65521ull);
+    adler[2 * seg + 1] = (unsigned)(sb % 65521ull);
+  }
+}
+
+// warp per segment: slot -> its place in the packed stream
+__global__ void __launch_bounds__(256)
+    png_compact_kernel(const unsigned char* __restrict__ slots, int slot_bytes, const int32_t* __restrict__ sizes,
+                       const long long* __restrict__ offsets, int n_segments, unsigned char* __restrict__ packed) {
+  const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (seg >= n_segments) return;
+  const unsigned char* src = slots + (size_t)seg * slot_bytes;
+  unsigned char* dst = packed + offsets[seg];
+  const int n = sizes[seg];
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+unsigned reverse_bits(unsigned v, int n) {
+  unsigned r = 0;
+  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+  return r;
+}
+
+void build_tables(HuffTables* t) {
+  for (int v = 0; v < 256; ++v) {
+    if (v < 144) {
+      t->lit_code[v] = (unsigned short)reverse_bits(0x30u + v, 8);
+      t->lit_len[v] = 8;
+    } else {
+      t->lit_code[v] = (unsigned short)reverse_bits(0x190u + (v - 144), 9);
+      t->lit_len[v] = 9;
+    }
+  }
+  // RFC 1951 3.2.5: length codes 257..285 (base length, extra bits)
+  static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  t->match_code[0] = 0, t->match_len[0] = 0;
+  for (int n = 1; n <= 64; ++n) {
+    const int len = 4 * n;
+    int c = 28;
+    while (c > 0 && base[c] > len) --c;
+    if (c == 28 && len != 258) c = 27;
+    const int sym = 257 + c;
+    unsigned bits;
+    int nb;
+    if (sym < 280) {
+      bits = reverse_bits((unsigned)(sym - 256), 7);
+      nb = 7;
+    } else {
+      bits = reverse_bits(0xC0u + (unsigned)(sym - 280), 8);
+      nb = 8;
+    }
+    bits |= (unsigned)(len - base[c]) << nb;  // extra bits: plain binary, LSB first
+    nb += extra[c];
+    bits |= reverse_bits(3u, 5) << nb;  // distance 4 = distance code 3 (no extra bits), 5-bit fixed code
+    nb += 5;
+    t->match_code[n] = bits;
+    t->match_len[n] = (unsigned char)nb;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t csg_png_slot_bytes(void) {
+  // 3 header bits + filter literal + 1024 pixels x 36 bits + EOB + stored header, padded, + LEN/NLEN, word rounded
+  return (int32_t)(((3 + 9 + kSegPixels * 36 + 10 + 7) / 8 + 4 + 15) / 16 * 16);
+}
+
+int32_t csg_png_segments(int32_t W, int32_t H) {
+  if (W <= 0 || H <= 0) return 0;
+  return (int32_t)(((long long)(W + kSegPixels - 1) / kSegPixels) * H);
+}
+
+int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
+                   const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, uint8_t* d_slots,
+                   int32_t* d_sizes, uint32_t* d_adler) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
+  if (!d_rgba || !d_canvases || !d_tiles || !d_slots || !d_sizes || !d_adler) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  static bool uploaded[64] = {false};
+  if (!uploaded[ctx->device & 63]) {
+    HuffTables h;
+    memset(&h, 0, sizeof(h));
+    build_tables(&h);
+    CSG_CUDA(ctx, cudaMemcpyToSymbol(c_huff, &h, sizeof(h)));
+    uploaded[ctx->device & 63] = true;
+  }
+  const int blocks = (n_segments + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  png_encode_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_canvases, n_canvases, d_tiles,
+                                                                     d_vlines, n_segments, d_slots, csg_png_slot_bytes(),
+                                                                     d_sizes, d_adler);
+  CSG_LAUNCH_CHECK(ctx, "png_encode_kernel");
+  return CSG_OK;
+}
+
+int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets, int n_segments,
+                    uint8_t* d_packed) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_segments <= 0) return CSG_OK;
+  if (!d_slots || !d_sizes || !d_offsets || !d_packed) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  const long long threads = (long long)n_segments * 32;
+  png_compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_slots, csg_png_slot_bytes(), d_sizes,
+                                                                                 (const long long*)d_offsets, n_segments,
+                                                                                 d_packed);
+  CSG_LAUNCH_CHECK(ctx, "png_compact_kernel");
+  return CSG_OK;
+}
+
+}  // extern "C"

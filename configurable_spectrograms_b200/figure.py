@@ -53,6 +53,25 @@ class _AxisSide:
         self.major_formatter = formatter
 
 
+class DeviceRaster:
+    """A panel that stays in HBM: where its RGBA raster lives in a batch's ``d_rgba`` buffer
+    (pixel offset, energies, time steps).  Stands in for the host array in ``imshow``; figures made
+    of such panels are composed and PNG-encoded on the device (``png.encode_figures_device``)."""
+
+    __slots__ = ("offset", "ne", "nt")
+
+    def __init__(self, offset: int, ne: int, nt: int):
+        self.offset, self.ne, self.nt = int(offset), int(ne), int(nt)
+
+    @property
+    def shape(self):
+        return (self.ne, self.nt, 4)
+
+    @property
+    def size(self):
+        return self.ne * self.nt * 4
+
+
 class RasterImage:
     """What ``imshow`` returned: one colour-mapped panel."""
 
@@ -87,7 +106,7 @@ class PanelAxes:
     def imshow(self, rgba, aspect="auto", origin="lower", extent=None, cmap=None, norm=None, vmin=None, vmax=None,
                index=None):
         """Store an already colour-mapped (E', T', 4) uint8 raster (row 0 = lowest energy)."""
-        img = RasterImage(np.asarray(rgba), index, extent, cmap, vmin, vmax, norm)
+        img = RasterImage(rgba if isinstance(rgba, DeviceRaster) else np.asarray(rgba), index, extent, cmap, vmin, vmax, norm)
         self.images.append(img)
         return img
 
@@ -139,22 +158,35 @@ class PanelAxes:
         return "xaxis"  # x in data units, y in axes fraction
 
     # -- composition
-    def render(self) -> np.ndarray | None:
-        """(rows, cols, 4) uint8, image row 0 at the TOP, vertical markers burnt in."""
+    def marker_columns(self) -> list[tuple[int, int, tuple[int, int, int, int]]]:
+        """(column, half width, colour) of every vertical marker burnt into the panel, in drawing order."""
         if not self.images:
-            return None
+            return []
         img = self.images[-1]
-        out = np.ascontiguousarray(img.rgba[::-1])  # origin="lower": flip for top-down image rows
-        if img.extent is not None and out.shape[1] > 0:
+        n_cols = img.rgba.shape[1]
+        out = []
+        if img.extent is not None and n_cols > 0:
             x0, x1 = float(img.extent[0]), float(img.extent[1])
             span = (x1 - x0) or 1.0
             for ln in self.lines:
                 if ln["kind"] != "vline":
                     continue
-                col = int(round((ln["x"] - x0) / span * (out.shape[1] - 1)))
-                if 0 <= col < out.shape[1]:
+                col = int(round((ln["x"] - x0) / span * (n_cols - 1)))
+                if 0 <= col < n_cols:
                     half = 1 if float(ln.get("linewidth", 1)) >= 4 else 0
-                    out[:, max(0, col - half) : col + half + 1] = _rgba(ln.get("color", "black"))
+                    out.append((col, half, _rgba(ln.get("color", "black"))))
+        return out
+
+    def render(self) -> np.ndarray | None:
+        """(rows, cols, 4) uint8, image row 0 at the TOP, vertical markers burnt in."""
+        if not self.images:
+            return None
+        img = self.images[-1]
+        if isinstance(img.rgba, DeviceRaster):
+            raise TypeError("this panel lives on the device: encode the figure with png.encode_figures_device")
+        out = np.ascontiguousarray(img.rgba[::-1])  # origin="lower": flip for top-down image rows
+        for col, half, colour in self.marker_columns():
+            out[:, max(0, col - half) : col + half + 1] = colour
         return out
 
 
@@ -211,36 +243,49 @@ class SpectrogramFigure:
     def clf(self):
         self.axes, self._grid, self.colorbars, self.texts = [], {}, [], []
 
-    def compose(self, row_height: int = 148, gap: int = 8, background=(255, 255, 255, 255)) -> np.ndarray:
-        """Every panel at cell resolution (time steps are columns), energy rows repeated to about
-        ``row_height`` pixels, laid out on the subplot grid with ``gap`` pixels in between."""
+    def layout(self, row_height: int = 148, gap: int = 8):
+        """Geometry of :meth:`compose`: ``(H, W, [(axes, y, x, rep)])`` -- every panel at cell
+        resolution (time steps are columns), energy rows repeated to about ``row_height`` pixels,
+        laid out on the subplot grid with ``gap`` pixels in between.  Shapes only, so it serves
+        host rasters and device-resident ones alike."""
         cells = {}
         n_rows = n_cols = 1
         for ax in self.axes:
             r, c, idx = self._grid[id(ax)]
             n_rows, n_cols = max(n_rows, r), max(n_cols, c)
-            panel = ax.render()
-            if panel is None or panel.size == 0:
+            if not ax.images:
                 continue
-            rep = max(1, row_height // panel.shape[0])
-            cells[((idx - 1) // c, (idx - 1) % c)] = np.repeat(panel, rep, axis=0)
+            ne, nt = ax.images[-1].rgba.shape[:2]
+            if ne * nt == 0:
+                continue
+            rep = max(1, row_height // ne)
+            cells[((idx - 1) // c, (idx - 1) % c)] = (ax, ne * rep, nt, rep)
         if not cells:
-            return np.full((1, 1, 4), background, dtype=np.uint8)
-        heights = [max([p.shape[0] for (r, _c), p in cells.items() if r == i] or [0]) for i in range(n_rows)]
-        widths = [max([p.shape[1] for (_r, c), p in cells.items() if c == j] or [0]) for j in range(n_cols)]
+            return 1, 1, []
+        heights = [max([v[1] for (r, _c), v in cells.items() if r == i] or [0]) for i in range(n_rows)]
+        widths = [max([v[2] for (_r, c), v in cells.items() if c == j] or [0]) for j in range(n_cols)]
         H = sum(heights) + gap * (n_rows + 1)
         W = sum(widths) + gap * (n_cols + 1)
-        canvas = np.empty((H, W, 4), dtype=np.uint8)
-        canvas[:] = background
+        placed = []
         y = gap
         for i in range(n_rows):
             x = gap
             for j in range(n_cols):
-                p = cells.get((i, j))
-                if p is not None:
-                    canvas[y : y + p.shape[0], x : x + p.shape[1]] = p
+                v = cells.get((i, j))
+                if v is not None:
+                    placed.append((v[0], y, x, v[3]))
                 x += widths[j] + gap
             y += heights[i] + gap
+        return H, W, placed
+
+    def compose(self, row_height: int = 148, gap: int = 8, background=(255, 255, 255, 255)) -> np.ndarray:
+        """The figure as one (H, W, 4) uint8 image (see :meth:`layout`)."""
+        H, W, placed = self.layout(row_height, gap)
+        canvas = np.empty((H, W, 4), dtype=np.uint8)
+        canvas[:] = background
+        for ax, y, x, rep in placed:
+            p = np.repeat(ax.render(), rep, axis=0)
+            canvas[y : y + p.shape[0], x : x + p.shape[1]] = p
         return canvas
 
     def savefig(self, path, dpi=None, compress_level: int = 6, **kw):

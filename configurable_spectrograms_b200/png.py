@@ -1,9 +1,16 @@
 """PNG hand-off for the RGBA rasters (the on-disk product of the reference:
 ``fast/process_orbit.py:98-117``, ``generic_batch.py:108-113``).
 
-Filter 0 + zlib DEFLATE on the host; ``zlib.compress`` releases the GIL, so a batch of figures
-is encoded on a thread pool while the GPU works on the next shard.  A GPU DEFLATE stage is the
-next item on the scope list.
+Two encoders, one file format (8-bit RGBA, non-interlaced):
+
+* :func:`encode_rgba` / :func:`write_rgba` -- filter 0 + zlib DEFLATE on the host, for figures whose
+  rasters are host arrays (the single-figure entry points);
+* :func:`encode_figures_device` / :func:`write_figures_device` -- figures whose panels are K3 rasters
+  in HBM are composed, Up-filtered and DEFLATE-encoded on the GPU (``csrc/png.cu``); only the
+  compressed bytes cross PCIe.  The host adds the zlib header / trailer and the PNG chunk framing.
+
+Both decode to the same pixels (``tests/test_gpu_api.py``); the host composer is the oracle of the
+device one.
 """
 
 from __future__ import annotations
@@ -60,9 +67,20 @@ def decode_rgba(data: bytes) -> np.ndarray:
         pos += 12 + n
     h, w = shape
     raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)
-    if raw[:, 0].any():
-        raise ValueError("only filter type 0 is supported")
-    return raw[:, 1:].reshape(h, w, 4).copy()
+    kinds = set(np.unique(raw[:, 0]).tolist())
+    if kinds <= {0}:
+        return raw[:, 1:].reshape(h, w, 4).copy()
+    if not kinds <= {0, 2}:
+        raise ValueError(f"only filter types 0 (None) and 2 (Up) are supported, found {sorted(kinds)}")
+    out = raw[:, 1:].copy()
+    up = raw[:, 0] == 2
+    if up.all():  # every line is a difference to the one above: a running sum modulo 256
+        out = np.cumsum(out, axis=0, dtype=np.uint64).astype(np.uint8)
+    else:
+        for r in range(h):
+            if up[r] and r > 0:
+                out[r] += out[r - 1]
+    return out.reshape(h, w, 4)
 
 
 def write_many(jobs, compress_level: int = 6, max_workers: int = 8) -> None:
@@ -72,3 +90,134 @@ def write_many(jobs, compress_level: int = 6, max_workers: int = 8) -> None:
         return
     with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(jobs)))) as pool:
         list(pool.map(lambda j: write_rgba(j[0], j[1], compress_level), jobs))
+
+
+# ----------------------------------------------------------------------------------------
+# device encoder (csrc/png.cu)
+# ----------------------------------------------------------------------------------------
+_ADLER = 65521
+
+
+def adler32_of_segments(sum_bytes: np.ndarray, weighted: np.ndarray, lengths: np.ndarray) -> int:
+    """Adler-32 of the concatenation of segments from their partial sums: ``sum_bytes[k]`` = sum of
+    the bytes of segment k, ``weighted[k]`` = sum of ``(n_k - t) * byte_t`` (both mod 65521),
+    ``lengths[k]`` = n_k.  With A the running byte sum (+1) before a segment, the segment adds
+    ``n_k * A + weighted[k]`` to B."""
+    sa = np.asarray(sum_bytes, dtype=np.int64) % _ADLER
+    sb = np.asarray(weighted, dtype=np.int64) % _ADLER
+    n = np.asarray(lengths, dtype=np.int64)
+    a_before = np.concatenate([[1], (1 + np.cumsum(sa)) % _ADLER])[:-1] if len(sa) else np.zeros(0, np.int64)
+    a = int((1 + int(sa.sum())) % _ADLER)
+    b = int((((n % _ADLER) * a_before) % _ADLER + sb).sum() % _ADLER)
+    return (b << 16) | a
+
+
+def _device_tables(figures, row_height, gap, background):
+    from ._lib import PNG_CANVAS, PNG_TILE, PNG_VLINE
+    from .figure import DeviceRaster, _rgba
+
+    def pack(c):
+        r, g, b, a = _rgba(c)
+        return r | (g << 8) | (b << 16) | (a << 24)
+
+    canvases, tiles, vlines = [], [], []
+    for fig in figures:
+        H, W, placed = fig.layout(row_height, gap)
+        first = len(tiles)
+        for ax, y, x, rep in placed:
+            ref = ax.images[-1].rgba
+            if not isinstance(ref, DeviceRaster):
+                raise TypeError("encode_figures_device needs panels drawn from device rasters (figure.DeviceRaster)")
+            v0 = len(vlines)
+            for col, half, colour in ax.marker_columns():
+                vlines.append((col, half, pack(colour), 0))
+            tiles.append((ref.offset, ref.ne, ref.nt, x, y, rep, v0, len(vlines) - v0, 0))
+        if len(tiles) - first > 32:
+            raise ValueError("at most 32 panels per figure")
+        canvases.append([W, H, first, len(tiles) - first, pack(background), 0, (W + 1023) // 1024, 0])
+    return (canvases, np.array(tiles, dtype=PNG_TILE) if tiles else np.zeros(1, PNG_TILE),
+            np.array(vlines, dtype=PNG_VLINE) if vlines else np.zeros(1, PNG_VLINE))
+
+
+def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, gap: int = 8,
+                          background=(255, 255, 255, 255), max_segments: int = 160_000) -> list[bytes]:
+    """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
+
+    ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
+    :class:`figure.DeviceRaster` references into the RGBA buffer at ``d_rgba_ptr`` (a batch's
+    ``d_rgba``).  Same geometry as ``SpectrogramFigure.compose`` (the host oracle).  Figures are
+    processed in groups of at most ``max_segments`` scanline segments (scratch: 4.6 KB each).
+    """
+    from ._lib import PNG_CANVAS
+
+    lib = ctx.lib
+    figures = list(figures)
+    canvases, tiles, vlines = _device_tables(figures, row_height, gap, background)
+    slot = int(lib.csg_png_slot_bytes())
+    scratch = ctx.__dict__.setdefault("_png_scratch", {})
+
+    def dev(name, nbytes):
+        buf = scratch.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            buf = scratch[name] = ctx.alloc(int(nbytes * 1.2) + 256)
+        return buf
+
+    d_tiles, d_vlines = ctx.to_device(tiles), ctx.to_device(vlines)
+    out: list[bytes] = []
+    k = 0
+    while k < len(figures):
+        # ---- the next group of figures that fits the segment budget
+        group, n_seg = [], 0
+        while k + len(group) < len(figures):
+            c = canvases[k + len(group)]
+            segs = int(lib.csg_png_segments(c[0], c[1]))
+            if group and n_seg + segs > max_segments:
+                break
+            c[5] = n_seg
+            group.append(c)
+            n_seg += segs
+        table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
+        d_canvases = ctx.to_device(table)
+        d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
+        ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_canvases.ptr, len(group), d_tiles.ptr, d_vlines.ptr, n_seg,
+                                      d_slots.ptr, d_sizes.ptr, d_adler.ptr))
+        sizes = d_sizes.download(np.int32, n_seg, sync=False)
+        adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
+        offsets = np.zeros(n_seg + 1, dtype=np.int64)
+        np.cumsum(sizes, out=offsets[1:])
+        total = int(offsets[-1])
+        d_off = dev("offsets", n_seg * 8)
+        d_off.upload(offsets[:-1])
+        d_packed = dev("packed", total)
+        ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
+        packed = d_packed.download(np.uint8, total)  # synchronises
+        for c in group:
+            W, H, s0 = c[0], c[1], c[5]
+            s1 = s0 + int(lib.csg_png_segments(W, H))
+            per_row = c[6]
+            # filtered bytes per segment: 4 per pixel, plus the filter-type byte on a line's first segment
+            chunk = np.arange(s1 - s0) % per_row
+            npx = np.minimum(1024, W - 1024 * chunk)
+            lengths = 4 * npx + (chunk == 0)
+            check = adler32_of_segments(adler[s0:s1, 0], adler[s0:s1, 1], lengths)
+            stream = b"".join((b"\x78\x01", packed[offsets[s0] : offsets[s1]].tobytes(), b"\x01\x00\x00\xff\xff",
+                               struct.pack(">I", check)))
+            ihdr = struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)
+            out.append(_SIGNATURE + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", stream) + _chunk(b"IEND", b""))
+        k += len(group)
+    return out
+
+
+def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwargs) -> None:
+    """``jobs``: iterable of (path, figure).  Device encode, then the files are written on a thread pool."""
+    jobs = list(jobs)
+    if not jobs:
+        return
+    blobs = encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], **kwargs)
+
+    def write(job):
+        with open(job[0][0], "wb") as f:
+            f.write(job[1])
+
+    with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(jobs)))) as pool:
+        list(pool.map(write, zip(jobs, blobs)))

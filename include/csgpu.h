@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 9
+#define CSG_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -402,6 +402,44 @@ CSG_API int csg_peer_allgather(csg_ctx* ctx, csg_peer* peer, const void* d_src, 
 CSG_API void* csg_peer_error_word(csg_peer* peer);
 CSG_API int csg_peer_clear_error(csg_ctx* ctx, csg_peer* peer); /* on the ctx stream */
 CSG_API int csg_peer_destroy(csg_ctx* ctx, csg_peer* peer);
+
+/* --------------------------------------------- K4: figure mosaics -> DEFLATE (PNG hand-off) */
+/* Replaces fig.savefig() of CS/fast/process_orbit.py:98-117 / CS/generic_batch.py:108-113 for
+ * figures whose panels are K3 rasters in HBM: the mosaic (figure.SpectrogramFigure.compose) is
+ * evaluated per scanline inside the encoder, filtered with PNG filter 2 and written as
+ * fixed-Huffman DEFLATE blocks, one per segment (<= 1024 pixels of one scanline), each closed
+ * by an empty stored block so that segments concatenate bytewise.  See csrc/png.cu. */
+typedef struct {
+  int64_t rgba_off;  /* pixel offset of the panel in d_rgba ([ne][nt], row 0 = lowest energy)   */
+  int32_t ne, nt;
+  int32_t x, y;      /* top-left corner on the canvas                                           */
+  int32_t rep;       /* every raster row is drawn rep times                                      */
+  int32_t vline_first, vline_count; /* cusp lines burnt into this panel (d_vlines)              */
+  int32_t pad;
+} csg_png_tile; /* 40 bytes */
+typedef struct {
+  int32_t col, half; /* panel columns col-half .. col+half                                      */
+  uint32_t rgba;
+  int32_t pad;
+} csg_png_vline; /* 16 bytes */
+typedef struct {
+  int32_t W, H;
+  int32_t tile_first, tile_count; /* at most 32 tiles per canvas                                */
+  uint32_t background;
+  int32_t seg_first;    /* id of the canvas' first segment; segments are numbered row by row    */
+  int32_t segs_per_row; /* ceil(W / 1024)                                                       */
+  int32_t pad;
+} csg_png_canvas; /* 32 bytes */
+CSG_API int32_t csg_png_slot_bytes(void);               /* capacity of one segment's output slot */
+CSG_API int32_t csg_png_segments(int32_t W, int32_t H); /* segments of one canvas                 */
+/* d_slots[n_segments][slot_bytes]: the encoded segments; d_sizes[n_segments]: their byte counts;
+ * d_adler[n_segments][2]: (sum of bytes, sum of (n - t) * byte_t) mod 65521 of the filtered bytes. */
+CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
+                   const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments,
+                   uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler);
+/* d_packed + d_offsets[s] <- slot s (d_offsets: exclusive prefix sum of d_sizes, from the host). */
+CSG_API int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets,
+                    int n_segments, uint8_t* d_packed);
 
 #ifdef __cplusplus
 }
