@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-orbits", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-png", action="store_true")
+    ap.add_argument("--png-orbits", type=int, default=8, help="orbits whose figures (20 each) go through the device PNG stage")
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--profile-host", default=None, help="write a cProfile of the timed step loop to this path")
     return ap.parse_args()
@@ -352,6 +354,38 @@ def main():
     pool_ms = float(np.mean(pool))
     sampler.mark(1)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ------------------------------------------------- K4 (outside the metric): figures -> PNG bytes
+    png_stage = None
+    if rank == 0 and not args.no_png:
+        from configurable_spectrograms_b200 import png as PNG
+        from configurable_spectrograms_b200.fast.plotting import figure_from_spec
+
+        step.run({})
+        step.finish()
+        norms = shard.batch.norms()
+        n_fig_orbits = min(args.png_orbits, n_local)
+        specs = [sp for ob in orbits[:n_fig_orbits] for wx in (False, True)
+                 for sp in shard.figures[slice(*step.figure_ranges[(ob["orbit"], wx)])]]
+        figs = [f for f in (figure_from_spec(shard, sp, "turbo", norms=norms, device_rasters=True)[0] for sp in specs) if f is not None]
+        PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs[:4])  # warm-up: tables, scratch
+        t0 = time.perf_counter()
+        blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs)
+        dev_s = time.perf_counter() - t0
+        raw_bytes = sum(4 * H * W + H for H, W, _ in (f.layout() for f in figs))
+        # the host encoder on the same mosaic (zlib level 6, one thread), a few figures
+        sample = figs[:: max(1, len(figs) // 6)][:6]
+        host_s, host_bytes = 0.0, 0
+        for f, blob in zip(sample, [blobs[figs.index(f)] for f in sample]):
+            img = PNG.decode_rgba(blob)
+            t0 = time.perf_counter()
+            host_bytes += len(PNG.encode_rgba(img))
+            host_s += time.perf_counter() - t0
+        png_stage = {"figures": len(figs), "raw_gb": raw_bytes / 1e9, "device_s": dev_s, "device_figures_per_s": len(figs) / dev_s,
+                     "device_raw_gb_per_s": raw_bytes / 1e9 / dev_s, "device_ratio": raw_bytes / max(1, sum(len(b) for b in blobs)),
+                     "host_zlib6_s_per_figure_1thread": host_s / max(1, len(sample)),
+                     "host_zlib6_ratio": sum(4 * H * W + H for H, W, _ in (f.layout() for f in sample)) / max(1, host_bytes),
+                     "note": "compose + Up filter + fixed-Huffman DEFLATE on the GPU, D2H of the compressed bytes and PNG framing included; not part of `value`"}
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -451,7 +485,7 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
             "step_roofline": {"algorithmic_bytes": int(step_bytes), "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "note": "this rank's whole step (K1+K2b+K2a+K3), SURVEY 8(d) B_orbit x orbits / step time"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+            "png_stage": png_stage, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
             "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
                          "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,
                          "percentile_regions_needing_radix_fallback": fallbacks},

@@ -204,7 +204,9 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             flush_batch_size=flush_batch_size, _shard=shard, _comm=comm,
         )
 
-    # ---- every figure of this rank's pending orbits: K2a + K3, then compose + encode on host threads
+    # ---- every figure of this rank's pending orbits: K2a + K3; the figures are planned on host
+    # threads from panel references, then composed and PNG-encoded on the device (K4): no raster
+    # ever crosses PCIe uncompressed
     my_pending = [o for o in pending if o in set(loaded_orbits)]
     submissions = (False, True) if need_extrema else (False,)
     sequence = [(o, {i: True for i in files}) for o, files in sorted_orbits]
@@ -214,11 +216,11 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
         step.finish()
     b = shard.batch
     norms = b.norms() if b.n_panels else None
-    rgba_flat = b.all_rgba() if b.n_pixels else None
 
     def render(orbit, with_extrema):
         """One submission of one orbit (= one FAST_process_single_orbit call of the reference)."""
         result: dict[str, Any] = {"orbit": orbit, "status": "ok", "errors": []}
+        saves: list[tuple[str, Any]] = []  # (path, figure): encoded and written after the planning pass
         for err in load_errors.get(orbit, []):
             result["status"] = "error"
             result["errors"].append(err)
@@ -232,23 +234,22 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             what = f"pitch angle grid for {spec.instrument}" if spec.kind == "pitch-angle" else "instrument grid"
             try:
                 fig, _canvas = figure_from_spec(shard, spec, colormap, cusp_marker_style, cusp_marker_kwargs, norms=norms,
-                                                rgba_flat=rgba_flat)
+                                                device_rasters=True)
                 if fig is None:
                     continue
                 path = os.path.join(out_dir, figure_filename(spec, y_scale, z_scale, colormap))
                 if not override_plots and os.path.exists(path):
                     log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
+                    close_all_axes_and_clear(fig)
                 else:
-                    fig.savefig(path, dpi=200)
-                    log_exception(f"[SAVED] {path}", level="message")
-                close_all_axes_and_clear(fig)
+                    saves.append((path, fig))
             except Exception as exc:
                 err = f"[FAIL] Plotting Orbit {orbit} {what}"
                 log_exception(err, exc, level="error")
                 result["status"] = "error"
                 if err not in result["errors"]:
                     result["errors"].append(err)
-        return result
+        return result, saves
 
     def record(result, pdisk):
         orbit = result["orbit"]
@@ -267,16 +268,40 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
     pdisk = dict(progress)
     since_flush = 0
     with ThreadPoolExecutor(max_workers=max(1, int(max_workers))) as pool:
-        for result in pool.map(lambda j: render(*j), jobs):
-            results.append(result)
-            if verbose:
-                log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
-            if progress_json_path is not None and rank == 0:
-                record(result, pdisk)
-                since_flush += 1
-                if since_flush >= flush_batch_size:
-                    _write_json(progress_json_path, pdisk)
-                    since_flush = 0
+        planned = list(pool.map(lambda j: render(*j), jobs))
+    rendered = [r for r, _s in planned]
+    # the reference runs the submissions one after the other: a later one finds the earlier one's file
+    # and skips it unless override_plots is set, in which case the later one wins
+    by_path: dict[str, Any] = {}
+    for _r, job_saves in planned:
+        for path, fig in job_saves:
+            if path in by_path and not override_plots:
+                log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
+                close_all_axes_and_clear(fig)
+                continue
+            if path in by_path:
+                close_all_axes_and_clear(by_path[path])
+            by_path[path] = fig
+    saves = list(by_path.items())
+    # ---- K4: compose + DEFLATE on the device, files written by a thread pool; progress is recorded
+    # only once the orbit's PNGs are on disk
+    if saves:
+        from ..png import write_figures_device
+
+        write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=max(1, int(max_workers)))
+        for path, fig in saves:
+            log_exception(f"[SAVED] {path}", level="message")
+            close_all_axes_and_clear(fig)
+    for result in rendered:
+        results.append(result)
+        if verbose:
+            log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
+        if progress_json_path is not None and rank == 0:
+            record(result, pdisk)
+            since_flush += 1
+            if since_flush >= flush_batch_size:
+                _write_json(progress_json_path, pdisk)
+                since_flush = 0
 
     if world > 1:  # every rank returns every result; rank 0 owns the progress file
         gathered: list = [None] * world

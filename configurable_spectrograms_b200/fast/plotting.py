@@ -17,7 +17,7 @@ import numpy as np
 from .. import _lib
 from ..cdf_utils import get_cdf_file_type, get_timestamps_for_orbit, load_fast_cdf_dataset
 from ..colormaps import get_lut
-from ..figure import FigureCanvas, SpectrogramFigure
+from ..figure import DeviceRaster, FigureCanvas, SpectrogramFigure
 from ..logging_utils import log_exception
 from ..plotting import _finish_multirow, date2num, draw_panel
 from .constants import DEFAULT_INSTRUMENT_ORDER, DEFAULT_PITCH_ANGLE_CATEGORIES
@@ -27,13 +27,15 @@ __all__ = ["FAST_plot_pitch_angle_grid", "FAST_plot_instrument_grid", "figure_fr
 
 
 def figure_from_spec(shard: ShardPlan, spec: FigureSpec, colormap="viridis", cusp_marker_style="both",
-                     cusp_marker_kwargs=None, norms=None, rgba_flat=None, index_flat=None):
+                     cusp_marker_kwargs=None, norms=None, rgba_flat=None, index_flat=None, device_rasters=False):
     """Compose the figure ``generic_plot_multirow_optional_zoom`` would return for one planned
     figure (reference ``plotting.py:583-698``) from the shard's finished rasters.
 
     ``norms`` / ``rgba_flat`` / ``index_flat``: the batch's downloaded tables (bulk D2H by the
-    batch driver); fetched per panel when omitted.  Raises the ``ValueError`` matplotlib would
-    raise at draw time for an invalid normalisation.
+    batch driver); fetched per panel when omitted.  ``device_rasters``: the panels stay in HBM
+    (``figure.DeviceRaster`` references into the batch's RGBA buffer) and the figure is meant for
+    ``png.encode_figures_device``.  Raises the ``ValueError`` matplotlib would raise at draw time
+    for an invalid normalisation.
     """
     if not spec.rows:
         return None, None
@@ -52,6 +54,8 @@ def figure_from_spec(shard: ShardPlan, spec: FigureSpec, colormap="viridis", cus
     def raster(pid):
         ne, nt = b.panel_shape(pid)
         off = b._panels[pid][6]
+        if device_rasters:
+            return DeviceRaster(off, ne, nt), None
         if rgba_flat is not None:
             rgba = rgba_flat[off * 4 : (off + ne * nt) * 4].reshape(ne, nt, 4)
         else:

@@ -191,7 +191,7 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         d_packed = dev("packed", total)
         ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
         packed = d_packed.download(np.uint8, total)  # synchronises
-        for c in group:
+        def frame(c):
             W, H, s0 = c[0], c[1], c[5]
             s1 = s0 + int(lib.csg_png_segments(W, H))
             per_row = c[6]
@@ -203,7 +203,11 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
             stream = b"".join((b"\x78\x01", packed[offsets[s0] : offsets[s1]].tobytes(), b"\x01\x00\x00\xff\xff",
                                struct.pack(">I", check)))
             ihdr = struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)
-            out.append(_SIGNATURE + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", stream) + _chunk(b"IEND", b""))
+            return _SIGNATURE + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", stream) + _chunk(b"IEND", b"")
+
+        # the chunk CRCs run over the compressed bytes: zlib.crc32 releases the GIL, so frame on threads
+        with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
+            out.extend(pool.map(frame, group))
         k += len(group)
     return out
 

@@ -175,6 +175,23 @@ def test_directory_driver_matches_reference_outputs(tmp_path, monkeypatch):
     assert prog["linear_log_last_orbit"] == 13005
     img = png.decode_rgba(open(os.path.join("./FAST_plots", gold["batch_pngs"][0]), "rb").read())
     assert img.ndim == 3 and img.shape[2] == 4 and img.shape[0] > 100
+    # the driver's PNGs were composed and encoded on the device (K4); the per-orbit worker composes
+    # on the host and encodes with zlib: same files, same pixels
+    from configurable_spectrograms_b200.cdf_utils import load_filtered_orbits
+    from configurable_spectrograms_b200.fast.orbit_discovery import discover_orbit_files
+    from configurable_spectrograms_b200.fast.process_orbit import FAST_process_single_orbit
+
+    files = discover_orbit_files("./FAST_data", ORDER)
+    for orbit in (13000, 13002):
+        r = FAST_process_single_orbit(orbit, files[orbit], load_filtered_orbits(), 6, "linear", "log", ORDER, "cividis",
+                                      "./host_out/", global_extrema=gold["batch_extrema"])
+        assert r["status"] == "ok"
+        names = sorted(os.listdir(f"./host_out/2000/01/{orbit}"))
+        assert names
+        for name in names:
+            dev_png = open(f"./FAST_plots/2000/01/{orbit}/{name}", "rb").read()
+            host_png = open(f"./host_out/2000/01/{orbit}/{name}", "rb").read()
+            assert np.array_equal(png.decode_rgba(dev_png), png.decode_rgba(host_png)), name
     # resume: nothing left to do, nothing re-plotted
     again = FAST_plot_spectrograms_directory(
         "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", colormap="cividis",

@@ -6,6 +6,7 @@ import json
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+import pytest
 
 
 def test_png_round_trip(tmp_path):
@@ -85,3 +86,51 @@ def test_date2num_matches_datetime_path():
     ref = np.array([stubs.date2num(datetime.fromtimestamp(float(x), tz=timezone.utc)) for x in t])
     assert np.array_equal(date2num(t).view(np.uint64), ref.view(np.uint64))
     assert date2num(946684800.0) == ref[0]
+
+
+def test_png_up_filter_decode_and_adler_of_segments():
+    """Host side of the device PNG stage: the decoder undoes filter 2 (Up), and the Adler-32 of a
+    stream follows from per-segment partial sums (what csrc/png.cu emits per scanline segment)."""
+    import struct
+    import zlib
+
+    from configurable_spectrograms_b200 import png
+
+    rng = np.random.default_rng(4)
+    segs = [rng.integers(0, 256, int(n), dtype=np.uint8) for n in (1, 4097, 4096, 13, 4097, 2)]
+    sa = [int(s.astype(np.int64).sum()) % 65521 for s in segs]
+    sb = [int(((len(s) - np.arange(len(s))) * s.astype(np.int64)).sum()) % 65521 for s in segs]
+    assert png.adler32_of_segments(sa, sb, [len(s) for s in segs]) == zlib.adler32(np.concatenate(segs).tobytes())
+    assert png.adler32_of_segments([], [], []) == zlib.adler32(b"")
+    img = rng.integers(0, 256, (9, 6, 4), dtype=np.uint8)
+    flat = img.reshape(9, 24)
+    for kinds in ([2] * 9, [0, 2, 2, 0, 2, 0, 0, 2, 2]):
+        raw = np.zeros((9, 25), np.uint8)
+        for r, kind in enumerate(kinds):
+            raw[r, 0] = kind
+            raw[r, 1:] = flat[r] - (flat[r - 1] if (kind == 2 and r > 0) else 0)
+        data = (png._SIGNATURE + png._chunk(b"IHDR", struct.pack(">IIBBBBB", 6, 9, 8, 6, 0, 0, 0))
+                + png._chunk(b"IDAT", zlib.compress(raw.tobytes())) + png._chunk(b"IEND", b""))
+        assert np.array_equal(png.decode_rgba(data), img)
+
+
+def test_figure_layout_serves_host_and_device_rasters():
+    from configurable_spectrograms_b200.figure import DeviceRaster, SpectrogramFigure
+
+    rng = np.random.default_rng(2)
+    shapes = [(74, 300), (74, 90), (30, 300)]
+    figs = []
+    for device in (False, True):
+        fig = SpectrogramFigure()
+        for cell, (ne, nt) in zip((1, 2, 3), shapes):
+            ax = fig.add_subplot(2, 2, cell)
+            ax.imshow(DeviceRaster(0, ne, nt) if device else rng.integers(0, 255, (ne, nt, 4), dtype=np.uint8),
+                      extent=(0.0, float(nt), 0.0, 1.0))
+            ax.axvline(12.0, color="red", linewidth=4)
+        figs.append(fig)
+    (H0, W0, p0), (H1, W1, p1) = figs[0].layout(), figs[1].layout()
+    assert (H0, W0) == (H1, W1) == figs[0].compose().shape[:2]
+    assert [(y, x, rep) for _a, y, x, rep in p0] == [(y, x, rep) for _a, y, x, rep in p1]
+    assert figs[0].axes[0].marker_columns() == figs[1].axes[0].marker_columns()
+    with pytest.raises(TypeError):
+        figs[1].compose()
