@@ -361,8 +361,8 @@ def main():
         from configurable_spectrograms_b200 import png as PNG
         from configurable_spectrograms_b200.fast.plotting import figure_from_spec
 
-        step.run({})
-        step.finish()
+        # (no collective here: the rasters of the last pass are still in HBM, the figures' zoom flags
+        # were resolved by step.finish() above)
         norms = shard.batch.norms()
         n_fig_orbits = min(args.png_orbits, n_local)
         specs = [sp for ob in orbits[:n_fig_orbits] for wx in (False, True)
