@@ -368,9 +368,10 @@ def main():
         specs = [sp for ob in orbits[:n_fig_orbits] for wx in (False, True)
                  for sp in shard.figures[slice(*step.figure_ranges[(ob["orbit"], wx)])]]
         figs = [f for f in (figure_from_spec(shard, sp, "turbo", norms=norms, device_rasters=True)[0] for sp in specs) if f is not None]
-        PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs[:4])  # warm-up: tables, scratch
+        PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs)  # warm-up: tables, device and pinned scratch
+        phases: dict = {}
         t0 = time.perf_counter()
-        blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs)
+        blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, timings=phases)
         dev_s = time.perf_counter() - t0
         raw_bytes = sum(4 * H * W + H for H, W, _ in (f.layout() for f in figs))
         # the host encoder on the same mosaic (zlib level 6, one thread), a few figures
@@ -383,7 +384,7 @@ def main():
             host_s += time.perf_counter() - t0
         png_stage = {"figures": len(figs), "raw_gb": raw_bytes / 1e9, "device_s": dev_s, "device_figures_per_s": len(figs) / dev_s,
                      "device_raw_gb_per_s": raw_bytes / 1e9 / dev_s, "device_ratio": raw_bytes / max(1, sum(len(b) for b in blobs)),
-                     "host_zlib6_s_per_figure_1thread": host_s / max(1, len(sample)),
+                     "phases_s": phases, "host_zlib6_s_per_figure_1thread": host_s / max(1, len(sample)),
                      "host_zlib6_ratio": sum(4 * H * W + H for H, W, _ in (f.layout() for f in sample)) / max(1, host_bytes),
                      "note": "compose + Up filter + fixed-Huffman DEFLATE on the GPU, D2H of the compressed bytes and PNG framing included; not part of `value`"}
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)

@@ -140,14 +140,27 @@ def _device_tables(figures, row_height, gap, background):
 
 
 def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, gap: int = 8,
-                          background=(255, 255, 255, 255), max_segments: int = 160_000) -> list[bytes]:
+                          background=(255, 255, 255, 255), max_segments: int = 160_000, consume=None,
+                          timings: dict | None = None) -> list[bytes]:
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
     ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
     :class:`figure.DeviceRaster` references into the RGBA buffer at ``d_rgba_ptr`` (a batch's
     ``d_rgba``).  Same geometry as ``SpectrogramFigure.compose`` (the host oracle).  Figures are
     processed in groups of at most ``max_segments`` scanline segments (scratch: 4.6 KB each).
+
+    ``consume(first_figure_index, parts)``: instead of returning the files, hand every group's files
+    -- each a list of buffers that alias pinned scratch, valid only during the call -- to the caller
+    (``write_figures_device`` writes them straight to disk without assembling them in memory).
+    ``timings`` (optional dict) accumulates host seconds per phase.
     """
+    import time
+
+    def tick(name, t0):
+        if timings is not None:
+            timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     from ._lib import PNG_CANVAS
 
     lib = ctx.lib
@@ -176,6 +189,7 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
             c[5] = n_seg
             group.append(c)
             n_seg += segs
+        t0 = time.perf_counter()
         table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
         d_canvases = ctx.to_device(table)
         d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
@@ -183,6 +197,7 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
                                       d_slots.ptr, d_sizes.ptr, d_adler.ptr))
         sizes = d_sizes.download(np.int32, n_seg, sync=False)
         adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
+        t0 = tick("encode_kernel_and_sizes", t0)
         offsets = np.zeros(n_seg + 1, dtype=np.int64)
         np.cumsum(sizes, out=offsets[1:])
         total = int(offsets[-1])
@@ -190,8 +205,16 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         d_off.upload(offsets[:-1])
         d_packed = dev("packed", total)
         ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
-        packed = d_packed.download(np.uint8, total)  # synchronises
+        pin = scratch.get("pinned")
+        if pin is None or pin.nbytes < total:
+            pin = scratch["pinned"] = ctx.pinned(int(total * 1.2) + 4096)
+        ctx._check(lib.csg_d2h(ctx.handle, pin.ptr, d_packed.ptr, total))
+        ctx.sync()
+        packed = pin.array
+        t0 = tick("compact_and_d2h", t0)
+
         def frame(c):
+            """The PNG file of one canvas as a list of buffers (the compressed stream is not copied)."""
             W, H, s0 = c[0], c[1], c[5]
             s1 = s0 + int(lib.csg_png_segments(W, H))
             per_row = c[6]
@@ -200,28 +223,39 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
             npx = np.minimum(1024, W - 1024 * chunk)
             lengths = 4 * npx + (chunk == 0)
             check = adler32_of_segments(adler[s0:s1, 0], adler[s0:s1, 1], lengths)
-            stream = b"".join((b"\x78\x01", packed[offsets[s0] : offsets[s1]].tobytes(), b"\x01\x00\x00\xff\xff",
-                               struct.pack(">I", check)))
+            body = memoryview(packed[offsets[s0] : offsets[s1]])
+            head, tail = b"\x78\x01", b"\x01\x00\x00\xff\xff" + struct.pack(">I", check)
+            crc = zlib.crc32(tail, zlib.crc32(body, zlib.crc32(head, zlib.crc32(b"IDAT"))))  # releases the GIL on the body
             ihdr = struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)
-            return _SIGNATURE + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", stream) + _chunk(b"IEND", b"")
+            return [_SIGNATURE + _chunk(b"IHDR", ihdr) + struct.pack(">I", len(head) + len(body) + len(tail)) + b"IDAT" + head,
+                    body, tail + struct.pack(">I", crc & 0xFFFFFFFF) + _chunk(b"IEND", b"")]
 
-        # the chunk CRCs run over the compressed bytes: zlib.crc32 releases the GIL, so frame on threads
         with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
-            out.extend(pool.map(frame, group))
+            parts = list(pool.map(frame, group))
+        t0 = tick("framing_crc", t0)
+        if consume is not None:
+            consume(k, parts)  # the buffers alias pinned scratch that the next group overwrites
+        else:
+            out.extend(b"".join(p) for p in parts)
+        t0 = tick("consume", t0)
         k += len(group)
     return out
 
 
 def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwargs) -> None:
-    """``jobs``: iterable of (path, figure).  Device encode, then the files are written on a thread pool."""
+    """``jobs``: iterable of (path, figure).  Device encode; every group's files are written by a
+    thread pool straight from the pinned read-back buffer."""
     jobs = list(jobs)
     if not jobs:
         return
-    blobs = encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], **kwargs)
 
     def write(job):
-        with open(job[0][0], "wb") as f:
-            f.write(job[1])
+        path, parts = job
+        with open(path, "wb") as f:
+            f.writelines(parts)
 
-    with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(jobs)))) as pool:
-        list(pool.map(write, zip(jobs, blobs)))
+    def consume(first, parts):
+        with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(parts)))) as pool:
+            list(pool.map(write, [(jobs[first + i][0], p) for i, p in enumerate(parts)]))
+
+    encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], consume=consume, **kwargs)
