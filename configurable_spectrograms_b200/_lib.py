@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -142,6 +142,8 @@ SIGNATURES = {
     "csg_abi_version": (_i, []),
     "csg_device_count": (_i, []),
     "csg_create": (_vp, [_i, _vp]),
+    "csg_create_side": (_vp, [_i, _i]),
+    "csg_wait_for": (_i, [_vp, _vp]),
     "csg_destroy": (None, [_vp]),
     "csg_last_error": (C.c_char_p, [_vp]),
     "csg_sync": (_i, [_vp]),
@@ -316,18 +318,34 @@ class PinnedBuf:
 class Context:
     """One GPU context (``csg_ctx``); all work runs on its stream."""
 
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, side: bool = False):
         self.lib = load_library()
         self.handle = None
         if self.lib.csg_device_count() <= 0:
             raise CsgError("no CUDA device available: libcsgpu has no CPU fallback")
-        # stream: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream); None/0 = own stream
-        h = self.lib.csg_create(int(device), _vp(stream) if stream else None)
+        # stream: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream); None/0 = own stream;
+        # side: a companion context with its own highest-priority stream (see side_context())
+        if side:
+            h = self.lib.csg_create_side(int(device), 1)
+        else:
+            h = self.lib.csg_create(int(device), _vp(stream) if stream else None)
         if not h:
             raise CsgError(self.lib.csg_last_error(None).decode())
         self.handle = h
         self.device = int(device)
         self._alive: list = []
+
+    def side_context(self) -> "Context":
+        """The companion context of this one (created on first use): same device, its own
+        highest-priority stream -- for work that should overlap this context's kernels."""
+        side = self.__dict__.get("_side")
+        if side is None:
+            side = self._side = Context(self.device, side=True)
+        return side
+
+    def wait_for(self, other: "Context"):
+        """Everything enqueued on ``other`` so far happens before what this context enqueues next."""
+        self._check(self.lib.csg_wait_for(self.handle, other.handle))
 
     # -- helpers
     def _check(self, status: int):

@@ -111,6 +111,30 @@ csg_ctx* csg_create(int device, void* external_stream) {
   return ctx;
 }
 
+csg_ctx* csg_create_side(int device, int high_priority) {
+  csg_ctx* ctx = csg_create(device, nullptr);
+  if (!ctx || !high_priority) return ctx;
+  // swap the default-priority stream for one the block scheduler serves first: small dependent
+  // kernels (the K2b digit loop) then slip in between the blocks of a wide kernel on another stream
+  int least = 0, greatest = 0;
+  cudaStream_t s = nullptr;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
+      cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest) == cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    ctx->stream = s;
+  } else {
+    cudaGetLastError();
+  }
+  return ctx;
+}
+
+int csg_wait_for(csg_ctx* waiter, csg_ctx* signal) {
+  if (!waiter || !signal) return CSG_ERR_ARG;
+  CSG_CUDA(waiter, cudaEventRecord(signal->ev_fork, signal->stream));
+  CSG_CUDA(waiter, cudaStreamWaitEvent(waiter->stream, signal->ev_fork, 0));
+  return CSG_OK;
+}
+
 void csg_destroy(csg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);

@@ -330,7 +330,8 @@ def _device_y_tables(instrument_order, eplan, max_E):
 
 
 def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, *, compute_mins=False,
-                    max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None, per_step=True):
+                    max_percentile=95.0, log_floor_cutoff=0.1, log_floor_value=-1.0, comm=None, per_step=True,
+                    overlap=False):
     """Enqueue the pooled-extrema selection (K2b) for an already collapsed :class:`pipeline.ShardPlan`.
 
     Everything runs asynchronously on the context's stream (``pool_select.DevicePoolSelector``);
@@ -345,6 +346,11 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
     every step (no ``on_step_done``): when the walk then reduces to independent max-merge chains
     (:func:`chain_ranges`) the y candidates are max-merged on the device too and the per-file
     counts never travel to the host.
+
+    ``overlap=True``: the selection runs on the batch context's side context (its own high-priority
+    stream, ordered after everything enqueued on the batch context so far), so kernels the caller
+    enqueues on the batch context afterwards (K2a, K3 of the panels that need no extrema) run
+    concurrently with the digit loop and its cross-GPU exchanges.
     """
     from ..pool_select import DevicePoolSelector, SingleRank
 
@@ -390,9 +396,13 @@ def extrema_enqueue(shard, sequence, instrument_order, y_scale, z_scale, state, 
     requests = [{"inst": ii, "p": max_percentile, "mode": "running_max"} for ii in range(len(instrument_order))]
     if compute_mins:
         requests += [{"inst": ii, "p": 1, "mode": "last"} for ii in range(len(instrument_order))]
-    selector = getattr(shard, "_pool_selector", None)
-    if selector is None:
-        selector = shard._pool_selector = DevicePoolSelector(shard.batch)  # persistent scratch across steps
+    attr = "_pool_selector_side" if overlap else "_pool_selector"
+    selector = getattr(shard, attr, None)
+    if selector is None:  # persistent scratch across steps
+        selector = DevicePoolSelector(shard.batch, ctx=shard.batch.ctx.side_context() if overlap else None)
+        setattr(shard, attr, selector)
+    if overlap:
+        selector.ctx.wait_for(shard.batch.ctx)  # the collapsed sums (K1) are complete before the histograms read them
     selector.enqueue(shard.batch.dtype, items, len(instrument_order), inst_len, max_E, requests, comm=comm,
                      count_rows=n_max, ydev=ydev)
     return {

@@ -475,7 +475,8 @@ class BatchStep:
         if state is None:
             pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
                                       dict(cache_state or {}), compute_mins=self.compute_mins,
-                                      max_percentile=self.max_percentile, comm=self.comm, per_step=False)
+                                      max_percentile=self.max_percentile, comm=self.comm, per_step=False,
+                                      overlap=planned)
             if planned:
                 independent_stages()
                 early = True

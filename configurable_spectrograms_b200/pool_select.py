@@ -218,10 +218,12 @@ class DevicePoolSelector:
     N_SLOTS = 16
     EVENT_SLOT = 31
 
-    def __init__(self, batch):
+    def __init__(self, batch, ctx=None):
+        """``ctx``: the context whose stream carries the selection (default: the batch's own; the batch
+        step passes the batch context's side context so the digit loop overlaps K2a / K3)."""
         self.batch = batch
-        self.ctx = batch.ctx
-        self.mem = _Grow(batch.ctx)
+        self.ctx = ctx if ctx is not None else batch.ctx
+        self.mem = _Grow(self.ctx)
         self._static_key = None
         self._pending = None
 

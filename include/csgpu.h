@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 10
+#define CSG_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -60,6 +60,12 @@ CSG_API int csg_abi_version(void);
 CSG_API int csg_device_count(void);
 /* external_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for an own stream */
 CSG_API csg_ctx* csg_create(int device, void* external_stream);
+/* A second context on the same device with its own (optionally highest-priority) stream: work
+ * that is independent of the main stream's next kernels (the K2b digit loop and its exchanges
+ * next to K2a / K3) overlaps them.  csg_wait_for: everything enqueued on `signal` so far
+ * happens before whatever is enqueued on `waiter` from now on. */
+CSG_API csg_ctx* csg_create_side(int device, int high_priority);
+CSG_API int csg_wait_for(csg_ctx* waiter, csg_ctx* signal);
 CSG_API void csg_destroy(csg_ctx* ctx);
 CSG_API const char* csg_last_error(csg_ctx* ctx); /* ctx may be NULL: error of a failed csg_create() */
 CSG_API int csg_sync(csg_ctx* ctx);
