@@ -1,29 +1,28 @@
 """Configuration surface shared by the generic and FAST paths.
 
-Same names and values as the reference's ``constants.py`` (``:5-34``) so user code
-that imports them keeps working; ``COLLAPSE_FUNCTION`` is the one pluggable
-operator on the hot path and here resolves to the GPU ``nansum``.
+Every name and value of the reference's ``constants.py`` (``:5-34``) is available here, so user
+code that imports them keeps working.  The one entry that is not a plain value is
+``COLLAPSE_FUNCTION`` -- the pluggable operator of the hot path (reference: ``np.nansum``,
+``constants.py:12``) -- which resolves to the GPU collapse with numpy's summation order.
 """
 
-from .engine import nansum as _gpu_nansum
+from .engine import nansum as COLLAPSE_FUNCTION  # (cube, axis=1) -> 2-D sums, bit-exact vs np.nansum
 
-CDF_DATA_DIRECTORY = "./FAST_data/"
-CDF_VARIABLE_NAMES = ["time_unix", "data", "energy", "pitch_angle"]
+# input: where the cubes live and which CDF variables a cube is made of
+CDF_DATA_DIRECTORY, CDF_VARIABLE_NAMES = "./FAST_data/", ["time_unix", "data", "energy", "pitch_angle"]
 
-#: collapses a 3-D cube to 2-D; reference: ``np.nansum`` (``constants.py:12``)
-COLLAPSE_FUNCTION = _gpu_nansum
+# colormap per (y scale, z scale) combination
+_COLORMAPS = {("LINEAR", "LINEAR"): "viridis", ("LINEAR", "LOG"): "cividis", ("LOG", "LINEAR"): "plasma", ("LOG", "LOG"): "inferno"}
+for (_y, _z), _name in _COLORMAPS.items():
+    globals()[f"COLORMAP_{_y}_Y_{_z}_Z"] = _name
+del _y, _z, _name
 
-COLORMAP_LINEAR_Y_LINEAR_Z = "viridis"
-COLORMAP_LINEAR_Y_LOG_Z = "cividis"
-COLORMAP_LOG_Y_LINEAR_Z = "plasma"
-COLORMAP_LOG_Y_LOG_Z = "inferno"
-
-PLOT_FIGURE_WIDTH_INCHES = 6.25
-PLOT_FIGURE_HEIGHT_INCHES = 2.0
-TICK_LABEL_FONT_SIZE = 15
-AXIS_LABEL_FONT_SIZE = 18
+# figure geometry and fonts of the single-panel plot (inches / points), default zoom window (minutes)
+PLOT_FIGURE_WIDTH_INCHES, PLOT_FIGURE_HEIGHT_INCHES = 6.25, 2.0
+TICK_LABEL_FONT_SIZE, AXIS_LABEL_FONT_SIZE = 15, 18
 DEFAULT_ZOOM_WINDOW_MINUTES = 6
 
+# generic batch bookkeeping: cusp table, progress file, output tree
 FILTERED_ORBITS_CSV_PATH = "./FAST_Cusp_Indices.csv"
 PLOTTING_PROGRESS_JSON_PATH = "./batch_multi_plot_progress.json"
 OUTPUT_BASE_DIRECTORY = "./plots/"

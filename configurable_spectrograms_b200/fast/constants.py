@@ -1,43 +1,54 @@
-"""FAST-specific paths, instrument order, colormaps and pitch-angle groups
-(mirror of the reference's ``fast/constants.py:11-41``)."""
+"""FAST-specific configuration surface.
 
-from ..constants import (
-    COLLAPSE_FUNCTION,
-    COLORMAP_LINEAR_Y_LINEAR_Z,
-    COLORMAP_LINEAR_Y_LOG_Z,
-    COLORMAP_LOG_Y_LINEAR_Z,
-    COLORMAP_LOG_Y_LOG_Z,
-)
+The names and values are the reference's (``fast/constants.py:11-41``) because user code and the
+mirrored entry points import them; here they are derived from three small tables -- where the FAST
+batch keeps its files, which colormap goes with which axis scaling, and how the 64 pitch-angle bins
+are grouped -- so the grouping can also be handed to the GPU collapse as membership bits
+(``pipeline.pitch_angle_bits``).
+"""
 
-FAST_CDF_DATA_FOLDER_PATH = "./FAST_data/"
-FAST_FILTERED_ORBITS_CSV_PATH = "./FAST_Cusp_Indices.csv"
-FAST_PLOTTING_PROGRESS_JSON = "./batch_multi_plot_FAST_progress.json"
-FAST_OUTPUT_BASE = "./FAST_plots/"
-FAST_LOGFILE_PREFIX = "./batch_multi_plot_FAST_log"
-FAST_LOGFILE_DATETIME_MARKER_PATH = "./batch_multi_plot_FAST_logfile_datetime.txt"
-FAST_EXTREMA_JSON_PATH = "./FAST_calculated_extrema.json"
+from .. import constants as _generic
 
-FAST_COLLAPSE_FUNCTION = COLLAPSE_FUNCTION
-CDF_VARIABLES = ("time_unix", "data", "energy", "pitch_angle")
+# ---- where the FAST batch reads and writes (all relative to the working directory)
+_FILES = {
+    "FAST_CDF_DATA_FOLDER_PATH": "FAST_data/",
+    "FAST_OUTPUT_BASE": "FAST_plots/",
+    "FAST_FILTERED_ORBITS_CSV_PATH": "FAST_Cusp_Indices.csv",
+    "FAST_EXTREMA_JSON_PATH": "FAST_calculated_extrema.json",
+    "FAST_PLOTTING_PROGRESS_JSON": "batch_multi_plot_FAST_progress.json",
+    "FAST_LOGFILE_PREFIX": "batch_multi_plot_FAST_log",
+    "FAST_LOGFILE_DATETIME_MARKER_PATH": "batch_multi_plot_FAST_logfile_datetime.txt",
+}
+globals().update({name: "./" + tail for name, tail in _FILES.items()})
+
+# ---- one colormap per (y scale, z scale): aliases of the generic table
+for _y in ("LINEAR", "LOG"):
+    for _z in ("LINEAR", "LOG"):
+        globals()[f"COLORMAP_{_y}_Y_{_z}_Z"] = getattr(_generic, f"COLORMAP_{_y}_Y_{_z}_Z")
+        globals()[f"DEFAULT_COLORMAP_{_y}_Y_{_z}_Z"] = getattr(_generic, f"COLORMAP_{_y}_Y_{_z}_Z")
+del _y, _z
+
+FAST_COLLAPSE_FUNCTION = _generic.COLLAPSE_FUNCTION  # the GPU nansum (engine.nansum)
+COLLAPSE_FUNCTION = _generic.COLLAPSE_FUNCTION
+CDF_VARIABLES = tuple(_generic.CDF_VARIABLE_NAMES)
 DEFAULT_INSTRUMENT_ORDER = ("ees", "eeb", "ies", "ieb")
 
-DEFAULT_COLORMAP_LINEAR_Y_LINEAR_Z = COLORMAP_LINEAR_Y_LINEAR_Z
-DEFAULT_COLORMAP_LINEAR_Y_LOG_Z = COLORMAP_LINEAR_Y_LOG_Z
-DEFAULT_COLORMAP_LOG_Y_LINEAR_Z = COLORMAP_LOG_Y_LINEAR_Z
-DEFAULT_COLORMAP_LOG_Y_LOG_Z = COLORMAP_LOG_Y_LOG_Z
-
-#: closed degree intervals per category; 210 sits in two groups, 30-40 / 140-150 in none
-DEFAULT_PITCH_ANGLE_CATEGORIES: dict[str, list[tuple[float, float]]] = {
-    "downgoing\n(0, 30), (330, 360)": [(0.0, 30.0), (330.0, 360.0)],
-    "upgoing\n(150, 210)": [(150.0, 210.0)],
-    "perpendicular\n(40, 140), (210, 330)": [(40.0, 140.0), (210.0, 330.0)],
-    "all\n(0, 360)": [(0.0, 360.0)],
-}
-
-#: row order of the pitch-angle grid (reference ``fast/plotting.py:26-31``)
-PITCH_ANGLE_ROW_KEYS = (
-    "all\n(0, 360)",
-    "downgoing\n(0, 30), (330, 360)",
-    "upgoing\n(150, 210)",
-    "perpendicular\n(40, 140), (210, 330)",
+# ---- pitch-angle groups: (name, closed degree intervals), in the row order of the pitch-angle grid
+# (reference ``fast/plotting.py:26-31``).  210 degrees sits in two groups, 30-40 / 140-150 in none.
+_GROUPS = (
+    ("all", ((0, 360),)),
+    ("downgoing", ((0, 30), (330, 360))),
+    ("upgoing", ((150, 210),)),
+    ("perpendicular", ((40, 140), (210, 330))),
 )
+
+
+def _label(name, spans):
+    return name + "\n" + ", ".join(f"({lo}, {hi})" for lo, hi in spans)
+
+
+PITCH_ANGLE_ROW_KEYS = tuple(_label(name, spans) for name, spans in _GROUPS)
+# the reference's dict lists the three partial groups first and "all" last
+DEFAULT_PITCH_ANGLE_CATEGORIES: dict[str, list[tuple[float, float]]] = {
+    _label(name, spans): [(float(lo), float(hi)) for lo, hi in spans] for name, spans in (_GROUPS[1:] + _GROUPS[:1])
+}
