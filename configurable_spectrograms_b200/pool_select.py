@@ -11,9 +11,15 @@ handful of buckets.
 
 Multi-GPU: ranks hold contiguous blocks of the ascending-orbit sequence.  Per digit one
 all-gather of each rank's bucket totals gives every rank the counts held by lower
-ranks (added on the fly by ``csg_pool_locate``); one all-gather of the surviving
-(instrument, prefix) pairs and their lower bounds keeps the slot tables identical
-everywhere.
+ranks (added on the fly by the locate kernels); one all-gather of [bounds | surviving
+(instrument, prefix) lists] keeps the slot tables identical everywhere; one last all-gather
+carries the results.  The all-gather itself is an ``exchange`` object (``comm.make_exchange``):
+peer mailboxes written over NVLink (``csrc/peer.cu``) or NCCL.
+
+Two drivers over the same kernels: :class:`DevicePoolSelector` (the whole digit loop enqueued on
+a stream, no host round trip -- the batch path) and :func:`prefix_percentiles` (host-driven,
+any number of candidate buckets -- the fallback when the device slot table overflows, and the
+form the gloo tests exercise with a numpy kernel stand-in).
 """
 
 from __future__ import annotations
@@ -209,7 +215,7 @@ class DevicePoolSelector:
     """The whole digit loop enqueued on the context's stream: no host round trip per digit.
 
     ``enqueue`` launches histograms, scans, the selection-table kernels of ``csrc/poolsel.cu`` and
-    (multi-rank) the NCCL exchanges on device buffers, then an asynchronous read-back of the
+    (multi-rank) the exchanges on device buffers, then an asynchronous read-back of the
     few results; ``result`` waits for that read-back only, so kernels enqueued afterwards (K2a)
     overlap the host bookkeeping.  When more than ``N_SLOTS`` distinct key prefixes survive a
     digit the device flags it and the caller falls back to the host-driven ``prefix_percentiles``.
