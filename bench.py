@@ -506,7 +506,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "collapse_stream_kernel<float,4,384>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ms": k1_ms,
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         # the peak above is a COPY (read + write bytes); K1 is 93 % reads, and a pure-read stream with
+                         # K1's addressing reaches 7488.6 GB/s on this GPU (scripts/read_bw.cu, profiles/r1_read_bw.txt)
+                         "read_stream_peak": 7488.6, "frac_of_read_stream_peak": achieved / 7488.6},
             "step_roofline": {"algorithmic_bytes": int(step_bytes), "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "note": "this rank's whole step (K1+K2b+K2a+K3), SURVEY 8(d) B_orbit x orbits / step time"},
             "png_stage": png_stage, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,

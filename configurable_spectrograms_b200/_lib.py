@@ -398,7 +398,10 @@ class Context:
         return name.value.decode(), sm.value, mem.value
 
     def launch_count(self) -> int:
-        return int(self.lib.csg_launch_count(self.handle))
+        """Kernels launched by this context and by its side context (if it has one)."""
+        n = int(self.lib.csg_launch_count(self.handle))
+        side = self.__dict__.get("_side")
+        return n + (side.launch_count() if side is not None else 0)
 
     def d2h_side(self, host_ptr: int, dev_ptr: int, nbytes: int):
         """Read a result back on the copy-out stream (overlaps later work on the main stream)."""
