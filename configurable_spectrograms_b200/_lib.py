@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -172,6 +172,7 @@ SIGNATURES = {
     "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _i]),
     "csg_sums_elems": (_i64, [C.c_int32, C.c_int32, _i]),
     "csg_collapse": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "csg_collapse_range": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "csg_window_any": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
@@ -343,6 +344,14 @@ class Context:
             side = self._side = Context(self.device, side=True)
         return side
 
+    def worker_context(self) -> "Context":
+        """A second companion context (own high-priority stream): the per-piece K2a / K3 work that runs
+        next to the main stream's K1 (``fast.pipeline.BatchStep``)."""
+        worker = self.__dict__.get("_worker")
+        if worker is None:
+            worker = self._worker = Context(self.device, side=True)
+        return worker
+
     def wait_for(self, other: "Context"):
         """Everything enqueued on ``other`` so far happens before what this context enqueues next."""
         self._check(self.lib.csg_wait_for(self.handle, other.handle))
@@ -400,8 +409,11 @@ class Context:
     def launch_count(self) -> int:
         """Kernels launched by this context and by its side context (if it has one)."""
         n = int(self.lib.csg_launch_count(self.handle))
-        side = self.__dict__.get("_side")
-        return n + (side.launch_count() if side is not None else 0)
+        for name in ("_side", "_worker"):
+            other = self.__dict__.get(name)
+            if other is not None:
+                n += other.launch_count()
+        return n
 
     def d2h_side(self, host_ptr: int, dev_ptr: int, nbytes: int):
         """Read a result back on the copy-out stream (overlaps later work on the main stream)."""

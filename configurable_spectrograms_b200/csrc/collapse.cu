@@ -213,7 +213,7 @@ template <typename T, int NG, int TPB, bool PIPE>
 __global__ void __launch_bounds__(TPB, (TPB <= 512 ? 2 : 1))
     collapse_stream_kernel(const csg_file_desc* __restrict__ files, int n_files, const int32_t* __restrict__ runs,
                            const uint8_t* __restrict__ pa_bits, int n_groups, T* __restrict__ sums,
-                           uint8_t* __restrict__ row_flags) {
+                           uint8_t* __restrict__ row_flags, int block_offset) {
   constexpr int V = VecOf<T>::N;
   constexpr int EV = TPB / kTileRows;  // energy chunks per row
   constexpr int E = EV * V;
@@ -221,9 +221,10 @@ __global__ void __launch_bounds__(TPB, (TPB <= 512 ? 2 : 1))
   T* s_out = reinterpret_cast<T*>(smem_raw);  // [(NG+1)][E][kOutPitch]; PIPE: first the threads' load slots [16][TPB] x 16 B
   __shared__ unsigned s_flags[kTileRows];
 
-  const int fi = find_file(files, n_files, blockIdx.x);
+  const int blk = (int)blockIdx.x + block_offset;  // a launch may cover a sub-range of the table's blocks
+  const int fi = find_file(files, n_files, blk);
   const csg_file_desc f = files[fi];
-  const int t0 = (blockIdx.x - f.first_block) * kTileRows;
+  const int t0 = (blk - f.first_block) * kTileRows;
   const int rows_here = min(kTileRows, f.T - t0);
   const int r = threadIdx.x / EV, c = threadIdx.x - r * EV;
   if (threadIdx.x < kTileRows) s_flags[threadIdx.x] = 0;
@@ -602,16 +603,19 @@ inline bool stream_pipe_enabled(int tpb) {
 
 template <typename T, int NG, int TPB>
 int launch_stream_one(csg_ctx* ctx, size_t smem, const csg_file_desc* d_files, int n_files, int total_blocks,
-                      const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+                      const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags,
+                      int block_offset) {
   if (stream_pipe_enabled(TPB)) {
     auto kern = collapse_stream_kernel<T, NG, TPB, true>;
     const size_t need = smem > (size_t)TPB * 256 ? smem : (size_t)TPB * 256;
     CSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    kern<<<total_blocks, TPB, need, ctx->stream>>>(d_files, n_files, d_runs, d_pa_bits, n_groups, d_sums, d_row_flags);
+    kern<<<total_blocks, TPB, need, ctx->stream>>>(d_files, n_files, d_runs, d_pa_bits, n_groups, d_sums, d_row_flags,
+                                                   block_offset);
   } else {
     auto kern = collapse_stream_kernel<T, NG, TPB, false>;
     CSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<total_blocks, TPB, smem, ctx->stream>>>(d_files, n_files, d_runs, d_pa_bits, n_groups, d_sums, d_row_flags);
+    kern<<<total_blocks, TPB, smem, ctx->stream>>>(d_files, n_files, d_runs, d_pa_bits, n_groups, d_sums, d_row_flags,
+                                                   block_offset);
   }
   CSG_LAUNCH_CHECK(ctx, "collapse_stream_kernel");
   return CSG_OK;
@@ -619,11 +623,12 @@ int launch_stream_one(csg_ctx* ctx, size_t smem, const csg_file_desc* d_files, i
 
 template <typename T, int NG>
 int launch_stream_ng(csg_ctx* ctx, int tpb, size_t smem, const csg_file_desc* d_files, int n_files, int total_blocks,
-                     const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+                     const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags,
+                     int block_offset) {
 #define CSG_GO(TPB)                                                                                                   \
   case TPB:                                                                                                           \
     return launch_stream_one<T, NG, TPB>(ctx, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums, \
-                                         d_row_flags);
+                                         d_row_flags, block_offset);
   switch (tpb) {
     CSG_GO(256)
     CSG_GO(384)
@@ -637,19 +642,20 @@ int launch_stream_ng(csg_ctx* ctx, int tpb, size_t smem, const csg_file_desc* d_
 
 template <typename T>
 int launch_stream(csg_ctx* ctx, int E, int dtype, const csg_file_desc* d_files, int n_files, int total_blocks,
-                  const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags) {
+                  const int32_t* d_runs, const uint8_t* d_pa_bits, int n_groups, T* d_sums, uint8_t* d_row_flags,
+                  int block_offset) {
   const int tpb = stream_tpb(E, dtype);
   const size_t smem = stream_smem(E, n_groups, dtype);
   if (tpb == 0 || smem > 200 * 1024)
     return csg_fail(ctx, CSG_ERR_ARG, "stream kernel cannot handle E=%d: use CSG_K1_GENERIC for this table", E);
   if (n_groups == 0)
     return launch_stream_ng<T, 0>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums,
-                                  d_row_flags);
+                                  d_row_flags, block_offset);
   if (n_groups <= 4)
     return launch_stream_ng<T, 4>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups, d_sums,
-                                  d_row_flags);
+                                  d_row_flags, block_offset);
   return launch_stream_ng<T, CSG_MAX_GROUPS>(ctx, tpb, smem, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
-                                             d_sums, d_row_flags);
+                                             d_sums, d_row_flags, block_offset);
 }
 
 template <typename T>
@@ -719,6 +725,13 @@ int64_t csg_sums_elems(int32_t T, int32_t E, int n_groups) {
 int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
                  const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E, int dtype,
                  int layout, int kernel, void* d_sums, uint8_t* d_row_flags) {
+  return csg_collapse_range(ctx, d_files, n_files, 0, total_blocks, d_pa_bits, d_runs, n_groups, max_P, max_E, dtype, layout,
+                            kernel, d_sums, d_row_flags);
+}
+
+int csg_collapse_range(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int block_offset, int total_blocks,
+                       const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E, int dtype,
+                       int layout, int kernel, void* d_sums, uint8_t* d_row_flags) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_groups < 0 || n_groups > CSG_MAX_GROUPS) return csg_fail(ctx, CSG_ERR_ARG, "n_groups %d out of range", n_groups);
   if (n_groups > 0 && !d_pa_bits) return csg_fail(ctx, CSG_ERR_ARG, "d_pa_bits is NULL with n_groups > 0");
@@ -732,14 +745,16 @@ int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int to
       if (!d_runs) return csg_fail(ctx, CSG_ERR_ARG, "d_runs is NULL for the stream kernel");
       if (dtype == CSG_F32)
         return launch_stream<float>(ctx, max_E, dtype, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
-                                    (float*)d_sums, d_row_flags);
+                                    (float*)d_sums, d_row_flags, block_offset);
       return launch_stream<double>(ctx, max_E, dtype, d_files, n_files, total_blocks, d_runs, d_pa_bits, n_groups,
-                                   (double*)d_sums, d_row_flags);
+                                   (double*)d_sums, d_row_flags, block_offset);
     }
+    if (block_offset != 0) return csg_fail(ctx, CSG_ERR_ARG, "block sub-ranges are only supported by the stream kernel");
     if (dtype == CSG_F32)
       return launch_tpe<float>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, (float*)d_sums, d_row_flags);
     return launch_tpe<double>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, (double*)d_sums, d_row_flags);
   }
+  if (block_offset != 0) return csg_fail(ctx, CSG_ERR_ARG, "block sub-ranges are only supported by the stream kernel");
   if (dtype == CSG_F32)
     return launch_tep<float>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (float*)d_sums, d_row_flags);
   return launch_tep<double>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (double*)d_sums, d_row_flags);

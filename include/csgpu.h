@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 11
+#define CSG_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -146,6 +146,12 @@ CSG_API int64_t csg_sums_elems(int32_t T, int32_t E, int n_groups);
  * all / group-k pitch bins (any energy); zero it before the call.
  * All files of one call share dtype, layout, kernel and n_groups. */
 CSG_API int csg_collapse(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int total_blocks,
+                 const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E,
+                 int dtype, int layout, int kernel, void* d_sums, uint8_t* d_row_flags);
+/* The same launch over the blocks [block_offset, block_offset + total_blocks) of the file table
+ * (stream kernel only): a shard collapsed in a few pieces lets the statistics and rasters of the
+ * files already done run on another stream while the next piece streams from HBM. */
+CSG_API int csg_collapse_range(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int block_offset, int total_blocks,
                  const uint8_t* d_pa_bits, const int32_t* d_runs, int n_groups, int max_P, int max_E,
                  int dtype, int layout, int kernel, void* d_sums, uint8_t* d_row_flags);
 
