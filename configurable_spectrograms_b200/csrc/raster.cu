@@ -252,6 +252,9 @@ __device__ __forceinline__ float fast_log2(float x) {
   return r;
 }
 
+__device__ __forceinline__ void lds(float& v, unsigned addr) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); }
+__device__ __forceinline__ void lds(double& v, unsigned addr) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); }
+
 template <bool B>
 struct Flag {
   static constexpr bool value = B;
@@ -285,8 +288,20 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
     const int idx = n == 0 ? I_UNDER : (n == kThr ? I_OVER : (n <= 256 ? n - 1 : I_BAD));
     s_lut[w] = (lut && n < 259) ? __ldg(lut + idx) : 0u;
   }
-  const T* my_thr = s_thr + lane;        // row r (threshold k = r - 1) at my_thr[r * 32]
-  const uint32_t* my_lut = s_lut + lane;
+  // explicit shared-window addresses of this lane's table columns: row r of a table is 32 words
+  // (128 bytes for float32 / the LUT) further on -- one add and one ld.shared per lookup
+  const unsigned thr_col = (unsigned)__cvta_generic_to_shared(s_thr + lane);  // row r (threshold k = r - 1)
+  const unsigned lut_col = (unsigned)__cvta_generic_to_shared(s_lut + lane);
+  auto thr_at = [&](int row) -> T {
+    T v;
+    lds(v, thr_col + (unsigned)row * (32u * (unsigned)sizeof(T)));
+    return v;
+  };
+  auto lut_at = [&](int row) -> uint32_t {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(lut_col + (unsigned)row * 128u));
+    return v;
+  };
 
   int cur_panel = -1;
   // panel state (reloaded when the block crosses into another panel)
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
       const int idx = degenerate == 1 ? 0 : I_BAD;
       const int row = degenerate == 1 ? 1 : 258;
       for (unsigned i = first + tid; i < last; i += kRasterThreads) {
-        if (out_rgba) out_rgba[i] = my_lut[row * 32];
+        if (out_rgba) out_rgba[i] = lut_at(row);
         if (out_idx) out_idx[i] = (uint16_t)idx;
       }
       continue;
@@ -379,12 +394,12 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
       gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
       int n = (int)gf;
       // n thresholds are <= v  <=>  thr[n-1] <= v < thr[n]   (rows are offset by one: thr[k] = row k+1)
-      const T b = my_thr[n * 32], c = my_thr[(n + 1) * 32];
+      const T b = thr_at(n), c = thr_at(n + 1);
       if (!(b <= v && !(c <= v))) {  // rare: the float guess was off
 #pragma unroll 1
-        while (n > 0 && !(my_thr[n * 32] <= v)) --n;
+        while (n > 0 && !(thr_at(n) <= v)) --n;
 #pragma unroll 1
-        while (n < kThr && my_thr[(n + 1) * 32] <= v) ++n;
+        while (n < kThr && thr_at(n + 1) <= v) ++n;
       }
       return is_nan(v) ? 258 : n;
     };
@@ -431,10 +446,10 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
         if (out_rgba) {
           if (out_vec)
             *reinterpret_cast<uint4*>(out_rgba + at) =
-                make_uint4(my_lut[n[0] * 32], my_lut[n[1] * 32], my_lut[n[2] * 32], my_lut[n[3] * 32]);
+                make_uint4(lut_at(n[0]), lut_at(n[1]), lut_at(n[2]), lut_at(n[3]));
           else {
 #pragma unroll
-            for (unsigned u = 0; u < G; ++u) out_rgba[at + u] = my_lut[n[u] * 32];
+            for (unsigned u = 0; u < G; ++u) out_rgba[at + u] = lut_at(n[u]);
           }
         }
         if (out_idx) {
@@ -476,7 +491,7 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
         unsigned jj = j, t = tt;
         for (unsigned p = i; p < last; ++p) {
           const int n = to_count(__ldg(mat + address(jj, t)), log_c);
-          if (out_rgba) out_rgba[p] = my_lut[n * 32];
+          if (out_rgba) out_rgba[p] = lut_at(n);
           if (out_idx) out_idx[p] = (uint16_t)count_to_index(n);
           if (++t == nt) t = 0, ++jj;
         }
