@@ -11,9 +11,12 @@
 //   segment   = up to 1024 pixels of one scanline = one warp = one fixed-Huffman block that ends
 //               with an empty stored block (the zlib "sync flush": byte aligned, so segments
 //               concatenate bytewise into a valid stream in any quantity)
-//   tokens    = per pixel: identical to the previous pixel of the filtered line -> it extends a
-//               (distance 4) match, else four literals.  After the Up filter repeated rows,
-//               gaps and flat areas are runs of zero pixels, i.e. long matches.
+//   filter    = per scanline, from the geometry alone: a line that repeats the one above (energy rows
+//               are drawn `rep` times; gaps) takes filter 2 (Up) and becomes zeros, a line with new
+//               content takes filter 0 and keeps its pixels -- at most 259 distinct LUT colours
+//   tokens    = per pixel: equal to its left neighbour -> it extends a distance-4 match; else equal
+//               to one of the 32 pixels before it -> a match at that distance (extended while the
+//               following pixels keep matching); else four literals.
 //   lanes     = 32 pixels each, encoded into private bit buffers; a warp prefix sum over the bit
 //               counts places them in the segment's stream (shared-memory atomicOr)
 //   adler32   = per segment (sum, weighted sum) of the filtered bytes, combined in order on the host
@@ -33,12 +36,15 @@ constexpr int kPixStride = 33;       // padded piece stride (words): conflict-fr
 constexpr int kTokWords = 37;        // per-lane token buffer: 32 pixels x 36 bits + header / trailer bits
 constexpr int kMergedWords = kPieces * kTokWords + 4;
 constexpr int kWarpsPerBlock = 4;
+constexpr int kMatchWindow = 32;     // pixels a match may reach back (distance <= 128 bytes)
 
 struct HuffTables {
   unsigned short lit_code[256];  // bit-reversed fixed-Huffman code of a literal byte
   unsigned char lit_len[256];    // 8 or 9
-  unsigned int match_code[65];   // match of 4*n bytes at distance 4: length code + extra bits + distance code
-  unsigned char match_len[65];
+  unsigned short len_code[65];   // match length 4*n bytes: fixed-Huffman length code + extra bits (<= 13 bits)
+  unsigned char len_len[65];
+  unsigned short dist_code[33];  // match distance 4*k bytes: 5-bit distance code + extra bits (<= 10 bits)
+  unsigned char dist_len[33];
 };
 __constant__ HuffTables c_huff;
 
@@ -102,14 +108,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     in_up = row - 1 >= t.y && row - 1 < t.y + h;
   }
   const unsigned mask_cur = __ballot_sync(0xffffffffu, in_cur), mask_up = __ballot_sync(0xffffffffu, in_up);
+  // does this scanline repeat the one above?  (same tiles, same raster row of each: a function of the
+  // tile table and the row only, so every segment of the line decides alike)
+  bool differs = false;
+  if (lane < cv.tile_count) {
+    const csg_png_tile t = tl[lane];
+    differs = in_cur != in_up || (in_cur && (row - t.y) / t.rep != (row - 1 - t.y) / t.rep);
+  }
+  const bool repeat = row > 0 && !__any_sync(0xffffffffu, differs);
+  const unsigned filter_type = repeat ? 2u : 0u;
 
   // ---- phase 1: compose + Up filter (coalesced), Adler partial sums
   unsigned* pix = s_pix[warp];
   unsigned long long sa = 0, sb = 0;
   for (int p = lane; p < npx; p += 32) {
-    const unsigned cur = mosaic_pixel(rgba, tl, vlines, mask_cur, x0 + p, row, cv.background);
-    const unsigned up = row > 0 ? mosaic_pixel(rgba, tl, vlines, mask_up, x0 + p, row - 1, cv.background) : 0u;
-    const unsigned f = sub4(cur, up);
+    // a repeated line is all zeros after the Up filter (identical content by construction)
+    const unsigned f = repeat ? 0u : mosaic_pixel(rgba, tl, vlines, mask_cur, x0 + p, row, cv.background);
     pix[(p >> 5) * kPixStride + (p & 31)] = f;
     const unsigned b0 = f & 255u, b1 = (f >> 8) & 255u, b2 = (f >> 16) & 255u, b3 = f >> 24;
     const unsigned t0 = (has_filter ? 1u : 0u) + 4u * (unsigned)p;  // position of b0 inside the segment
@@ -117,7 +131,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     sb += (unsigned long long)(n_raw - t0) * b0 + (unsigned long long)(n_raw - t0 - 1) * b1 +
           (unsigned long long)(n_raw - t0 - 2) * b2 + (unsigned long long)(n_raw - t0 - 3) * b3;
   }
-  if (lane == 0 && has_filter) sa += 2u, sb += 2ull * (unsigned long long)n_raw;  // the filter-type byte (2 = Up)
+  if (lane == 0 && has_filter) sa += filter_type, sb += (unsigned long long)filter_type * (unsigned long long)n_raw;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
@@ -140,32 +154,44 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   };
   if (lane == 0) {
     put(2u, 3);  // BFINAL = 0, BTYPE = 01 (fixed Huffman)
-    if (has_filter) put(c_huff.lit_code[2], c_huff.lit_len[2]);
+    if (has_filter) put(c_huff.lit_code[filter_type], c_huff.lit_len[filter_type]);
   }
   const int p_begin = lane * kPiecePixels, p_end = min(npx, p_begin + kPiecePixels);
   if (p_begin < npx) {
-    // a run may start on the last pixel of the previous lane's piece (distance 4 reaches back into it)
-    unsigned prev = p_begin > 0 ? pix[((p_begin - 1) >> 5) * kPixStride + ((p_begin - 1) & 31)] : 0u;
-    bool have_prev = p_begin > 0;
-    int run = 0;
-    const unsigned* mine = pix + lane * kPixStride;
+    // pixel q of the segment (any lane's piece): matches may reach back into earlier pieces
+    auto at = [&](int q) { return pix[(q >> 5) * kPixStride + (q & 31)]; };
+    int run = 0, dist = 0;  // an open match of `run` pixels at distance `dist` pixels
+    auto flush = [&]() {
+      if (run) {
+        put((unsigned)c_huff.len_code[run] | ((unsigned)c_huff.dist_code[dist] << c_huff.len_len[run]),
+            c_huff.len_len[run] + c_huff.dist_len[dist]);
+        run = 0;
+      }
+    };
     for (int p = p_begin; p < p_end; ++p) {
-      const unsigned x = mine[p - p_begin];
-      if (have_prev && x == prev) {
+      const unsigned x = at(p);
+      if (run && x == at(p - dist)) {  // the open match goes on (run <= 32 pixels = 128 bytes)
         ++run;
         continue;
       }
-      if (run) {
-        put(c_huff.match_code[run], c_huff.match_len[run]);
-        run = 0;
+      flush();
+      int k = 0;
+      const int reach = p < kMatchWindow ? p : kMatchWindow;
+      for (int d = 1; d <= reach; ++d)
+        if (at(p - d) == x) {
+          k = d;
+          break;
+        }
+      if (k) {
+        run = 1, dist = k;
+        continue;
       }
       const unsigned b0 = x & 255u, b1 = (x >> 8) & 255u, b2 = (x >> 16) & 255u, b3 = x >> 24;
       // two puts of <= 18 bits: the 64-bit accumulator holds < 32 pending bits
       put(c_huff.lit_code[b0] | ((unsigned)c_huff.lit_code[b1] << c_huff.lit_len[b0]), c_huff.lit_len[b0] + c_huff.lit_len[b1]);
       put(c_huff.lit_code[b2] | ((unsigned)c_huff.lit_code[b3] << c_huff.lit_len[b2]), c_huff.lit_len[b2] + c_huff.lit_len[b3]);
-      prev = x, have_prev = true;
     }
-    if (run) put(c_huff.match_code[run], c_huff.match_len[run]);  // run <= 32 pixels = 128 bytes
+    flush();
   }
   const bool last_lane = p_begin < npx && p_end == npx;
   if (last_lane) put(0u, 7 + 3);  // end-of-block (7 zero bits) + header of the empty stored block (000)
@@ -241,12 +267,11 @@ void build_tables(HuffTables* t) {
   // RFC 1951 3.2.5: length codes 257..285 (base length, extra bits)
   static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-  t->match_code[0] = 0, t->match_len[0] = 0;
+  t->len_code[0] = 0, t->len_len[0] = 0;
   for (int n = 1; n <= 64; ++n) {
     const int len = 4 * n;
     int c = 28;
     while (c > 0 && base[c] > len) --c;
-    if (c == 28 && len != 258) c = 27;
     const int sym = 257 + c;
     unsigned bits;
     int nb;
@@ -259,10 +284,22 @@ void build_tables(HuffTables* t) {
     }
     bits |= (unsigned)(len - base[c]) << nb;  // extra bits: plain binary, LSB first
     nb += extra[c];
-    bits |= reverse_bits(3u, 5) << nb;  // distance 4 = distance code 3 (no extra bits), 5-bit fixed code
-    nb += 5;
-    t->match_code[n] = bits;
-    t->match_len[n] = (unsigned char)nb;
+    t->len_code[n] = (unsigned short)bits;
+    t->len_len[n] = (unsigned char)nb;
+  }
+  // RFC 1951 3.2.5: distance codes 0..29 (base distance, extra bits); fixed code = 5 bits, reversed
+  static const int dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  static const int dextra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  t->dist_code[0] = 0, t->dist_len[0] = 0;
+  for (int k = 1; k <= 32; ++k) {
+    const int d = 4 * k;
+    int c = 29;
+    while (c > 0 && dbase[c] > d) --c;
+    unsigned bits = reverse_bits((unsigned)c, 5);
+    bits |= (unsigned)(d - dbase[c]) << 5;
+    t->dist_code[k] = (unsigned short)bits;
+    t->dist_len[k] = (unsigned char)(5 + dextra[c]);
   }
 }
 
