@@ -20,7 +20,6 @@ import numpy as np
 
 from .. import _lib
 from ..engine import Batch
-from ..logging_utils import log_exception
 from .constants import DEFAULT_INSTRUMENT_ORDER, DEFAULT_PITCH_ANGLE_CATEGORIES, PITCH_ANGLE_ROW_KEYS
 
 

@@ -27,7 +27,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from ._lib import POOL_ITEM, POOL_QUERY, POOL_REQUEST, POOL_SEL
+from ._lib import POOL_QUERY, POOL_REQUEST, POOL_SEL
 
 FIRST_BITS = 11
 NEXT_BITS = 10
@@ -252,7 +252,7 @@ class DevicePoolSelector:
         candidates -- ``{"order": int32[n_inst][max_E], "keys": float64[n_inst][max_E],
         "n_keys": int32[n_inst], "limit": int32[n_inst]}`` -- in which case the per-file counts
         are neither gathered nor read back (``result_counts`` is not available)."""
-        from .comm import LocalExchange, NcclExchange, make_exchange
+        from .comm import NcclExchange, make_exchange
 
         comm = comm or SingleRank()
         if exchange is None:

@@ -2,7 +2,6 @@
 the image the host composer builds (figure.SpectrogramFigure.compose -- the oracle of this stage)."""
 
 import io
-import zlib
 
 import numpy as np
 import pytest

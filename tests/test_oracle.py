@@ -1,7 +1,6 @@
 """CPU: pin the oracle (oracle/restate.py) against numpy, the reference's own
 doctest pins, and the golden vectors captured from the unmodified reference."""
 
-import json
 
 import numpy as np
 import pytest
