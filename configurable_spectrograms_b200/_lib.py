@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -168,6 +168,7 @@ SIGNATURES = {
     "csg_event_record": (_i, [_vp, _i]),
     "csg_event_sync": (_i, [_vp, _i]),
     "csg_collapse_kernel": (_i, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp]),
+    "csg_collapse_kernel_for": (_i, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i]),
     "csg_pitch_runs": (_i, [_vp, _i, _i, _vp, _vp]),
     "csg_collapse_blocks": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i, _i, _i]),
     "csg_sums_elems": (_i64, [C.c_int32, C.c_int32, _i]),

@@ -533,6 +533,100 @@ __global__ void collapse_tep_kernel(const csg_file_desc* __restrict__ files, int
   }
 }
 
+// ---------------------------------------------------------------------------------
+// layout TEP, total only (no pitch-angle groups), 8 <= P <= 128, P % 8 == 0: the generic stress cubes
+// of BASELINE config 5.  numpy sums a contiguous axis of n <= 128 elements with eight interleaved
+// accumulators r[k] += a[8j + k] and combines them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Two
+// lanes share a (t, e) row: lane h owns r[4h .. 4h+3], i.e. the float4 at 8j + 4h of every group of
+// eight -- P/8 independent 128-bit loads per lane, all in flight, 32-byte segments of 16 rows per
+// warp instruction.  A block owns 32 consecutive time steps x every energy (one contiguous slab
+// of the cube), stages the sums [e][t] in shared memory and writes 128-byte rows of the
+// energy-major output; it also owns the zoom flags of its time steps.
+// ---------------------------------------------------------------------------------
+constexpr int kTepTile = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    collapse_tep_rows_kernel(const csg_file_desc* __restrict__ files, int n_files, T* __restrict__ sums,
+                             uint8_t* __restrict__ row_flags) {
+  constexpr int V = VecOf<T>::N;       // elements per 16-byte load
+  constexpr int LPR = 8 / V;           // lanes per row: each lane owns V of the eight accumulators
+  constexpr int RPW = 32 / LPR;        // rows per warp pass
+  constexpr int MAXJ = 16;             // P <= 128
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_out = reinterpret_cast<T*>(smem_raw);  // [E][kTepTile + 1]
+  __shared__ unsigned s_flags[kTepTile];
+
+  const int fi = find_file(files, n_files, blockIdx.x);
+  const csg_file_desc f = files[fi];
+  const int P = f.P, E = f.E, nj = P / 8;
+  const int t0 = (blockIdx.x - f.first_block) * kTepTile;
+  const int nt = min(kTepTile, f.T - t0);
+  const long long n_rows = (long long)nt * E;  // rows (t, e) of this tile: one contiguous slab
+  const T* slab = static_cast<const T*>(f.d_cube) + (long long)t0 * E * P;
+  if (threadIdx.x < kTepTile) s_flags[threadIdx.x] = 0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int sub = lane / LPR, h = lane % LPR;
+  for (long long base = (long long)warp * RPW; base < n_rows; base += (long long)n_warps * RPW) {
+    const long long row = base + sub;
+    const bool in = row < n_rows;
+    const T* q = slab + (in ? row : 0) * P + h * V;
+    Chunk<T, V> x[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (j < nj) load_chunk(x[j], q + 8 * j, true, V);
+    T r[V];
+    bool any = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const bool ok = !is_nan(x[0].v[v]);
+      any |= ok;
+      r[v] = ok ? x[0].v[v] : T(0);
+    }
+#pragma unroll
+    for (int j = 1; j < MAXJ; ++j)
+      if (j < nj) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const bool ok = !is_nan(x[j].v[v]);
+          any |= ok;
+          r[v] = add_rn(r[v], ok ? x[j].v[v] : T(0));
+        }
+      }
+    // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)): pairs inside the lane first, then across the row's lanes
+    T s;
+    if (V == 4) {
+      s = add_rn(add_rn(r[0], r[1]), add_rn(r[V - 2], r[V - 1]));
+      s = add_rn(s, __shfl_down_sync(0xffffffffu, s, 1));  // lane h=0 holds left + right
+    } else {  // V == 2: four lanes per row own (r0,r1) (r2,r3) (r4,r5) (r6,r7)
+      s = add_rn(r[0], r[V - 1]);
+      s = add_rn(s, __shfl_down_sync(0xffffffffu, s, 1));  // h=0: (r0+r1)+(r2+r3); h=2: (r4+r5)+(r6+r7)
+      s = add_rn(s, __shfl_down_sync(0xffffffffu, s, 2));  // h=0: left + right
+    }
+    unsigned okmask = __ballot_sync(0xffffffffu, any);
+    if (in && h == 0) {
+      const int tl = (int)(row / E), e = (int)(row - (long long)tl * E);
+      s_out[e * (kTepTile + 1) + tl] = add_rn(T(0), s);  // the reduction is seeded with +0.0
+      if ((okmask >> (lane & ~(LPR - 1))) & ((1u << LPR) - 1u)) atomicOr(&s_flags[tl], 1u);
+    }
+  }
+  __syncthreads();
+  const int Tp = pitch_of(f.T);
+  T* out = sums + f.sums_off + t0;
+  const int tl = threadIdx.x & (kTepTile - 1);
+  if (tl < nt)
+    for (int e = threadIdx.x / kTepTile; e < E; e += blockDim.x / kTepTile) out[(long long)e * Tp + tl] = s_out[e * (kTepTile + 1) + tl];
+  if (row_flags != nullptr && threadIdx.x < nt && s_flags[threadIdx.x])
+    row_flags[f.flags_off + t0 + threadIdx.x] = (uint8_t)s_flags[threadIdx.x];  // the block owns these time steps
+}
+
+inline bool tep_rows_ok(int32_t T, int32_t P, int32_t E, const void* d_cube, int n_groups) {
+  return n_groups == 0 && T > 0 && P >= 8 && P <= 128 && P % 8 == 0 && E > 0 && E <= 1024 &&
+         (reinterpret_cast<uintptr_t>(d_cube) & 15) == 0;
+}
+
 // warp = one zoom window: any row with the group's bit set?
 __global__ void window_any_kernel(const uint8_t* __restrict__ row_flags, const csg_flag_window* __restrict__ windows,
                                   int n_windows, const int32_t* __restrict__ pool, uint8_t* __restrict__ out) {
@@ -685,7 +779,11 @@ int launch_tep(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, int tota
 extern "C" {
 
 int csg_collapse_kernel(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube) {
-  if (layout == CSG_LAYOUT_TEP) return CSG_K1_GENERIC;
+  return csg_collapse_kernel_for(T, P, E, dtype, layout, d_cube, /*n_groups: unknown, assume some*/ 1);
+}
+
+int csg_collapse_kernel_for(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube, int n_groups) {
+  if (layout == CSG_LAYOUT_TEP) return tep_rows_ok(T, P, E, d_cube, n_groups) ? CSG_K1_STREAM : CSG_K1_GENERIC;
   return stream_file_ok(T, P, E, dtype, d_cube) ? CSG_K1_STREAM : CSG_K1_GENERIC;
 }
 
@@ -708,6 +806,7 @@ int csg_pitch_runs(const uint8_t* h_pa_bits, int P, int n_groups, int32_t* h_run
 int32_t csg_collapse_blocks(int32_t T, int32_t P, int32_t E, int dtype, int layout, int kernel) {
   if (T <= 0 || E <= 0) return 0;
   if (layout == CSG_LAYOUT_TEP) {
+    if (kernel == CSG_K1_STREAM) return (T + kTepTile - 1) / kTepTile;
     const int rows = tep_rows_per_block(P, dtype);
     return (int32_t)(((long long)T * E + rows - 1) / rows);
   }
@@ -755,6 +854,20 @@ int csg_collapse_range(csg_ctx* ctx, const csg_file_desc* d_files, int n_files, 
     return launch_tpe<double>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, (double*)d_sums, d_row_flags);
   }
   if (block_offset != 0) return csg_fail(ctx, CSG_ERR_ARG, "block sub-ranges are only supported by the stream kernel");
+  if (kernel == CSG_K1_STREAM) {  // the row kernel: total only, 8 <= P <= 128, P % 8 == 0 (csg_collapse_kernel_for)
+    if (n_groups != 0 || max_P > 128 || max_P % 8 != 0)
+      return csg_fail(ctx, CSG_ERR_ARG, "the TEP row kernel needs n_groups = 0 and P a multiple of 8 up to 128");
+    const size_t smem = (size_t)max_E * (kTepTile + 1) * (dtype == CSG_F64 ? 8 : 4);
+    if (dtype == CSG_F32) {
+      cudaFuncSetAttribute(collapse_tep_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      collapse_tep_rows_kernel<float><<<total_blocks, 256, smem, ctx->stream>>>(d_files, n_files, (float*)d_sums, d_row_flags);
+    } else {
+      cudaFuncSetAttribute(collapse_tep_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      collapse_tep_rows_kernel<double><<<total_blocks, 256, smem, ctx->stream>>>(d_files, n_files, (double*)d_sums, d_row_flags);
+    }
+    CSG_LAUNCH_CHECK(ctx, "collapse_tep_rows_kernel");
+    return CSG_OK;
+  }
   if (dtype == CSG_F32)
     return launch_tep<float>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (float*)d_sums, d_row_flags);
   return launch_tep<double>(ctx, d_files, n_files, total_blocks, d_pa_bits, n_groups, max_P, dtype, (double*)d_sums, d_row_flags);

@@ -194,7 +194,7 @@ class Batch:
                 continue
             if f["device_ptr"] is None:
                 raise CsgError("cube not on the device: call upload_cubes() first")
-            kern = lib.csg_collapse_kernel(f["T"], f["P"], f["E"], self.code, f["layout"], f["device_ptr"])
+            kern = lib.csg_collapse_kernel_for(f["T"], f["P"], f["E"], self.code, f["layout"], f["device_ptr"], self.G)
             # every file of a stream-kernel table shares one energy count (it fixes the block shape)
             groups.setdefault((f["layout"], kern, f["E"] if kern == _lib.K1_STREAM else 0), []).append(i)
         # runs of constant pitch-angle group membership (stream kernel), one entry per distinct table
@@ -261,7 +261,7 @@ class Batch:
         if len(self.d_files) != 1:
             return None
         (layout, kern, _e), (_tab, n, blocks, _mp, _me) = next(iter(self.d_files.items()))
-        if kern != _lib.K1_STREAM or n != len(self.files):
+        if kern != _lib.K1_STREAM or layout != _lib.LAYOUT_TPE or n != len(self.files):
             return None
         per_file = [self.ctx.lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout, kern) for f in self.files]
         first = np.concatenate([[0], np.cumsum(per_file)])

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 12
+#define CSG_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -128,6 +128,10 @@ typedef struct {
  * a STREAM table has the same E (= max_E). */
 enum { CSG_K1_GENERIC = 0, CSG_K1_STREAM = 1 };
 CSG_API int csg_collapse_kernel(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube);
+/* The same choice when the number of pitch-angle groups is known: a stored (T,E,P) view with no
+ * groups, 8 <= P <= 128 and P % 8 == 0 takes the row kernel (CSG_K1_STREAM for layout TEP). */
+CSG_API int csg_collapse_kernel_for(int32_t T, int32_t P, int32_t E, int dtype, int layout, const void* d_cube,
+                            int n_groups);
 /* Host helper: runs of constant group membership along the pitch axis as {p0, p1, mask} int32
  * triples (at most P of them) for csg_file_desc.reserved[0..1]; *alias (-> reserved[2]) = groups
  * that contain every bin -- their bits are cleared from the masks, the kernel copies the total. */

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""BASELINE config 5: the collapse alone on a generic stress cube (100 000 time x 96 x 64, float32,
+2.46 GB): layout A = C-contiguous (T, P, E) collapsed over axis 1 (stream kernel), layout B = the
+stored (T, E, P) view (pitch contiguous).  Prints achieved GB/s of algorithmic bytes (cube + sums)
+per layout, CUDA-event timed, and checks a slab of the result against numpy bit for bit."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+
+    from configurable_spectrograms_b200 import _lib
+    from configurable_spectrograms_b200.engine import Batch
+
+    T, P, E = 100_000, 96, 64
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = _lib.Context(0, stream=stream.cuda_stream)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    cube = torch.rand((T, P, E), device=dev, generator=gen) * 1000.0
+    cube[torch.rand((T, P, E), device=dev, generator=gen) < 0.005] = float("nan")
+    out = {}
+    for name, layout, shape in (("A_tpe", None, (T, P, E)), ("B_tep_view", _lib.LAYOUT_TEP, (T, P, E))):
+        src = cube if layout is None else cube.transpose(1, 2).contiguous()  # (T, E, P) stored
+        torch.cuda.synchronize()
+        b = Batch(ctx, np.float32, n_groups=0)
+        f = b.add_file(None, None, shape=shape, layout=layout, device_ptr=src.data_ptr())
+        b.upload_cubes()
+        for _ in range(3):
+            b.collapse()
+        ctx.sync()
+        ms = []
+        for _ in range(5):
+            ctx.timer_start(0)
+            b.collapse()
+            ctx.timer_stop(0)
+            ms.append(ctx.timer_ms(0))
+        got = b.sums(f)[:2000]
+        ref_src = cube[:2000].cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            ref = np.nansum(ref_src if layout is None else np.ascontiguousarray(ref_src.transpose(0, 2, 1)).transpose(0, 2, 1), axis=1)
+        exact = bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32)))
+        bytes_ = 4 * (T * P * E + T * E)
+        out[name] = {"ms": float(np.mean(ms)), "gb_per_s": bytes_ / (np.mean(ms) * 1e-3) / 1e9, "bit_exact_vs_numpy_first_2000_rows": exact,
+                     "kernel": "stream" if any(k[1] == _lib.K1_STREAM for k in b.d_files) else "generic/tep"}
+        del b, src
+    print(json.dumps({"workload": "config5 generic stress cube (100000, 96, 64) float32, 2.46 GB", **out}))
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,39 @@ def test_collapse_tep_view_bit_exact(ctx, dtype, shape):
     assert np.array_equal((b.flags(f) & 1).astype(bool), nn.any(axis=(1, 2)))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(37, 8, 5), (70, 128, 3), (33, 64, 17), (5, 96, 96), (64, 16, 32), (2, 24, 2)])
+def test_collapse_tep_row_kernel_total_only(ctx, dtype, shape):
+    """Stored (T,E,P) views without pitch-angle groups (generic cubes, BASELINE config 5) take the
+    two-lanes-per-row kernel: numpy's eight-accumulator pairwise order bit for bit, ragged tiles,
+    all-NaN rows and time steps, several files in one launch."""
+    from configurable_spectrograms_b200 import _lib
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(23)
+    T, P, E = shape
+    b = Batch(ctx, dtype, n_groups=0)
+    views, ids = [], []
+    for k in range(3):
+        Tk = T + 7 * k
+        stored = _rand_cube(rng, (Tk, E, P), dtype, nan=0.1)
+        stored[rng.integers(0, Tk)] = np.nan  # a time step without a single sample
+        stored[:, rng.integers(0, E), :] = np.nan  # a dead energy row
+        if k == 1:
+            stored[0, 0, :] = -0.0  # a row that sums to zero: the reduction is seeded with +0.0
+        view = np.transpose(stored, (0, 2, 1))
+        views.append(view)
+        ids.append(b.add_file(view))
+    b.upload_cubes()
+    b.collapse()
+    assert all(k[0] == _lib.LAYOUT_TEP and k[1] == _lib.K1_STREAM for k in b.d_files), "expected the TEP row kernel"
+    for view, f in zip(views, ids):
+        with np.errstate(invalid="ignore"):
+            ref = np.nansum(view, axis=1)
+        assert same_bits(b.sums(f, 0), ref, zero_sign_insensitive=False)
+        assert np.array_equal((b.flags(f) & 1).astype(bool), (~np.isnan(view)).any(axis=(1, 2)))
+
+
 def test_collapse_ragged_batch_and_host_entry(ctx):
     from configurable_spectrograms_b200.engine import Batch, collapse_host, nansum
 
