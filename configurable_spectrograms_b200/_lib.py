@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -124,6 +124,11 @@ PNG_CANVAS = np.dtype(
     [("W", "<i4"), ("H", "<i4"), ("tile_first", "<i4"), ("tile_count", "<i4"), ("background", "<u4"),
      ("seg_first", "<i4"), ("segs_per_row", "<i4"), ("pad", "<i4")], align=True
 )
+PNG_TABLES = np.dtype(
+    [("lit_code", "<u2", (256,)), ("lit_len", "u1", (256,)), ("len_code", "<u4", (65,)), ("dist_code", "<u4", (129,)),
+     ("len_sym", "<u2", (65,)), ("len_len", "u1", (65,)), ("dist_len", "u1", (129,)), ("dist_sym", "u1", (129,)),
+     ("eob_len", "u1"), ("eob_code", "<u2"), ("header_bits", "<i4"), ("header", "<u4", (40,))], align=True
+)
 assert PNG_TILE.itemsize == 40 and PNG_VLINE.itemsize == 16 and PNG_CANVAS.itemsize == 32
 POOL_REQUEST = np.dtype([("inst", "<i4"), ("mode", "<i4"), ("p", "<f8")], align=True)
 POOL_SEL = np.dtype(
@@ -188,6 +193,9 @@ SIGNATURES = {
     "csg_pool_energy_candidates": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "csg_pool_pack_results": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]),
     "csg_pool_reduce_max": (_i, [_vp, _vp, _i, _i, _vp]),
+    "csg_png_fixed_tables": (_i, [_vp]),
+    "csg_png_set_tables": (_i, [_vp, _vp]),
+    "csg_png_count": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "csg_png_slot_bytes": (C.c_int32, []),
     "csg_png_segments": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_png_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),

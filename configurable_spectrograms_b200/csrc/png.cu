@@ -15,7 +15,7 @@
 //               are drawn `rep` times; gaps) takes filter 2 (Up) and becomes zeros, a line with new
 //               content takes filter 0 and keeps its pixels -- at most 259 distinct LUT colours
 //   tokens    = per pixel: equal to its left neighbour -> it extends a distance-4 match; else equal
-//               to one of the 32 pixels before it -> a match at that distance (extended while the
+//               to one of the 128 pixels before it -> a match at that distance (extended while the
 //               following pixels keep matching); else four literals.
 //   lanes     = 32 pixels each, encoded into private bit buffers; a warp prefix sum over the bit
 //               counts places them in the segment's stream (shared-memory atomicOr)
@@ -30,22 +30,21 @@
 namespace {
 
 constexpr int kSegPixels = 1024;
+constexpr int kMatchWindow = 128;    // pixels a match may reach back (distance <= 512 bytes)
 constexpr int kPieces = 32;          // lanes
 constexpr int kPiecePixels = 32;     // pixels per lane
 constexpr int kPixStride = 33;       // padded piece stride (words): conflict-free column reads
 constexpr int kTokWords = 37;        // per-lane token buffer: 32 pixels x 36 bits + header / trailer bits
-constexpr int kMergedWords = kPieces * kTokWords + 4;
+constexpr int kHeaderWords = 40;     // block header (BFINAL/BTYPE + a dynamic block's code lengths): <= 160 bytes
+constexpr int kMergedWords = kPieces * kTokWords + kHeaderWords + 4;
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMatchWindow = 32;     // pixels a match may reach back (distance <= 128 bytes)
 
-struct HuffTables {
-  unsigned short lit_code[256];  // bit-reversed fixed-Huffman code of a literal byte
-  unsigned char lit_len[256];    // 8 or 9
-  unsigned short len_code[65];   // match length 4*n bytes: fixed-Huffman length code + extra bits (<= 13 bits)
-  unsigned char len_len[65];
-  unsigned short dist_code[33];  // match distance 4*k bytes: 5-bit distance code + extra bits (<= 10 bits)
-  unsigned char dist_len[33];
-};
+// The code tables of one batch of figures (csg_png_tables in csgpu.h): either RFC 1951's fixed codes
+// or a custom (dynamic-block) code built by the host from the batch's own symbol counts.  Codes are
+// stored bit-reversed, ready to be OR-ed into the LSB-first stream; match entries hold the Huffman
+// code followed by the extra bits.  Literal / length codes are limited to 9 bits, so a pixel never
+// costs more than with the fixed code and the buffer sizes below hold for both.
+typedef csg_png_tables HuffTables;
 __constant__ HuffTables c_huff;
 
 __device__ __forceinline__ unsigned sub4(unsigned a, unsigned b) { return __vsub4(a, b); }
@@ -76,12 +75,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     png_encode_kernel(const uint32_t* __restrict__ rgba, const csg_png_canvas* __restrict__ canvases, int n_canvases,
                       const csg_png_tile* __restrict__ tiles, const csg_png_vline* __restrict__ vlines, int n_segments,
                       unsigned char* __restrict__ slots, int slot_bytes, int32_t* __restrict__ sizes,
-                      uint32_t* __restrict__ adler) {
+                      uint32_t* __restrict__ adler, unsigned* __restrict__ counts, int count_stride) {
+  // counts != NULL: no output, only the symbol statistics of every count_stride-th segment
+  // (literal / length symbols 0..285, then distance symbols 0..29) for the host's custom code
+  __shared__ unsigned s_counts[kWarpsPerBlock][286 + 30];
+  if (counts) {
+    for (int i = threadIdx.x; i < kWarpsPerBlock * (286 + 30); i += blockDim.x) (&s_counts[0][0])[i] = 0;
+    __syncthreads();
+  }
   __shared__ unsigned s_pix[kWarpsPerBlock][kMergedWords];  // filtered pixels (padded pieces), then the merged stream
   __shared__ unsigned s_tok[kWarpsPerBlock][kPieces * kTokWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * kWarpsPerBlock + warp;
-  if (seg >= n_segments) return;
+  const int seg = (blockIdx.x * kWarpsPerBlock + warp) * (counts ? count_stride : 1);
+  const bool active = seg < n_segments;
+  if (!active && !counts) return;
+  if (active) {
   // ---- which canvas / scanline / chunk
   int lo = 0, hi = n_canvases - 1;
   while (lo < hi) {
@@ -152,9 +160,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
       nacc -= 32;
     }
   };
-  if (lane == 0) {
-    put(2u, 3);  // BFINAL = 0, BTYPE = 01 (fixed Huffman)
-    if (has_filter) put(c_huff.lit_code[filter_type], c_huff.lit_len[filter_type]);
+  unsigned* cnt = counts ? s_counts[warp] : nullptr;
+  // (the block header -- BFINAL / BTYPE and, for a custom code, its code lengths -- is the same bit
+  // string for every segment: it is copied in front of the lanes' bits in the merge phase)
+  if (lane == 0 && has_filter) {
+    if (cnt) atomicAdd(&cnt[filter_type], 1u);
+    put(c_huff.lit_code[filter_type], c_huff.lit_len[filter_type]);
   }
   const int p_begin = lane * kPiecePixels, p_end = min(npx, p_begin + kPiecePixels);
   if (p_begin < npx) {
@@ -163,8 +174,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     int run = 0, dist = 0;  // an open match of `run` pixels at distance `dist` pixels
     auto flush = [&]() {
       if (run) {
-        put((unsigned)c_huff.len_code[run] | ((unsigned)c_huff.dist_code[dist] << c_huff.len_len[run]),
-            c_huff.len_len[run] + c_huff.dist_len[dist]);
+        if (cnt) {
+          atomicAdd(&cnt[c_huff.len_sym[run]], 1u);
+          atomicAdd(&cnt[286 + c_huff.dist_sym[dist]], 1u);
+        }
+        put(c_huff.len_code[run], c_huff.len_len[run]);   // <= 14 bits
+        put(c_huff.dist_code[dist], c_huff.dist_len[dist]);  // <= 14 bits
         run = 0;
       }
     };
@@ -187,6 +202,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         continue;
       }
       const unsigned b0 = x & 255u, b1 = (x >> 8) & 255u, b2 = (x >> 16) & 255u, b3 = x >> 24;
+      if (cnt) {
+        atomicAdd(&cnt[b0], 1u);
+        atomicAdd(&cnt[b1], 1u);
+        atomicAdd(&cnt[b2], 1u);
+        atomicAdd(&cnt[b3], 1u);
+      }
       // two puts of <= 18 bits: the 64-bit accumulator holds < 32 pending bits
       put(c_huff.lit_code[b0] | ((unsigned)c_huff.lit_code[b1] << c_huff.lit_len[b0]), c_huff.lit_len[b0] + c_huff.lit_len[b1]);
       put(c_huff.lit_code[b2] | ((unsigned)c_huff.lit_code[b3] << c_huff.lit_len[b2]), c_huff.lit_len[b2] + c_huff.lit_len[b3]);
@@ -194,7 +215,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     flush();
   }
   const bool last_lane = p_begin < npx && p_end == npx;
-  if (last_lane) put(0u, 7 + 3);  // end-of-block (7 zero bits) + header of the empty stored block (000)
+  if (last_lane) {
+    if (cnt) atomicAdd(&cnt[256], 1u);
+    put(c_huff.eob_code, c_huff.eob_len + 3);  // end-of-block, then the header of the empty stored block (000)
+  }
   if (nacc) tok[nwords] = (unsigned)acc;
   const int my_bits = nwords * 32 + nacc;
 
@@ -205,13 +229,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  const int total_bits = __shfl_sync(0xffffffffu, incl, 31);
-  const int off = incl - my_bits;
+  const int hdr_bits = c_huff.header_bits;
+  const int total_bits = hdr_bits + __shfl_sync(0xffffffffu, incl, 31);
+  const int off = hdr_bits + incl - my_bits;
+  if (!counts) {
   __syncwarp();  // every lane is done reading pixels: the buffer becomes the merged stream
   unsigned* out = s_pix[warp];
   const int total_bytes = (total_bits + 7) / 8 + 4;  // pad to a byte, then LEN = 0000, NLEN = FFFF
   const int total_words = (total_bytes + 3) / 4;
-  for (int w = lane; w < total_words; w += 32) out[w] = 0u;
+  // the block header first (same bits for every segment), zeros behind it
+  const int hdr_words = (hdr_bits + 31) / 32;
+  for (int w = lane; w < total_words; w += 32) out[w] = w < hdr_words ? c_huff.header[w] : 0u;
   __syncwarp();
   const int my_words = (my_bits + 31) / 32;
   const int w0 = off >> 5, sh = off & 31;
@@ -234,6 +262,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     adler[2 * seg] = (unsigned)(sa % 65521ull);
     adler[2 * seg + 1] = (unsigned)(sb % 65521ull);
   }
+  }  // output mode
+  }  // active
+  if (counts) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 286 + 30; i += blockDim.x) {
+      unsigned n = 0;
+      for (int w = 0; w < kWarpsPerBlock; ++w) n += s_counts[w][i];
+      if (n) atomicAdd(&counts[i], n);
+    }
+  }
 }
 
 // warp per segment: slot -> its place in the packed stream
@@ -254,7 +292,8 @@ unsigned reverse_bits(unsigned v, int n) {
   return r;
 }
 
-void build_tables(HuffTables* t) {
+void build_fixed_tables(HuffTables* t) {
+  memset(t, 0, sizeof(*t));
   for (int v = 0; v < 256; ++v) {
     if (v < 144) {
       t->lit_code[v] = (unsigned short)reverse_bits(0x30u + v, 8);
@@ -267,7 +306,6 @@ void build_tables(HuffTables* t) {
   // RFC 1951 3.2.5: length codes 257..285 (base length, extra bits)
   static const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   static const int extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-  t->len_code[0] = 0, t->len_len[0] = 0;
   for (int n = 1; n <= 64; ++n) {
     const int len = 4 * n;
     int c = 28;
@@ -284,24 +322,31 @@ void build_tables(HuffTables* t) {
     }
     bits |= (unsigned)(len - base[c]) << nb;  // extra bits: plain binary, LSB first
     nb += extra[c];
-    t->len_code[n] = (unsigned short)bits;
+    t->len_code[n] = bits;
     t->len_len[n] = (unsigned char)nb;
+    t->len_sym[n] = (unsigned short)sym;
   }
   // RFC 1951 3.2.5: distance codes 0..29 (base distance, extra bits); fixed code = 5 bits, reversed
   static const int dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
                                 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
   static const int dextra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-  t->dist_code[0] = 0, t->dist_len[0] = 0;
-  for (int k = 1; k <= 32; ++k) {
+  for (int k = 1; k <= kMatchWindow; ++k) {
     const int d = 4 * k;
     int c = 29;
     while (c > 0 && dbase[c] > d) --c;
     unsigned bits = reverse_bits((unsigned)c, 5);
     bits |= (unsigned)(d - dbase[c]) << 5;
-    t->dist_code[k] = (unsigned short)bits;
+    t->dist_code[k] = bits;
     t->dist_len[k] = (unsigned char)(5 + dextra[c]);
+    t->dist_sym[k] = (unsigned char)c;
   }
+  t->eob_code = 0, t->eob_len = 7;
+  t->header[0] = 2u, t->header_bits = 3;  // BFINAL = 0, BTYPE = 01 (fixed Huffman)
 }
+
+bool g_tables_ready[64] = {false};
+bool ctx_tables_ready(csg_ctx* ctx) { return g_tables_ready[ctx->device & 63]; }
+void ctx_tables_set(csg_ctx* ctx) { g_tables_ready[ctx->device & 63] = true; }
 
 }  // namespace
 
@@ -309,12 +354,52 @@ extern "C" {
 
 int32_t csg_png_slot_bytes(void) {
   // 3 header bits + filter literal + 1024 pixels x 36 bits + EOB + stored header, padded, + LEN/NLEN, word rounded
-  return (int32_t)(((3 + 9 + kSegPixels * 36 + 10 + 7) / 8 + 4 + 15) / 16 * 16);
+  return (int32_t)(((kHeaderWords * 32 + 9 + kSegPixels * 36 + 15 + 3 + 7) / 8 + 4 + 15) / 16 * 16);
 }
 
 int32_t csg_png_segments(int32_t W, int32_t H) {
   if (W <= 0 || H <= 0) return 0;
   return (int32_t)(((long long)(W + kSegPixels - 1) / kSegPixels) * H);
+}
+
+int csg_png_fixed_tables(csg_png_tables* out) {
+  if (!out) return CSG_ERR_ARG;
+  build_fixed_tables(out);
+  return CSG_OK;
+}
+
+int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables) {
+  if (!ctx) return CSG_ERR_ARG;
+  HuffTables h;
+  if (tables)
+    h = *tables;
+  else
+    build_fixed_tables(&h);
+  if (h.header_bits < 3 || h.header_bits > kHeaderWords * 32 || h.eob_len < 1 || h.eob_len > 15)
+    return csg_fail(ctx, CSG_ERR_ARG, "bad PNG code tables (header %d bits, end-of-block %d bits)", h.header_bits, (int)h.eob_len);
+  for (int v = 0; v < 256; ++v)
+    if (h.lit_len[v] < 1 || h.lit_len[v] > 9) return csg_fail(ctx, CSG_ERR_ARG, "literal %d has a %d-bit code (1..9 allowed)", v, (int)h.lit_len[v]);
+  // stream-ordered: segments already enqueued keep the tables they were launched with
+  CSG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_huff, &h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `h` lives on this stack frame
+  ctx_tables_set(ctx);
+  return CSG_OK;
+}
+
+static int png_launch(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
+                      const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, uint8_t* d_slots,
+                      int32_t* d_sizes, uint32_t* d_adler, uint32_t* d_counts, int count_stride) {
+  if (!ctx_tables_ready(ctx)) {
+    const int st = csg_png_set_tables(ctx, nullptr);
+    if (st != CSG_OK) return st;
+  }
+  const int work = d_counts ? (n_segments + count_stride - 1) / count_stride : n_segments;
+  const int blocks = (work + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  png_encode_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_canvases, n_canvases, d_tiles,
+                                                                     d_vlines, n_segments, d_slots, csg_png_slot_bytes(),
+                                                                     d_sizes, d_adler, d_counts, count_stride);
+  CSG_LAUNCH_CHECK(ctx, "png_encode_kernel");
+  return CSG_OK;
 }
 
 int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
@@ -323,20 +408,16 @@ int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_
   if (!ctx) return CSG_ERR_ARG;
   if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
   if (!d_rgba || !d_canvases || !d_tiles || !d_slots || !d_sizes || !d_adler) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
-  static bool uploaded[64] = {false};
-  if (!uploaded[ctx->device & 63]) {
-    HuffTables h;
-    memset(&h, 0, sizeof(h));
-    build_tables(&h);
-    CSG_CUDA(ctx, cudaMemcpyToSymbol(c_huff, &h, sizeof(h)));
-    uploaded[ctx->device & 63] = true;
-  }
-  const int blocks = (n_segments + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  png_encode_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_canvases, n_canvases, d_tiles,
-                                                                     d_vlines, n_segments, d_slots, csg_png_slot_bytes(),
-                                                                     d_sizes, d_adler);
-  CSG_LAUNCH_CHECK(ctx, "png_encode_kernel");
-  return CSG_OK;
+  return png_launch(ctx, d_rgba, d_canvases, n_canvases, d_tiles, d_vlines, n_segments, d_slots, d_sizes, d_adler, nullptr, 1);
+}
+
+int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
+                  const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, int stride,
+                  uint32_t* d_counts) {
+  if (!ctx) return CSG_ERR_ARG;
+  if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
+  if (!d_rgba || !d_canvases || !d_tiles || !d_counts || stride < 1) return csg_fail(ctx, CSG_ERR_ARG, "bad argument");
+  return png_launch(ctx, d_rgba, d_canvases, n_canvases, d_tiles, d_vlines, n_segments, nullptr, nullptr, nullptr, d_counts, stride);
 }
 
 int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets, int n_segments,

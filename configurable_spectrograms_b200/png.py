@@ -97,6 +97,171 @@ def write_many(jobs, compress_level: int = 6, max_workers: int = 8) -> None:
 # ----------------------------------------------------------------------------------------
 _ADLER = 65521
 
+# RFC 1951 3.2.5 / 3.2.7
+_LEN_BASE = (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258)
+_LEN_EXTRA = (0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0)
+_DIST_BASE = (1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097,
+              6145, 8193, 12289, 16385, 24577)
+_DIST_EXTRA = (0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13)
+_CL_ORDER = (16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15)
+MATCH_PIXELS, WINDOW_PIXELS = 64, 128  # longest match / farthest distance the device tokeniser emits, in pixels
+
+
+def _limited_lengths(freq, maxlen: int) -> list[int]:
+    """Huffman code lengths (<= maxlen) for the symbols with a non-zero count; at least two get a code."""
+    import heapq
+
+    n = len(freq)
+    syms = [s for s in range(n) if freq[s] > 0] or [0]
+    lens = [0] * n
+    if len(syms) == 1:
+        lens[syms[0]] = lens[1 if syms[0] == 0 else 0] = 1
+        return lens
+    weight = {s: max(int(freq[s]), 1) for s in syms}
+    while True:
+        heap = [(w, i, (s,)) for i, (s, w) in enumerate(weight.items())]
+        heapq.heapify(heap)
+        serial, depth = len(heap), dict.fromkeys(syms, 0)
+        while len(heap) > 1:
+            a, b = heapq.heappop(heap), heapq.heappop(heap)
+            for s in a[2] + b[2]:
+                depth[s] += 1
+            serial += 1
+            heapq.heappush(heap, (a[0] + b[0], serial, a[2] + b[2]))
+        if max(depth.values()) <= maxlen:
+            for s, d in depth.items():
+                lens[s] = d
+            return lens
+        weight = {s: (w + 1) // 2 + 1 for s, w in weight.items()}  # flatten the distribution and retry
+
+
+def _canonical_codes(lens) -> list[int]:
+    top = max(lens) if lens else 0
+    per_len = [0] * (top + 2)
+    for length in lens:
+        if length:
+            per_len[length] += 1
+    code, first = 0, [0] * (top + 2)
+    for bits in range(1, top + 1):
+        code = (code + per_len[bits - 1]) << 1
+        first[bits] = code
+    codes = [0] * len(lens)
+    for s, length in enumerate(lens):
+        if length:
+            codes[s] = first[length]
+            first[length] += 1
+    return codes
+
+
+def _reverse(value: int, bits: int) -> int:
+    out = 0
+    for i in range(bits):
+        out |= ((value >> i) & 1) << (bits - 1 - i)
+    return out
+
+
+def _dynamic_header(ll_lens, d_lens) -> tuple[int, int]:
+    """(bits, count) of a dynamic block's header after BFINAL/BTYPE: HLIT, HDIST, HCLEN, the code-length
+    code and the run-length coded lengths of both alphabets (RFC 1951 3.2.7)."""
+    hlit = max(257, max(i for i, l in enumerate(ll_lens) if l) + 1)
+    hdist = max(1, max((i for i, l in enumerate(d_lens) if l), default=0) + 1)
+    seq = list(ll_lens[:hlit]) + list(d_lens[:hdist])
+    items, i = [], 0
+    while i < len(seq):
+        length, j = seq[i], i
+        while j < len(seq) and seq[j] == length:
+            j += 1
+        run = j - i
+        if length == 0:
+            while run >= 11:
+                r = min(run, 138)
+                items.append((18, r - 11, 7))
+                run -= r
+            if run >= 3:
+                items.append((17, run - 3, 3))
+                run = 0
+            items += [(0, 0, 0)] * run
+        else:
+            items.append((length, 0, 0))
+            run -= 1
+            while run >= 3:
+                r = min(run, 6)
+                items.append((16, r - 3, 2))
+                run -= r
+            items += [(length, 0, 0)] * run
+        i = j
+    cl_freq = [0] * 19
+    for s, _x, _n in items:
+        cl_freq[s] += 1
+    cl_lens = _limited_lengths(cl_freq, 7)
+    cl_codes = _canonical_codes(cl_lens)
+    hclen = max(4, max(k for k in range(19) if cl_lens[_CL_ORDER[k]]) + 1)
+    acc, n = 0, 0
+
+    def put(value, bits):
+        nonlocal acc, n
+        acc |= value << n
+        n += bits
+
+    put(hlit - 257, 5), put(hdist - 1, 5), put(hclen - 4, 4)
+    for k in range(hclen):
+        put(cl_lens[_CL_ORDER[k]], 3)
+    for s, x, nx in items:
+        put(_reverse(cl_codes[s], cl_lens[s]), cl_lens[s])
+        if nx:
+            put(x, nx)
+    return acc, n
+
+
+def _symbol_of(value: int, base) -> int:
+    c = len(base) - 1
+    while base[c] > value:
+        c -= 1
+    return c
+
+
+def custom_tables(counts) -> np.ndarray:
+    """``csg_png_tables`` of a dynamic-Huffman code fitted to symbol counts (``csg_png_count``: 286
+    literal / length counts, then 30 distance counts).  Every symbol the device tokeniser can emit gets
+    a code whatever the counts say; literal / length codes use at most 9 bits, distance codes at most 7
+    (the kernel's buffers are sized for that)."""
+    from ._lib import PNG_TABLES
+
+    counts = np.asarray(counts, dtype=np.int64)
+    ll = counts[:286].copy()
+    dd = counts[286:316].copy()
+    ll[:257] += 1  # every literal byte and the end-of-block symbol may occur
+    len_syms = [257 + _symbol_of(4 * n, _LEN_BASE) for n in range(1, MATCH_PIXELS + 1)]
+    dist_syms = [_symbol_of(4 * k, _DIST_BASE) for k in range(1, WINDOW_PIXELS + 1)]
+    for s in set(len_syms):
+        ll[s] += 1
+    for s in set(dist_syms):
+        dd[s] += 1
+    ll_lens, d_lens = _limited_lengths(ll.tolist(), 9), _limited_lengths(dd.tolist(), 7)
+    ll_codes, d_codes = _canonical_codes(ll_lens), _canonical_codes(d_lens)
+    t = np.zeros(1, dtype=PNG_TABLES)[0]
+    for v in range(256):
+        t["lit_code"][v], t["lit_len"][v] = _reverse(ll_codes[v], ll_lens[v]), ll_lens[v]
+    for n in range(1, MATCH_PIXELS + 1):
+        s = len_syms[n - 1]
+        c = s - 257
+        t["len_code"][n] = _reverse(ll_codes[s], ll_lens[s]) | ((4 * n - _LEN_BASE[c]) << ll_lens[s])
+        t["len_len"][n], t["len_sym"][n] = ll_lens[s] + _LEN_EXTRA[c], s
+    for k in range(1, WINDOW_PIXELS + 1):
+        c = dist_syms[k - 1]
+        t["dist_code"][k] = _reverse(d_codes[c], d_lens[c]) | ((4 * k - _DIST_BASE[c]) << d_lens[c])
+        t["dist_len"][k], t["dist_sym"][k] = d_lens[c] + _DIST_EXTRA[c], c
+    t["eob_code"], t["eob_len"] = _reverse(ll_codes[256], ll_lens[256]), ll_lens[256]
+    head, nbits = _dynamic_header(ll_lens, d_lens)
+    head = 0b100 | (head << 3)  # BFINAL = 0, BTYPE = 10 (dynamic Huffman), LSB first
+    nbits += 3
+    if nbits > 40 * 32:
+        raise ValueError("dynamic block header does not fit the device table")
+    t["header_bits"] = nbits
+    for w in range((nbits + 31) // 32):
+        t["header"][w] = (head >> (32 * w)) & 0xFFFFFFFF
+    return t
+
 
 def adler32_of_segments(sum_bytes: np.ndarray, weighted: np.ndarray, lengths: np.ndarray) -> int:
     """Adler-32 of the concatenation of segments from their partial sums: ``sum_bytes[k]`` = sum of
@@ -141,7 +306,7 @@ def _device_tables(figures, row_height, gap, background):
 
 def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, gap: int = 8,
                           background=(255, 255, 255, 255), max_segments: int = 160_000, consume=None,
-                          timings: dict | None = None) -> list[bytes]:
+                          timings: dict | None = None, huffman: str = "custom") -> list[bytes]:
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
     ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
@@ -152,7 +317,10 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
     ``consume(first_figure_index, parts)``: instead of returning the files, hand every group's files
     -- each a list of buffers that alias pinned scratch, valid only during the call -- to the caller
     (``write_figures_device`` writes them straight to disk without assembling them in memory).
-    ``timings`` (optional dict) accumulates host seconds per phase.
+    ``timings`` (optional dict) accumulates host seconds per phase.  ``huffman``: "custom" fits a
+    dynamic-Huffman code to the symbol statistics of the first group of figures (one counting pass of
+    the same tokeniser over every 4th scanline segment) and uses it for the whole call; "fixed" uses
+    RFC 1951's fixed code.
     """
     import time
 
@@ -192,6 +360,20 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         t0 = time.perf_counter()
         table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
         d_canvases = ctx.to_device(table)
+        if k == 0:  # the code of this call
+            if huffman == "custom":
+                d_counts = dev("counts", 316 * 4)
+                d_counts.zero()
+                ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
+                ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_canvases.ptr, len(group), d_tiles.ptr, d_vlines.ptr,
+                                             n_seg, 4, d_counts.ptr))
+                tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
+                ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
+            elif huffman == "fixed":
+                ctx._check(lib.csg_png_set_tables(ctx.handle, None))
+            else:
+                raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
+            t0 = tick("code_tables", t0)
         d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
         ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_canvases.ptr, len(group), d_tiles.ptr, d_vlines.ptr, n_seg,
                                       d_slots.ptr, d_sizes.ptr, d_adler.ptr))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 13
+#define CSG_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -446,6 +446,33 @@ typedef struct {
   int32_t segs_per_row; /* ceil(W / 1024)                                                       */
   int32_t pad;
 } csg_png_canvas; /* 32 bytes */
+/* The DEFLATE code of a batch of figures.  Codes are bit-reversed (ready for the LSB-first stream);
+ * len_code[n] / dist_code[k] = the Huffman code of a match of 4n bytes / at distance 4k bytes followed
+ * by its extra bits; *_len = total bits; *_sym = the symbol (for csg_png_count).  Literal / length
+ * codes may use at most 9 bits, distance codes at most 7.  header = the block header every segment
+ * starts with, BFINAL/BTYPE included: 3 bits for the fixed code, BTYPE=10 + code lengths for a custom
+ * one (png.py builds it from the counts of csg_png_count). */
+typedef struct {
+  uint16_t lit_code[256];
+  uint8_t lit_len[256];
+  uint32_t len_code[65];
+  uint32_t dist_code[129];
+  uint16_t len_sym[65];
+  uint8_t len_len[65];
+  uint8_t dist_len[129];
+  uint8_t dist_sym[129];
+  uint8_t eob_len;
+  uint16_t eob_code;
+  int32_t header_bits;
+  uint32_t header[40];
+} csg_png_tables;
+CSG_API int csg_png_fixed_tables(csg_png_tables* out);                        /* RFC 1951 fixed code    */
+CSG_API int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables);  /* NULL: the fixed code   */
+/* Symbol statistics of every stride-th segment: d_counts[286 + 30] (uint32, zeroed by the caller) +=
+ * literal / length symbol counts, then distance symbol counts.  Nothing is encoded. */
+CSG_API int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
+                  const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, int stride,
+                  uint32_t* d_counts);
 CSG_API int32_t csg_png_slot_bytes(void);               /* capacity of one segment's output slot */
 CSG_API int32_t csg_png_segments(int32_t W, int32_t H); /* segments of one canvas                 */
 /* d_slots[n_segments][slot_bytes]: the encoded segments; d_sizes[n_segments]: their byte counts;

@@ -134,3 +134,70 @@ def test_figure_layout_serves_host_and_device_rasters():
     assert figs[0].axes[0].marker_columns() == figs[1].axes[0].marker_columns()
     with pytest.raises(TypeError):
         figs[1].compose()
+
+
+def test_png_custom_huffman_tables_decode_with_zlib():
+    """png.custom_tables: a dynamic-Huffman code fitted to symbol counts.  The device tokeniser's bit
+    stream (header, filter literal, literals / matches, end of block, sync flush) is replayed on the
+    host with these tables and must inflate to the original pixels -- with fitted counts and with
+    none at all (every symbol the tokeniser can emit still has a code)."""
+    import random
+    import zlib
+
+    from configurable_spectrograms_b200 import png
+
+    random.seed(3)
+    for trial in range(12):
+        npx = random.randint(1, 300)
+        palette = [0, 0xFF0000FF, 0xFF112233, 0x01020304]
+        pix = [random.choice(palette + [random.getrandbits(32)]) for _ in range(npx)]
+        seq, p, run, dist = [], 0, 0, 0
+        while p < npx:  # csrc/png.cu's tokeniser at pixel granularity (one lane owning the whole line)
+            x = pix[p]
+            if run and x == pix[p - dist] and run < png.MATCH_PIXELS:
+                run += 1
+                p += 1
+                continue
+            if run:
+                seq.append((run, dist))
+                run = 0
+            k = next((d for d in range(1, min(p, png.WINDOW_PIXELS) + 1) if pix[p - d] == x), 0)
+            if k:
+                run, dist = 1, k
+            else:
+                seq.append(x)
+            p += 1
+        if run:
+            seq.append((run, dist))
+        counts = np.zeros(316, np.int64)
+        if trial % 2:
+            for t in seq:
+                if isinstance(t, tuple):
+                    counts[257 + png._symbol_of(4 * t[0], png._LEN_BASE)] += 1
+                    counts[286 + png._symbol_of(4 * t[1], png._DIST_BASE)] += 1
+                else:
+                    for shift in (0, 8, 16, 24):
+                        counts[(t >> shift) & 255] += 1
+        T = png.custom_tables(counts)
+        assert int(max(T["lit_len"])) <= 9 and int(max(T["dist_len"])) <= 14 and int(max(T["len_len"])) <= 14
+        acc = [0, 0]
+
+        def put(value, bits):
+            acc[0] |= int(value) << acc[1]
+            acc[1] += int(bits)
+
+        head = sum(int(T["header"][w]) << (32 * w) for w in range(40))
+        put(head & ((1 << int(T["header_bits"])) - 1), T["header_bits"])
+        put(T["lit_code"][0], T["lit_len"][0])  # the filter-type byte
+        for t in seq:
+            if isinstance(t, tuple):
+                put(T["len_code"][t[0]], T["len_len"][t[0]])
+                put(T["dist_code"][t[1]], T["dist_len"][t[1]])
+            else:
+                for shift in (0, 8, 16, 24):
+                    b = (t >> shift) & 255
+                    put(T["lit_code"][b], T["lit_len"][b])
+        put(T["eob_code"], T["eob_len"])
+        put(0, 3)
+        stream = acc[0].to_bytes((acc[1] + 7) // 8, "little") + b"\x00\x00\xff\xff" + b"\x01\x00\x00\xff\xff"
+        assert zlib.decompress(stream, -15) == b"\x00" + b"".join(int(x).to_bytes(4, "little") for x in pix)
