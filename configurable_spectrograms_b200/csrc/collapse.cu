@@ -19,13 +19,18 @@
 // Kernels
 //   collapse_stream_kernel (TPE, the FAST shapes) block = 16 time rows x all energy chunks; the pitch
 //       axis is walked in host-built runs of constant group membership with a loop body
-//       specialised per membership mask, eight 128-bit streaming loads in flight per thread;
-//       the transposed 16-row tile leaves through shared memory as 64-byte row segments.
+//       specialised per membership mask.  PIPE: every thread keeps a two-stage cp.async pipeline
+//       of its own 16-byte chunks (8 pitch bins per stage) in shared memory, so loads stay in
+//       flight while the previous bins are summed (6.7 TB/s; the register-staged variant with
+//       eight 128-bit streaming loads per batch reaches 5.7 TB/s).  The transposed 16-row tile
+//       leaves through shared memory as 64-byte row segments.
 //       (A TMA variant -- per-warp rings of cp.async.bulk stages -- was measured slower: with
 //       24 of 32 lanes per energy row and per-stage bookkeeping it was issue-bound at 8-16
 //       warps per SM; see DESIGN.md.)
-//   collapse_tpe_kernel    (TPE, any shape/alignment) register-staged generic path.
-//   collapse_tep_kernel    (stored (T,E,P) view).
+//   collapse_tpe_kernel      (TPE, any shape/alignment) register-staged generic path.
+//   collapse_tep_rows_kernel (stored (T,E,P) view, no groups, 8 <= P <= 128, P % 8 == 0) two lanes
+//       per (t,e) row own numpy's eight pairwise accumulators; P/8 vector loads in flight.
+//   collapse_tep_kernel      (stored (T,E,P) view, general) rows staged in shared memory.
 #include <stdlib.h>
 #include <string.h>
 
