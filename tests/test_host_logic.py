@@ -163,3 +163,125 @@ def test_walk_chain_fast_path_equals_step_loop():
             folded_scan.range_max = range_max
             folded = X._walk(sequence, order, ys, zs, json_copy(start), totals, 0.1, -1.0, folded_scan)
             assert folded == slow, (trial, ys, zs)
+
+
+class _FakeSelector:
+    """Stands in for pool_select.DevicePoolSelector on the CPU: answers from the collapsed matrices
+    with numpy what the kernels answer on the device (single rank)."""
+
+    def __init__(self, mats, order, energy):
+        self.mats, self.order, self.energy = mats, order, energy  # mats[(inst, local orbit index)] = (T, E) sums
+
+    def enqueue(self, dtype, items, n_inst, inst_len, max_E, requests, comm=None, count_rows=None, ydev=None, **_kw):
+        self.items, self.requests, self.ydev, self.max_E = items, requests, ydev, max_E
+
+    def _files(self, ii):  # this instrument's files in position order
+        rows = [it for it in self.items if it["inst"] == ii]
+        return [self.mats[int(it["mat_off"])] for it in sorted(rows, key=lambda it: it["pos"])]
+
+    def result_counts(self):
+        counts = np.zeros((len(self.items), self.max_E), np.int32)
+        npos = np.zeros(len(self.items), np.int32)
+        for k, it in enumerate(self.items):
+            m = self.mats[int(it["mat_off"])]
+            pos = np.isfinite(m) & (m > 0)
+            counts[k, : m.shape[1]] = pos.sum(axis=0)
+            npos[k] = pos.sum()
+        return counts, npos
+
+    def result_values(self):
+        out = []
+        for rq in self.requests:
+            pool, best, last = [], None, None
+            for m in self._files(rq["inst"]):
+                pos = m[np.isfinite(m) & (m > 0)]
+                if pos.size:
+                    pool.append(pos)
+                if pool:
+                    last = float(np.nanpercentile(np.concatenate(pool), rq["p"]))
+                    best = last if best is None else max(best, last)
+            out.append(best if rq["mode"] == "running_max" else last)
+        return out
+
+    def result_y_candidates(self):
+        """csg_pool_energy_candidates: the largest 99 %-coverage energy over the positions below `limit`."""
+        out = []
+        for ii in range(len(self.order)):
+            files = self._files(ii)[: int(self.ydev["limit"][ii])]
+            if not files:
+                out.append(None)
+                continue
+            counts = [(np.isfinite(m) & (m > 0)).sum(axis=0) for m in files]
+            out.append(max(X.energy_candidates([self.energy[ii]] * len(files), np.asarray(counts))))
+        return out
+
+
+def test_device_merged_extrema_equal_the_per_step_walk():
+    """extrema_enqueue(per_step=False) + extrema_finish: one merge per instrument from the largest
+    candidates (what the device returns) must give the state of the per-step walk over gathered
+    counts -- with missing files at the start of a chain, instruments that "complete" early,
+    resumed runs and empty files."""
+    import types
+
+    from configurable_spectrograms_b200._lib import POOL_ITEM
+
+    rng = np.random.default_rng(17)
+    order = ("ees", "eeb", "ies")
+    energy = [np.geomspace(30000.0, 4.0, 12), np.geomspace(5.0, 25000.0, 12), rng.permutation(np.linspace(1.0, 4000.0, 12))]
+    for trial in range(25):
+        n = int(rng.integers(2, 9))
+        orbits, mats, file_meta, files = [], {}, [], []
+        for k in range(n):
+            entry = {"orbit": 13000 + 2 * k, "files": {}, "lines": {}}
+            for ii, inst in enumerate(order):
+                if rng.random() < 0.25:
+                    continue
+                m = rng.gamma(2.0, 3.0, (int(rng.integers(3, 9)), 12)) * (40.0 if k == 1 else 1.0)
+                m[rng.random(m.shape) < 0.3] = 0.0
+                if rng.random() < 0.15:
+                    m[:] = 0.0
+                fid = len(files)
+                files.append({"T": m.shape[0], "E": 12})
+                mats[fid] = m.astype(np.float32)
+                file_meta.append({"energy": energy[ii]})
+                entry["files"][inst] = fid
+            orbits.append(entry)
+        sequence = [(o["orbit"], {i: True for i in o["files"]}) for o in orbits]
+
+        def make_shard():
+            sh = types.SimpleNamespace(orbits=orbits, file_meta=file_meta, first_orbit_index=0, instrument_order=order)
+            sh.batch = types.SimpleNamespace(dtype=np.float32, files=files, mat_off=lambda f, g: f)
+
+            def pool_items(steps_by_inst):
+                rows, owners, inst_len = [], [], np.zeros(len(order), np.int32)
+                for ii, inst in enumerate(order):
+                    pos = 0
+                    for oi in steps_by_inst.get(inst, []):
+                        f = orbits[oi]["files"].get(inst)
+                        if f is None:
+                            continue
+                        rows.append((f, files[f]["T"], 12, ii, pos))
+                        owners.append((inst, oi, f))
+                        pos += 1
+                    inst_len[ii] = pos
+                return (np.array(rows, dtype=POOL_ITEM) if rows else np.zeros(0, POOL_ITEM)), inst_len, owners
+
+            sh.pool_items = pool_items
+            sh._pool_selector = _FakeSelector(mats, order, energy)
+            return sh
+
+        for ys, zs in (("linear", "log"), ("log", "log")):
+            start = {}
+            if trial % 4 == 1:
+                start[f"{ys}_{zs}_last_orbit"] = 13000  # resume after the first orbit
+            if trial % 4 == 2:
+                start[f"ees_{ys}_{zs}_y_max"], start[f"ees_{ys}_{zs}_z_max"] = 55, 3.0
+            results = []
+            for per_step in (True, False):
+                sh = make_shard()
+                pending = X.extrema_enqueue(sh, sequence, order, ys, zs, json_copy(start), max_percentile=99.0,
+                                            compute_mins=trial % 2 == 0, per_step=per_step)
+                if not per_step:
+                    assert pending["ydev"] is not None, "the chain preconditions hold for every case generated here"
+                results.append(X.extrema_finish(pending))
+            assert results[0] == results[1], (trial, ys, zs, results)
