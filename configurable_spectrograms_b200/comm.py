@@ -209,9 +209,16 @@ class IpcPeerExchange(PeerExchange):
         self.comm.barrier()  # nobody may still be writing into a mailbox that is about to go away
         mine = self._create(int(slot_bytes * 1.25))
         handles = self.comm.allgather_object(mine)
-        if any(h == bytes(64) for h in handles):
-            raise RuntimeError("CUDA IPC is unavailable on at least one rank")
-        self.connect_ipc(handles)
+        ok = all(h != bytes(64) for h in handles)
+        if ok:
+            try:
+                self.connect_ipc(handles)
+            except Exception:  # e.g. no peer access between two of the GPUs
+                ok = False
+        # the decision is collective: either every rank talks through mailboxes or none does
+        if not all(self.comm.allgather_object(ok)):
+            self.destroy()
+            raise RuntimeError("CUDA IPC / peer access is unavailable on at least one rank")
         self.comm.barrier()
 
 
