@@ -285,3 +285,18 @@ def test_device_merged_extrema_equal_the_per_step_walk():
                     assert pending["ydev"] is not None, "the chain preconditions hold for every case generated here"
                 results.append(X.extrema_finish(pending))
             assert results[0] == results[1], (trial, ys, zs, results)
+
+
+def test_mirrored_modules_pass_their_doctests():
+    """The mirrors carry the reference's doctest examples (its only known-answer pins, SURVEY.md
+    section 4): percentile_utils, fast.extrema, cdf_utils, fast.orbit_discovery."""
+    import doctest
+    import importlib
+
+    total = 0
+    for name in ("percentile_utils", "fast.extrema", "cdf_utils", "fast.orbit_discovery"):
+        mod = importlib.import_module("configurable_spectrograms_b200." + name)
+        result = doctest.testmod(mod, optionflags=doctest.ELLIPSIS | doctest.NORMALIZE_WHITESPACE)
+        assert result.failed == 0, (name, result)
+        total += result.attempted
+    assert total >= 20
