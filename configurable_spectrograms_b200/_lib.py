@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -207,6 +207,7 @@ SIGNATURES = {
     "csg_peer_allgather": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "csg_peer_error_word": (_vp, [_vp]),
     "csg_peer_clear_error": (_i, [_vp, _vp]),
+    "csg_peer_disconnect": (_i, [_vp, _vp]),
     "csg_peer_destroy": (_i, [_vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "csg_pool_scan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),

@@ -207,6 +207,9 @@ class IpcPeerExchange(PeerExchange):
     def _grow(self, slot_bytes: int):
         self.ctx.sync()
         self.comm.barrier()  # nobody may still be writing into a mailbox that is about to go away
+        if self.handle is not None:  # growing: every rank unmaps its imports before any exporter frees
+            self.ctx.lib.csg_peer_disconnect(self.ctx.handle, self.handle)
+            self.comm.barrier()
         mine = self._create(int(slot_bytes * 1.25))
         handles = self.comm.allgather_object(mine)
         ok = all(h != bytes(64) for h in handles)

@@ -201,6 +201,19 @@ int csg_peer_clear_error(csg_ctx* ctx, csg_peer* p) {
   return csg_fill(ctx, p->d_error, 0, sizeof(int));
 }
 
+int csg_peer_disconnect(csg_ctx* ctx, csg_peer* p) {
+  if (!p) return CSG_OK;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < p->n_ranks; ++r)
+    if (p->opened[r] && p->peers[r]) {
+      cudaIpcCloseMemHandle(p->peers[r]);
+      p->peers[r] = nullptr;
+      p->opened[r] = false;
+    }
+  p->connected = false;
+  return CSG_OK;
+}
+
 int csg_peer_destroy(csg_ctx* ctx, csg_peer* p) {
   if (!p) return CSG_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 14
+#define CSG_ABI_VERSION 15
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -417,6 +417,9 @@ CSG_API int csg_peer_allgather(csg_ctx* ctx, csg_peer* peer, const void* d_src, 
 /* int32 on the device: 0, or 1 + the rank whose flag did not arrive within ~2 s. */
 CSG_API void* csg_peer_error_word(csg_peer* peer);
 CSG_API int csg_peer_clear_error(csg_ctx* ctx, csg_peer* peer); /* on the ctx stream */
+/* Unmap the other ranks' mailboxes (every rank does this, then a barrier, before any rank destroys its
+ * own mailbox: an exporter must not free memory an importer still has open). */
+CSG_API int csg_peer_disconnect(csg_ctx* ctx, csg_peer* peer);
 CSG_API int csg_peer_destroy(csg_ctx* ctx, csg_peer* peer);
 
 /* --------------------------------------------- K4: figure mosaics -> DEFLATE (PNG hand-off) */

@@ -46,6 +46,26 @@ def main():
         shard.collapse()
         state = extrema_from_shard(shard, sequence, ORDER, ys, zs, {}, max_percentile=p, compute_mins=mins, comm=comm)
         assert state == gold[key], (rank, key, state, gold[key])
+    # the peer exchange on its own, through real CUDA IPC: payloads of several sizes, then mailboxes that
+    # must grow (every rank unmaps its imports before any exporter frees) and further exchanges
+    import numpy as np
+
+    from configurable_spectrograms_b200.comm import IpcPeerExchange
+
+    ex = IpcPeerExchange(comm, ctx)
+    for slot, sizes in ((4096, (16, 4096, 48)), (1 << 20, (1 << 20, 64, 4096, 1 << 19, 32))):
+        ex.ensure(slot)
+        for k, nbytes in enumerate(sizes):
+            mine = np.full(nbytes, (17 * rank + k) % 251, dtype=np.uint8)
+            src = ctx.to_device(mine)
+            gathered = ex.allgather(src.ptr, nbytes)
+            host = np.empty(world * nbytes, np.uint8)
+            ctx._check(ctx.lib.csg_d2h(ctx.handle, host.ctypes.data, gathered, world * nbytes))
+            ctx.sync()
+            want = np.concatenate([np.full(nbytes, (17 * r + k) % 251, dtype=np.uint8) for r in range(world)])
+            assert np.array_equal(host, want), (rank, slot, nbytes)
+    ex.destroy()
+    dist.barrier()
     # the directory driver across ranks (shared working directory prepared by the parent test)
     work = sys.argv[1]
     os.chdir(work)
