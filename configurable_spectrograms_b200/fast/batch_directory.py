@@ -85,6 +85,11 @@ def FAST_plot_spectrograms_directory(
     without, once with the global extrema, ``:237-243``).  Progress keys:
     ``{y}_{z}_last_orbit``, ``{y}_{z}_error_plotting``, ``orbit_{y}_{z}_timed_out`` and the
     per-reason error lists (``:277-321``).  Raises ``KeyboardInterrupt`` on SIGINT / SIGTERM.
+
+    ``orbit_timeout_seconds``, ``instrument_timeout_seconds`` and ``retry_timeouts`` are accepted for
+    call compatibility and have nothing to act on: the reference times out and retries worker
+    *processes* (``:344-420,455-492``); here an orbit is a slice of a few kernel launches, so the
+    ``orbit_{y}_{z}_timed_out`` list is written and stays empty.
     """
     interrupted = {"flag": False}
 
