@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-png", action="store_true")
     ap.add_argument("--png-orbits", type=int, default=8, help="orbits whose figures (20 each) go through the device PNG stage")
     ap.add_argument("--seed", type=int, default=4)
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity leg (outside the timed region)")
+    ap.add_argument("--verify-orbits", type=int, default=3, help="orbits of this shard whose every panel is compared with the oracle")
     ap.add_argument("--profile-host", default=None, help="write a cProfile of the timed step loop to this path")
     return ap.parse_args()
 
@@ -202,24 +204,276 @@ def run_cpu_port(orbits, steps, warmup):
     return float(np.mean(times)), cores
 
 
+def scratch_dir(prefix):
+    """A scratch directory on the fastest local filesystem (tmpfs when there is one)."""
+    import tempfile
+
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return tempfile.mkdtemp(prefix=prefix, dir=base)
+
+
+def workload_config(n_local, world):
+    """The ``config`` both arms print (the reference arm times a bounded sample OF this workload)."""
+    return {
+        "workload": f"config4 shard: {n_local} orbits/GPU ({world * n_local} orbits total; 1000 at 8 GPUs), "
+                    "4 instruments, FAST batch step linear y / log z, turbo, max_processing_percentile=99",
+        "orbits_per_gpu": n_local, "bytes_per_orbit": int(sum(NOMINAL_T[i] for i in ORDER) * P * E * 4),
+        "l2_policy": f"inputs larger than L2 ({n_local * sum(NOMINAL_T[i] for i in ORDER) * P * E * 4 / 1e9:.1f} GB of cubes streamed per step)",
+    }
+
+
+def run_reference_directory(n_orbits, seed, steps, warmup, render="cell"):
+    """The UNMODIFIED reference (``oracle/_ref``) over a synthetic directory of ``n_orbits`` orbits:
+    ``FAST_plot_spectrograms_directory`` with a fork pool on every host core, fresh JSON state and
+    output tree per step.  Returns (mean seconds per step, cores, pngs per step, png bytes per step)."""
+    import shutil
+
+    from oracle import ref_driver as RD
+
+    work = scratch_dir("csg_ref_")
+    try:
+        RD.prepare_directory(work, n_orbits, seed=seed)
+        cores = os.cpu_count() or 1
+        times, last = [], None
+        for i in range(warmup + steps):
+            last = RD.run_directory(work, workers=cores, render=render)
+            bad = [r for r in last["results"] if r.get("status") != "ok"]
+            if bad:
+                raise RuntimeError(f"reference run reported errors: {bad[:2]}")
+            if i >= warmup:
+                times.append(last["seconds"])
+        return float(np.mean(times)), cores, last["pngs"], last["png_bytes"]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def reference_arm(args):
+    """``--impl reference``: the reference's own CPU implementation of the path on the host cores.
+    ``oracle/_ref`` (the unmodified reference under the cdflib / matplotlib stand-ins of
+    ``oracle/stubs.py``) when it travelled with the snapshot, else the numpy port of its numeric
+    work (``oracle/cpu_pipeline.py``).  Each step = one whole batch step over a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_driver as RD
+
     n = args.cpu_sample_orbits
-    orbits = cpu_sample_orbits(n, args.seed)
-    sec, cores = run_cpu_port(orbits, args.steps, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    extra = {}
+    if RD.available():
+        sec, cores, pngs, png_bytes = run_reference_directory(n, args.seed, args.steps, args.warmup)
+        kind = "reference"
+        sample = (f"{n} synthetic FAST orbits (4 instruments, nominal shapes) as .npz side-cars on tmpfs; the unmodified reference's "
+                  f"FAST_plot_spectrograms_directory: serial extrema pre-pass + fork ProcessPoolExecutor({cores}), both submissions, "
+                  f"{pngs} PNGs ({png_bytes / 1e6:.1f} MB) per step; cdflib -> .npz stub, matplotlib -> numpy norm+LUT at cell "
+                  "resolution + Pillow PNG (no Agg resampling / text: optimistic for the reference)")
+        warm = args.warmup
+        # the numeric-only port beside it (no file IO, no PNG): what round 1 reported
+        psec, _ = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
+        extra["port_numeric_only"] = {"value": n / psec, "unit": "orbits/s", "kind": "port"}
+    else:
+        warm = min(args.warmup, 1)
+        sec, cores = run_cpu_port(cpu_sample_orbits(n, args.seed), args.steps, warm)
+        kind = "port"
+        sample = f"{n} synthetic FAST orbits (4 instruments, nominal shapes), both submissions, numeric path only (no Agg/PNG): oracle/_ref did not travel"
     value = n / sec
-    sample = f"{n} synthetic FAST orbits (4 instruments, nominal shapes), both submissions, numeric path only (no Agg/PNG)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "orbits/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config4 shard: FAST batch step, linear y / log z, max_processing_percentile=99", "sample_orbits": n},
-        "cpu_baseline": {"value": value, "unit": "orbits/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.orbits_per_gpu, world),
+        "cpu_baseline": {"value": value, "unit": "orbits/s", "cores": cores, "kind": kind, "sample": sample, "sample_orbits": n, **extra},
         "e2e": {"value": value, "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# parity leg (outside every timed region): the bench workload itself against numpy / the oracle
+# ----------------------------------------------------------------------------------------
+def _host_cube(cubes, f):
+    n = f["T"] * P * E
+    return cubes[f["offset"] : f["offset"] + n].cpu().numpy().reshape(f["T"], P, E)
+
+
+def verify_shard(args, torch, cubes, files, orbits, shard, step, state, lut, rank, world):
+    """``parity_checked``: (1) K1 sums of sampled files bit for bit against ``np.nansum``; (2) the global
+    z_max / y_max of EVERY instrument against an independent oracle over the whole ascending orbit
+    sequence -- per-file value histograms (the synthetic sums are integer counts), prefix by prefix,
+    numpy's rank arithmetic restated in float32 (``oracle/restate.percentile_rank`` / ``lerp``) --
+    itself pinned against brute-force ``np.nanpercentile(np.concatenate(blocks so far), p)`` on
+    sampled prefixes (``CS/fast/extrema.py:270-300``); (3) every panel of every figure of both
+    submissions of a few orbits -- resolved bounds and colormap index planes -- against the oracle
+    port of the reference's figure builders (``oracle/cpu_pipeline.py`` + ``oracle/restate.py``)."""
+    import math
+
+    from configurable_spectrograms_b200.fast.pipeline import check_norm_status
+    from oracle import cpu_pipeline as CP
+    from oracle import restate as R
+
+    t_start = time.perf_counter()
+    out = {"ok": True, "failures": []}
+
+    def fail(msg):
+        out["ok"] = False
+        if len(out["failures"]) < 8:
+            out["failures"].append(msg)
+
+    b = shard.batch
+    energy = orbits[0]["files"][ORDER[0]]["energy"]
+    # ---- (1) + per-file oracle inputs for (2)
+    per_file = []  # (inst index, global orbit index, value histogram, per-energy positive counts)
+    blocks = {i: [] for i in range(len(ORDER))}  # positives of this rank's first files (brute-force pin)
+    n_sums_checked = 0
+    first = rank * len(orbits)
+    for k, ob in enumerate(orbits):
+        for inst in ORDER:
+            fd = ob["files"].get(inst)
+            if fd is None:
+                continue
+            f = files[fd["index"]]
+            cube = _host_cube(cubes, f)
+            with np.errstate(invalid="ignore", over="ignore"):
+                m = np.nansum(cube, axis=1)
+            if k % 16 == 0:
+                fid = shard.orbits[k]["files"][inst]
+                got = b.sums(fid, 0)
+                same = (got.view(np.uint32) == m.view(np.uint32)) | (np.isnan(got) & np.isnan(m))
+                n_sums_checked += 1
+                if not same.all():
+                    fail(f"K1 total differs from np.nansum: orbit {ob['orbit']} {inst}")
+            ok = np.isfinite(m) & (m > 0)
+            pos = m[ok]
+            if not (np.all(pos == np.floor(pos)) and (pos.size == 0 or pos.max() < 2**24)):
+                fail("synthetic sums are not integer counts: the histogram oracle does not apply")
+                return out
+            per_file.append((ORDER.index(inst), first + k, np.bincount(pos.astype(np.int64)), ok.sum(axis=0).astype(np.int64)))
+            if k < 8:
+                blocks[ORDER.index(inst)].append(pos)
+    out["k1_files_checked"] = n_sums_checked
+    if world > 1:
+        gathered = [None] * world
+        torch.distributed.all_gather_object(gathered, per_file)
+        per_file = [row for part in gathered for row in part]
+    if rank == 0:
+        e_sorted = np.sort(np.asarray(energy, dtype=np.float64))
+        e_order = np.argsort(np.asarray(energy, dtype=np.float64), kind="stable")
+        n_prefix, brute = 0, 0
+        for ii, inst in enumerate(ORDER):
+            rows = sorted((r for r in per_file if r[0] == ii), key=lambda r: r[1])
+            width = max(len(r[2]) for r in rows)
+            hist = np.zeros(width, dtype=np.int64)
+            ecount = np.zeros(len(energy), dtype=np.int64)
+            best_z, best_e = -np.inf, -np.inf
+            per_prefix = []
+            for _ii, _oi, h, ec in rows:
+                hist[: len(h)] += h
+                ecount += ec
+                n = int(hist.sum())
+                cand_z = 0.0
+                if n:
+                    lo, hi, g = R.percentile_rank(n, 99.0, np.float32)
+                    cum = np.cumsum(hist)
+                    a, c = np.searchsorted(cum, [lo, hi], side="right")
+                    cand_z = float(R.lerp(np.float32(a), np.float32(c), g, np.float32))
+                cand_e = 0.0
+                if ecount.sum():
+                    cum_e = np.cumsum(ecount[e_order])
+                    idx = min(int(np.searchsorted(cum_e, 0.99 * cum_e[-1], side="right")), len(e_sorted) - 1)
+                    # the reference keys only energies that have seen a count; zero-count keys do not move the sum
+                    cand_e = float(e_sorted[idx])
+                per_prefix.append(cand_z)
+                best_z, best_e = max(best_z, cand_z), max(best_e, cand_e)
+                n_prefix += 1
+            stem = f"{inst}_linear_log"
+            want_z, want_y = float(math.ceil(best_z)), int(min(4000, math.ceil(best_e)))
+            if state.get(f"{stem}_z_max") != want_z:
+                fail(f"{stem}_z_max: GPU {state.get(f'{stem}_z_max')} != oracle {want_z}")
+            if state.get(f"{stem}_y_max") != want_y:
+                fail(f"{stem}_y_max: GPU {state.get(f'{stem}_y_max')} != oracle {want_y}")
+            # pin the histogram oracle itself: brute-force numpy on the first prefixes (the storm orbits live there)
+            pool = []
+            for k, blk in enumerate(blocks[ii]):
+                pool.append(blk)
+                want = float(np.nanpercentile(np.concatenate(pool), 99.0))
+                brute += 1
+                if per_prefix[k] != want:
+                    fail(f"{inst} prefix {k}: histogram oracle {per_prefix[k]} != np.nanpercentile {want}")
+        out.update(extrema_instruments=len(ORDER), extrema_prefixes_walked=n_prefix, extrema_prefixes_brute_force=brute,
+                   extrema={k: v for k, v in state.items() if k.endswith(("_z_max", "_y_max"))})
+    # ---- (3) panels of a few orbits of this rank: a cusp orbit, a storm orbit, a plain one
+    b.rasterise(want_rgba=True, want_index=True)
+    b.ctx.sync()
+    norms = b.norms()
+    picks = []
+    for want in (lambda g: g % 3 == 0, lambda g: g in (1, 2, 5), lambda g: g % 3 != 0 and g not in (1, 2, 5)):
+        picks += [k for k in range(len(orbits)) if want(first + k) and k not in picks][:1]
+    picks = (picks + [k for k in range(len(orbits)) if k not in picks])[: max(1, args.verify_orbits)]
+    old_native = CP.NATIVE_LOG
+    CP.NATIVE_LOG = False  # the correctly rounded float32 log10 the parity tests grade against
+    n_panels = n_figs = 0
+
+    def compare(fig, expected, what):
+        nonlocal n_panels
+        exp = iter(expected)
+        need = fig.zoom is not None and fig.zoom_needed
+        for row in fig.rows:
+            for pid in [row.full_panel] + ([row.zoom_panel] if need else []):
+                e = next(exp, "missing")
+                if isinstance(e, str):
+                    return fail(f"{what}: the oracle draws fewer panels")
+                if pid is None:
+                    if e is not None:
+                        fail(f"{what}: panel missing on the GPU side")
+                    continue
+                try:
+                    check_norm_status(norms[pid], str(what))
+                except ValueError:
+                    if e is not None:
+                        fail(f"{what}: norm rejected on the GPU side only")
+                    continue
+                if e is None:
+                    fail(f"{what}: norm rejected by the oracle only")
+                elif not np.array_equal(b.panel_index(pid), e[0]):
+                    fail(f"{what} {row.label}: colormap index plane differs")
+                n_panels += 1
+        if next(exp, "end") != "end":
+            fail(f"{what}: the oracle draws more panels")
+
+    try:
+        with np.errstate(all="ignore"):
+            for k in sorted(picks):
+                ob = orbits[k]
+                dsets = {inst: {"times": fd["times"], "energy": fd["energy"], "pitch_angle": fd["pitch_angle"],
+                                "data": _host_cube(cubes, files[fd["index"]])} for inst, fd in ob["files"].items()}
+                lines = ob["lines"]
+                for wx in (False, True):
+                    figs = iter(shard.figures[slice(*step.figure_ranges[(ob["orbit"], wx)])])
+                    extrema = state if wx else None
+                    for inst in ORDER:
+                        ov = R.extrema_overrides(extrema, inst, "linear", "log")
+                        for variant, kw in (("given", dict(y_min=ov[0], y_max=ov[1], z_min=ov[2], z_max=ov[3])), ("raw", {})):
+                            fig = next(figs)
+                            compare(fig, CP.pitch_angle_grid(dsets[inst], lines.get(inst), "log", lut, minutes=6, **kw),
+                                    (ob["orbit"], inst, variant, wx))
+                            n_figs += 1
+                    first_lines = next((lines.get(i) for i in ORDER if i in dsets), None)
+                    for variant, ge in (("given", extrema), ("raw", None)):
+                        fig = next(figs)
+                        compare(fig, CP.instrument_grid(dsets, first_lines, "log", lut, ge, "linear", minutes=6),
+                                (ob["orbit"], "grid", variant, wx))
+                        n_figs += 1
+    finally:
+        CP.NATIVE_LOG = old_native
+    out.update(panel_orbits=[orbits[k]["orbit"] for k in sorted(picks)], figures_checked=n_figs, panels_checked=n_panels,
+               seconds=round(time.perf_counter() - t_start, 2))
+    if world > 1:  # every rank checked its own panels: one verdict
+        oks = [None] * world
+        torch.distributed.all_gather_object(oks, (out["ok"], n_panels, out["failures"]))
+        out["ok"] = all(o[0] for o in oks)
+        out["panels_checked"] = sum(o[1] for o in oks)
+        out["failures"] = [m for o in oks for m in o[2]][:8]
+    return out
 
 
 def bind_near_gpu(torch, local):
@@ -377,6 +631,11 @@ def main():
     sampler.mark(1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ------------------------------------------------- parity of this very workload (outside the metric)
+    parity = None
+    if not args.no_verify:
+        parity = verify_shard(args, torch, cubes, files, orbits, shard, step, state, lut, rank, world)
+
     # ------------------------------------------------- K4 (outside the metric): figures -> PNG bytes
     png_stage = None
     if rank == 0 and not args.no_png:
@@ -484,25 +743,27 @@ def main():
     # ----------------------------------------------------------- CPU baseline beside it
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_driver as RD
+
         n = args.cpu_sample_orbits
-        sec, cores = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
-        cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "port",
-               "sample": f"{n} synthetic FAST orbits of the same workload, both submissions, numeric path only (no Agg/PNG), {sec:.1f} s wall"}
+        if RD.available():
+            sec, cores, pngs, png_bytes = run_reference_directory(n, args.seed, 1, 0)
+            cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "reference", "sample_orbits": n,
+                   "sample": f"{n} synthetic FAST orbits of the same workload through the unmodified reference's FAST_plot_spectrograms_directory "
+                             f"(oracle/_ref under the cdflib/matplotlib stand-ins, fork pool on {cores} cores, {pngs} cell-resolution PNGs), {sec:.1f} s wall"}
+        else:
+            sec, cores = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
+            cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "port", "sample_orbits": n,
+                   "sample": f"{n} synthetic FAST orbits of the same workload, both submissions, numeric path only (no Agg/PNG), {sec:.1f} s wall"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "orbits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"config4 shard: {n_local} orbits/GPU ({world * n_local} orbits total; 1000 at 8 GPUs), "
-                            "4 instruments, FAST batch step linear y / log z, turbo, max_processing_percentile=99",
-                "orbits_per_gpu": n_local, "bytes_per_orbit": int(cube_bytes // n_local),
-                "panels_per_gpu": shard.batch.n_panels, "regions_per_gpu": shard.batch.n_regions,
-                "pixels_per_gpu": shard.batch.n_pixels,
-                "numa_bound_cpus": numa_cpus,
-                "l2_policy": f"inputs larger than L2 ({cube_bytes / 1e9:.1f} GB of cubes streamed per step)",
-            },
+            "config": workload_config(n_local, world),
+            "plan": {"panels_per_gpu": shard.batch.n_panels, "regions_per_gpu": shard.batch.n_regions,
+                     "pixels_per_gpu": shard.batch.n_pixels, "numa_bound_cpus": numa_cpus},
             "roofline": {"bound": "hbm", "kernel": "collapse_stream_kernel<float,4,384>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ms": k1_ms,
                          "algorithmic_bytes": int(cube_bytes + sums_bytes),
@@ -512,7 +773,7 @@ def main():
                          "read_stream_peak": 7488.6, "frac_of_read_stream_peak": achieved / 7488.6},
             "step_roofline": {"algorithmic_bytes": int(step_bytes), "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "note": "this rank's whole step (K1+K2b+K2a+K3), SURVEY 8(d) B_orbit x orbits / step time"},
-            "png_stage": png_stage, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+            "parity_checked": parity, "png_stage": png_stage, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
             "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
                          "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,
                          "percentile_regions_needing_radix_fallback": fallbacks},

@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -183,6 +183,7 @@ SIGNATURES = {
     "csg_collapse_host": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "csg_region_stats_fallbacks": (_i, [_vp, _i, C.POINTER(_i)]),
+    "csg_region_stats_force_exact": (_i, [_vp, _i]),
     "csg_raster_blocks": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -20,6 +20,7 @@ struct csg_ctx {
   int64_t launches;
   void* scratch;  // device scratch owned by the context (grow-only)
   size_t scratch_bytes;
+  int stats_force_exact;  // csg_region_stats_force_exact(): K2a sends every percentile region to the exact select
   char err[512];
 };
 

@@ -200,7 +200,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 6)
     region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
                         const int32_t* __restrict__ pool, csg_region_stats* __restrict__ out,
-                        uint8_t* __restrict__ todo) {
+                        uint8_t* __restrict__ todo, int force_exact) {
   typedef typename Key<T>::U U;
   constexpr U KEY_MIN = 0;       // below the key of every non-NaN value (-inf maps above 0)
   constexpr U KEY_MAX = ~(U)0;   // above the key of +inf
@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(kThreads, 6)
   }
   __syncthreads();
   const int n0 = s_ncand[0], n1 = share ? n0 : s_ncand[1];
-  bool fail = n0 > kCand || n1 > kCand;
+  // force_exact (csg_region_stats_force_exact): every percentile region is handed to the exact radix
+  // select below -- the path a rank that escapes its bracket takes about once in a thousand regions
+  bool fail = force_exact != 0 || n0 > kCand || n1 > kCand;
   // every thread holds the same reduced counters: the rank arithmetic below is block-uniform
   long long rank[kTargets];
   T gamma[2];
@@ -629,18 +631,24 @@ extern "C" int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype,
   if (st != CSG_OK) return st;
   if (dtype == CSG_F32) {
     region_stats_kernel<float><<<n_regions, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out,
-                                                                        (uint8_t*)todo);
+                                                                        (uint8_t*)todo, ctx->stats_force_exact);
     CSG_LAUNCH_CHECK(ctx, "region_stats_kernel");
     region_select_kernel<float><<<n_regions, kThreads, 0, ctx->stream>>>((const float*)d_mats, d_regions, d_index_pool, d_out,
                                                                          (const uint8_t*)todo);
   } else {
     region_stats_kernel<double><<<n_regions, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
-                                                                         d_out, (uint8_t*)todo);
+                                                                         d_out, (uint8_t*)todo, ctx->stats_force_exact);
     CSG_LAUNCH_CHECK(ctx, "region_stats_kernel");
     region_select_kernel<double><<<n_regions, kThreads, 0, ctx->stream>>>((const double*)d_mats, d_regions, d_index_pool,
                                                                           d_out, (const uint8_t*)todo);
   }
   CSG_LAUNCH_CHECK(ctx, "region_select_kernel");
+  return CSG_OK;
+}
+
+extern "C" int csg_region_stats_force_exact(csg_ctx* ctx, int on) {
+  if (!ctx) return CSG_ERR_ARG;
+  ctx->stats_force_exact = on ? 1 : 0;
   return CSG_OK;
 }
 

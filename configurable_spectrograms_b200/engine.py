@@ -488,6 +488,11 @@ class Batch:
             )
         )
 
+    def force_exact_stats(self, on: bool = True):
+        """Test knob (``csg_region_stats_force_exact``): route every percentile region of later
+        :meth:`run_stats` calls on this batch's context through the exact radix-select fallback."""
+        self.ctx._check(self.ctx.lib.csg_region_stats_force_exact(self.ctx.handle, int(bool(on))))
+
     def stats_fallbacks(self) -> int:
         """Regions of the last run_stats() that needed the exact radix-select fallback."""
         n = C.c_int(0)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 15
+#define CSG_ABI_VERSION 16
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -209,6 +209,11 @@ CSG_API int csg_region_stats_run(csg_ctx* ctx, const void* d_mats, int dtype, co
 /* Diagnostics: regions of the last run whose percentile ranks escaped the sampled brackets and
  * were redone by the exact radix select (synchronises the stream). */
 CSG_API int csg_region_stats_fallbacks(csg_ctx* ctx, int n_regions, int* count);
+/* Test knob: on != 0 makes every later csg_region_stats_run() of this context resolve ALL percentile
+ * regions with the exact multi-pass radix select (the path a rank escaping its sampled bracket takes),
+ * so that path can be compared with np.nanpercentile on ordinary inputs.  Results are identical either
+ * way; only the route differs. */
+CSG_API int csg_region_stats_force_exact(csg_ctx* ctx, int on);
 
 /* ------------------------------------------------------ K3: norm + colormap */
 /* One imshow panel (CS/plotting.py:276-287 log, :308-324 linear). */

@@ -235,6 +235,74 @@ def test_region_stats_tail_percentiles_take_the_single_pass(ctx, dtype, kind):
         assert same_float(st[r]["p_hi"], float(np.nanpercentile(ref, 99)))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["counts", "continuous", "sparse", "ties_inf"])
+def test_region_stats_exact_fallback_forced(ctx, dtype, kind):
+    """The exact multi-pass radix select (``region_select_kernel``) normally runs only for the rare
+    region whose rank escapes its sampled bracket; ``csg_region_stats_force_exact`` sends EVERY
+    percentile region through it: FAST-sized full panels, zoom row lists, single cells, heavy ties,
+    +-inf and NaN cells, several percentile pairs -- bit for bit ``np.nanpercentile``
+    (``CS/percentile_utils.py:87-88``) -- and the same answers as the bracket path."""
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(77)
+    shape = (800, 4, 96)
+    if kind == "counts":
+        cube = rng.poisson(2.0, shape).astype(dtype)
+    elif kind == "continuous":
+        cube = rng.gamma(2.0, 50.0, shape).astype(dtype)
+    elif kind == "sparse":
+        cube = (rng.poisson(0.02, shape) * rng.integers(1, 50, shape)).astype(dtype)
+    else:  # three distinct values, whole rows of +inf / -inf, NaN cells through inf - inf
+        cube = rng.choice(np.array([0.0, 1.0, 7.0], dtype=dtype), shape)
+        cube[5, 0, :] = np.inf
+        cube[6, 0, :40] = -np.inf
+        cube[7, 0, 10:20], cube[7, 1, 10:20] = np.inf, -np.inf
+        cube[8, :, 3] = -2.5
+    cube[rng.random(shape) < 0.01] = np.nan
+    b = Batch(ctx, dtype, 0)
+    f = b.add_file(cube)
+    b.upload_cubes()
+    b.collapse()
+    with np.errstate(invalid="ignore"):
+        m = np.nansum(cube, axis=1)
+    cases = [
+        (np.arange(96)[::-1][11:85], np.arange(800), (1, 99)),
+        (np.arange(96), np.arange(3, 800), (1, 99)),
+        (np.arange(10, 40), np.arange(100, 359), (1, 99)),
+        (np.arange(96), np.arange(800), (0, 100)),
+        (np.arange(0, 96, 3), np.array([3, 5, 6, 7, 8, 200, 799]), (5, 95)),
+        (np.arange(20, 21), np.arange(30, 31), (50, 50.5)),
+        (np.arange(96), np.arange(800), (33.3, 99.9)),
+        (np.arange(10, 20), np.arange(7, 8), (1, 99)),  # every cell NaN (inf - inf) in the ties_inf cube
+    ]
+    regs = [b.add_region(f, 0, cols, rows=rows, want_pct=True, p_lo=pl, p_hi=ph) for cols, rows, (pl, ph) in cases]
+    b.upload_tables()
+    b.run_stats()
+    usual = b.stats().copy()
+    b.force_exact_stats(True)
+    try:
+        b.run_stats()
+        n_pct = sum(1 for r in regs if usual[r]["n_valid"] > 0)
+        assert b.stats_fallbacks() == n_pct, "every non-empty percentile region must take the exact select"
+        st = b.stats()
+    finally:
+        b.force_exact_stats(False)
+    for r, (cols, rows, (pl, ph)) in zip(regs, cases):
+        ref = _region_ref(m, cols, rows)
+        with np.errstate(invalid="ignore"), np.testing.suppress_warnings() as sup:
+            sup.filter(RuntimeWarning)
+            some = (~np.isnan(ref)).any()
+            elo = float(np.nanpercentile(ref, pl)) if some else np.nan
+            ehi = float(np.nanpercentile(ref, ph)) if some else np.nan
+        assert same_float(st[r]["p_lo"], elo), (kind, r, st[r]["p_lo"], elo)
+        assert same_float(st[r]["p_hi"], ehi), (kind, r, st[r]["p_hi"], ehi)
+        assert same_float(usual[r]["p_lo"], elo) and same_float(usual[r]["p_hi"], ehi), (kind, r)
+        assert st[r]["n_valid"] == (~np.isnan(ref)).sum()
+    b.run_stats()
+    assert b.stats_fallbacks() < n_pct, "the knob is off again: the bracket path answers"
+
+
 def _lut():
     rng = np.random.default_rng(99)
     from oracle import restate as R
@@ -397,6 +465,63 @@ def test_pool_prefix_percentiles_exact(ctx, dtype, integer, selector):
         ok = np.isfinite(m) & (m > 0)
         assert np.array_equal(counts[j], ok.sum(axis=0))
         assert npos[j] == ok.sum()
+
+
+@pytest.mark.parametrize("selector", ["device", "host_driven"])
+def test_pool_percentiles_float32_pool_beyond_2_pow_24(ctx, selector):
+    """The regime config 4 runs in (SURVEY section 7 hard part 2): a float32 pool of more than 2**24
+    positives, where numpy's float32 rank arithmetic ``(n-1)*q`` is several positions away from the
+    float64 one.  40 files x (4500 x 96) cells per instrument; running-max and whole-pool percentiles
+    against ``np.nanpercentile(np.concatenate(blocks so far), p)`` (``CS/fast/extrema.py:280-300``)
+    for every prefix, brute force."""
+    from configurable_spectrograms_b200._lib import POOL_ITEM
+    from configurable_spectrograms_b200.engine import Batch
+    from configurable_spectrograms_b200.pool_select import DevicePoolSelector, GpuPoolBackend, prefix_percentiles
+
+    rng = np.random.default_rng(2024)
+    n_files, T, E = 40, 4500, 96
+    b = Batch(ctx, np.float32, 0)
+    cubes = {}
+    for i in range(2):
+        for k in range(n_files):
+            if i == 0:  # counts: massive ties, an early storm so that the running max is not the last prefix
+                c = (rng.poisson(6.0 * (5.0 if k == 2 else 1.0), (T, 2, E)) + 1).astype(np.float32)
+            else:  # continuous: the lerp between two distinct neighbours matters
+                c = rng.gamma(2.0, 30.0 * (3.0 if k == 1 else 1.0), (T, 2, E)).astype(np.float32) + np.float32(1e-3)
+            cubes[(i, k)] = (b.add_file(c), c)
+    b.upload_cubes()
+    b.collapse()
+    items = np.zeros(len(cubes), dtype=POOL_ITEM)
+    for j, ((i, k), (f, c)) in enumerate(cubes.items()):
+        items[j] = (b.mat_off(f, 0), T, E, i, k)
+    inst_len = np.array([n_files, n_files], dtype=np.int32)
+    reqs = [{"inst": i, "p": 99.0, "mode": "running_max"} for i in range(2)]
+    reqs += [{"inst": i, "p": p, "mode": "last"} for i in range(2) for p in (1, 50.0, 99.0, 99.9)]
+    if selector == "device":
+        sel = DevicePoolSelector(b)
+        sel.enqueue(np.float32, items, 2, inst_len, E, reqs)
+        vals, _counts, npos = sel.result()
+        assert vals is not None
+    else:
+        vals, _counts, npos = prefix_percentiles(GpuPoolBackend(b), np.float32, items, 2, inst_len, E, reqs)
+    assert int(np.asarray(npos).reshape(2, n_files)[0].sum()) > 2**24
+    for i in range(2):
+        blocks, best = [], -np.inf
+        for k in range(n_files):
+            m = np.nansum(cubes[(i, k)][1], axis=1)
+            blocks.append(m[np.isfinite(m) & (m > 0)])
+            pool = np.concatenate(blocks)
+            assert pool.dtype == np.float32
+            best = max(best, float(np.nanpercentile(pool, 99.0)))
+        assert pool.size > 2**24
+        assert vals[i] == best, (i, vals[i], best)
+        # float32 rank arithmetic really differs from float64's here
+        q32 = np.float32(pool.size - 1) * (np.float32(99.9) / np.float32(100))
+        assert abs(float(q32) - (pool.size - 1) * 0.999) >= 0.5
+        for j, p in enumerate((1, 50.0, 99.0, 99.9)):
+            got = vals[2 + 4 * i + j]
+            want = float(np.nanpercentile(pool, p))
+            assert got == want, (i, p, got, want)
 
 
 def test_device_selector_slot_overflow_falls_back(ctx):

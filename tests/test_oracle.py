@@ -190,3 +190,43 @@ def test_native_float32_log10_flip_rate_is_tiny():
     a = R.colormap_index(R.lognorm(m, 1.0, 2000.0))
     b = R.colormap_index(R.lognorm(m, 1.0, 2000.0, native_log=True))
     assert np.mean(a != b) < 1e-3
+
+
+def test_oracle_ref_reproduces_the_golden_batch_run(tmp_path):
+    """``oracle/_ref`` (the unmodified reference, copied by ``oracle/make_ref.sh``) driven by
+    ``oracle/ref_driver.py`` -- the bench's reference arm -- over the golden 6-orbit tree: statuses, PNG
+    tree and extrema JSON equal the fixtures captured from ``/root/reference`` itself, with the rendering
+    stand-in on (every PNG is a real image).  A subprocess keeps the cdflib / matplotlib stubs out of
+    this interpreter.  Skipped where ``oracle/_ref`` has not been built."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    from oracle import ref_driver as RD
+    from tests.test_gpu_api import _write_tree
+
+    if not RD.available():
+        pytest.skip("oracle/_ref not built (sh oracle/make_ref.sh needs the reference checkout)")
+    _write_tree(tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import json, sys, os\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from oracle import ref_driver as RD\n"
+        f"r = RD.run_directory({str(tmp_path)!r}, workers=2, render='cell', colormap='cividis')\n"
+        f"os.chdir({str(tmp_path)!r})\n"
+        "pngs = sorted(os.path.relpath(os.path.join(d, f), './FAST_plots_ref') for d, _s, fs in os.walk('./FAST_plots_ref') for f in fs)\n"
+        "from PIL import Image\n"
+        "sizes = [Image.open(os.path.join('./FAST_plots_ref', p)).size for p in pngs[:3]]\n"
+        "print('RESULT' + json.dumps({'status': sorted((x['orbit'], x['status']) for x in r['results']), 'pngs': pngs,\n"
+        "      'extrema': json.load(open('FAST_calculated_extrema.json')), 'sizes': sizes}))\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    got = json.loads(next(line for line in out.stdout.splitlines() if line.startswith("RESULT"))[6:])
+    gold = load_json("extrema_tree.json")
+    assert [tuple(x) for x in got["status"]] == [tuple(x) for x in gold["batch_status"]]
+    assert got["pngs"] == gold["batch_pngs"]
+    assert got["extrema"] == gold["batch_extrema"]
+    assert all(w > 8 and h > 8 for w, h in got["sizes"])
