@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -222,6 +222,21 @@ SIGNATURES = {
     "csg_pool_sel_finish": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "csg_pool_base": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _vp]),
 }
+
+SIGNATURES.update({
+    "csg_cdf_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "csg_cdf_close": (None, [_vp]),
+    "csg_cdf_var_count": (_i, [_vp]),
+    "csg_cdf_var_info": (_i, [_vp, C.c_char_p, _i, _vp]),
+    "csg_cdf_read": (_i, [_vp, C.c_char_p, _i64, _i64, _vp, _sz]),
+    "csg_cdf_last_error": (C.c_char_p, []),
+})
+CDF_VAR = np.dtype(
+    [("name", "S260"), ("data_type", "<i4"), ("elem_bytes", "<i4"), ("n_dims", "<i4"), ("dims", "<i4", (8,)),
+     ("rec_vary", "<i4"), ("compressed", "<i4"), ("row_major", "<i4"), ("n_records", "<i8"), ("values_per_record", "<i8")],
+    align=True,
+)
+assert CDF_VAR.itemsize == 336
 
 _lib = None
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcsgpu.so")
-SOURCES = ("ctx.cu", "collapse.cu", "stats.cu", "raster.cu", "pool.cu", "poolsel.cu", "peer.cu", "png.cu")
+SOURCES = ("ctx.cu", "collapse.cu", "stats.cu", "raster.cu", "pool.cu", "poolsel.cu", "peer.cu", "png.cu", "cdf.cpp")
 
 NVCC_FLAGS = [
     "-gencode",
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(build_dir, src.replace(".cu", ".o"))
+        obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     tmp = LIB + ".tmp"
-    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-lz"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -22,7 +22,18 @@ cdf_type_cache: dict = {}
 INSTRUMENT_TAGS = ("ees", "eeb", "ies", "ieb")
 
 
-def _read_variables(cdf_path: str, names) -> list[np.ndarray]:
+def _read_variables(cdf_path: str, names, data_alloc=None) -> list[np.ndarray]:
+    """The named variables of a file: a binary CDF v3 goes through the native reader (``cdf_reader``:
+    ``energy`` / ``pitch_angle`` are cut to record 0, all the loader uses), an empty marker file with a
+    ``<file>.npz`` side-car through numpy (synthetic data, ``synth.py``), anything else through cdflib."""
+    from . import cdf_reader
+
+    if cdf_reader.is_cdf_v3(str(cdf_path)):
+        if tuple(names) == tuple(CDF_VARIABLE_NAMES):
+            got = cdf_reader.read_fast_variables(str(cdf_path), data_alloc)
+            return [got[n] for n in names]
+        with cdf_reader.CdfFile(str(cdf_path)) as cdf:
+            return [cdf.read(n) for n in names]
     side_car = str(cdf_path) + ".npz"
     if os.path.exists(side_car):
         with np.load(side_car) as z:
@@ -128,11 +139,14 @@ def get_cdf_var_shapes(cdf_folder_path: str = CDF_DATA_DIRECTORY, variable_names
     return {name: [get_variable_shape(p, name) for p in paths] for name in variable_names}
 
 
-def load_fast_cdf_dataset(cdf_path: str, variable_names=tuple(CDF_VARIABLE_NAMES)) -> dict[str, np.ndarray]:
+def load_fast_cdf_dataset(cdf_path: str, variable_names=tuple(CDF_VARIABLE_NAMES), data_alloc=None) -> dict[str, np.ndarray]:
     """``{'times','data','energy','pitch_angle'}`` with 1-D bin arrays and ``data`` as a
     (time, pitch, energy) array or transposed *view* (``:222-256``) -- the view is kept
-    un-copied because numpy's summation order, reproduced on the GPU, depends on it."""
-    times, data, energy_full, pitch_full = _read_variables(cdf_path, variable_names)
+    un-copied because numpy's summation order, reproduced on the GPU, depends on it.
+
+    ``data_alloc(shape, dtype)`` (batch driver): memory the cube is decoded into -- a pinned staging
+    slot -- when the file goes through the native reader."""
+    times, data, energy_full, pitch_full = _read_variables(cdf_path, variable_names, data_alloc)
     energy = energy_full[0, 0, :] if energy_full.ndim == 3 else energy_full
     pitch = pitch_full[0, :, 0] if pitch_full.ndim == 3 else pitch_full
     if data.shape[1] == len(energy) and data.shape[2] == len(pitch):

@@ -1,0 +1,462 @@
+// Native CDF v3 ingest: the four variables load_fast_cdf_dataset() consumes, straight into
+// caller memory (pinned staging slots) -- SURVEY.md section 8(f) row 3.
+//
+// Replaces the cdflib calls of CS/cdf_utils.py:247-251 (`cdf.varget(name)` x 4) for the batch
+// path.  The reference reads the whole data-sized `pitch_angle` variable to use 64 numbers of
+// its first record (CS/cdf_utils.py:253) and decodes every file >= 5 times per submission
+// (CS/fast/process_orbit.py:139, CS/fast/plotting.py:99,255); here a file is memory-mapped once,
+// its variable index (zVDR / rVDR -> VXR tree -> VVR / CVVR) is walked, and only the records asked
+// for are copied (uncompressed) or inflated (gzip) into the destination, with the byte order
+// converted when the file's encoding differs from the host's.
+//
+// Format: CDF 3.x internal format (64-bit offsets): magic 0xCDF30001 + 0x0000FFFF (plain) or
+// 0xCCCC0001 (whole-file compression: CCR / CPR, gzip only); internal records are big-endian
+// {int64 size, int32 type, ...}: CDR 1, GDR 2, rVDR 3, VXR 6, VVR 7, zVDR 8, CCR 10, CPR 11, CVVR 13.
+//
+// PARITY UNPINNED: cdflib 1.3.12 and real FAST CDFs are not available offline; this reader is
+// validated against CDF files produced by tests/cdf_writer.py from the same published layout
+// (row-major, network and IBMPC encodings, plain and gzip-compressed variables, sparse records).
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "csgpu.h"
+
+namespace {
+
+thread_local char g_cdf_err[512] = "";
+
+int cdf_fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_cdf_err, sizeof g_cdf_err, fmt, ap);
+  va_end(ap);
+  return CSG_ERR_ARG;
+}
+
+struct VarIndex {
+  std::string name;
+  int32_t data_type = 0, num_elems = 1, max_rec = -1, flags = 0, n_dims = 0;
+  int32_t dims[CSG_CDF_MAX_DIMS] = {0};
+  int32_t varys[CSG_CDF_MAX_DIMS] = {0};
+  int64_t vxr_head = 0, cpr_offset = -1;
+  bool compressed = false;
+  std::vector<uint8_t> pad;  // one element (host byte order), empty when the file has none
+  struct Extent {
+    int32_t first, last;
+    int64_t offset;  // of a VVR / CVVR
+  };
+  std::vector<Extent> extents;
+  bool indexed = false;
+};
+
+}  // namespace
+
+struct csg_cdf {
+  const uint8_t* base = nullptr;  // the (possibly decompressed) file image
+  size_t size = 0;
+  void* map = nullptr;
+  size_t map_size = 0;
+  std::vector<uint8_t> inflated;  // whole-file compression: the image lives here
+  int32_t encoding = 0;
+  bool row_major = true, swap = false;
+  std::vector<VarIndex> vars;
+};
+
+namespace {
+
+inline bool in_range(const csg_cdf* f, int64_t off, int64_t n) {
+  return off >= 0 && n >= 0 && (uint64_t)off + (uint64_t)n <= f->size;
+}
+inline int64_t be64(const uint8_t* p) {
+  uint64_t v = 0;
+  for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+  return (int64_t)v;
+}
+inline int32_t be32(const uint8_t* p) {
+  return (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]);
+}
+
+// bytes of one element of a CDF data type (0: unknown)
+int elem_bytes(int32_t t) {
+  switch (t) {
+    case 1: case 11: case 41: case 51: case 52: return 1;  // INT1, UINT1, BYTE, CHAR, UCHAR
+    case 2: case 12: return 2;                              // INT2, UINT2
+    case 4: case 14: case 21: case 44: return 4;            // INT4, UINT4, REAL4, FLOAT
+    case 8: case 22: case 31: case 33: case 45: return 8;   // INT8, REAL8, EPOCH, TIME_TT2000, DOUBLE
+    case 32: return 16;                                     // EPOCH16 (two doubles)
+    default: return 0;
+  }
+}
+// width of the unit that is byte-swapped (EPOCH16 swaps as two 8-byte halves)
+int swap_unit(int32_t t) { return t == 32 ? 8 : elem_bytes(t); }
+
+// host is little-endian (x86-64 / aarch64 Linux); encodings stored big-endian: NETWORK 1, SUN 2,
+// NeXT 12, PPC 9, SGi 5, IBMRS 7, HP 11; little-endian: DECSTATION 4, IBMPC 6, ALPHAOSF1 13,
+// ALPHAVMSi 16, ARM_LITTLE 17, IA64 variants 19-21.  VAX / Alpha-VMS float formats are not supported.
+int encoding_is_big(int32_t enc) {
+  switch (enc) {
+    case 1: case 2: case 5: case 7: case 9: case 11: case 12: case 18: return 1;
+    case 4: case 6: case 13: case 16: case 17: case 19: case 20: case 21: return 0;
+    default: return -1;
+  }
+}
+
+void swap_copy(uint8_t* dst, const uint8_t* src, size_t n_bytes, int unit) {
+  if (unit == 4) {
+    const uint32_t* s = (const uint32_t*)src;
+    uint32_t* d = (uint32_t*)dst;
+    for (size_t i = 0; i < n_bytes / 4; ++i) d[i] = __builtin_bswap32(s[i]);
+  } else if (unit == 8) {
+    const uint64_t* s = (const uint64_t*)src;
+    uint64_t* d = (uint64_t*)dst;
+    for (size_t i = 0; i < n_bytes / 8; ++i) d[i] = __builtin_bswap64(s[i]);
+  } else if (unit == 2) {
+    const uint16_t* s = (const uint16_t*)src;
+    uint16_t* d = (uint16_t*)dst;
+    for (size_t i = 0; i < n_bytes / 2; ++i) d[i] = __builtin_bswap16(s[i]);
+  } else {
+    memcpy(dst, src, n_bytes);
+  }
+}
+
+int inflate_into(const uint8_t* src, size_t n_src, uint8_t* dst, size_t n_dst, size_t* produced) {
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 15 + 32) != Z_OK) return cdf_fail("inflateInit2 failed");  // zlib or gzip framing
+  zs.next_in = const_cast<Bytef*>(src);
+  zs.avail_in = (uInt)n_src;
+  zs.next_out = dst;
+  zs.avail_out = (uInt)n_dst;
+  const int rc = inflate(&zs, Z_FINISH);
+  *produced = zs.total_out;
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END && !(rc == Z_BUF_ERROR && zs.avail_out == 0)) return cdf_fail("inflate failed (%d)", rc);
+  return CSG_OK;
+}
+
+// record header {int64 size, int32 type} at off
+int rec_header(const csg_cdf* f, int64_t off, int32_t want_type, int64_t* size) {
+  if (!in_range(f, off, 12)) return cdf_fail("record offset %lld outside the file", (long long)off);
+  *size = be64(f->base + off);
+  const int32_t type = be32(f->base + off + 8);
+  if (*size < 12 || !in_range(f, off, *size)) return cdf_fail("record at %lld has a bad size", (long long)off);
+  if (want_type > 0 && type != want_type) return cdf_fail("record at %lld has type %d, expected %d", (long long)off, type, want_type);
+  return CSG_OK;
+}
+
+int parse_vdr(csg_cdf* f, int64_t off, bool z_var, int32_t r_ndims, const int32_t* r_dims, int64_t* next) {
+  int64_t size;
+  int st = rec_header(f, off, z_var ? 8 : 3, &size);
+  if (st != CSG_OK) return st;
+  const uint8_t* p = f->base + off;
+  // size 8 | type 4 | VDRnext 8 | DataType 4 | MaxRec 4 | VXRhead 8 | VXRtail 8 | Flags 4 | SRecords 4 |
+  // rfuB 4 | rfuC 4 | rfuF 4 | NumElems 4 | Num 4 | CPRorSPRoffset 8 | BlockingFactor 4 | Name 256 |
+  // [zNumDims 4 | zDimSizes 4*n] | DimVarys 4*n | PadValue
+  if (size < 12 + 8 + 4 + 4 + 8 + 8 + 4 + 4 + 12 + 4 + 4 + 8 + 4 + 256) return cdf_fail("VDR at %lld too short", (long long)off);
+  VarIndex v;
+  *next = be64(p + 12);
+  v.data_type = be32(p + 20);
+  v.max_rec = be32(p + 24);
+  v.vxr_head = be64(p + 28);
+  v.flags = be32(p + 44);
+  v.num_elems = be32(p + 64);
+  v.cpr_offset = be64(p + 72);
+  char name[257];
+  memcpy(name, p + 84, 256);
+  name[256] = 0;
+  v.name = name;
+  int64_t q = 84 + 256;
+  if (z_var) {
+    v.n_dims = be32(p + q);
+    q += 4;
+    if (v.n_dims < 0 || v.n_dims > CSG_CDF_MAX_DIMS) return cdf_fail("variable %s has %d dimensions", name, v.n_dims);
+    for (int d = 0; d < v.n_dims; ++d, q += 4) v.dims[d] = be32(p + q);
+  } else {
+    v.n_dims = r_ndims;
+    for (int d = 0; d < v.n_dims; ++d) v.dims[d] = r_dims[d];
+  }
+  for (int d = 0; d < v.n_dims; ++d, q += 4) v.varys[d] = be32(p + q);
+  if (q > size) return cdf_fail("VDR of %s overruns its record", name);
+  const int eb = elem_bytes(v.data_type);
+  if (eb == 0) return CSG_OK;  // unknown type: skipped, not an error for the variables we never read
+  v.compressed = (v.flags & 4) != 0;
+  if ((v.flags & 2) && q + (int64_t)eb * v.num_elems <= size) {  // pad value present
+    v.pad.resize((size_t)eb);
+    if (f->swap)
+      swap_copy(v.pad.data(), p + q, (size_t)eb, swap_unit(v.data_type));
+    else
+      memcpy(v.pad.data(), p + q, (size_t)eb);
+  }
+  f->vars.push_back(v);
+  return CSG_OK;
+}
+
+int walk_vxr(const csg_cdf* f, int64_t off, VarIndex& v, int depth) {
+  while (off > 0) {
+    if (depth > 16) return cdf_fail("VXR tree of %s too deep", v.name.c_str());
+    int64_t size;
+    int st = rec_header(f, off, 6, &size);
+    if (st != CSG_OK) return st;
+    const uint8_t* p = f->base + off;
+    const int64_t next = be64(p + 12);
+    const int32_t n_entries = be32(p + 20), n_used = be32(p + 24);
+    if (n_entries < 0 || n_used < 0 || n_used > n_entries || 28 + (int64_t)n_entries * 16 > size)
+      return cdf_fail("VXR at %lld is malformed", (long long)off);
+    const uint8_t* first = p + 28;
+    const uint8_t* last = first + 4 * (int64_t)n_entries;
+    const uint8_t* offs = last + 4 * (int64_t)n_entries;
+    for (int i = 0; i < n_used; ++i) {
+      const int32_t a = be32(first + 4 * i), b = be32(last + 4 * i);
+      const int64_t o = be64(offs + 8 * i);
+      if (!in_range(f, o, 12)) return cdf_fail("VXR entry of %s points outside the file", v.name.c_str());
+      const int32_t type = be32(f->base + o + 8);
+      if (type == 6) {  // a lower level of the index
+        st = walk_vxr(f, o, v, depth + 1);
+        if (st != CSG_OK) return st;
+      } else if (type == 7 || type == 13) {
+        v.extents.push_back({a, b, o});
+      } else {
+        return cdf_fail("VXR entry of %s has record type %d", v.name.c_str(), type);
+      }
+    }
+    off = next;
+  }
+  return CSG_OK;
+}
+
+int parse_image(csg_cdf* f) {
+  if (f->size < 8 + 56) return cdf_fail("file too short to be a CDF");
+  const uint32_t magic = (uint32_t)be32(f->base), flag = (uint32_t)be32(f->base + 4);
+  if (magic != 0xCDF30001u) return cdf_fail("not a CDF v3 file (magic %08x)", magic);
+  if (flag == 0xCCCC0001u) {
+    // CCR: size 8 | type 4 (=10) | CPRoffset 8 | uSize 8 | rfuA 4 | data;  CPR: size 8 | type 4 (=11) | cType 4 | ...
+    int64_t size;
+    const csg_cdf tmp_view = *f;
+    (void)tmp_view;
+    int st = rec_header(f, 8, 10, &size);
+    if (st != CSG_OK) return st;
+    const int64_t cpr = be64(f->base + 8 + 12), usize = be64(f->base + 8 + 20);
+    int64_t cpr_size;
+    st = rec_header(f, cpr, 11, &cpr_size);
+    if (st != CSG_OK) return st;
+    if (be32(f->base + cpr + 12) != 5) return cdf_fail("whole-file compression type %d is not gzip", be32(f->base + cpr + 12));
+    if (usize < 0 || usize > ((int64_t)1 << 36)) return cdf_fail("implausible uncompressed size");
+    std::vector<uint8_t> image((size_t)usize + 8);
+    memcpy(image.data(), f->base, 4);
+    const uint32_t plain = 0x0000FFFFu;
+    image[4] = (uint8_t)(plain >> 24), image[5] = (uint8_t)(plain >> 16), image[6] = (uint8_t)(plain >> 8), image[7] = (uint8_t)plain;
+    size_t produced = 0;
+    st = inflate_into(f->base + 8 + 32, (size_t)(size - 32), image.data() + 8, (size_t)usize, &produced);
+    if (st != CSG_OK) return st;
+    if ((int64_t)produced != usize) return cdf_fail("whole-file inflate produced %zu of %lld bytes", produced, (long long)usize);
+    f->inflated.swap(image);
+    f->base = f->inflated.data();
+    f->size = f->inflated.size();
+  } else if (flag != 0x0000FFFFu) {
+    return cdf_fail("unknown CDF compression flag %08x", flag);
+  }
+  int64_t size;
+  int st = rec_header(f, 8, 1, &size);  // CDR
+  if (st != CSG_OK) return st;
+  const uint8_t* cdr = f->base + 8;
+  const int64_t gdr_off = be64(cdr + 12);
+  f->encoding = be32(cdr + 28);
+  const int32_t cdr_flags = be32(cdr + 32);
+  f->row_major = (cdr_flags & 1) != 0;
+  const int big = encoding_is_big(f->encoding);
+  if (big < 0) return cdf_fail("CDF encoding %d is not supported (IEEE big / little endian only)", f->encoding);
+  f->swap = big == 1;
+  st = rec_header(f, gdr_off, 2, &size);  // GDR
+  if (st != CSG_OK) return st;
+  const uint8_t* g = f->base + gdr_off;
+  // size 8 | type 4 | rVDRhead 8 | zVDRhead 8 | ADRhead 8 | eof 8 | NrVars 4 | NumAttr 4 | rMaxRec 4 | rNumDims 4 |
+  // NzVars 4 | UIRhead 8 | rfuC 4 | LeapSecondLastUpdated 4 | rfuE 4 | rDimSizes 4*n
+  const int64_t r_head = be64(g + 12), z_head = be64(g + 20);
+  const int32_t r_ndims = be32(g + 56);
+  int32_t r_dims[CSG_CDF_MAX_DIMS] = {0};
+  if (r_ndims < 0 || r_ndims > CSG_CDF_MAX_DIMS || 84 + 4 * (int64_t)r_ndims > size) return cdf_fail("GDR is malformed");
+  for (int d = 0; d < r_ndims; ++d) r_dims[d] = be32(g + 84 + 4 * d);
+  for (int pass = 0; pass < 2; ++pass) {
+    int64_t off = pass == 0 ? z_head : r_head;
+    int guard = 0;
+    while (off > 0) {
+      if (++guard > 100000) return cdf_fail("VDR list does not terminate");
+      int64_t next = 0;
+      st = parse_vdr(f, off, pass == 0, r_ndims, r_dims, &next);
+      if (st != CSG_OK) return st;
+      off = next;
+    }
+  }
+  return CSG_OK;
+}
+
+VarIndex* find_var(csg_cdf* f, const char* name) {
+  for (auto& v : f->vars)
+    if (v.name == name) return &v;
+  return nullptr;
+}
+
+int64_t values_per_record(const VarIndex& v) {
+  int64_t n = 1;
+  for (int d = 0; d < v.n_dims; ++d)
+    if (v.varys[d]) n *= v.dims[d];
+  return n * (v.num_elems > 0 && (v.data_type == 51 || v.data_type == 52) ? v.num_elems : 1);
+}
+
+// copy `count` records starting at file record `rec` out of the extent's VVR / CVVR into dst (host order)
+int read_extent(csg_cdf* f, const VarIndex& v, const VarIndex::Extent& ex, int32_t rec, int32_t count, uint8_t* dst,
+                size_t rec_bytes, std::vector<uint8_t>& scratch) {
+  int64_t size;
+  int st = rec_header(f, ex.offset, 0, &size);
+  if (st != CSG_OK) return st;
+  const int32_t type = be32(f->base + ex.offset + 8);
+  const size_t skip = (size_t)(rec - ex.first) * rec_bytes, want = (size_t)count * rec_bytes;
+  const int unit = swap_unit(v.data_type);
+  const uint8_t* src = nullptr;
+  if (type == 7) {
+    if ((int64_t)(12 + skip + want) > size) return cdf_fail("VVR of %s is shorter than its index entry says", v.name.c_str());
+    src = f->base + ex.offset + 12 + skip;
+  } else {
+    // CVVR: size 8 | type 4 | rfuA 4 | cSize 8 | data
+    const int64_t csize = be64(f->base + ex.offset + 16);
+    if (csize < 0 || 24 + csize > size) return cdf_fail("CVVR of %s is malformed", v.name.c_str());
+    const size_t full = (size_t)(ex.last - ex.first + 1) * rec_bytes;
+    if (skip == 0 && want == full && !f->swap) {  // inflate straight into the destination
+      size_t produced = 0;
+      st = inflate_into(f->base + ex.offset + 24, (size_t)csize, dst, want, &produced);
+      if (st != CSG_OK) return st;
+      if (produced != want) return cdf_fail("CVVR of %s inflated to %zu of %zu bytes", v.name.c_str(), produced, want);
+      return CSG_OK;
+    }
+    scratch.resize(full);
+    size_t produced = 0;
+    st = inflate_into(f->base + ex.offset + 24, (size_t)csize, scratch.data(), full, &produced);
+    if (st != CSG_OK) return st;
+    if (produced < skip + want) return cdf_fail("CVVR of %s inflated to %zu bytes, need %zu", v.name.c_str(), produced, skip + want);
+    src = scratch.data() + skip;
+  }
+  if (f->swap)
+    swap_copy(dst, src, want, unit);
+  else
+    memcpy(dst, src, want);
+  return CSG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* csg_cdf_last_error(void) { return g_cdf_err; }
+
+int csg_cdf_open(const char* path, csg_cdf** out) {
+  if (!path || !out) return cdf_fail("csg_cdf_open: NULL argument");
+  *out = nullptr;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return cdf_fail("cannot open %s: %s", path, strerror(errno));
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+    close(fd);
+    return cdf_fail("cannot stat %s (or empty file)", path);
+  }
+  void* map = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return cdf_fail("mmap of %s failed: %s", path, strerror(errno));
+  madvise(map, (size_t)sb.st_size, MADV_SEQUENTIAL);
+  csg_cdf* f = new csg_cdf();
+  f->map = map, f->map_size = (size_t)sb.st_size;
+  f->base = (const uint8_t*)map, f->size = (size_t)sb.st_size;
+  const int st = parse_image(f);
+  if (st != CSG_OK) {
+    csg_cdf_close(f);
+    return st;
+  }
+  *out = f;
+  return CSG_OK;
+}
+
+void csg_cdf_close(csg_cdf* f) {
+  if (!f) return;
+  if (f->map) munmap(f->map, f->map_size);
+  delete f;
+}
+
+int csg_cdf_var_count(csg_cdf* f) { return f ? (int)f->vars.size() : 0; }
+
+int csg_cdf_var_info(csg_cdf* f, const char* name, int index, csg_cdf_var* info) {
+  if (!f || !info) return cdf_fail("csg_cdf_var_info: NULL argument");
+  VarIndex* v = name ? find_var(f, name) : (index >= 0 && index < (int)f->vars.size() ? &f->vars[(size_t)index] : nullptr);
+  if (!v) return cdf_fail("variable %s not found", name ? name : "(index out of range)");
+  memset(info, 0, sizeof *info);
+  snprintf(info->name, sizeof info->name, "%s", v->name.c_str());
+  info->data_type = v->data_type;
+  info->elem_bytes = elem_bytes(v->data_type);
+  info->n_records = (int64_t)v->max_rec + 1;
+  info->rec_vary = (v->flags & 1) != 0;
+  info->compressed = v->compressed;
+  info->n_dims = 0;
+  for (int d = 0; d < v->n_dims; ++d)
+    if (v->varys[d]) info->dims[info->n_dims++] = v->dims[d];  // non-varying dimensions are dropped, like cdflib does
+  info->values_per_record = values_per_record(*v);
+  info->row_major = f->row_major;
+  return CSG_OK;
+}
+
+int csg_cdf_read(csg_cdf* f, const char* name, int64_t rec0, int64_t n_rec, void* dst, size_t dst_bytes) {
+  if (!f || !name || (!dst && n_rec > 0)) return cdf_fail("csg_cdf_read: NULL argument");
+  VarIndex* v = find_var(f, name);
+  if (!v) return cdf_fail("variable %s not found", name);
+  const int eb = elem_bytes(v->data_type);
+  if (eb == 0) return cdf_fail("variable %s has unsupported data type %d", name, v->data_type);
+  const int64_t per = values_per_record(*v);
+  const size_t rec_bytes = (size_t)per * (size_t)eb;
+  if (rec0 < 0 || n_rec < 0 || rec0 + n_rec > (int64_t)v->max_rec + 1)
+    return cdf_fail("records [%lld, %lld) of %s out of range (%d written)", (long long)rec0, (long long)(rec0 + n_rec), name, v->max_rec + 1);
+  if (dst_bytes < rec_bytes * (size_t)n_rec) return cdf_fail("destination too small for %s", name);
+  if (n_rec == 0) return CSG_OK;
+  if (!f->row_major && v->n_dims > 1) {
+    int varying = 0;
+    for (int d = 0; d < v->n_dims; ++d) varying += v->varys[d] ? 1 : 0;
+    if (varying > 1) return cdf_fail("variable %s is column-major: not supported", name);
+  }
+  if (!v->indexed) {
+    int st = walk_vxr(f, v->vxr_head, *v, 0);
+    if (st != CSG_OK) return st;
+    v->indexed = true;
+  }
+  uint8_t* out = (uint8_t*)dst;
+  // sparse / never-written records: the pad value (zeros when the file has none)
+  std::vector<uint8_t> covered((size_t)n_rec, 0);
+  std::vector<uint8_t> scratch;
+  for (const auto& ex : v->extents) {
+    const int64_t a = ex.first > rec0 ? ex.first : rec0;
+    const int64_t b = (int64_t)ex.last < rec0 + n_rec - 1 ? (int64_t)ex.last : rec0 + n_rec - 1;
+    if (a > b) continue;
+    int st = read_extent(f, *v, ex, (int32_t)a, (int32_t)(b - a + 1), out + (size_t)(a - rec0) * rec_bytes, rec_bytes, scratch);
+    if (st != CSG_OK) return st;
+    memset(covered.data() + (a - rec0), 1, (size_t)(b - a + 1));
+  }
+  for (int64_t r = 0; r < n_rec; ++r) {
+    if (covered[(size_t)r]) continue;
+    uint8_t* p = out + (size_t)r * rec_bytes;
+    if (v->pad.empty()) {
+      memset(p, 0, rec_bytes);
+    } else {
+      for (int64_t i = 0; i < per; ++i) memcpy(p + (size_t)i * eb, v->pad.data(), (size_t)eb);
+    }
+  }
+  return CSG_OK;
+}
+
+}  // extern "C"

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 16
+#define CSG_ABI_VERSION 17
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -491,6 +491,35 @@ CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_ca
 /* d_packed + d_offsets[s] <- slot s (d_offsets: exclusive prefix sum of d_sizes, from the host). */
 CSG_API int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets,
                     int n_segments, uint8_t* d_packed);
+
+/* ------------------------------------------------ ingest: native CDF v3 reader (host only) */
+/* Replaces the four cdflib `varget` calls of load_fast_cdf_dataset (CS/cdf_utils.py:247-251) for the
+ * batch path: the file is memory-mapped once, the variable index (zVDR / rVDR -> VXR -> VVR / CVVR)
+ * is walked and only the records asked for are copied or inflated (gzip) into caller memory -- a
+ * pinned staging slot -- in host byte order, row-major.  `energy[0,0,:]` and `pitch_angle[0,:,0]`
+ * (CS/cdf_utils.py:252-253) need record 0 only, not the data-sized variables the reference decodes.
+ * Thread-safe per handle (one handle per thread); errors: csg_cdf_last_error() (thread-local).
+ * See csrc/cdf.cpp for the supported subset (IEEE encodings, row-major, plain / gzip). */
+#define CSG_CDF_MAX_DIMS 8
+typedef struct csg_cdf csg_cdf;
+typedef struct {
+  char name[260];
+  int32_t data_type;  /* CDF data type code: 21/44 REAL4/FLOAT, 22/45 REAL8/DOUBLE, 31 EPOCH, 33 TT2000, 4 INT4 ... */
+  int32_t elem_bytes; /* bytes of one value; 0 = unsupported type                                            */
+  int32_t n_dims;     /* varying dimensions of one record                                                    */
+  int32_t dims[CSG_CDF_MAX_DIMS];
+  int32_t rec_vary, compressed, row_major;
+  int64_t n_records;         /* records written (MaxRec + 1)                                                 */
+  int64_t values_per_record; /* product of dims                                                              */
+} csg_cdf_var;               /* 336 bytes */
+CSG_API int csg_cdf_open(const char* path, csg_cdf** out);
+CSG_API void csg_cdf_close(csg_cdf* cdf);
+CSG_API int csg_cdf_var_count(csg_cdf* cdf);
+/* by name, or by index when name is NULL */
+CSG_API int csg_cdf_var_info(csg_cdf* cdf, const char* name, int index, csg_cdf_var* info);
+/* records [rec0, rec0 + n_rec) of the variable -> h_dst (n_rec * values_per_record * elem_bytes bytes) */
+CSG_API int csg_cdf_read(csg_cdf* cdf, const char* name, int64_t rec0, int64_t n_rec, void* h_dst, size_t dst_bytes);
+CSG_API const char* csg_cdf_last_error(void);
 
 #ifdef __cplusplus
 }

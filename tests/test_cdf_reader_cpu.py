@@ -1,0 +1,106 @@
+"""CPU: the native CDF v3 reader (``csrc/cdf.cpp`` through the C ABI) against files written by
+``tests/cdf_writer.py`` -- encodings, gzip variables, index shapes, sparse records, whole-file
+compression -- and ``load_fast_cdf_dataset`` on a real (synthetic-content) ``.cdf`` file."""
+
+import numpy as np
+import pytest
+
+from tests import cdf_writer as W
+
+
+def _vars(rng, n_rec=37):
+    return [
+        {"name": "time_unix", "data": 946684800.0 + 2.5 * np.arange(n_rec)},
+        {"name": "data", "data": rng.gamma(2.0, 3.0, (n_rec, 5, 7)).astype(np.float32)},
+        {"name": "counts", "data": rng.integers(-5, 1000, (n_rec, 3), dtype=np.int32)},
+        {"name": "scalar64", "data": rng.integers(0, 2**40, (n_rec,), dtype=np.int64)},
+    ]
+
+
+@pytest.mark.parametrize("encoding", [W.NETWORK, W.IBMPC])
+@pytest.mark.parametrize("gzip", [None, 6])
+@pytest.mark.parametrize("file_gzip", [False, True])
+def test_reader_round_trip(tmp_path, encoding, gzip, file_gzip):
+    from configurable_spectrograms_b200.cdf_reader import CdfFile, is_cdf_v3
+
+    rng = np.random.default_rng(5)
+    variables = _vars(rng)
+    for v in variables:
+        v["gzip"] = gzip
+        v["records_per_block"] = 8  # several VVR / CVVR per variable, chained VXRs of 3 entries
+    variables[1]["two_level"] = True
+    path = tmp_path / "t.cdf"
+    W.write_cdf(path, variables, encoding=encoding, file_gzip=file_gzip)
+    assert is_cdf_v3(str(path))
+    with CdfFile(str(path)) as cdf:
+        assert cdf.variables() == [v["name"] for v in variables]
+        for v in variables:
+            assert cdf.shape(v["name"]) == v["data"].shape
+            got = cdf.read(v["name"])
+            assert got.dtype == v["data"].dtype and np.array_equal(got, v["data"])
+            # a window that starts and ends inside blocks
+            part = cdf.read(v["name"], 5, 20)
+            assert np.array_equal(part, v["data"][5:25])
+        # decode into caller memory (the pinned-slot path)
+        out = np.empty(37 * 5 * 7 + 11, dtype=np.float32)
+        view = cdf.read("data", out=out)
+        assert view.base is not None and np.array_equal(view, variables[1]["data"])
+        with pytest.raises(KeyError):
+            cdf.shape("nope")
+        with pytest.raises(Exception):
+            cdf.read("data", 30, 20)
+
+
+def test_reader_sparse_records_and_pad(tmp_path):
+    from configurable_spectrograms_b200.cdf_reader import CdfFile
+
+    rng = np.random.default_rng(6)
+    a = rng.normal(size=(20, 4)).astype(np.float32)
+    b = rng.normal(size=(20, 4))
+    path = tmp_path / "s.cdf"
+    W.write_cdf(path, [
+        {"name": "a", "data": a, "sparse": {3, 4, 11}, "pad": np.float32(-1e31), "records_per_block": 5},
+        {"name": "b", "data": b, "sparse": {0, 19}, "gzip": 1, "records_per_block": 4},
+    ], encoding=W.NETWORK)
+    with CdfFile(str(path)) as cdf:
+        want = a.copy()
+        want[[3, 4, 11]] = np.float32(-1e31)
+        assert np.array_equal(cdf.read("a"), want)
+        want = b.copy()
+        want[[0, 19]] = 0.0  # no pad value in the file: zeros
+        assert np.array_equal(cdf.read("b"), want)
+
+
+def test_reader_rejects_non_cdf(tmp_path):
+    from configurable_spectrograms_b200 import _lib
+    from configurable_spectrograms_b200.cdf_reader import CdfFile, is_cdf_v3
+
+    p = tmp_path / "x.cdf"
+    p.write_bytes(b"")
+    assert not is_cdf_v3(str(p))
+    with pytest.raises(_lib.CsgError):
+        CdfFile(str(p))
+    p.write_bytes(b"\xcd\xf3\x00\x01\x00\x00\xff\xff" + b"\0" * 100)
+    with pytest.raises(_lib.CsgError):
+        CdfFile(str(p))
+
+
+@pytest.mark.parametrize("stored_layout", ["tpe", "tep"])
+def test_load_fast_cdf_dataset_from_a_cdf_file(tmp_path, stored_layout):
+    """``load_fast_cdf_dataset`` on a binary CDF equals the side-car path on the same arrays
+    (``CS/cdf_utils.py:247-256``: 1-D bins from record 0, conditional transpose to a (T,P,E) view)."""
+    from configurable_spectrograms_b200 import synth
+    from configurable_spectrograms_b200.cdf_utils import load_fast_cdf_dataset
+    from tests.helpers import dataset_from_arrays
+
+    rng = np.random.default_rng(8)
+    arrays = synth.make_file_arrays(rng, "ees", n_time=50, quirks=True, stored_layout=stored_layout)
+    path = tmp_path / synth.fast_filename("ees", arrays["time_unix"][0], 777)
+    W.write_fast_cdf(path, arrays, encoding=W.NETWORK, gzip=6, records_per_block=16)
+    ds = load_fast_cdf_dataset(str(path))
+    ref = dataset_from_arrays(arrays)
+    for key in ("times", "energy", "pitch_angle"):
+        assert np.array_equal(ds[key], ref[key], equal_nan=True), key
+    assert ds["data"].shape == ref["data"].shape and ds["data"].dtype == ref["data"].dtype
+    assert ds["data"].flags.c_contiguous == ref["data"].flags.c_contiguous  # the transposed view is kept a view
+    assert np.array_equal(ds["data"], ref["data"], equal_nan=True)
