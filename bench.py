@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-png", action="store_true")
     ap.add_argument("--png-orbits", type=int, default=8, help="orbits whose figures (20 each) go through the device PNG stage")
     ap.add_argument("--seed", type=int, default=4)
+    ap.add_argument("--no-api-e2e", action="store_true", help="skip the public-API end-to-end leg (directory of .npz side-cars -> PNGs on disk)")
+    ap.add_argument("--api-orbits", type=int, default=0, help="orbits of the api_e2e directory (default: --orbits-per-gpu)")
+    ap.add_argument("--api-ref", action="store_true", help="also run the unmodified reference over the SAME api_e2e directory (minutes)")
     ap.add_argument("--no-verify", action="store_true", help="skip the parity leg (outside the timed region)")
     ap.add_argument("--verify-orbits", type=int, default=3, help="orbits of this shard whose every panel is compared with the oracle")
     ap.add_argument("--profile-host", default=None, help="write a cProfile of the timed step loop to this path")
@@ -476,6 +479,107 @@ def verify_shard(args, torch, cubes, files, orbits, shard, step, state, lut, ran
     return out
 
 
+# ----------------------------------------------------------------------------------------
+# api_e2e: the call a user makes -- FAST_plot_spectrograms_directory on a directory -> PNGs on disk
+# ----------------------------------------------------------------------------------------
+def write_api_directory(work, cubes, files, orbits, n_orbits):
+    """The first ``n_orbits`` orbits of this rank's synthetic shard as a FAST tree: empty ``.cdf`` markers +
+    ``.cdf.npz`` side-cars (what both arms read; CDF decoding itself is out of scope) + the cusp TSV."""
+    from concurrent.futures import ThreadPoolExecutor
+    from datetime import datetime, timezone
+
+    from configurable_spectrograms_b200 import synth
+
+    root = os.path.join(work, "FAST_data")
+    rows = [synth.CUSP_CSV_COLUMNS]
+    jobs = []
+    for ob in orbits[:n_orbits]:
+        start = float(ob["files"][ORDER[0]]["times"][0])
+        dt = datetime.fromtimestamp(start, tz=timezone.utc)
+        folder = os.path.join(root, f"{dt.year:04d}", f"{dt.month:02d}")
+        os.makedirs(folder, exist_ok=True)
+        cells = {}
+        for inst in ORDER:
+            fd = ob["files"][inst]
+            f = files[fd["index"]]
+            path = os.path.join(folder, synth.fast_filename(inst, start, ob["orbit"]))
+            jobs.append((path, f, fd))
+            cells[inst] = (os.path.basename(path),) + (tuple(str(v) for v in f["win"]) if f["win"] else ("", ""))
+        rows.append("\t".join([str(ob["orbit"]), folder, f"fa_k0_orb_{ob['orbit']}_v01.cdf", "0", "0"]
+                              + [x for inst in ("eeb", "ees", "ieb", "ies") for x in ("True",) + cells[inst]]))
+
+    def write(job):
+        path, f, fd = job
+        open(path, "wb").close()
+        np.savez(path + ".npz", time_unix=fd["times"], data=_host_cube(cubes, f),
+                 energy=np.asarray(fd["energy"], np.float32)[None, None, :], pitch_angle=np.asarray(fd["pitch_angle"], np.float32)[None, :, None])
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        list(pool.map(write, jobs))
+    with open(os.path.join(work, "FAST_Cusp_Indices.csv"), "w") as fh:
+        fh.write("\n".join(rows) + "\n")
+    return len(jobs)
+
+
+def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
+    """Wall clock of the public API on a fresh directory: discovery, streaming ingest through pinned
+    slots, K1, the global-extrema pre-pass, planning, K2a, K3, K4 and the PNG files on disk."""
+    import shutil
+
+    from configurable_spectrograms_b200 import cdf_utils
+    from configurable_spectrograms_b200.fast.batch_directory import FAST_plot_spectrograms_directory
+
+    n = min(args.api_orbits or args.orbits_per_gpu, len(orbits))
+    work = scratch_dir("csg_api_")
+    cwd = os.getcwd()
+    try:
+        t0 = time.perf_counter()
+        n_files = write_api_directory(work, cubes, files, orbits, n)
+        t_write = time.perf_counter() - t0
+        os.chdir(work)
+        out = {}
+        for label in ("cold", "warm"):  # cold: first call of the process (plans, scratch, page cache); warm: steady state
+            for name in ("progress.json", "FAST_calculated_extrema.json"):
+                if os.path.exists(name):
+                    os.remove(name)
+            shutil.rmtree("FAST_plots", ignore_errors=True)
+            cdf_utils.filtered_orbits_cache.clear()
+            cdf_utils.orbit_column_cache.clear()
+            phases: dict = {}
+            t0 = time.perf_counter()
+            res = FAST_plot_spectrograms_directory(
+                "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", zoom_duration_minutes=6, colormap="turbo",
+                max_processing_percentile=99, max_workers=16, progress_json_path="./progress.json", verbose=False, _timings=phases,
+            )
+            sec = time.perf_counter() - t0
+            bad = [r for r in res if r.get("status") != "ok"]
+            pngs = sum(len(fs) for _d, _s, fs in os.walk("./FAST_plots"))
+            png_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _s, fs in os.walk("./FAST_plots") for f in fs)
+            got = json.load(open("./FAST_calculated_extrema.json"))
+            out[label] = {"seconds": sec, "orbits_per_s": n / sec, "pngs": pngs, "png_mb": png_bytes / 1e6, "errors": len(bad),
+                          "phases_s": {k: round(v, 4) for k, v in phases.items()}}
+        # the same extrema as the device-resident arm computed for these orbits?  (only when the directory IS the shard)
+        same = None
+        if n == len(orbits) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            same = all(got.get(k) == v for k, v in state.items() if k.endswith(("_z_max", "_y_max")))
+        line = {"value": out["warm"]["orbits_per_s"], "unit": "orbits/s", "orbits": n, "files": n_files,
+                "input_gb": sum(files[fd["index"]]["T"] for ob in orbits[:n] for fd in ob["files"].values()) * P * E * 4 / 1e9,
+                "directory_write_s": round(t_write, 2), "cold": out["cold"], "warm": out["warm"], "extrema_equal_device_arm": same,
+                "what": "FAST_plot_spectrograms_directory(dir, max_processing_percentile=99, turbo) on .npz side-cars in tmpfs -> "
+                        "PNG files (cell-resolution mosaics) on tmpfs; everything inside the clock"}
+        if with_reference:
+            from oracle import ref_driver as RD
+
+            if RD.available():
+                r = RD.run_directory(work, workers=os.cpu_count() or 1, render="cell")
+                line["reference_same_directory"] = {"seconds": r["seconds"], "orbits_per_s": n / r["seconds"], "pngs": r["pngs"],
+                                                    "png_mb": r["png_bytes"] / 1e6, "cores": r["workers"], "kind": "reference"}
+        return line
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def bind_near_gpu(torch, local):
     """Multi-rank runs: keep this process (and so the first-touch placement of its pinned staging
     buffers) on the CPUs of the GPU's NUMA node, so every rank's H2D traffic stays on its own socket."""
@@ -740,6 +844,11 @@ def main():
         e2e = {"value": total_orbits / (float(dt.item()) / n_e2e), "unit": "orbits/s",
                "h2d_bytes_per_step": int(cube_bytes), "d2h_bytes_per_step": int(n_px * 4), "steps": n_e2e}
 
+    # ------------------------------------------------ api_e2e: the public call, directory -> PNG files
+    api = None
+    if rank == 0 and world == 1 and not args.no_api_e2e:
+        api = api_e2e_leg(args, cubes, files, orbits, state, args.api_ref)
+
     # ----------------------------------------------------------- CPU baseline beside it
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -773,7 +882,7 @@ def main():
                          "read_stream_peak": 7488.6, "frac_of_read_stream_peak": achieved / 7488.6},
             "step_roofline": {"algorithmic_bytes": int(step_bytes), "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "note": "this rank's whole step (K1+K2b+K2a+K3), SURVEY 8(d) B_orbit x orbits / step time"},
-            "parity_checked": parity, "png_stage": png_stage, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+            "parity_checked": parity, "png_stage": png_stage, "e2e": e2e, "api_e2e": api, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
             "stage_ms": {"collapse": k1_ms, "pool_extrema": pool_ms, "region_stats": stats_ms, "panel_prepare": prep_ms,
                          "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,
                          "percentile_regions_needing_radix_fallback": fallbacks},

@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -162,6 +162,7 @@ SIGNATURES = {
     "csg_host_unregister": (_i, [_vp, _vp]),
     "csg_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "csg_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "csg_d2d": (_i, [_vp, _vp, _vp, _sz]),
     "csg_memset": (_i, [_vp, _vp, _i, _sz]),
     "csg_d2h_side": (_i, [_vp, _vp, _vp, _sz]),
     "csg_side_join": (_i, [_vp]),
@@ -296,11 +297,14 @@ class DevBuf:
         except Exception:
             pass
 
-    def upload(self, arr: np.ndarray, offset: int = 0):
+    def upload(self, arr: np.ndarray, offset: int = 0, keep: bool = True):
+        """Asynchronous H2D on the context stream.  ``keep=False``: the caller owns the source's lifetime
+        (pinned staging slots; pageable sources are staged by the driver before the call returns)."""
         arr = np.ascontiguousarray(arr)
         assert offset + arr.nbytes <= self.nbytes, (offset, arr.nbytes, self.nbytes)
         self.ctx._check(self.ctx.lib.csg_h2d(self.ctx.handle, self.ptr + offset, arr.ctypes.data, arr.nbytes))
-        self.ctx._keep(arr)
+        if keep:
+            self.ctx._keep(arr)
 
     def download(self, dtype, count: int, offset: int = 0, sync: bool = True) -> np.ndarray:
         out = np.empty(count, dtype=dtype)
@@ -340,6 +344,69 @@ class PinnedBuf:
             self.free()
         except Exception:
             pass
+
+
+class PinnedRing:
+    """Pinned staging slots for streaming ingest (north_star: "cdflib arrays staged into pinned buffers").
+
+    Loader threads decode cubes straight into the current slot (:meth:`alloc` is a thread-safe bump
+    allocator handing out numpy views of page-locked memory), the main thread enqueues the asynchronous
+    H2D copies + K1 of that chunk and calls :meth:`release`, which records an event on the context
+    stream; :meth:`acquire` of the same slot, ``n_slots`` chunks later, waits for that event only -- so
+    decoding chunk k+1 overlaps the copies of chunk k and nothing is ever overwritten while in flight.
+    """
+
+    FIRST_EVENT = 8  # csg_event slots 8 .. 8 + n_slots - 1 (30 / 31 belong to the pool selector)
+
+    def __init__(self, ctx: "Context", n_slots: int = 3, slot_bytes: int = 1 << 30):
+        import threading
+
+        if not 1 <= n_slots <= 16:
+            raise ValueError("n_slots must be 1..16")
+        self.ctx = ctx
+        self.slot_bytes = int(slot_bytes)
+        self.slots = [ctx.pinned(self.slot_bytes) for _ in range(n_slots)]
+        self._used = [0] * n_slots
+        self._in_flight = [False] * n_slots
+        self._next = 0
+        self._lock = threading.Lock()
+        self.overflow_bytes = 0  # cubes that did not fit a slot and went through pageable memory
+
+    def acquire(self) -> int:
+        """The next slot, empty and safe to write (blocks until its previous copies have finished)."""
+        k = self._next
+        self._next = (k + 1) % len(self.slots)
+        if self._in_flight[k]:
+            self.ctx.event_sync(self.FIRST_EVENT + k)
+            self._in_flight[k] = False
+        self._used[k] = 0
+        return k
+
+    def alloc(self, slot: int, shape, dtype) -> np.ndarray:
+        """A C-contiguous array of ``shape`` inside the slot (256-byte aligned); pageable memory when the
+        slot is full -- slower to upload, never wrong."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        with self._lock:
+            off = (self._used[slot] + 255) & ~255
+            if off + n > self.slot_bytes:
+                self.overflow_bytes += n
+                return np.empty(shape, dtype=dt)
+            self._used[slot] = off + n
+        return self.slots[slot].array[off : off + n].view(dt).reshape(shape)
+
+    def release(self, slot: int):
+        """Call after the slot's copies have been enqueued on the context stream."""
+        self.ctx.event_record(self.FIRST_EVENT + slot)
+        self._in_flight[slot] = True
+
+    def close(self):
+        for k, busy in enumerate(self._in_flight):
+            if busy:
+                self.ctx.event_sync(self.FIRST_EVENT + k)
+        for s in self.slots:
+            s.free()
+        self.slots = []
 
 
 class Context:

@@ -36,8 +36,7 @@ def _read_variables(cdf_path: str, names, data_alloc=None) -> list[np.ndarray]:
             return [cdf.read(n) for n in names]
     side_car = str(cdf_path) + ".npz"
     if os.path.exists(side_car):
-        with np.load(side_car) as z:
-            return [np.asarray(z[n]) for n in names]
+        return _read_npz(side_car, names, data_alloc)
     try:
         import cdflib
     except ImportError as exc:
@@ -46,6 +45,43 @@ def _read_variables(cdf_path: str, names, data_alloc=None) -> list[np.ndarray]:
         ) from exc
     with cdflib.CDF(cdf_path) as cdf:
         return [np.asarray(cdf.varget(n)) for n in names]
+
+
+def _read_npz(side_car: str, names, data_alloc=None) -> list[np.ndarray]:
+    """Members of an ``np.savez`` archive.  With ``data_alloc`` the (uncompressed, C-ordered) ``data``
+    member is read from the file straight into the memory the allocator hands out -- one pass over the
+    bytes, no intermediate array, no CRC pass -- which is what staging into pinned slots wants; every
+    other case goes through ``np.load``."""
+    if data_alloc is not None and "data" in names:
+        import zipfile
+        from numpy.lib import format as npy_format
+
+        try:
+            with zipfile.ZipFile(side_car) as zf:
+                info = zf.getinfo("data.npy")
+                direct = info.compress_type == zipfile.ZIP_STORED
+            if direct:
+                with open(side_car, "rb") as f:
+                    f.seek(info.header_offset)
+                    local = f.read(30)
+                    name_len, extra_len = int.from_bytes(local[26:28], "little"), int.from_bytes(local[28:30], "little")
+                    f.seek(info.header_offset + 30 + name_len + extra_len)
+                    version = npy_format.read_magic(f)
+                    shape, fortran, dtype = (npy_format.read_array_header_1_0(f) if version == (1, 0)
+                                             else npy_format.read_array_header_2_0(f))
+                    if not fortran and not dtype.hasobject:
+                        out = data_alloc(shape, dtype)
+                        if out is not None and out.flags.c_contiguous:
+                            flat = out.reshape(-1).view(np.uint8)
+                            got = f.readinto(memoryview(flat))
+                            if got != flat.nbytes:
+                                raise OSError(f"{side_car}: data.npy is truncated ({got} of {flat.nbytes} bytes)")
+                            with np.load(side_car) as z:
+                                return [out if n == "data" else np.asarray(z[n]) for n in names]
+        except (KeyError, ValueError, zipfile.BadZipFile):
+            pass  # not the layout np.savez writes: the generic path below decides
+    with np.load(side_car) as z:
+        return [np.asarray(z[n]) for n in names]
 
 
 def load_filtered_orbits(csv_path: str = FILTERED_ORBITS_CSV_PATH):

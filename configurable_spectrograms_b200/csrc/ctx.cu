@@ -220,6 +220,11 @@ int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   CSG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return CSG_OK;
 }
+int csg_d2d(csg_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return CSG_OK;
+  CSG_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return CSG_OK;
+}
 int csg_d2h_side(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   if (!ctx) return CSG_ERR_ARG;
   if (bytes == 0) return CSG_OK;

@@ -255,6 +255,21 @@ __device__ __forceinline__ float fast_log2(float x) {
 __device__ __forceinline__ void lds(float& v, unsigned addr) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); }
 __device__ __forceinline__ void lds(double& v, unsigned addr) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); }
 
+// The out-of-line half of the rasteriser's value -> threshold-count lookup: walk the lane's own table
+// column from a wrong first guess; NaN (it fails every comparison) counts as 258 = "bad".
+template <typename T>
+__device__ __forceinline__ int recount(T v, int n, unsigned thr_col) {
+  if (is_nan(v)) return 258;
+  auto thr_at = [&](int row) -> T {
+    T t;
+    lds(t, thr_col + (unsigned)row * (32u * (unsigned)sizeof(T)));
+    return t;
+  };
+  while (n > 0 && !(thr_at(n) <= v)) --n;
+  while (n < kThr && thr_at(n + 1) <= v) ++n;
+  return n;
+}
+
 template <bool B>
 struct Flag {
   static constexpr bool value = B;
@@ -290,8 +305,11 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
   }
   // explicit shared-window addresses of this lane's table columns: row r of a table is 32 words
   // (128 bytes for float32 / the LUT) further on -- one add and one ld.shared per lookup
-  const unsigned thr_col = (unsigned)__cvta_generic_to_shared(s_thr + lane);  // row r (threshold k = r - 1)
-  const unsigned lut_col = (unsigned)__cvta_generic_to_shared(s_lut + lane);
+  unsigned thr_col = (unsigned)__cvta_generic_to_shared(s_thr + lane);  // row r (threshold k = r - 1)
+  unsigned lut_col = (unsigned)__cvta_generic_to_shared(s_lut + lane);
+  // opaque to the optimiser: otherwise both addresses are re-derived from %tid (seven instructions each)
+  // at every lookup instead of living in a register
+  asm volatile("" : "+r"(thr_col), "+r"(lut_col));
   auto thr_at = [&](int row) -> T {
     T v;
     lds(v, thr_col + (unsigned)row * (32u * (unsigned)sizeof(T)));
@@ -379,29 +397,30 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
       continue;
     }
 
-    // value -> number of thresholds <= value (258 for NaN): fast float guess, verified against the exact table
+    // value -> number of thresholds <= value (258 for NaN): fast float guess, verified against the exact table.
+    // The common path is ~16 instructions: clamp (2 compares + select), lg2 + fma, clamp + convert, one
+    // address, two ld.shared, two compares; everything else -- a guess that is off by one or more, and NaN
+    // (which fails every comparison and therefore always lands there) -- is out of line.
     auto to_count = [&](T v, auto log_c) -> int {
       constexpr bool LOG = decltype(log_c)::value;
       // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
       if (LOG) {
-        v = (is_finite(v) && v > T(0)) ? v : fill_lo;
+        v = (v > T(0) && is_finite(v)) ? v : fill_lo;
       } else {
         v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
         v = (v == (T)CUDART_INF) ? fill_hi : v;
       }
       const float fv = (float)v;
-      float gf = (LOG ? fast_log2(fv) : fv) * c1 + c0;
+      float gf = __fmaf_rn(LOG ? fast_log2(fv) : fv, c1, c0);
       gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
       int n = (int)gf;
       // n thresholds are <= v  <=>  thr[n-1] <= v < thr[n]   (rows are offset by one: thr[k] = row k+1)
-      const T b = thr_at(n), c = thr_at(n + 1);
-      if (!(b <= v && !(c <= v))) {  // rare: the float guess was off
-#pragma unroll 1
-        while (n > 0 && !(thr_at(n) <= v)) --n;
-#pragma unroll 1
-        while (n < kThr && thr_at(n + 1) <= v) ++n;
-      }
-      return is_nan(v) ? 258 : n;
+      const unsigned row = thr_col + (unsigned)n * (32u * (unsigned)sizeof(T));
+      T b, c;
+      lds(b, row);
+      lds(c, row + 32u * (unsigned)sizeof(T));
+      if (!(b <= v && !(c <= v))) n = recount<T>(v, n, thr_col);  // rare: the float guess was off, or v is NaN
+      return n;
     };
     auto count_to_index = [](int n) -> int { return n == 0 ? I_UNDER : (n == kThr ? I_OVER : (n == 258 ? I_BAD : n - 1)); };
 

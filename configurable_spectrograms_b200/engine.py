@@ -129,6 +129,12 @@ class Batch:
         self._zvals_dirty = False
         self._raster_blocks = 0
         self._tables_dirty = True
+        self._runs_cache: dict[bytes, tuple] = {}
+        self._table_bufs: dict[str, DevBuf] = {}
+        self.d_stage: DevBuf | None = None  # collapse_pending(): the cubes of one call
+        self._n_collapsed = 0
+        self._sums_valid_bytes = 0
+        self._flags_valid_bytes = 0
 
     # ------------------------------------------------------------------ files
     def add_file(self, cube: np.ndarray | None, pa_bits: np.ndarray | None = None, *, shape=None, layout=None, device_ptr=None) -> int:
@@ -184,17 +190,30 @@ class Batch:
                 f["device_ptr"] = self.d_cubes.ptr + f["cube_off"]
         self._tables_dirty = True
 
-    def _build_file_tables(self):
-        """One descriptor table per (storage layout, K1 kernel, E): a launch handles files of one kind."""
+    def _table(self, name: str, arr: np.ndarray) -> DevBuf:
+        """Upload a small table into a persistent, grow-only device buffer (stream-ordered re-use: the
+        kernels still reading the previous contents precede this copy on the stream; no cudaFree /
+        cudaMalloc -- both synchronise the device -- in a steady-state streaming loop)."""
+        arr = np.ascontiguousarray(arr)
+        buf = self._table_bufs.get(name)
+        if buf is None or buf.nbytes < arr.nbytes:
+            buf = self._table_bufs[name] = self.ctx.alloc(max(2 * arr.nbytes, 4096))
+        buf.upload(arr)
+        return buf
+
+    def _file_tables(self, indices, ptr_of, tag="all"):
+        """Descriptor tables for the files ``indices``: one per (storage layout, K1 kernel, E) -- a launch
+        handles files of one kind.  ``ptr_of(i)``: device address of file i's cube.  Returns
+        ``({key: (table, n, blocks, max_P, max_E)}, d_runs, d_bits)``; the pitch-angle membership bytes
+        are packed for these files only (``bits_off`` is local to the returned ``d_bits``)."""
         lib = self.ctx.lib
-        self.d_files = {}
+        indices = list(indices)
         groups: dict[tuple[int, int, int], list[int]] = {}
-        for i, f in enumerate(self.files):
+        for i in indices:
+            f = self.files[i]
             if f["T"] <= 0:
                 continue
-            if f["device_ptr"] is None:
-                raise CsgError("cube not on the device: call upload_cubes() first")
-            kern = lib.csg_collapse_kernel_for(f["T"], f["P"], f["E"], self.code, f["layout"], f["device_ptr"], self.G)
+            kern = lib.csg_collapse_kernel_for(f["T"], f["P"], f["E"], self.code, f["layout"], ptr_of(i), self.G)
             # every file of a stream-kernel table shares one energy count (it fixes the block shape)
             groups.setdefault((f["layout"], kern, f["E"] if kern == _lib.K1_STREAM else 0), []).append(i)
         # runs of constant pitch-angle group membership (stream kernel), one entry per distinct table
@@ -208,49 +227,123 @@ class Batch:
                 bits = self._bits[i]
                 key = bits.tobytes()
                 if key not in runs_of:
-                    buf = np.zeros(3 * len(bits) + 3, dtype=np.int32)
-                    alias = C.c_int32(0)
-                    n = lib.csg_pitch_runs(bits.ctypes.data, len(bits), self.G, buf.ctypes.data, C.byref(alias))
-                    runs_of[key] = (runs_len, n, int(alias.value))
-                    runs_tab.append(buf[: 3 * n])
-                    runs_len += n
-        self.d_runs = self.ctx.to_device(np.concatenate(runs_tab)) if runs_tab else None
+                    hit = self._runs_cache.get(key)
+                    if hit is None:
+                        buf = np.zeros(3 * len(bits) + 3, dtype=np.int32)
+                        alias = C.c_int32(0)
+                        n = lib.csg_pitch_runs(bits.ctypes.data, len(bits), self.G, buf.ctypes.data, C.byref(alias))
+                        hit = self._runs_cache[key] = (buf[: 3 * n].copy(), n, int(alias.value))
+                    runs_of[key] = (runs_len, hit[1], hit[2])
+                    runs_tab.append(hit[0])
+                    runs_len += hit[1]
+        d_runs = self._table(f"{tag}_runs", np.concatenate(runs_tab)) if runs_tab else None
+        bits_off, off = {}, 0
+        for i in indices:
+            bits_off[i] = off
+            off += len(self._bits[i])
+        tables = {}
         for (layout, kern, _e), idx in groups.items():
             tab = np.zeros(len(idx), dtype=FILE_DESC)
             blocks, max_p, max_e = 0, 1, 1
             for j, i in enumerate(idx):
                 f = self.files[i]
-                tab[j]["d_cube"] = f["device_ptr"]
+                tab[j]["d_cube"] = ptr_of(i)
                 tab[j]["sums_off"] = f["sums_off"]
                 tab[j]["flags_off"] = f["flags_off"]
                 tab[j]["T"], tab[j]["P"], tab[j]["E"] = f["T"], f["P"], f["E"]
-                tab[j]["bits_off"] = f["bits_off"]
+                tab[j]["bits_off"] = bits_off[i]
                 tab[j]["first_block"] = blocks
                 if kern == _lib.K1_STREAM:
                     tab[j]["reserved"] = runs_of[self._bits[i].tobytes()]
                 blocks += lib.csg_collapse_blocks(f["T"], f["P"], f["E"], self.code, layout, kern)
                 max_p, max_e = max(max_p, f["P"]), max(max_e, f["E"])
-            self.d_files[(layout, kern, _e)] = (self.ctx.to_device(tab), len(idx), blocks, max_p, max_e)
-        self.d_bits = self.ctx.to_device(np.concatenate(self._bits) if self._bits else np.zeros(1, np.uint8))
-        if self.d_sums is None or self.d_sums.nbytes < self._sums_elems * self.dtype.itemsize:
-            self.d_sums = self.ctx.alloc(max(self._sums_elems, 1) * self.dtype.itemsize)
-        if self.d_flags is None or self.d_flags.nbytes < self._flags_bytes:
-            self.d_flags = self.ctx.alloc(max(self._flags_bytes, 4))
+            tables[(layout, kern, _e)] = (self._table(f"{tag}_files_{layout}_{kern}_{_e}", tab), len(idx), blocks, max_p, max_e)
+        packed = [self._bits[i] for i in indices]
+        d_bits = self._table(f"{tag}_bits", np.concatenate(packed) if packed else np.zeros(1, np.uint8))
+        return tables, d_runs, d_bits
+
+    def _ensure_outputs_of_k1(self):
+        """Room for every registered file's sums and row flags; what is already there survives a growth
+        (a device-to-device copy on the stream, ordered after the kernels that wrote it)."""
+        need = max(self._sums_elems, 1) * self.dtype.itemsize
+        if self.d_sums is None or self.d_sums.nbytes < need:
+            old, used = self.d_sums, self._sums_valid_bytes
+            self.d_sums = self.ctx.alloc(need if old is None else max(need, 2 * old.nbytes))
+            if old is not None and used:
+                self.ctx._check(self.ctx.lib.csg_d2d(self.ctx.handle, self.d_sums.ptr, old.ptr, used))
+                self.ctx.sync()  # `old` is freed when it goes out of scope
+        need = max(self._flags_bytes, 4)
+        if self.d_flags is None or self.d_flags.nbytes < need:
+            old, used = self.d_flags, self._flags_valid_bytes
+            self.d_flags = self.ctx.alloc(need if old is None else max(need, 2 * old.nbytes))
+            if old is not None and used:
+                self.ctx._check(self.ctx.lib.csg_d2d(self.ctx.handle, self.d_flags.ptr, old.ptr, used))
+                self.ctx.sync()
+
+    def _build_file_tables(self):
+        """Tables over EVERY file (cubes resident in HBM: the all-at-once path)."""
+        for f in self.files:
+            if f["T"] > 0 and f["device_ptr"] is None:
+                raise CsgError("cube not on the device: call upload_cubes() first")
+        self.d_files, self.d_runs, self.d_bits = self._file_tables(range(len(self.files)), lambda i: self.files[i]["device_ptr"])
+        self._ensure_outputs_of_k1()
         self._tables_dirty = False
+
+    def _launch_k1(self, tables, d_runs, d_bits):
+        for (layout, kern, _e), (tab, n, blocks, max_p, max_e) in tables.items():
+            self.ctx._check(
+                self.ctx.lib.csg_collapse(
+                    self.ctx.handle, tab.ptr, n, blocks, d_bits.ptr, d_runs.ptr if d_runs is not None else None, self.G,
+                    max_p, max_e, self.code, layout, kern, self.d_sums.ptr, self.d_flags.ptr,
+                )
+            )
 
     def collapse(self):
         """K1 over every file (one launch per storage layout / kernel / block shape present)."""
         if self._tables_dirty:
             self._build_file_tables()
         self.d_flags.zero()
-        for (layout, kern, _e), (tab, n, blocks, max_p, max_e) in self.d_files.items():
-            self.ctx._check(
-                self.ctx.lib.csg_collapse(
-                    self.ctx.handle, tab.ptr, n, blocks, self.d_bits.ptr,
-                    self.d_runs.ptr if self.d_runs is not None else None, self.G, max_p, max_e, self.code, layout, kern,
-                    self.d_sums.ptr, self.d_flags.ptr,
-                )
-            )
+        self._launch_k1(self.d_files, self.d_runs, self.d_bits)
+        self._sums_valid_bytes = self._sums_elems * self.dtype.itemsize
+        self._flags_valid_bytes = self._flags_bytes
+        self._n_collapsed = len(self.files)
+
+    def collapse_pending(self):
+        """Streaming ingest: upload and collapse the files registered since the last call, then forget
+        their cubes.  The cubes pass through ONE device staging buffer (stream order: this call's uploads
+        wait for the previous call's K1), so HBM holds the sums and flags of everything but the cubes of
+        one call only; host arrays are released as soon as the copies are enqueued -- from pinned memory
+        (``_lib.PinnedRing``) the copy is asynchronous, and the caller re-uses a slot once the event it
+        records after this call has passed.  Returns the number of files collapsed."""
+        first = self._n_collapsed
+        todo = [i for i in range(first, len(self.files)) if self.files[i]["T"] > 0]
+        self._ensure_outputs_of_k1()
+        new_flags = self._flags_bytes - self._flags_valid_bytes
+        if new_flags > 0:
+            self.ctx._check(self.ctx.lib.csg_memset(self.ctx.handle, self.d_flags.ptr + self._flags_valid_bytes, 0, new_flags))
+        if todo:
+            base = self.files[todo[0]]["cube_off"]
+            span = self._cube_bytes - base
+            if self.d_stage is None or self.d_stage.nbytes < span:
+                self.d_stage = None  # free before the larger allocation
+                self.d_stage = self.ctx.alloc(span)
+            # the small tables first: their (pageable) uploads wait for the stream, which at this point holds
+            # the PREVIOUS call's copies and K1 only -- normally long finished while the host was decoding
+            tables, d_runs, d_bits = self._file_tables(todo, lambda i: self.d_stage.ptr + self.files[i]["cube_off"] - base,
+                                                       tag="pending")
+            for i in todo:
+                f = self.files[i]
+                if f["host"] is None:
+                    raise CsgError("collapse_pending() needs host cubes (device-resident files use collapse())")
+                self.d_stage.upload(f["host"], f["cube_off"] - base, keep=False)
+            self._launch_k1(tables, d_runs, d_bits)
+            for i in todo:
+                self.files[i]["host"] = None
+        self._sums_valid_bytes = self._sums_elems * self.dtype.itemsize
+        self._flags_valid_bytes = self._flags_bytes
+        self._n_collapsed = len(self.files)
+        self._tables_dirty = True
+        return len(todo)
 
     def piece_blocks(self, file_bounds):
         """Block ranges of K1 for pieces of the file list: ``file_bounds`` = ascending file indices

@@ -77,6 +77,7 @@ def FAST_plot_spectrograms_directory(
     log_flush_batch_size: int | None = None,
     max_processing_percentile: float | None = None,
     override_plots: bool = True,
+    _timings: dict | None = None,
 ) -> list[dict[str, Any]]:
     """Plot every orbit under ``directory_path`` (reference ``:32-433``).
 
@@ -86,10 +87,17 @@ def FAST_plot_spectrograms_directory(
     ``{y}_{z}_last_orbit``, ``{y}_{z}_error_plotting``, ``orbit_{y}_{z}_timed_out`` and the
     per-reason error lists (``:277-321``).  Raises ``KeyboardInterrupt`` on SIGINT / SIGTERM.
 
-    ``orbit_timeout_seconds``, ``instrument_timeout_seconds`` and ``retry_timeouts`` are accepted for
-    call compatibility and have nothing to act on: the reference times out and retries worker
-    *processes* (``:344-420,455-492``); here an orbit is a slice of a few kernel launches, so the
-    ``orbit_{y}_{z}_timed_out`` list is written and stays empty.
+    Timeouts keep the reference's soft, after-the-fact semantics (``process_orbit.py:203-211,276-283``): a
+    chunk of orbits is planned, rasterised, encoded and written together, its wall time is shared evenly
+    between its submissions, and a share above ``orbit_timeout_seconds`` marks them ``"timeout"``
+    (``timeout_type: "orbit"``, listed under ``orbit_{y}_{z}_timed_out``).  With ``retry_timeouts`` every
+    timed-out orbit is re-run once through ``FAST_process_single_orbit`` without global extrema
+    (``instrument_timeout_seconds`` applies there) and cleared from the lists when it succeeds
+    (``:422-431,455-514``); retries run on single-GPU calls only.
+
+    Memory: cubes stream through three pinned host slots and one device staging buffer
+    (``CSG_CHUNK_ORBITS`` orbits at a time, default 8); only the collapsed sums (6 MB per orbit) stay in
+    HBM for the whole call.  ``_timings`` (internal, bench): seconds per phase.
     """
     interrupted = {"flag": False}
 
@@ -110,6 +118,7 @@ def FAST_plot_spectrograms_directory(
             directory_path, output_base, y_scale, z_scale, zoom_duration_minutes, tuple(instrument_order), verbose,
             progress_json_path, ignore_progress_json, colormap, cusp_marker_style, cusp_marker_kwargs, max_workers,
             flush_batch_size, log_flush_batch_size, max_processing_percentile, override_plots,
+            orbit_timeout_seconds, instrument_timeout_seconds, retry_timeouts, _timings,
         )
     finally:
         for sig, handler in previous.items():
@@ -119,9 +128,29 @@ def FAST_plot_spectrograms_directory(
                 pass
 
 
+def _chunk_orbits_default() -> int:
+    """Orbits per streaming chunk (``CSG_CHUNK_ORBITS``): a nominal 4-instrument orbit is 84 MB of cubes,
+    so the default keeps one pinned slot / the device staging buffer near 0.7 GB."""
+    try:
+        return max(1, int(os.environ.get("CSG_CHUNK_ORBITS", "8")))
+    except ValueError:
+        return 8
+
+
 def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_minutes, instrument_order, verbose,
                    progress_json_path, ignore_progress_json, colormap, cusp_marker_style, cusp_marker_kwargs, max_workers,
-                   flush_batch_size, log_flush_batch_size, max_processing_percentile, override_plots):
+                   flush_batch_size, log_flush_batch_size, max_processing_percentile, override_plots,
+                   orbit_timeout_seconds=60, instrument_timeout_seconds=30, retry_timeouts=True, timings=None):
+    import time as _time
+
+    from .extrema import load_extrema_state, orbits_the_scan_needs
+
+    def tick(name, t0):
+        if timings is not None:
+            timings[name] = timings.get(name, 0.0) + _time.perf_counter() - t0
+        return _time.perf_counter()
+
+    t_phase = _time.perf_counter()
     rank, world, dist = _rank_world()
     frame = load_filtered_orbits()
     configure_log_batch(log_flush_batch_size or flush_batch_size)
@@ -154,9 +183,11 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
         log_exception("[RESUME] No previous progress found. Starting from the first orbit. "
                       f"{len(error_orbits)} error orbits will be skipped if present.", level="message")
     pending = [o for o, _ in sorted_orbits[start_idx:] if o not in error_orbits]
+    pending_set = set(pending)
     flush_batch_size = max(1, flush_batch_size)
+    n_threads = max(1, int(max_workers))
 
-    # ---- this rank's contiguous block of the ascending orbit sequence, resident in one shard
+    # ---- this rank's contiguous block of the ascending orbit sequence
     per = (total_orbits + world - 1) // world if total_orbits else 0
     lo, hi = rank * per, min(total_orbits, (rank + 1) * per)
     comm = None
@@ -167,40 +198,88 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
 
         comm = TorchComm(dist, torch.device("cuda", torch.cuda.current_device()))
     need_extrema = max_processing_percentile is not None
+    sequence = [(o, {i: True for i in files}) for o, files in sorted_orbits]
     mine = sorted_orbits[lo:hi]
-    load = [(o, files) for o, files in mine if need_extrema or o in set(pending)]
+    # which cubes this rank has to read: every pending orbit it draws, and -- for the extrema pre-pass -- the
+    # (orbit, instrument) steps that still reach the scan given the cached extrema JSON (a finished cache needs none)
+    scan_needs: dict[int, set] = {}
+    if need_extrema:
+        scan_needs = orbits_the_scan_needs(sequence, instrument_order, y_scale, z_scale, load_extrema_state())
     results: list[dict[str, Any]] = []
     ctx = _lib.default_context(_current_device())
     shard = ShardPlan(ctx, y_scale, z_scale, zoom_duration_minutes, instrument_order=instrument_order)
     shard.first_orbit_index = lo
     load_errors: dict[int, list[str]] = {}
-    loaded_orbits = []
-    for orbit, files in load:
-        datasets, lines = {}, {}
+    loaded_orbits: list[int] = []
+
+    # ---- phase A: streaming ingest.  Loader threads decode the next chunk's files straight into a pinned
+    # staging slot while the copy engine uploads the previous chunk and K1 collapses it; neither host RAM
+    # nor HBM ever holds more cubes than the slots of the ring (the sums and row flags of every orbit stay)
+    chunk_n = _chunk_orbits_default()
+    chunks = [list(range(a, min(a + chunk_n, len(mine)))) for a in range(0, len(mine), chunk_n)]
+    slot_bytes = int(os.environ.get("CSG_SLOT_BYTES", str(max(1 << 28, chunk_n * 100 * (1 << 20)))))
+    ring = _lib.PinnedRing(ctx, n_slots=3, slot_bytes=slot_bytes) if chunks else None
+
+    def load_one(slot, index):
+        orbit, files = mine[index]
+        wanted = set(scan_needs.get(lo + index, ()))
+        if orbit in pending_set:
+            wanted |= set(instrument_order)
+        datasets, lines, errors = {}, {}, []
         for inst in DEFAULT_INSTRUMENT_ORDER:
             path = files.get(inst)
-            if not path or inst not in instrument_order:
+            if not path or inst not in instrument_order or inst not in wanted:
                 continue
             try:
                 detected = get_cdf_file_type(path)
                 if detected is None or detected == "orb":
                     continue
-                ds = load_fast_cdf_dataset(path)
+                ds = load_fast_cdf_dataset(path, data_alloc=lambda shape, dtype: ring.alloc(slot, shape, dtype))
                 datasets[inst] = ds
                 lines[inst] = get_timestamps_for_orbit(frame, orbit, detected, ds["times"])
             except Exception as exc:
                 err = f"[FAIL] Plotting Orbit {orbit} pitch angle grid for {inst}"
                 log_exception(err, exc, level="error")
-                load_errors.setdefault(orbit, []).append(err)
-        shard.add_orbit(orbit, datasets, lines)
-        loaded_orbits.append(orbit)
+                errors.append(err)
+        return orbit, datasets, lines, errors
+
+    t_phase = tick("discover_and_resume", t_phase)
+    with ThreadPoolExecutor(max_workers=n_threads) as pool:
+        def submit(k):
+            slot = ring.acquire()
+            return slot, [pool.submit(load_one, slot, i) for i in chunks[k]]
+
+        in_flight = submit(0) if chunks else None
+        for k in range(len(chunks)):
+            slot, futures = in_flight
+            loaded = [f.result() for f in futures]
+            # the next chunk decodes while this one is registered, uploaded and collapsed
+            in_flight = submit(k + 1) if k + 1 < len(chunks) else None
+            for orbit, datasets, lines, errors in loaded:
+                if errors:
+                    load_errors.setdefault(orbit, []).extend(errors)
+                try:
+                    shard.add_orbit(orbit, datasets, lines)
+                except TypeError as exc:  # a cube of another float dtype than the shard's: refused, not cast
+                    err = f"[FAIL] Orbit {orbit} processing"
+                    log_exception(err, exc, level="error")
+                    load_errors.setdefault(orbit, []).append(err)
+                    shard.add_orbit(orbit, {}, {})
+                loaded_orbits.append(orbit)
+            shard.collapse_pending()
+            ring.release(slot)
+    if ring is not None:
+        if ring.overflow_bytes:
+            log_exception(f"[INGEST] {ring.overflow_bytes} bytes of cubes did not fit the pinned slots "
+                          f"({slot_bytes} bytes each; CSG_SLOT_BYTES / CSG_CHUNK_ORBITS) and were uploaded from pageable memory",
+                          level="message")
+        ring.close()
     # ranks that loaded only part of the sequence still index it globally
     if not need_extrema:
         shard.first_orbit_index = 0
-    shard.upload()
-    shard.collapse()
+    t_phase = tick("ingest_and_collapse", t_phase)
 
-    # ---- global extrema pre-pass (reference :159-171), from the collapsed matrices already in HBM
+    # ---- phase B: global extrema pre-pass (reference :159-171), from the collapsed matrices already in HBM
     global_extrema = None
     if need_extrema:
         global_extrema = compute_global_extrema(
@@ -208,105 +287,126 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             max_percentile=float(max_processing_percentile), log_floor_cutoff=0.1, log_floor_value=-1.0,
             flush_batch_size=flush_batch_size, _shard=shard, _comm=comm,
         )
+    t_phase = tick("global_extrema", t_phase)
 
-    # ---- every figure of this rank's pending orbits: K2a + K3; the figures are planned on host
-    # threads from panel references, then composed and PNG-encoded on the device (K4): no raster
-    # ever crosses PCIe uncompressed
-    my_pending = [o for o in pending if o in set(loaded_orbits)]
+    # ---- phase C: the figures, chunk by chunk: K2a + K3 for the chunk's panels, the figures planned on host
+    # threads from panel references, composed and PNG-encoded on the device (K4: no raster ever crosses PCIe
+    # uncompressed), files written, progress recorded -- an interrupt loses at most the chunk in flight
+    loaded_set = set(loaded_orbits)
+    my_pending = [o for o in pending if o in loaded_set]
     submissions = (False, True) if need_extrema else (False,)
-    sequence = [(o, {i: True for i in files}) for o, files in sorted_orbits]
-    step = BatchStep(shard, sequence, comm=comm, lut259=get_lut(colormap), plot_orbits=my_pending, submissions=submissions)
-    if my_pending:
-        step.run(state=global_extrema if global_extrema is not None else {}, collapse=False)
-        step.finish()
+    lut = get_lut(colormap)
     b = shard.batch
-    norms = b.norms() if b.n_panels else None
-
-    def render(orbit, with_extrema):
-        """One submission of one orbit (= one FAST_process_single_orbit call of the reference)."""
-        result: dict[str, Any] = {"orbit": orbit, "status": "ok", "errors": []}
-        saves: list[tuple[str, Any]] = []  # (path, figure): encoded and written after the planning pass
-        for err in load_errors.get(orbit, []):
-            result["status"] = "error"
-            result["errors"].append(err)
-        files = orbit_to_instruments[orbit]
-        first_path = next((files[k] for k in DEFAULT_INSTRUMENT_ORDER if k in files), None)
-        year, month = _parse_year_month(first_path) if first_path else ("unknown", "unknown")
-        out_dir = os.path.join(output_base, str(year), str(month), str(orbit))
-        os.makedirs(out_dir, exist_ok=True)
-        first, last = step.figure_ranges.get((orbit, with_extrema), (0, 0))
-        for spec in shard.figures[first:last]:
-            what = f"pitch angle grid for {spec.instrument}" if spec.kind == "pitch-angle" else "instrument grid"
-            try:
-                fig, _canvas = figure_from_spec(shard, spec, colormap, cusp_marker_style, cusp_marker_kwargs, norms=norms,
-                                                device_rasters=True)
-                if fig is None:
-                    continue
-                path = os.path.join(out_dir, figure_filename(spec, y_scale, z_scale, colormap))
-                if not override_plots and os.path.exists(path):
-                    log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
-                    close_all_axes_and_clear(fig)
-                else:
-                    saves.append((path, fig))
-            except Exception as exc:
-                err = f"[FAIL] Plotting Orbit {orbit} {what}"
-                log_exception(err, exc, level="error")
-                result["status"] = "error"
-                if err not in result["errors"]:
-                    result["errors"].append(err)
-        return result, saves
+    pdisk = dict(progress)
+    since_flush = 0
 
     def record(result, pdisk):
         orbit = result["orbit"]
         pdisk[progress_key] = orbit
         pdisk.setdefault(error_key, [])
         pdisk.setdefault(timeout_key, [])
-        if result.get("status") == "error":
+        status = result.get("status")
+        if status == "error":
             _add_to_orbit_list(pdisk, error_key, orbit)
             for msg in result.get("errors") or []:
                 reason = _classify_error_reason(msg)
                 inst = next((c for c in _INSTRUMENT_KEYS if c in msg.lower()), "unknown")
                 _add_to_orbit_list(pdisk, f"{inst}_{y_scale}_{z_scale}_error-{reason}", orbit)
                 _add_to_orbit_list(pdisk, f"{y_scale}_{z_scale}_error-{reason}", orbit)
+        elif status == "timeout":  # reference :316-324
+            if result.get("timeout_type") == "orbit":
+                _add_to_orbit_list(pdisk, timeout_key, orbit)
+            elif result.get("timeout_type") == "instrument":
+                inst = result.get("timeout_instrument") or "unknown_instrument"
+                _add_to_orbit_list(pdisk, f"{inst}_{y_scale}_{z_scale}_timed_out", orbit)
 
-    jobs = [(o, flag) for o in my_pending for flag in submissions]
-    pdisk = dict(progress)
-    since_flush = 0
-    with ThreadPoolExecutor(max_workers=max(1, int(max_workers))) as pool:
-        planned = list(pool.map(lambda j: render(*j), jobs))
-    rendered = [r for r, _s in planned]
-    # the reference runs the submissions one after the other: a later one finds the earlier one's file
-    # and skips it unless override_plots is set, in which case the later one wins
-    by_path: dict[str, Any] = {}
-    for _r, job_saves in planned:
-        for path, fig in job_saves:
-            if path in by_path and not override_plots:
-                log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
-                close_all_axes_and_clear(fig)
-                continue
-            if path in by_path:
-                close_all_axes_and_clear(by_path[path])
-            by_path[path] = fig
-    saves = list(by_path.items())
-    # ---- K4: compose + DEFLATE on the device, files written by a thread pool; progress is recorded
-    # only once the orbit's PNGs are on disk
-    if saves:
-        from ..png import write_figures_device
+    from ..png import write_figures_device
 
-        write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=max(1, int(max_workers)))
-        for path, fig in saves:
-            log_exception(f"[SAVED] {path}", level="message")
-            close_all_axes_and_clear(fig)
-    for result in rendered:
-        results.append(result)
-        if verbose:
-            log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
-        if progress_json_path is not None and rank == 0:
-            record(result, pdisk)
-            since_flush += 1
-            if since_flush >= flush_batch_size:
-                _write_json(progress_json_path, pdisk)
-                since_flush = 0
+    with ThreadPoolExecutor(max_workers=n_threads) as pool:
+        for a in range(0, len(my_pending), chunk_n):
+            chunk = my_pending[a : a + chunk_n]
+            t_chunk = _time.perf_counter()
+            step = BatchStep(shard, sequence, comm=comm, lut259=lut, plot_orbits=chunk, submissions=submissions)
+            step.run(state=global_extrema if global_extrema is not None else {}, collapse=False)
+            t_phase = tick("plan_and_enqueue", t_phase)
+            step.finish()
+            norms = b.norms() if b.n_panels else None
+            t_phase = tick("kernels_wait", t_phase)
+
+            def render(job, step=step, norms=norms):
+                """One submission of one orbit (= one FAST_process_single_orbit call of the reference)."""
+                orbit, with_extrema = job
+                result: dict[str, Any] = {"orbit": orbit, "status": "ok", "errors": []}
+                saves: list[tuple[str, Any]] = []  # (path, figure): encoded and written after the planning pass
+                for err in load_errors.get(orbit, []):
+                    result["status"] = "error"
+                    result["errors"].append(err)
+                files = orbit_to_instruments[orbit]
+                first_path = next((files[k] for k in DEFAULT_INSTRUMENT_ORDER if k in files), None)
+                year, month = _parse_year_month(first_path) if first_path else ("unknown", "unknown")
+                out_dir = os.path.join(output_base, str(year), str(month), str(orbit))
+                os.makedirs(out_dir, exist_ok=True)
+                first, last = step.figure_ranges.get((orbit, with_extrema), (0, 0))
+                for spec in shard.figures[first:last]:
+                    what = f"pitch angle grid for {spec.instrument}" if spec.kind == "pitch-angle" else "instrument grid"
+                    try:
+                        fig, _canvas = figure_from_spec(shard, spec, colormap, cusp_marker_style, cusp_marker_kwargs, norms=norms,
+                                                        device_rasters=True)
+                        if fig is None:
+                            continue
+                        path = os.path.join(out_dir, figure_filename(spec, y_scale, z_scale, colormap))
+                        if not override_plots and os.path.exists(path):
+                            log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
+                            close_all_axes_and_clear(fig)
+                        else:
+                            saves.append((path, fig))
+                    except Exception as exc:
+                        err = f"[FAIL] Plotting Orbit {orbit} {what}"
+                        log_exception(err, exc, level="error")
+                        result["status"] = "error"
+                        if err not in result["errors"]:
+                            result["errors"].append(err)
+                return result, saves
+
+            jobs = [(o, flag) for o in chunk for flag in submissions]
+            planned = list(pool.map(render, jobs))
+            # the reference runs the submissions one after the other: a later one finds the earlier one's file
+            # and skips it unless override_plots is set, in which case the later one wins
+            by_path: dict[str, Any] = {}
+            for _r, job_saves in planned:
+                for path, fig in job_saves:
+                    if path in by_path and not override_plots:
+                        log_exception(f"[SKIP] Plot already exists, skipping: {path}", level="message")
+                        close_all_axes_and_clear(fig)
+                        continue
+                    if path in by_path:
+                        close_all_axes_and_clear(by_path[path])
+                    by_path[path] = fig
+            saves = list(by_path.items())
+            t_phase = tick("figures_host", t_phase)
+            if saves:
+                write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads)
+                for path, fig in saves:
+                    log_exception(f"[SAVED] {path}", level="message")
+                    close_all_axes_and_clear(fig)
+            t_phase = tick("png_encode_and_write", t_phase)
+            # soft timeouts, checked after the work like the reference's (process_orbit.py:203-211,276-283): a
+            # chunk's wall time is shared evenly between its submissions
+            share = (_time.perf_counter() - t_chunk) / max(1, len(jobs))
+            for result, _s in planned:
+                if share > orbit_timeout_seconds and result["status"] == "ok":
+                    log_exception(f"[TIMEOUT] Orbit {result['orbit']} exceeded {orbit_timeout_seconds:.0f}s total.", level="message")
+                    result["status"], result["timeout_type"] = "timeout", "orbit"
+                results.append(result)
+                if verbose:
+                    log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
+                if progress_json_path is not None and rank == 0:
+                    record(result, pdisk)
+                    since_flush += 1
+                    if since_flush >= flush_batch_size:
+                        _write_json(progress_json_path, pdisk)
+                        since_flush = 0
+            t_phase = tick("progress", t_phase)
 
     if world > 1:  # every rank returns every result; rank 0 owns the progress file
         gathered: list = [None] * world
@@ -319,7 +419,67 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
     if progress_json_path is not None and rank == 0 and (results or os.path.exists(progress_json_path)):
         _write_json(progress_json_path, pdisk)
     flush_log_buffer(force=True)
+    if retry_timeouts and world == 1:
+        results = _retry_timed_out_orbits(results, orbit_to_instruments, frame, zoom_duration_minutes, y_scale, z_scale,
+                                          instrument_order, colormap, output_base, orbit_timeout_seconds,
+                                          instrument_timeout_seconds, override_plots, cusp_marker_style, cusp_marker_kwargs,
+                                          progress_json_path)
+    tick("finish", t_phase)
     return results
+
+
+def _retry_timed_out_orbits(results, orbit_to_instruments, frame, zoom_duration_minutes, y_scale, z_scale, instrument_order,
+                            colormap, output_base, orbit_timeout_seconds, instrument_timeout_seconds, override_plots,
+                            cusp_marker_style, cusp_marker_kwargs, progress_json_path):
+    """Every orbit whose status is ``'timeout'`` once more, one orbit at a time through
+    ``FAST_process_single_orbit`` without global extrema -- the reference's retry pool (``:455-492``:
+    ``orbit_args_fn(o, files, None)``).  Like there, the results collapse to one entry per orbit when
+    anything was retried, and a successful retry clears the orbit from every ``*_timed_out`` list."""
+    from .process_orbit import FAST_process_single_orbit
+
+    timed_out = sorted({r["orbit"] for r in results if r.get("status") == "timeout"})
+    if not timed_out:
+        return results
+    log_exception(f"[RETRY] Retrying {len(timed_out)} timed-out orbits once.", level="message")
+    retried = []
+    for orbit in timed_out:
+        if orbit not in orbit_to_instruments:
+            continue
+        try:
+            r = FAST_process_single_orbit(
+                orbit, orbit_to_instruments[orbit], frame, zoom_duration_minutes, y_scale, z_scale, instrument_order, colormap,
+                output_base, orbit_timeout_seconds=orbit_timeout_seconds, instrument_timeout_seconds=instrument_timeout_seconds,
+                global_extrema=None, override_plots=override_plots, cusp_marker_style=cusp_marker_style,
+                cusp_marker_kwargs=cusp_marker_kwargs,
+            )
+            log_exception(f"[RETRY] Completed orbit {orbit}: {r.get('status')}", level="message")
+            if progress_json_path is not None and r.get("status") == "ok":
+                _clear_timeout_flag(progress_json_path, orbit, y_scale, z_scale)
+        except Exception as exc:
+            log_exception(f"[RETRY] Orbit {orbit} retry failed", exc, level="error")
+            r = {"orbit": orbit, "status": "error", "errors": [str(exc)]}
+        retried.append(r)
+    merged = {r["orbit"]: r for r in results}
+    for r in retried:
+        merged[r["orbit"]] = r
+    return list(merged.values())
+
+
+def _clear_timeout_flag(progress_json_path, orbit, y_scale, z_scale):
+    """Remove ``orbit`` from every ``*_timed_out`` list of the progress JSON (reference ``:495-514``)."""
+    try:
+        with open(progress_json_path) as f:
+            pdisk = json.load(f)
+    except (OSError, json.JSONDecodeError) as exc:
+        log_exception("[WARN] Could not read progress JSON for retry cleanup", exc, level="message")
+        return
+    changed = False
+    for key in [k for k in pdisk if k.endswith(f"_{y_scale}_{z_scale}_timed_out")]:
+        if isinstance(pdisk.get(key), list) and orbit in pdisk[key]:
+            pdisk[key] = [x for x in pdisk[key] if x != orbit]
+            changed = True
+    if changed:
+        _write_json(progress_json_path, pdisk)
 
 
 def _write_json(path, data):

@@ -544,6 +544,29 @@ def extrema_from_shard(shard, sequence, instrument_order, y_scale, z_scale, stat
     return extrema_finish(pending, on_step_done)
 
 
+def load_extrema_state(extrema_json_path: str = FAST_EXTREMA_JSON_PATH) -> dict[str, Any]:
+    """The cached extrema JSON (``{}`` when absent or unreadable, reference ``:137-149``)."""
+    if not os.path.exists(extrema_json_path):
+        return {}
+    try:
+        with open(extrema_json_path) as handle:
+            return json.load(handle)
+    except (OSError, json.JSONDecodeError) as exc:
+        log_exception(f"[EXTREMA] Failed to read existing extrema JSON '{extrema_json_path}' (starting fresh)", exc, level="message")
+        return {}
+
+
+def orbits_the_scan_needs(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff=0.1, log_floor_value=-1.0):
+    """``{orbit index: {instrument, ...}}`` -- the files whose cubes the pre-pass still has to read with this
+    cache state (a finished or re-usable cache needs none: the walk then only copies / transforms keys)."""
+    steps, _ = plan_scanned_steps(sequence, tuple(instrument_order), y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
+    needs: dict[int, set] = {}
+    for inst, indices in steps.items():
+        for oi in indices:
+            needs.setdefault(oi, set()).add(inst)
+    return needs
+
+
 def compute_global_extrema(
     directory_path: str,
     y_scale: str,
@@ -560,73 +583,82 @@ def compute_global_extrema(
 ) -> dict[str, Any]:
     """Compute or resume the cached per-instrument extrema (reference ``:73-366``).
 
-    ``_shard`` (internal) re-uses cubes a batch driver already holds on the GPU.
+    ``_shard`` (internal) re-uses sums a batch driver already holds on the GPU; stand-alone, the files the
+    scan needs stream through pinned slots chunk by chunk (``Batch.collapse_pending``), so neither host
+    RAM nor HBM holds more than a few chunks of cubes.
+
+    ``flush_batch_size`` is accepted for call compatibility: the reference rewrites the JSON every
+    ``flush_batch_size`` steps of a pass that takes minutes to hours, so that an interrupted run can resume
+    (``:333-344``); here the whole pass is a few kernel launches whose results -- the maxima over EVERY
+    prefix pool -- arrive together, so there is no meaningful intermediate state to persist and the cache
+    is written once, complete, when the pass is done.
     """
     from ..cdf_utils import load_fast_cdf_dataset
     from .orbit_discovery import discover_orbit_files
 
     instrument_order = tuple(instrument_order)
-    state: dict[str, Any] = {}
-    if os.path.exists(extrema_json_path):
-        try:
-            with open(extrema_json_path) as handle:
-                state = json.load(handle)
-        except (OSError, json.JSONDecodeError) as exc:
-            log_exception(f"[EXTREMA] Failed to read existing extrema JSON '{extrema_json_path}' (starting fresh)", exc, level="message")
-            state = {}
+    state = load_extrema_state(extrema_json_path)
 
     orbit_files = discover_orbit_files(directory_path, instrument_order)
     orbits = sorted(orbit_files)
     sequence = [(o, {i: True for i in orbit_files[o]}) for o in orbits]
     last_key = f"{y_scale}_{z_scale}_last_orbit"
-    flush_state = {"since": 0}
 
-    def dump(ordered_first: bool):
+    def dump():
         if _comm is not None and getattr(_comm, "rank", 0) != 0:
-            return True  # every rank holds the same state; rank 0 owns the cache file
+            return  # every rank holds the same state; rank 0 owns the cache file
         payload = state
-        if ordered_first and last_key in state:
+        if last_key in state:
             payload = {last_key: state[last_key], **{k: v for k, v in state.items() if k != last_key}}
         try:
             with open(extrema_json_path, "w") as handle:
                 json.dump(payload, handle, indent=2)
-            return True
         except OSError as exc:
             log_exception("[EXTREMA] flush failure", exc, level="message")
-            return False
-
-    def step_done(reuse: bool):
-        if reuse:
-            dump(False)  # the reference rewrites the cache right after a re-use (:234-236)
-            return
-        flush_state["since"] += 1
-        if flush_state["since"] >= flush_batch_size and dump(False):
-            flush_state["since"] = 0
 
     shard = _shard
+    touched = False
     if shard is None:
-        steps, _ = plan_scanned_steps(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
-        needed = sorted({oi for lst in steps.values() for oi in lst})
-        if needed:
+        needs = orbits_the_scan_needs(sequence, instrument_order, y_scale, z_scale, state, log_floor_cutoff, log_floor_value)
+        if needs:
+            from concurrent.futures import ThreadPoolExecutor
+
             from .. import _lib
             from .pipeline import ShardPlan
 
-            shard = ShardPlan(_lib.default_context(), y_scale, z_scale, instrument_order=instrument_order)
+            ctx = _lib.default_context()
+            shard = ShardPlan(ctx, y_scale, z_scale, instrument_order=instrument_order)
             shard.first_orbit_index = 0
-            wanted = {oi: {i for i in instrument_order if oi in steps[i]} for oi in needed}
-            for oi, orbit in enumerate(orbits):
+            chunk_n = max(1, int(os.environ.get("CSG_CHUNK_ORBITS", "8")))
+            ring = _lib.PinnedRing(ctx, n_slots=3, slot_bytes=int(os.environ.get("CSG_SLOT_BYTES", str(max(1 << 28, chunk_n * 100 * (1 << 20))))))
+
+            def load_one(slot, oi):
                 datasets = {}
-                for inst in wanted.get(oi, ()):
-                    path = orbit_files[orbit].get(inst)
+                for inst in needs.get(oi, ()):
+                    path = orbit_files[orbits[oi]].get(inst)
                     if path is None:
                         continue
                     try:
-                        datasets[inst] = load_fast_cdf_dataset(path)
+                        datasets[inst] = load_fast_cdf_dataset(path, data_alloc=lambda shape, dtype: ring.alloc(slot, shape, dtype))
                     except Exception as exc:
-                        log_exception(f"[EXTREMA] Ingest failure inst={inst} orbit={orbit} file={path}", exc, level="message")
-                shard.add_orbit(orbit, datasets)
-            shard.upload()
-            shard.collapse()
+                        log_exception(f"[EXTREMA] Ingest failure inst={inst} orbit={orbits[oi]} file={path}", exc, level="message")
+                return datasets
+
+            try:
+                with ThreadPoolExecutor(max_workers=4) as pool:
+                    for a in range(0, len(orbits), chunk_n):
+                        slot = ring.acquire()
+                        loaded = list(pool.map(lambda oi: load_one(slot, oi), range(a, min(a + chunk_n, len(orbits)))))
+                        for oi, datasets in zip(range(a, a + len(loaded)), loaded):
+                            try:
+                                shard.add_orbit(orbits[oi], datasets)
+                            except TypeError as exc:
+                                log_exception(f"[EXTREMA] Ingest failure orbit={orbits[oi]}", exc, level="message")
+                                shard.add_orbit(orbits[oi], {})
+                        shard.collapse_pending()
+                        ring.release(slot)
+            finally:
+                ring.close()
     if shard is None:
         # nothing reaches the scan (everything re-used or complete): only the bookkeeping runs
         totals = {i: sum(1 for _, h in sequence if i in h) for i in instrument_order}
@@ -634,16 +666,22 @@ def compute_global_extrema(
         def unreachable(inst, orbit_index, handle):
             raise AssertionError("scan step without a planned shard")
 
+        def step_done(reuse: bool):
+            nonlocal touched
+            touched = True
+
         _walk(sequence, instrument_order, y_scale, z_scale, state, totals, log_floor_cutoff, log_floor_value,
               unreachable, step_done)
     else:
+        before = json.dumps(state, sort_keys=True, default=str)
         extrema_from_shard(
             shard, sequence, instrument_order, y_scale, z_scale, state, compute_mins=compute_mins,
             max_percentile=max_percentile, log_floor_cutoff=log_floor_cutoff, log_floor_value=log_floor_value,
-            comm=_comm, on_step_done=step_done,
+            comm=_comm,
         )
-    if flush_state["since"] > 0:
-        dump(True)
+        touched = json.dumps(state, sort_keys=True, default=str) != before
+    if touched:
+        dump()
     if last_key in state:
         return {last_key: state[last_key], **{k: v for k, v in state.items() if k != last_key}}
     return state

@@ -81,14 +81,18 @@ class ShardPlan:
     """Plans and runs the batch path for a list of orbits on one GPU."""
 
     def __init__(self, ctx, y_scale="linear", z_scale="linear", zoom_duration_minutes=6.25,
-                 instrument_order=DEFAULT_INSTRUMENT_ORDER, pitch_angle_categories=None, dtype=np.float32):
+                 instrument_order=DEFAULT_INSTRUMENT_ORDER, pitch_angle_categories=None, dtype=None):
+        """``dtype``: the cube dtype D every kernel computes in (numpy sums, ranks and normalises in the
+        array's own dtype, so D is part of the result).  ``None`` = taken from the first cube added; a
+        later cube of another float dtype is refused (:meth:`add_orbit`) -- never cast silently."""
         self.ctx = ctx
         self.y_scale, self.z_scale = y_scale, z_scale
         self.zoom_minutes = zoom_duration_minutes
         self.instrument_order = tuple(instrument_order)
         self.categories = pitch_angle_categories or DEFAULT_PITCH_ANGLE_CATEGORIES
         self.n_groups = len([k for k in PITCH_ANGLE_ROW_KEYS if k in self.categories])
-        self.batch = Batch(ctx, dtype, n_groups=self.n_groups)
+        self._dtype = None if dtype is None else np.dtype(dtype)
+        self._batch = None if dtype is None else Batch(ctx, dtype, n_groups=self.n_groups)
         self.orbits: list[dict] = []  # {"orbit", "files": {inst: file_id}, "lines": {inst: [..]}}
         self.file_meta: list[dict] = []
         self.figures: list[FigureSpec] = []
@@ -99,9 +103,38 @@ class ShardPlan:
         self._flags_host = None
         self._window_cache: dict = {}
 
+    @property
+    def batch(self) -> Batch:
+        if self._batch is None:  # nothing added yet: float32 (FAST counts are CDF_FLOAT) until a cube says otherwise
+            self._dtype = np.dtype(np.float32)
+            self._batch = Batch(self.ctx, self._dtype, n_groups=self.n_groups)
+        return self._batch
+
+    @staticmethod
+    def compute_dtype(data_dtype) -> np.dtype:
+        """The dtype numpy computes a cube of ``data_dtype`` in: float32 / float64 stay; everything else
+        (integer counts) goes through float64, the dtype ``np.nanpercentile`` and matplotlib use for it."""
+        dt = np.dtype(data_dtype)
+        return dt if dt in (np.float32, np.float64) else np.dtype(np.float64)
+
     # ------------------------------------------------------------- phase 1: files
     def add_orbit(self, orbit: int, datasets: dict, lines: dict | None = None):
-        """``datasets``: {inst: load_fast_cdf_dataset(...) dict}; ``lines``: {inst: cusp timestamps}."""
+        """``datasets``: {inst: load_fast_cdf_dataset(...) dict}; ``lines``: {inst: cusp timestamps}.
+
+        Raises ``TypeError`` when a cube's float dtype differs from the shard's: the reference computes
+        every file in its own dtype, and pools of mixed dtypes in float64 (``np.concatenate`` promotes,
+        ``CS/fast/extrema.py:280``); one shard computes in one dtype, so the caller has to keep files
+        of different dtypes in different shards rather than have them cast behind its back."""
+        for inst, ds in datasets.items():
+            if "device_ptr" in ds:
+                continue
+            want = self.compute_dtype(np.asarray(ds["data"]).dtype)
+            if self._dtype is None:
+                self._dtype = want
+                self._batch = Batch(self.ctx, want, n_groups=self.n_groups)
+            elif want != self._dtype:
+                raise TypeError(f"orbit {orbit} {inst}: cube dtype {np.asarray(ds['data']).dtype} in a {self._dtype} shard "
+                                "(mixed dtypes are not cast silently: use one shard per dtype)")
         entry = {"orbit": orbit, "files": {}, "lines": lines or {}}
         for inst, ds in datasets.items():
             energy = np.asarray(ds["energy"])
@@ -111,7 +144,7 @@ class ShardPlan:
                 fid = self.batch.add_file(None, bits, shape=ds["shape"], layout=ds.get("layout"), device_ptr=ds["device_ptr"])
             else:
                 data = np.asarray(ds["data"])
-                if data.dtype != self.batch.dtype:
+                if data.dtype != self.batch.dtype:  # integer counts only (see compute_dtype): exact in float64
                     data = data.astype(self.batch.dtype)
                 fid = self.batch.add_file(data, bits)
             self.file_meta.append({"times": np.asarray(ds["times"]), "energy": energy, "keys": keys, "inst": inst, "orbit": orbit})
@@ -123,6 +156,11 @@ class ShardPlan:
 
     def collapse(self):
         self.batch.collapse()
+
+    def collapse_pending(self) -> int:
+        """Streaming ingest (``engine.Batch.collapse_pending``): upload + K1 for the orbits added since
+        the last call; their cubes are not kept, neither on the host nor in HBM."""
+        return self.batch.collapse_pending()
 
     def fetch_flags(self):
         self._flags_host = self.batch.all_flags()

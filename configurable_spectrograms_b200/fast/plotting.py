@@ -135,10 +135,8 @@ def FAST_plot_pitch_angle_grid(
         if not vertical_lines:
             log_exception(f"No vertical lines found for orbit {orbit_number} in {cdf_file_path}. Skipping.", level="message")
     key = instrument_type or "unknown"
-    data = np.asarray(dataset["data"])
     shard = ShardPlan(_lib.default_context(), scale_function_y, scale_function_z, zoom_duration_minutes,
-                      instrument_order=(key,), pitch_angle_categories=pitch_angle_categories,
-                      dtype=data.dtype if data.dtype in (np.float32, np.float64) else np.float64)
+                      instrument_order=(key,), pitch_angle_categories=pitch_angle_categories)
     shard.add_orbit(orbit_number, {key: dataset}, {key: vertical_lines})
     shard.upload()
     shard.collapse()
@@ -173,7 +171,6 @@ def FAST_plot_instrument_grid(
     and skipped.  Returns ``(fig, canvas)`` or ``(None, None)``."""
     datasets, lines = {}, {}
     first = True
-    dtype = np.float32
     for inst in instrument_order:
         path = cdf_file_paths.get(inst)
         if not path:
@@ -181,8 +178,6 @@ def FAST_plot_instrument_grid(
         try:
             ds = load_fast_cdf_dataset(path)
             datasets[inst] = ds
-            if np.asarray(ds["data"]).dtype == np.float64:
-                dtype = np.float64
             if first and filtered_orbits_df is not None and orbit_number is not None:
                 # only the first loadable instrument is asked for cusp timestamps (reference :258-265)
                 lines[inst] = get_timestamps_for_orbit(filtered_orbits_df, orbit_number, get_cdf_file_type(path), ds["times"])
@@ -194,7 +189,7 @@ def FAST_plot_instrument_grid(
     if not datasets:
         return None, None
     shard = ShardPlan(_lib.default_context(), scale_function_y, scale_function_z, zoom_duration_minutes,
-                      instrument_order=tuple(instrument_order), dtype=dtype)
+                      instrument_order=tuple(instrument_order))  # dtype from the files; mixed float dtypes raise
     shard.add_orbit(orbit_number, datasets, lines if lines else None)
     shard.upload()
     shard.collapse()

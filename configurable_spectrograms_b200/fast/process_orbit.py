@@ -106,7 +106,7 @@ def FAST_process_single_orbit(
         os.makedirs(output_dir, exist_ok=True)
 
         # ---- load every instrument once (the reference reloads each file five times or more)
-        datasets, lines, dtype = {}, {}, np.float32
+        datasets, lines = {}, {}
         for inst in DEFAULT_INSTRUMENT_ORDER:
             path = instrument_file_paths.get(inst)
             if not path:
@@ -118,16 +118,16 @@ def FAST_process_single_orbit(
                 ds = load_fast_cdf_dataset(path)
                 datasets[inst] = ds
                 lines[inst] = get_timestamps_for_orbit(filtered_orbits_dataframe, orbit_number, detected, ds["times"])
-                if np.asarray(ds["data"]).dtype == np.float64:
-                    dtype = np.float64
             except Exception as exc:
                 err = f"[FAIL] Plotting Orbit {orbit_number} pitch angle grid for {inst}"
                 log_exception(err, exc, level="error")
                 result["status"] = "error"
                 result["errors"].append(err)
         if datasets:
+            # the shard computes in the files' own dtype (numpy's results depend on it); files of different
+            # float dtypes in one orbit are refused by add_orbit -> "[FAIL] Orbit ... processing" below
             shard = ShardPlan(_lib.default_context(), y_axis_scale, z_axis_scale, zoom_duration_minutes,
-                              instrument_order=tuple(instrument_order), dtype=dtype)
+                              instrument_order=tuple(instrument_order))
             shard.add_orbit(orbit_number, datasets, lines)
             shard.upload()
             shard.collapse()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 17
+#define CSG_ABI_VERSION 18
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -83,6 +83,7 @@ CSG_API int csg_host_register(csg_ctx* ctx, void* h_ptr, size_t bytes); /* pin c
 CSG_API int csg_host_unregister(csg_ctx* ctx, void* h_ptr);
 CSG_API int csg_h2d(csg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
 CSG_API int csg_d2h(csg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
+CSG_API int csg_d2d(csg_ctx* ctx, void* d_dst, const void* d_src, size_t bytes); /* async on the ctx stream */
 CSG_API int csg_memset(csg_ctx* ctx, void* d_dst, int byte_value, size_t bytes);
 /* Result read-back on the context's copy-out stream: ordered after everything enqueued on the
  * ctx stream so far, but later ctx-stream work (the next shard's uploads and kernels) does not

@@ -135,19 +135,15 @@ def write_cdf(path, variables, encoding=IBMPC, file_gzip=False):
 
 
 def write_fast_cdf(path, arrays, encoding=IBMPC, gzip=None, records_per_block=64, file_gzip=False):
-    """The four FAST ESA variables of ``synth.make_file_arrays`` as a CDF file.  ``energy`` /
-    ``pitch_angle`` get the real files' shapes: a few records of (P, E) and one (P, E) record per
-    time step respectively (``FAST CDF variables.txt``), although only record 0 is ever used."""
+    """The four FAST ESA variables of ``synth.make_file_arrays`` as a CDF file.  Like the real files,
+    ``energy`` holds a few records and ``pitch_angle`` one record per time step (``FAST CDF variables.txt``)
+    although only record 0 of either is ever used (``CS/cdf_utils.py:252-253``)."""
     T = len(arrays["time_unix"])
-    data = np.asarray(arrays["data"])
-    P_, E_ = data.shape[1], data.shape[2]
-    energy = np.broadcast_to(np.asarray(arrays["energy"], dtype=np.float32).reshape(1, -1, E_)[:, :1, :], (2, P_, E_)).copy() \
-        if np.asarray(arrays["energy"]).shape[1] == 1 else np.repeat(np.asarray(arrays["energy"], dtype=np.float32), 2, axis=0)
-    pa0 = np.asarray(arrays["pitch_angle"], dtype=np.float32)
-    pa = np.broadcast_to(pa0.reshape(1, P_, -1)[:, :, :1], (T, P_, E_)).copy() if pa0.shape[2] == 1 else np.repeat(pa0, T, axis=0)
+    energy = np.repeat(np.asarray(arrays["energy"], dtype=np.float32)[:1], 2, axis=0)
+    pa = np.repeat(np.asarray(arrays["pitch_angle"], dtype=np.float32)[:1], max(T, 1), axis=0)
     write_cdf(path, [
         {"name": "time_unix", "data": np.asarray(arrays["time_unix"], dtype=np.float64), "gzip": gzip, "records_per_block": 256},
-        {"name": "data", "data": data, "gzip": gzip, "records_per_block": records_per_block},
+        {"name": "data", "data": np.asarray(arrays["data"]), "gzip": gzip, "records_per_block": records_per_block},
         {"name": "energy", "data": energy, "gzip": gzip},
         {"name": "pitch_angle", "data": pa, "gzip": gzip, "records_per_block": records_per_block},
     ], encoding=encoding, file_gzip=file_gzip)

@@ -200,6 +200,157 @@ def test_directory_driver_matches_reference_outputs(tmp_path, monkeypatch):
     assert again == []
 
 
+def _run_driver(**kw):
+    from configurable_spectrograms_b200 import cdf_utils
+    from configurable_spectrograms_b200.fast.batch_directory import FAST_plot_spectrograms_directory
+
+    cdf_utils.filtered_orbits_cache.clear()
+    cdf_utils.orbit_column_cache.clear()
+    args = dict(output_base="./FAST_plots/", y_scale="linear", z_scale="log", colormap="cividis", max_processing_percentile=99,
+                max_workers=2, progress_json_path="./progress.json")
+    args.update(kw)
+    return FAST_plot_spectrograms_directory("./FAST_data", **args)
+
+
+def _png_tree(base="./FAST_plots"):
+    out = []
+    for dirpath, _dirs, fs in os.walk(base):
+        out += [os.path.relpath(os.path.join(dirpath, fn), base) for fn in fs]
+    return sorted(out)
+
+
+def test_directory_driver_streams_in_small_chunks(tmp_path, monkeypatch):
+    """The streaming pipeline with chunks of 2 orbits and pinned slots too small for a chunk (some cubes
+    overflow into pageable memory): same statuses, PNG tree, extrema JSON and pixels as one big chunk."""
+    from configurable_spectrograms_b200 import png
+
+    _write_tree(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    gold = load_json("extrema_tree.json")
+    monkeypatch.setenv("CSG_CHUNK_ORBITS", "64")
+    res = _run_driver(output_base="./big/")
+    assert sorted((r["orbit"], r["status"]) for r in res) == [tuple(x) for x in gold["batch_status"]]
+    os.remove("./progress.json"), os.remove("./FAST_calculated_extrema.json")
+    monkeypatch.setenv("CSG_CHUNK_ORBITS", "2")
+    monkeypatch.setenv("CSG_SLOT_BYTES", str(1 << 20))  # 1 MB: two to three of the small test cubes fit, the rest overflow
+    flushes = []
+    import configurable_spectrograms_b200.fast.batch_directory as BD
+
+    real_write = BD._write_json
+    monkeypatch.setattr(BD, "_write_json", lambda path, data: (flushes.append(data.get("linear_log_last_orbit")), real_write(path, data)))
+    res = _run_driver(output_base="./small/", flush_batch_size=2)
+    assert sorted((r["orbit"], r["status"]) for r in res) == [tuple(x) for x in gold["batch_status"]]
+    assert _png_tree("./small") == _png_tree("./big") == gold["batch_pngs"]
+    assert json.load(open("./FAST_calculated_extrema.json")) == gold["batch_extrema"]
+    # progress reaches the disk chunk by chunk (an interrupt loses at most the chunk in flight)
+    assert len(flushes) >= 3 and flushes[0] < flushes[-1] == 13005
+    for name in gold["batch_pngs"][::7]:
+        a = png.decode_rgba(open(os.path.join("./small", name), "rb").read())
+        c = png.decode_rgba(open(os.path.join("./big", name), "rb").read())
+        assert np.array_equal(a, c), name
+
+
+def test_directory_driver_timeouts_and_retry(tmp_path, monkeypatch):
+    """Soft timeouts after the fact + one retry (reference batch_directory.py:316-324,422-431,455-514)."""
+    _write_tree(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    res = _run_driver(orbit_timeout_seconds=0, retry_timeouts=False)
+    assert res and all(r["status"] == "timeout" and r["timeout_type"] == "orbit" for r in res)
+    prog = json.load(open("./progress.json"))
+    assert prog["orbit_linear_log_timed_out"] == sorted({r["orbit"] for r in res})
+    assert prog["linear_log_error_plotting"] == []
+    # with the retry every timed-out orbit is re-run once through FAST_process_single_orbit (whose own soft
+    # limits are generous here) and cleared from the list; results collapse to one entry per orbit
+    os.remove("./progress.json")
+    import configurable_spectrograms_b200.fast.process_orbit as PO
+
+    real = PO.FAST_process_single_orbit
+    calls = []
+
+    def patient(*a, **k):  # the retry hands the same limits down; give the re-run a limit it can meet
+        calls.append(a[0])
+        assert k["orbit_timeout_seconds"] == 0 and k["global_extrema"] is None
+        k["orbit_timeout_seconds"] = 600
+        return real(*a, **k)
+
+    monkeypatch.setattr(PO, "FAST_process_single_orbit", patient)
+    res = _run_driver(orbit_timeout_seconds=0, retry_timeouts=True, output_base="./retry/")
+    assert sorted(calls) == sorted({r["orbit"] for r in res})
+    assert sorted(r["orbit"] for r in res) == sorted({r["orbit"] for r in res})
+    assert all(r["status"] == "ok" for r in res), res
+    prog = json.load(open("./progress.json"))
+    assert prog["orbit_linear_log_timed_out"] == []
+
+
+def test_directory_driver_float64_and_mixed_dtypes(tmp_path, monkeypatch):
+    """A float64 archive is computed in float64 (numpy's sums, ranks and extrema depend on the dtype):
+    extrema JSON against the oracle walk on the same float64 cubes.  One float64 file inside a float32
+    archive is refused -- reported as an error of that orbit -- not cast."""
+    tree = load_npz("extrema_tree.npz")
+    keys = sorted({k.rsplit("_", 1)[0] for k in tree if k.endswith("_relpath")})
+
+    def write(root, dtype_of):
+        for stem in keys:
+            path = root / str(tree[f"{stem}_relpath"])
+            path.parent.mkdir(parents=True, exist_ok=True)
+            path.write_bytes(b"")
+            arrays = {v: tree[f"{stem}_{v}"] for v in ("time_unix", "data", "energy", "pitch_angle")}
+            arrays["data"] = arrays["data"].astype(dtype_of(stem)) * (1.0 + 1e-9 if dtype_of(stem) == np.float64 else 1.0)
+            np.savez(str(path) + ".npz", **arrays)
+        (root / "FAST_Cusp_Indices.csv").write_text(str(tree["csv"]))
+
+    f64 = tmp_path / "f64"
+    f64.mkdir()
+    write(f64, lambda stem: np.float64)
+    monkeypatch.chdir(f64)
+    res = _run_driver()
+    assert res and all(r["status"] == "ok" for r in res)
+    files = []
+    orbits = sorted({int(k.split("_")[0]) for k in keys})
+    for o in orbits:
+        entry = {}
+        for inst in ORDER:
+            if f"{o}_{inst}_data" in tree:
+                ds = dataset_from_arrays({v: tree[f"{o}_{inst}_{v}"] for v in ("time_unix", "data", "energy", "pitch_angle")})
+                entry[inst] = (ds["energy"], ds["data"].astype(np.float64) * (1.0 + 1e-9))
+        files.append((o, entry))
+    want = R.global_extrema(files, ORDER, "linear", "log", state={}, max_percentile=99.0)
+    got = json.load(open("./FAST_calculated_extrema.json"))
+    assert got == want
+    mixed = tmp_path / "mixed"
+    mixed.mkdir()
+    odd = next(k for k in keys if k.startswith("13002_ees"))
+    write(mixed, lambda stem: np.float64 if stem == odd else np.float32)
+    monkeypatch.chdir(mixed)
+    res = _run_driver()
+    by_orbit = {}
+    for r in res:
+        by_orbit.setdefault(r["orbit"], set()).add(r["status"])
+    assert by_orbit[13002] == {"error"} and all(v == {"ok"} for o, v in by_orbit.items() if o != 13002)
+    assert json.load(open("./progress.json"))["linear_log_error_plotting"] == [13002]
+
+
+def test_directory_driver_reads_binary_cdf_files(tmp_path, monkeypatch):
+    """The same golden tree stored as real CDF v3 files (gzip-compressed variables, network byte order) --
+    read by the native reader straight into the pinned slots -- gives the reference's outputs."""
+    from tests import cdf_writer as W
+
+    tree = load_npz("extrema_tree.npz")
+    keys = sorted({k.rsplit("_", 1)[0] for k in tree if k.endswith("_relpath")})
+    for stem in keys:
+        path = tmp_path / str(tree[f"{stem}_relpath"])
+        path.parent.mkdir(parents=True, exist_ok=True)
+        W.write_fast_cdf(path, {v: tree[f"{stem}_{v}"] for v in ("time_unix", "data", "energy", "pitch_angle")},
+                         encoding=W.NETWORK, gzip=4, records_per_block=8)
+    (tmp_path / "FAST_Cusp_Indices.csv").write_text(str(tree["csv"]))
+    monkeypatch.chdir(tmp_path)
+    gold = load_json("extrema_tree.json")
+    res = _run_driver()
+    assert sorted((r["orbit"], r["status"]) for r in res) == [tuple(x) for x in gold["batch_status"]]
+    assert _png_tree() == gold["batch_pngs"]
+    assert json.load(open("./FAST_calculated_extrema.json")) == gold["batch_extrema"]
+
+
 def test_process_single_orbit_and_generic_batch(tmp_path, monkeypatch):
     from configurable_spectrograms_b200 import cdf_utils
     from configurable_spectrograms_b200.cdf_utils import load_fast_cdf_dataset, load_filtered_orbits

@@ -138,6 +138,45 @@ def test_collapse_ragged_batch_and_host_entry(ctx):
     assert np.array_equal(bits(nansum(cubes[3])), bits(np.nansum(cubes[3], axis=1)))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_collapse_pending_streams_through_a_pinned_ring(ctx, dtype):
+    """Streaming ingest: files registered and collapsed chunk by chunk through pinned slots (one too
+    small, so a cube overflows into pageable memory), host cubes dropped after each chunk, the sums /
+    flags buffers growing along the way -- bit for bit the all-at-once result."""
+    from configurable_spectrograms_b200 import _lib
+    from configurable_spectrograms_b200.engine import Batch
+
+    rng = np.random.default_rng(31)
+    shapes = [(40, 64, 96), (7, 10, 12), (55, 64, 96), (1, 64, 96), (0, 64, 96), (33, 16, 96), (90, 64, 96), (12, 5, 4)]
+    cubes = [_rand_cube(rng, s, dtype) for s in shapes]
+    masks = [[rng.random(s[1]) < f for f in (0.8, 0.3)] for s in shapes]
+    ring = _lib.PinnedRing(ctx, n_slots=2, slot_bytes=40 * 64 * 96 * np.dtype(dtype).itemsize + 4096)
+    b = Batch(ctx, dtype, n_groups=2)
+    ids = []
+    for lo in range(0, len(cubes), 3):
+        slot = ring.acquire()
+        for c, m in zip(cubes[lo : lo + 3], masks[lo : lo + 3]):
+            staged = ring.alloc(slot, c.shape, c.dtype)
+            staged[...] = c
+            ids.append(b.add_file(staged, _bits_from_masks(m)))
+        assert b.collapse_pending() == sum(1 for c in cubes[lo : lo + 3] if c.shape[0] > 0)
+        ring.release(slot)
+        assert all(f["host"] is None for f in b.files if f["T"] > 0)
+    assert ring.overflow_bytes > 0
+    ref = Batch(ctx, dtype, n_groups=2)
+    rids = [ref.add_file(c, _bits_from_masks(m)) for c, m in zip(cubes, masks)]
+    ref.upload_cubes()
+    ref.collapse()
+    for f, r, c, m in zip(ids, rids, cubes, masks):
+        with np.errstate(invalid="ignore"):
+            assert same_bits(b.sums(f, 0), np.nansum(c, axis=1), zero_sign_insensitive=False)
+        for g in range(3):
+            assert same_bits(b.sums(f, g), ref.sums(r, g), zero_sign_insensitive=False)
+        assert np.array_equal(b.flags(f), ref.flags(r))
+    assert b.collapse_pending() == 0
+    ring.close()
+
+
 def _region_ref(m, cols, rows):
     return m[np.ix_(rows, cols)].T
 
