@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--orbits-per-gpu", type=int, default=125)
+    ap.add_argument("--total-orbits", type=int, default=0,
+                    help="strong scaling: this many orbits in all, split over the GPUs (1000 = BASELINE config 4; fits one B200)")
     ap.add_argument("--cpu-sample-orbits", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -633,7 +635,10 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # nvidia-smi needs ~1 s before its first row: start it ahead of the GPU work
-    n_local = args.orbits_per_gpu
+    strong = args.total_orbits > 0
+    if strong and args.total_orbits % world:
+        raise SystemExit(f"--total-orbits {args.total_orbits} does not divide over {world} GPUs")
+    n_local = args.total_orbits // world if strong else args.orbits_per_gpu
     first = rank * n_local
     files, orbits, total_elems = orbit_layout(n_local, first, args.seed)
     cubes = generate_cubes(torch, files, total_elems, dev)
@@ -772,6 +777,16 @@ def main():
                      "phases_s": phases, "host_zlib6_s_per_figure_1thread": host_s / max(1, len(sample)),
                      "host_zlib6_ratio": sum(4 * H * W + H for H, W, _ in (f.layout() for f in sample)) / max(1, host_bytes),
                      "note": "compose + Up filter + fixed-Huffman DEFLATE on the GPU, D2H of the compressed bytes and PNG framing included; not part of `value`"}
+    # the carrier of the extrema exchange and what its all-gathers waited for (rank skew + link latency)
+    exchange, exchange_info = None, {"exchange": "none (1 rank)"}
+    if world > 1:
+        sel = getattr(shard, "_pool_selector_side", None) or getattr(shard, "_pool_selector", None)
+        exchange = getattr(sel, "_exchange", None) if sel is not None else None
+        kind = getattr(exchange, "kind", "unknown")
+        exchange_info = {"exchange": "peer mailboxes over NVLink (csrc/peer.cu)" if kind == "peer" else "NCCL all_gather_into_tensor",
+                         "exchanges_per_step": 6, "rendezvous": "torch.distributed NCCL (barriers, timing all-reduce only)"}
+        if kind == "peer":
+            exchange_info["wait_us"] = exchange.wait_stats(60)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -831,6 +846,23 @@ def main():
 
         e2e_step()
         e2e_drain()
+        # stand-alone ceilings of the two copies the e2e step makes: the same pinned buffers, no kernels, every
+        # rank at once (the ranks share the host's memory and PCIe fabric) -- e2e is bounded by max(H2D, D2H) of these
+        def copy_rate(fn, nbytes, reps=3):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            ctx.sync()
+            ctx.side_sync()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+            return world * nbytes * reps / float(dt.item()) / 1e9
+
+        h2d_gbs = copy_rate(lambda: ctx._check(ctx.lib.csg_h2d(ctx.handle, cubes.data_ptr(), host.data_ptr(), cube_bytes)), cube_bytes)
+        d2h_gbs = copy_rate(lambda: ctx.d2h_side(rgba_host.data_ptr(), shard.batch.d_rgba.ptr, n_px * 4), n_px * 4)
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(2, min(args.steps, 4))
@@ -841,8 +873,13 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
-        e2e = {"value": total_orbits / (float(dt.item()) / n_e2e), "unit": "orbits/s",
-               "h2d_bytes_per_step": int(cube_bytes), "d2h_bytes_per_step": int(n_px * 4), "steps": n_e2e}
+        e2e_value = total_orbits / (float(dt.item()) / n_e2e)
+        ceiling = world * n_local / (cube_bytes / (h2d_gbs / world * 1e9))  # orbits/s if nothing but the upload took time
+        e2e = {"value": e2e_value, "unit": "orbits/s",
+               "h2d_bytes_per_step": int(cube_bytes), "d2h_bytes_per_step": int(n_px * 4), "steps": n_e2e,
+               "h2d_ceiling_gbs": h2d_gbs, "d2h_ceiling_gbs": d2h_gbs, "h2d_achieved_gbs": e2e_value / total_orbits * world * cube_bytes / 1e9,
+               "frac_of_h2d_ceiling": e2e_value / ceiling,
+               "note": "ceilings: aggregate over all ranks of the same pinned copies alone (no kernels), all ranks copying at once"}
 
     # ------------------------------------------------ api_e2e: the public call, directory -> PNG files
     api = None
@@ -868,9 +905,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "orbits/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_local, world),
+            "collective": exchange_info,
             "plan": {"panels_per_gpu": shard.batch.n_panels, "regions_per_gpu": shard.batch.n_regions,
                      "pixels_per_gpu": shard.batch.n_pixels, "numa_bound_cpus": numa_cpus},
             "roofline": {"bound": "hbm", "kernel": "collapse_stream_kernel<float,4,384>", "achieved": achieved, "peak": peak,
@@ -889,6 +927,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if exchange is not None and hasattr(exchange, "close"):
+            exchange.close()  # collective: unmap the peers' mailboxes, barrier, free the own one
         torch.distributed.destroy_process_group()
 
 

@@ -12,9 +12,10 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcsgpu.so")
+# CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
+LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -209,6 +210,7 @@ SIGNATURES = {
     "csg_peer_allgather": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "csg_peer_error_word": (_vp, [_vp]),
     "csg_peer_clear_error": (_i, [_vp, _vp]),
+    "csg_peer_wait_stats": (_i, [_vp, _vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "csg_peer_disconnect": (_i, [_vp, _vp]),
     "csg_peer_destroy": (_i, [_vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
@@ -365,6 +367,7 @@ class PinnedRing:
             raise ValueError("n_slots must be 1..16")
         self.ctx = ctx
         self.slot_bytes = int(slot_bytes)
+        self.limit = self.slot_bytes  # bytes of a slot handed out per chunk (shared_ring may lower it for a call)
         self.slots = [ctx.pinned(self.slot_bytes) for _ in range(n_slots)]
         self._used = [0] * n_slots
         self._in_flight = [False] * n_slots
@@ -389,7 +392,7 @@ class PinnedRing:
         n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
         with self._lock:
             off = (self._used[slot] + 255) & ~255
-            if off + n > self.slot_bytes:
+            if off + n > self.limit:
                 self.overflow_bytes += n
                 return np.empty(shape, dtype=dt)
             self._used[slot] = off + n
@@ -400,13 +403,35 @@ class PinnedRing:
         self.ctx.event_record(self.FIRST_EVENT + slot)
         self._in_flight[slot] = True
 
-    def close(self):
+    def drain(self):
+        """Wait until no slot is in flight (the ring itself stays allocated for the next call)."""
         for k, busy in enumerate(self._in_flight):
             if busy:
                 self.ctx.event_sync(self.FIRST_EVENT + k)
+                self._in_flight[k] = False
+
+    def close(self):
+        self.drain()
         for s in self.slots:
             s.free()
         self.slots = []
+
+
+def shared_ring(ctx: "Context", n_slots: int = 3, slot_bytes: int = 1 << 30) -> PinnedRing:
+    """The context's staging ring, allocated on first use and kept: page-locking memory costs about a
+    quarter of a second per GB, far more than a streaming call spends anywhere else.  A call that asks for
+    larger slots replaces it."""
+    ring = ctx.__dict__.get("_ring")
+    if ring is not None and (ring.slot_bytes < slot_bytes or len(ring.slots) < n_slots):
+        ring.close()
+        ring = None
+    if ring is None:
+        ring = ctx.__dict__["_ring"] = PinnedRing(ctx, n_slots, slot_bytes)
+    ring.drain()
+    ring.overflow_bytes = 0
+    ring._next = 0
+    ring.limit = min(int(slot_bytes), ring.slot_bytes)
+    return ring
 
 
 class Context:

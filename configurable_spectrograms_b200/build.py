@@ -42,36 +42,42 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into ``libcsgpu.so`` (cross-compiles without a GPU)."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: str | None = None) -> str:
+    """Compile every CUDA source into ``libcsgpu.so`` (cross-compiles without a GPU).
+
+    ``defines`` / ``out``: an experiment build (``-DNAME=VALUE`` flags, another output file, its own
+    object directory) to A/B against the product library through ``CSG_LIBRARY``."""
+    if out is None and not defines and not force and not is_stale():
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out).replace(".", "_"))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-        if verbose and out:
-            print(out)
-    tmp = LIB + ".tmp"
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+        if verbose and log:
+            print(log)
+    target = LIB if out is None else out
+    tmp = target + ".tmp"
     cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-lz"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, target)
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

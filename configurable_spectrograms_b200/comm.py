@@ -172,7 +172,20 @@ class PeerExchange:
         self._grow(slot_bytes)
 
     def _grow(self, slot_bytes: int):
-        raise NotImplementedError
+        """Abstract: (re)create the mailboxes with room for ``slot_bytes`` per rank and wire the ranks up
+        (CUDA IPC in :class:`IpcPeerExchange`, raw pointers in :class:`_SharedPeer`)."""
+        raise NotImplementedError(f"{type(self).__name__} must implement _grow()")
+
+    def wait_stats(self, last_n: int = 64) -> dict:
+        """``{"mean_us", "max_us"}`` of the time the last ``last_n`` exchanges spent waiting for the other
+        ranks' epochs (rank skew + link latency; ``clock64`` inside the exchange kernel)."""
+        import ctypes as C
+
+        if self.handle is None:
+            return {"mean_us": 0.0, "max_us": 0.0}
+        mean, top = C.c_double(), C.c_double()
+        self.ctx._check(self.ctx.lib.csg_peer_wait_stats(self.ctx.handle, self.handle, int(last_n), C.byref(mean), C.byref(top)))
+        return {"mean_us": mean.value, "max_us": top.value}
 
     def allgather(self, src_ptr: int, nbytes: int) -> int:
         import ctypes as C
@@ -220,9 +233,21 @@ class IpcPeerExchange(PeerExchange):
                 ok = False
         # the decision is collective: either every rank talks through mailboxes or none does
         if not all(self.comm.allgather_object(ok)):
-            self.destroy()
+            self.close()  # two-phase: some ranks may have mapped this mailbox already
             raise RuntimeError("CUDA IPC / peer access is unavailable on at least one rank")
         self.comm.barrier()
+
+
+    def close(self):
+        """Collective teardown (every rank calls it): unmap the other ranks' mailboxes, meet, and only then
+        free the own one -- an exporter must not free memory an importer still has mapped.  ``destroy()`` /
+        ``__del__`` alone are only safe once every peer process has closed or exited."""
+        if self.handle is None:
+            return
+        self.ctx.sync()
+        self.ctx.lib.csg_peer_disconnect(self.ctx.handle, self.handle)
+        self.comm.barrier()
+        self.destroy()
 
 
 class SharedPeerGroup:

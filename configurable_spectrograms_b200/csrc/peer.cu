@@ -3,11 +3,11 @@
 // ranks' HBM over NVLink / NVSwitch instead of library collectives.
 //
 // Every rank owns a mailbox in its own HBM:  flags[region][src_rank] (uint64 epochs) and
-// data[region][src_rank][...].  An all-gather is one `put` kernel -- each rank copies its
-// (tiny: a few hundred KB of bucket totals at most) payload into every peer's mailbox with
-// 128-bit stores, fences at system scope and then publishes the epoch in every peer's flag
-// word with a release store -- plus one `wait` kernel that spins (acquire loads) on the local
-// flag words until every rank's epoch has arrived.  Consumers then read their own HBM.
+// data[region][src_rank][...].  An all-gather is ONE kernel: each rank copies its (tiny: a few
+// hundred KB of bucket totals at most) payload into every peer's mailbox with 128-bit stores,
+// fences at system scope, publishes the epoch in every peer's flag word with a release store,
+// and its last block then spins (acquire loads) on the local flag words until every rank's
+// epoch has arrived.  Consumers follow on the stream and read their own HBM.
 // Payloads travel once, nothing leaves the stream, the host never blocks, and the latency
 // of one exchange is a few microseconds.
 //
@@ -36,6 +36,7 @@ struct csg_peer {
   unsigned long long epoch;
   unsigned* d_counter;
   int* d_error;  // 0, or 1 + the rank whose epoch did not arrive in time
+  long long* d_wait_log;  // cycles the last 64 exchanges spent waiting for the other ranks' epochs
   bool connected;
 };
 
@@ -54,38 +55,46 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// grid (chunks, n_ranks): blockIdx.y = destination rank
+// One kernel per all-gather.  grid (chunks, n_ranks): blockIdx.y = destination rank.  Every block stores its
+// share of the payload into that rank's mailbox and fences; the block that finishes last publishes the
+// epoch in every peer's flag word and then -- still inside the kernel, so the consumer simply follows on
+// the stream -- waits until every rank's epoch has arrived in the local flags (lane r watches rank r).
+// wait_log[epoch % 64] receives the cycles spent in that wait (rank skew + link latency).
 __global__ void __launch_bounds__(256)
-    peer_put_kernel(PeerTable tbl, const uint4* __restrict__ src, size_t n16, size_t data_off, size_t flag_off,
-                    unsigned long long epoch, unsigned* __restrict__ counter, int n_ranks) {
+    peer_exchange_kernel(PeerTable tbl, const uint4* __restrict__ src, size_t n16, size_t data_off, size_t flag_off,
+                         unsigned long long epoch, unsigned* __restrict__ counter, int n_ranks,
+                         const unsigned long long* __restrict__ local_flags, int* __restrict__ error, long long timeout_cycles,
+                         long long* __restrict__ wait_log) {
   uint4* dst = reinterpret_cast<uint4*>(tbl.p[blockIdx.y] + data_off);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
   __threadfence_system();
   __syncthreads();
+  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(counter, 1u) + 1u;
-    if (done == gridDim.x * gridDim.y) {  // every block's stores are fenced: publish
+    s_last = done == gridDim.x * gridDim.y;
+    if (s_last) {  // every block's stores are fenced: publish
       *counter = 0;
       __threadfence_system();
       for (int r = 0; r < n_ranks; ++r)
         st_release_sys(reinterpret_cast<unsigned long long*>(tbl.p[r] + flag_off), epoch);
     }
   }
-}
-
-__global__ void peer_wait_kernel(const unsigned long long* __restrict__ flags, int n_ranks, unsigned long long epoch,
-                                 int* __restrict__ error, long long timeout_cycles) {
-  const int r = threadIdx.x;
-  if (r >= n_ranks) return;
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
   const long long t0 = clock64();
-  while (ld_acquire_sys(flags + r) < epoch) {
-    if (clock64() - t0 > timeout_cycles) {  // never hang the GPU: flag the step, let it finish
-      atomicCAS(error, 0, 1 + r);
-      break;
+  if ((int)threadIdx.x < n_ranks) {
+    while (ld_acquire_sys(local_flags + threadIdx.x) < epoch) {
+      if (clock64() - t0 > timeout_cycles) {  // never hang the GPU: flag the step, let it finish
+        atomicCAS(error, 0, 1 + (int)threadIdx.x);
+        break;
+      }
+      __nanosleep(32);
     }
-    __nanosleep(64);
   }
+  __syncwarp();
+  if (threadIdx.x == 0) wait_log[epoch & 63ull] = clock64() - t0;
 }
 
 size_t round_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
@@ -106,9 +115,9 @@ int csg_peer_create(csg_ctx* ctx, int rank, int n_ranks, size_t slot_bytes, csg_
   p->flags_bytes = round_up((size_t)p->n_regions * CSG_PEER_MAX * sizeof(unsigned long long), 4096);
   p->mailbox_bytes = p->flags_bytes + (size_t)p->n_regions * n_ranks * p->slot_bytes;
   cudaError_t e = cudaMalloc((void**)&p->local, p->mailbox_bytes);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_counter, 256);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_counter, 1024);
   if (e == cudaSuccess) e = cudaMemset(p->local, 0, p->mailbox_bytes);  // epochs start at 0
-  if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, 256);
+  if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, 1024);
   if (e != cudaSuccess) {
     if (p->local) cudaFree(p->local);
     if (p->d_counter) cudaFree(p->d_counter);
@@ -116,6 +125,7 @@ int csg_peer_create(csg_ctx* ctx, int rank, int n_ranks, size_t slot_bytes, csg_
     return csg_fail(ctx, CSG_ERR_CUDA, "peer mailbox allocation failed: %s", cudaGetErrorString(e));
   }
   p->d_error = reinterpret_cast<int*>(p->d_counter) + 32;
+  p->d_wait_log = reinterpret_cast<long long*>(p->d_counter) + 32;  // bytes 256 .. 767
   p->peers[rank] = p->local;
   if (ipc_handle_64) {
     cudaIpcMemHandle_t h;
@@ -175,9 +185,6 @@ int csg_peer_allgather(csg_ctx* ctx, csg_peer* p, const void* d_src, size_t nbyt
   int chunks = (int)((n16 + 1023) / 1024);
   if (chunks < 1) chunks = 1;
   if (chunks > 32) chunks = 32;
-  peer_put_kernel<<<dim3(chunks, p->n_ranks), 256, 0, ctx->stream>>>(tbl, (const uint4*)d_src, n16, data_off, flag_off, epoch,
-                                                                     p->d_counter, p->n_ranks);
-  CSG_LAUNCH_CHECK(ctx, "peer_put_kernel");
   const unsigned long long* flags =
       reinterpret_cast<const unsigned long long*>(p->local + (size_t)region * CSG_PEER_MAX * sizeof(unsigned long long));
   // a rank may arrive seconds late (first-step planning, lazy module loads): wait long, never forever
@@ -188,13 +195,37 @@ int csg_peer_allgather(csg_ctx* ctx, csg_peer* p, const void* d_src, size_t nbyt
     if (!(seconds > 0.0)) seconds = 20.0;
     timeout_cycles = (long long)(seconds * 2.0e9);
   }
-  peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, p->n_ranks, epoch, p->d_error, timeout_cycles);
-  CSG_LAUNCH_CHECK(ctx, "peer_wait_kernel");
+  peer_exchange_kernel<<<dim3(chunks, p->n_ranks), 256, 0, ctx->stream>>>(tbl, (const uint4*)d_src, n16, data_off, flag_off,
+                                                                          epoch, p->d_counter, p->n_ranks, flags, p->d_error,
+                                                                          timeout_cycles, p->d_wait_log);
+  CSG_LAUNCH_CHECK(ctx, "peer_exchange_kernel");
   *d_gathered = p->local + region_off;
   return CSG_OK;
 }
 
 void* csg_peer_error_word(csg_peer* p) { return p ? (void*)p->d_error : nullptr; }
+
+int csg_peer_wait_stats(csg_ctx* ctx, csg_peer* p, int last_n, double* mean_us, double* max_us) {
+  if (!ctx || !p || !mean_us || !max_us) return CSG_ERR_ARG;
+  *mean_us = *max_us = 0.0;
+  long long log[64];
+  CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CSG_CUDA(ctx, cudaMemcpy(log, p->d_wait_log, sizeof log, cudaMemcpyDeviceToHost));
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);  // clock64 ticks at the SM clock
+  const double us_per_cycle = khz > 0 ? 1000.0 / (double)khz : 1.0 / 1965.0;
+  if (last_n > 64) last_n = 64;
+  if ((unsigned long long)last_n > p->epoch) last_n = (int)p->epoch;
+  if (last_n <= 0) return CSG_OK;
+  double sum = 0.0, top = 0.0;
+  for (int k = 0; k < last_n; ++k) {
+    const double us = (double)log[(p->epoch - (unsigned long long)k) & 63ull] * us_per_cycle;
+    sum += us;
+    if (us > top) top = us;
+  }
+  *mean_us = sum / last_n, *max_us = top;
+  return CSG_OK;
+}
 
 int csg_peer_clear_error(csg_ctx* ctx, csg_peer* p) {
   if (!ctx || !p) return CSG_ERR_ARG;

@@ -245,6 +245,10 @@ constexpr int kPixPerThread = 16;
 constexpr int kPixPerBlock = kRasterThreads * kPixPerThread;
 constexpr int kRows = kThr + 2;       // thr[-1] = -inf, thr[0..256], thr[257] = +inf
 constexpr int kLutRows = 260;
+#ifndef CSG_K3_PIPE
+#define CSG_K3_PIPE 0
+#endif
+constexpr bool kPipe = CSG_K3_PIPE != 0;  // software-pipeline the pixel loop by one group
 
 __device__ __forceinline__ float fast_log2(float x) {
   float r;
@@ -258,7 +262,7 @@ __device__ __forceinline__ void lds(double& v, unsigned addr) { asm volatile("ld
 // The out-of-line half of the rasteriser's value -> threshold-count lookup: walk the lane's own table
 // column from a wrong first guess; NaN (it fails every comparison) counts as 258 = "bad".
 template <typename T>
-__device__ __forceinline__ int recount(T v, int n, unsigned thr_col) {
+__device__ __noinline__ int recount(T v, int n, unsigned thr_col) {
   if (is_nan(v)) return 258;
   auto thr_at = [&](int row) -> T {
     T t;
@@ -397,39 +401,48 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
       continue;
     }
 
-    // value -> number of thresholds <= value (258 for NaN): fast float guess, verified against the exact table.
-    // The common path is ~16 instructions: clamp (2 compares + select), lg2 + fma, clamp + convert, one
-    // address, two ld.shared, two compares; everything else -- a guess that is off by one or more, and NaN
-    // (which fails every comparison and therefore always lands there) -- is out of line.
-    auto to_count = [&](T v, auto log_c) -> int {
+    // value -> number of thresholds <= value (258 for NaN).  A fast float guess n of the count is verified
+    // against the two exact thresholds around it: n thresholds are <= v  <=>  thr[n-1] <= v < thr[n] (table
+    // rows are offset by one: thr[k] = row k + 1).  The common path of a pixel is ~15 instructions: clamp
+    // (2 compares + select), lg2 + fma, 2 x fmnmx + convert, one address, two ld.shared, two compares whose
+    // verdict is only accumulated; a group of four pixels branches ONCE, and only when some guess was off or
+    // some value is NaN (it fails every comparison) does the out-of-line walk (recount) run.
+    auto substituted = [&](T v, auto log_c) -> T {
       constexpr bool LOG = decltype(log_c)::value;
       // the reference's clamps before imshow: CS/plotting.py:278 (log), :310-312 (linear)
-      if (LOG) {
-        v = (v > T(0) && is_finite(v)) ? v : fill_lo;
-      } else {
-        v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
-        v = (v == (T)CUDART_INF) ? fill_hi : v;
-      }
+      if (LOG) return (v > T(0)) & is_finite(v) ? v : fill_lo;
+      v = (is_nan(v) || v == (T)(-CUDART_INF)) ? fill_lo : v;
+      return (v == (T)CUDART_INF) ? fill_hi : v;
+    };
+    auto guess = [&](T v, auto log_c, bool& ok) -> int {
+      constexpr bool LOG = decltype(log_c)::value;
       const float fv = (float)v;
       float gf = __fmaf_rn(LOG ? fast_log2(fv) : fv, c1, c0);
       gf = fminf(fmaxf(gf, 0.f), (float)kThr);  // NaN -> 0
-      int n = (int)gf;
-      // n thresholds are <= v  <=>  thr[n-1] <= v < thr[n]   (rows are offset by one: thr[k] = row k+1)
+      const int n = (int)gf;
       const unsigned row = thr_col + (unsigned)n * (32u * (unsigned)sizeof(T));
-      T b, c;
-      lds(b, row);
-      lds(c, row + 32u * (unsigned)sizeof(T));
-      if (!(b <= v && !(c <= v))) n = recount<T>(v, n, thr_col);  // rare: the float guess was off, or v is NaN
+      T lo_thr, hi_thr;
+      lds(lo_thr, row);
+      lds(hi_thr, row + 32u * (unsigned)sizeof(T));
+      ok = ok & (lo_thr <= v) & !(hi_thr <= v);
       return n;
+    };
+    auto to_count = [&](T raw, auto log_c) -> int {  // single pixels (panel tails)
+      const T v = substituted(raw, log_c);
+      bool ok = true;
+      const int n = guess(v, log_c, ok);
+      return ok ? n : recount<T>(v, n, thr_col);
     };
     auto count_to_index = [](int n) -> int { return n == 0 ? I_UNDER : (n == kThr ? I_OVER : (n == 258 ? I_BAD : n - 1)); };
 
-    // the pixel loop, specialised on the scale and on how time steps are addressed; 32-bit index
-    // math; a thread takes four consecutive pixels per step
+    // the pixel loop, specialised on the scale, on how time steps are addressed and on what is written
+    // (RGBA / index plane; 128-bit stores when the panel's output is aligned -- it always is for buffers
+    // laid out by the host wrapper); 32-bit index math; a thread takes four consecutive pixels per step
     const bool out_vec = (out_off & 3) == 0 && (!out_rgba || (reinterpret_cast<uintptr_t>(rgba) & 15) == 0) &&
                          (!out_idx || (reinterpret_cast<uintptr_t>(index) & 7) == 0);
-    auto pixels = [&](auto log_c, auto rowlist_c) {
+    auto pixels = [&](auto log_c, auto rowlist_c, auto rgba_c, auto idx_c, auto vec_c) {
       constexpr bool ROWLIST = decltype(rowlist_c)::value;
+      constexpr bool RGBA = decltype(rgba_c)::value, INDEX = decltype(idx_c)::value, VEC = decltype(vec_c)::value;
       constexpr unsigned G = 4, STEP = G * kRasterThreads;
       unsigned i = first + G * tid;
       unsigned j = i / nt, tt = i - j * nt;
@@ -462,20 +475,19 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
         }
       };
       auto store4 = [&](unsigned at, const int* n) {
-        if (out_rgba) {
-          if (out_vec)
-            *reinterpret_cast<uint4*>(out_rgba + at) =
-                make_uint4(lut_at(n[0]), lut_at(n[1]), lut_at(n[2]), lut_at(n[3]));
+        if constexpr (RGBA) {
+          if constexpr (VEC)
+            *reinterpret_cast<uint4*>(out_rgba + at) = make_uint4(lut_at(n[0]), lut_at(n[1]), lut_at(n[2]), lut_at(n[3]));
           else {
 #pragma unroll
             for (unsigned u = 0; u < G; ++u) out_rgba[at + u] = lut_at(n[u]);
           }
         }
-        if (out_idx) {
+        if constexpr (INDEX) {
           int idx[G];
 #pragma unroll
           for (unsigned u = 0; u < G; ++u) idx[u] = count_to_index(n[u]);
-          if (out_vec)
+          if constexpr (VEC)
             *reinterpret_cast<uint2*>(out_idx + at) =
                 make_uint2((unsigned)idx[0] | ((unsigned)idx[1] << 16), (unsigned)idx[2] | ((unsigned)idx[3] << 16));
           else {
@@ -488,44 +500,78 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
         i += STEP, j += dq, tt += dr;
         if (tt >= nt) tt -= nt, ++j;
       };
-      // full groups, software-pipelined by one: the next group's cells are requested before the
-      // current group is classified
-      T cur[G];
-      bool have = i + (G - 1) < last;
-      if (have) load4(j, tt, cur);
-      while (have) {
-        const unsigned at = i;
-        advance();
-        T nxt[G];
-        have = i + (G - 1) < last;
-        if (have) load4(j, tt, nxt);
+      // full groups; with kPipe the loop is software-pipelined by one (the next group's cells are requested
+      // before the current group is classified)
+      auto classify_store = [&](unsigned at, T* v) {
         int x[G];
+        bool ok = true;
 #pragma unroll
-        for (unsigned u = 0; u < G; ++u) x[u] = to_count(cur[u], log_c);
+        for (unsigned u = 0; u < G; ++u) {
+          v[u] = substituted(v[u], log_c);
+          x[u] = guess(v[u], log_c, ok);
+        }
+        if (!ok) {  // rare (fully unrolled: a dynamic index would push x[] / v[] into local memory)
+#pragma unroll
+          for (unsigned u = 0; u < G; ++u) x[u] = recount<T>(v[u], x[u], thr_col);
+        }
         store4(at, x);
+      };
+      if constexpr (kPipe) {
+        T cur[G];
+        bool have = i + (G - 1) < last;
+        if (have) load4(j, tt, cur);
+        while (have) {
+          const unsigned at = i;
+          advance();
+          T nxt[G];
+          have = i + (G - 1) < last;
+          if (have) load4(j, tt, nxt);
+          classify_store(at, cur);
 #pragma unroll
-        for (unsigned u = 0; u < G; ++u) cur[u] = nxt[u];
+          for (unsigned u = 0; u < G; ++u) cur[u] = nxt[u];
+        }
+      } else {
+        while (i + (G - 1) < last) {
+          T cur[G];
+          load4(j, tt, cur);
+          classify_store(i, cur);
+          advance();
+        }
       }
       if (i < last) {  // the last, partial group of the panel (i was advanced past every full group)
         unsigned jj = j, t = tt;
         for (unsigned p = i; p < last; ++p) {
           const int n = to_count(__ldg(mat + address(jj, t)), log_c);
-          if (out_rgba) out_rgba[p] = lut_at(n);
-          if (out_idx) out_idx[p] = (uint16_t)count_to_index(n);
+          if constexpr (RGBA) out_rgba[p] = lut_at(n);
+          if constexpr (INDEX) out_idx[p] = (uint16_t)count_to_index(n);
           if (++t == nt) t = 0, ++jj;
         }
       }
     };
+    auto by_output = [&](auto log_c, auto rowlist_c) {
+      // the two configurations the batch path runs get their own instantiation with 128-bit stores; everything
+      // else (index plane only, unaligned output) shares the scalar-store variants
+      if (out_rgba && !out_idx && out_vec)
+        pixels(log_c, rowlist_c, Flag<true>{}, Flag<false>{}, Flag<true>{});
+      else if (out_rgba && out_idx && out_vec)
+        pixels(log_c, rowlist_c, Flag<true>{}, Flag<true>{}, Flag<true>{});
+      else if (out_rgba && out_idx)
+        pixels(log_c, rowlist_c, Flag<true>{}, Flag<true>{}, Flag<false>{});
+      else if (out_rgba)
+        pixels(log_c, rowlist_c, Flag<true>{}, Flag<false>{}, Flag<false>{});
+      else if (out_idx)
+        pixels(log_c, rowlist_c, Flag<false>{}, Flag<true>{}, Flag<false>{});
+    };
     if (log_scale) {
       if (rows_off < 0)
-        pixels(Flag<true>{}, Flag<false>{});
+        by_output(Flag<true>{}, Flag<false>{});
       else
-        pixels(Flag<true>{}, Flag<true>{});
+        by_output(Flag<true>{}, Flag<true>{});
     } else {
       if (rows_off < 0)
-        pixels(Flag<false>{}, Flag<false>{});
+        by_output(Flag<false>{}, Flag<false>{});
       else
-        pixels(Flag<false>{}, Flag<true>{});
+        by_output(Flag<false>{}, Flag<true>{});
     }
   }
 }

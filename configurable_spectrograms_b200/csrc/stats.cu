@@ -28,7 +28,6 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kSample = 4096;   // storage shared by the sample and the candidate lists
 constexpr int kDraw = 2048;     // sample size: two-sided brackets at the 1st / 99th percentile need m*(1-q) > margin
 constexpr int kCand = 2048;     // candidate capacity per bracket (the lists reuse the sample's storage)
@@ -123,6 +122,29 @@ __device__ void block_sort(U* a, int n_pow2) {
 // the few unaligned head / tail cells of every row and row-list regions take a scalar loop.
 // fn(v, in) is called with block-uniform control flow (`in` = this lane holds a real cell), so
 // it may use full-mask warp primitives.
+template <bool B>
+struct Flag {
+  static constexpr bool value = B;
+};
+
+// c += (v OP r): one compare and one predicated add.  (Written as `c += cond ? 1 : 0` the compiler emits
+// add-to-temporary / predicated move / move back -- three instructions per counter per cell.)
+#define CSG_COUNT_IF(NAME, OP)                                                                              \
+  __device__ __forceinline__ void NAME(unsigned& c, float v, float r) {                                     \
+    asm("{ .reg .pred q; setp." OP ".f32 q, %1, %2; @q add.u32 %0, %0, 1; }" : "+r"(c) : "f"(v), "f"(r));    \
+  }                                                                                                         \
+  __device__ __forceinline__ void NAME(unsigned& c, double v, double r) {                                   \
+    asm("{ .reg .pred q; setp." OP ".f64 q, %1, %2; @q add.u32 %0, %0, 1; }" : "+r"(c) : "d"(v), "d"(r));    \
+  }
+__device__ __forceinline__ float min_of(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float max_of(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double min_of(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double max_of(double a, double b) { return fmax(a, b); }
+CSG_COUNT_IF(count_if_gt, "gt")
+CSG_COUNT_IF(count_if_lt, "lt")
+CSG_COUNT_IF(count_if_eq, "eq")
+#undef CSG_COUNT_IF
+
 template <typename T, typename Fn>
 __device__ __forceinline__ void for_each_cell(const T* __restrict__ mats, const csg_region& rg,
                                               const int32_t* __restrict__ pool, const int* s_cols, bool cols_in_smem,
@@ -196,6 +218,68 @@ __device__ __forceinline__ void for_each_cell(const T* __restrict__ mats, const 
   }
 }
 
+// The same walk for per-thread work: fn(v) is called for real cells only (no lane masks, no warp
+// primitives inside fn); a thread takes whole 16-byte vectors, two in flight.
+template <typename T, typename Fn>
+__device__ __forceinline__ void for_each_real_cell(const T* __restrict__ mats, const csg_region& rg,
+                                                   const int32_t* __restrict__ pool, const int* s_cols, bool cols_in_smem,
+                                                   Fn&& fn) {
+  constexpr int V = 16 / sizeof(T);
+  const int tid = threadIdx.x;
+  const T* base = mats + rg.mat_off;
+  const int ne = rg.ne, nt = rg.nt;
+  auto col_of = [&](int j) { return cols_in_smem ? s_cols[j] : __ldg(pool + rg.cols_off + j); };
+  const bool vec_ok = rg.rows_off < 0 && (rg.ld % V) == 0 && ((reinterpret_cast<uintptr_t>(mats) & 15) == 0);
+  int head = 0, nvec = 0;
+  if (vec_ok) {
+    const int mis = (int)((rg.mat_off + rg.t0) % V);
+    head = (V - mis) % V;
+    if (head > nt) head = nt;
+    nvec = (nt - head) / V;
+  }
+  if (nvec > 0) {
+    const int total = ne * nvec;  // vectors of the region (a region is far below 2^31 cells)
+    const int stride = 2 * kThreads;
+    const int dq = stride / nvec, dr = stride - dq * nvec;
+    int ra = tid / nvec, va = tid - ra * nvec;
+    int rb = (tid + kThreads) / nvec, vb = (tid + kThreads) - rb * nvec;
+    const T* row0 = base + rg.t0 + head;
+    for (int it = tid; it < total; it += stride) {
+      const bool inb = it + kThreads < total;
+      if constexpr (sizeof(T) == 4) {
+        const float4 qa = __ldg(reinterpret_cast<const float4*>(row0 + (long long)col_of(ra) * rg.ld) + va);
+        float4 qb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inb) qb = __ldg(reinterpret_cast<const float4*>(row0 + (long long)col_of(rb) * rg.ld) + vb);
+        fn((T)qa.x), fn((T)qa.y), fn((T)qa.z), fn((T)qa.w);
+        if (inb) fn((T)qb.x), fn((T)qb.y), fn((T)qb.z), fn((T)qb.w);
+      } else {
+        const double2 qa = __ldg(reinterpret_cast<const double2*>(row0 + (long long)col_of(ra) * rg.ld) + va);
+        double2 qb = make_double2(0.0, 0.0);
+        if (inb) qb = __ldg(reinterpret_cast<const double2*>(row0 + (long long)col_of(rb) * rg.ld) + vb);
+        fn((T)qa.x), fn((T)qa.y);
+        if (inb) fn((T)qb.x), fn((T)qb.y);
+      }
+      ra += dq, va += dr;
+      if (va >= nvec) va -= nvec, ++ra;
+      rb += dq, vb += dr;
+      if (vb >= nvec) vb -= nvec, ++rb;
+    }
+  }
+  // scalar cells: the head and tail of every row (vector path), or every cell otherwise
+  const int done = head + nvec * V;  // cells [head, done) of a row went through the vector loop
+  const int per_row = nvec > 0 ? nt - (done - head) : nt;
+  if (per_row > 0) {
+    const long long total = (long long)ne * per_row;
+    for (long long it = tid; it < total; it += kThreads) {
+      const int j = (int)(it / per_row);
+      int k = (int)(it - (long long)j * per_row);
+      if (nvec > 0 && k >= head) k += done - head;  // skip the vectorised middle
+      const int t = rg.rows_off < 0 ? rg.t0 + k : __ldg(pool + rg.rows_off + k);
+      fn(__ldg(base + (long long)col_of(j) * rg.ld + t));
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 6)
     region_stats_kernel(const T* __restrict__ mats, const csg_region* __restrict__ regions,
@@ -208,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 6)
   U* s_keys = s_buf;
   U(*s_cand)[kCand] = reinterpret_cast<U(*)[kCand]>(s_buf);
   __shared__ int s_ncand[2];
+  __shared__ unsigned s_rare[3];  // NaN, +inf, -inf cells
   __shared__ int s_cols[kMaxCols];
   __shared__ unsigned s_u[32];
   __shared__ T s_t[32];
@@ -222,13 +307,14 @@ __global__ void __launch_bounds__(kThreads, 6)
   if (threadIdx.x == 0) todo[blockIdx.x] = 0;
   if (rg.want_pct == 2) return;  // geometry only
   const bool pct = rg.want_pct == 1;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const bool cols_in_smem = rg.ne <= kMaxCols;
   const long long n_cells = (long long)rg.ne * rg.nt;
 
   if (cols_in_smem)
     for (int i = tid; i < rg.ne; i += kThreads) s_cols[i] = __ldg(pool + rg.cols_off + i);
   if (tid < 2) s_ncand[tid] = 0;
+  if (tid < 3) s_rare[tid] = 0;
   __syncthreads();
 
   // ---- brackets
@@ -275,85 +361,83 @@ __global__ void __launch_bounds__(kThreads, 6)
   const U plo0 = s_pivot[0][0], phi0 = s_pivot[0][1], plo1 = s_pivot[1][0], phi1 = s_pivot[1][1];
   const bool share = small;  // both percentiles read list 0
 
-  // ---- the pass
-  unsigned n_valid = 0, n_nan = 0, n_pos = 0, n_pinf = 0, n_ninf = 0;
-  unsigned lt0 = 0, eqlo0 = 0, eqhi0 = 0, lt1 = 0, eqlo1 = 0, eqhi1 = 0;
+  // ---- the pass: everything a cell needs is per-thread work -- no votes, no shuffles.  A finite cell
+  // (nansum leaves nothing else but the rare inf / inf-inf) costs two min/max, the positive count and
+  // minimum, and two compares that tell whether it reaches into a bracket at all; only those cells touch
+  // the bracket counters (float compares against the pivot VALUES: for finite cells they order exactly
+  // like the keys, with -0.0 == +0.0) and the few strictly inside a bracket are appended to its list with
+  // one shared-memory atomic each.  Non-finite cells take the key-based branch.
+  unsigned n_pos = 0;
+  unsigned lt0 = 0, eqlo0 = 0, eqhi0 = 0, eqlo1 = 0, eqhi1 = 0, ge1 = 0;
   const T kInf = (T)CUDART_INF;
   T min_pos = kInf, fin_min = kInf, fin_max = -kInf;
-  auto append = [&](int b, U key, bool want) {  // warp-uniform call
-    const unsigned peers = __ballot_sync(0xffffffffu, want);
-    if (peers == 0u) return;
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&s_ncand[b], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) {
-      const int pos = base + __popc(peers & ((1u << lane) - 1u));
-      if (pos < kCand) s_cand[b][pos] = key;
-    }
+  auto pivot_value = [&](U key, T sentinel) { return (key == KEY_MIN || key == KEY_MAX) ? sentinel : Key<T>::val(key); };
+  const T lo0 = pivot_value(plo0, -kInf), hi0 = pivot_value(phi0, kInf);
+  const T lo1 = pivot_value(plo1, -kInf), hi1 = pivot_value(phi1, kInf);
+  auto append = [&](int b, U key) {
+    const int pos = atomicAdd(&s_ncand[b], 1);
+    if (pos < kCand) s_cand[b][pos] = key;
   };
-  // ge1 counts the cells at or above bracket 1's lower pivot (few), not the ones below it (nearly
-  // all): a cell strictly between the two brackets touches no bracket counter at all
-  unsigned ge1 = 0, n_fast = 0;
-  auto bracket0 = [&](U k, bool valid) {
-    lt0 += (valid && k < plo0) ? 1u : 0u;
-    eqlo0 += (valid && k == plo0) ? 1u : 0u;
-    eqhi0 += (valid && k == phi0 && phi0 != plo0) ? 1u : 0u;
-    append(0, k, valid && k > plo0 && k < phi0);
-  };
-  auto bracket1 = [&](U k, bool valid) {
-    ge1 += (valid && k >= plo1) ? 1u : 0u;
-    eqlo1 += (valid && k == plo1) ? 1u : 0u;
-    eqhi1 += (valid && k == phi1 && phi1 != plo1) ? 1u : 0u;
-    append(1, k, valid && k > plo1 && k < phi1);
-  };
-  for_each_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v, bool in) {
-    if (__all_sync(0xffffffffu, in && is_finite(v))) {
-      // the common warp: 32 real, finite cells (the collapsed sums hold no NaN: nansum replaced them)
-      ++n_fast;
-      const bool pos = v > T(0);
-      n_pos += pos ? 1u : 0u;
-      fin_min = v < fin_min ? v : fin_min;
-      fin_max = v > fin_max ? v : fin_max;
-      const T h = pos ? v : kInf;
-      min_pos = h < min_pos ? h : min_pos;
-      if (pct) {
-        const U k = Key<T>::key(v);
-        if (__any_sync(0xffffffffu, k <= phi0)) bracket0(k, true);
-        if (!share && __any_sync(0xffffffffu, k >= plo1)) bracket1(k, true);
-      }
+  auto by_key = [&](T v) {  // NaN / +-inf: rare, so its counters live in shared memory and the key pivots are re-read
+    if (is_nan(v)) {
+      atomicAdd(&s_rare[0], 1u);
       return;
     }
-    const bool valid = in && !is_nan(v);
-    const bool fin = valid && is_finite(v);
-    const bool pos = v > T(0);
-    n_valid += valid ? 1u : 0u;
-    n_nan += (in && !valid) ? 1u : 0u;
-    n_pos += (fin && pos) ? 1u : 0u;
-    n_pinf += (valid && !fin && pos) ? 1u : 0u;
-    n_ninf += (valid && !fin && !pos) ? 1u : 0u;
-    const T f = fin ? v : kInf;
-    fin_min = f < fin_min ? f : fin_min;
-    const T g = fin ? v : -kInf;
-    fin_max = g > fin_max ? g : fin_max;
-    const T h = (fin && pos) ? v : kInf;
-    min_pos = h < min_pos ? h : min_pos;
-    if (pct) {
-      const U k = Key<T>::key(v);
-      bracket0(k, valid);
-      if (!share) bracket1(k, valid);
+    atomicAdd(&s_rare[v > T(0) ? 1 : 2], 1u);
+    if (!pct) return;
+    const U k = Key<T>::key(v);
+    const U a0 = s_pivot[0][0], b0 = s_pivot[0][1], a1 = s_pivot[1][0], b1 = s_pivot[1][1];
+    lt0 += k < a0 ? 1u : 0u;
+    eqlo0 += k == a0 ? 1u : 0u;
+    eqhi0 += k == b0 ? 1u : 0u;
+    if (k > a0 && k < b0) append(0, k);
+    if (!share) {
+      ge1 += k >= a1 ? 1u : 0u;
+      eqlo1 += k == a1 ? 1u : 0u;
+      eqhi1 += k == b1 ? 1u : 0u;
+      if (k > a1 && k < b1) append(1, k);
     }
-  });
-  n_valid += n_fast;
+  };
+  auto cell = [&](T v, auto pct_c, auto share_c) {
+    if (!is_finite(v)) {
+      by_key(v);
+      return;
+    }
+    fin_min = min_of(fin_min, v);  // v is finite here: the hardware min / max (NaN-agnostic) are exact
+    fin_max = max_of(fin_max, v);
+    count_if_gt(n_pos, v, T(0));
+    min_pos = min_of(min_pos, v > T(0) ? v : kInf);
+    if constexpr (decltype(pct_c)::value) {
+      constexpr bool SHARE = decltype(share_c)::value;
+      if (v <= hi0) {
+        count_if_lt(lt0, v, lo0);
+        count_if_eq(eqlo0, v, lo0);
+        count_if_eq(eqhi0, v, hi0);
+        if (v > lo0 && v < hi0) append(0, Key<T>::key(v));
+      }
+      if constexpr (!SHARE) {
+        if (v >= lo1) {
+          ++ge1;
+          count_if_eq(eqlo1, v, lo1);
+          count_if_eq(eqhi1, v, hi1);
+          if (v > lo1 && v < hi1) append(1, Key<T>::key(v));
+        }
+      }
+    }
+  };
+  if (!pct)
+    for_each_real_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v) { cell(v, Flag<false>{}, Flag<true>{}); });
+  else if (share)
+    for_each_real_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v) { cell(v, Flag<true>{}, Flag<true>{}); });
+  else
+    for_each_real_cell<T>(mats, rg, pool, s_cols, cols_in_smem, [&](T v) { cell(v, Flag<true>{}, Flag<false>{}); });
 
   auto addu = [](unsigned a, unsigned b) { return a + b; };
   auto mint = [](T a, T b) { return a < b ? a : b; };
   auto maxt = [](T a, T b) { return a > b ? a : b; };
-  n_valid = block_reduce(n_valid, addu, 0u, s_u);
-  n_nan = block_reduce(n_nan, addu, 0u, s_u);
-  n_pos = block_reduce(n_pos, addu, 0u, s_u);
-  n_pinf = block_reduce(n_pinf, addu, 0u, s_u);
-  n_ninf = block_reduce(n_ninf, addu, 0u, s_u);
+  n_pos = block_reduce(n_pos, addu, 0u, s_u);  // (its barriers also publish s_rare)
+  const unsigned n_nan = s_rare[0], n_pinf = s_rare[1], n_ninf = s_rare[2];
+  const unsigned n_valid = (unsigned)n_cells - n_nan;
   min_pos = block_reduce(min_pos, mint, kInf, s_t);
   fin_min = block_reduce(fin_min, mint, kInf, s_t);
   fin_max = block_reduce(fin_max, maxt, (T)(-kInf), s_t);
@@ -372,11 +456,15 @@ __global__ void __launch_bounds__(kThreads, 6)
   lt0 = block_reduce(lt0, addu, 0u, s_u);
   eqlo0 = block_reduce(eqlo0, addu, 0u, s_u);
   eqhi0 = block_reduce(eqhi0, addu, 0u, s_u);
+  // a bracket collapsed onto one (tied) value -- equal keys, or -0.0 / +0.0 -- counted it under both names
+  if (plo0 == phi0 || lo0 == hi0) eqhi0 = 0;
+  unsigned lt1 = 0;
   if (!share) {
     ge1 = block_reduce(ge1, addu, 0u, s_u);
     lt1 = n_valid - ge1;
     eqlo1 = block_reduce(eqlo1, addu, 0u, s_u);
     eqhi1 = block_reduce(eqhi1, addu, 0u, s_u);
+    if (plo1 == phi1 || lo1 == hi1) eqhi1 = 0;
   }
   __syncthreads();
   const int n0 = s_ncand[0], n1 = share ? n0 : s_ncand[1];

@@ -218,7 +218,7 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
     chunk_n = _chunk_orbits_default()
     chunks = [list(range(a, min(a + chunk_n, len(mine)))) for a in range(0, len(mine), chunk_n)]
     slot_bytes = int(os.environ.get("CSG_SLOT_BYTES", str(max(1 << 28, chunk_n * 100 * (1 << 20)))))
-    ring = _lib.PinnedRing(ctx, n_slots=3, slot_bytes=slot_bytes) if chunks else None
+    ring = _lib.shared_ring(ctx, n_slots=3, slot_bytes=slot_bytes) if chunks else None
 
     def load_one(slot, index):
         orbit, files = mine[index]
@@ -273,7 +273,7 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             log_exception(f"[INGEST] {ring.overflow_bytes} bytes of cubes did not fit the pinned slots "
                           f"({slot_bytes} bytes each; CSG_SLOT_BYTES / CSG_CHUNK_ORBITS) and were uploaded from pageable memory",
                           level="message")
-        ring.close()
+        ring.drain()  # the ring belongs to the context and serves the next call too
     # ranks that loaded only part of the sequence still index it globally
     if not need_extrema:
         shard.first_orbit_index = 0

@@ -630,7 +630,7 @@ def compute_global_extrema(
             shard = ShardPlan(ctx, y_scale, z_scale, instrument_order=instrument_order)
             shard.first_orbit_index = 0
             chunk_n = max(1, int(os.environ.get("CSG_CHUNK_ORBITS", "8")))
-            ring = _lib.PinnedRing(ctx, n_slots=3, slot_bytes=int(os.environ.get("CSG_SLOT_BYTES", str(max(1 << 28, chunk_n * 100 * (1 << 20))))))
+            ring = _lib.shared_ring(ctx, n_slots=3, slot_bytes=int(os.environ.get("CSG_SLOT_BYTES", str(max(1 << 28, chunk_n * 100 * (1 << 20))))))
 
             def load_one(slot, oi):
                 datasets = {}
@@ -658,7 +658,7 @@ def compute_global_extrema(
                         shard.collapse_pending()
                         ring.release(slot)
             finally:
-                ring.close()
+                ring.drain()
     if shard is None:
         # nothing reaches the scan (everything re-used or complete): only the bookkeeping runs
         totals = {i: sum(1 for _, h in sequence if i in h) for i in instrument_order}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 18
+#define CSG_ABI_VERSION 19
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -406,8 +406,8 @@ CSG_API int csg_pool_reduce_max(csg_ctx* ctx, const double* d_gathered, int n_ra
 /* ------------------------------------------- peer exchange (NVLink / NVSwitch stores) */
 /* The exchange step of the global extrema without library collectives:
  * every rank owns a mailbox in its HBM; an all-gather is one kernel that stores the payload
- * into every peer's mailbox and publishes an epoch flag (release, system scope), plus one
- * kernel that waits for every rank's flag (acquire).  See csrc/peer.cu. */
+ * into every peer's mailbox, publishes an epoch flag (release, system scope) and waits for every
+ * rank's flag (acquire).  See csrc/peer.cu. */
 typedef struct csg_peer csg_peer;
 /* slot_bytes: largest payload of one rank.  ipc_handle_64 (may be NULL): receives the 64-byte
  * cudaIpcMemHandle_t of this rank's mailbox (zeros when the platform has no IPC). */
@@ -420,8 +420,12 @@ CSG_API int csg_peer_connect_ptrs(csg_ctx* ctx, csg_peer* peer, void* const* mai
 /* nbytes: multiple of 16, <= slot_bytes; *d_gathered: n_ranks payloads, nbytes apart, valid until
  * the third following exchange. */
 CSG_API int csg_peer_allgather(csg_ctx* ctx, csg_peer* peer, const void* d_src, size_t nbytes, void** d_gathered);
-/* int32 on the device: 0, or 1 + the rank whose flag did not arrive within ~2 s. */
+/* int32 on the device: 0, or 1 + the rank whose flag did not arrive within the timeout (20 s, or
+ * CSG_PEER_TIMEOUT_S: a rank may arrive seconds late -- first-step planning, lazy module loads). */
 CSG_API void* csg_peer_error_word(csg_peer* peer);
+/* Time the last `last_n` (<= 64) all-gathers spent waiting for the other ranks' epochs, in microseconds:
+ * rank skew + link latency, measured inside the exchange kernel with clock64 (synchronises the stream). */
+CSG_API int csg_peer_wait_stats(csg_ctx* ctx, csg_peer* peer, int last_n, double* mean_us, double* max_us);
 CSG_API int csg_peer_clear_error(csg_ctx* ctx, csg_peer* peer); /* on the ctx stream */
 /* Unmap the other ranks' mailboxes (every rank does this, then a barrier, before any rank destroys its
  * own mailbox: an exporter must not free memory an importer still has open). */

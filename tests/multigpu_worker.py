@@ -64,7 +64,10 @@ def main():
             ctx.sync()
             want = np.concatenate([np.full(nbytes, (17 * r + k) % 251, dtype=np.uint8) for r in range(world)])
             assert np.array_equal(host, want), (rank, slot, nbytes)
-    ex.destroy()
+    stats = ex.wait_stats(8)
+    assert 0.0 <= stats["mean_us"] <= stats["max_us"] < 5e6, stats
+    ex.close()  # collective: every rank unmaps its imports, barrier, then frees its own mailbox
+    assert ex.handle is None
     dist.barrier()
     # the directory driver across ranks (shared working directory prepared by the parent test)
     work = sys.argv[1]
