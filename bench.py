@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--orbits-per-gpu", type=int, default=125)
     ap.add_argument("--total-orbits", type=int, default=0,
                     help="strong scaling: this many orbits in all, split over the GPUs (1000 = BASELINE config 4; fits one B200)")
-    ap.add_argument("--cpu-sample-orbits", type=int, default=8)
+    ap.add_argument("--cpu-sample-orbits", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-png", action="store_true")
@@ -227,7 +227,7 @@ def workload_config(n_local, world):
     }
 
 
-def run_reference_directory(n_orbits, seed, steps, warmup, render="cell"):
+def run_reference_directory(n_orbits, seed, steps, warmup, render="display"):
     """The UNMODIFIED reference (``oracle/_ref``) over a synthetic directory of ``n_orbits`` orbits:
     ``FAST_plot_spectrograms_directory`` with a fork pool on every host core, fresh JSON state and
     output tree per step.  Returns (mean seconds per step, cores, pngs per step, png bytes per step)."""
@@ -270,8 +270,8 @@ def reference_arm(args):
         kind = "reference"
         sample = (f"{n} synthetic FAST orbits (4 instruments, nominal shapes) as .npz side-cars on tmpfs; the unmodified reference's "
                   f"FAST_plot_spectrograms_directory: serial extrema pre-pass + fork ProcessPoolExecutor({cores}), both submissions, "
-                  f"{pngs} PNGs ({png_bytes / 1e6:.1f} MB) per step; cdflib -> .npz stub, matplotlib -> numpy norm+LUT at cell "
-                  "resolution + Pillow PNG (no Agg resampling / text: optimistic for the reference)")
+                  f"{pngs} PNGs ({png_bytes / 1e6:.1f} MB) per step; cdflib -> .npz stub, matplotlib -> numpy norm+LUT, nearest "
+                  "resample to figsize x dpi (4800 x 2400) + Pillow PNG (no text / Agg anti-aliasing: optimistic for the reference)")
         warm = args.warmup
         # the numeric-only port beside it (no file IO, no PNG): what round 1 reported
         psec, _ = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
@@ -568,12 +568,12 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
                 "input_gb": sum(files[fd["index"]]["T"] for ob in orbits[:n] for fd in ob["files"].values()) * P * E * 4 / 1e9,
                 "directory_write_s": round(t_write, 2), "cold": out["cold"], "warm": out["warm"], "extrema_equal_device_arm": same,
                 "what": "FAST_plot_spectrograms_directory(dir, max_processing_percentile=99, turbo) on .npz side-cars in tmpfs -> "
-                        "PNG files (cell-resolution mosaics) on tmpfs; everything inside the clock"}
+                        "PNG files at the reference's 200 dpi (panels resampled, axes / labels / colour bars drawn) on tmpfs; everything inside the clock"}
         if with_reference:
             from oracle import ref_driver as RD
 
             if RD.available():
-                r = RD.run_directory(work, workers=os.cpu_count() or 1, render="cell")
+                r = RD.run_directory(work, workers=os.cpu_count() or 1, render="display")
                 line["reference_same_directory"] = {"seconds": r["seconds"], "orbits_per_s": n / r["seconds"], "pngs": r["pngs"],
                                                     "png_mb": r["png_bytes"] / 1e6, "cores": r["workers"], "kind": "reference"}
         return line
@@ -758,12 +758,17 @@ def main():
         specs = [sp for ob in orbits[:n_fig_orbits] for wx in (False, True)
                  for sp in shard.figures[slice(*step.figure_ranges[(ob["orbit"], wx)])]]
         figs = [f for f in (figure_from_spec(shard, sp, "turbo", norms=norms, device_rasters=True)[0] for sp in specs) if f is not None]
-        PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs)  # warm-up: tables, device and pinned scratch
+        PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, dpi=200)  # warm-up: tables, sprites, device and pinned scratch
         phases: dict = {}
         t0 = time.perf_counter()
-        blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, timings=phases)
+        blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, dpi=200, timings=phases)
         dev_s = time.perf_counter() - t0
-        raw_bytes = sum(4 * H * W + H for H, W, _ in (f.layout() for f in figs))
+
+        def raw_size(f):  # filtered bytes of the figure at 200 dpi
+            W, H = int(round(f.figsize[0] * 200)), int(round(f.figsize[1] * 200))
+            return 4 * H * W + H
+
+        raw_bytes = sum(raw_size(f) for f in figs)
         # the host encoder on the same mosaic (zlib level 6, one thread), a few figures
         sample = figs[:: max(1, len(figs) // 6)][:6]
         host_s, host_bytes = 0.0, 0
@@ -775,8 +780,9 @@ def main():
         png_stage = {"figures": len(figs), "raw_gb": raw_bytes / 1e9, "device_s": dev_s, "device_figures_per_s": len(figs) / dev_s,
                      "device_raw_gb_per_s": raw_bytes / 1e9 / dev_s, "device_ratio": raw_bytes / max(1, sum(len(b) for b in blobs)),
                      "phases_s": phases, "host_zlib6_s_per_figure_1thread": host_s / max(1, len(sample)),
-                     "host_zlib6_ratio": sum(4 * H * W + H for H, W, _ in (f.layout() for f in sample)) / max(1, host_bytes),
-                     "note": "compose + Up filter + fixed-Huffman DEFLATE on the GPU, D2H of the compressed bytes and PNG framing included; not part of `value`"}
+                     "host_zlib6_ratio": sum(raw_size(f) for f in sample) / max(1, host_bytes),
+                     "note": "figures at the reference's 200 dpi (4800 x 2400 for the two-column grids): resample + annotations composed "
+                             "and DEFLATE-encoded on the GPU, D2H of the compressed bytes and PNG framing included; not part of `value`"}
     # the carrier of the extrema exchange and what its all-gathers waited for (rank skew + link latency)
     exchange, exchange_info = None, {"exchange": "none (1 rank)"}
     if world > 1:
@@ -896,7 +902,7 @@ def main():
             sec, cores, pngs, png_bytes = run_reference_directory(n, args.seed, 1, 0)
             cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "reference", "sample_orbits": n,
                    "sample": f"{n} synthetic FAST orbits of the same workload through the unmodified reference's FAST_plot_spectrograms_directory "
-                             f"(oracle/_ref under the cdflib/matplotlib stand-ins, fork pool on {cores} cores, {pngs} cell-resolution PNGs), {sec:.1f} s wall"}
+                             f"(oracle/_ref under the cdflib/matplotlib stand-ins, fork pool on {cores} cores, {pngs} PNGs at figsize x dpi without text), {sec:.1f} s wall"}
         else:
             sec, cores = run_cpu_port(cpu_sample_orbits(n, args.seed), 1, 0)
             cpu = {"value": n / sec, "unit": "orbits/s", "cores": cores, "kind": "port", "sample_orbits": n,

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
 LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -117,20 +117,21 @@ FLAG_WINDOW = np.dtype(
 )
 assert FLAG_WINDOW.itemsize == 24
 PNG_TILE = np.dtype(
-    [("rgba_off", "<i8"), ("ne", "<i4"), ("nt", "<i4"), ("x", "<i4"), ("y", "<i4"), ("rep", "<i4"),
-     ("vline_first", "<i4"), ("vline_count", "<i4"), ("pad", "<i4")], align=True
+    [("rgba_off", "<i8"), ("ne", "<i4"), ("nt", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"),
+     ("vline_first", "<i4"), ("vline_count", "<i4"), ("flags", "<i4"), ("pad", "<i4")], align=True
 )
+TILE_OVERLAY, TILE_TOP_ORIGIN = 1, 2
 PNG_VLINE = np.dtype([("col", "<i4"), ("half", "<i4"), ("rgba", "<u4"), ("pad", "<i4")], align=True)
 PNG_CANVAS = np.dtype(
     [("W", "<i4"), ("H", "<i4"), ("tile_first", "<i4"), ("tile_count", "<i4"), ("background", "<u4"),
-     ("seg_first", "<i4"), ("segs_per_row", "<i4"), ("pad", "<i4")], align=True
+     ("seg_first", "<i4"), ("segs_per_row", "<i4"), ("row_first", "<i4")], align=True
 )
 PNG_TABLES = np.dtype(
     [("lit_code", "<u2", (256,)), ("lit_len", "u1", (256,)), ("len_code", "<u4", (65,)), ("dist_code", "<u4", (129,)),
      ("len_sym", "<u2", (65,)), ("len_len", "u1", (65,)), ("dist_len", "u1", (129,)), ("dist_sym", "u1", (129,)),
      ("eob_len", "u1"), ("eob_code", "<u2"), ("header_bits", "<i4"), ("header", "<u4", (40,))], align=True
 )
-assert PNG_TILE.itemsize == 40 and PNG_VLINE.itemsize == 16 and PNG_CANVAS.itemsize == 32
+assert PNG_TILE.itemsize == 48 and PNG_VLINE.itemsize == 16 and PNG_CANVAS.itemsize == 32
 POOL_REQUEST = np.dtype([("inst", "<i4"), ("mode", "<i4"), ("p", "<f8")], align=True)
 POOL_SEL = np.dtype(
     [("inst", "<i4"), ("pos", "<i4"), ("req", "<i4"), ("active", "<i4"), ("slot", "<i4", (2,)), ("rank", "<i8", (2,)),
@@ -198,10 +199,11 @@ SIGNATURES = {
     "csg_pool_reduce_max": (_i, [_vp, _vp, _i, _i, _vp]),
     "csg_png_fixed_tables": (_i, [_vp]),
     "csg_png_set_tables": (_i, [_vp, _vp]),
-    "csg_png_count": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "csg_png_count": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "csg_png_max_segment_tiles": (C.c_int32, []),
     "csg_png_slot_bytes": (C.c_int32, []),
     "csg_png_segments": (C.c_int32, [C.c_int32, C.c_int32]),
-    "csg_png_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "csg_png_encode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "csg_png_compact": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "csg_peer_create": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
     "csg_peer_mailbox": (_vp, [_vp]),

@@ -3,17 +3,22 @@
 // The reference's product is one PNG per figure (CS/fast/process_orbit.py:98-117 ->
 // fig.savefig, CS/generic_batch.py:108-113); there nearly all wall time goes into Agg and zlib.
 // Here the colour-mapped panels (K3) already sit in HBM, so a figure never exists as raw pixels
-// anywhere: one kernel evaluates the mosaic (panels flipped to origin="lower", energy rows
-// repeated to the row height, cusp lines burnt in, background in the gaps -- the arithmetic of
-// figure.SpectrogramFigure.compose) for the scanline it encodes and for the one above it, applies
-// PNG filter 2 ("Up"), and writes finished DEFLATE blocks:
+// anywhere: one kernel evaluates the mosaic for the scanline it encodes -- every tile is a source
+// raster (a K3 panel in d_rgba, flipped to origin="lower"; or a host-drawn annotation sprite in the
+// overlay atlas) resampled nearest-neighbour into its rectangle on the canvas, the way
+// imshow(aspect="auto") fills an axes box at display resolution (CS/plotting.py:280-287,606-611:
+// 4800 x 2400 pixels for the FAST grids); cusp lines burnt in; background in the gaps -- the
+// arithmetic of figure.SpectrogramFigure.compose -- and writes finished DEFLATE blocks:
 //
-//   segment   = up to 1024 pixels of one scanline = one warp = one fixed-Huffman block that ends
+//   segment   = up to 1024 pixels of one scanline = one warp = one Huffman block that ends
 //               with an empty stored block (the zlib "sync flush": byte aligned, so segments
 //               concatenate bytewise into a valid stream in any quantity)
-//   filter    = per scanline, from the geometry alone: a line that repeats the one above (energy rows
-//               are drawn `rep` times; gaps) takes filter 2 (Up) and becomes zeros, a line with new
-//               content takes filter 0 and keeps its pixels -- at most 259 distinct LUT colours
+//   rows      = only scanlines with NEW content are encoded: the host lists them per canvas from the
+//               geometry alone (a resampled panel repeats every raster row several times; gaps
+//               repeat the background).  They take filter 2 ("Up") like every other line: what a
+//               listed line shares with the one above -- often all but one sprite or one step of a
+//               colour bar -- turns into zeros.  Runs of repeated lines are Up lines of nothing but
+//               zeros, a constant the host splices in between the segments (png.py)
 //   tokens    = per pixel: equal to its left neighbour -> it extends a distance-4 match; else equal
 //               to one of the 128 pixels before it -> a match at that distance (extended while the
 //               following pixels keep matching); else four literals.
@@ -49,22 +54,41 @@ __constant__ HuffTables c_huff;
 
 __device__ __forceinline__ unsigned sub4(unsigned a, unsigned b) { return __vsub4(a, b); }
 
-// One pixel of a figure's mosaic: the tiles whose rows contain y are listed in `mask`.
-__device__ __forceinline__ unsigned mosaic_pixel(const uint32_t* __restrict__ rgba, const csg_png_tile* __restrict__ tiles,
-                                                 const csg_png_vline* __restrict__ vlines, unsigned mask, int x, int y,
-                                                 unsigned background) {
-  while (mask) {
-    const int t = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const csg_png_tile& tl = tiles[t];
-    const int col = x - tl.x;
-    if (col < 0 || col >= tl.nt) continue;
-    const int r = (y - tl.y) / tl.rep;       // image row from the top
-    const int src = tl.ne - 1 - r;           // rasters are stored lowest energy first (origin="lower")
-    unsigned px = __ldg(rgba + tl.rgba_off + (long long)src * tl.nt + col);
-    for (int v = 0; v < tl.vline_count; ++v) {  // later lines overwrite earlier ones
-      const csg_png_vline ln = vlines[tl.vline_first + v];
-      if (col >= ln.col - ln.half && col <= ln.col + ln.half) px = ln.rgba;
+// A tile as one segment sees it: the columns it covers on this scanline and the source row they read.
+struct SegTile {
+  const uint32_t* row;          // first pixel of the source row this scanline shows
+  float xs;                     // source columns per canvas pixel
+  int vline_first;
+  unsigned short x0, x1;        // canvas columns [x0, x1) inside the segment's range (canvases are < 65536 wide)
+  unsigned short tx;            // the tile's left edge on the canvas
+  unsigned short nt_minus_1;    // last source column (the nearest-neighbour index is clamped to it)
+  unsigned short vline_count, pad;
+};                              // 32 bytes
+constexpr int kSegTiles = 48;   // tiles one 1024-pixel segment may intersect on one scanline (the device flags more)
+// dynamic shared memory of png_encode_kernel: symbol counts | pixels / merged stream | lane token buffers | tile lists
+constexpr size_t kOffPix = (size_t)kWarpsPerBlock * (286 + 30) * sizeof(unsigned);
+constexpr size_t kOffTok = kOffPix + (size_t)kWarpsPerBlock * kMergedWords * sizeof(unsigned);
+constexpr size_t kOffSeg = (kOffTok + (size_t)kWarpsPerBlock * kPieces * kTokWords * sizeof(unsigned) + 15) / 16 * 16;
+constexpr size_t kEncodeSmem = kOffSeg + (size_t)kWarpsPerBlock * 2 * kSegTiles * 32;
+
+// source index of destination pixel d (0-based) of `n_dst`, nearest neighbour, pixel centres:
+// floor((d + 0.5) * n_src / n_dst) in float32 -- figure.py evaluates the same float32 expression
+__device__ __forceinline__ int nearest(int d, float scale, int last) {
+  const int k = (int)(__fmul_rn(__fadd_rn((float)d, 0.5f), scale));
+  return k > last ? last : k;
+}
+
+// One pixel of a figure's mosaic: the first listed tile that covers column x, else the background.
+__device__ __forceinline__ unsigned mosaic_pixel(const SegTile* __restrict__ list, int n_list,
+                                                 const csg_png_vline* __restrict__ vlines, int x, unsigned background) {
+  for (int k = 0; k < n_list; ++k) {
+    const SegTile& t = list[k];
+    if (x < (int)t.x0 || x >= (int)t.x1) continue;
+    const int dx = x - (int)t.tx;
+    unsigned px = __ldg(t.row + nearest(dx, t.xs, t.nt_minus_1));
+    for (int v = 0; v < (int)t.vline_count; ++v) {  // later lines overwrite earlier ones
+      const csg_png_vline ln = vlines[t.vline_first + v];
+      if (dx >= ln.col - ln.half && dx <= ln.col + ln.half) px = ln.rgba;
     }
     return px;
   }
@@ -72,19 +96,23 @@ __device__ __forceinline__ unsigned mosaic_pixel(const uint32_t* __restrict__ rg
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    png_encode_kernel(const uint32_t* __restrict__ rgba, const csg_png_canvas* __restrict__ canvases, int n_canvases,
-                      const csg_png_tile* __restrict__ tiles, const csg_png_vline* __restrict__ vlines, int n_segments,
+    png_encode_kernel(const uint32_t* __restrict__ rgba, const uint32_t* __restrict__ overlay,
+                      const csg_png_canvas* __restrict__ canvases, int n_canvases, const csg_png_tile* __restrict__ tiles,
+                      const csg_png_vline* __restrict__ vlines, const int32_t* __restrict__ rows, int n_segments,
                       unsigned char* __restrict__ slots, int slot_bytes, int32_t* __restrict__ sizes,
-                      uint32_t* __restrict__ adler, unsigned* __restrict__ counts, int count_stride) {
+                      uint32_t* __restrict__ adler, unsigned* __restrict__ counts, int count_stride, int* __restrict__ error) {
   // counts != NULL: no output, only the symbol statistics of every count_stride-th segment
   // (literal / length symbols 0..285, then distance symbols 0..29) for the host's custom code
-  __shared__ unsigned s_counts[kWarpsPerBlock][286 + 30];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned(*s_counts)[286 + 30] = reinterpret_cast<unsigned(*)[286 + 30]>(s_dyn);
+  unsigned(*s_pix)[kMergedWords] = reinterpret_cast<unsigned(*)[kMergedWords]>(s_dyn + kOffPix);
+  unsigned(*s_tok)[kPieces * kTokWords] = reinterpret_cast<unsigned(*)[kPieces * kTokWords]>(s_dyn + kOffTok);
+  SegTile(*s_seg)[2 * kSegTiles] = reinterpret_cast<SegTile(*)[2 * kSegTiles]>(s_dyn + kOffSeg);
   if (counts) {
     for (int i = threadIdx.x; i < kWarpsPerBlock * (286 + 30); i += blockDim.x) (&s_counts[0][0])[i] = 0;
     __syncthreads();
   }
-  __shared__ unsigned s_pix[kWarpsPerBlock][kMergedWords];  // filtered pixels (padded pieces), then the merged stream
-  __shared__ unsigned s_tok[kWarpsPerBlock][kPieces * kTokWords];
+  // s_pix: filtered pixels (padded pieces), then the merged stream; s_seg: the tile lists of this scanline and the one above
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seg = (blockIdx.x * kWarpsPerBlock + warp) * (counts ? count_stride : 1);
   const bool active = seg < n_segments;
@@ -101,37 +129,62 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   }
   const csg_png_canvas cv = canvases[lo];
   const int local = seg - cv.seg_first;
-  const int row = local / cv.segs_per_row, chunk = local - row * cv.segs_per_row;
+  const int k_row = local / cv.segs_per_row, chunk = local - k_row * cv.segs_per_row;
+  const int row = __ldg(rows + cv.row_first + k_row);  // the k-th scanline of this canvas that has new content
   const int x0 = chunk * kSegPixels;
   const int npx = min(kSegPixels, cv.W - x0);
   const bool has_filter = chunk == 0;
   const int n_raw = (has_filter ? 1 : 0) + 4 * npx;  // filtered bytes this segment feeds to DEFLATE
-  const csg_png_tile* tl = tiles + cv.tile_first;
-  // tiles crossing this scanline / the one above (at most 32 tiles per figure)
-  bool in_cur = false, in_up = false;
-  if (lane < cv.tile_count) {
-    const csg_png_tile t = tl[lane];
-    const int h = t.ne * t.rep;
-    in_cur = row >= t.y && row < t.y + h;
-    in_up = row - 1 >= t.y && row - 1 < t.y + h;
+  // Up filter on every listed scanline but the first of the canvas: what a listed line shares with the line
+  // above (it may differ from it in one text sprite or one step of a colour bar only) becomes zeros
+  const unsigned filter_type = row > 0 ? 2u : 0u;
+  // ---- the tiles crossing this scanline (and the one above) inside [x0, x0 + npx), in table order (first match wins)
+  SegTile* list = s_seg[warp];
+  SegTile* list_up = s_seg[warp] + kSegTiles;
+  int n_list = 0, n_up = 0;
+  for (int which = 0; which < (row > 0 ? 2 : 1); ++which) {
+    const int r = row - which;
+    SegTile* dst = which ? list_up : list;
+    int n = 0;
+    for (int base = 0; base < cv.tile_count; base += 32) {
+      const int ti = base + lane;
+      bool hit = false;
+      csg_png_tile t;
+      if (ti < cv.tile_count) {
+        t = tiles[cv.tile_first + ti];
+        hit = t.w > 0 && t.h > 0 && r >= t.y && r < t.y + t.h && t.x < x0 + npx && t.x + t.w > x0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int at = n + __popc(m & ((1u << lane) - 1u));
+        if (at < kSegTiles) {
+          const int r_top = nearest(r - t.y, __fdiv_rn((float)t.ne, (float)t.h), t.ne - 1);  // source row, counted from the top
+          const int src_row = (t.flags & 2) ? r_top : t.ne - 1 - r_top;  // rasters store the lowest energy first
+          SegTile e;
+          e.x0 = (unsigned short)max(t.x, x0), e.x1 = (unsigned short)min(t.x + t.w, x0 + npx);
+          e.tx = (unsigned short)t.x, e.nt_minus_1 = (unsigned short)(t.nt - 1);
+          e.xs = __fdiv_rn((float)t.nt, (float)t.w);
+          e.vline_first = t.vline_first, e.vline_count = (unsigned short)t.vline_count, e.pad = 0;
+          e.row = ((t.flags & 1) ? overlay : rgba) + t.rgba_off + (long long)src_row * t.nt;
+          dst[at] = e;
+        }
+      }
+      n += __popc(m);
+    }
+    if (n > kSegTiles) {
+      if (lane == 0 && error) atomicExch(error, 1 + lo);  // the host raises: too many tiles meet in one segment
+      n = kSegTiles;
+    }
+    if (which) n_up = n; else n_list = n;
   }
-  const unsigned mask_cur = __ballot_sync(0xffffffffu, in_cur), mask_up = __ballot_sync(0xffffffffu, in_up);
-  // does this scanline repeat the one above?  (same tiles, same raster row of each: a function of the
-  // tile table and the row only, so every segment of the line decides alike)
-  bool differs = false;
-  if (lane < cv.tile_count) {
-    const csg_png_tile t = tl[lane];
-    differs = in_cur != in_up || (in_cur && (row - t.y) / t.rep != (row - 1 - t.y) / t.rep);
-  }
-  const bool repeat = row > 0 && !__any_sync(0xffffffffu, differs);
-  const unsigned filter_type = repeat ? 2u : 0u;
+  __syncwarp();
 
   // ---- phase 1: compose + Up filter (coalesced), Adler partial sums
   unsigned* pix = s_pix[warp];
   unsigned long long sa = 0, sb = 0;
   for (int p = lane; p < npx; p += 32) {
-    // a repeated line is all zeros after the Up filter (identical content by construction)
-    const unsigned f = repeat ? 0u : mosaic_pixel(rgba, tl, vlines, mask_cur, x0 + p, row, cv.background);
+    const unsigned cur = mosaic_pixel(list, n_list, vlines, x0 + p, cv.background);
+    const unsigned f = filter_type ? sub4(cur, mosaic_pixel(list_up, n_up, vlines, x0 + p, cv.background)) : cur;
     pix[(p >> 5) * kPixStride + (p & 31)] = f;
     const unsigned b0 = f & 255u, b1 = (f >> 8) & 255u, b2 = (f >> 16) & 255u, b3 = f >> 24;
     const unsigned t0 = (has_filter ? 1u : 0u) + 4u * (unsigned)p;  // position of b0 inside the segment
@@ -357,10 +410,12 @@ int32_t csg_png_slot_bytes(void) {
   return (int32_t)(((kHeaderWords * 32 + 9 + kSegPixels * 36 + 15 + 3 + 7) / 8 + 4 + 15) / 16 * 16);
 }
 
-int32_t csg_png_segments(int32_t W, int32_t H) {
-  if (W <= 0 || H <= 0) return 0;
-  return (int32_t)(((long long)(W + kSegPixels - 1) / kSegPixels) * H);
+int32_t csg_png_segments(int32_t W, int32_t n_rows) {
+  if (W <= 0 || n_rows <= 0) return 0;
+  return (int32_t)(((long long)(W + kSegPixels - 1) / kSegPixels) * n_rows);
 }
+
+int32_t csg_png_max_segment_tiles(void) { return kSegTiles; }
 
 int csg_png_fixed_tables(csg_png_tables* out) {
   if (!out) return CSG_ERR_ARG;
@@ -386,38 +441,47 @@ int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables) {
   return CSG_OK;
 }
 
-static int png_launch(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
-                      const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, uint8_t* d_slots,
-                      int32_t* d_sizes, uint32_t* d_adler, uint32_t* d_counts, int count_stride) {
+static int png_launch(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
+                      int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
+                      int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, uint32_t* d_counts,
+                      int count_stride, int32_t* d_error) {
   if (!ctx_tables_ready(ctx)) {
     const int st = csg_png_set_tables(ctx, nullptr);
     if (st != CSG_OK) return st;
   }
   const int work = d_counts ? (n_segments + count_stride - 1) / count_stride : n_segments;
   const int blocks = (work + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  png_encode_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_canvases, n_canvases, d_tiles,
-                                                                     d_vlines, n_segments, d_slots, csg_png_slot_bytes(),
-                                                                     d_sizes, d_adler, d_counts, count_stride);
+  static bool configured_dev[64] = {false};
+  if (!configured_dev[ctx->device & 63]) {
+    CSG_CUDA(ctx, cudaFuncSetAttribute(png_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncodeSmem));
+    configured_dev[ctx->device & 63] = true;
+  }
+  png_encode_kernel<<<blocks, kWarpsPerBlock * 32, kEncodeSmem, ctx->stream>>>(
+      (const uint32_t*)d_rgba, (const uint32_t*)d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, d_slots,
+      csg_png_slot_bytes(), d_sizes, d_adler, d_counts, count_stride, d_error);
   CSG_LAUNCH_CHECK(ctx, "png_encode_kernel");
   return CSG_OK;
 }
 
-int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
-                   const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, uint8_t* d_slots,
-                   int32_t* d_sizes, uint32_t* d_adler) {
+int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
+                   int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
+                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
-  if (!d_rgba || !d_canvases || !d_tiles || !d_slots || !d_sizes || !d_adler) return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
-  return png_launch(ctx, d_rgba, d_canvases, n_canvases, d_tiles, d_vlines, n_segments, d_slots, d_sizes, d_adler, nullptr, 1);
+  if (!d_rgba || !d_canvases || !d_tiles || !d_rows || !d_slots || !d_sizes || !d_adler)
+    return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
+  return png_launch(ctx, d_rgba, d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, d_slots, d_sizes,
+                    d_adler, nullptr, 1, d_error);
 }
 
-int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
-                  const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, int stride,
-                  uint32_t* d_counts) {
+int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
+                  int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
+                  int n_segments, int stride, uint32_t* d_counts) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
-  if (!d_rgba || !d_canvases || !d_tiles || !d_counts || stride < 1) return csg_fail(ctx, CSG_ERR_ARG, "bad argument");
-  return png_launch(ctx, d_rgba, d_canvases, n_canvases, d_tiles, d_vlines, n_segments, nullptr, nullptr, nullptr, d_counts, stride);
+  if (!d_rgba || !d_canvases || !d_tiles || !d_rows || !d_counts || stride < 1) return csg_fail(ctx, CSG_ERR_ARG, "bad argument");
+  return png_launch(ctx, d_rgba, d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, nullptr, nullptr,
+                    nullptr, d_counts, stride, nullptr);
 }
 
 int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets, int n_segments,

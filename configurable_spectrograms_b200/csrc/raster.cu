@@ -531,6 +531,19 @@ __global__ void __launch_bounds__(kRasterThreads, sizeof(T) == 4 ? 3 : 2)
           for (unsigned u = 0; u < G; ++u) cur[u] = nxt[u];
         }
       } else {
+        // two groups per trip: both loads are in flight before either group is classified (the kernel is
+        // bound by the latency of these loads, not by issue slots: ncu long-scoreboard stall 10-12 per issue)
+        while (i + STEP + (G - 1) < last) {
+          T a[G], b[G];
+          const unsigned ia = i;
+          load4(j, tt, a);
+          advance();
+          const unsigned ib = i;
+          load4(j, tt, b);
+          advance();
+          classify_store(ia, a);
+          classify_store(ib, b);
+        }
         while (i + (G - 1) < last) {
           T cur[G];
           load4(j, tt, cur);

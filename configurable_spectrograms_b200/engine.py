@@ -498,6 +498,14 @@ class Batch:
             return np.arange(r[2], r[2] + r[3])
         return self._pool_array()[r[4] : r[4] + r[3]]
 
+    def region_time_ends(self, region: int) -> tuple[int, int]:
+        """Time steps of the first and last image column of a region."""
+        r = self._regions[region]
+        if r[4] < 0:
+            return r[2], r[2] + r[3] - 1
+        pool = self._pool_array()
+        return int(pool[r[4]]), int(pool[r[4] + r[3] - 1])
+
     def add_panel(self, region: int, pct_region: int = -1, log_scale: bool = False, z_min=None, z_max=None,
                   stat_region: int = -1) -> int:
         r = self._regions[region]

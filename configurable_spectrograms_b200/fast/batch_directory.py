@@ -37,7 +37,7 @@ from .extrema import compute_global_extrema
 from .orbit_discovery import _add_to_orbit_list, _classify_error_reason, _parse_year_month, discover_orbit_files
 from .pipeline import BatchStep, ShardPlan
 from .plotting import figure_from_spec
-from .process_orbit import figure_filename
+from .process_orbit import SAVE_DPI, figure_filename
 
 _INSTRUMENT_KEYS = DEFAULT_INSTRUMENT_ORDER
 
@@ -385,7 +385,7 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             saves = list(by_path.items())
             t_phase = tick("figures_host", t_phase)
             if saves:
-                write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads)
+                write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads, dpi=SAVE_DPI)
                 for path, fig in saves:
                     log_exception(f"[SAVED] {path}", level="message")
                     close_all_axes_and_clear(fig)

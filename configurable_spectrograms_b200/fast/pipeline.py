@@ -102,6 +102,7 @@ class ShardPlan:
         self._full_stats: dict = {}  # (file, group) -> percentile region over the [0,4000] eV cells, every row
         self._flags_host = None
         self._window_cache: dict = {}
+        self._full_region_of: dict = {}  # region id -> (file, group) for full panels over every time row
 
     @property
     def batch(self) -> Batch:
@@ -278,6 +279,8 @@ class ShardPlan:
             if n_rows:
                 shared = self._full_stats.get((file, group), -1) if isinstance(rows, tuple) else -1
                 reg = self._region(file, group, cols, rk, rows, 2 if shared >= 0 else 0)
+                if isinstance(rows, tuple):
+                    self._full_region_of[reg] = (file, group)
                 row.full_panel = self._panel(reg, pct, z_lo, z_hi, shared)
             if zoom is not None:
                 rk, rows = self._rows_zoom(file, zoom)
@@ -347,11 +350,37 @@ class ShardPlan:
         self.batch.reset_tables()
         self.figures = []
         self._panel_cache, self._region_cache, self._full_stats, self._window_cache = {}, {}, {}, {}
+        self._full_region_of = {}
         if hasattr(self, "_zoom_index"):
             del self._zoom_index
 
     # ------------------------------------------------------------------ execution
+    def share_full_stats(self):
+        """One pass per cell set: a full panel planned BEFORE the percentile region of the same cells existed
+        (the "given" figures come first, ``fast/process_orbit.py:148-190``) asked for its own reductions; the
+        percentile region over the [0, 4000] eV rows of the same (file, group) computes exactly those
+        (safe_vmin, nanmin / nanmax are order-free), so such panels are pointed at it and regions nobody
+        reads any more become geometry only -- K2a touches every cell set once instead of twice."""
+        b = self.batch
+        own = set()
+        for pid, p in enumerate(b._panels):
+            region, stat_region = p[0], p[7]
+            if stat_region < 0:
+                shared = self._full_stats.get(self._full_region_of.get(region))
+                if shared is not None and shared != region:
+                    q = list(p)
+                    q[7] = shared
+                    b._panels[pid] = tuple(q)
+                    continue
+                own.add(region)
+        for rid, r in enumerate(b._regions):
+            if r[7] == 0 and rid not in own and rid in self._full_region_of:
+                q = list(r)
+                q[7] = 2
+                b._regions[rid] = tuple(q)
+
     def upload_tables(self):
+        self.share_full_stats()
         self.batch.upload_tables()
 
     def run_panels(self, lut259=None, want_index=True):

@@ -75,10 +75,14 @@ def figure_from_spec(shard: ShardPlan, spec: FigureSpec, colormap="viridis", cus
             nm = norms[pid]
             check_norm_status(nm, f"orbit {spec.orbit} {spec.kind} {row.label}")
             rgba, index = raster(pid)
+            # the axes only need the ends of the panel's time and energy ranges (extent, limits, markers)
             region = b._panels[pid][0]
-            t_sel = row.times[b.region_time_index(region)]
-            y_kept = row.energy[b.region_energy_index(region)]
-            x_plot = date2num(t_sel)
+            t_first, t_last = b.region_time_ends(region)
+            e_index = b.region_energy_index(region)
+            y_kept = row.energy[e_index[[0, -1]]] if len(e_index) > 2 else row.energy[e_index]
+            if len(e_index) > 2:
+                y_kept = _Ends(y_kept, len(e_index))
+            x_plot = date2num(row.times[[t_first, t_last]])
             ax = axes[i, j]
             if j == 1:
                 centre, duration = spec.zoom
@@ -91,6 +95,26 @@ def figure_from_spec(shard: ShardPlan, spec: FigureSpec, colormap="viridis", cus
     datasets = [{"x": r.times, "label": r.label} for r in spec.rows]
     _finish_multirow(fig, axes, datasets, spec.vertical_lines, spec.title)
     return fig, canvas
+
+
+class _Ends:
+    """First and last value of a long axis array that report the original length (``draw_panel`` looks at
+    ``[0]``, ``[-1]`` and ``len``): a batch of thousands of figures does not slice every axis in full."""
+
+    __slots__ = ("first", "last", "n")
+
+    def __init__(self, pair, n):
+        self.first, self.last, self.n = pair[0], pair[-1], n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, k):
+        if k == 0:
+            return self.first
+        if k == -1:
+            return self.last
+        raise IndexError("only the ends of the axis are kept")
 
 
 def _run_single(shard: ShardPlan, spec: FigureSpec, colormap, cusp_marker_style, cusp_marker_kwargs):

@@ -25,9 +25,13 @@ from .constants import DEFAULT_INSTRUMENT_ORDER
 from .extrema import _extrema_overrides
 from .orbit_discovery import _parse_year_month
 from .pipeline import FigureSpec, ShardPlan
+from ..png import write_figures_device
 from .plotting import figure_from_spec
 
-__all__ = ["FAST_process_single_orbit", "figure_filename", "plan_orbit_figures"]
+__all__ = ["FAST_process_single_orbit", "figure_filename", "plan_orbit_figures", "SAVE_DPI"]
+
+#: ``fig.savefig(out_path, dpi=200)`` (reference ``:110``): a 24 x 12 in grid becomes 4800 x 2400 pixels
+SAVE_DPI = 200
 
 
 def figure_filename(spec: FigureSpec, y_scale: str, z_scale: str, colormap: str) -> str:
@@ -82,7 +86,8 @@ def FAST_process_single_orbit(
     orbit_start = _time.time()
     timeout_type = timeout_instrument = None
 
-    def save(fig, out_path, desc):
+    def save(fig, out_path, desc, ctx, d_rgba_ptr):
+        """The panels are still in HBM: the figure is composed at ``SAVE_DPI`` and DEFLATE-encoded on the device."""
         if not override_plots and os.path.exists(out_path):
             log_exception(f"[SKIP] Plot already exists, skipping: {out_path}", level="message")
             close_all_axes_and_clear(fig)
@@ -90,7 +95,7 @@ def FAST_process_single_orbit(
         try:
             log_exception(f"[DEBUG] Saving {desc} plot: y_axis_scale={y_axis_scale}, z_axis_scale={z_axis_scale}, "
                           f"filename={out_path}", level="message")
-            fig.savefig(out_path, dpi=200)
+            write_figures_device(ctx, d_rgba_ptr, [(out_path, fig)], max_workers=1, dpi=SAVE_DPI)
             log_exception(f"[SAVED] {out_path}", level="message")
         except Exception as exc:
             log_exception(f"[FAIL] Saving figure {out_path}", exc, level="error")
@@ -139,7 +144,6 @@ def FAST_process_single_orbit(
             if b._windows:
                 shard.resolve_zoom_flags(b.d_window_any.download(np.uint8, len(b._windows)))
             norms = b.norms()
-            rgba_flat = b.all_rgba() if b.n_pixels else None
             group_start, group_key = _time.time(), None
             for spec in specs:
                 key = spec.instrument if spec.kind == "pitch-angle" else "instrument_grid"
@@ -148,11 +152,12 @@ def FAST_process_single_orbit(
                 what = (f"pitch angle grid for {spec.instrument}" if spec.kind == "pitch-angle" else "instrument grid")
                 try:
                     fig, _canvas = figure_from_spec(shard, spec, colormap, cusp_marker_style, cusp_marker_kwargs, norms=norms,
-                                                    rgba_flat=rgba_flat)
+                                                    device_rasters=True)
                     if fig is not None:
                         desc = (f"pitch-angle {spec.instrument}" if spec.kind == "pitch-angle" else "instrument-grid")
                         desc += " (given extrema)" if spec.variant == "given" else " (raw extrema)"
-                        save(fig, os.path.join(output_dir, figure_filename(spec, y_axis_scale, z_axis_scale, colormap)), desc)
+                        save(fig, os.path.join(output_dir, figure_filename(spec, y_axis_scale, z_axis_scale, colormap)), desc,
+                             b.ctx, b.d_rgba.ptr)
                 except Exception as exc:
                     err = f"[FAIL] Plotting Orbit {orbit_number} {what}"
                     log_exception(err, exc, level="error")

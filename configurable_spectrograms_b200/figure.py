@@ -1,22 +1,35 @@
-"""Raster figures: the host-side stand-in for the matplotlib objects the reference draws into.
+"""Figures at display resolution: the stand-in for the matplotlib objects the reference draws into.
 
-The reference hands every panel to ``Axes.imshow`` and lets Agg resample, colour-map and
-composite it (``plotting.py:280-287,316-324``).  On this path the GPU has already produced
-the colour-mapped cells (K3), so a figure here is a grid of finished RGBA rasters plus the
-annotations the host still owns (titles, labels, ticks, cusp markers), recorded through the
-same small slice of the Axes / Figure API the reference touches.  ``savefig`` composes the
-panels at cell resolution into one PNG (``png.py``); resampling to the reference's display
-resolution is the next item on the scope list.
+The reference hands every panel to ``Axes.imshow(aspect="auto")`` and lets Agg resample it into the axes
+box, draw ticks, labels, colour bars and markers, and composite the figure at ``figsize x dpi`` pixels
+(``plotting.py:280-387,606-611``; 24 x 12 in at 200 dpi = 4800 x 2400 for the FAST grids,
+``fast/process_orbit.py:110``).  Here a figure is a list of *tiles* (``csg_png_tile``): every panel is a
+finished RGBA raster (K3) stretched nearest-neighbour over its image rectangle, every annotation a sprite
+of ``overlay.ATLAS`` -- rendered text at its own size, or one pixel / one colour ramp stretched into a
+line, a frame edge, a colour bar.  The same tile list is
 
-The classes are duck-typed like their matplotlib namesakes so the mirrored functions
-(``plotting.make_spectrogram`` ...) and ``cusp_marking`` read like the reference's.
+* evaluated by :meth:`SpectrogramFigure.compose` in numpy (the oracle, and ``savefig`` for figures whose
+  rasters are host arrays), and
+* composed + DEFLATE-encoded on the device by ``png.encode_figures_device`` (``csrc/png.cu``) for figures
+  whose panels stay in HBM (:class:`DeviceRaster`) -- pixel for pixel the same image.
+
+The layout is this package's own (margins from the rendered label sizes, one colour bar per panel at a
+twentieth of the box height, ticks on "nice" times of day); it follows the reference's figure sizes, fonts
+and content, not matplotlib's ``tight_layout`` arithmetic.  The classes are duck-typed like their
+matplotlib namesakes so the mirrored functions (``plotting.make_spectrogram`` ...) and ``cusp_marking``
+read like the reference's.
 """
 
 from __future__ import annotations
 
+import math
+from datetime import datetime, timedelta, timezone
+
 import numpy as np
 
 from . import png
+from ._lib import PNG_TILE, TILE_OVERLAY, TILE_TOP_ORIGIN
+from .overlay import ATLAS
 
 _COLORS = {
     "black": (0, 0, 0, 255),
@@ -24,7 +37,10 @@ _COLORS = {
     "white": (255, 255, 255, 255),
     "blue": (0, 0, 255, 255),
     "green": (0, 128, 0, 255),
+    "gray": (128, 128, 128, 255),
 }
+_BACKGROUND = (255, 255, 255, 255)
+DEFAULT_DPI = 100
 
 
 def _rgba(color) -> tuple[int, int, int, int]:
@@ -36,9 +52,33 @@ def _rgba(color) -> tuple[int, int, int, int]:
     return (int(c[0]), int(c[1]), int(c[2]), int(c[3]) if len(c) > 3 else 255)
 
 
+def nearest_index(n_dst: int, n_src: int) -> np.ndarray:
+    """Source index of every destination pixel, nearest neighbour on pixel centres:
+    ``floor((d + 0.5) * n_src / n_dst)`` evaluated in float32 exactly like ``csrc/png.cu``."""
+    scale = np.float32(n_src) / np.float32(n_dst)
+    k = ((np.arange(n_dst, dtype=np.float32) + np.float32(0.5)) * scale).astype(np.int64)
+    return np.minimum(k, n_src - 1)
+
+
+_change_rows_cache: dict = {}
+_content_rows_cache: dict = {}
+
+
+def _change_rows(ne: int, h: int) -> np.ndarray:
+    """Destination rows (0-based, inside a tile ``h`` pixels high) at which the source row changes."""
+    key = (ne, h)
+    hit = _change_rows_cache.get(key)
+    if hit is None:
+        idx = nearest_index(h, ne)
+        hit = _change_rows_cache[key] = np.concatenate([[0], np.flatnonzero(np.diff(idx)) + 1]).astype(np.int32)
+        if len(_change_rows_cache) > 4096:
+            _change_rows_cache.clear()
+    return hit
+
+
 class _Label:
     def __init__(self):
-        self.text, self.fontsize = "", None
+        self.text, self.fontsize, self.rotation = "", None, None
 
     def set_fontsize(self, size):
         self.fontsize = size
@@ -81,9 +121,11 @@ class RasterImage:
 
 
 class Colorbar:
+    """A colour bar beside its panel: ramp of the panel's colormap, ticks, label."""
+
     def __init__(self, image, label, ticks=None, fmt=None):
         self.image, self.label, self.ticks, self.format = image, label, ticks, fmt
-        self.ax = PanelAxes(None)
+        self.ax = PanelAxes(None)  # the tick_params / set_ylabel calls the reference makes on cbar.ax
 
 
 class PanelAxes:
@@ -95,12 +137,15 @@ class PanelAxes:
         self.lines: list[dict] = []
         self.texts: list[dict] = []
         self.xaxis, self.yaxis = _AxisSide(), _AxisSide()
-        self.title = ""
+        self.title, self.title_fontsize = "", None
         self._xlim = (0.0, 1.0)
         self.yticks = None
         self.yticklabels = None
         self.yscale = "linear"
-        self.tick_params_calls: list[dict] = []
+        self.tick_labelsize = None
+        self.tick_length = None
+        self.colorbar: Colorbar | None = None
+        self.row_label_pad = 0
 
     # -- the Axes calls the path makes (plotting.py:234-387, cusp_marking.py)
     def imshow(self, rgba, aspect="auto", origin="lower", extent=None, cmap=None, norm=None, vmin=None, vmax=None,
@@ -118,14 +163,20 @@ class PanelAxes:
 
     def set_xlabel(self, text, **kw):
         self.xaxis.label.text = text
+        if "fontsize" in kw:
+            self.xaxis.label.fontsize = kw["fontsize"]
 
     def set_ylabel(self, text, **kw):
         self.yaxis.label.text = text
         if "fontsize" in kw:
             self.yaxis.label.fontsize = kw["fontsize"]
+        if "labelpad" in kw:
+            self.row_label_pad = kw["labelpad"]
 
     def set_title(self, text, **kw):
         self.title = text
+        if "fontsize" in kw:
+            self.title_fontsize = kw["fontsize"]
 
     def set_yticks(self, ticks):
         self.yticks = list(ticks)
@@ -137,7 +188,9 @@ class PanelAxes:
         self.yscale = scale
 
     def tick_params(self, **kw):
-        self.tick_params_calls.append(kw)
+        if kw.get("which", "major") == "major":
+            self.tick_labelsize = kw.get("labelsize", self.tick_labelsize)
+            self.tick_length = kw.get("length", self.tick_length)
 
     def axvline(self, x, **kw):
         line = {"kind": "vline", "x": float(x), **kw}
@@ -157,43 +210,223 @@ class PanelAxes:
     def get_xaxis_transform(self):
         return "xaxis"  # x in data units, y in axes fraction
 
-    # -- composition
-    def marker_columns(self) -> list[tuple[int, int, tuple[int, int, int, int]]]:
-        """(column, half width, colour) of every vertical marker burnt into the panel, in drawing order."""
-        if not self.images:
-            return []
-        img = self.images[-1]
-        n_cols = img.rgba.shape[1]
-        out = []
-        if img.extent is not None and n_cols > 0:
-            x0, x1 = float(img.extent[0]), float(img.extent[1])
-            span = (x1 - x0) or 1.0
-            for ln in self.lines:
-                if ln["kind"] != "vline":
-                    continue
-                col = int(round((ln["x"] - x0) / span * (n_cols - 1)))
-                if 0 <= col < n_cols:
-                    half = 1 if float(ln.get("linewidth", 1)) >= 4 else 0
-                    out.append((col, half, _rgba(ln.get("color", "black"))))
-        return out
-
-    def render(self) -> np.ndarray | None:
-        """(rows, cols, 4) uint8, image row 0 at the TOP, vertical markers burnt in."""
-        if not self.images:
-            return None
-        img = self.images[-1]
-        if isinstance(img.rgba, DeviceRaster):
-            raise TypeError("this panel lives on the device: encode the figure with png.encode_figures_device")
-        out = np.ascontiguousarray(img.rgba[::-1])  # origin="lower": flip for top-down image rows
-        for col, half, colour in self.marker_columns():
-            out[:, max(0, col - half) : col + half + 1] = colour
-        return out
-
 
 class FigureCanvas:
     def __init__(self, figure):
         self.figure = figure
         figure.canvas = self
+
+
+# --------------------------------------------------------------------------------------------
+# tick choices
+# --------------------------------------------------------------------------------------------
+_TIME_STEPS = (1, 2, 5, 10, 15, 30, 60, 120, 300, 600, 900, 1800, 3600, 7200, 10800, 21600, 43200, 86400)
+
+
+def time_ticks(left_days: float, right_days: float, max_ticks: int = 7):
+    """Tick positions (days since 1970, the x unit of the path) on round times of day."""
+    span = (right_days - left_days) * 86400.0
+    if not (span > 0) or not math.isfinite(span):
+        return []
+    step = next((s for s in _TIME_STEPS if span / s <= max_ticks), 86400 * math.ceil(span / 86400 / max_ticks))
+    first = math.ceil(left_days * 86400.0 / step - 1e-9) * step
+    out, t = [], first
+    while t <= right_days * 86400.0 + 1e-6 and len(out) < 64:
+        out.append(t / 86400.0)
+        t += step
+    return out
+
+
+def _format_time(days: float, fmt: str) -> str:
+    return (datetime(1970, 1, 1, tzinfo=timezone.utc) + timedelta(seconds=round(days * 86400.0))).strftime(fmt)
+
+
+def linear_ticks(lo: float, hi: float, max_ticks: int = 6):
+    if not (math.isfinite(lo) and math.isfinite(hi)) or hi <= lo:
+        return []
+    raw = (hi - lo) / max_ticks
+    mag = 10.0 ** math.floor(math.log10(raw))
+    step = next(m * mag for m in (1, 2, 5, 10) if m * mag >= raw)
+    first = math.ceil(lo / step - 1e-9) * step
+    return [first + k * step for k in range(int((hi - first) / step + 1e-9) + 1)]
+
+
+def _format_number(v: float) -> str:
+    if v == 0:
+        return "0"
+    if abs(v) >= 1e4 or abs(v) < 1e-2:
+        mant, exp = f"{v:.1e}".split("e")
+        mant = mant.rstrip("0").rstrip(".")
+        return f"{mant}e{int(exp)}" if mant != "1" else f"1e{int(exp)}"
+    return f"{v:g}"
+
+
+_OVERLAY_FLAGS = TILE_OVERLAY | TILE_TOP_ORIGIN
+
+
+class FigureTiles:
+    """The tile list of one figure: what both composers consume."""
+
+    __slots__ = ("W", "H", "records", "sources", "background")
+
+    def __init__(self, W, H, background):
+        self.W, self.H, self.background = int(W), int(H), background
+        self.records: list[tuple] = []  # PNG_TILE fields, in drawing priority (the first tile covering a pixel wins)
+        self.sources: dict = {}         # record index -> DeviceRaster | ndarray, for the panel rasters
+
+    def sprite(self, ref, x, y, w=None, h=None):
+        off, sh, sw = ref
+        w, h = sw if w is None else w, sh if h is None else h
+        if w <= 0 or h <= 0:
+            return
+        x = min(max(int(x), 0), max(self.W - w, 0))
+        y = min(max(int(y), 0), max(self.H - h, 0))
+        self.records.append((off, sh, sw, x, y, min(w, self.W - x), min(h, self.H - y), 0, 0, _OVERLAY_FLAGS, 0))
+
+    def rect(self, color, x, y, w, h):
+        """A filled rectangle (clipped to the canvas)."""
+        x0, y0 = max(int(x), 0), max(int(y), 0)
+        x1, y1 = min(int(x) + int(w), self.W), min(int(y) + int(h), self.H)
+        if x1 > x0 and y1 > y0:
+            self.records.append((ATLAS.solid(color)[0], 1, 1, x0, y0, x1 - x0, y1 - y0, 0, 0, _OVERLAY_FLAGS, 0))
+
+    def raster(self, source, ne, nt, x, y, w, h):
+        if w <= 0 or h <= 0 or ne <= 0 or nt <= 0:
+            return
+        off = source.offset if isinstance(source, DeviceRaster) else 0
+        self.sources[len(self.records)] = source
+        self.records.append((off, ne, nt, int(x), int(y), int(w), int(h), 0, 0, 0, 0))
+
+    def table(self) -> np.ndarray:
+        return np.array(self.records, dtype=PNG_TILE) if self.records else np.zeros(0, dtype=PNG_TILE)
+
+    def content_rows(self, table: np.ndarray | None = None) -> np.ndarray:
+        """Ascending scanlines whose content may differ from the line above: where a tile starts, ends or
+        moves on to another source row (the device encodes these; the runs in between repeat)."""
+        t = self.table() if table is None else table
+        # rows depend on the vertical geometry only, which the figures of one kind share
+        key = (self.H, t["y"].tobytes(), t["h"].tobytes(), t["ne"].tobytes()) if len(t) else (self.H,)
+        hit = _content_rows_cache.get(key)
+        if hit is not None:
+            return hit
+        mark = np.zeros(self.H + 2, dtype=bool)
+        mark[0] = True
+        if len(t):
+            y, h, ne = t["y"].astype(np.int64), t["h"].astype(np.int64), t["ne"].astype(np.int64)
+            mark[np.minimum(y, self.H)] = True
+            mark[np.minimum(y + h, self.H)] = True
+            one_to_one = (ne == h) & (h > 1)
+            if one_to_one.any():  # sprites at their own size: every row is new (+1 / -1 over their spans)
+                delta = np.zeros(self.H + 2, dtype=np.int32)
+                np.add.at(delta, np.minimum(y[one_to_one], self.H), 1)
+                np.add.at(delta, np.minimum(y[one_to_one] + h[one_to_one], self.H), -1)
+                mark[:-1] |= np.cumsum(delta[:-1]) > 0
+            for k in np.flatnonzero((ne != h) & (ne > 1)):  # resampled rasters and ramps: a few per figure
+                rows = _change_rows(int(ne[k]), int(h[k])) + int(y[k])
+                mark[rows[rows <= self.H]] = True
+        rows = np.flatnonzero(mark[: self.H]).astype(np.int32)
+        if len(_content_rows_cache) > 256:
+            _content_rows_cache.clear()
+        _content_rows_cache[key] = rows
+        return rows
+
+
+_static_blocks: dict = {}
+_tick_blocks: dict = {}  # time / colour-bar tick marks and labels, relative to their box
+
+
+def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float, pad: int, y_lo: float, y_hi: float):
+    """``(tiles, geometry)`` of a subplot's figure-independent part, relative to the cell's top-left corner:
+    tiles as ``(rgba_off, ne, nt, x, y, w, h, flags)``; geometry = ``(box x, box y, box w, box h, tick label px,
+    tick length, line width, colour-bar x, colour-bar width, colour-bar tick label px)`` or ``None`` when the
+    cell leaves no room for a box.  The margins come from the rendered sizes of the labels; the room kept for
+    the (per-figure) time and colour-bar tick labels is that of a five-digit label."""
+    black = (0, 0, 0, 255)
+    tick_px = max(6, int(round((ax.tick_labelsize or 10) * pt)))
+    tick_len = max(2, int(round((ax.tick_length or 4) * pt)))
+    line_w = max(1, int(round(0.8 * pt)))
+    solid = ATLAS.solid(black)[0]
+    tiles: list[tuple] = []
+
+    def rect(x, y, w, h):
+        if w > 0 and h > 0:
+            tiles.append((solid, 1, 1, int(x), int(y), int(w), int(h), _OVERLAY_FLAGS))
+
+    def sprite(ref, x, y, w=None, h=None):
+        tiles.append((ref[0], ref[1], ref[2], max(int(x), 0), max(int(y), 0), ref[2] if w is None else int(w),
+                      ref[1] if h is None else int(h), _OVERLAY_FLAGS))
+
+    def label_px(label, default=10):
+        return max(6, int(round((label.fontsize or default) * pt)))
+
+    ylabel = ATLAS.text(ax.yaxis.label.text, label_px(ax.yaxis.label), rotate=True) if ax.yaxis.label.text else None
+    xlabel = ATLAS.text(ax.xaxis.label.text, label_px(ax.xaxis.label)) if ax.xaxis.label.text else None
+    title = ATLAS.text(ax.title, max(6, int(round((ax.title_fontsize or 12) * pt)))) if ax.title else None
+    log_y = ax.yscale == "log" and y_lo > 0 and y_hi > 0
+    if ax.yticks is not None:
+        yt = [float(v) for v in ax.yticks]
+        yl = list(ax.yticklabels) if ax.yticklabels is not None else [_format_number(v) for v in yt]
+    elif log_y:
+        yt = [10.0 ** k for k in range(math.ceil(math.log10(min(y_lo, y_hi)) - 1e-9), math.floor(math.log10(max(y_lo, y_hi)) + 1e-9) + 1)]
+        yl = [_format_number(v) for v in yt]
+    else:
+        yt = linear_ticks(min(y_lo, y_hi), max(y_lo, y_hi))
+        yl = [_format_number(v) for v in yt]
+    y_refs = [ATLAS.text(str(s), tick_px) for s in yl]
+    cb = ax.colorbar
+    cb_px, cb_label, cb_room = tick_px, None, 0
+    if cb is not None:
+        cb_px = max(6, int(round((cb.ax.tick_labelsize or ax.tick_labelsize or 10) * pt)))
+        cb_room = ATLAS.text("00000", cb_px)[2]
+        text = cb.ax.yaxis.label.text or cb.label
+        if text:
+            cb_label = ATLAS.text(text, max(6, int(round((cb.ax.yaxis.label.fontsize or ax.yaxis.label.fontsize or 10) * pt))), rotate=True)
+    # ---- margins -> the axes box
+    m_left = pad + (ylabel[2] + pad if ylabel else 0) + max([r[2] for r in y_refs] or [0]) + pad + tick_len
+    m_bottom = tick_len + pad + tick_px + pad + (xlabel[1] + pad if xlabel else 0) + pad
+    m_top = pad + (title[1] + pad if title else 0)
+    bh = ch - m_top - m_bottom
+    bar_w = cb_gap = 0
+    m_right = 2 * pad
+    if cb is not None:
+        bar_w, cb_gap = max(4, bh // 20), 3 * pad
+        m_right = cb_gap + bar_w + tick_len + pad + cb_room + pad + (cb_label[2] + pad if cb_label else 0) + pad
+    bx, by, bw = m_left, m_top, cw - m_left - m_right
+    if bw < 8 or bh < 8:
+        return [], None
+    # ---- frame, energy ticks, labels
+    rect(bx - line_w, by - line_w, bw + 2 * line_w, line_w)
+    rect(bx - line_w, by + bh, bw + 2 * line_w, line_w)
+    rect(bx - line_w, by, line_w, bh)
+    rect(bx + bw, by, line_w, bh)
+    for v, ref in zip(yt, y_refs):
+        if log_y:
+            f = (math.log10(v) - math.log10(y_lo)) / (math.log10(y_hi) - math.log10(y_lo)) if v > 0 else -1.0
+        else:
+            f = (v - y_lo) / (y_hi - y_lo) if y_hi != y_lo else 0.0
+        py = by + bh - f * bh
+        if by - 0.5 <= py <= by + bh + 0.5:
+            rect(bx - line_w - tick_len, int(round(py - line_w / 2)), tick_len, line_w)
+            sprite(ref, bx - line_w - tick_len - pad - ref[2], int(round(py - ref[1] / 2)))
+    if ylabel:
+        sprite(ylabel, pad, int(by + bh / 2 - ylabel[1] / 2))
+    if xlabel:
+        sprite(xlabel, int(bx + bw / 2 - xlabel[2] / 2), by + bh + line_w + tick_len + pad + tick_px + pad)
+    if title:
+        sprite(title, int(bx + bw / 2 - title[2] / 2), pad)
+    # ---- colour bar: frame, the colormap's ramp (highest value on top), label
+    kx = bx + bw + cb_gap
+    if cb is not None:
+        from .colormaps import get_lut
+
+        rect(kx - line_w, by - line_w, bar_w + 2 * line_w, line_w)
+        rect(kx - line_w, by + bh, bar_w + 2 * line_w, line_w)
+        rect(kx - line_w, by, line_w, bh)
+        rect(kx + bar_w, by, line_w, bh)
+        sprite(ATLAS.ramp(get_lut(img.cmap or "viridis")), kx, by, bar_w, bh)
+        if cb_label:
+            sprite(cb_label, kx + bar_w + line_w + tick_len + pad + cb_room + pad, int(by + bh / 2 - cb_label[1] / 2))
+    return tiles, (bx, by, bw, bh, tick_px, tick_len, line_w, kx, bar_w, cb_px)
 
 
 class SpectrogramFigure:
@@ -206,9 +439,10 @@ class SpectrogramFigure:
         self.axes: list[PanelAxes] = []
         self._grid: dict[int, tuple[int, int, int]] = {}
         self.colorbars: list[Colorbar] = []
-        self.suptitle_text = None
+        self.suptitle_text, self.suptitle_fontsize = None, None
         self.texts: list[dict] = []
         self.canvas = None
+        self.rect = (0.0, 0.0, 1.0, 1.0)
         self.number = SpectrogramFigure._next_number
         SpectrogramFigure._next_number += 1
 
@@ -221,19 +455,22 @@ class SpectrogramFigure:
     def colorbar(self, image, ax=None, label=None, ticks=None, format=None):
         cb = Colorbar(image, label, ticks, format)
         self.colorbars.append(cb)
+        if ax is not None:
+            ax.colorbar = cb
         return cb
 
     def suptitle(self, text, **kw):
-        self.suptitle_text = text
+        self.suptitle_text, self.suptitle_fontsize = text, kw.get("fontsize")
 
     def text(self, x, y, s, **kw):
         self.texts.append({"x": x, "y": y, "text": s, **kw})
 
-    def tight_layout(self, **kw):
-        pass
+    def tight_layout(self, rect=None, **kw):
+        if rect is not None:
+            self.rect = tuple(float(v) for v in rect)
 
     def subplots_adjust(self, **kw):
-        pass
+        pass  # superseded by tight_layout in every figure of the path
 
     def delaxes(self, ax):
         if ax in self.axes:
@@ -243,53 +480,187 @@ class SpectrogramFigure:
     def clf(self):
         self.axes, self._grid, self.colorbars, self.texts = [], {}, [], []
 
-    def layout(self, row_height: int = 148, gap: int = 8):
-        """Geometry of :meth:`compose`: ``(H, W, [(axes, y, x, rep)])`` -- every panel at cell
-        resolution (time steps are columns), energy rows repeated to about ``row_height`` pixels,
-        laid out on the subplot grid with ``gap`` pixels in between.  Shapes only, so it serves
-        host rasters and device-resident ones alike."""
-        cells = {}
-        n_rows = n_cols = 1
+    # ------------------------------------------------------------------ layout
+    def tiles(self, dpi: float | None = None) -> FigureTiles:
+        """The figure as tiles on a ``figsize x dpi`` canvas."""
+        dpi = float(dpi or DEFAULT_DPI)
+        W, H = max(1, int(round(self.figsize[0] * dpi))), max(1, int(round(self.figsize[1] * dpi)))
+        out = FigureTiles(W, H, _BACKGROUND)
+        pt = dpi / 72.0  # pixels per point
+        pad = max(2, int(round(3 * pt)))
+        black = (0, 0, 0, 255)
+        if not self.axes:
+            return out
+        n_rows = max(self._grid[id(a)][0] for a in self.axes)
+        n_cols = max(self._grid[id(a)][1] for a in self.axes)
+        left, bottom, right, top = self.rect
+        area_x, area_w = left * W, (right - left) * W
+        area_y, area_h = (1.0 - top) * H, (top - bottom) * H
+        if self.suptitle_text:
+            ref = ATLAS.text(self.suptitle_text, int(round((self.suptitle_fontsize or 14) * pt)))
+            out.sprite(ref, (W - ref[2]) // 2, max(pad, int(area_y) - ref[1] - pad) if top < 1.0 else pad)
+            if top >= 1.0:
+                area_y += ref[1] + 2 * pad
+                area_h -= ref[1] + 2 * pad
+        for entry in self.texts:  # figure text: (x, y) in figure fractions, y from the bottom
+            ref = ATLAS.text(entry["text"], int(round(entry.get("fontsize", 10) * pt)), _rgba(entry.get("color", "black")))
+            x = entry["x"] * W - (ref[2] / 2 if entry.get("ha") == "center" else (ref[2] if entry.get("ha") == "right" else 0))
+            y = (1.0 - entry["y"]) * H - (ref[1] if entry.get("va", "bottom") == "bottom" else (ref[1] / 2 if entry.get("va") == "center" else 0))
+            out.sprite(ref, int(round(x)), int(round(y)))
+        cell_w, cell_h = area_w / n_cols, area_h / n_rows
         for ax in self.axes:
             r, c, idx = self._grid[id(ax)]
-            n_rows, n_cols = max(n_rows, r), max(n_cols, c)
-            if not ax.images:
-                continue
-            ne, nt = ax.images[-1].rgba.shape[:2]
-            if ne * nt == 0:
-                continue
-            rep = max(1, row_height // ne)
-            cells[((idx - 1) // c, (idx - 1) % c)] = (ax, ne * rep, nt, rep)
-        if not cells:
-            return 1, 1, []
-        heights = [max([v[1] for (r, _c), v in cells.items() if r == i] or [0]) for i in range(n_rows)]
-        widths = [max([v[2] for (_r, c), v in cells.items() if c == j] or [0]) for j in range(n_cols)]
-        H = sum(heights) + gap * (n_rows + 1)
-        W = sum(widths) + gap * (n_cols + 1)
-        placed = []
-        y = gap
-        for i in range(n_rows):
-            x = gap
-            for j in range(n_cols):
-                v = cells.get((i, j))
-                if v is not None:
-                    placed.append((v[0], y, x, v[3]))
-                x += widths[j] + gap
-            y += heights[i] + gap
-        return H, W, placed
+            i, j = (idx - 1) // c, (idx - 1) % c
+            self._axes_tiles(out, ax, area_x + j * cell_w, area_y + i * cell_h, cell_w, cell_h, pt, pad, black)
+        return out
 
-    def compose(self, row_height: int = 148, gap: int = 8, background=(255, 255, 255, 255)) -> np.ndarray:
-        """The figure as one (H, W, 4) uint8 image (see :meth:`layout`)."""
-        H, W, placed = self.layout(row_height, gap)
-        canvas = np.empty((H, W, 4), dtype=np.uint8)
-        canvas[:] = background
-        for ax, y, x, rep in placed:
-            p = np.repeat(ax.render(), rep, axis=0)
-            canvas[y : y + p.shape[0], x : x + p.shape[1]] = p
+    def _axes_tiles(self, out: FigureTiles, ax: PanelAxes, cx, cy, cw, ch, pt, pad, black):
+        """One subplot as tiles.  Everything that does not change from figure to figure of a batch -- the box
+        geometry, frames, energy ticks and their labels, axis labels, the title, the colour bar's frame, ramp
+        and label -- is built once per distinct set of settings (``_static_block``) and only shifted to the
+        cell; the cusp markers, the time ticks, the colour-bar ticks and the panel itself are per figure."""
+        if not ax.images:
+            return
+        img = ax.images[-1]
+        ne, nt = img.rgba.shape[:2]
+        if ne * nt == 0:
+            return
+        cx, cy = int(round(cx)), int(round(cy))
+        x_lo, x_hi = ax._xlim
+        ex = img.extent if img.extent is not None else (x_lo, x_hi, 0.0, 1.0)
+        y_lo, y_hi = float(ex[2]), float(ex[3])
+        cb = ax.colorbar
+        key = (int(cw), int(ch), pt, pad, ax.tick_labelsize, ax.tick_length, ax.yaxis.label.text, ax.yaxis.label.fontsize,
+               ax.xaxis.label.text, ax.xaxis.label.fontsize, ax.title, ax.title_fontsize,
+               None if ax.yticks is None else tuple(ax.yticks), None if ax.yticklabels is None else tuple(ax.yticklabels),
+               ax.yscale, y_lo, y_hi, cb is not None,
+               None if cb is None else (cb.label, cb.ax.yaxis.label.text, cb.ax.yaxis.label.fontsize, cb.ax.tick_labelsize, img.cmap))
+        hit = _static_blocks.get(key)
+        if hit is None:
+            hit = _static_blocks[key] = _static_block(ax, img, int(cw), int(ch), pt, pad, y_lo, y_hi)
+            if len(_static_blocks) > 512:
+                _static_blocks.clear()
+        block, geo = hit
+        if geo is None:
+            return  # the cell is too small for a box
+        bx, by, bw, bh, tick_px, tick_len, line_w, kx, bar_w, cb_px = geo
+        bx, by, kx = bx + cx, by + cy, kx + cx
+        span = x_hi - x_lo
+        scale = bw / span if span != 0 else 0.0
+        records = out.records
+
+        # ---- markers first (the first tile covering a pixel wins): vertical lines, brackets, captions
+        for ln in reversed(ax.lines):  # later artists are on top
+            colour = _rgba(ln.get("color", "black"))
+            lw = max(1, int(round(float(ln.get("linewidth", 1)) * pt)))
+            if ln["kind"] == "vline":
+                px = bx + (ln["x"] - x_lo) * scale
+                if bx <= px <= bx + bw:
+                    out.rect(colour, int(round(px - lw / 2)), by, lw, bh)
+            else:  # polyline in (data x, axes-fraction y): horizontal / vertical strokes of a bracket
+                pts = [(bx + (x - x_lo) * scale, by + (1.0 - y) * bh) for x, y in zip(ln["x"], ln["y"])]
+                for (xa, ya), (xb, yb) in zip(pts[:-1], pts[1:]):
+                    if abs(xa - xb) < 0.5:
+                        out.rect(colour, int(round(xa - lw / 2)), int(round(min(ya, yb))), lw, int(round(abs(ya - yb))) + lw)
+                    else:
+                        out.rect(colour, int(round(min(xa, xb))), int(round(ya - lw / 2)), int(round(abs(xa - xb))) + lw, lw)
+        for t in ax.texts:
+            ref = ATLAS.text(t["text"], max(6, int(round((t.get("fontsize") or ax.tick_labelsize or 10) * pt))), _rgba(t.get("color", "black")))
+            out.sprite(ref, int(round(bx + (t["x"] - x_lo) * scale - ref[2] / 2)), int(round(by + (1.0 - t["y"]) * bh)))
+        # ---- the static block, shifted to this cell
+        records.extend([(o, a, b, x + cx, y + cy, w, h, 0, 0, f, 0) for (o, a, b, x, y, w, h, f) in block])
+        # ---- time ticks and colour-bar ticks: positions relative to the box, shared by every panel that shows
+        # the same time range / value range at the same size (the rows of a grid; the variants of a figure)
+        fmt = ax.xaxis.major_formatter
+        x_key = (x_lo, x_hi, fmt, tick_px, bw, line_w, tick_len, pad)
+        x_block = _tick_blocks.get(x_key)
+        if x_block is None:
+            solid_black = ATLAS.solid(black)[0]
+            if isinstance(fmt, str):  # a time axis (the formatter is the strftime pattern the reference picks)
+                xt = time_ticks(x_lo, x_hi)
+                xl = [_format_time(v, fmt) for v in xt]
+            else:
+                xt = linear_ticks(x_lo, x_hi)
+                xl = [_format_number(v) for v in xt]
+            x_block = []
+            for v, label in zip(xt, xl):
+                px = (v - x_lo) * scale
+                if -0.5 <= px <= bw + 0.5:
+                    ref = ATLAS.text(label, tick_px)
+                    x_block.append((solid_black, 1, 1, int(round(px - line_w / 2)), line_w, line_w, tick_len))
+                    x_block.append((ref[0], ref[1], ref[2], int(round(px - ref[2] / 2)), line_w + tick_len + pad, ref[2], ref[1]))
+            if len(_tick_blocks) > 8192:
+                _tick_blocks.clear()
+            _tick_blocks[x_key] = x_block
+        W, H = out.W, out.H
+        ox, oy = bx, by + bh
+        roomy = bx >= 200 and bx + bw + 400 <= W and by + bh + 200 <= H  # no label of this cell can leave the canvas
+        if roomy:
+            records.extend([(o, a, b, x + ox, y + oy, w, h, 0, 0, _OVERLAY_FLAGS, 0) for o, a, b, x, y, w, h in x_block])
+        else:
+            for o, a, b, x, y, w, h in x_block:  # shifted below the box, kept inside the canvas
+                x, y = min(max(x + ox, 0), max(W - w, 0)), min(max(y + oy, 0), max(H - h, 0))
+                records.append((o, a, b, x, y, min(w, W - x), min(h, H - y), 0, 0, _OVERLAY_FLAGS, 0))
+        if cb is not None:
+            v0, v1 = float(img.vmin), float(img.vmax)
+            c_key = (v0, v1, img.norm, None if cb.ticks is None else tuple(cb.ticks), bh, cb_px, line_w, tick_len, pad, bar_w)
+            c_block = _tick_blocks.get(c_key)
+            if c_block is None:
+                solid_black = ATLAS.solid(black)[0]
+                log_z = img.norm == "log" and v0 > 0 and v1 > 0
+                if cb.ticks is not None:
+                    cb_ticks = [float(t) for t in cb.ticks]
+                elif log_z:
+                    cb_ticks = [10.0 ** k for k in range(math.ceil(math.log10(v0) - 1e-9), math.floor(math.log10(v1) + 1e-9) + 1)]
+                else:
+                    cb_ticks = linear_ticks(v0, v1, 5)
+                l0, l1 = (math.log10(v0), math.log10(v1)) if log_z else (v0, v1)
+                c_block = []
+                for v in cb_ticks:
+                    if l1 == l0 or (log_z and v <= 0):
+                        continue
+                    f = ((math.log10(v) if log_z else v) - l0) / (l1 - l0)
+                    if -1e-9 <= f <= 1.0 + 1e-9:
+                        py = bh - f * bh
+                        ref = ATLAS.text(_format_number(v), cb_px)
+                        c_block.append((solid_black, 1, 1, bar_w + line_w, int(round(py - line_w / 2)), tick_len, line_w))
+                        c_block.append((ref[0], ref[1], ref[2], bar_w + line_w + tick_len + pad, int(round(py - ref[1] / 2)), ref[2], ref[1]))
+                _tick_blocks[c_key] = c_block
+            if roomy:
+                records.extend([(o, a, b, x + kx, y + by, w, h, 0, 0, _OVERLAY_FLAGS, 0) for o, a, b, x, y, w, h in c_block])
+            else:
+                for o, a, b, x, y, w, h in c_block:
+                    x, y = min(max(x + kx, 0), max(W - w, 0)), min(max(y + by, 0), max(H - h, 0))
+                    records.append((o, a, b, x, y, min(w, W - x), min(h, H - y), 0, 0, _OVERLAY_FLAGS, 0))
+        # ---- the panel itself: the image covers its extent inside the x limits (imshow aspect="auto")
+        ix0 = int(round(min(max(bx + (float(ex[0]) - x_lo) * scale, bx), bx + bw)))
+        ix1 = int(round(min(max(bx + (float(ex[1]) - x_lo) * scale, bx), bx + bw)))
+        if ix1 - ix0 < 1:
+            ix0, ix1 = bx, bx + bw
+        out.raster(img.rgba, ne, nt, ix0, by, ix1 - ix0, bh)
+
+    # --------------------------------------------------------------- composing
+    def compose(self, dpi: float | None = None) -> np.ndarray:
+        """The figure as one (H, W, 4) uint8 image: the numpy evaluation of :meth:`tiles` (the oracle of
+        the device composer, ``csrc/png.cu``).  Needs host rasters."""
+        t = self.tiles(dpi)
+        canvas = np.empty((t.H, t.W, 4), dtype=np.uint8)
+        canvas[:] = t.background
+        atlas = ATLAS.pixels()
+        for k in range(len(t.records) - 1, -1, -1):  # the first tile of the list ends up on top
+            off, ne, nt, x, y, w, h, _vf, _vc, flags, _pad = t.records[k]
+            src = t.sources.get(k)
+            if isinstance(src, DeviceRaster):
+                raise TypeError("this panel lives on the device: encode the figure with png.encode_figures_device")
+            source = atlas[off : off + ne * nt].view(np.uint8).reshape(ne, nt, 4) if flags & TILE_OVERLAY else src
+            rows = nearest_index(h, ne)
+            if not flags & TILE_TOP_ORIGIN:
+                rows = ne - 1 - rows  # rasters store the lowest energy first (imshow origin="lower")
+            canvas[y : y + h, x : x + w] = source[rows][:, nearest_index(w, nt)]
         return canvas
 
     def savefig(self, path, dpi=None, compress_level: int = 6, **kw):
-        png.write_rgba(path, self.compose(), compress_level=compress_level)
+        png.write_rgba(path, self.compose(dpi), compress_level=compress_level)
 
 
 def close_all_axes_and_clear(fig) -> None:

@@ -217,66 +217,67 @@ def make_spectrogram(
     return axis_object, x_axis_plot
 
 
+def _decade_ticks(z_lo, z_hi):
+    """Colour-bar ticks of a log panel: the powers of ten inside [z_lo, z_hi] (reference ``:288-299``)."""
+    if not (z_lo > 0 and z_hi > 0 and np.isfinite(z_lo) and np.isfinite(z_hi)):
+        return None
+    decades = range(int(np.floor(np.log10(z_lo))), int(np.ceil(np.log10(z_hi))) + 1)
+    return [10**k for k in decades if z_lo <= 10**k <= z_hi]
+
+
+def _energy_ticks(y_axis_min, y_axis_max):
+    """The reference's y ticks for a linear energy axis (``:335-352``): a step of one power of ten read off
+    the PRINTED form of ``y_axis_max`` (so 4000 and 4000.0 tick differently, as there), an upper tick of
+    ``d`` or ``d + 0.5`` leading digits, ticks up to 10 % beyond it."""
+    printed = str(y_axis_max)
+    width, lead, nxt = len(printed), int(printed[0]), int(printed[1])
+    if nxt >= 5:
+        step, top = 10**width, lead * 10 ** (width - 1)
+    else:
+        step, top = 10 ** (width - 1), (lead + 0.5) * 10 ** (width - 1)
+    return [v for v in range(y_axis_min, int(top) + 1, step) if v / top <= 1.1]
+
+
 def draw_panel(axis_object, rgba, index, z_lo, z_hi, log_scale, x_axis_plot, y_kept, *, x_label="Time (UTC)",
                x_axis_is_unix=True, y_axis_scale_function=None, y_axis_label=None, y_axis_min=0, y_axis_max=4000,
                z_axis_label=None, colormap="viridis", instrument_label=None, vertical_lines_unix=None,
                cusp_marker_style="both", cusp_marker_kwargs=None):
-    """Everything ``make_spectrogram`` does to the axes once the raster exists (reference
-    ``:280-387``): imshow, colorbar, labels, y ticks, time formatter, cusp markers."""
-    fig = axis_object.figure
-    extent = (x_axis_plot[0], x_axis_plot[-1], y_kept[0], y_kept[-1])
-    im = axis_object.imshow(rgba, aspect="auto", origin="lower", extent=extent, cmap=_colormap_name(colormap),
-                            norm="log" if log_scale else None, vmin=z_lo, vmax=z_hi, index=index)
-    ticks = None
-    if log_scale and z_lo > 0 and z_hi > 0 and np.isfinite(z_lo) and np.isfinite(z_hi):
-        lo_e, hi_e = int(np.floor(np.log10(z_lo))), int(np.ceil(np.log10(z_hi)))
-        ticks = [10**i for i in range(lo_e, hi_e + 1) if z_lo <= 10**i <= z_hi]
-    colorbar = fig.colorbar(im, ax=axis_object, label=z_axis_label if z_axis_label is not None else "Counts", ticks=ticks)
-
-    axis_object.set_xlabel(x_label)
-    axis_object.set_ylabel(y_axis_label if y_axis_label is not None else "Energy (eV)")
+    """What ``make_spectrogram`` puts on the axes once the raster exists (reference ``:280-387``): the image
+    with its extent, a colour bar (decade ticks on a log panel), axis labels, energy ticks, the time format
+    chosen by the displayed span, cusp markers inside the plotted range, the path's font sizes."""
+    ax, fig = axis_object, axis_object.figure
+    image = ax.imshow(rgba, aspect="auto", origin="lower", extent=(x_axis_plot[0], x_axis_plot[-1], y_kept[0], y_kept[-1]),
+                      cmap=_colormap_name(colormap), norm="log" if log_scale else None, vmin=z_lo, vmax=z_hi, index=index)
+    bar = fig.colorbar(image, ax=ax, label="Counts" if z_axis_label is None else z_axis_label,
+                       ticks=_decade_ticks(z_lo, z_hi) if log_scale else None)
+    ax.set_xlabel(x_label)
+    ax.set_ylabel("Energy (eV)" if y_axis_label is None else y_axis_label)
     if instrument_label is not None:
-        axis_object.set_title(instrument_label)
-
-    if len(y_kept) >= 2:  # y ticks (:335-355)
-        if y_axis_scale_function != "log":
-            y_max_str = str(y_axis_max)
-            digits = len(y_max_str)
-            first, second = int(y_max_str[0]), int(y_max_str[1])
-            if second >= 5:
-                step, y_max_tick = 10**digits, first * 10 ** (digits - 1)
-            else:
-                step, y_max_tick = 10 ** (digits - 1), (first + 0.5) * 10 ** (digits - 1)
-            yticks = [i for i in range(y_axis_min, int(y_max_tick) + 1, step) if (i / y_max_tick) <= 1.1]
-            if yticks:
-                axis_object.set_yticks(yticks)
-                axis_object.set_yticklabels([f"{int(e)}" for e in yticks])
+        ax.set_title(instrument_label)
+    if len(y_kept) >= 2:
+        if y_axis_scale_function == "log":
+            ax.set_yscale("log")
         else:
-            axis_object.set_yscale("log")
-
-    if x_axis_is_unix:  # tick format by displayed span (:357-368)
-        left, right = axis_object.get_xlim()
-        span = (num2date(right) - num2date(left)).total_seconds()
-        axis_object.xaxis.set_major_formatter("%H:%M:%S" if span < 120 else "%H:%M")
-
-    if vertical_lines_unix is not None and len(vertical_lines_unix) > 0:  # :370-381
-        if x_axis_is_unix:
-            marks = [v for v in date2num(list(vertical_lines_unix)) if x_axis_plot[0] <= v <= x_axis_plot[-1]]
-        else:
-            marks = [v for v in vertical_lines_unix if x_axis_plot[0] <= v <= x_axis_plot[-1]]
-        draw_marker = _CUSP_MARKER_DRAWERS.get(cusp_marker_style, draw_cusp_both_markers)
-        marker_kwargs = dict(cusp_marker_kwargs or {})
-        marker_kwargs.setdefault("line_color", "white" if colormap in _RED_HEAVY_COLORMAPS else "red")
-        draw_marker(axis_object, marks, **marker_kwargs)
-
-    axis_object.tick_params(axis="both", which="major", labelsize=TICK_LABEL_FONT_SIZE, length=8, width=1)
-    axis_object.tick_params(axis="both", which="minor", labelsize=TICK_LABEL_FONT_SIZE, length=5, width=1)
-    colorbar.ax.tick_params(labelsize=TICK_LABEL_FONT_SIZE, length=6, width=1)
-    colorbar.ax.tick_params(which="minor", labelsize=TICK_LABEL_FONT_SIZE, length=3, width=1)
-    axis_object.xaxis.label.set_fontsize(AXIS_LABEL_FONT_SIZE)
-    axis_object.yaxis.label.set_fontsize(AXIS_LABEL_FONT_SIZE)
-    colorbar.ax.set_ylabel("Counts", fontsize=AXIS_LABEL_FONT_SIZE)
-    return im
+            ticks = _energy_ticks(y_axis_min, y_axis_max)
+            if ticks:
+                ax.set_yticks(ticks)
+                ax.set_yticklabels([f"{int(v)}" for v in ticks])
+    if x_axis_is_unix:  # seconds matter only on a window shorter than two minutes (:357-368)
+        left, right = ax.get_xlim()
+        ax.xaxis.set_major_formatter("%H:%M:%S" if (num2date(right) - num2date(left)).total_seconds() < 120 else "%H:%M")
+    if vertical_lines_unix is not None and len(vertical_lines_unix) > 0:
+        positions = date2num(list(vertical_lines_unix)) if x_axis_is_unix else vertical_lines_unix
+        inside = [v for v in positions if x_axis_plot[0] <= v <= x_axis_plot[-1]]
+        options = dict(cusp_marker_kwargs or {})
+        options.setdefault("line_color", "white" if colormap in _RED_HEAVY_COLORMAPS else "red")
+        _CUSP_MARKER_DRAWERS.get(cusp_marker_style, draw_cusp_both_markers)(ax, inside, **options)
+    for target, which, length in ((ax, "major", 8), (ax, "minor", 5), (bar.ax, "major", 6), (bar.ax, "minor", 3)):
+        extra = {"axis": "both"} if target is ax else {}
+        target.tick_params(which=which, labelsize=TICK_LABEL_FONT_SIZE, length=length, width=1, **extra)
+    for label in (ax.xaxis.label, ax.yaxis.label):
+        label.set_fontsize(AXIS_LABEL_FONT_SIZE)
+    bar.ax.set_ylabel("Counts", fontsize=AXIS_LABEL_FONT_SIZE)
+    return image
 
 
 def generic_plot_spectrogram_set(
@@ -413,26 +414,25 @@ def generic_plot_multirow_optional_zoom(
     return fig, canvas
 
 
+def _utc(seconds) -> str:
+    return datetime.fromtimestamp(float(seconds), tz=timezone.utc).strftime("%Y-%m-%d %H:%M:%S")
+
+
 def _finish_multirow(fig, axes, datasets, vertical_lines, title, row_label_pad=50, row_label_rotation=90):
-    """Row labels, column titles, footer texts of a multirow figure (reference ``:659-693``)."""
-    n_cols = axes.shape[1]
-    for i, ds in enumerate(datasets):
-        axes[i, 0].set_ylabel(ds.get("label", ""), fontsize=AXIS_LABEL_FONT_SIZE, rotation=row_label_rotation,
-                              labelpad=row_label_pad, va="center")
-    axes[0, 0].set_title("Full", fontsize=AXIS_LABEL_FONT_SIZE)
-    if n_cols == 2:
-        axes[0, 1].set_title("Zoomed", fontsize=AXIS_LABEL_FONT_SIZE)
+    """What a multirow figure carries besides its panels (reference ``:659-693``): the dataset label as the
+    y label of every row's first panel, "Full" / "Zoomed" column heads, the title, and two footers -- the
+    time span of the first dataset and, in red, the marked (cusp) range."""
+    for row, dataset in zip(axes, datasets):
+        row[0].set_ylabel(dataset.get("label", ""), fontsize=AXIS_LABEL_FONT_SIZE, rotation=row_label_rotation,
+                          labelpad=row_label_pad, va="center")
+    for head, ax in zip(("Full", "Zoomed"), axes[0]):
+        ax.set_title(head, fontsize=AXIS_LABEL_FONT_SIZE)
     if title:
         fig.suptitle(title, fontsize=AXIS_LABEL_FONT_SIZE + 2)
-    base_times = datasets[0]["x"]
-    t0 = datetime.fromtimestamp(float(base_times[0]), tz=timezone.utc)
-    t1 = datetime.fromtimestamp(float(base_times[-1]), tz=timezone.utc)
-    span = f"Data timespan: {t0.strftime('%Y-%m-%d %H:%M:%S')} to {t1.strftime('%Y-%m-%d %H:%M:%S')} UTC"
-    fig.subplots_adjust(bottom=0.18)
-    fig.text(0.5, 0.01, span, ha="center", va="bottom", fontsize=13)
+    footers = [(0.01, f"Data timespan: {_utc(datasets[0]['x'][0])} to {_utc(datasets[0]['x'][-1])} UTC", "black")]
     if vertical_lines is not None and len(vertical_lines) > 0:
-        v0 = datetime.fromtimestamp(float(min(vertical_lines)), tz=timezone.utc)
-        v1 = datetime.fromtimestamp(float(max(vertical_lines)), tz=timezone.utc)
-        marked = f"Marked range: {v0.strftime('%Y-%m-%d %H:%M:%S')} to {v1.strftime('%Y-%m-%d %H:%M:%S')} UTC"
-        fig.text(0.5, 0.045, marked, ha="center", va="bottom", fontsize=13, color="red")
+        footers.append((0.045, f"Marked range: {_utc(min(vertical_lines))} to {_utc(max(vertical_lines))} UTC", "red"))
+    fig.subplots_adjust(bottom=0.18)
+    for height, text, colour in footers:
+        fig.text(0.5, height, text, ha="center", va="bottom", fontsize=13, color=colour)
     fig.tight_layout(rect=(0, 0.08, 1, 0.95))

@@ -277,46 +277,122 @@ def adler32_of_segments(sum_bytes: np.ndarray, weighted: np.ndarray, lengths: np
     return (b << 16) | a
 
 
-def _device_tables(figures, row_height, gap, background):
-    from ._lib import PNG_CANVAS, PNG_TILE, PNG_VLINE
-    from .figure import DeviceRaster, _rgba
+_zero_runs: dict = {}
+
+
+def zero_run(width: int, n_lines: int) -> bytes:
+    """``n_lines`` scanlines that repeat the line above -- filter type 2 ("Up") followed by ``4 * width``
+    zero bytes each -- as a byte-aligned piece of a raw DEFLATE stream (ends with an empty stored block,
+    like the device's segments, so pieces concatenate).  A constant per (width, run length): cached."""
+    key = (width, n_lines)
+    hit = _zero_runs.get(key)
+    if hit is None:
+        comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+        line = b"\x02" + bytes(4 * width)
+        hit = comp.compress(line * n_lines) + comp.flush(zlib.Z_SYNC_FLUSH)
+        if len(_zero_runs) > 4096:
+            _zero_runs.clear()
+        _zero_runs[key] = hit
+    return hit
+
+
+def assemble_png(W: int, H: int, rows, per_row: int, packed, offsets, s0: int, adler) -> list:
+    """The PNG file of one canvas as a list of buffers (the compressed stream is not copied).
+
+    ``rows``: the canvas' content scanlines (ascending); their segments -- ``per_row`` per scanline, numbered
+    from ``s0`` -- are ``packed[offsets[s] : offsets[s + 1]]`` (byte-aligned DEFLATE pieces) with Adler-32
+    partial sums ``adler[s] = (sum of bytes, sum of (n - t) * byte_t)`` of their filtered bytes.  The
+    scanlines in between repeat the line above: :func:`zero_run` pieces."""
+    n_rows_c = len(rows)
+    s1 = s0 + per_row * n_rows_c
+    # filtered bytes per device segment: 4 per pixel, plus the filter-type byte on a line's first segment
+    chunk = np.arange(s1 - s0) % per_row
+    npx = np.minimum(1024, W - 1024 * chunk)
+    seg_len = 4 * npx + (chunk == 0)
+    gap = np.diff(np.concatenate([rows, [H]])) - 1  # repeated lines after every content row
+    line_bytes = 1 + 4 * W
+    has_gap = np.flatnonzero(gap > 0)
+    # Adler-32 pieces in stream order: per content row its segments, then (maybe) a run of Up lines whose
+    # only non-zero bytes are the filter bytes (value 2) at the start of every line
+    n_pieces = (s1 - s0) + len(has_gap)
+    sa, sb, ln = np.zeros(n_pieces, np.int64), np.zeros(n_pieces, np.int64), np.zeros(n_pieces, np.int64)
+    seg_pos = np.arange(s1 - s0) + np.searchsorted(has_gap, np.arange(s1 - s0) // per_row, side="left")
+    sa[seg_pos], sb[seg_pos], ln[seg_pos] = adler[s0:s1, 0], adler[s0:s1, 1], seg_len
+    if len(has_gap):
+        g = gap[has_gap].astype(np.int64)
+        run_pos = (has_gap + 1) * per_row + np.arange(len(has_gap))
+        L = g * line_bytes
+        sa[run_pos] = (2 * g) % _ADLER
+        sb[run_pos] = (2 * (g * L - line_bytes * (g * (g - 1) // 2))) % _ADLER  # sum over lines k of (L - k * line_bytes) * 2
+        ln[run_pos] = L
+    check = adler32_of_segments(sa, sb, ln)
+    pieces: list = []
+    start = 0
+    for r in has_gap.tolist():  # device bytes up to and including content row r, then the run after it
+        end = (r + 1) * per_row
+        pieces.append(memoryview(packed[offsets[s0 + start] : offsets[s0 + end]]))
+        pieces.append(zero_run(W, int(gap[r])))
+        start = end
+    if start < s1 - s0:
+        pieces.append(memoryview(packed[offsets[s0 + start] : offsets[s1]]))
+    head, tail = b"\x78\x01", b"\x01\x00\x00\xff\xff" + struct.pack(">I", check)
+    crc = zlib.crc32(head, zlib.crc32(b"IDAT"))
+    size = len(head) + len(tail)
+    for piece in pieces:
+        crc = zlib.crc32(piece, crc)  # releases the GIL on large buffers
+        size += len(piece)
+    crc = zlib.crc32(tail, crc)
+    ihdr = struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)
+    return [_SIGNATURE + _chunk(b"IHDR", ihdr) + struct.pack(">I", size) + b"IDAT" + head, *pieces,
+            tail + struct.pack(">I", crc & 0xFFFFFFFF) + _chunk(b"IEND", b"")]
+
+
+def _device_tables(figures, dpi):
+    """Tile / canvas / row tables of a list of figures.  Returns ``(canvases, tiles, rows, per_figure)`` with
+    ``canvases`` a list of mutable rows of ``PNG_CANVAS`` (``seg_first`` is filled per group), ``tiles`` one
+    ``PNG_TILE`` array, ``rows`` one int32 array of content rows and ``per_figure`` = [(W, H, content rows)]."""
+    from ._lib import PNG_TILE
+    from .figure import DeviceRaster
 
     def pack(c):
-        r, g, b, a = _rgba(c)
+        r, g, b, a = c
         return r | (g << 8) | (b << 16) | (a << 24)
 
-    canvases, tiles, vlines = [], [], []
+    canvases, tile_parts, row_parts, per_figure = [], [], [], []
+    n_tiles = n_rows = 0
     for fig in figures:
-        H, W, placed = fig.layout(row_height, gap)
-        first = len(tiles)
-        for ax, y, x, rep in placed:
-            ref = ax.images[-1].rgba
-            if not isinstance(ref, DeviceRaster):
+        t = fig.tiles(dpi)
+        for src in t.sources.values():
+            if not isinstance(src, DeviceRaster):
                 raise TypeError("encode_figures_device needs panels drawn from device rasters (figure.DeviceRaster)")
-            v0 = len(vlines)
-            for col, half, colour in ax.marker_columns():
-                vlines.append((col, half, pack(colour), 0))
-            tiles.append((ref.offset, ref.ne, ref.nt, x, y, rep, v0, len(vlines) - v0, 0))
-        if len(tiles) - first > 32:
-            raise ValueError("at most 32 panels per figure")
-        canvases.append([W, H, first, len(tiles) - first, pack(background), 0, (W + 1023) // 1024, 0])
-    return (canvases, np.array(tiles, dtype=PNG_TILE) if tiles else np.zeros(1, PNG_TILE),
-            np.array(vlines, dtype=PNG_VLINE) if vlines else np.zeros(1, PNG_VLINE))
+        table = t.table()
+        rows = t.content_rows(table)
+        canvases.append([t.W, t.H, n_tiles, len(table), pack(t.background), 0, (t.W + 1023) // 1024, n_rows])
+        tile_parts.append(table)
+        row_parts.append(rows)
+        per_figure.append((t.W, t.H, rows))
+        n_tiles += len(table)
+        n_rows += len(rows)
+    tiles = np.concatenate(tile_parts) if n_tiles else np.zeros(1, PNG_TILE)
+    rows = np.concatenate(row_parts) if n_rows else np.zeros(1, np.int32)
+    return canvases, tiles, rows, per_figure
 
 
-def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, gap: int = 8,
-                          background=(255, 255, 255, 255), max_segments: int = 160_000, consume=None,
+def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = None, max_segments: int = 160_000, consume=None,
                           timings: dict | None = None, huffman: str = "custom") -> list[bytes]:
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
     ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
     :class:`figure.DeviceRaster` references into the RGBA buffer at ``d_rgba_ptr`` (a batch's
-    ``d_rgba``).  Same geometry as ``SpectrogramFigure.compose`` (the host oracle).  Figures are
-    processed in groups of at most ``max_segments`` scanline segments (scratch: 4.6 KB each).
+    ``d_rgba``); annotations come from ``overlay.ATLAS``.  Same pixels as ``SpectrogramFigure.compose(dpi)``
+    (the host oracle).  The device encodes the scanlines with new content; the runs of repeated lines in
+    between (a resampled panel shows every raster row several times) are constants spliced in here
+    (:func:`zero_run`).  Figures are processed in groups of at most ``max_segments`` scanline segments
+    (scratch: 4.6 KB each).
 
     ``consume(first_figure_index, parts)``: instead of returning the files, hand every group's files
-    -- each a list of buffers that alias pinned scratch, valid only during the call -- to the caller
-    (``write_figures_device`` writes them straight to disk without assembling them in memory).
+    -- each a list of buffers, some aliasing pinned scratch that is valid only during the call -- to the
+    caller (``write_figures_device`` writes them straight to disk without assembling them in memory).
     ``timings`` (optional dict) accumulates host seconds per phase.  ``huffman``: "custom" fits a
     dynamic-Huffman code to the symbol statistics of the first group of figures (one counting pass of
     the same tokeniser over every 4th scanline segment) and uses it for the whole call; "fixed" uses
@@ -330,10 +406,12 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         return time.perf_counter()
 
     from ._lib import PNG_CANVAS
+    from .overlay import ATLAS
 
     lib = ctx.lib
     figures = list(figures)
-    canvases, tiles, vlines = _device_tables(figures, row_height, gap, background)
+    t0 = time.perf_counter()
+    canvases, tiles, rows, per_figure = _device_tables(figures, dpi)
     slot = int(lib.csg_png_slot_bytes())
     scratch = ctx.__dict__.setdefault("_png_scratch", {})
 
@@ -343,7 +421,11 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
             buf = scratch[name] = ctx.alloc(int(nbytes * 1.2) + 256)
         return buf
 
-    d_tiles, d_vlines = ctx.to_device(tiles), ctx.to_device(vlines)
+    d_tiles, d_rows = ctx.to_device(tiles), ctx.to_device(rows)
+    d_overlay = ATLAS.device_ptr(ctx)
+    d_error = dev("error", 4)
+    d_error.zero()
+    t0 = tick("tile_tables", t0)
     out: list[bytes] = []
     k = 0
     while k < len(figures):
@@ -351,7 +433,7 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         group, n_seg = [], 0
         while k + len(group) < len(figures):
             c = canvases[k + len(group)]
-            segs = int(lib.csg_png_segments(c[0], c[1]))
+            segs = c[6] * len(per_figure[k + len(group)][2])
             if group and n_seg + segs > max_segments:
                 break
             c[5] = n_seg
@@ -365,8 +447,8 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
                 d_counts = dev("counts", 316 * 4)
                 d_counts.zero()
                 ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
-                ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_canvases.ptr, len(group), d_tiles.ptr, d_vlines.ptr,
-                                             n_seg, 4, d_counts.ptr))
+                ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                             d_rows.ptr, n_seg, 4, d_counts.ptr))
                 tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
                 ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
             elif huffman == "fixed":
@@ -375,10 +457,14 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
                 raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
             t0 = tick("code_tables", t0)
         d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
-        ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_canvases.ptr, len(group), d_tiles.ptr, d_vlines.ptr, n_seg,
-                                      d_slots.ptr, d_sizes.ptr, d_adler.ptr))
+        ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                      d_rows.ptr, n_seg, d_slots.ptr, d_sizes.ptr, d_adler.ptr, d_error.ptr))
         sizes = d_sizes.download(np.int32, n_seg, sync=False)
+        bad = d_error.download(np.int32, 1, sync=False)
         adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
+        if bad[0]:
+            raise ValueError(f"figure {k + int(bad[0]) - 1}: more than {int(lib.csg_png_max_segment_tiles())} tiles meet in one "
+                             "1024-pixel scanline segment")
         t0 = tick("encode_kernel_and_sizes", t0)
         offsets = np.zeros(n_seg + 1, dtype=np.int64)
         np.cumsum(sizes, out=offsets[1:])
@@ -395,25 +481,12 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, row_height: int = 148, 
         packed = pin.array
         t0 = tick("compact_and_d2h", t0)
 
-        def frame(c):
-            """The PNG file of one canvas as a list of buffers (the compressed stream is not copied)."""
-            W, H, s0 = c[0], c[1], c[5]
-            s1 = s0 + int(lib.csg_png_segments(W, H))
-            per_row = c[6]
-            # filtered bytes per segment: 4 per pixel, plus the filter-type byte on a line's first segment
-            chunk = np.arange(s1 - s0) % per_row
-            npx = np.minimum(1024, W - 1024 * chunk)
-            lengths = 4 * npx + (chunk == 0)
-            check = adler32_of_segments(adler[s0:s1, 0], adler[s0:s1, 1], lengths)
-            body = memoryview(packed[offsets[s0] : offsets[s1]])
-            head, tail = b"\x78\x01", b"\x01\x00\x00\xff\xff" + struct.pack(">I", check)
-            crc = zlib.crc32(tail, zlib.crc32(body, zlib.crc32(head, zlib.crc32(b"IDAT"))))  # releases the GIL on the body
-            ihdr = struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)
-            return [_SIGNATURE + _chunk(b"IHDR", ihdr) + struct.pack(">I", len(head) + len(body) + len(tail)) + b"IDAT" + head,
-                    body, tail + struct.pack(">I", crc & 0xFFFFFFFF) + _chunk(b"IEND", b"")]
+        def frame(job):
+            c, (W, H, rows_c) = job
+            return assemble_png(W, H, rows_c, c[6], packed, offsets, c[5], adler)
 
         with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
-            parts = list(pool.map(frame, group))
+            parts = list(pool.map(frame, zip(group, per_figure[k : k + len(group)])))
         t0 = tick("framing_crc", t0)
         if consume is not None:
             consume(k, parts)  # the buffers alias pinned scratch that the next group overwrites

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 19
+#define CSG_ABI_VERSION 20
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -433,31 +433,39 @@ CSG_API int csg_peer_disconnect(csg_ctx* ctx, csg_peer* peer);
 CSG_API int csg_peer_destroy(csg_ctx* ctx, csg_peer* peer);
 
 /* --------------------------------------------- K4: figure mosaics -> DEFLATE (PNG hand-off) */
-/* Replaces fig.savefig() of CS/fast/process_orbit.py:98-117 / CS/generic_batch.py:108-113 for
- * figures whose panels are K3 rasters in HBM: the mosaic (figure.SpectrogramFigure.compose) is
- * evaluated per scanline inside the encoder, filtered with PNG filter 2 and written as
- * fixed-Huffman DEFLATE blocks, one per segment (<= 1024 pixels of one scanline), each closed
- * by an empty stored block so that segments concatenate bytewise.  See csrc/png.cu. */
+/* Replaces fig.savefig() of CS/fast/process_orbit.py:98-117 / CS/generic_batch.py:108-113 for figures
+ * whose panels are K3 rasters in HBM.  A canvas is a list of tiles; every tile is a source raster
+ * resampled nearest-neighbour into its rectangle on the canvas -- a K3 panel filling its axes box the way
+ * imshow(aspect="auto") does at display resolution (CS/plotting.py:280-287,606-611; 4800 x 2400 pixels
+ * for the FAST grids, CS/fast/process_orbit.py:110), or a host-drawn annotation sprite (text, tick marks,
+ * frames, colour bars) from the overlay atlas at its own size.  The mosaic
+ * (figure.SpectrogramFigure.compose is its host oracle) is evaluated per scanline inside the encoder and
+ * written as Huffman-coded DEFLATE blocks, one per segment (<= 1024 pixels of one scanline), each closed
+ * by an empty stored block so that segments concatenate bytewise.  Only scanlines with new content are
+ * encoded (d_rows lists them per canvas); runs of repeated lines are constants the host splices in.
+ * See csrc/png.cu. */
 typedef struct {
-  int64_t rgba_off;  /* pixel offset of the panel in d_rgba ([ne][nt], row 0 = lowest energy)   */
-  int32_t ne, nt;
-  int32_t x, y;      /* top-left corner on the canvas                                           */
-  int32_t rep;       /* every raster row is drawn rep times                                      */
-  int32_t vline_first, vline_count; /* cusp lines burnt into this panel (d_vlines)              */
+  int64_t rgba_off;  /* pixel offset of the [ne][nt] source raster in d_rgba (flags bit 0 clear) or d_overlay */
+  int32_t ne, nt;    /* source rows x columns                                                               */
+  int32_t x, y;      /* top-left corner on the canvas                                                        */
+  int32_t w, h;      /* size on the canvas: source index = floor((d + 0.5) * n_src / n_dst), float32         */
+  int32_t vline_first, vline_count; /* cusp lines burnt into this tile (d_vlines)                            */
+  int32_t flags;     /* bit 0: source in the overlay atlas; bit 1: source row 0 is the TOP row (a K3 raster
+                        stores the lowest energy first and is flipped: imshow origin="lower")                */
   int32_t pad;
-} csg_png_tile; /* 40 bytes */
+} csg_png_tile; /* 48 bytes */
 typedef struct {
-  int32_t col, half; /* panel columns col-half .. col+half                                      */
+  int32_t col, half; /* canvas columns col-half .. col+half, relative to the tile's left edge              */
   uint32_t rgba;
   int32_t pad;
 } csg_png_vline; /* 16 bytes */
 typedef struct {
   int32_t W, H;
-  int32_t tile_first, tile_count; /* at most 32 tiles per canvas                                */
+  int32_t tile_first, tile_count; /* first matching tile wins: list annotations before what they cover      */
   uint32_t background;
-  int32_t seg_first;    /* id of the canvas' first segment; segments are numbered row by row    */
-  int32_t segs_per_row; /* ceil(W / 1024)                                                       */
-  int32_t pad;
+  int32_t seg_first;    /* id of the canvas' first segment; segments are numbered listed row by listed row */
+  int32_t segs_per_row; /* ceil(W / 1024)                                                                  */
+  int32_t row_first;    /* index in d_rows of the canvas' first listed scanline                            */
 } csg_png_canvas; /* 32 bytes */
 /* The DEFLATE code of a batch of figures.  Codes are bit-reversed (ready for the LSB-first stream);
  * len_code[n] / dist_code[k] = the Huffman code of a match of 4n bytes / at distance 4k bytes followed
@@ -483,16 +491,20 @@ CSG_API int csg_png_fixed_tables(csg_png_tables* out);                        /*
 CSG_API int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables);  /* NULL: the fixed code   */
 /* Symbol statistics of every stride-th segment: d_counts[286 + 30] (uint32, zeroed by the caller) +=
  * literal / length symbol counts, then distance symbol counts.  Nothing is encoded. */
-CSG_API int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
-                  const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments, int stride,
-                  uint32_t* d_counts);
-CSG_API int32_t csg_png_slot_bytes(void);               /* capacity of one segment's output slot */
-CSG_API int32_t csg_png_segments(int32_t W, int32_t H); /* segments of one canvas                 */
-/* d_slots[n_segments][slot_bytes]: the encoded segments; d_sizes[n_segments]: their byte counts;
- * d_adler[n_segments][2]: (sum of bytes, sum of (n - t) * byte_t) mod 65521 of the filtered bytes. */
-CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const csg_png_canvas* d_canvases, int n_canvases,
-                   const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, int n_segments,
-                   uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler);
+CSG_API int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
+                  int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
+                  int n_segments, int stride, uint32_t* d_counts);
+CSG_API int32_t csg_png_slot_bytes(void);                    /* capacity of one segment's output slot        */
+CSG_API int32_t csg_png_segments(int32_t W, int32_t n_rows); /* segments of n_rows listed scanlines of width W */
+CSG_API int32_t csg_png_max_segment_tiles(void);             /* tiles one segment may intersect               */
+/* d_rows: ascending scanline numbers with new content, canvas after canvas (csg_png_canvas.row_first).
+ * d_slots[n_segments][slot_bytes]: the encoded segments; d_sizes[n_segments]: their byte counts;
+ * d_adler[n_segments][2]: (sum of bytes, sum of (n - t) * byte_t) mod 65521 of the filtered bytes;
+ * d_error (int32, may be NULL, zeroed by the caller): 1 + the canvas in which more than
+ * csg_png_max_segment_tiles() tiles met in one segment (its output is wrong: the host raises). */
+CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
+                   int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
+                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error);
 /* d_packed + d_offsets[s] <- slot s (d_offsets: exclusive prefix sum of d_sizes, from the host). */
 CSG_API int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets,
                     int n_segments, uint8_t* d_packed);

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header_sizes():
     from configurable_spectrograms_b200 import _lib
 
-    sizes = {"csg_pool_item": (_lib.POOL_ITEM, 24), "csg_pool_query": (_lib.POOL_QUERY, 32), "csg_png_tile": (_lib.PNG_TILE, 40),
+    sizes = {"csg_pool_item": (_lib.POOL_ITEM, 24), "csg_pool_query": (_lib.POOL_QUERY, 32), "csg_png_tile": (_lib.PNG_TILE, 48),
              "csg_png_vline": (_lib.PNG_VLINE, 16), "csg_png_canvas": (_lib.PNG_CANVAS, 32), "csg_pool_request": (_lib.POOL_REQUEST, 16),
              "csg_pool_sel": (_lib.POOL_SEL, 64), "csg_cdf_var": (_lib.CDF_VAR, 336)}
     header = open(os.path.join(ROOT, "include", "csgpu.h")).read()

@@ -17,19 +17,41 @@ def ctx():
 
 
 def _twin_figures(rng, flat, specs, grid, lines):
-    """The same figure twice: panels as host arrays, and as references into the device buffer."""
+    """The same figure twice: panels as host arrays, and as references into the device buffer; with the
+    annotations of a real figure (labels, ticks, colour bars, title, footer, cusp lines and brackets)."""
+    from configurable_spectrograms_b200.cusp_marking import draw_cusp_bracket_marker
     from configurable_spectrograms_b200.figure import DeviceRaster, SpectrogramFigure
 
     figs = []
+    n_rows, n_cols = grid
     for device in (False, True):
-        fig = SpectrogramFigure()
-        n_rows, n_cols = grid
+        fig = SpectrogramFigure(figsize=(12 * n_cols, 3 * n_rows))
         for k, (cell, off, ne, nt) in enumerate(specs):
             ax = fig.add_subplot(n_rows, n_cols, cell)
             host = flat[off : off + ne * nt].view(np.uint8).reshape(ne, nt, 4)
-            ax.imshow(DeviceRaster(off, ne, nt) if device else host, extent=(100.0, 100.0 + nt, 0.0, 1.0))
-            for x, width, colour in lines.get(k, []):
-                ax.axvline(x, color=colour, linewidth=width)
+            x0 = 10957.0 + 0.01 * k
+            x1 = x0 + nt * 2.5 / 86400.0
+            ax.set_xlim(x0 - (0.001 if k % 2 else 0.0), x1 + (0.002 if k % 2 else 0.0))  # odd panels: image inside wider limits
+            im = ax.imshow(DeviceRaster(off, ne, nt) if device else host, extent=(x0, x1, 4.0, 4000.0), cmap="turbo",
+                           norm="log" if k % 2 == 0 else None, vmin=1.0, vmax=2400.0)
+            fig.colorbar(im, ax=ax, label="Counts", ticks=[1, 10, 100, 1000] if k % 2 == 0 else None)
+            ax.set_xlabel("Time (UTC)")
+            ax.set_ylabel("Energy (eV)", fontsize=14)
+            ax.set_yticks([0, 1000, 2000, 3000, 4000])
+            ax.set_yticklabels(["0", "1000", "2000", "3000", "4000"])
+            ax.xaxis.set_major_formatter("%H:%M:%S" if nt < 40 else "%H:%M")
+            ax.tick_params(axis="both", which="major", labelsize=11, length=6)
+            if k == 0:
+                ax.set_title("Full", fontsize=14)
+            marks = []
+            for frac, width, colour in lines.get(k, []):
+                marks.append(x0 + frac * (x1 - x0))
+                ax.axvline(marks[-1], color=colour, linewidth=width)
+            if marks:
+                draw_cusp_bracket_marker(ax, marks, caption="cusp")
+        fig.suptitle(f"Orbit 13000 - figure with {len(specs)} panels", fontsize=16)
+        fig.text(0.5, 0.01, "Data timespan: 2000-01-01 00:00:00 to 2000-01-01 00:33:20 UTC", ha="center", va="bottom", fontsize=11)
+        fig.tight_layout(rect=(0, 0.06, 1, 0.95))
         figs.append(fig)
     return figs
 
@@ -56,10 +78,11 @@ def test_device_png_matches_host_compose(ctx):
     d_rgba = ctx.to_device(flat)
     layouts = [
         # (grid, [(cell, panel)], {panel position: [(x, linewidth, colour)]})
-        ((4, 2), [(1, 0), (2, 1), (3, 2), (5, 8), (6, 3), (7, 0)], {0: [(350.0, 1, "black"), (420.5, 4, "red")], 1: [(150.0, 4, "red")]}),
-        ((1, 1), [(1, 5)], {0: [(1599.0, 4, "red"), (100.0, 1, "black")]}),
+        # lines: (fraction of the panel's time span, linewidth in points, colour)
+        ((4, 2), [(1, 0), (2, 1), (3, 2), (5, 8), (6, 3), (7, 0)], {0: [(0.31, 4, "black"), (0.31, 2, "red")], 1: [(0.5, 4, "red")]}),
+        ((1, 1), [(1, 5)], {0: [(1.0, 4, "red"), (0.0, 1, "black")]}),
         ((2, 2), [(1, 4), (4, 6)], {}),
-        ((2, 1), [(1, 7), (2, 2)], {0: [(1124.0, 4, "red"), (1123.0, 1, "black")]}),
+        ((2, 1), [(1, 7), (2, 2)], {0: [(0.53, 4, "red"), (0.53, 1, "black")]}),
         ((1, 1), [], {}),
     ]
     host_figs, dev_figs = [], []
@@ -68,11 +91,11 @@ def test_device_png_matches_host_compose(ctx):
         h, d = _twin_figures(rng, flat, specs, grid, lines)
         host_figs.append(h)
         dev_figs.append(d)
-    for budget in (160_000, 700):  # one group, then several groups of figures
-        blobs = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, max_segments=budget)
+    for budget, dpi in ((160_000, 100), (700, 100), (160_000, 200), (160_000, 37)):  # one group / several groups; three resolutions
+        blobs = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, max_segments=budget, dpi=dpi)
         assert len(blobs) == len(host_figs)
         for blob, fig in zip(blobs, host_figs):
-            want = fig.compose()
+            want = fig.compose(dpi)
             got = png.decode_rgba(blob)
             assert got.shape == want.shape
             assert np.array_equal(got, want)
@@ -81,9 +104,10 @@ def test_device_png_matches_host_compose(ctx):
 
     for blob, fig in zip(blobs, host_figs):
         im = np.asarray(Image.open(io.BytesIO(blob)).convert("RGBA"))
-        assert np.array_equal(im, fig.compose())
-    # compression: flat / repeated content shrinks, noise cannot expand much
+        assert np.array_equal(im, fig.compose(37))
+    # compression at display resolution: repeated lines and stretched cells shrink a lot
+    blobs = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, dpi=200)
     sizes = [len(b) for b in blobs]
-    raws = [f.compose().nbytes for f in host_figs]
-    assert sizes[0] < 0.7 * raws[0]
-    assert all(s < 1.16 * r + 200 for s, r in zip(sizes, raws))
+    raws = [f.compose(200).nbytes for f in host_figs]
+    assert sizes[0] < 0.2 * raws[0]
+    assert all(s < 0.5 * r + 2000 for s, r in zip(sizes, raws))

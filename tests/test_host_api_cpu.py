@@ -24,6 +24,10 @@ def test_png_round_trip(tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "0.png")), img)
 
 
+def _raster_tiles(tiles):
+    return [(tiles.records[k], src) for k, src in sorted(tiles.sources.items())]
+
+
 def test_figure_compose_and_markers():
     from configurable_spectrograms_b200.cusp_marking import draw_cusp_both_markers, draw_cusp_bracket_marker
     from configurable_spectrograms_b200.figure import FigureCanvas, SpectrogramFigure, close_all_axes_and_clear
@@ -34,19 +38,31 @@ def test_figure_compose_and_markers():
     axes = [fig.add_subplot(2, 2, k + 1) for k in range(4)]
     for k, ax in enumerate(axes[:3]):
         rgba = np.full((5, 20 + 10 * k, 4), 40 * (k + 1), dtype=np.uint8)
-        rgba[0] = 255  # lowest energy row: must end up at the bottom of the image
-        ax.imshow(rgba, extent=(0.0, 1.0, 4.0, 4000.0), vmin=1.0, vmax=10.0)
+        rgba[0] = (255, 0, 255, 255)  # lowest energy row: must end up at the bottom of the image
+        im = ax.imshow(rgba, extent=(0.0, 1.0, 4.0, 4000.0), vmin=1.0, vmax=10.0, cmap="viridis")
         ax.set_xlim(0.0, 1.0)
+        ax.set_ylabel("Energy (eV)")
+        fig.colorbar(im, ax=ax, label="Counts")
     artists = draw_cusp_both_markers(axes[0], [0.25, 0.75], line_color="white")
     assert len(artists) == 5  # two lines per position + the bracket
     assert draw_cusp_bracket_marker(axes[0], []) == []
     one = draw_cusp_bracket_marker(axes[1], [0.5], caption="cusp")
     assert len(one) == 2 and axes[1].texts[-1]["text"] == "cusp"
-    img = fig.compose(row_height=20, gap=2)
-    assert img.shape[2] == 4 and img.dtype == np.uint8
-    panel = axes[0].render()
-    assert (panel[-1, 0] == 255).all() and panel.shape == (5, 20, 4)
-    assert (panel[:, round(0.25 * 19)] == (255, 255, 255, 255)).all()  # the white cusp line on top of the black one
+    fig.suptitle("a title")
+    img = fig.compose(dpi=50)
+    assert img.shape == (300, 1200, 4) and img.dtype == np.uint8
+    tiles = fig.tiles(50)
+    rasters = _raster_tiles(tiles)
+    assert len(rasters) == 3  # the fourth subplot holds no image
+    (_off, ne, nt, x, y, w, h, *_rest), _src = rasters[0]
+    assert (ne, nt) == (5, 20) and w > 100 and h > 30  # stretched over the axes box (imshow aspect="auto")
+    assert (img[y + h - 1, x + 1] == (255, 0, 255, 255)).all() and (img[y, x + 1] == (40, 40, 40, 40)).all()
+    line_x = x + round(0.25 * w)
+    near = img[y + h // 2, line_x - 3 : line_x + 4]
+    assert (near == (255, 255, 255, 255)).all(axis=1).any()  # the white cusp line on top of the black one ...
+    assert (near == (0, 0, 0, 255)).all(axis=1).any()  # ... whose wider stroke shows on both sides
+    assert (img[y + h + 2 : y + h + 30, x - 2 : x + w + 2] != 255).any()  # the bracket below the axis
+    assert (img[:12] != 255).any()  # the title
     close_all_axes_and_clear(fig)
     assert fig.axes == []
 
@@ -115,25 +131,74 @@ def test_png_up_filter_decode_and_adler_of_segments():
 
 
 def test_figure_layout_serves_host_and_device_rasters():
-    from configurable_spectrograms_b200.figure import DeviceRaster, SpectrogramFigure
+    from configurable_spectrograms_b200.figure import DeviceRaster, SpectrogramFigure, nearest_index
 
     rng = np.random.default_rng(2)
     shapes = [(74, 300), (74, 90), (30, 300)]
     figs = []
     for device in (False, True):
-        fig = SpectrogramFigure()
+        fig = SpectrogramFigure(figsize=(12, 6))
         for cell, (ne, nt) in zip((1, 2, 3), shapes):
             ax = fig.add_subplot(2, 2, cell)
-            ax.imshow(DeviceRaster(0, ne, nt) if device else rng.integers(0, 255, (ne, nt, 4), dtype=np.uint8),
+            ax.imshow(DeviceRaster(16 * cell, ne, nt) if device else rng.integers(0, 255, (ne, nt, 4), dtype=np.uint8),
                       extent=(0.0, float(nt), 0.0, 1.0))
+            ax.set_xlim(0.0, float(nt))
             ax.axvline(12.0, color="red", linewidth=4)
         figs.append(fig)
-    (H0, W0, p0), (H1, W1, p1) = figs[0].layout(), figs[1].layout()
-    assert (H0, W0) == (H1, W1) == figs[0].compose().shape[:2]
-    assert [(y, x, rep) for _a, y, x, rep in p0] == [(y, x, rep) for _a, y, x, rep in p1]
-    assert figs[0].axes[0].marker_columns() == figs[1].axes[0].marker_columns()
+    t0, t1 = figs[0].tiles(100), figs[1].tiles(100)
+    assert (t0.W, t0.H) == (t1.W, t1.H) == (1200, 600) == figs[0].compose(100).shape[1::-1]
+    assert [r[1:] for r in t0.records] == [r[1:] for r in t1.records]  # same geometry; only the raster offsets differ
+    assert [rec[0] for rec, _s in _raster_tiles(t1)] == [16, 32, 48]
     with pytest.raises(TypeError):
         figs[1].compose()
+    # nearest neighbour on pixel centres, float32 like the device: identity at 1:1, whole repeats at k:1
+    assert np.array_equal(nearest_index(7, 7), np.arange(7)) and np.array_equal(nearest_index(12, 4), np.repeat(np.arange(4), 3))
+    rows = t0.content_rows()
+    assert rows[0] == 0 and np.all(np.diff(rows) > 0) and rows[-1] < t0.H
+
+
+def test_png_assembly_splices_repeated_lines():
+    """``png.assemble_png``: content scanlines come as byte-aligned DEFLATE pieces (here from zlib, standing in
+    for the device's segments), the runs of repeated lines in between are ``png.zero_run`` constants; the file
+    decodes (own decoder and Pillow: Adler-32 and CRC verified) to the composed image."""
+    import io
+    import zlib
+
+    from PIL import Image
+
+    from configurable_spectrograms_b200 import png
+    from configurable_spectrograms_b200.figure import SpectrogramFigure
+
+    rng = np.random.default_rng(4)
+    fig = SpectrogramFigure(figsize=(26, 4))
+    for cell, nt in ((1, 300), (2, 41)):
+        ax = fig.add_subplot(1, 2, cell)
+        im = ax.imshow(rng.integers(0, 255, (9, nt, 4), dtype=np.uint8), extent=(0.0, 1.0, 4.0, 4000.0), cmap="turbo", vmin=1.0, vmax=9.0)
+        ax.set_xlim(0.0, 1.0)
+        ax.set_xlabel("Time (UTC)")
+        fig.colorbar(im, ax=ax, label="Counts")
+    tiles = fig.tiles(100)
+    img, rows = fig.compose(100), tiles.content_rows()
+    W, H = tiles.W, tiles.H
+    assert W > 2048 and 0 < len(rows) < H  # three segments per scanline, and some lines repeat
+    for r in range(1, H):  # every line that is not listed repeats the one above
+        if r not in set(rows.tolist()):
+            assert np.array_equal(img[r], img[r - 1]), r
+    per_row = (W + 1023) // 1024
+    segs, adler = [], []
+    for r in rows:
+        line = img[r].reshape(-1)
+        for c in range(per_row):
+            raw = (b"\x00" if c == 0 else b"") + line[4096 * c : 4096 * (c + 1)].tobytes()
+            comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+            segs.append(comp.compress(raw) + comp.flush(zlib.Z_SYNC_FLUSH))
+            b = np.frombuffer(raw, np.uint8).astype(np.int64)
+            adler.append((int(b.sum() % 65521), int((b * (len(b) - np.arange(len(b)))).sum() % 65521)))
+    packed = np.frombuffer(b"".join(segs), np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(x) for x in segs])])
+    blob = b"".join(bytes(p) for p in png.assemble_png(W, H, rows, per_row, packed, offsets, 0, np.array(adler, dtype=np.uint32)))
+    assert np.array_equal(png.decode_rgba(blob), img)
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(blob)).convert("RGBA")), img)
 
 
 def test_png_custom_huffman_tables_decode_with_zlib():
