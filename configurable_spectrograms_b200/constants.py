@@ -12,10 +12,10 @@ from .engine import nansum as COLLAPSE_FUNCTION  # (cube, axis=1) -> 2-D sums, b
 CDF_DATA_DIRECTORY, CDF_VARIABLE_NAMES = "./FAST_data/", ["time_unix", "data", "energy", "pitch_angle"]
 
 # colormap per (y scale, z scale) combination
-_COLORMAPS = {("LINEAR", "LINEAR"): "viridis", ("LINEAR", "LOG"): "cividis", ("LOG", "LINEAR"): "plasma", ("LOG", "LOG"): "inferno"}
-for (_y, _z), _name in _COLORMAPS.items():
-    globals()[f"COLORMAP_{_y}_Y_{_z}_Z"] = _name
-del _y, _z, _name
+COLORMAP_LINEAR_Y_LINEAR_Z = "viridis"
+COLORMAP_LINEAR_Y_LOG_Z = "cividis"
+COLORMAP_LOG_Y_LINEAR_Z = "plasma"
+COLORMAP_LOG_Y_LOG_Z = "inferno"
 
 # figure geometry and fonts of the single-panel plot (inches / points), default zoom window (minutes)
 PLOT_FIGURE_WIDTH_INCHES, PLOT_FIGURE_HEIGHT_INCHES = 6.25, 2.0

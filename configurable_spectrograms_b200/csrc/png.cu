@@ -59,17 +59,19 @@ struct SegTile {
   const uint32_t* row;          // first pixel of the source row this scanline shows
   float xs;                     // source columns per canvas pixel
   int vline_first;
+  int nt_minus_1;               // last source column (the nearest-neighbour index is clamped to it)
   unsigned short x0, x1;        // canvas columns [x0, x1) inside the segment's range (canvases are < 65536 wide)
   unsigned short tx;            // the tile's left edge on the canvas
-  unsigned short nt_minus_1;    // last source column (the nearest-neighbour index is clamped to it)
-  unsigned short vline_count, pad;
+  unsigned short vline_count;
+  int pad;
 };                              // 32 bytes
 constexpr int kSegTiles = 48;   // tiles one 1024-pixel segment may intersect on one scanline (the device flags more)
 // dynamic shared memory of png_encode_kernel: symbol counts | pixels / merged stream | lane token buffers | tile lists
 constexpr size_t kOffPix = (size_t)kWarpsPerBlock * (286 + 30) * sizeof(unsigned);
 constexpr size_t kOffTok = kOffPix + (size_t)kWarpsPerBlock * kMergedWords * sizeof(unsigned);
 constexpr size_t kOffSeg = (kOffTok + (size_t)kWarpsPerBlock * kPieces * kTokWords * sizeof(unsigned) + 15) / 16 * 16;
-constexpr size_t kEncodeSmem = kOffSeg + (size_t)kWarpsPerBlock * 2 * kSegTiles * 32;
+constexpr size_t kEncodeSmem = kOffSeg + (size_t)kWarpsPerBlock * 2 * kSegTiles * sizeof(SegTile);
+static_assert(sizeof(SegTile) == 32, "SegTile layout");
 
 // source index of destination pixel d (0-based) of `n_dst`, nearest neighbour, pixel centres:
 // floor((d + 0.5) * n_src / n_dst) in float32 -- figure.py evaluates the same float32 expression
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
           const int src_row = (t.flags & 2) ? r_top : t.ne - 1 - r_top;  // rasters store the lowest energy first
           SegTile e;
           e.x0 = (unsigned short)max(t.x, x0), e.x1 = (unsigned short)min(t.x + t.w, x0 + npx);
-          e.tx = (unsigned short)t.x, e.nt_minus_1 = (unsigned short)(t.nt - 1);
+          e.tx = (unsigned short)t.x, e.nt_minus_1 = t.nt - 1;
           e.xs = __fdiv_rn((float)t.nt, (float)t.w);
           e.vline_first = t.vline_first, e.vline_count = (unsigned short)t.vline_count, e.pad = 0;
           e.row = ((t.flags & 1) ? overlay : rgba) + t.rgba_off + (long long)src_row * t.nt;

@@ -1,32 +1,27 @@
 """FAST-specific configuration surface.
 
 The names and values are the reference's (``fast/constants.py:11-41``) because user code and the
-mirrored entry points import them; here they are derived from three small tables -- where the FAST
-batch keeps its files, which colormap goes with which axis scaling, and how the 64 pitch-angle bins
-are grouped -- so the grouping can also be handed to the GPU collapse as membership bits
-(``pipeline.pitch_angle_bits``).
+mirrored entry points import them.  The pitch-angle grouping is kept as one table of (name, closed
+degree intervals) from which both the reference's dict and the row order are derived, so it can also be
+handed to the GPU collapse as membership bits (``pipeline.pitch_angle_bits``).
 """
 
 from .. import constants as _generic
 
 # ---- where the FAST batch reads and writes (all relative to the working directory)
-_FILES = {
-    "FAST_CDF_DATA_FOLDER_PATH": "FAST_data/",
-    "FAST_OUTPUT_BASE": "FAST_plots/",
-    "FAST_FILTERED_ORBITS_CSV_PATH": "FAST_Cusp_Indices.csv",
-    "FAST_EXTREMA_JSON_PATH": "FAST_calculated_extrema.json",
-    "FAST_PLOTTING_PROGRESS_JSON": "batch_multi_plot_FAST_progress.json",
-    "FAST_LOGFILE_PREFIX": "batch_multi_plot_FAST_log",
-    "FAST_LOGFILE_DATETIME_MARKER_PATH": "batch_multi_plot_FAST_logfile_datetime.txt",
-}
-globals().update({name: "./" + tail for name, tail in _FILES.items()})
+FAST_CDF_DATA_FOLDER_PATH = "./FAST_data/"
+FAST_OUTPUT_BASE = "./FAST_plots/"
+FAST_FILTERED_ORBITS_CSV_PATH = "./FAST_Cusp_Indices.csv"
+FAST_EXTREMA_JSON_PATH = "./FAST_calculated_extrema.json"
+FAST_PLOTTING_PROGRESS_JSON = "./batch_multi_plot_FAST_progress.json"
+FAST_LOGFILE_PREFIX = "./batch_multi_plot_FAST_log"
+FAST_LOGFILE_DATETIME_MARKER_PATH = "./batch_multi_plot_FAST_logfile_datetime.txt"
 
-# ---- one colormap per (y scale, z scale): aliases of the generic table
-for _y in ("LINEAR", "LOG"):
-    for _z in ("LINEAR", "LOG"):
-        globals()[f"COLORMAP_{_y}_Y_{_z}_Z"] = getattr(_generic, f"COLORMAP_{_y}_Y_{_z}_Z")
-        globals()[f"DEFAULT_COLORMAP_{_y}_Y_{_z}_Z"] = getattr(_generic, f"COLORMAP_{_y}_Y_{_z}_Z")
-del _y, _z
+# ---- one colormap per (y scale, z scale): the generic table under both of the reference's names
+COLORMAP_LINEAR_Y_LINEAR_Z = DEFAULT_COLORMAP_LINEAR_Y_LINEAR_Z = _generic.COLORMAP_LINEAR_Y_LINEAR_Z
+COLORMAP_LINEAR_Y_LOG_Z = DEFAULT_COLORMAP_LINEAR_Y_LOG_Z = _generic.COLORMAP_LINEAR_Y_LOG_Z
+COLORMAP_LOG_Y_LINEAR_Z = DEFAULT_COLORMAP_LOG_Y_LINEAR_Z = _generic.COLORMAP_LOG_Y_LINEAR_Z
+COLORMAP_LOG_Y_LOG_Z = DEFAULT_COLORMAP_LOG_Y_LOG_Z = _generic.COLORMAP_LOG_Y_LOG_Z
 
 FAST_COLLAPSE_FUNCTION = _generic.COLLAPSE_FUNCTION  # the GPU nansum (engine.nansum)
 COLLAPSE_FUNCTION = _generic.COLLAPSE_FUNCTION

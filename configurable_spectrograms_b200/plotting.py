@@ -27,6 +27,7 @@ from .figure import FigureCanvas, SpectrogramFigure, close_all_axes_and_clear
 from .logging_utils import log_message
 
 __all__ = [
+    "SpectrogramGroup",
     "make_spectrogram",
     "generic_plot_spectrogram_set",
     "generic_plot_multirow_optional_zoom",
@@ -112,6 +113,7 @@ def make_spectrogram(
     cusp_marker_style="both",
     cusp_marker_kwargs=None,
     _context=None,
+    _group=None,
 ):
     """Plot a spectrogram by collapsing a 3-D array along an axis (reference ``:92-389``).
 
@@ -180,41 +182,109 @@ def make_spectrogram(
         return None, None
 
     # ---- the numeric path on the GPU: K1 collapse, K2a bounds, K3 norm + colormap
+    log_scale = z_axis_scale_function == "log"
+    annotate = dict(x_label=x_label, x_axis_is_unix=x_axis_is_unix, y_axis_scale_function=y_axis_scale_function,
+                    y_axis_label=y_axis_label, y_axis_min=y_axis_min, y_axis_max=y_axis_max, z_axis_label=z_axis_label,
+                    colormap=colormap, instrument_label=instrument_label, vertical_lines_unix=vertical_lines_unix,
+                    cusp_marker_style=cusp_marker_style, cusp_marker_kwargs=cusp_marker_kwargs)
+    if _group is not None:  # planned now, computed with every other panel of the group, drawn by group.run()
+        _group.plan(cube, keep, rows, log_scale, z_axis_min, z_axis_max, axis_object, x_axis_plot, y_kept, annotate)
+        return axis_object, x_axis_plot
     ctx = _context or _lib.default_context()
     batch = Batch(ctx, cube.dtype, n_groups=0)
     f = batch.add_file(cube)
     batch.upload_cubes()
     batch.collapse()
-    log_scale = z_axis_scale_function == "log"
     region = batch.add_region(f, 0, keep, rows=rows, want_pct=z_axis_min is None or z_axis_max is None)
     panel = batch.add_panel(region, -1, log_scale, z_axis_min, z_axis_max)
     batch.upload_tables()
     batch.run_stats()
     batch.prepare()
-    lut = get_lut(colormap)
-    batch.set_lut(lut)
+    batch.set_lut(get_lut(colormap))
     batch.rasterise(want_rgba=True, want_index=True)
-    norm = batch.norms()[panel]
-    st = int(norm["status"])
-    if st == _lib.NORM_VMIN_GT_VMAX:  # what matplotlib raises when the figure is drawn
+    z_lo, z_hi = _resolved_bounds(batch.norms()[panel], batch.stats()[region] if log_scale else None, log_scale)
+    draw_panel(axis_object, batch.panel_rgba(panel), batch.panel_index(panel), z_lo, z_hi, log_scale, x_axis_plot, y_kept, **annotate)
+    return axis_object, x_axis_plot
+
+
+def _resolved_bounds(norm, stats, log_scale):
+    """``(vmin, vmax)`` of a panel's resolved normalisation; raises what matplotlib raises when the figure is
+    drawn with an invalid one, and logs the reference's warning for a log panel that holds non-positive cells
+    (``:264-275``)."""
+    status = int(norm["status"])
+    if status == _lib.NORM_VMIN_GT_VMAX:
         raise ValueError("vmin must be less or equal to vmax")
-    if st == _lib.NORM_INVALID:
+    if status == _lib.NORM_INVALID:
         raise ValueError("Invalid vmin or vmax")
     z_lo, z_hi = float(norm["vmin"]), float(norm["vmax"])
-    if log_scale:
-        stats = batch.stats()[region]
+    if log_scale and stats is not None:
         if stats["n_pos"] < stats["n_valid"] + stats["n_nan"] or not (np.isfinite(z_lo) and z_hi > z_lo > 0):
-            log_message(
-                "[WARNING] Non-positive values found in matrix for log colorbar. "
-                "Masking to z_axis_min and enforcing log scale."
-            )
-    rgba, index = batch.panel_rgba(panel), batch.panel_index(panel)
-    draw_panel(axis_object, rgba, index, z_lo, z_hi, log_scale, x_axis_plot, y_kept, x_label=x_label,
-               x_axis_is_unix=x_axis_is_unix, y_axis_scale_function=y_axis_scale_function, y_axis_label=y_axis_label,
-               y_axis_min=y_axis_min, y_axis_max=y_axis_max, z_axis_label=z_axis_label, colormap=colormap,
-               instrument_label=instrument_label, vertical_lines_unix=vertical_lines_unix,
-               cusp_marker_style=cusp_marker_style, cusp_marker_kwargs=cusp_marker_kwargs)
-    return axis_object, x_axis_plot
+            log_message("[WARNING] Non-positive values found in matrix for log colorbar. "
+                        "Masking to z_axis_min and enforcing log scale.")
+    return z_lo, z_hi
+
+
+class SpectrogramGroup:
+    """Many ``make_spectrogram`` calls, one pass over the GPU.
+
+    The reference draws every generic item in its own worker process (``generic_batch.py:90-118``); one call
+    here costs a handful of kernel launches that leave a B200 idle.  A group collects the panels of many
+    figures instead -- every cube is uploaded and collapsed as it is planned (streaming:
+    ``Batch.collapse_pending``; the host array is not kept) -- then :meth:`run` selects every panel's
+    percentiles in ONE K2a launch, rasterises them in ONE K3 launch and finishes the axes from device
+    rasters, so the figures go to ``png.write_figures_device`` without a pixel crossing PCIe uncompressed.
+    One batch per cube dtype (numpy computes each cube in its own dtype)."""
+
+    def __init__(self, colormap="viridis", context=None):
+        self.ctx = context or _lib.default_context()
+        self.colormap = colormap
+        self.batches: dict = {}
+        self.pending: list = []
+
+    def plan(self, cube, keep, rows, log_scale, z_min, z_max, axis_object, x_axis_plot, y_kept, annotate):
+        batch = self.batches.get(cube.dtype)
+        if batch is None:
+            batch = self.batches[cube.dtype] = Batch(self.ctx, cube.dtype, n_groups=0)
+        f = batch.add_file(cube)
+        batch.collapse_pending()
+        region = batch.add_region(f, 0, keep, rows=rows, want_pct=z_min is None or z_max is None)
+        panel = batch.add_panel(region, -1, log_scale, z_min, z_max)
+        self.pending.append((batch, region, panel, log_scale, axis_object, x_axis_plot, y_kept, annotate))
+
+    def run(self) -> list:
+        """Compute and draw everything planned so far.  Returns one entry per planned panel: ``None``, or the
+        exception drawing it raised (an invalid normalisation) -- the caller decides which figure that fails."""
+        from .figure import DeviceRaster
+
+        lut = get_lut(self.colormap)
+        for batch in self.batches.values():
+            batch.upload_tables()
+            batch.run_stats()
+            batch.prepare()
+            batch.set_lut(lut)
+            batch.rasterise(want_rgba=True, want_index=False)
+        tables = {id(b): (b.norms(), b.stats()) for b in self.batches.values()}
+        outcome = []
+        for batch, region, panel, log_scale, axis_object, x_axis_plot, y_kept, annotate in self.pending:
+            norms, stats = tables[id(batch)]
+            try:
+                z_lo, z_hi = _resolved_bounds(norms[panel], stats[region] if log_scale else None, log_scale)
+                ne, nt = batch.panel_shape(panel)
+                draw_panel(axis_object, DeviceRaster(batch._panels[panel][6], ne, nt), None, z_lo, z_hi, log_scale, x_axis_plot,
+                           y_kept, **annotate)
+                axis_object.images[-1].batch = batch  # which RGBA buffer the raster lives in
+                outcome.append(None)
+            except ValueError as exc:
+                outcome.append(exc)
+        self.pending = []
+        return outcome
+
+    def rgba_ptr(self, figure) -> int:
+        """Device address of the RGBA buffer a figure's panels live in (one dtype per figure)."""
+        owners = {id(ax.images[-1].batch): ax.images[-1].batch for ax in figure.axes if ax.images and hasattr(ax.images[-1], "batch")}
+        if len(owners) != 1:
+            raise ValueError("a figure drawn from a group must hold panels of one cube dtype")
+        return next(iter(owners.values())).d_rgba.ptr
 
 
 def _decade_ticks(z_lo, z_hi):
@@ -298,6 +368,7 @@ def generic_plot_spectrogram_set(
     z_max=None,
     cusp_marker_style="both",
     cusp_marker_kwargs=None,
+    _group=None,
 ):
     """A vertical stack of generic spectrograms (reference ``:392-502``): one ``make_spectrogram``
     per dataset dict (required keys ``x, y, data``; optional ``label, y_label, z_label, x_label,
@@ -333,6 +404,7 @@ def generic_plot_spectrogram_set(
             cusp_marker_style=cusp_marker_style,
             cusp_marker_kwargs=cusp_marker_kwargs,
             axis_object=axis_obj,
+            _group=_group,
         )
         if dataset.get("label"):
             axis_obj.set_title(dataset["label"])

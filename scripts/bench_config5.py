@@ -52,6 +52,46 @@ def main():
         out[name] = {"ms": float(np.mean(ms)), "gb_per_s": bytes_ / (np.mean(ms) * 1e-3) / 1e9, "bit_exact_vs_numpy_first_2000_rows": exact,
                      "kernel": "stream" if any(k[1] == _lib.K1_STREAM for k in b.d_files) else "generic/tep"}
         del b, src
+    # ---- the same cubes through the public API: generic_batch_plot (reference generic_batch.py:15-129), the
+    # items of a group sharing one K2a / K3 pass, figures at 150 dpi written as PNG files
+    import shutil
+    import tempfile
+    import time
+
+    from configurable_spectrograms_b200.generic_batch import generic_batch_plot
+
+    n_items = int(os.environ.get("CONFIG5_ITEMS", "4"))
+    host_cubes = []
+    for k in range(n_items):  # host arrays, as a user's build_datasets_fn would hand them over
+        c = cube.cpu().numpy().copy()
+        c[k :: n_items] += np.float32(k)  # the items differ
+        host_cubes.append(c)
+    del cube
+    torch.cuda.empty_cache()
+    times = 946684800.0 + 0.02 * np.arange(T)
+    energy = np.geomspace(4.0, 30000.0, E)[::-1].astype(np.float32)
+
+    def build(item):
+        return [{"x": times, "y": energy, "data": host_cubes[item], "label": f"cube {item}", "y_max": 4000}]
+
+    work = tempfile.mkdtemp(prefix="config5_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        api = {}
+        for label in ("cold", "warm"):
+            shutil.rmtree(os.path.join(work, "out"), ignore_errors=True)
+            t0 = time.perf_counter()
+            res = generic_batch_plot(list(range(n_items)), os.path.join(work, "out"), build, y_scale="linear", z_scale="log",
+                                     colormap="viridis", max_workers=4, progress_json_path=os.path.join(work, f"p_{label}.json"),
+                                     install_signal_handlers=False)
+            sec = time.perf_counter() - t0
+            pngs = sum(len(fs) for _d, _s, fs in os.walk(os.path.join(work, "out")))
+            api[label] = {"seconds": sec, "items_per_s": n_items / sec, "input_gb_per_s": n_items * 4 * T * P * E / sec / 1e9,
+                          "statuses": sorted({st for _i, st in res}), "pngs": pngs}
+        out["generic_batch_plot"] = {"items": n_items, "cube_gb": 4 * T * P * E / 1e9, **api,
+                                     "note": "host cubes (pageable numpy, as the reference's build_datasets_fn returns them) -> "
+                                             "H2D + K1 per item, one K2a + K3 + K4 pass per group, generic.png per item; wall clock"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
     print(json.dumps({"workload": "config5 generic stress cube (100000, 96, 64) float32, 2.46 GB", **out}))
 
 

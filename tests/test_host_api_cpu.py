@@ -266,3 +266,30 @@ def test_png_custom_huffman_tables_decode_with_zlib():
         put(0, 3)
         stream = acc[0].to_bytes((acc[1] + 7) // 8, "little") + b"\x00\x00\xff\xff" + b"\x01\x00\x00\xff\xff"
         assert zlib.decompress(stream, -15) == b"\x00" + b"".join(int(x).to_bytes(4, "little") for x in pix)
+
+
+def test_grouped_executor_serves_run_batch(tmp_path):
+    """``generic_batch.GroupedExecutor`` under ``run_batch``: items are handed over in groups, every item
+    still gets its own future / status / progress entry, a failing group fails its items only."""
+    from configurable_spectrograms_b200.batch_runner import run_batch
+    from configurable_spectrograms_b200.generic_batch import GroupedExecutor
+
+    groups = []
+
+    def process(items):
+        groups.append(list(items))
+        if "boom" in items:
+            raise RuntimeError("group machinery failed")
+        return [(item, "no_data" if item == "empty" else "ok") for item in items]
+
+    items = [f"i{k}" for k in range(7)] + ["empty"]
+    path = tmp_path / "progress.json"
+    res = run_batch(items, None, functools.partial(GroupedExecutor, process, 3), progress_json_path=str(path),
+                    install_signal_handlers=False)
+    assert sorted(res) == sorted([(f"i{k}", "ok") for k in range(7)] + [("empty", "no_data")])
+    assert [x for g in groups for x in g] == items and max(len(g) for g in groups) <= 3
+    state = json.loads(path.read_text())
+    assert sorted(state["completed_items"]) == sorted(repr(f"i{k}") for k in range(7)) and state["no_data"] == [repr("empty")]
+    res = run_batch(["a", "boom", "b"], None, functools.partial(GroupedExecutor, process, 8), progress_json_path=None,
+                    install_signal_handlers=False)
+    assert sorted(res) == [("a", "error"), ("b", "error"), ("boom", "error")]
