@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
 LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 20
+ABI_VERSION = 21
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -121,6 +121,8 @@ PNG_TILE = np.dtype(
      ("vline_first", "<i4"), ("vline_count", "<i4"), ("flags", "<i4"), ("pad", "<i4")], align=True
 )
 TILE_OVERLAY, TILE_TOP_ORIGIN = 1, 2
+PNG_ZERO_SEGMENT = np.dtype([("n_raw", "<i4"), ("len", "<i4"), ("bytes", "u1", (56,))], align=True)
+assert PNG_ZERO_SEGMENT.itemsize == 64
 PNG_VLINE = np.dtype([("col", "<i4"), ("half", "<i4"), ("rgba", "<u4"), ("pad", "<i4")], align=True)
 PNG_CANVAS = np.dtype(
     [("W", "<i4"), ("H", "<i4"), ("tile_first", "<i4"), ("tile_count", "<i4"), ("background", "<u4"),
@@ -199,11 +201,11 @@ SIGNATURES = {
     "csg_pool_reduce_max": (_i, [_vp, _vp, _i, _i, _vp]),
     "csg_png_fixed_tables": (_i, [_vp]),
     "csg_png_set_tables": (_i, [_vp, _vp]),
-    "csg_png_count": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "csg_png_count": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
     "csg_png_max_segment_tiles": (C.c_int32, []),
     "csg_png_slot_bytes": (C.c_int32, []),
     "csg_png_segments": (C.c_int32, [C.c_int32, C.c_int32]),
-    "csg_png_encode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "csg_png_encode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "csg_png_compact": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "csg_peer_create": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
     "csg_peer_mailbox": (_vp, [_vp]),

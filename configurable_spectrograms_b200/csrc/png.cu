@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
                       const csg_png_canvas* __restrict__ canvases, int n_canvases, const csg_png_tile* __restrict__ tiles,
                       const csg_png_vline* __restrict__ vlines, const int32_t* __restrict__ rows, int n_segments,
                       unsigned char* __restrict__ slots, int slot_bytes, int32_t* __restrict__ sizes,
-                      uint32_t* __restrict__ adler, unsigned* __restrict__ counts, int count_stride, int* __restrict__ error) {
+                      uint32_t* __restrict__ adler, unsigned* __restrict__ counts, int count_stride, int* __restrict__ error,
+                      const csg_png_zero_segment* __restrict__ zero_table, int n_zero) {
   // counts != NULL: no output, only the symbol statistics of every count_stride-th segment
   // (literal / length symbols 0..285, then distance symbols 0..29) for the host's custom code
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -184,10 +185,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   // ---- phase 1: compose + Up filter (coalesced), Adler partial sums
   unsigned* pix = s_pix[warp];
   unsigned long long sa = 0, sb = 0;
+  unsigned nonzero = 0;
   for (int p = lane; p < npx; p += 32) {
     const unsigned cur = mosaic_pixel(list, n_list, vlines, x0 + p, cv.background);
     const unsigned f = filter_type ? sub4(cur, mosaic_pixel(list_up, n_up, vlines, x0 + p, cv.background)) : cur;
     pix[(p >> 5) * kPixStride + (p & 31)] = f;
+    nonzero |= f;
     const unsigned b0 = f & 255u, b1 = (f >> 8) & 255u, b2 = (f >> 16) & 255u, b3 = f >> 24;
     const unsigned t0 = (has_filter ? 1u : 0u) + 4u * (unsigned)p;  // position of b0 inside the segment
     sa += b0 + b1 + b2 + b3;
@@ -201,6 +204,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     sb += __shfl_xor_sync(0xffffffffu, sb, o);
   }
   __syncwarp();
+  // A segment that only repeats the line above -- all zeros after the Up filter: most segments of a scanline
+  // on which just one colour bar or one label moved on -- is a constant of its length: the host supplies it
+  // ready made (zlib's encoding of the zeros, byte aligned like every segment) and no token is formed.
+  const csg_png_zero_segment* canned = nullptr;
+  if (filter_type == 2u && !__any_sync(0xffffffffu, nonzero != 0u))
+    for (int z = 0; z < n_zero; ++z)
+      if (zero_table[z].n_raw == n_raw) canned = zero_table + z;
+  const int npx_tok = canned ? 0 : npx;  // pixels that go through the tokeniser
 
   // ---- phase 2: every lane turns its 32 pixels into tokens in a private bit buffer
   unsigned* tok = s_tok[warp] + lane * kTokWords;
@@ -218,12 +229,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   unsigned* cnt = counts ? s_counts[warp] : nullptr;
   // (the block header -- BFINAL / BTYPE and, for a custom code, its code lengths -- is the same bit
   // string for every segment: it is copied in front of the lanes' bits in the merge phase)
-  if (lane == 0 && has_filter) {
+  if (lane == 0 && has_filter && !canned) {
     if (cnt) atomicAdd(&cnt[filter_type], 1u);
     put(c_huff.lit_code[filter_type], c_huff.lit_len[filter_type]);
   }
-  const int p_begin = lane * kPiecePixels, p_end = min(npx, p_begin + kPiecePixels);
-  if (p_begin < npx) {
+  const int p_begin = lane * kPiecePixels, p_end = min(npx_tok, p_begin + kPiecePixels);
+  if (p_begin < npx_tok) {
     // pixel q of the segment (any lane's piece): matches may reach back into earlier pieces
     auto at = [&](int q) { return pix[(q >> 5) * kPixStride + (q & 31)]; };
     int run = 0, dist = 0;  // an open match of `run` pixels at distance `dist` pixels
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
     flush();
   }
-  const bool last_lane = p_begin < npx && p_end == npx;
+  const bool last_lane = p_begin < npx_tok && p_end == npx_tok;
   if (last_lane) {
     if (cnt) atomicAdd(&cnt[256], 1u);
     put(c_huff.eob_code, c_huff.eob_len + 3);  // end-of-block, then the header of the empty stored block (000)
@@ -287,7 +298,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   const int hdr_bits = c_huff.header_bits;
   const int total_bits = hdr_bits + __shfl_sync(0xffffffffu, incl, 31);
   const int off = hdr_bits + incl - my_bits;
-  if (!counts) {
+  if (!counts && canned) {
+    unsigned char* dst = slots + (size_t)seg * slot_bytes;
+    for (int i = lane; i < canned->len; i += 32) dst[i] = canned->bytes[i];
+    if (lane == 0) {
+      sizes[seg] = canned->len;
+      adler[2 * seg] = (unsigned)(sa % 65521ull);
+      adler[2 * seg + 1] = (unsigned)(sb % 65521ull);
+    }
+  } else if (!counts) {
   __syncwarp();  // every lane is done reading pixels: the buffer becomes the merged stream
   unsigned* out = s_pix[warp];
   const int total_bytes = (total_bits + 7) / 8 + 4;  // pad to a byte, then LEN = 0000, NLEN = FFFF
@@ -446,7 +465,7 @@ int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables) {
 static int png_launch(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
                       int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
                       int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, uint32_t* d_counts,
-                      int count_stride, int32_t* d_error) {
+                      int count_stride, int32_t* d_error, const csg_png_zero_segment* d_zero, int n_zero) {
   if (!ctx_tables_ready(ctx)) {
     const int st = csg_png_set_tables(ctx, nullptr);
     if (st != CSG_OK) return st;
@@ -460,30 +479,31 @@ static int png_launch(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_over
   }
   png_encode_kernel<<<blocks, kWarpsPerBlock * 32, kEncodeSmem, ctx->stream>>>(
       (const uint32_t*)d_rgba, (const uint32_t*)d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, d_slots,
-      csg_png_slot_bytes(), d_sizes, d_adler, d_counts, count_stride, d_error);
+      csg_png_slot_bytes(), d_sizes, d_adler, d_counts, count_stride, d_error, d_zero, d_zero ? n_zero : 0);
   CSG_LAUNCH_CHECK(ctx, "png_encode_kernel");
   return CSG_OK;
 }
 
 int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
                    int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
-                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error) {
+                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error,
+                   const csg_png_zero_segment* d_zero, int n_zero) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
   if (!d_rgba || !d_canvases || !d_tiles || !d_rows || !d_slots || !d_sizes || !d_adler)
     return csg_fail(ctx, CSG_ERR_ARG, "NULL argument");
   return png_launch(ctx, d_rgba, d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, d_slots, d_sizes,
-                    d_adler, nullptr, 1, d_error);
+                    d_adler, nullptr, 1, d_error, d_zero, n_zero);
 }
 
 int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
                   int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
-                  int n_segments, int stride, uint32_t* d_counts) {
+                  int n_segments, int stride, uint32_t* d_counts, const csg_png_zero_segment* d_zero, int n_zero) {
   if (!ctx) return CSG_ERR_ARG;
   if (n_canvases <= 0 || n_segments <= 0) return CSG_OK;
   if (!d_rgba || !d_canvases || !d_tiles || !d_rows || !d_counts || stride < 1) return csg_fail(ctx, CSG_ERR_ARG, "bad argument");
   return png_launch(ctx, d_rgba, d_overlay, d_canvases, n_canvases, d_tiles, d_vlines, d_rows, n_segments, nullptr, nullptr,
-                    nullptr, d_counts, stride, nullptr);
+                    nullptr, d_counts, stride, nullptr, d_zero, n_zero);
 }
 
 int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets, int n_segments,

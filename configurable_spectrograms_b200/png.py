@@ -347,6 +347,29 @@ def assemble_png(W: int, H: int, rows, per_row: int, packed, offsets, s0: int, a
             tail + struct.pack(">I", crc & 0xFFFFFFFF) + _chunk(b"IEND", b"")]
 
 
+def zero_segment_table(widths) -> np.ndarray:
+    """``csg_png_zero_segment`` entries for every segment length the canvases of these widths produce: the
+    1024-pixel chunks and the last chunk of a scanline, with and without the leading filter byte (2 = Up)."""
+    from ._lib import PNG_ZERO_SEGMENT
+
+    lengths = set()
+    for W in set(int(w) for w in widths):
+        per_row = (W + 1023) // 1024
+        for chunk in range(per_row):
+            npx = min(1024, W - 1024 * chunk)
+            lengths.add(4 * npx + (1 if chunk == 0 else 0))
+    table = np.zeros(len(lengths), dtype=PNG_ZERO_SEGMENT)
+    for entry, n_raw in zip(table, sorted(lengths)):
+        comp = zlib.compressobj(9, zlib.DEFLATED, -15)
+        raw = (b"\x02" if n_raw & 1 else b"") + bytes(n_raw - (n_raw & 1))
+        piece = comp.compress(raw) + comp.flush(zlib.Z_SYNC_FLUSH)
+        if len(piece) > 56:
+            raise ValueError(f"zero segment of {n_raw} bytes compresses to {len(piece)} bytes (> 56)")
+        entry["n_raw"], entry["len"] = n_raw, len(piece)
+        entry["bytes"][: len(piece)] = np.frombuffer(piece, np.uint8)
+    return table
+
+
 def _device_tables(figures, dpi):
     """Tile / canvas / row tables of a list of figures.  Returns ``(canvases, tiles, rows, per_figure)`` with
     ``canvases`` a list of mutable rows of ``PNG_CANVAS`` (``seg_first`` is filled per group), ``tiles`` one
@@ -378,7 +401,7 @@ def _device_tables(figures, dpi):
     return canvases, tiles, rows, per_figure
 
 
-def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = None, max_segments: int = 160_000, consume=None,
+def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = None, max_segments: int = 400_000, consume=None,
                           timings: dict | None = None, huffman: str = "custom") -> list[bytes]:
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
@@ -422,79 +445,101 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
         return buf
 
     d_tiles, d_rows = ctx.to_device(tiles), ctx.to_device(rows)
+    zero_table = zero_segment_table([c[0] for c in canvases]) if canvases else np.zeros(0, dtype=np.uint8)
+    d_zero = ctx.to_device(zero_table) if len(zero_table) else None
+    zero_args = (d_zero.ptr if d_zero is not None else None, len(zero_table))
     d_overlay = ATLAS.device_ptr(ctx)
     d_error = dev("error", 4)
     d_error.zero()
     t0 = tick("tile_tables", t0)
-    out: list[bytes] = []
-    k = 0
-    while k < len(figures):
-        # ---- the next group of figures that fits the segment budget
-        group, n_seg = [], 0
-        while k + len(group) < len(figures):
-            c = canvases[k + len(group)]
-            segs = c[6] * len(per_figure[k + len(group)][2])
-            if group and n_seg + segs > max_segments:
-                break
-            c[5] = n_seg
-            group.append(c)
-            n_seg += segs
+    # Groups are pipelined: while a background thread frames (CRC-32) and hands over group g from one pinned
+    # buffer, this thread already encodes, compacts and reads back group g + 1 into the other one.
+    results: dict[int, list] = {}
+    finisher = ThreadPoolExecutor(max_workers=1)
+    in_flight: list = [None, None]  # the future still reading pinned buffer 0 / 1
+    k = n_group = 0
+    try:
+        while k < len(figures):
+            # ---- the next group of figures that fits the segment budget
+            group, n_seg = [], 0
+            while k + len(group) < len(figures):
+                c = canvases[k + len(group)]
+                segs = c[6] * len(per_figure[k + len(group)][2])
+                if group and n_seg + segs > max_segments:
+                    break
+                c[5] = n_seg
+                group.append(c)
+                n_seg += segs
+            t0 = time.perf_counter()
+            table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
+            d_canvases = ctx.to_device(table)
+            if k == 0:  # the code of this call
+                if huffman == "custom":
+                    d_counts = dev("counts", 316 * 4)
+                    d_counts.zero()
+                    ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
+                    ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                                 d_rows.ptr, n_seg, 4, d_counts.ptr, *zero_args))
+                    tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
+                    ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
+                elif huffman == "fixed":
+                    ctx._check(lib.csg_png_set_tables(ctx.handle, None))
+                else:
+                    raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
+                t0 = tick("code_tables", t0)
+            d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
+            ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                          d_rows.ptr, n_seg, d_slots.ptr, d_sizes.ptr, d_adler.ptr, d_error.ptr, *zero_args))
+            sizes = d_sizes.download(np.int32, n_seg, sync=False)
+            bad = d_error.download(np.int32, 1, sync=False)
+            adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
+            if bad[0]:
+                raise ValueError(f"figure {k + int(bad[0]) - 1}: more than {int(lib.csg_png_max_segment_tiles())} tiles meet in one "
+                                 "1024-pixel scanline segment")
+            t0 = tick("encode_kernel_and_sizes", t0)
+            offsets = np.zeros(n_seg + 1, dtype=np.int64)
+            np.cumsum(sizes, out=offsets[1:])
+            total = int(offsets[-1])
+            d_off = dev("offsets", n_seg * 8)
+            d_off.upload(offsets[:-1])
+            d_packed = dev("packed", total)
+            ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
+            parity = n_group & 1
+            if in_flight[parity] is not None:
+                in_flight[parity].result()  # the group that last used this pinned buffer is on disk
+                in_flight[parity] = None
+                t0 = tick("wait_for_host", t0)
+            name = f"pinned{parity}"
+            pin = scratch.get(name)
+            if pin is None or pin.nbytes < total:
+                pin = scratch[name] = ctx.pinned(int(total * 1.2) + 4096)
+            ctx._check(lib.csg_d2h(ctx.handle, pin.ptr, d_packed.ptr, total))
+            ctx.sync()
+            t0 = tick("compact_and_d2h", t0)
+
+            def finish(first=k, group=group, jobs=per_figure[k : k + len(group)], packed=pin.array, offsets=offsets, adler=adler):
+                t1 = time.perf_counter()
+                with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
+                    parts = list(pool.map(lambda job: assemble_png(job[1][0], job[1][1], job[1][2], job[0][6], packed, offsets, job[0][5], adler),
+                                          zip(group, jobs)))
+                t1 = tick("framing_crc", t1)
+                if consume is not None:
+                    consume(first, parts)  # the buffers alias pinned scratch that the group after next overwrites
+                else:
+                    results[first] = [b"".join(p) for p in parts]
+                tick("consume", t1)
+
+            in_flight[parity] = finisher.submit(finish)
+            k += len(group)
+            n_group += 1
         t0 = time.perf_counter()
-        table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
-        d_canvases = ctx.to_device(table)
-        if k == 0:  # the code of this call
-            if huffman == "custom":
-                d_counts = dev("counts", 316 * 4)
-                d_counts.zero()
-                ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
-                ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
-                                             d_rows.ptr, n_seg, 4, d_counts.ptr))
-                tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
-                ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
-            elif huffman == "fixed":
-                ctx._check(lib.csg_png_set_tables(ctx.handle, None))
-            else:
-                raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
-            t0 = tick("code_tables", t0)
-        d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
-        ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
-                                      d_rows.ptr, n_seg, d_slots.ptr, d_sizes.ptr, d_adler.ptr, d_error.ptr))
-        sizes = d_sizes.download(np.int32, n_seg, sync=False)
-        bad = d_error.download(np.int32, 1, sync=False)
-        adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
-        if bad[0]:
-            raise ValueError(f"figure {k + int(bad[0]) - 1}: more than {int(lib.csg_png_max_segment_tiles())} tiles meet in one "
-                             "1024-pixel scanline segment")
-        t0 = tick("encode_kernel_and_sizes", t0)
-        offsets = np.zeros(n_seg + 1, dtype=np.int64)
-        np.cumsum(sizes, out=offsets[1:])
-        total = int(offsets[-1])
-        d_off = dev("offsets", n_seg * 8)
-        d_off.upload(offsets[:-1])
-        d_packed = dev("packed", total)
-        ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
-        pin = scratch.get("pinned")
-        if pin is None or pin.nbytes < total:
-            pin = scratch["pinned"] = ctx.pinned(int(total * 1.2) + 4096)
-        ctx._check(lib.csg_d2h(ctx.handle, pin.ptr, d_packed.ptr, total))
-        ctx.sync()
-        packed = pin.array
-        t0 = tick("compact_and_d2h", t0)
-
-        def frame(job):
-            c, (W, H, rows_c) = job
-            return assemble_png(W, H, rows_c, c[6], packed, offsets, c[5], adler)
-
-        with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
-            parts = list(pool.map(frame, zip(group, per_figure[k : k + len(group)])))
-        t0 = tick("framing_crc", t0)
-        if consume is not None:
-            consume(k, parts)  # the buffers alias pinned scratch that the next group overwrites
-        else:
-            out.extend(b"".join(p) for p in parts)
-        t0 = tick("consume", t0)
-        k += len(group)
-    return out
+        for fut in in_flight:
+            if fut is not None:
+                fut.result()
+        tick("wait_for_host", t0)
+    finally:
+        finisher.shutdown(wait=True)
+    return [blob for first in sorted(results) for blob in results[first]]
 
 
 def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwargs) -> None:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 20
+#define CSG_ABI_VERSION 21
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -467,6 +467,16 @@ typedef struct {
   int32_t segs_per_row; /* ceil(W / 1024)                                                                  */
   int32_t row_first;    /* index in d_rows of the canvas' first listed scanline                            */
 } csg_png_canvas; /* 32 bytes */
+/* A segment whose filtered bytes are all zero (it repeats the line above: most segments of a scanline on
+ * which only one colour bar or one label moved on) is a constant of its length n_raw = 4 * pixels (+ 1 with
+ * the filter byte, which is 2): the host supplies the byte-aligned DEFLATE piece ready made (png.py:
+ * zlib's encoding), the encoder copies it instead of forming tokens. */
+typedef struct {
+  int32_t n_raw; /* filtered bytes of the segment                     */
+  int32_t len;   /* bytes of the piece (<= 56)                        */
+  uint8_t bytes[56];
+} csg_png_zero_segment; /* 64 bytes */
+
 /* The DEFLATE code of a batch of figures.  Codes are bit-reversed (ready for the LSB-first stream);
  * len_code[n] / dist_code[k] = the Huffman code of a match of 4n bytes / at distance 4k bytes followed
  * by its extra bits; *_len = total bits; *_sym = the symbol (for csg_png_count).  Literal / length
@@ -493,7 +503,7 @@ CSG_API int csg_png_set_tables(csg_ctx* ctx, const csg_png_tables* tables);  /* 
  * literal / length symbol counts, then distance symbol counts.  Nothing is encoded. */
 CSG_API int csg_png_count(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
                   int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
-                  int n_segments, int stride, uint32_t* d_counts);
+                  int n_segments, int stride, uint32_t* d_counts, const csg_png_zero_segment* d_zero, int n_zero);
 CSG_API int32_t csg_png_slot_bytes(void);                    /* capacity of one segment's output slot        */
 CSG_API int32_t csg_png_segments(int32_t W, int32_t n_rows); /* segments of n_rows listed scanlines of width W */
 CSG_API int32_t csg_png_max_segment_tiles(void);             /* tiles one segment may intersect               */
@@ -504,7 +514,8 @@ CSG_API int32_t csg_png_max_segment_tiles(void);             /* tiles one segmen
  * csg_png_max_segment_tiles() tiles met in one segment (its output is wrong: the host raises). */
 CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d_overlay, const csg_png_canvas* d_canvases,
                    int n_canvases, const csg_png_tile* d_tiles, const csg_png_vline* d_vlines, const int32_t* d_rows,
-                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error);
+                   int n_segments, uint8_t* d_slots, int32_t* d_sizes, uint32_t* d_adler, int32_t* d_error,
+                   const csg_png_zero_segment* d_zero, int n_zero); /* d_zero may be NULL */
 /* d_packed + d_offsets[s] <- slot s (d_offsets: exclusive prefix sum of d_sizes, from the host). */
 CSG_API int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets,
                     int n_segments, uint8_t* d_packed);
