@@ -23,10 +23,11 @@
 //       of its own 16-byte chunks (8 pitch bins per stage) in shared memory, so loads stay in
 //       flight while the previous bins are summed (6.7 TB/s; the register-staged variant with
 //       eight 128-bit streaming loads per batch reaches 5.7 TB/s).  The transposed 16-row tile
-//       leaves through shared memory as 64-byte row segments.
-//       (A TMA variant -- per-warp rings of cp.async.bulk stages -- was measured slower: with
-//       24 of 32 lanes per energy row and per-stage bookkeeping it was issue-bound at 8-16
-//       warps per SM; see DESIGN.md.)
+//       leaves through shared memory as 64-byte row segments.  The tile loads are per-thread
+//       cp.async (LDGSTS), not TMA: every thread consumes exactly the bytes it requested, so there
+//       is no block-wide tile to hand around and no mbarrier to wait on; the kernel sits at the
+//       measured copy bandwidth with 99.8 % useful DRAM traffic (profiles/r1_k1_traffic.json), so a
+//       bulk-tensor variant has nothing left to win here and none is kept in the tree.
 //   collapse_tpe_kernel      (TPE, any shape/alignment) register-staged generic path.
 //   collapse_tep_rows_kernel (stored (T,E,P) view, no groups, 8 <= P <= 128, P % 8 == 0) two lanes
 //       per (t,e) row own numpy's eight pairwise accumulators; P/8 vector loads in flight.

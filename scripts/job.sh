@@ -1,15 +1,15 @@
 #!/bin/bash
-# scratch GPU job: 2 GPUs -- the multi-rank parity test at HEAD, then the bench at N=2
-nvidia-smi -L
-python -m pytest tests/test_gpu_api.py -m gpu -x -q -k two_gpu 2>&1 | tail -15 > gpurun_out/pytest_2gpu.log
-cat gpurun_out/pytest_2gpu.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
+# scratch GPU job (rewritten per gpurun call)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/pytest.log
+cat gpurun_out/pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/bench_2gpu.json").read().strip().splitlines()[-1])
-print("value", d["value"], "ms/step", d["ms_per_step"], "launches", d["gpu_launches"])
-print("collective", json.dumps(d["collective"]))
-print("e2e", json.dumps(d["e2e"])[:700])
-print("parity", json.dumps(d["parity_checked"])[:900])
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms/step", d["ms_per_step"], {k: round(v,3) for k,v in d["stage_ms"].items() if isinstance(v,float)})
+print("png_stage", json.dumps(d["png_stage"])[:1300])
+print("api_e2e", json.dumps(d["api_e2e"])[:2200])
+print("parity", d["parity_checked"]["ok"], d["parity_checked"]["failures"])
 PY
-tail -3 gpurun_out/bench_2gpu.err | cut -c1-300
+tail -2 gpurun_out/bench.err | cut -c1-200
+python scripts/bench_config5.py > gpurun_out/config5.json 2> gpurun_out/config5.err; cat gpurun_out/config5.json | cut -c1-2500; tail -3 gpurun_out/config5.err
