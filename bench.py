@@ -540,7 +540,7 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
         t_write = time.perf_counter() - t0
         os.chdir(work)
         out = {}
-        for label in ("cold", "warm"):  # cold: first call of the process (plans, scratch, page cache); warm: steady state
+        for label in ("cold", "warm", "warm2"):  # cold: first call of the process (plans, scratch, page cache); warm: steady state
             for name in ("progress.json", "FAST_calculated_extrema.json"):
                 if os.path.exists(name):
                     os.remove(name)
@@ -549,24 +549,40 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
             cdf_utils.orbit_column_cache.clear()
             phases: dict = {}
             t0 = time.perf_counter()
+            prof = None
+            if label == "warm2" and os.environ.get("CSG_API_PROFILE"):  # main-thread cProfile of one steady-state call
+                import cProfile
+
+                prof = cProfile.Profile()
+                prof.enable()
             res = FAST_plot_spectrograms_directory(
                 "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", zoom_duration_minutes=6, colormap="turbo",
                 max_processing_percentile=99, max_workers=16, progress_json_path="./progress.json", verbose=False, _timings=phases,
             )
+            if prof is not None:
+                import pstats
+
+                prof.disable()
+                with open(os.environ["CSG_API_PROFILE"], "w") as fh:
+                    pstats.Stats(prof, stream=fh).sort_stats("cumulative").print_stats(70)
+                    pstats.Stats(prof, stream=fh).sort_stats("tottime").print_stats(40)
             sec = time.perf_counter() - t0
             bad = [r for r in res if r.get("status") != "ok"]
             pngs = sum(len(fs) for _d, _s, fs in os.walk("./FAST_plots"))
             png_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _s, fs in os.walk("./FAST_plots") for f in fs)
             got = json.load(open("./FAST_calculated_extrema.json"))
             out[label] = {"seconds": sec, "orbits_per_s": n / sec, "pngs": pngs, "png_mb": png_bytes / 1e6, "errors": len(bad),
-                          "phases_s": {k: round(v, 4) for k, v in phases.items()}}
+                          "phases_s": {k: round(v, 4) for k, v in phases.items()},
+                          "outside_phases_s": round(sec - sum(v for k, v in phases.items() if "/" not in k), 4)}
+        if out["warm2"]["seconds"] < out["warm"]["seconds"]:  # `warm` = the better of the two steady-state calls
+            out["warm"], out["warm2"] = out["warm2"], out["warm"]
         # the same extrema as the device-resident arm computed for these orbits?  (only when the directory IS the shard)
         same = None
         if n == len(orbits) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
             same = all(got.get(k) == v for k, v in state.items() if k.endswith(("_z_max", "_y_max")))
         line = {"value": out["warm"]["orbits_per_s"], "unit": "orbits/s", "orbits": n, "files": n_files,
                 "input_gb": sum(files[fd["index"]]["T"] for ob in orbits[:n] for fd in ob["files"].values()) * P * E * 4 / 1e9,
-                "directory_write_s": round(t_write, 2), "cold": out["cold"], "warm": out["warm"], "extrema_equal_device_arm": same,
+                "directory_write_s": round(t_write, 2), "cold": out["cold"], "warm": out["warm"], "warm_other": out["warm2"], "extrema_equal_device_arm": same,
                 "what": "FAST_plot_spectrograms_directory(dir, max_processing_percentile=99, turbo) on .npz side-cars in tmpfs -> "
                         "PNG files at the reference's 200 dpi (panels resampled, axes / labels / colour bars drawn) on tmpfs; everything inside the clock"}
         if with_reference:

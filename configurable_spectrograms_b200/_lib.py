@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
 LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 21
+ABI_VERSION = 22
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -123,6 +123,11 @@ PNG_TILE = np.dtype(
 TILE_OVERLAY, TILE_TOP_ORIGIN = 1, 2
 PNG_ZERO_SEGMENT = np.dtype([("n_raw", "<i4"), ("len", "<i4"), ("bytes", "u1", (56,))], align=True)
 assert PNG_ZERO_SEGMENT.itemsize == 64
+PNG_FILE = np.dtype(
+    [("path", "<u8"), ("row_first", "<i8"), ("seg_first", "<i8"), ("file_bytes", "<i8"), ("width", "<i4"), ("height", "<i4"),
+     ("n_rows", "<i4"), ("segs_per_row", "<i4"), ("status", "<i4"), ("pad", "<i4")], align=True
+)
+assert PNG_FILE.itemsize == 56
 PNG_VLINE = np.dtype([("col", "<i4"), ("half", "<i4"), ("rgba", "<u4"), ("pad", "<i4")], align=True)
 PNG_CANVAS = np.dtype(
     [("W", "<i4"), ("H", "<i4"), ("tile_first", "<i4"), ("tile_count", "<i4"), ("background", "<u4"),
@@ -160,6 +165,8 @@ SIGNATURES = {
     "csg_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_sz)]),
     "csg_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "csg_dev_free": (_i, [_vp, _vp]),
+    "csg_dev_trim": (_i, [_vp, C.POINTER(_sz)]),
+    "csg_dev_cached": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "csg_host_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "csg_host_free": (_i, [_vp, _vp]),
     "csg_host_register": (_i, [_vp, _vp, _sz]),
@@ -207,6 +214,7 @@ SIGNATURES = {
     "csg_png_segments": (C.c_int32, [C.c_int32, C.c_int32]),
     "csg_png_encode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "csg_png_compact": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "csg_png_write_files": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i]),
     "csg_peer_create": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
     "csg_peer_mailbox": (_vp, [_vp]),
     "csg_peer_connect_ipc": (_i, [_vp, _vp, _vp]),
@@ -515,6 +523,18 @@ class Context:
 
     def pinned(self, nbytes: int) -> PinnedBuf:
         return PinnedBuf(self, nbytes)
+
+    def cached(self) -> tuple[int, int]:
+        """(bytes parked in the device block cache, bytes handed out) on this context's device."""
+        idle, live = _sz(), _sz()
+        self._check(self.lib.csg_dev_cached(self.handle, C.byref(idle), C.byref(live)))
+        return int(idle.value), int(live.value)
+
+    def trim(self) -> int:
+        """Return every parked device block to the driver; the bytes released."""
+        n = _sz()
+        self._check(self.lib.csg_dev_trim(self.handle, C.byref(n)))
+        return int(n.value)
 
     def to_device(self, arr: np.ndarray) -> DevBuf:
         arr = np.ascontiguousarray(arr)

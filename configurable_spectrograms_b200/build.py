@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcsgpu.so")
-SOURCES = ("ctx.cu", "collapse.cu", "stats.cu", "raster.cu", "pool.cu", "poolsel.cu", "peer.cu", "png.cu", "cdf.cpp")
+SOURCES = ("ctx.cu", "collapse.cu", "stats.cu", "raster.cu", "pool.cu", "poolsel.cu", "peer.cu", "png.cu", "png_host.cpp", "cdf.cpp")
 
 NVCC_FLAGS = [
     "-gencode",

@@ -113,6 +113,9 @@ def FAST_plot_spectrograms_directory(
     except (ValueError, OSError) as exc:
         log_exception("[WARN] Could not register signal handlers", exc, level="message")
 
+    import time as _time
+
+    t_call = _time.perf_counter()
     try:
         return _run_directory(
             directory_path, output_base, y_scale, z_scale, zoom_duration_minutes, tuple(instrument_order), verbose,
@@ -121,6 +124,8 @@ def FAST_plot_spectrograms_directory(
             orbit_timeout_seconds, instrument_timeout_seconds, retry_timeouts, _timings,
         )
     finally:
+        if _timings is not None:  # what is left once the phases are subtracted: releasing the shard's buffers
+            _timings["release"] = _time.perf_counter() - t_call - sum(v for k, v in _timings.items() if "/" not in k)
         for sig, handler in previous.items():
             try:
                 signal.signal(sig, handler)
@@ -322,6 +327,39 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
 
     from ..png import write_figures_device
 
+    png_timings: dict | None = {} if timings is not None else None
+    code_cache: dict = {}  # the DEFLATE code fitted to the first chunk's figures serves the whole run
+    previous_chunk = None
+
+    def settle(chunk_state, since_flush):
+        """The host half of a chunk ends here: its PNG files are on disk (the framing and writing ran on the
+        encoder's finisher thread while the next chunk was ingested and planned), then the soft timeouts and
+        the progress records -- in that order, so that progress never names an orbit whose files are missing."""
+        writes, paths, planned, n_jobs, seconds = chunk_state
+        t_wait = _time.perf_counter()
+        for fut in writes:
+            fut.result()
+        seconds += _time.perf_counter() - t_wait
+        for path in paths:
+            log_exception(f"[SAVED] {path}", level="message")
+        # soft timeouts, checked after the work like the reference's (process_orbit.py:203-211,276-283): a
+        # chunk's wall time is shared evenly between its submissions
+        share = seconds / max(1, n_jobs)
+        for result, _s in planned:
+            if share > orbit_timeout_seconds and result["status"] == "ok":
+                log_exception(f"[TIMEOUT] Orbit {result['orbit']} exceeded {orbit_timeout_seconds:.0f}s total.", level="message")
+                result["status"], result["timeout_type"] = "timeout", "orbit"
+            results.append(result)
+            if verbose:
+                log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
+            if progress_json_path is not None and rank == 0:
+                record(result, pdisk)
+                since_flush += 1
+                if since_flush >= flush_batch_size:
+                    _write_json(progress_json_path, pdisk)
+                    since_flush = 0
+        return since_flush
+
     with ThreadPoolExecutor(max_workers=n_threads) as pool:
         for a in range(0, len(my_pending), chunk_n):
             chunk = my_pending[a : a + chunk_n]
@@ -384,29 +422,21 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
                     by_path[path] = fig
             saves = list(by_path.items())
             t_phase = tick("figures_host", t_phase)
+            if previous_chunk is not None:  # its files were framed and written while this chunk was planned
+                since_flush = settle(previous_chunk, since_flush)
+                previous_chunk = None
+                t_phase = tick("png_wait_previous_chunk", t_phase)
+            writes = []
             if saves:
-                write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads, dpi=SAVE_DPI)
-                for path, fig in saves:
-                    log_exception(f"[SAVED] {path}", level="message")
+                writes = write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads, dpi=SAVE_DPI, timings=png_timings,
+                                              wait=False, code_cache=code_cache)
+                for _path, fig in saves:
                     close_all_axes_and_clear(fig)
-            t_phase = tick("png_encode_and_write", t_phase)
-            # soft timeouts, checked after the work like the reference's (process_orbit.py:203-211,276-283): a
-            # chunk's wall time is shared evenly between its submissions
-            share = (_time.perf_counter() - t_chunk) / max(1, len(jobs))
-            for result, _s in planned:
-                if share > orbit_timeout_seconds and result["status"] == "ok":
-                    log_exception(f"[TIMEOUT] Orbit {result['orbit']} exceeded {orbit_timeout_seconds:.0f}s total.", level="message")
-                    result["status"], result["timeout_type"] = "timeout", "orbit"
-                results.append(result)
-                if verbose:
-                    log_exception(f"[BATCH] Completed orbit {result['orbit']}: {result['status']}", level="message")
-                if progress_json_path is not None and rank == 0:
-                    record(result, pdisk)
-                    since_flush += 1
-                    if since_flush >= flush_batch_size:
-                        _write_json(progress_json_path, pdisk)
-                        since_flush = 0
-            t_phase = tick("progress", t_phase)
+            previous_chunk = (writes, [path for path, _f in saves], planned, len(jobs), _time.perf_counter() - t_chunk)
+            t_phase = tick("png_encode", t_phase)
+        if previous_chunk is not None:
+            since_flush = settle(previous_chunk, since_flush)
+            t_phase = tick("png_wait_last_chunk", t_phase)
 
     if world > 1:  # every rank returns every result; rank 0 owns the progress file
         gathered: list = [None] * world
@@ -425,6 +455,8 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
                                           instrument_timeout_seconds, override_plots, cusp_marker_style, cusp_marker_kwargs,
                                           progress_json_path)
     tick("finish", t_phase)
+    if timings is not None:
+        timings.update({f"png/{k}": v for k, v in (png_timings or {}).items()})
     return results
 
 

@@ -15,6 +15,7 @@ device one.
 
 from __future__ import annotations
 
+import os
 import struct
 import zlib
 from concurrent.futures import ThreadPoolExecutor
@@ -402,7 +403,8 @@ def _device_tables(figures, dpi):
 
 
 def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = None, max_segments: int = 400_000, consume=None,
-                          timings: dict | None = None, huffman: str = "custom") -> list[bytes]:
+                          timings: dict | None = None, huffman: str = "custom", wait: bool = True, code_cache: dict | None = None,
+                          paths=None, write_threads: int = 16):
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
     ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
@@ -419,7 +421,17 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
     ``timings`` (optional dict) accumulates host seconds per phase.  ``huffman``: "custom" fits a
     dynamic-Huffman code to the symbol statistics of the first group of figures (one counting pass of
     the same tokeniser over every 4th scanline segment) and uses it for the whole call; "fixed" uses
-    RFC 1951's fixed code.
+    RFC 1951's fixed code.  ``code_cache`` (a dict the caller keeps): the fitted code is stored there and
+    reused by later calls instead of being fitted again (the chunks of one directory run look alike).
+
+    ``paths`` (one per figure): frame and write the files natively (``csg_png_write_files``: CRC-32 +
+    ``writev`` from the pinned buffer on ``write_threads`` native threads, no interpreter lock held) instead of
+    building them here; nothing is returned or handed to ``consume`` then.
+
+    ``wait=False`` (needs ``consume`` or ``paths``): return as soon as the last group is read back, with the futures of
+    the host work (framing + ``consume``) still running on the context's finisher thread; the caller
+    collects them (``future.result()``) before it relies on the files.  The next call on the same context
+    may start meanwhile -- the two pinned read-back buffers are fenced by those futures.
     """
     import time
 
@@ -453,11 +465,21 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
     d_error.zero()
     t0 = tick("tile_tables", t0)
     # Groups are pipelined: while a background thread frames (CRC-32) and hands over group g from one pinned
-    # buffer, this thread already encodes, compacts and reads back group g + 1 into the other one.
+    # buffer, this thread already encodes, compacts and reads back group g + 1 into the other one.  The
+    # thread and the fences of the two buffers belong to the context, so the pipeline runs across calls too.
+    if not wait and consume is None and paths is None:
+        raise ValueError("wait=False needs a consume callback or paths (the files are handed over, not returned)")
+    if paths is not None and len(paths) != len(figures):
+        raise ValueError(f"{len(paths)} paths for {len(figures)} figures")
     results: dict[int, list] = {}
-    finisher = ThreadPoolExecutor(max_workers=1)
-    in_flight: list = [None, None]  # the future still reading pinned buffer 0 / 1
-    k = n_group = 0
+    pipe = scratch.get("finisher")
+    if pipe is None:
+        pipe = scratch["finisher"] = {"pool": ThreadPoolExecutor(max_workers=1, thread_name_prefix="csg-png"),
+                                      "framers": ThreadPoolExecutor(max_workers=16, thread_name_prefix="csg-crc"),
+                                      "in_flight": [None, None], "groups": 0}
+    finisher, framers, in_flight = pipe["pool"], pipe["framers"], pipe["in_flight"]  # in_flight: the future reading pinned buffer 0 / 1
+    mine: list = []
+    k = 0
     try:
         while k < len(figures):
             # ---- the next group of figures that fits the segment budget
@@ -474,7 +496,9 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
             table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
             d_canvases = ctx.to_device(table)
             if k == 0:  # the code of this call
-                if huffman == "custom":
+                if huffman == "custom" and code_cache is not None and "tables" in code_cache:
+                    ctx._check(lib.csg_png_set_tables(ctx.handle, code_cache["tables"].ctypes.data))
+                elif huffman == "custom":
                     d_counts = dev("counts", 316 * 4)
                     d_counts.zero()
                     ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
@@ -482,6 +506,8 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
                                                  d_rows.ptr, n_seg, 4, d_counts.ptr, *zero_args))
                     tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
                     ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
+                    if code_cache is not None:
+                        code_cache["tables"] = tables
                 elif huffman == "fixed":
                     ctx._check(lib.csg_png_set_tables(ctx.handle, None))
                 else:
@@ -504,7 +530,7 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
             d_off.upload(offsets[:-1])
             d_packed = dev("packed", total)
             ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
-            parity = n_group & 1
+            parity = pipe["groups"] & 1
             if in_flight[parity] is not None:
                 in_flight[parity].result()  # the group that last used this pinned buffer is on disk
                 in_flight[parity] = None
@@ -519,9 +545,12 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
 
             def finish(first=k, group=group, jobs=per_figure[k : k + len(group)], packed=pin.array, offsets=offsets, adler=adler):
                 t1 = time.perf_counter()
-                with ThreadPoolExecutor(max_workers=min(16, max(1, len(group)))) as pool:
-                    parts = list(pool.map(lambda job: assemble_png(job[1][0], job[1][1], job[1][2], job[0][6], packed, offsets, job[0][5], adler),
-                                          zip(group, jobs)))
+                if paths is not None:
+                    write_files_native(lib, paths[first : first + len(group)], group, jobs, rows, packed, offsets, adler, write_threads)
+                    tick("frame_and_write_native", t1)
+                    return
+                parts = list(framers.map(lambda job: assemble_png(job[1][0], job[1][1], job[1][2], job[0][6], packed, offsets, job[0][5], adler),
+                                         zip(group, jobs)))
                 t1 = tick("framing_crc", t1)
                 if consume is not None:
                     consume(first, parts)  # the buffers alias pinned scratch that the group after next overwrites
@@ -530,32 +559,58 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
                 tick("consume", t1)
 
             in_flight[parity] = finisher.submit(finish)
+            mine.append(in_flight[parity])
             k += len(group)
-            n_group += 1
-        t0 = time.perf_counter()
-        for fut in in_flight:
-            if fut is not None:
+            pipe["groups"] += 1
+    except BaseException:
+        for fut in mine:  # leave no work of a failed call behind
+            try:
                 fut.result()
-        tick("wait_for_host", t0)
-    finally:
-        finisher.shutdown(wait=True)
+            except Exception:
+                pass
+        raise
+    if not wait:
+        return mine
+    t0 = time.perf_counter()
+    for fut in mine:
+        fut.result()
+    tick("wait_for_host", t0)
     return [blob for first in sorted(results) for blob in results[first]]
 
 
-def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwargs) -> None:
-    """``jobs``: iterable of (path, figure).  Device encode; every group's files are written by a
-    thread pool straight from the pinned read-back buffer."""
+def write_files_native(lib, paths, group, jobs, rows, packed, offsets, adler, n_threads: int = 16) -> None:
+    """Frame and write one group's files through ``csg_png_write_files``.  ``group``: the canvases' table rows
+    (``[W, H, tile_first, tile_count, background, seg_first, segs_per_row, row_first]``); ``jobs``:
+    ``(W, H, content rows)`` per figure; ``rows``: every canvas' content rows, concatenated."""
+    from ._lib import PNG_FILE, CsgError
+
+    table = np.zeros(len(group), dtype=PNG_FILE)
+    encoded = [os.fsencode(p) + b"\0" for p in paths]
+    keep = [np.frombuffer(e, dtype=np.uint8) for e in encoded]
+    for entry, c, job, name in zip(table, group, jobs, keep):
+        entry["path"] = name.ctypes.data
+        entry["row_first"], entry["seg_first"] = c[7], c[5]
+        entry["width"], entry["height"], entry["n_rows"], entry["segs_per_row"] = c[0], c[1], len(job[2]), c[6]
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    adler = np.ascontiguousarray(adler, dtype=np.uint32)
+    status = lib.csg_png_write_files(table.ctypes.data, len(table), rows.ctypes.data, packed.ctypes.data, offsets.ctypes.data,
+                                     adler.ctypes.data, int(n_threads))
+    if status:
+        bad = [(p, os.strerror(int(e["status"]))) for p, e in zip(paths, table) if e["status"]]
+        if bad:
+            raise OSError(f"{len(bad)} PNG file(s) not written, first: {bad[0][0]}: {bad[0][1]}")
+        raise CsgError(f"csg_png_write_files failed with status {status}")
+
+
+def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwargs):
+    """``jobs``: iterable of (path, figure).  Device encode; every group's files are framed and written
+    straight from the pinned read-back buffer by native threads (``csg_png_write_files``).  With
+    ``wait=False`` the call returns the futures of the framing + writing still under way (see
+    :func:`encode_figures_device`); the files are complete once every ``future.result()`` has returned."""
     jobs = list(jobs)
     if not jobs:
-        return
-
-    def write(job):
-        path, parts = job
-        with open(path, "wb") as f:
-            f.writelines(parts)
-
-    def consume(first, parts):
-        with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(parts)))) as pool:
-            list(pool.map(write, [(jobs[first + i][0], p) for i, p in enumerate(parts)]))
-
-    encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], consume=consume, **kwargs)
+        return []
+    out = encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], paths=[str(p) for p, _f in jobs],
+                                write_threads=max(1, int(max_workers)), **kwargs)
+    return out if kwargs.get("wait") is False else []

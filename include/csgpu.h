@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 21
+#define CSG_ABI_VERSION 22
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -41,7 +41,8 @@ typedef enum {
   CSG_ERR_CUDA = 1,   /* a CUDA runtime call failed (message has the CUDA error) */
   CSG_ERR_ARG = 2,    /* invalid argument */
   CSG_ERR_NOMEM = 3,  /* allocation failed */
-  CSG_ERR_NODEV = 4   /* no usable CUDA device */
+  CSG_ERR_NODEV = 4,  /* no usable CUDA device */
+  CSG_ERR_IO = 5      /* a file could not be written (csg_png_write_files: per-file errno in csg_png_file.status) */
 } csg_status;
 
 enum { CSG_F32 = 0, CSG_F64 = 1 };
@@ -75,8 +76,18 @@ CSG_API void* csg_stream_handle(csg_ctx* ctx);
 CSG_API int csg_device_info(csg_ctx* ctx, char* name, int name_len, int* sm_count, size_t* total_mem);
 
 /* ------------------------------------------------------------------- memory */
+/* Device blocks come from a per-device cache: csg_dev_free parks the block (fenced with an event on every
+   stream of every live context, so nobody gets it back before all work enqueued so far is over) and
+   csg_dev_alloc reuses a parked block of the same size class (4 classes per power of two) -- a directory run
+   allocates per-chunk tables at a rate at which cudaMalloc / cudaFree (device-wide synchronisation, ms each)
+   showed up as half the wall time.  CSG_POOL=0 restores plain cudaMalloc / cudaFree; CSG_POOL_MAX_MB caps the
+   parked bytes (default 32768).  An allocation the driver refuses is retried after the cache is emptied. */
 CSG_API int csg_dev_alloc(csg_ctx* ctx, size_t bytes, void** d_ptr);
 CSG_API int csg_dev_free(csg_ctx* ctx, void* d_ptr);
+/* return every parked block of the context's device to the driver; released_bytes may be NULL */
+CSG_API int csg_dev_trim(csg_ctx* ctx, size_t* released_bytes);
+/* bytes parked in the cache / bytes handed out and not yet freed (either pointer may be NULL) */
+CSG_API int csg_dev_cached(csg_ctx* ctx, size_t* idle_bytes, size_t* live_bytes);
 CSG_API int csg_host_alloc(csg_ctx* ctx, size_t bytes, void** h_ptr); /* pinned */
 CSG_API int csg_host_free(csg_ctx* ctx, void* h_ptr);
 CSG_API int csg_host_register(csg_ctx* ctx, void* h_ptr, size_t bytes); /* pin caller memory (cdflib arrays) */
@@ -519,6 +530,29 @@ CSG_API int csg_png_encode(csg_ctx* ctx, const uint8_t* d_rgba, const uint8_t* d
 /* d_packed + d_offsets[s] <- slot s (d_offsets: exclusive prefix sum of d_sizes, from the host). */
 CSG_API int csg_png_compact(csg_ctx* ctx, const uint8_t* d_slots, const int32_t* d_sizes, const int64_t* d_offsets,
                     int n_segments, uint8_t* d_packed);
+
+/* Host half of K4: frame + write.  One PNG file per entry, built in place from the read-back buffer (no
+ * copy: one CRC-32 pass, then writev) on `n_threads` native threads, outside the interpreter lock:
+ *   signature, IHDR, ONE IDAT = zlib header + for every content row its `segs_per_row` device pieces
+ *   (packed[offsets[s] .. offsets[s+1]), s from seg_first) + after a row followed by g repeated scanlines a
+ *   constant "g x (filter Up + 4*width zero bytes)" DEFLATE piece + final empty block + Adler-32 (combined
+ *   from adler[s][2], the device's per-piece partial sums), IEND.
+ * Replaces the host side of fig.savefig (CS/fast/process_orbit.py:98-117: Agg's PNG writer).  `rows`: the
+ * content scanlines of every canvas (csg_png_encode's d_rows, host copy).  Returns CSG_ERR_IO when any file
+ * failed (status = errno per file), CSG_OK otherwise. */
+typedef struct csg_png_file {
+  const char* path;     /* destination (created or truncated) */
+  int64_t row_first;    /* index of the canvas' first content row in rows[] */
+  int64_t seg_first;    /* index of its first segment in offsets[] / adler[] */
+  int64_t file_bytes;   /* out: size of the file written */
+  int32_t width, height;
+  int32_t n_rows;       /* content rows */
+  int32_t segs_per_row; /* ceil(width / 1024) */
+  int32_t status;       /* out: 0 or errno */
+  int32_t pad;
+} csg_png_file; /* 56 bytes */
+CSG_API int csg_png_write_files(csg_png_file* files, int n_files, const int32_t* rows, const uint8_t* packed,
+                                const int64_t* offsets, const uint32_t* adler, int n_threads);
 
 /* ------------------------------------------------ ingest: native CDF v3 reader (host only) */
 /* Replaces the four cdflib `varget` calls of load_fast_cdf_dataset (CS/cdf_utils.py:247-251) for the

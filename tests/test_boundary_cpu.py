@@ -36,7 +36,8 @@ def test_struct_layouts_match_the_header_sizes():
 
     sizes = {"csg_pool_item": (_lib.POOL_ITEM, 24), "csg_pool_query": (_lib.POOL_QUERY, 32), "csg_png_tile": (_lib.PNG_TILE, 48),
              "csg_png_vline": (_lib.PNG_VLINE, 16), "csg_png_canvas": (_lib.PNG_CANVAS, 32), "csg_pool_request": (_lib.POOL_REQUEST, 16),
-             "csg_pool_sel": (_lib.POOL_SEL, 64), "csg_cdf_var": (_lib.CDF_VAR, 336)}
+             "csg_pool_sel": (_lib.POOL_SEL, 64), "csg_cdf_var": (_lib.CDF_VAR, 336), "csg_png_file": (_lib.PNG_FILE, 56),
+             "csg_png_zero_segment": (_lib.PNG_ZERO_SEGMENT, 64)}
     header = open(os.path.join(ROOT, "include", "csgpu.h")).read()
     for name, (dtype, nbytes) in sizes.items():
         assert dtype.itemsize == nbytes, name

@@ -759,3 +759,40 @@ def test_device_selector_ranks_and_device_y_candidates(dtype, n_ranks):
     del sels, keep, exchanges
     for c in ctxs:
         c.close()
+
+
+def test_device_block_cache_reuses_and_fences(ctx):
+    """csg_dev_free parks blocks, csg_dev_alloc reuses them by size class -- and never while work enqueued
+    before the release (on ANY context's stream) is still running."""
+    ctx.trim()
+    idle0, live0 = ctx.cached()
+    a = ctx.alloc(1_000_000)  # class: 1 MiB
+    ptr = a.ptr
+    assert ctx.cached()[1] == live0 + (1 << 20)
+    a.free()
+    assert ctx.cached() == (idle0 + (1 << 20), live0)
+    b = ctx.alloc(1_040_000)  # same class (4 per power of two) -> the same block
+    assert b.ptr == ptr and ctx.cached() == (idle0, live0 + (1 << 20))
+    c = ctx.alloc(1_000_000)  # the class is empty again -> a new block
+    assert c.ptr != ptr
+    b.free()
+    c.free()
+    assert ctx.trim() >= 2 << 20 and ctx.cached()[0] == 0
+    # ---- a block released while ANOTHER context's stream still writes it: the next owner must not get it
+    # before those writes are over (cudaFree used to guarantee that by synchronising the device)
+    side = ctx.side_context()
+    n = 512 << 20
+    big = ctx.alloc(n)
+    ptr = big.ptr
+    for k in range(24):  # ~24 x 512 MB of fills queued on the side stream
+        side._check(side.lib.csg_memset(side.handle, big.ptr, 0xAB, n))
+    big.free()
+    again = ctx.alloc(n)
+    assert again.ptr == ptr
+    again.zero()
+    got = again.download(np.uint8, 1 << 20, offset=n - (1 << 20))
+    side.sync()
+    late = again.download(np.uint8, 1 << 20, offset=n - (1 << 20))
+    assert not got.any() and not late.any()
+    again.free()
+    ctx.trim()

@@ -3,6 +3,7 @@ composition, cusp markers, batch_runner's resumable progress."""
 
 import functools
 import json
+import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -199,6 +200,30 @@ def test_png_assembly_splices_repeated_lines():
     blob = b"".join(bytes(p) for p in png.assemble_png(W, H, rows, per_row, packed, offsets, 0, np.array(adler, dtype=np.uint32)))
     assert np.array_equal(png.decode_rgba(blob), img)
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(blob)).convert("RGBA")), img)
+    # ---- the native framer / writer (csg_png_write_files, a host-only entry point of the library): two files
+    # from one packed buffer, the second canvas' segments and rows at an offset; plus a path that cannot be opened
+    import tempfile
+
+    from configurable_spectrograms_b200 import _lib
+
+    lib = _lib.load_library()
+    adler2 = np.concatenate([np.array(adler, dtype=np.uint32)] * 2)
+    packed2 = np.concatenate([packed, packed])
+    sizes = np.array([len(x) for x in segs] * 2)
+    offsets2 = np.concatenate([[0], np.cumsum(sizes)])
+    rows2 = np.concatenate([rows, rows]).astype(np.int32)
+    group = [[W, H, 0, 0, 0, 0, per_row, 0], [W, H, 0, 0, 0, len(segs), per_row, len(rows)]]
+    jobs = [(W, H, rows), (W, H, rows)]
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = [os.path.join(tmp, "a.png"), os.path.join(tmp, "b \u00e9.png")]
+        png.write_files_native(lib, paths, group, jobs, rows2, packed2, offsets2, adler2, n_threads=2)
+        for path in paths:
+            data = open(path, "rb").read()
+            assert np.array_equal(png.decode_rgba(data), img)
+            assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGBA")), img)
+        with pytest.raises(OSError, match="not written"):
+            png.write_files_native(lib, [os.path.join(tmp, "missing_dir", "c.png"), paths[0]], group, jobs, rows2, packed2, offsets2, adler2)
+        assert np.array_equal(png.decode_rgba(open(paths[0], "rb").read()), img)  # the good file of a failing group is still written
 
 
 def test_png_custom_huffman_tables_decode_with_zlib():
