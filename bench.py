@@ -523,42 +523,60 @@ def write_api_directory(work, cubes, files, orbits, n_orbits):
     return len(jobs)
 
 
-def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
+def api_e2e_leg(args, cubes, files, orbits, state, with_reference, dist=None, rank=0, world=1):
     """Wall clock of the public API on a fresh directory: discovery, streaming ingest through pinned
-    slots, K1, the global-extrema pre-pass, planning, K2a, K3, K4 and the PNG files on disk."""
+    slots, K1, the global-extrema pre-pass, planning, K2a, K3, K4 and the PNG files on disk.  With several
+    ranks the directory is rank 0's shard and every rank takes its share of those orbits (the same directory,
+    more GPUs: strong scaling of the call); the clock is the slowest rank's."""
     import shutil
 
     from configurable_spectrograms_b200 import cdf_utils
     from configurable_spectrograms_b200.fast.batch_directory import FAST_plot_spectrograms_directory
 
     n = min(args.api_orbits or args.orbits_per_gpu, len(orbits))
-    work = scratch_dir("csg_api_")
     cwd = os.getcwd()
-    try:
+    box = [None, 0, 0.0]
+    if rank == 0:
+        work = scratch_dir("csg_api_")
         t0 = time.perf_counter()
-        n_files = write_api_directory(work, cubes, files, orbits, n)
-        t_write = time.perf_counter() - t0
+        box = [work, write_api_directory(work, cubes, files, orbits, n), time.perf_counter() - t0]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    work, n_files, t_write = box
+
+    def clock():
+        """seconds since the previous call, as the maximum over ranks (ranks leave a barrier together)"""
+        if world > 1:
+            dist.barrier()
+        now = time.perf_counter()
+        sec, clock.t = now - clock.t, now
+        return sec
+
+    clock.t = 0.0
+    try:
         os.chdir(work)
         out = {}
         for label in ("cold", "warm", "warm2"):  # cold: first call of the process (plans, scratch, page cache); warm: steady state
-            for name in ("progress.json", "FAST_calculated_extrema.json"):
-                if os.path.exists(name):
-                    os.remove(name)
-            shutil.rmtree("FAST_plots", ignore_errors=True)
+            if rank == 0:
+                for name in ("progress.json", "FAST_calculated_extrema.json"):
+                    if os.path.exists(name):
+                        os.remove(name)
+                shutil.rmtree("FAST_plots", ignore_errors=True)
             cdf_utils.filtered_orbits_cache.clear()
             cdf_utils.orbit_column_cache.clear()
             phases: dict = {}
-            t0 = time.perf_counter()
             prof = None
-            if label == "warm2" and os.environ.get("CSG_API_PROFILE"):  # main-thread cProfile of one steady-state call
+            if label == "warm2" and os.environ.get("CSG_API_PROFILE") and rank == 0:  # main-thread cProfile of one steady-state call
                 import cProfile
 
                 prof = cProfile.Profile()
                 prof.enable()
+            clock()
             res = FAST_plot_spectrograms_directory(
                 "./FAST_data", output_base="./FAST_plots/", y_scale="linear", z_scale="log", zoom_duration_minutes=6, colormap="turbo",
                 max_processing_percentile=99, max_workers=16, progress_json_path="./progress.json", verbose=False, _timings=phases,
             )
+            sec = clock()
             if prof is not None:
                 import pstats
 
@@ -566,26 +584,29 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
                 with open(os.environ["CSG_API_PROFILE"], "w") as fh:
                     pstats.Stats(prof, stream=fh).sort_stats("cumulative").print_stats(70)
                     pstats.Stats(prof, stream=fh).sort_stats("tottime").print_stats(40)
-            sec = time.perf_counter() - t0
+            if rank != 0:
+                continue
             bad = [r for r in res if r.get("status") != "ok"]
             pngs = sum(len(fs) for _d, _s, fs in os.walk("./FAST_plots"))
             png_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _s, fs in os.walk("./FAST_plots") for f in fs)
             got = json.load(open("./FAST_calculated_extrema.json"))
             out[label] = {"seconds": sec, "orbits_per_s": n / sec, "pngs": pngs, "png_mb": png_bytes / 1e6, "errors": len(bad),
-                          "phases_s": {k: round(v, 4) for k, v in phases.items()},
-                          "outside_phases_s": round(sec - sum(v for k, v in phases.items() if "/" not in k), 4)}
+                          "results": len(res), "phases_s": {k: round(v, 4) for k, v in phases.items()}}
+        if rank != 0:
+            return None
         if out["warm2"]["seconds"] < out["warm"]["seconds"]:  # `warm` = the better of the two steady-state calls
             out["warm"], out["warm2"] = out["warm2"], out["warm"]
         # the same extrema as the device-resident arm computed for these orbits?  (only when the directory IS the shard)
         same = None
-        if n == len(orbits) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        if n == len(orbits) and world == 1:
             same = all(got.get(k) == v for k, v in state.items() if k.endswith(("_z_max", "_y_max")))
-        line = {"value": out["warm"]["orbits_per_s"], "unit": "orbits/s", "orbits": n, "files": n_files,
+        line = {"value": out["warm"]["orbits_per_s"], "unit": "orbits/s", "orbits": n, "files": n_files, "n_gpus": world,
                 "input_gb": sum(files[fd["index"]]["T"] for ob in orbits[:n] for fd in ob["files"].values()) * P * E * 4 / 1e9,
                 "directory_write_s": round(t_write, 2), "cold": out["cold"], "warm": out["warm"], "warm_other": out["warm2"], "extrema_equal_device_arm": same,
                 "what": "FAST_plot_spectrograms_directory(dir, max_processing_percentile=99, turbo) on .npz side-cars in tmpfs -> "
-                        "PNG files at the reference's 200 dpi (panels resampled, axes / labels / colour bars drawn) on tmpfs; everything inside the clock"}
-        if with_reference:
+                        "PNG files at the reference's 200 dpi (panels resampled, axes / labels / colour bars drawn) on tmpfs; everything inside the clock"
+                        + ("; ONE directory shared by all ranks (strong scaling), phases are rank 0's" if world > 1 else "")}
+        if with_reference and world == 1:
             from oracle import ref_driver as RD
 
             if RD.available():
@@ -595,7 +616,10 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference):
         return line
     finally:
         os.chdir(cwd)
-        shutil.rmtree(work, ignore_errors=True)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(work, ignore_errors=True)
 
 
 def bind_near_gpu(torch, local):
@@ -905,8 +929,8 @@ def main():
 
     # ------------------------------------------------ api_e2e: the public call, directory -> PNG files
     api = None
-    if rank == 0 and world == 1 and not args.no_api_e2e:
-        api = api_e2e_leg(args, cubes, files, orbits, state, args.api_ref)
+    if not args.no_api_e2e:  # (every rank takes part: the directory driver shards the orbits itself)
+        api = api_e2e_leg(args, cubes, files, orbits, state, args.api_ref, torch.distributed if world > 1 else None, rank, world)
 
     # ----------------------------------------------------------- CPU baseline beside it
     cpu = None

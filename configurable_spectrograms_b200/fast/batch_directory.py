@@ -273,6 +273,21 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
                 loaded_orbits.append(orbit)
             shard.collapse_pending()
             ring.release(slot)
+    if world > 1:
+        # one pool, one key width: every rank computes in the same dtype.  A rank without orbits of its own
+        # (more GPUs than orbits) adopts its peers'; ranks that read cubes of different float dtypes cannot
+        # share a pool (ShardPlan.add_orbit refuses that within a shard for the same reason)
+        mine_dtype = None if shard._dtype is None else shard._dtype.name
+        seen: list = [None] * world
+        dist.all_gather_object(seen, mine_dtype)
+        kinds = sorted({d for d in seen if d is not None})
+        if len(kinds) > 1:
+            raise TypeError(f"ranks read cubes of different dtypes ({', '.join(kinds)}): one run computes in one dtype")
+        if shard._dtype is None and kinds:
+            shard._dtype = np.dtype(kinds[0])
+            shard._batch = None
+    if not chunks:  # such a rank still joins the extrema exchange, with empty outputs of K1
+        shard.collapse_pending()
     if ring is not None:
         if ring.overflow_bytes:
             log_exception(f"[INGEST] {ring.overflow_bytes} bytes of cubes did not fit the pinned slots "

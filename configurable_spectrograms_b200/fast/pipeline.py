@@ -106,8 +106,9 @@ class ShardPlan:
 
     @property
     def batch(self) -> Batch:
-        if self._batch is None:  # nothing added yet: float32 (FAST counts are CDF_FLOAT) until a cube says otherwise
-            self._dtype = np.dtype(np.float32)
+        if self._batch is None:  # nothing added yet: float32 (FAST counts are CDF_FLOAT) unless a dtype was given
+            if self._dtype is None:
+                self._dtype = np.dtype(np.float32)
             self._batch = Batch(self.ctx, self._dtype, n_groups=self.n_groups)
         return self._batch
 
