@@ -1,6 +1,5 @@
 #!/bin/bash
-# scratch GPU job (rewritten per gpurun call): the multi-rank parity worker on 8 ranks (6 orbits: two empty shards)
-CSG_TEST_WORLD=8 timeout 600 python -m pytest tests/test_gpu_api.py -m gpu -x -q -k two_gpu 2>&1 | tail -30 > gpurun_out/worker8.log
-tail -30 gpurun_out/worker8.log | cut -c1-400
-grep -a "rank[0-9]\]:" gpurun_out/multigpu_worker_failure.log 2>/dev/null | tail -30
-exit 0
+# scratch GPU job (rewritten per gpurun call): strong-scaling point N=1 of config 4 (1000 orbits on one GPU)
+timeout 1500 python bench.py --total-orbits 1000 --steps 10 --warmup 3 --no-e2e --no-png --no-api-e2e --no-cpu-baseline --verify-orbits 2 > gpurun_out/strong1.json 2> gpurun_out/strong1.err
+echo "rc=$?"; cut -c1-1200 gpurun_out/strong1.json; tail -3 gpurun_out/strong1.err | cut -c1-300
+nvidia-smi --query-gpu=memory.used --format=csv,noheader

@@ -230,3 +230,30 @@ def test_oracle_ref_reproduces_the_golden_batch_run(tmp_path):
     assert got["pngs"] == gold["batch_pngs"]
     assert got["extrema"] == gold["batch_extrema"]
     assert all(w > 8 and h > 8 for w, h in got["sizes"])
+
+
+def test_norm_and_colormap_index_against_real_matplotlib():
+    """R9 is restated, not pinned, because matplotlib is not installable offline.  This test pins it by
+    itself the day ``import matplotlib`` succeeds (skipped until then): ``Normalize`` / ``LogNorm`` followed by
+    ``Colormap.__call__(bytes=True)`` must colour every cell like ``restate.normalize | lognorm`` ->
+    ``colormap_index`` -> LUT row (reference call sites ``CS/plotting.py:276-287,316-324``)."""
+    mpl = pytest.importorskip("matplotlib")
+    if not hasattr(mpl, "__version__") or not hasattr(mpl, "colormaps"):
+        pytest.skip("a matplotlib stand-in is on the path, not matplotlib")
+    from matplotlib import colors
+
+    from oracle import restate as R
+
+    rng = np.random.default_rng(9)
+    cmap = mpl.colormaps["viridis"].with_extremes(bad=(0, 0, 0, 0))
+    lut = R.lut_with_extremes((np.asarray(cmap(np.arange(256), bytes=True))).astype(np.uint8))
+    for dtype in (np.float32, np.float64):
+        m = (rng.gamma(0.7, 300.0, (64, 500)) + 1e-3).astype(dtype)
+        m[rng.random(m.shape) < 0.02] = np.nan
+        for vmin, vmax in ((0.5, 2500.0), (1.0, 1.0e4), (3.0, 900.0)):
+            got = np.asarray(cmap(colors.LogNorm(vmin=vmin, vmax=vmax)(m), bytes=True))
+            want = lut[R.colormap_index(R.lognorm(m, vmin, vmax, native_log=True))]
+            assert np.array_equal(got, want), ("log", dtype, vmin, vmax)
+            got = np.asarray(cmap(colors.Normalize(vmin=vmin, vmax=vmax)(np.ma.masked_invalid(m)), bytes=True))
+            want = lut[R.colormap_index(R.normalize(m, vmin, vmax))]
+            assert np.array_equal(got, want), ("linear", dtype, vmin, vmax)
