@@ -760,6 +760,15 @@ def main():
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps
     step.finish()
     barrier()
+
+    def exchange_of(sh):
+        sel = getattr(sh, "_pool_selector_side", None) or getattr(sh, "_pool_selector", None)
+        return getattr(sel, "_exchange", None) if sel is not None else None
+
+    # the last two timed steps' exchanges as rank 0's GPU saw them (6 per step): [start, published, peers seen] in us
+    trace_in_step = None
+    if world > 1 and getattr(exchange_of(shard), "kind", "") == "peer":
+        trace_in_step = exchange_of(shard).trace(12)
     launches = ctx.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
     assert state == state0, "extrema changed between steps"
@@ -789,6 +798,12 @@ def main():
         extrema_finish(pending)
         pool.append(ctx.timer_ms(0))
     pool_ms = float(np.mean(pool))
+    trace_alone = None
+    if world > 1:
+        sel_main = getattr(shard, "_pool_selector", None)
+        ex_main = getattr(sel_main, "_exchange", None) if sel_main is not None else None
+        if getattr(ex_main, "kind", "") == "peer":
+            trace_alone = ex_main.trace(12)
     sampler.mark(1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -845,6 +860,8 @@ def main():
                          "exchanges_per_step": 6, "rendezvous": "torch.distributed NCCL (barriers, timing all-reduce only)"}
         if kind == "peer":
             exchange_info["wait_us"] = exchange.wait_stats(60)
+            exchange_info["trace_us_last_two_timed_steps"] = trace_in_step
+            exchange_info["trace_us_k2b_alone"] = trace_alone
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
 LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 22
+ABI_VERSION = 23
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -200,6 +200,7 @@ SIGNATURES = {
     "csg_threshold_bytes": (_sz, [_i, _i]),
     "csg_panel_prepare": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "csg_rasterise": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "csg_rasterise_blocks_per_sm": (_i, [_vp, _i]),
     "csg_pool_hist_first": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "csg_pool_scan_cols": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "csg_pool_slot_payload_bytes": (_sz, [_i, _i]),
@@ -223,6 +224,7 @@ SIGNATURES = {
     "csg_peer_error_word": (_vp, [_vp]),
     "csg_peer_clear_error": (_i, [_vp, _vp]),
     "csg_peer_wait_stats": (_i, [_vp, _vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "csg_peer_trace": (_i, [_vp, _vp, _i, _vp, C.POINTER(_i)]),
     "csg_peer_disconnect": (_i, [_vp, _vp]),
     "csg_peer_destroy": (_i, [_vp, _vp]),
     "csg_pool_hist_refine": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),

@@ -187,6 +187,23 @@ class PeerExchange:
         self.ctx._check(self.ctx.lib.csg_peer_wait_stats(self.ctx.handle, self.handle, int(last_n), C.byref(mean), C.byref(top)))
         return {"mean_us": mean.value, "max_us": top.value}
 
+    def trace(self, last_n: int = 12) -> list[list[float]]:
+        """Timeline of the last ``last_n`` exchanges, oldest first: ``[kernel start, epoch published, every
+        peer's epoch seen]`` in microseconds since the first entry's start (``%globaltimer`` of this GPU)."""
+        import ctypes as C
+
+        import numpy as np
+
+        if self.handle is None:
+            return []
+        ns = np.zeros(3 * 64, dtype=np.uint64)
+        n = C.c_int()
+        self.ctx._check(self.ctx.lib.csg_peer_trace(self.ctx.handle, self.handle, int(last_n), ns.ctypes.data, C.byref(n)))
+        rows = ns[: 3 * n.value].reshape(-1, 3).astype(np.int64)
+        if not len(rows):
+            return []
+        return [[round(float(v - rows[0, 0]) / 1e3, 2) for v in row] for row in rows]
+
     def allgather(self, src_ptr: int, nbytes: int) -> int:
         import ctypes as C
 

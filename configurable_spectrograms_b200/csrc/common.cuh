@@ -20,6 +20,7 @@ struct csg_ctx {
   int64_t launches;
   void* scratch;  // device scratch owned by the context (grow-only)
   size_t scratch_bytes;
+  int raster_blocks_per_sm;  // csg_rasterise_blocks_per_sm(): cap on K3's persistent blocks per SM (0 = as many as fit)
   int stats_force_exact;  // csg_region_stats_force_exact(): K2a sends every percentile region to the exact select
   char err[512];
 };

@@ -37,6 +37,7 @@ struct csg_peer {
   unsigned* d_counter;
   int* d_error;  // 0, or 1 + the rank whose epoch did not arrive in time
   long long* d_wait_log;  // cycles the last 64 exchanges spent waiting for the other ranks' epochs
+  unsigned long long* d_trace;  // globaltimer ns of the last 64 exchanges: [epoch % 64][kernel start, published, wait over, -]
   bool connected;
 };
 
@@ -48,6 +49,11 @@ struct PeerTable {
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -64,7 +70,8 @@ __global__ void __launch_bounds__(256)
     peer_exchange_kernel(PeerTable tbl, const uint4* __restrict__ src, size_t n16, size_t data_off, size_t flag_off,
                          unsigned long long epoch, unsigned* __restrict__ counter, int n_ranks,
                          const unsigned long long* __restrict__ local_flags, int* __restrict__ error, long long timeout_cycles,
-                         long long* __restrict__ wait_log) {
+                         long long* __restrict__ wait_log, unsigned long long* __restrict__ trace) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) trace[(epoch & 63ull) * 4 + 0] = global_ns();
   uint4* dst = reinterpret_cast<uint4*>(tbl.p[blockIdx.y] + data_off);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
@@ -74,15 +81,18 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(counter, 1u) + 1u;
     s_last = done == gridDim.x * gridDim.y;
-    if (s_last) {  // every block's stores are fenced: publish
+    if (s_last) {  // every block's stores are fenced
       *counter = 0;
       __threadfence_system();
-      for (int r = 0; r < n_ranks; ++r)
-        st_release_sys(reinterpret_cast<unsigned long long*>(tbl.p[r] + flag_off), epoch);
     }
   }
   __syncthreads();
   if (!s_last || threadIdx.x >= 32) return;
+  // publish: lane r tells rank r (one NVLink round trip for the whole warp instead of one per rank)
+  if ((int)threadIdx.x < n_ranks)
+    st_release_sys(reinterpret_cast<unsigned long long*>(tbl.p[threadIdx.x] + flag_off), epoch);
+  __syncwarp();
+  if (threadIdx.x == 0) trace[(epoch & 63ull) * 4 + 1] = global_ns();
   const long long t0 = clock64();
   if ((int)threadIdx.x < n_ranks) {
     while (ld_acquire_sys(local_flags + threadIdx.x) < epoch) {
@@ -94,7 +104,10 @@ __global__ void __launch_bounds__(256)
     }
   }
   __syncwarp();
-  if (threadIdx.x == 0) wait_log[epoch & 63ull] = clock64() - t0;
+  if (threadIdx.x == 0) {
+    wait_log[epoch & 63ull] = clock64() - t0;
+    trace[(epoch & 63ull) * 4 + 2] = global_ns();
+  }
 }
 
 size_t round_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
@@ -115,9 +128,9 @@ int csg_peer_create(csg_ctx* ctx, int rank, int n_ranks, size_t slot_bytes, csg_
   p->flags_bytes = round_up((size_t)p->n_regions * CSG_PEER_MAX * sizeof(unsigned long long), 4096);
   p->mailbox_bytes = p->flags_bytes + (size_t)p->n_regions * n_ranks * p->slot_bytes;
   cudaError_t e = cudaMalloc((void**)&p->local, p->mailbox_bytes);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_counter, 1024);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_counter, 4096);
   if (e == cudaSuccess) e = cudaMemset(p->local, 0, p->mailbox_bytes);  // epochs start at 0
-  if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, 1024);
+  if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, 4096);
   if (e != cudaSuccess) {
     if (p->local) cudaFree(p->local);
     if (p->d_counter) cudaFree(p->d_counter);
@@ -126,6 +139,7 @@ int csg_peer_create(csg_ctx* ctx, int rank, int n_ranks, size_t slot_bytes, csg_
   }
   p->d_error = reinterpret_cast<int*>(p->d_counter) + 32;
   p->d_wait_log = reinterpret_cast<long long*>(p->d_counter) + 32;  // bytes 256 .. 767
+  p->d_trace = reinterpret_cast<unsigned long long*>(p->d_counter) + 128;  // bytes 1024 .. 3071
   p->peers[rank] = p->local;
   if (ipc_handle_64) {
     cudaIpcMemHandle_t h;
@@ -197,7 +211,7 @@ int csg_peer_allgather(csg_ctx* ctx, csg_peer* p, const void* d_src, size_t nbyt
   }
   peer_exchange_kernel<<<dim3(chunks, p->n_ranks), 256, 0, ctx->stream>>>(tbl, (const uint4*)d_src, n16, data_off, flag_off,
                                                                           epoch, p->d_counter, p->n_ranks, flags, p->d_error,
-                                                                          timeout_cycles, p->d_wait_log);
+                                                                          timeout_cycles, p->d_wait_log, p->d_trace);
   CSG_LAUNCH_CHECK(ctx, "peer_exchange_kernel");
   *d_gathered = p->local + region_off;
   return CSG_OK;
@@ -224,6 +238,22 @@ int csg_peer_wait_stats(csg_ctx* ctx, csg_peer* p, int last_n, double* mean_us, 
     if (us > top) top = us;
   }
   *mean_us = sum / last_n, *max_us = top;
+  return CSG_OK;
+}
+
+int csg_peer_trace(csg_ctx* ctx, csg_peer* p, int last_n, uint64_t* ns3, int* n_written) {
+  if (!ctx || !p || !ns3 || !n_written) return CSG_ERR_ARG;
+  *n_written = 0;
+  unsigned long long log[256];
+  CSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CSG_CUDA(ctx, cudaMemcpy(log, p->d_trace, sizeof log, cudaMemcpyDeviceToHost));
+  if (last_n > 64) last_n = 64;
+  if ((unsigned long long)last_n > p->epoch) last_n = (int)p->epoch;
+  for (int k = 0; k < last_n; ++k) {  // oldest first
+    const unsigned long long e = p->epoch - (unsigned long long)(last_n - 1 - k);
+    for (int j = 0; j < 3; ++j) ns3[3 * k + j] = log[(e & 63ull) * 4 + j];
+  }
+  *n_written = last_n > 0 ? last_n : 0;
   return CSG_OK;
 }
 

@@ -644,7 +644,8 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
                                        (int)raster_smem_bytes<double>()));
     configured = true;
   }
-  const int per_sm = dtype == CSG_F32 ? 3 : 2;
+  int per_sm = dtype == CSG_F32 ? 3 : 2;
+  if (ctx->raster_blocks_per_sm > 0 && ctx->raster_blocks_per_sm < per_sm) per_sm = ctx->raster_blocks_per_sm;
   int grid = ctx->sm_count * per_sm;
   if (grid > total_blocks) grid = total_blocks;
   if (dtype == CSG_F32)
@@ -658,6 +659,12 @@ int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg_region*
   else
     return csg_fail(ctx, CSG_ERR_ARG, "bad dtype %d", dtype);
   CSG_LAUNCH_CHECK(ctx, "rasterise_kernel");
+  return CSG_OK;
+}
+
+int csg_rasterise_blocks_per_sm(csg_ctx* ctx, int blocks_per_sm) {
+  if (!ctx || blocks_per_sm < 0) return CSG_ERR_ARG;
+  ctx->raster_blocks_per_sm = blocks_per_sm;
   return CSG_OK;
 }
 

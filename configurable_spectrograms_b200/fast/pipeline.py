@@ -585,7 +585,17 @@ class BatchStep:
                 return
             b.run_stats()
             b.prepare(part=0)
-            b.rasterise(want_rgba=want_rgba, want_index=self.want_index, part=0)
+            # with several ranks the digit loop and its peer exchanges are still running on the side stream
+            # at this point, and K3's persistent blocks would fill every SM to the last register: leave room
+            # (measured at 8 GPUs: the loop's next kernel waited 190-360 us for K3 to END)
+            share = self.comm is not None and state is None and planned
+            if share:
+                b.ctx._check(b.ctx.lib.csg_rasterise_blocks_per_sm(b.ctx.handle, _k3_shared_blocks()))
+            try:
+                b.rasterise(want_rgba=want_rgba, want_index=self.want_index, part=0)
+            finally:
+                if share:
+                    b.ctx._check(b.ctx.lib.csg_rasterise_blocks_per_sm(b.ctx.handle, 0))
 
         if state is None:
             pending = extrema_enqueue(sh, self.sequence, sh.instrument_order, sh.y_scale, sh.z_scale,
@@ -632,6 +642,16 @@ class BatchStep:
         if b._windows:
             self.shard.resolve_zoom_flags(self._win_pin.view(np.uint8, len(b._windows)))
         return self.state
+
+
+def _k3_shared_blocks() -> int:
+    """K3 blocks per SM while the extrema chain runs beside it (``CSG_K3_SHARED_BLOCKS``, default 2; 0 = no cap)."""
+    import os
+
+    try:
+        return max(0, int(os.environ.get("CSG_K3_SHARED_BLOCKS", "2")))
+    except ValueError:
+        return 2
 
 
 def check_norm_status(norm_row, what: str):

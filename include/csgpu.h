@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 22
+#define CSG_ABI_VERSION 23
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -283,6 +283,12 @@ CSG_API int csg_rasterise(csg_ctx* ctx, const void* d_mats, int dtype, const csg
                   const csg_panel_norm* d_norms, const void* d_thresholds, int n_panels,
                   int total_blocks, int block_offset, const int32_t* d_block_panel, const uint8_t* d_lut,
                   uint8_t* d_rgba, uint16_t* d_index);
+/* K3 runs persistent blocks, as many as fit an SM (3 for float32: 1536 threads, 61 K registers, 199 KB shared).
+ * A full house leaves no room for ANY other block, so kernels on a concurrent high-priority stream -- the
+ * global-extrema digit loop and its peer exchanges (K2b) -- stall until K3 ends.  While such a chain is in
+ * flight the batch step caps K3 at 2 blocks per SM (0 restores the default): K3 loses a little occupancy, the
+ * chain keeps moving.  Applies to the following csg_rasterise calls of this context. */
+CSG_API int csg_rasterise_blocks_per_sm(csg_ctx* ctx, int blocks_per_sm);
 
 /* ---------------------------------------------- K2b: global extrema (pooled) */
 /* The pooled finite-positive samples of CS/fast/extrema.py:259-267 are never
@@ -437,6 +443,11 @@ CSG_API void* csg_peer_error_word(csg_peer* peer);
 /* Time the last `last_n` (<= 64) all-gathers spent waiting for the other ranks' epochs, in microseconds:
  * rank skew + link latency, measured inside the exchange kernel with clock64 (synchronises the stream). */
 CSG_API int csg_peer_wait_stats(csg_ctx* ctx, csg_peer* peer, int last_n, double* mean_us, double* max_us);
+/* Timeline of the last `last_n` (<= 64) exchanges, oldest first: ns3[3k + {0,1,2}] = %globaltimer nanoseconds at
+ * which exchange k's kernel started, published its epoch to the peers, and saw every peer's epoch; *n_written =
+ * how many exchanges were written.  The gap between "saw" of one exchange and "started" of the next is the
+ * consumer / producer kernels in between. */
+CSG_API int csg_peer_trace(csg_ctx* ctx, csg_peer* peer, int last_n, uint64_t* ns3, int* n_written);
 CSG_API int csg_peer_clear_error(csg_ctx* ctx, csg_peer* peer); /* on the ctx stream */
 /* Unmap the other ranks' mailboxes (every rank does this, then a barrier, before any rank destroys its
  * own mailbox: an exporter must not free memory an importer still has open). */

@@ -1,5 +1,10 @@
 #!/bin/bash
-# scratch GPU job (rewritten per gpurun call): strong-scaling point N=1 of config 4 (1000 orbits on one GPU)
-timeout 1500 python bench.py --total-orbits 1000 --steps 10 --warmup 3 --no-e2e --no-png --no-api-e2e --no-cpu-baseline --verify-orbits 2 > gpurun_out/strong1.json 2> gpurun_out/strong1.err
-echo "rc=$?"; cut -c1-1200 gpurun_out/strong1.json; tail -3 gpurun_out/strong1.err | cut -c1-300
-nvidia-smi --query-gpu=memory.used --format=csv,noheader
+# scratch GPU job: host profile of the timed step loop (1 GPU)
+python bench.py --steps 200 --warmup 5 --no-e2e --no-png --no-api-e2e --no-verify --no-cpu-baseline --profile-host gpurun_out/host_prof > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo rc=$?
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms/step", d["ms_per_step"], d["stage_ms"])
+PY
+head -70 gpurun_out/host_prof.rank0 | cut -c1-200
