@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--api-ref", action="store_true", help="also run the unmodified reference over the SAME api_e2e directory (minutes)")
     ap.add_argument("--no-verify", action="store_true", help="skip the parity leg (outside the timed region)")
     ap.add_argument("--verify-orbits", type=int, default=3, help="orbits of this shard whose every panel is compared with the oracle")
+    ap.add_argument("--profile-region", default="steps", choices=("steps", "png"),
+                    help="what sits between cudaProfilerStart/Stop for `ncu --profile-from-start off`: the timed steps or the PNG stage")
     ap.add_argument("--profile-host", default=None, help="write a cProfile of the timed step loop to this path")
     return ap.parse_args()
 
@@ -736,7 +738,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = ctx.launch_count()
-    torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` sees the timed steps only
+    if args.profile_region == "steps":
+        torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` sees the timed steps only
     host_t0 = time.perf_counter()
     prof = None
     if args.profile_host:
@@ -748,7 +751,8 @@ def main():
     for _ in range(args.steps):
         state = step.run({})
     ev1.record(tstream)
-    torch.cuda.profiler.stop()
+    if args.profile_region == "steps":
+        torch.cuda.profiler.stop()
     if prof is not None:
         prof.disable()
         import io
@@ -827,9 +831,13 @@ def main():
         figs = [f for f in (figure_from_spec(shard, sp, "turbo", norms=norms, device_rasters=True)[0] for sp in specs) if f is not None]
         PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, dpi=200)  # warm-up: tables, sprites, device and pinned scratch
         phases: dict = {}
+        if args.profile_region == "png":
+            torch.cuda.profiler.start()
         t0 = time.perf_counter()
         blobs = PNG.encode_figures_device(ctx, shard.batch.d_rgba.ptr, figs, dpi=200, timings=phases)
         dev_s = time.perf_counter() - t0
+        if args.profile_region == "png":
+            torch.cuda.profiler.stop()
 
         def raw_size(f):  # filtered bytes of the figure at 200 dpi
             W, H = int(round(f.figsize[0] * 200)), int(round(f.figsize[1] * 200))
