@@ -36,6 +36,7 @@ namespace {
 
 constexpr int kSegPixels = 1024;
 constexpr int kMatchWindow = 128;    // pixels a match may reach back (distance <= 512 bytes)
+constexpr int kShortWindow = 8;      // ... while the lane's recent pixels found nothing (noise: see the tokeniser)
 constexpr int kPieces = 32;          // lanes
 constexpr int kPiecePixels = 32;     // pixels per lane
 constexpr int kPixStride = 33;       // padded piece stride (words): conflict-free column reads
@@ -181,14 +182,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     if (which) n_up = n; else n_list = n;
   }
   __syncwarp();
+  // ---- where can this scanline differ from the one above?  When both cross the same tiles in the same order,
+  // a pixel's winner is the same tile on both lines and only a tile whose SOURCE row moved on can change it:
+  // everything outside those tiles' columns is zero after the Up filter and is never evaluated (a colour bar
+  // stepping to its next colour dirties 60 of 4800 pixels; a segment it does not touch is dismissed here).
+  int dirty0 = x0, dirty1 = x0 + npx;
+  if (row > 0 && n_list == n_up) {
+    bool structural = false;
+    int d0 = 0x7fffffff, d1 = -1;
+    for (int i = lane; i < n_list; i += 32) {
+      const SegTile a = list[i], b = list_up[i];
+      if (a.tx != b.tx || a.x0 != b.x0 || a.x1 != b.x1 || a.xs != b.xs || a.nt_minus_1 != b.nt_minus_1 ||
+          a.vline_first != b.vline_first || a.vline_count != b.vline_count)
+        structural = true;  // another tile: the line starts or ends something
+      else if (a.row != b.row)
+        d0 = min(d0, (int)a.x0), d1 = max(d1, (int)a.x1);
+    }
+    structural = __any_sync(0xffffffffu, structural);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 = min(d0, __shfl_xor_sync(0xffffffffu, d0, o));
+      d1 = max(d1, __shfl_xor_sync(0xffffffffu, d1, o));
+    }
+    if (!structural) dirty0 = d0, dirty1 = d1;  // empty when d1 < d0
+  }
 
   // ---- phase 1: compose + Up filter (coalesced), Adler partial sums
   unsigned* pix = s_pix[warp];
   unsigned long long sa = 0, sb = 0;
   unsigned nonzero = 0;
   for (int p = lane; p < npx; p += 32) {
-    const unsigned cur = mosaic_pixel(list, n_list, vlines, x0 + p, cv.background);
-    const unsigned f = filter_type ? sub4(cur, mosaic_pixel(list_up, n_up, vlines, x0 + p, cv.background)) : cur;
+    const int x = x0 + p;
+    if (x < dirty0 || x >= dirty1) {  // same winner, same source row as above
+      pix[(p >> 5) * kPixStride + (p & 31)] = 0u;
+      continue;
+    }
+    const unsigned cur = mosaic_pixel(list, n_list, vlines, x, cv.background);
+    const unsigned f = filter_type ? sub4(cur, mosaic_pixel(list_up, n_up, vlines, x, cv.background)) : cur;
     pix[(p >> 5) * kPixStride + (p & 31)] = f;
     nonzero |= f;
     const unsigned b0 = f & 255u, b1 = (f >> 8) & 255u, b2 = (f >> 16) & 255u, b3 = f >> 24;
@@ -236,8 +266,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   const int p_begin = lane * kPiecePixels, p_end = min(npx_tok, p_begin + kPiecePixels);
   if (p_begin < npx_tok) {
     // pixel q of the segment (any lane's piece): matches may reach back into earlier pieces
-    auto at = [&](int q) { return pix[(q >> 5) * kPixStride + (q & 31)]; };
+    static_assert(kPixStride == 33 && kPiecePixels == 32, "at(): q + (q >> 5) is the padded index");
+    auto at = [&](int q) { return pix[q + (q >> 5)]; };
     int run = 0, dist = 0;  // an open match of `run` pixels at distance `dist` pixels
+    // The backward search was 62 % of this kernel's instructions (ncu, profiles/r2_ncu_full_png.txt): a pixel
+    // of a line with new content (the difference of two neighbouring spectrogram rows) usually has no equal
+    // within reach and pays for all 128 probes.  After two misses in a row the lane only looks 8 pixels
+    // back until something matches again: noise costs 16x less, structure keeps the full window.
+    int misses = 0;
     auto flush = [&]() {
       if (run) {
         if (cnt) {
@@ -257,16 +293,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
       }
       flush();
       int k = 0;
-      const int reach = p < kMatchWindow ? p : kMatchWindow;
+      const int reach = min(p, misses >= 2 ? kShortWindow : kMatchWindow);
       for (int d = 1; d <= reach; ++d)
         if (at(p - d) == x) {
           k = d;
           break;
         }
       if (k) {
-        run = 1, dist = k;
+        run = 1, dist = k, misses = 0;
         continue;
       }
+      ++misses;
       const unsigned b0 = x & 255u, b1 = (x >> 8) & 255u, b2 = (x >> 16) & 255u, b3 = x >> 24;
       if (cnt) {
         atomicAdd(&cnt[b0], 1u);

@@ -1,11 +1,12 @@
 #!/bin/bash
-# scratch GPU job: round-2 ncu evidence (launch list of the timed steps; full captures of K1 / K2a / K3 / K4)
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-api-e2e --no-verify --no-cpu-baseline --png-orbits 2"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
-echo "launch list rc=$?"; tail -2 gpurun_out/ncu_launches.log | cut -c1-200
-ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:collapse_stream|region_stats_kernel|rasterise_kernel" -c 6 -o gpurun_out/r2_prof_step $CMD > gpurun_out/ncu_step.log 2>&1
-echo "step capture rc=$?"; tail -2 gpurun_out/ncu_step.log | cut -c1-200
-ncu --set full --clock-control none --import-source on -k "regex:png_encode_kernel" -s 1 -c 2 -o gpurun_out/r2_prof_png $CMD > gpurun_out/ncu_png.log 2>&1
-echo "png capture rc=$?"; tail -2 gpurun_out/ncu_png.log | cut -c1-200
-ls -la gpurun_out/
+# scratch GPU job: K4 adaptive match window, with / without per-row tile lists
+python -m pytest tests/test_gpu_png.py -m gpu -x -q 2>&1 | tail -2
+for rt in 1 0; do
+CSG_PNG_ROW_TILES=$rt python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-verify --no-e2e > gpurun_out/bench_rt$rt.json 2> gpurun_out/bench.err
+python - $rt <<'PY'
+import json, sys
+d=json.loads(open(f"gpurun_out/bench_rt{sys.argv[1]}.json").read().strip().splitlines()[-1])
+p=d["png_stage"]; print("row_tiles", sys.argv[1], "png figs/s", round(p["device_figures_per_s"]), "ratio", round(p["device_ratio"],2), {k: round(v,4) for k,v in p["phases_s"].items()})
+a=d["api_e2e"]; print("   api", round(a["value"],2), round(a["warm"]["seconds"],3), "png_mb", a["warm"]["png_mb"], {k: v for k,v in a["warm"]["phases_s"].items() if k.startswith("png") or k=="figures_host"})
+PY
+done
