@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from datetime import datetime, timezone
 
+import math
+
 import numpy as np
 
 from . import _lib
@@ -53,6 +55,16 @@ def date2num(unix_seconds):
     ``_dt64_to_ordinalf`` then computes ``(whole_seconds + microseconds * 1000 / 1e9) / 86400``
     in float64.  Both steps are reproduced so the extents and marker positions match bit for bit.
     """
+    if type(unix_seconds) in (float, int, np.float64):  # the per-panel limits and marker positions: plain float math
+        frac, whole = math.modf(float(unix_seconds))
+        micro = float(round(frac * 1e6))  # round(): half to even, like np.rint
+        if micro == 0.0:
+            micro = math.copysign(0.0, frac)  # (np.rint keeps the sign of a zero)
+        if micro >= 1e6:
+            whole, micro = whole + 1.0, micro - 1e6
+        if micro < 0:  # negative timestamps: borrow a second, like divmod
+            whole, micro = whole - 1.0, micro + 1e6
+        return (whole + (micro * 1000.0) / 1.0e9) / 86400.0
     t = np.asarray(unix_seconds, dtype=np.float64)
     frac, whole = np.modf(t)
     micro = np.rint(frac * 1e6)

@@ -1,12 +1,14 @@
 #!/bin/bash
-# scratch GPU job: K4 adaptive match window, with / without per-row tile lists
-python -m pytest tests/test_gpu_png.py -m gpu -x -q 2>&1 | tail -2
-for rt in 1 0; do
-CSG_PNG_ROW_TILES=$rt python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-verify --no-e2e > gpurun_out/bench_rt$rt.json 2> gpurun_out/bench.err
-python - $rt <<'PY'
-import json, sys
-d=json.loads(open(f"gpurun_out/bench_rt{sys.argv[1]}.json").read().strip().splitlines()[-1])
-p=d["png_stage"]; print("row_tiles", sys.argv[1], "png figs/s", round(p["device_figures_per_s"]), "ratio", round(p["device_ratio"],2), {k: round(v,4) for k,v in p["phases_s"].items()})
-a=d["api_e2e"]; print("   api", round(a["value"],2), round(a["warm"]["seconds"],3), "png_mb", a["warm"]["png_mb"], {k: v for k,v in a["warm"]["phases_s"].items() if k.startswith("png") or k=="figures_host"})
+# scratch GPU job: what the driver runs at round end, on one GPU
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest.log; cat gpurun_out/pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -3
+python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-900 gpurun_out/bench_ref.json
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("metric","value","unit","n_gpus","steps","warmup","ms_per_step","scaling","vs_baseline","dtype","gpu_launches")})
+print("roofline", d["roofline"]); print("e2e", d["e2e"]); print("cpu", d["cpu_baseline"]); print("clocks", d["clocks"])
+print("api", d["api_e2e"]["value"], d["api_e2e"]["warm"]["seconds"], d["api_e2e"]["warm"]["phases_s"])
+print("png", d["png_stage"]["device_figures_per_s"], "parity", d["parity_checked"]["ok"])
 PY
-done

@@ -103,6 +103,11 @@ def test_date2num_matches_datetime_path():
     ref = np.array([stubs.date2num(datetime.fromtimestamp(float(x), tz=timezone.utc)) for x in t])
     assert np.array_equal(date2num(t).view(np.uint64), ref.view(np.uint64))
     assert date2num(946684800.0) == ref[0]
+    # the scalar path (plain float arithmetic: panel limits, marker positions) against the vectorised one,
+    # bit for bit, negative timestamps and signed zeros included
+    more = np.concatenate([t, rng.uniform(-1e6, 2e9, 5000), [0.0, -0.0, -0.5, -1e-7, 1e-7, 1.9999995, 0.9999995]])
+    scalars = np.array([date2num(float(x)) for x in more])
+    assert np.array_equal(scalars.view(np.uint64), date2num(more).view(np.uint64))
 
 
 def test_png_up_filter_decode_and_adler_of_segments():
