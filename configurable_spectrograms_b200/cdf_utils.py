@@ -114,19 +114,33 @@ def get_timestamps_for_orbit(filtered_orbits_dataframe, orbit_number, instrument
     if frame is None or instrument_type is None or time_unix_array is None:
         return []
     key = (id(frame), instrument_type)
-    if key not in orbit_column_cache:
+    cached = orbit_column_cache.get(key)
+    if cached is None or cached[0] is not frame:  # (the entry keeps its frame alive, so an id is never re-used under it)
         lowered = {c: c.lower() for c in frame.columns}
         orbit_col = next(c for c, l in lowered.items() if "orbit" in l)
         lo_col = next(c for c, l in lowered.items() if instrument_type in l and "min index" in l)
         hi_col = next(c for c, l in lowered.items() if instrument_type in l and "max index" in l)
-        orbit_column_cache[key] = (orbit_col, lo_col, hi_col)
-    orbit_col, lo_col, hi_col = orbit_column_cache[key]
-    hit = frame[frame[orbit_col] == orbit_number]
-    if hit.empty:
+        # first row per orbit number, like ``frame[frame[orbit] == n].iloc[0]`` -- looked up once per file of a
+        # directory run, where the boolean-mask filter of the whole table cost milliseconds per call
+        first_rows: dict = {}
+        for number, lo_value, hi_value in zip(frame[orbit_col].tolist(), frame[lo_col].tolist(), frame[hi_col].tolist()):
+            try:
+                first_rows.setdefault(number, (lo_value, hi_value))
+            except TypeError:  # an unhashable cell can never equal an orbit number
+                pass
+        if len(orbit_column_cache) > 64:
+            orbit_column_cache.clear()
+        cached = orbit_column_cache[key] = (frame, first_rows)
+    first_rows = cached[1]
+    try:
+        hit = first_rows.get(orbit_number)
+    except TypeError:
+        hit = None
+    if hit is None:
         return []
     try:
-        lo = int(hit.iloc[0][lo_col])
-        hi = int(hit.iloc[0][hi_col])
+        lo = int(hit[0])
+        hi = int(hit[1])
     except (TypeError, ValueError):
         log_message("[WARN] Non-integer indices found in orbit row, using 0.")
         return []

@@ -344,7 +344,14 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
 
     png_timings: dict | None = {} if timings is not None else None
     code_cache: dict = {}  # the DEFLATE code fitted to the first chunk's figures serves the whole run
-    previous_chunk = None
+    # K4 runs on a companion context (its own stream): chunk k's encode kernel works while the host plans chunk
+    # k + 1 and its K2a / K3 run on the main stream -- into the OTHER of two raster buffers, the one chunk k - 1's
+    # encode has long finished with.  A chunk passes through three states: `encoding` (kernel launched),
+    # `writing` (compressed bytes read back, native threads framing and writing), settled (progress recorded).
+    encoder_ctx = ctx.worker_context()
+    raster_buffers: list = [None, None]
+    encoding = writing = None
+    n_chunk = 0
 
     def settle(chunk_state, since_flush):
         """The host half of a chunk ends here: its PNG files are on disk (the framing and writing ran on the
@@ -380,9 +387,12 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
             chunk = my_pending[a : a + chunk_n]
             t_chunk = _time.perf_counter()
             step = BatchStep(shard, sequence, comm=comm, lut259=lut, plot_orbits=chunk, submissions=submissions)
+            b.d_rgba = raster_buffers[n_chunk & 1]  # not the buffer the previous chunk's encode kernel is reading
             step.run(state=global_extrema if global_extrema is not None else {}, collapse=False)
             t_phase = tick("plan_and_enqueue", t_phase)
             step.finish()
+            raster_buffers[n_chunk & 1] = b.d_rgba
+            n_chunk += 1
             norms = b.norms() if b.n_panels else None
             t_phase = tick("kernels_wait", t_phase)
 
@@ -437,21 +447,32 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
                     by_path[path] = fig
             saves = list(by_path.items())
             t_phase = tick("figures_host", t_phase)
-            if previous_chunk is not None:  # its files were framed and written while this chunk was planned
-                since_flush = settle(previous_chunk, since_flush)
-                previous_chunk = None
+            if writing is not None:  # the chunk before last: its files were written while two chunks were planned
+                since_flush = settle(writing, since_flush)
+                writing = None
                 t_phase = tick("png_wait_previous_chunk", t_phase)
-            writes = []
+            if encoding is not None:  # the last chunk: its kernel ran while this one was planned
+                if not isinstance(encoding[0], list):
+                    encoding[0] = encoding[0].complete()
+                writing, encoding = encoding, None
+                t_phase = tick("png_read_back", t_phase)
             if saves:
-                writes = write_figures_device(ctx, b.d_rgba.ptr, saves, max_workers=n_threads, dpi=SAVE_DPI, timings=png_timings,
-                                              wait=False, code_cache=code_cache)
+                encoder_ctx.wait_for(ctx)  # (the rasters are complete: step.finish() above; ordering kept explicit)
+                handle = write_figures_device(encoder_ctx, b.d_rgba.ptr, saves, max_workers=n_threads, dpi=SAVE_DPI,
+                                              timings=png_timings, wait=False, defer=True, code_cache=code_cache,
+                                              max_segments=1_000_000)
                 for _path, fig in saves:
                     close_all_axes_and_clear(fig)
-            previous_chunk = (writes, [path for path, _f in saves], planned, len(jobs), _time.perf_counter() - t_chunk)
+                encoding = [handle, [path for path, _f in saves], planned, len(jobs), _time.perf_counter() - t_chunk]
+            else:  # nothing to draw: the chunk still takes its turn, so that progress is recorded in orbit order
+                encoding = [[], [], planned, len(jobs), _time.perf_counter() - t_chunk]
             t_phase = tick("png_encode", t_phase)
-        if previous_chunk is not None:
-            since_flush = settle(previous_chunk, since_flush)
-            t_phase = tick("png_wait_last_chunk", t_phase)
+        for state in (writing, encoding):  # oldest first: progress is recorded in orbit order
+            if state is not None:
+                if not isinstance(state[0], list):
+                    state[0] = state[0].complete()
+                since_flush = settle(state, since_flush)
+        t_phase = tick("png_wait_last_chunk", t_phase)
 
     if world > 1:  # every rank returns every result; rank 0 owns the progress file
         gathered: list = [None] * world

@@ -404,7 +404,7 @@ def _device_tables(figures, dpi):
 
 def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = None, max_segments: int = 400_000, consume=None,
                           timings: dict | None = None, huffman: str = "custom", wait: bool = True, code_cache: dict | None = None,
-                          paths=None, write_threads: int = 16):
+                          paths=None, write_threads: int = 16, defer: bool = False):
     """PNG bytes of every figure, composed and DEFLATE-encoded on the GPU.
 
     ``figures``: :class:`figure.SpectrogramFigure` objects whose panels were drawn from
@@ -428,6 +428,11 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
     ``writev`` from the pinned buffer on ``write_threads`` native threads, no interpreter lock held) instead of
     building them here; nothing is returned or handed to ``consume`` then.
 
+    ``defer=True`` (with ``wait=False``): the LAST group's encode kernel is only launched; the call returns a
+    :class:`DeferredEncode` whose ``complete()`` reads the sizes back, compacts, copies out and hands the
+    group to the finisher thread -- the caller does host work (plans the next chunk) while the kernel runs,
+    and must call ``complete()`` before the next encode on this context.
+
     ``wait=False`` (needs ``consume`` or ``paths``): return as soon as the last group is read back, with the futures of
     the host work (framing + ``consume``) still running on the context's finisher thread; the caller
     collects them (``future.result()``) before it relies on the files.  The next call on the same context
@@ -449,6 +454,10 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
     canvases, tiles, rows, per_figure = _device_tables(figures, dpi)
     slot = int(lib.csg_png_slot_bytes())
     scratch = ctx.__dict__.setdefault("_png_scratch", {})
+    if scratch.get("deferred") is not None:
+        raise RuntimeError("a deferred encode is still open on this context: call its complete() first")
+    if defer and wait:
+        raise ValueError("defer=True needs wait=False")
 
     def dev(name, nbytes):
         buf = scratch.get(name)
@@ -479,7 +488,96 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
                                       "in_flight": [None, None], "groups": 0}
     finisher, framers, in_flight = pipe["pool"], pipe["framers"], pipe["in_flight"]  # in_flight: the future reading pinned buffer 0 / 1
     mine: list = []
+
+    def launch(k, group, n_seg):
+        """Tables of the group, the code of the call (first group), the encode kernel: nothing waits for the GPU
+        except the one-time count pass."""
+        t0 = time.perf_counter()
+        table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
+        d_canvases = ctx.to_device(table)
+        if k == 0:  # the code of this call
+            if huffman == "custom" and code_cache is not None and "tables" in code_cache:
+                ctx._check(lib.csg_png_set_tables(ctx.handle, code_cache["tables"].ctypes.data))
+            elif huffman == "custom":
+                d_counts = dev("counts", 316 * 4)
+                d_counts.zero()
+                ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
+                ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                             d_rows.ptr, n_seg, 4, d_counts.ptr, *zero_args))
+                tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
+                ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
+                if code_cache is not None:
+                    code_cache["tables"] = tables
+            elif huffman == "fixed":
+                ctx._check(lib.csg_png_set_tables(ctx.handle, None))
+            else:
+                raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
+            t0 = tick("code_tables", t0)
+        d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
+        ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
+                                      d_rows.ptr, n_seg, d_slots.ptr, d_sizes.ptr, d_adler.ptr, d_error.ptr, *zero_args))
+        tick("encode_launch", t0)
+        return (k, group, n_seg, d_canvases, d_slots, d_sizes, d_adler)
+
+    def complete(state):
+        """Sizes back (waits for the kernel), compaction, read-back into a pinned buffer, hand-over."""
+        k, group, n_seg, _d_canvases, d_slots, d_sizes, d_adler = state
+        t0 = time.perf_counter()
+        sizes = d_sizes.download(np.int32, n_seg, sync=False)
+        bad = d_error.download(np.int32, 1, sync=False)
+        adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
+        if bad[0]:
+            raise ValueError(f"figure {k + int(bad[0]) - 1}: more than {int(lib.csg_png_max_segment_tiles())} tiles meet in one "
+                             "1024-pixel scanline segment")
+        t0 = tick("encode_kernel_and_sizes", t0)
+        offsets = np.zeros(n_seg + 1, dtype=np.int64)
+        np.cumsum(sizes, out=offsets[1:])
+        total = int(offsets[-1])
+        d_off = dev("offsets", n_seg * 8)
+        d_off.upload(offsets[:-1])
+        d_packed = dev("packed", total)
+        ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
+        parity = pipe["groups"] & 1
+        if in_flight[parity] is not None:
+            in_flight[parity].result()  # the group that last used this pinned buffer is on disk
+            in_flight[parity] = None
+            t0 = tick("wait_for_host", t0)
+        name = f"pinned{parity}"
+        pin = scratch.get(name)
+        if pin is None or pin.nbytes < total:
+            pin = scratch[name] = ctx.pinned(int(total * 1.2) + 4096)
+        ctx._check(lib.csg_d2h(ctx.handle, pin.ptr, d_packed.ptr, total))
+        ctx.sync()
+        t0 = tick("compact_and_d2h", t0)
+
+        def finish(first=k, group=group, jobs=per_figure[k : k + len(group)], packed=pin.array, offsets=offsets, adler=adler):
+            t1 = time.perf_counter()
+            if paths is not None:
+                write_files_native(lib, paths[first : first + len(group)], group, jobs, rows, packed, offsets, adler, write_threads)
+                tick("frame_and_write_native", t1)
+                return
+            parts = list(framers.map(lambda job: assemble_png(job[1][0], job[1][1], job[1][2], job[0][6], packed, offsets, job[0][5], adler),
+                                     zip(group, jobs)))
+            t1 = tick("framing_crc", t1)
+            if consume is not None:
+                consume(first, parts)  # the buffers alias pinned scratch that the group after next overwrites
+            else:
+                results[first] = [b"".join(p) for p in parts]
+            tick("consume", t1)
+
+        in_flight[parity] = finisher.submit(finish)
+        mine.append(in_flight[parity])
+        pipe["groups"] += 1
+
+    def settle_failed():
+        for fut in mine:  # leave no work of a failed call behind
+            try:
+                fut.result()
+            except Exception:
+                pass
+
     k = 0
+    open_state = None
     try:
         while k < len(figures):
             # ---- the next group of figures that fits the segment budget
@@ -492,83 +590,32 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
                 c[5] = n_seg
                 group.append(c)
                 n_seg += segs
-            t0 = time.perf_counter()
-            table = np.array([tuple(c) for c in group], dtype=PNG_CANVAS)
-            d_canvases = ctx.to_device(table)
-            if k == 0:  # the code of this call
-                if huffman == "custom" and code_cache is not None and "tables" in code_cache:
-                    ctx._check(lib.csg_png_set_tables(ctx.handle, code_cache["tables"].ctypes.data))
-                elif huffman == "custom":
-                    d_counts = dev("counts", 316 * 4)
-                    d_counts.zero()
-                    ctx._check(lib.csg_png_set_tables(ctx.handle, None))  # the count pass needs valid symbol tables
-                    ctx._check(lib.csg_png_count(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
-                                                 d_rows.ptr, n_seg, 4, d_counts.ptr, *zero_args))
-                    tables = np.ascontiguousarray(custom_tables(d_counts.download(np.uint32, 316)))
-                    ctx._check(lib.csg_png_set_tables(ctx.handle, tables.ctypes.data))
-                    if code_cache is not None:
-                        code_cache["tables"] = tables
-                elif huffman == "fixed":
-                    ctx._check(lib.csg_png_set_tables(ctx.handle, None))
-                else:
-                    raise ValueError(f"huffman must be 'custom' or 'fixed', not {huffman!r}")
-                t0 = tick("code_tables", t0)
-            d_slots, d_sizes, d_adler = dev("slots", n_seg * slot), dev("sizes", n_seg * 4), dev("adler", n_seg * 8)
-            ctx._check(lib.csg_png_encode(ctx.handle, d_rgba_ptr, d_overlay, d_canvases.ptr, len(group), d_tiles.ptr, None,
-                                          d_rows.ptr, n_seg, d_slots.ptr, d_sizes.ptr, d_adler.ptr, d_error.ptr, *zero_args))
-            sizes = d_sizes.download(np.int32, n_seg, sync=False)
-            bad = d_error.download(np.int32, 1, sync=False)
-            adler = d_adler.download(np.uint32, 2 * n_seg).reshape(n_seg, 2)  # synchronises
-            if bad[0]:
-                raise ValueError(f"figure {k + int(bad[0]) - 1}: more than {int(lib.csg_png_max_segment_tiles())} tiles meet in one "
-                                 "1024-pixel scanline segment")
-            t0 = tick("encode_kernel_and_sizes", t0)
-            offsets = np.zeros(n_seg + 1, dtype=np.int64)
-            np.cumsum(sizes, out=offsets[1:])
-            total = int(offsets[-1])
-            d_off = dev("offsets", n_seg * 8)
-            d_off.upload(offsets[:-1])
-            d_packed = dev("packed", total)
-            ctx._check(lib.csg_png_compact(ctx.handle, d_slots.ptr, d_sizes.ptr, d_off.ptr, n_seg, d_packed.ptr))
-            parity = pipe["groups"] & 1
-            if in_flight[parity] is not None:
-                in_flight[parity].result()  # the group that last used this pinned buffer is on disk
-                in_flight[parity] = None
-                t0 = tick("wait_for_host", t0)
-            name = f"pinned{parity}"
-            pin = scratch.get(name)
-            if pin is None or pin.nbytes < total:
-                pin = scratch[name] = ctx.pinned(int(total * 1.2) + 4096)
-            ctx._check(lib.csg_d2h(ctx.handle, pin.ptr, d_packed.ptr, total))
-            ctx.sync()
-            t0 = tick("compact_and_d2h", t0)
-
-            def finish(first=k, group=group, jobs=per_figure[k : k + len(group)], packed=pin.array, offsets=offsets, adler=adler):
-                t1 = time.perf_counter()
-                if paths is not None:
-                    write_files_native(lib, paths[first : first + len(group)], group, jobs, rows, packed, offsets, adler, write_threads)
-                    tick("frame_and_write_native", t1)
-                    return
-                parts = list(framers.map(lambda job: assemble_png(job[1][0], job[1][1], job[1][2], job[0][6], packed, offsets, job[0][5], adler),
-                                         zip(group, jobs)))
-                t1 = tick("framing_crc", t1)
-                if consume is not None:
-                    consume(first, parts)  # the buffers alias pinned scratch that the group after next overwrites
-                else:
-                    results[first] = [b"".join(p) for p in parts]
-                tick("consume", t1)
-
-            in_flight[parity] = finisher.submit(finish)
-            mine.append(in_flight[parity])
+            state = launch(k, group, n_seg)
             k += len(group)
-            pipe["groups"] += 1
+            if defer and k >= len(figures):
+                open_state = state
+                break
+            complete(state)
     except BaseException:
-        for fut in mine:  # leave no work of a failed call behind
-            try:
-                fut.result()
-            except Exception:
-                pass
+        settle_failed()
         raise
+    if open_state is not None:
+        keep_alive = {"tables": (d_tiles, d_rows, d_zero)}  # device tables the open kernel reads
+
+        def complete_open():
+            try:
+                complete(open_state)
+            except BaseException:
+                settle_failed()
+                raise
+            finally:
+                scratch["deferred"] = None
+                keep_alive.clear()
+            return mine
+
+        handle = DeferredEncode(complete_open)
+        scratch["deferred"] = handle
+        return handle
     if not wait:
         return mine
     t0 = time.perf_counter()
@@ -576,6 +623,21 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
         fut.result()
     tick("wait_for_host", t0)
     return [blob for first in sorted(results) for blob in results[first]]
+
+
+class DeferredEncode:
+    """The open end of ``encode_figures_device(..., defer=True)``: ``complete()`` finishes the last group and
+    returns the futures of every group's host work (framing + writing)."""
+
+    def __init__(self, complete):
+        self._complete = complete
+        self.futures: list | None = None
+
+    def complete(self) -> list:
+        if self._complete is not None:
+            fn, self._complete = self._complete, None
+            self.futures = fn()
+        return self.futures or []
 
 
 def write_files_native(lib, paths, group, jobs, rows, packed, offsets, adler, n_threads: int = 16) -> None:
@@ -613,4 +675,4 @@ def write_figures_device(ctx, d_rgba_ptr: int, jobs, max_workers: int = 8, **kwa
         return []
     out = encode_figures_device(ctx, d_rgba_ptr, [fig for _p, fig in jobs], paths=[str(p) for p, _f in jobs],
                                 write_threads=max(1, int(max_workers)), **kwargs)
-    return out if kwargs.get("wait") is False else []
+    return out if kwargs.get("wait") is False else []  # (futures, or a DeferredEncode with defer=True)
