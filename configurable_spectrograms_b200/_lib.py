@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # CSG_LIBRARY: another build of the same ABI (A/B experiments: a kernel variant compiled with a different -D)
 LIB_PATH = os.environ.get("CSG_LIBRARY") or os.path.join(HERE, "libcsgpu.so")
 
-ABI_VERSION = 23
+ABI_VERSION = 24
 F32, F64 = 0, 1
 LAYOUT_TPE, LAYOUT_TEP = 0, 1
 K1_GENERIC, K1_STREAM = 0, 1
@@ -157,6 +157,7 @@ SIGNATURES = {
     "csg_device_count": (_i, []),
     "csg_create": (_vp, [_i, _vp]),
     "csg_create_side": (_vp, [_i, _i]),
+    "csg_create_with_priority": (_vp, [_i, _i]),
     "csg_wait_for": (_i, [_vp, _vp]),
     "csg_destroy": (None, [_vp]),
     "csg_last_error": (C.c_char_p, [_vp]),
@@ -451,15 +452,18 @@ def shared_ring(ctx: "Context", n_slots: int = 3, slot_bytes: int = 1 << 30) -> 
 class Context:
     """One GPU context (``csg_ctx``); all work runs on its stream."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, side: bool = False):
+    def __init__(self, device: int = 0, stream: int | None = None, side: bool = False, priority: int | None = None):
         self.lib = load_library()
         self.handle = None
         if self.lib.csg_device_count() <= 0:
             raise CsgError("no CUDA device available: libcsgpu has no CPU fallback")
         # stream: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream); None/0 = own stream;
         # side: a companion context with its own highest-priority stream (see side_context())
+        # priority: own stream, that many steps more urgent than the least urgent level (0 = default)
         if side:
             h = self.lib.csg_create_side(int(device), 1)
+        elif priority is not None and not stream:
+            h = self.lib.csg_create_with_priority(int(device), int(priority))
         else:
             h = self.lib.csg_create(int(device), _vp(stream) if stream else None)
         if not h:
@@ -483,6 +487,14 @@ class Context:
         if worker is None:
             worker = self._worker = Context(self.device, side=True)
         return worker
+
+    def background_context(self) -> "Context":
+        """A companion context on the LEAST urgent stream: long kernels that should yield to everything else
+        (the K4 encoder beside the next chunk's K2a / K3)."""
+        background = self.__dict__.get("_background")
+        if background is None:
+            background = self._background = Context(self.device, priority=0)
+        return background
 
     def wait_for(self, other: "Context"):
         """Everything enqueued on ``other`` so far happens before what this context enqueues next."""
@@ -594,6 +606,6 @@ def default_context(device: int = 0) -> Context:
     """Process-wide context per device (created on first use)."""
     ctx = _default_ctx.get(device)
     if ctx is None or ctx.handle is None:
-        ctx = Context(device)
+        ctx = Context(device, priority=1)  # one step above background work (see Context.background_context)
         _default_ctx[device] = ctx
     return ctx

@@ -186,22 +186,29 @@ csg_ctx* csg_create(int device, void* external_stream) {
   return ctx;
 }
 
-csg_ctx* csg_create_side(int device, int high_priority) {
+csg_ctx* csg_create_with_priority(int device, int level) {
   csg_ctx* ctx = csg_create(device, nullptr);
-  if (!ctx || !high_priority) return ctx;
-  // swap the default-priority stream for one the block scheduler serves first: small dependent
-  // kernels (the K2b digit loop) then slip in between the blocks of a wide kernel on another stream
+  if (!ctx || level <= 0) return ctx;
+  // swap the default-priority stream for a more urgent one: the block scheduler serves it first, so its
+  // kernels slip in between the blocks of a wide kernel on a less urgent stream
   int least = 0, greatest = 0;
   cudaStream_t s = nullptr;
-  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
-      cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest) == cudaSuccess) {
-    std::lock_guard<std::mutex> hold(cache_of(device).lock);  // csg_dev_free records fences on enrolled streams
-    cudaStreamDestroy(ctx->stream);
-    ctx->stream = s;
-  } else {
-    cudaGetLastError();
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) {
+    int prio = least - level;  // numerically lower = more urgent
+    if (prio < greatest) prio = greatest;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio) == cudaSuccess) {
+      std::lock_guard<std::mutex> hold(cache_of(device).lock);  // csg_dev_free records fences on enrolled streams
+      cudaStreamDestroy(ctx->stream);
+      ctx->stream = s;
+      return ctx;
+    }
   }
+  cudaGetLastError();
   return ctx;
+}
+
+csg_ctx* csg_create_side(int device, int high_priority) {
+  return csg_create_with_priority(device, high_priority ? 1 << 20 : 0);  // the most urgent level there is
 }
 
 int csg_wait_for(csg_ctx* waiter, csg_ctx* signal) {
@@ -263,28 +270,29 @@ int csg_dev_alloc(csg_ctx* ctx, size_t bytes, void** d_ptr) {
     Block hit;
     bool found = false;
     {
+      // a parked block whose fences have all passed; one that is still fenced (another context's kernel
+      // is running: the K4 encoder beside the planner) is left alone rather than waited for
       std::lock_guard<std::mutex> hold(cache.lock);
-      auto it = cache.idle.find(want);
-      if (it != cache.idle.end()) {
+      auto range = cache.idle.equal_range(want);
+      for (auto it = range.first; it != range.second && !found; ++it) {
+        bool ready = true;
+        for (cudaEvent_t ev : it->second.fences)
+          if (cudaEventQuery(ev) != cudaSuccess) {
+            cudaGetLastError();
+            ready = false;
+            break;
+          }
+        if (!ready) continue;
         hit = std::move(it->second);
         cache.idle.erase(it);
         cache.idle_bytes -= want;
         cache.live[hit.ptr] = want;
+        cache.spare_events.insert(cache.spare_events.end(), hit.fences.begin(), hit.fences.end());
         found = true;
+        break;
       }
     }
     if (found) {
-      // The previous owner's work (every stream that existed when the block was released) must be over
-      // before anybody writes to it again.  Nearly always it already is -- owners read their results back
-      // before letting go -- so this is a query, not a wait.
-      for (cudaEvent_t ev : hit.fences) {
-        if (cudaEventQuery(ev) != cudaSuccess) {
-          cudaGetLastError();
-          cudaEventSynchronize(ev);
-        }
-      }
-      std::lock_guard<std::mutex> hold(cache.lock);
-      cache.spare_events.insert(cache.spare_events.end(), hit.fences.begin(), hit.fences.end());
       *d_ptr = hit.ptr;
       return CSG_OK;
     }
@@ -292,7 +300,7 @@ int csg_dev_alloc(csg_ctx* ctx, size_t bytes, void** d_ptr) {
   cudaError_t e = cudaMalloc(d_ptr, want);
   if (e != cudaSuccess && cache.enabled) {  // give the driver back what is parked here, then once more
     cudaGetLastError();
-    trim(cache);
+    trim(cache);  // (cudaFree synchronises: whatever the fences guarded is over afterwards)
     e = cudaMalloc(d_ptr, want);
   }
   if (e != cudaSuccess) {

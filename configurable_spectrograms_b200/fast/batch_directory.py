@@ -348,7 +348,7 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
     # k + 1 and its K2a / K3 run on the main stream -- into the OTHER of two raster buffers, the one chunk k - 1's
     # encode has long finished with.  A chunk passes through three states: `encoding` (kernel launched),
     # `writing` (compressed bytes read back, native threads framing and writing), settled (progress recorded).
-    encoder_ctx = ctx.worker_context()
+    encoder_ctx = ctx.background_context()  # least urgent stream: K2a / K3 of the next chunk overtake the encoder
     raster_buffers: list = [None, None]
     encoding = writing = None
     n_chunk = 0

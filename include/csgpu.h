@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSG_ABI_VERSION 23
+#define CSG_ABI_VERSION 24
 
 #if defined(__GNUC__)
 #define CSG_API __attribute__((visibility("default")))
@@ -66,6 +66,10 @@ CSG_API csg_ctx* csg_create(int device, void* external_stream);
  * next to K2a / K3) overlaps them.  csg_wait_for: everything enqueued on `signal` so far
  * happens before whatever is enqueued on `waiter` from now on. */
 CSG_API csg_ctx* csg_create_side(int device, int high_priority);
+/* a context with its own stream at priority `level` steps above the device's least urgent level (0 = what
+ * csg_create gives; clamped to the most urgent).  The directory driver runs its planner's kernels (K2a / K3,
+ * short) one step above the K4 encoder's (long), and the extrema chain on the most urgent stream. */
+CSG_API csg_ctx* csg_create_with_priority(int device, int level);
 CSG_API int csg_wait_for(csg_ctx* waiter, csg_ctx* signal);
 CSG_API void csg_destroy(csg_ctx* ctx);
 CSG_API const char* csg_last_error(csg_ctx* ctx); /* ctx may be NULL: error of a failed csg_create() */
@@ -78,7 +82,8 @@ CSG_API int csg_device_info(csg_ctx* ctx, char* name, int name_len, int* sm_coun
 /* ------------------------------------------------------------------- memory */
 /* Device blocks come from a per-device cache: csg_dev_free parks the block (fenced with an event on every
    stream of every live context, so nobody gets it back before all work enqueued so far is over) and
-   csg_dev_alloc reuses a parked block of the same size class (4 classes per power of two) -- a directory run
+   csg_dev_alloc reuses a parked block of the same size class (4 classes per power of two) whose fences have
+   passed -- a block still fenced is skipped, never waited for -- a directory run
    allocates per-chunk tables at a rate at which cudaMalloc / cudaFree (device-wide synchronisation, ms each)
    showed up as half the wall time.  CSG_POOL=0 restores plain cudaMalloc / cudaFree; CSG_POOL_MAX_MB caps the
    parked bytes (default 32768).  An allocation the driver refuses is retried after the cache is emptied. */

@@ -778,8 +778,8 @@ def test_device_block_cache_reuses_and_fences(ctx):
     b.free()
     c.free()
     assert ctx.trim() >= 2 << 20 and ctx.cached()[0] == 0
-    # ---- a block released while ANOTHER context's stream still writes it: the next owner must not get it
-    # before those writes are over (cudaFree used to guarantee that by synchronising the device)
+    # ---- a block released while ANOTHER context's stream still writes it: nobody gets it before those writes
+    # are over (cudaFree used to guarantee that by synchronising the device)
     side = ctx.side_context()
     n = 512 << 20
     big = ctx.alloc(n)
@@ -788,11 +788,14 @@ def test_device_block_cache_reuses_and_fences(ctx):
         side._check(side.lib.csg_memset(side.handle, big.ptr, 0xAB, n))
     big.free()
     again = ctx.alloc(n)
-    assert again.ptr == ptr
+    assert again.ptr != ptr  # still fenced by the side stream's fills: left parked, a fresh block is handed out
     again.zero()
     got = again.download(np.uint8, 1 << 20, offset=n - (1 << 20))
     side.sync()
     late = again.download(np.uint8, 1 << 20, offset=n - (1 << 20))
     assert not got.any() and not late.any()
+    third = ctx.alloc(n)  # the fences have passed now: the parked block comes back
+    assert third.ptr == ptr
+    third.free()
     again.free()
     ctx.trim()
