@@ -1,13 +1,19 @@
 #!/bin/bash
-# scratch GPU job: block cache skips fenced blocks; full GPU tests + bench
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench.json 2> gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
-print("value", d["value"], d["ms_per_step"], "parity", d["parity_checked"]["ok"], "png", d["png_stage"]["device_figures_per_s"])
-a=d["api_e2e"]
-for k in ("cold","warm","warm_other"):
-    print(k, round(a[k]["seconds"],3), a[k]["pngs"], a[k]["errors"], {x: y for x, y in a[k]["phases_s"].items() if not x.startswith("png/")})
+# scratch GPU job (4 GPUs): weak + strong series at N=4 and N=2
+run() { # name nproc devices args...
+  name=$1; n=$2; dev=$3; shift 3
+  CUDA_VISIBLE_DEVICES=$dev timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2964$n bench.py --gpus $n "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err
+  echo "$name rc=$?"
+  python - $name <<'PY'
+import json, sys
+try:
+    d=json.loads(open(f"gpurun_out/{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print("  ", d["n_gpus"], d["scaling"], "value", round(d["value"]), "ms/step", round(d["ms_per_step"],3), "e2e", d["e2e"] and round(d["e2e"]["value"],1), "parity", (d.get("parity_checked") or {}).get("ok"), "wait", d["collective"].get("wait_us"))
+except Exception as e:
+    print("   no line:", e)
 PY
-tail -3 gpurun_out/bench.err | cut -c1-300
+}
+run weak4 4 0,1,2,3 --steps 20 --warmup 5 --no-png --no-api-e2e
+run strong4 4 0,1,2,3 --steps 20 --warmup 5 --total-orbits 1000 --no-png --no-api-e2e --no-e2e --no-verify
+run weak2 2 0,1 --steps 20 --warmup 5 --no-png --no-api-e2e
+run strong2 2 0,1 --steps 20 --warmup 5 --total-orbits 1000 --no-png --no-api-e2e --no-e2e --no-verify
