@@ -544,7 +544,7 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference, dist=None, ra
     more GPUs: strong scaling of the call); the clock is the slowest rank's."""
     import shutil
 
-    from configurable_spectrograms_b200 import cdf_utils
+    from configurable_spectrograms_b200 import cdf_utils, overlay
     from configurable_spectrograms_b200.fast.batch_directory import FAST_plot_spectrograms_directory
 
     n = min(args.api_orbits or args.orbits_per_gpu, len(orbits))
@@ -578,6 +578,9 @@ def api_e2e_leg(args, cubes, files, orbits, state, with_reference, dist=None, ra
                 shutil.rmtree("FAST_plots", ignore_errors=True)
             cdf_utils.filtered_orbits_cache.clear()
             cdf_utils.orbit_column_cache.clear()
+            # every run composes its text sprites anew: a directory of NEW orbits has its own times of day, titles
+            # and colour-bar values, and a warm run over the same orbits would find them all in the atlas
+            overlay.ATLAS.clear()
             phases: dict = {}
             prof = None
             if label == "warm2" and os.environ.get("CSG_API_PROFILE") and rank == 0:  # main-thread cProfile of one steady-state call

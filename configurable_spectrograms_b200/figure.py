@@ -333,6 +333,7 @@ class FigureTiles:
 
 _static_blocks: dict = {}
 _tick_blocks: dict = {}  # time / colour-bar tick marks and labels, relative to their box
+ATLAS.on_clear(lambda: (_static_blocks.clear(), _tick_blocks.clear()))  # both hold sprite offsets
 
 
 def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float, pad: int, y_lo: float, y_hi: float):
@@ -361,7 +362,8 @@ def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float
 
     ylabel = ATLAS.text(ax.yaxis.label.text, label_px(ax.yaxis.label), rotate=True) if ax.yaxis.label.text else None
     xlabel = ATLAS.text(ax.xaxis.label.text, label_px(ax.xaxis.label)) if ax.xaxis.label.text else None
-    title = ATLAS.text(ax.title, max(6, int(round((ax.title_fontsize or 12) * pt)))) if ax.title else None
+    # (width, height, word sprites): titles change with every orbit, their words do not
+    title = ATLAS.text_parts(ax.title, max(6, int(round((ax.title_fontsize or 12) * pt)))) if ax.title else None
     log_y = ax.yscale == "log" and y_lo > 0 and y_hi > 0
     if ax.yticks is not None:
         yt = [float(v) for v in ax.yticks]
@@ -413,7 +415,9 @@ def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float
     if xlabel:
         sprite(xlabel, int(bx + bw / 2 - xlabel[2] / 2), by + bh + line_w + tick_len + pad + tick_px + pad)
     if title:
-        sprite(title, int(bx + bw / 2 - title[2] / 2), pad)
+        x0 = max(0, int(bx + bw / 2 - title[0] / 2))
+        for ref, dx, dy in title[2]:
+            sprite(ref, x0 + dx, pad + dy)
     # ---- colour bar: frame, the colormap's ramp (highest value on top), label
     kx = bx + bw + cb_gap
     if cb is not None:
@@ -497,11 +501,13 @@ class SpectrogramFigure:
         area_x, area_w = left * W, (right - left) * W
         area_y, area_h = (1.0 - top) * H, (top - bottom) * H
         if self.suptitle_text:
-            ref = ATLAS.text(self.suptitle_text, int(round((self.suptitle_fontsize or 14) * pt)))
-            out.sprite(ref, (W - ref[2]) // 2, max(pad, int(area_y) - ref[1] - pad) if top < 1.0 else pad)
+            t_w, t_h, parts = ATLAS.text_parts(self.suptitle_text, int(round((self.suptitle_fontsize or 14) * pt)))
+            x0, y0 = max(0, (W - t_w) // 2), max(pad, int(area_y) - t_h - pad) if top < 1.0 else pad
+            for ref, dx, dy in parts:
+                out.sprite(ref, x0 + dx, y0 + dy)
             if top >= 1.0:
-                area_y += ref[1] + 2 * pad
-                area_h -= ref[1] + 2 * pad
+                area_y += t_h + 2 * pad
+                area_h -= t_h + 2 * pad
         for entry in self.texts:  # figure text: (x, y) in figure fractions, y from the bottom
             ref = ATLAS.text(entry["text"], int(round(entry.get("fontsize", 10) * pt)), _rgba(entry.get("color", "black")))
             x = entry["x"] * W - (ref[2] / 2 if entry.get("ha") == "center" else (ref[2] if entry.get("ha") == "right" else 0))

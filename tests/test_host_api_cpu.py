@@ -323,3 +323,58 @@ def test_grouped_executor_serves_run_batch(tmp_path):
     res = run_batch(["a", "boom", "b"], None, functools.partial(GroupedExecutor, process, 8), progress_json_path=None,
                     install_signal_handlers=False)
     assert sorted(res) == [("a", "error"), ("b", "error"), ("boom", "error")]
+
+
+def test_text_sprites_are_composed_from_glyphs_and_survive_an_atlas_reset():
+    """``overlay.SpriteAtlas.text``: strings are put together from per-character coverage masks (one Pillow
+    render per character and size).  A figure composed before and after ``ATLAS.clear()`` (which also empties
+    the layout caches that hold sprite offsets) is the same image; repeated strings share one sprite."""
+    from configurable_spectrograms_b200.figure import SpectrogramFigure
+    from configurable_spectrograms_b200.overlay import ATLAS, SpriteAtlas
+
+    atlas = SpriteAtlas()
+    a, b = atlas.text("12:34", 28), atlas.text("12:34", 28)
+    assert a == b and atlas.text("12:35", 28) != a
+    sprite = atlas.sprite(a)
+    assert sprite.shape == (a[1], a[2], 4) and sprite[..., 3].min() == 255  # opaque on its background
+    ink = sprite[..., 0] < 128
+    assert ink.any() and not ink[0].any() and not ink[-1].any() and not ink[:, 0].any() and not ink[:, -1].any()  # 1 px margin
+    two = atlas.sprite(atlas.text("Orbit 7\nees", 28))
+    one = atlas.sprite(atlas.text("Orbit 7", 28))
+    assert two.shape[0] > one.shape[0] and two.shape[1] == one.shape[1]  # centred under the wider line
+    up = atlas.sprite(atlas.text("Counts", 28, rotate=True))
+    flat = atlas.sprite(atlas.text("Counts", 28))
+    assert np.array_equal(up, np.rot90(flat))
+    red = atlas.sprite(atlas.text("9", 28, color=(255, 0, 0, 255)))
+    assert (red[..., 0] == 255).all() and (red[..., 1] < 255).any()
+
+    # a long string as one sprite per word (titles): put together, the words are the line
+    line = "Orbit 13042 - EES pitch angle (0, 30) gyp"
+    width, height, parts = atlas.text_parts(line, 33)
+    canvas = np.full((height, width, 4), 255, dtype=np.uint8)
+    for ref, dx, dy in parts:
+        canvas[dy : dy + ref[1], dx : dx + ref[2]] = np.minimum(canvas[dy : dy + ref[1], dx : dx + ref[2]], atlas.sprite(ref))
+    whole = atlas._blend((0, 0, 0, 255), (255, 255, 255, 255))[atlas._line(line, 33)]
+    assert np.array_equal(canvas[: whole.shape[0], : whole.shape[1]], whole[:height, :width])
+    assert len(parts) == len(line.split()) and atlas.text_parts("Orbit 99", 33)[2][0][0] == parts[0][0]  # "Orbit" is shared
+    w2, h2, p2 = atlas.text_parts("ab\nabcdef", 33)
+    assert h2 > height and p2[0][1] > 0 and p2[1][1] == 0 and p2[1][2] > p2[0][2]  # centred first line, second line below
+
+    def build():
+        rng = np.random.default_rng(2)
+        fig = SpectrogramFigure(figsize=(12, 4))
+        ax = fig.add_subplot(1, 1, 1)
+        im = ax.imshow(rng.integers(0, 255, (24, 200, 4), dtype=np.uint8), extent=(10957.0, 10957.02, 4.0, 4000.0),
+                       cmap="turbo", vmin=1.0, vmax=2400.0)
+        ax.set_xlim(10957.0, 10957.02)
+        ax.xaxis.set_major_formatter("%H:%M")
+        ax.set_ylabel("Energy (eV)")
+        ax.set_title("Orbit 13042 EES")
+        fig.suptitle("Pitch angle grid\nOrbit 13042")
+        fig.colorbar(im, ax=ax, label="Counts")
+        return fig
+
+    before = build().compose(100)
+    ATLAS.clear()
+    after = build().compose(100)
+    assert np.array_equal(before, after)
