@@ -336,7 +336,7 @@ _tick_blocks: dict = {}  # time / colour-bar tick marks and labels, relative to 
 ATLAS.on_clear(lambda: (_static_blocks.clear(), _tick_blocks.clear()))  # both hold sprite offsets
 
 
-def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float, pad: int, y_lo: float, y_hi: float):
+def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float, pad: int, y_lo: float, y_hi: float, title_h: int = 0):
     """``(tiles, geometry)`` of a subplot's figure-independent part, relative to the cell's top-left corner:
     tiles as ``(rgba_off, ne, nt, x, y, w, h, flags)``; geometry = ``(box x, box y, box w, box h, tick label px,
     tick length, line width, colour-bar x, colour-bar width, colour-bar tick label px)`` or ``None`` when the
@@ -362,8 +362,6 @@ def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float
 
     ylabel = ATLAS.text(ax.yaxis.label.text, label_px(ax.yaxis.label), rotate=True) if ax.yaxis.label.text else None
     xlabel = ATLAS.text(ax.xaxis.label.text, label_px(ax.xaxis.label)) if ax.xaxis.label.text else None
-    # (width, height, word sprites): titles change with every orbit, their words do not
-    title = ATLAS.text_parts(ax.title, max(6, int(round((ax.title_fontsize or 12) * pt)))) if ax.title else None
     log_y = ax.yscale == "log" and y_lo > 0 and y_hi > 0
     if ax.yticks is not None:
         yt = [float(v) for v in ax.yticks]
@@ -386,7 +384,7 @@ def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float
     # ---- margins -> the axes box
     m_left = pad + (ylabel[2] + pad if ylabel else 0) + max([r[2] for r in y_refs] or [0]) + pad + tick_len
     m_bottom = tick_len + pad + tick_px + pad + (xlabel[1] + pad if xlabel else 0) + pad
-    m_top = pad + (title[1] + pad if title else 0)
+    m_top = pad + (title_h + pad if title_h else 0)  # the title itself changes with every orbit: drawn by the caller
     bh = ch - m_top - m_bottom
     bar_w = cb_gap = 0
     m_right = 2 * pad
@@ -414,10 +412,6 @@ def _static_block(ax: "PanelAxes", img: RasterImage, cw: int, ch: int, pt: float
         sprite(ylabel, pad, int(by + bh / 2 - ylabel[1] / 2))
     if xlabel:
         sprite(xlabel, int(bx + bw / 2 - xlabel[2] / 2), by + bh + line_w + tick_len + pad + tick_px + pad)
-    if title:
-        x0 = max(0, int(bx + bw / 2 - title[0] / 2))
-        for ref, dx, dy in title[2]:
-            sprite(ref, x0 + dx, pad + dy)
     # ---- colour bar: frame, the colormap's ramp (highest value on top), label
     kx = bx + bw + cb_gap
     if cb is not None:
@@ -522,7 +516,7 @@ class SpectrogramFigure:
 
     def _axes_tiles(self, out: FigureTiles, ax: PanelAxes, cx, cy, cw, ch, pt, pad, black):
         """One subplot as tiles.  Everything that does not change from figure to figure of a batch -- the box
-        geometry, frames, energy ticks and their labels, axis labels, the title, the colour bar's frame, ramp
+        geometry, frames, energy ticks and their labels, axis labels, the room for the title, the colour bar's frame, ramp
         and label -- is built once per distinct set of settings (``_static_block``) and only shifted to the
         cell; the cusp markers, the time ticks, the colour-bar ticks and the panel itself are per figure."""
         if not ax.images:
@@ -536,14 +530,17 @@ class SpectrogramFigure:
         ex = img.extent if img.extent is not None else (x_lo, x_hi, 0.0, 1.0)
         y_lo, y_hi = float(ex[2]), float(ex[3])
         cb = ax.colorbar
+        # (width, height, word sprites): a title changes with every orbit, its words and its height do not
+        title = ATLAS.text_parts(ax.title, max(6, int(round((ax.title_fontsize or 12) * pt)))) if ax.title else None
+        title_h = title[1] if title else 0
         key = (int(cw), int(ch), pt, pad, ax.tick_labelsize, ax.tick_length, ax.yaxis.label.text, ax.yaxis.label.fontsize,
-               ax.xaxis.label.text, ax.xaxis.label.fontsize, ax.title, ax.title_fontsize,
+               ax.xaxis.label.text, ax.xaxis.label.fontsize, title_h,
                None if ax.yticks is None else tuple(ax.yticks), None if ax.yticklabels is None else tuple(ax.yticklabels),
                ax.yscale, y_lo, y_hi, cb is not None,
                None if cb is None else (cb.label, cb.ax.yaxis.label.text, cb.ax.yaxis.label.fontsize, cb.ax.tick_labelsize, img.cmap))
         hit = _static_blocks.get(key)
         if hit is None:
-            hit = _static_blocks[key] = _static_block(ax, img, int(cw), int(ch), pt, pad, y_lo, y_hi)
+            hit = _static_blocks[key] = _static_block(ax, img, int(cw), int(ch), pt, pad, y_lo, y_hi, title_h)
             if len(_static_blocks) > 512:
                 _static_blocks.clear()
         block, geo = hit
@@ -575,6 +572,10 @@ class SpectrogramFigure:
             out.sprite(ref, int(round(bx + (t["x"] - x_lo) * scale - ref[2] / 2)), int(round(by + (1.0 - t["y"]) * bh)))
         # ---- the static block, shifted to this cell
         records.extend([(o, a, b, x + cx, y + cy, w, h, 0, 0, f, 0) for (o, a, b, x, y, w, h, f) in block])
+        if title:
+            x0 = max(0, int(bx + bw / 2 - title[0] / 2))
+            for ref, dx, dy in title[2]:
+                out.sprite(ref, x0 + dx, cy + pad + dy)
         # ---- time ticks and colour-bar ticks: positions relative to the box, shared by every panel that shows
         # the same time range / value range at the same size (the rows of a grid; the variants of a figure)
         fmt = ax.xaxis.major_formatter

@@ -1,14 +1,14 @@
 #!/bin/bash
-# scratch GPU job: glyph-composed text; warm runs compose their sprites anew
-python -m pytest tests/test_gpu_api.py tests/test_gpu_png.py -m gpu -x -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-verify --no-e2e > gpurun_out/bench.json 2> gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
-print("png", d["png_stage"]["device_figures_per_s"], d["png_stage"]["phases_s"])
-a=d["api_e2e"]
-for k in ("cold","warm","warm_other"):
-    print(k, round(a[k]["seconds"],3), a[k]["pngs"], a[k]["errors"], a[k]["png_mb"], {x: y for x, y in a[k]["phases_s"].items()})
+# scratch GPU job: K2a loads-in-flight variants (A/B through CSG_LIBRARY); layout change validation
+python -m pytest tests/test_gpu_kernels.py tests/test_gpu_png.py tests/test_gpu_api.py -m gpu -x -q 2>&1 | tail -3
+for v in head f2_b6 f3_b6 f4_b5 f4_b4; do
+  CSG_LIBRARY=$PWD/variants/libcsgpu_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-verify --no-e2e --no-png --no-api-e2e > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
+  python - $v <<'PY'
+import json, sys
+try:
+    d=json.loads(open(f"gpurun_out/bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], "region_stats", round(d["stage_ms"]["region_stats"],4), "step", round(d["ms_per_step"],4), "fallbacks", d["stage_ms"]["percentile_regions_needing_radix_fallback"])
+except Exception as e:
+    print(sys.argv[1], "failed", e)
 PY
-tail -3 gpurun_out/bench.err | cut -c1-300
+done
