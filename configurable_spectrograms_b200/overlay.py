@@ -34,6 +34,7 @@ class SpriteAtlas:
         self._fonts: dict = {}
         self._glyphs: dict = {}  # (character, px) -> (coverage mask, advance)
         self._words: dict = {}  # (run of characters, px) -> (coverage mask, advance)
+        self._parts: dict = {}  # (string, px, colour, background) -> text_parts() result
         self._blends: dict = {}  # (colour, background) -> (256, 4) uint8
         self._dependents: list = []
         self._device: dict = {}  # id(ctx) -> (DevBuf, pixels uploaded)
@@ -187,6 +188,10 @@ class SpriteAtlas:
         new -- the words are sprites of their own, shared by every title that uses them."""
         px = int(px)
         fg, bg = tuple(int(c) for c in color), tuple(int(c) for c in background)
+        cache_key = (string, px, fg, bg)
+        cached = self._parts.get(cache_key)
+        if cached is not None:
+            return cached
         space = self._glyph(" ", px)[1]
         gap = max(2, px // 5)
         lines, width, y = [], 0, 0
@@ -212,6 +217,9 @@ class SpriteAtlas:
             y += line_h + gap
         height = max(1, y - gap)
         parts = [(ref, x + (width - line_w) // 2, top) for placed, line_w, top in lines for ref, x in placed]
+        if len(self._parts) > 50_000:
+            self._parts.clear()
+        self._parts[cache_key] = (width, height, parts)
         return width, height, parts
 
     def _blend(self, fg, bg) -> np.ndarray:
@@ -227,7 +235,7 @@ class SpriteAtlas:
         """Forget every sprite (and the device mirrors); the per-character glyph masks stay.  Only between
         runs: tiles built before the call refer to offsets that no longer exist."""
         with self._lock:
-            self._chunks, self._size, self._index, self._device = [], 0, {}, {}
+            self._chunks, self._size, self._index, self._device, self._parts = [], 0, {}, {}, {}
         for forget in self._dependents:
             forget()
 
