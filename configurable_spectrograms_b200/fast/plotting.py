@@ -82,7 +82,7 @@ def figure_from_spec(shard: ShardPlan, spec: FigureSpec, colormap="viridis", cus
             y_kept = row.energy[e_index[[0, -1]]] if len(e_index) > 2 else row.energy[e_index]
             if len(e_index) > 2:
                 y_kept = _Ends(y_kept, len(e_index))
-            x_plot = date2num(row.times[[t_first, t_last]])
+            x_plot = (date2num(float(row.times[t_first])), date2num(float(row.times[t_last])))
             ax = axes[i, j]
             if j == 1:
                 centre, duration = spec.zoom

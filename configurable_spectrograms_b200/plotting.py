@@ -301,9 +301,10 @@ class SpectrogramGroup:
 
 def _decade_ticks(z_lo, z_hi):
     """Colour-bar ticks of a log panel: the powers of ten inside [z_lo, z_hi] (reference ``:288-299``)."""
-    if not (z_lo > 0 and z_hi > 0 and np.isfinite(z_lo) and np.isfinite(z_hi)):
+    z_lo, z_hi = float(z_lo), float(z_hi)
+    if not (z_lo > 0 and z_hi > 0 and math.isfinite(z_lo) and math.isfinite(z_hi)):
         return None
-    decades = range(int(np.floor(np.log10(z_lo))), int(np.ceil(np.log10(z_hi))) + 1)
+    decades = range(int(math.floor(math.log10(z_lo))), int(math.ceil(math.log10(z_hi))) + 1)
     return [10**k for k in decades if z_lo <= 10**k <= z_hi]
 
 
@@ -346,9 +347,11 @@ def draw_panel(axis_object, rgba, index, z_lo, z_hi, log_scale, x_axis_plot, y_k
                 ax.set_yticklabels([f"{int(v)}" for v in ticks])
     if x_axis_is_unix:  # seconds matter only on a window shorter than two minutes (:357-368)
         left, right = ax.get_xlim()
-        ax.xaxis.set_major_formatter("%H:%M:%S" if (num2date(right) - num2date(left)).total_seconds() < 120 else "%H:%M")
+        # (num2date(right) - num2date(left)).total_seconds(): both ends rounded to microseconds, then subtracted
+        span_us = round(float(right) * 86400e6) - round(float(left) * 86400e6)
+        ax.xaxis.set_major_formatter("%H:%M:%S" if span_us / 1e6 < 120 else "%H:%M")
     if vertical_lines_unix is not None and len(vertical_lines_unix) > 0:
-        positions = date2num(list(vertical_lines_unix)) if x_axis_is_unix else vertical_lines_unix
+        positions = [date2num(float(v)) for v in vertical_lines_unix] if x_axis_is_unix else vertical_lines_unix
         inside = [v for v in positions if x_axis_plot[0] <= v <= x_axis_plot[-1]]
         options = dict(cusp_marker_kwargs or {})
         options.setdefault("line_color", "white" if colormap in _RED_HEAVY_COLORMAPS else "red")
