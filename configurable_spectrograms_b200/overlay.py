@@ -27,7 +27,7 @@ class SpriteAtlas:
     """Flat store of RGBA sprites (uint32 pixels, row-major, top row first) with a device mirror per context."""
 
     def __init__(self):
-        self._chunks: list[np.ndarray] = []
+        self._store = np.empty(0, dtype=np.uint32)  # every sprite's pixels, back to back; grows by doubling
         self._size = 0
         self._index: dict = {}
         self._lock = threading.Lock()
@@ -47,9 +47,14 @@ class SpriteAtlas:
         with self._lock:
             hit = self._index.get(key)
             if hit is None:
+                need = self._size + flat.size
+                if need > len(self._store):  # the store doubles: readers keep views of the old one, which stay valid
+                    grown = np.empty(max(need, 2 * len(self._store), 1 << 16), dtype=np.uint32)
+                    grown[: self._size] = self._store[: self._size]
+                    self._store = grown
+                self._store[self._size : need] = flat
                 hit = self._index[key] = (self._size, h, w)
-                self._chunks.append(flat)
-                self._size += flat.size
+                self._size = need
         return hit
 
     def solid(self, color) -> tuple[int, int, int]:
@@ -152,9 +157,18 @@ class SpriteAtlas:
         colour-bar values); shaping each with Pillow cost 0.7 ms, more than everything else the host does for
         the figure.  Strings are therefore composed here from per-character coverage masks (Pillow renders a
         character once per size; no kerning), ~30 us each."""
+        if type(color) is not tuple:
+            color = tuple(int(c) for c in color)
+        if type(background) is not tuple:
+            background = tuple(int(c) for c in background)
+        key = ("text", string, px, color, rotate, background)
+        hit = self._index.get(key)
+        if hit is not None:
+            return hit
         key = ("text", string, int(px), tuple(int(c) for c in color), bool(rotate), tuple(int(c) for c in background))
         hit = self._index.get(key)
         if hit is not None:
+            self._index[("text", string, px, color, rotate, background)] = hit  # (the caller's spelling of the same key)
             return hit
         px = int(px)
         lines = [self._line(line, px) for line in string.split("\n")]
@@ -235,7 +249,7 @@ class SpriteAtlas:
         """Forget every sprite (and the device mirrors); the per-character glyph masks stay.  Only between
         runs: tiles built before the call refer to offsets that no longer exist."""
         with self._lock:
-            self._chunks, self._size, self._index, self._device, self._parts = [], 0, {}, {}, {}
+            self._store, self._size, self._index, self._device, self._parts = np.empty(0, dtype=np.uint32), 0, {}, {}, {}
         for forget in self._dependents:
             forget()
 
@@ -245,11 +259,9 @@ class SpriteAtlas:
 
     # ------------------------------------------------------------------- access
     def pixels(self) -> np.ndarray:
-        """The whole store as one uint32 array (host composer, uploads)."""
+        """The whole store as one uint32 array (host composer, uploads): a view, valid until the store grows."""
         with self._lock:
-            if len(self._chunks) > 1:
-                self._chunks = [np.concatenate(self._chunks)]
-            return self._chunks[0] if self._chunks else np.zeros(0, np.uint32)
+            return self._store[: self._size]
 
     def sprite(self, ref) -> np.ndarray:
         """(h, w, 4) uint8 view of one sprite."""

@@ -1,12 +1,4 @@
 #!/bin/bash
-# scratch GPU job (8 GPUs): the default bench line exactly as the driver launches it
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29688 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench8.json 2> gpurun_out/bench8.err
-echo "bench8 rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/bench8.json").read().strip().splitlines()[-1])
-print({k: d[k] for k in ("value","n_gpus","ms_per_step","scaling","gpu_launches")}, "e2e", d["e2e"]["value"], d["e2e"]["frac_of_h2d_ceiling"], "parity", d["parity_checked"]["ok"])
-a=d["api_e2e"]; print("api", a["value"], a["n_gpus"], "cold", a["cold"]["seconds"], "warm", a["warm"]["seconds"], a["warm"]["pngs"], a["warm"]["errors"], a["warm"]["phases_s"])
-print(d["collective"]["wait_us"], d["clocks"], d["stage_ms"])
-PY
-tail -3 gpurun_out/bench8.err | cut -c1-300
+# scratch GPU job: all-thread cProfile of one steady-state directory call
+CSG_API_PROFILE=$PWD/gpurun_out/api_profile.txt python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-verify --no-png > gpurun_out/bench.json 2> gpurun_out/bench.err
+grep -v "^$" gpurun_out/api_profile.txt | awk '/Ordered by: internal time/{p=1} p' | cut -c1-150 | head -50
