@@ -104,3 +104,39 @@ def test_load_fast_cdf_dataset_from_a_cdf_file(tmp_path, stored_layout):
     assert ds["data"].shape == ref["data"].shape and ds["data"].dtype == ref["data"].dtype
     assert ds["data"].flags.c_contiguous == ref["data"].flags.c_contiguous  # the transposed view is kept a view
     assert np.array_equal(ds["data"], ref["data"], equal_nan=True)
+
+
+@pytest.mark.parametrize("gzip", [None, 6])
+def test_reader_against_cdflib_when_it_is_installed(tmp_path, gzip):
+    """The native reader is "parity unpinned" because ``cdflib`` (the reference's reader,
+    ``CS/cdf_utils.py:247-251``) is not installable offline.  The day it is, this test pins both halves by
+    itself: a file ``cdflib`` WRITES must read the same through ``csrc/cdf.cpp`` as through ``cdflib``, and
+    a file of ``tests/cdf_writer.py`` must read the same through ``cdflib`` (skipped until then)."""
+    cdflib = pytest.importorskip("cdflib")
+    if not hasattr(cdflib, "CDF") or "oracle" in (getattr(cdflib, "__file__", "") or ""):
+        pytest.skip("a cdflib stand-in is on the path, not cdflib")
+    from configurable_spectrograms_b200.cdf_reader import CdfFile
+
+    rng = np.random.default_rng(11)
+    variables = _vars(rng)
+    for v in variables:
+        v["gzip"] = gzip
+        v["records_per_block"] = 8
+    ours = tmp_path / "ours.cdf"
+    W.write_cdf(ours, variables, encoding=W.IBMPC)
+    theirs_reader = cdflib.CDF(str(ours))
+    for v in variables:  # our writer -> cdflib
+        assert np.array_equal(np.asarray(theirs_reader.varget(v["name"])), v["data"]), v["name"]
+    writer = getattr(getattr(cdflib, "cdfwrite", None), "CDF", None)
+    if writer is None:
+        return
+    theirs = tmp_path / "theirs.cdf"
+    out = writer(str(theirs), cdf_spec={"Compressed": 6 if gzip else 0}, delete=True)
+    for k, v in enumerate(variables):
+        spec = {"Variable": v["name"], "Data_Type": W.CDF_TYPES[v["data"].dtype], "Num_Elements": 1, "Rec_Vary": True,
+                "Var_Type": "zVariable", "Dim_Sizes": list(v["data"].shape[1:]), "Compress": 6 if gzip else 0}
+        out.write_var(spec, var_data=v["data"])
+    out.close()
+    with CdfFile(str(theirs)) as cdf:  # cdflib's writer -> the native reader
+        for v in variables:
+            assert np.array_equal(cdf.read(v["name"]), v["data"]), v["name"]
