@@ -133,6 +133,26 @@ def FAST_plot_spectrograms_directory(
                 pass
 
 
+class _OpenEncode:
+    """Leaves no deferred K4 encode open when the chunk loop is left by an exception (an interrupt): the next
+    call in this process finds the encoder context free."""
+
+    def __init__(self, current):
+        self._current = current
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, kind, _value, _trace):
+        state = self._current()
+        if kind is not None and state is not None and hasattr(state[0], "abandon"):
+            try:
+                state[0].abandon()
+            except Exception:
+                pass
+        return False
+
+
 def _chunk_orbits_default() -> int:
     """Orbits per streaming chunk (``CSG_CHUNK_ORBITS``): a nominal 4-instrument orbit is 84 MB of cubes,
     so the default keeps one pinned slot / the device staging buffer near 0.7 GB."""
@@ -382,7 +402,7 @@ def _run_directory(directory_path, output_base, y_scale, z_scale, zoom_duration_
                     since_flush = 0
         return since_flush
 
-    with ThreadPoolExecutor(max_workers=n_threads) as pool:
+    with ThreadPoolExecutor(max_workers=n_threads) as pool, _OpenEncode(lambda: encoding):
         for a in range(0, len(my_pending), chunk_n):
             chunk = my_pending[a : a + chunk_n]
             t_chunk = _time.perf_counter()

@@ -613,7 +613,15 @@ def encode_figures_device(ctx, d_rgba_ptr: int, figures, dpi: float | None = Non
                 keep_alive.clear()
             return mine
 
-        handle = DeferredEncode(complete_open)
+        def abandon_open():
+            try:
+                ctx.sync()  # the kernel still reads the tables kept alive here
+            finally:
+                scratch["deferred"] = None
+                keep_alive.clear()
+                settle_failed()
+
+        handle = DeferredEncode(complete_open, abandon_open)
         scratch["deferred"] = handle
         return handle
     if not wait:
@@ -629,15 +637,22 @@ class DeferredEncode:
     """The open end of ``encode_figures_device(..., defer=True)``: ``complete()`` finishes the last group and
     returns the futures of every group's host work (framing + writing)."""
 
-    def __init__(self, complete):
-        self._complete = complete
+    def __init__(self, complete, abandon=None):
+        self._complete, self._abandon = complete, abandon
         self.futures: list | None = None
 
     def complete(self) -> list:
         if self._complete is not None:
-            fn, self._complete = self._complete, None
+            fn, self._complete, self._abandon = self._complete, None, None
             self.futures = fn()
         return self.futures or []
+
+    def abandon(self) -> None:
+        """Give the last group up (an interrupted run): wait for its kernel, release the context for the next
+        encode; the groups already handed over finish as usual."""
+        if self._abandon is not None:
+            fn, self._complete, self._abandon = self._abandon, None, None
+            fn()
 
 
 def write_files_native(lib, paths, group, jobs, rows, packed, offsets, adler, n_threads: int = 16) -> None:

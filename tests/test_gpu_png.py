@@ -2,6 +2,7 @@
 the image the host composer builds (figure.SpectrogramFigure.compose -- the oracle of this stage)."""
 
 import io
+import os
 
 import numpy as np
 import pytest
@@ -111,3 +112,24 @@ def test_device_png_matches_host_compose(ctx):
     raws = [f.compose(200).nbytes for f in host_figs]
     assert sizes[0] < 0.2 * raws[0]
     assert all(s < 0.5 * r + 2000 for s, r in zip(sizes, raws))
+    # ---- deferred mode (the directory driver's): files through the native writer; the last group is completed
+    # later, or given up -- after which the context encodes again
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = [f"{tmp}/f{k}.png" for k in range(len(dev_figs))]
+        for budget in (160_000, 700):  # everything deferred / only the last of several groups
+            handle = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, dpi=100, max_segments=budget, paths=paths, wait=False, defer=True)
+            with pytest.raises(RuntimeError, match="deferred encode is still open"):
+                png.encode_figures_device(ctx, d_rgba.ptr, dev_figs[:1], dpi=100)
+            for fut in handle.complete():
+                fut.result()
+            assert handle.complete() == handle.futures  # idempotent
+            for path, fig in zip(paths, host_figs):
+                assert np.array_equal(png.decode_rgba(open(path, "rb").read()), fig.compose(100))
+                os.remove(path)
+        handle = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, dpi=100, paths=paths, wait=False, defer=True)
+        handle.abandon()
+        assert handle.complete() == [] and not any(os.path.exists(p) for p in paths)
+        blobs = png.encode_figures_device(ctx, d_rgba.ptr, dev_figs, dpi=100)  # the context is free again
+        assert np.array_equal(png.decode_rgba(blobs[0]), host_figs[0].compose(100))
