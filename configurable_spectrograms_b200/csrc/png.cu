@@ -43,7 +43,14 @@ constexpr int kPixStride = 33;       // padded piece stride (words): conflict-fr
 constexpr int kTokWords = 37;        // per-lane token buffer: 32 pixels x 36 bits + header / trailer bits
 constexpr int kHeaderWords = 40;     // block header (BFINAL/BTYPE + a dynamic block's code lengths): <= 160 bytes
 constexpr int kMergedWords = kPieces * kTokWords + kHeaderWords + 4;
-constexpr int kWarpsPerBlock = 4;
+#ifndef CSG_K4_WARPS
+#define CSG_K4_WARPS 1
+#endif
+// One warp = one segment = one block: segments differ a lot in work (a dismissed one ends at once, a line of new
+// spectrogram cells takes the full tokeniser), and a block lives as long as its slowest warp.  Measured on 320
+// figures of 4800x2400: 115.6 / 96.8 / 85.5 ms with 4 / 2 / 1 warps per block (achieved occupancy was 13.7 % of a
+// theoretical 25 % with 4).
+constexpr int kWarpsPerBlock = CSG_K4_WARPS;
 
 // The code tables of one batch of figures (csg_png_tables in csgpu.h): either RFC 1951's fixed codes
 // or a custom (dynamic-block) code built by the host from the batch's own symbol counts.  Codes are
