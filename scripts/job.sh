@@ -1,15 +1,10 @@
 #!/bin/bash
-# scratch GPU job: K4 warps per block 4 (default) / 2 / 1
-for v in default w2 w1; do
-  lib=$PWD/configurable_spectrograms_b200/libcsgpu.so; [ $v != default ] && lib=$PWD/variants/libcsgpu_$v.so
-  CSG_LIBRARY=$lib python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-verify --no-e2e --no-api-e2e --png-orbits 16 > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
-  python - $v <<'PY'
-import json, sys
-try:
-    d=json.loads(open(f"gpurun_out/bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    p=d["png_stage"]; print(sys.argv[1], "figs/s", round(p["device_figures_per_s"]), "encode", round(p["phases_s"]["encode_kernel_and_sizes"],4), "figures", p["figures"], "ratio", round(p["device_ratio"],2))
-except Exception as e:
-    print(sys.argv[1], "failed", e)
+# scratch GPU job: final validation of HEAD on one GPU (what the driver runs at round end)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest.log; cat gpurun_out/pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value","ms_per_step","gpu_launches")}, "e2e", d["e2e"]["value"], "api", d["api_e2e"]["value"], d["api_e2e"]["warm"]["seconds"], d["api_e2e"]["cold"]["seconds"], "png", d["png_stage"]["device_figures_per_s"], "parity", d["parity_checked"]["ok"], d["clocks"]["reasons"])
 PY
-done
-CSG_LIBRARY=$PWD/variants/libcsgpu_w1.so python -m pytest tests/test_gpu_png.py -m gpu -x -q 2>&1 | tail -2
