@@ -1,10 +1,11 @@
 #!/bin/bash
-# scratch GPU job: planning threads 16 (default) / 4 / 1
-for t in 16 4 1; do
-  CSG_RENDER_THREADS=$t python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-verify --no-e2e --no-png > gpurun_out/bench_t$t.json 2> gpurun_out/bench_t$t.err
-  python - $t <<'PY'
-import json, sys
-d=json.loads(open(f"gpurun_out/bench_t{sys.argv[1]}.json").read().strip().splitlines()[-1])
-a=d["api_e2e"]; print("threads", sys.argv[1], "warm", round(a["warm"]["seconds"],3), round(a["warm_other"]["seconds"],3), "figures_host", a["warm"]["phases_s"]["figures_host"], a["warm_other"]["phases_s"]["figures_host"], "tile", a["warm"]["phases_s"]["png/tile_tables"])
+# GPU job run by scripts/gpusnap.sh (rewritten per call while developing); this version: what the driver runs at
+# round end on one GPU -- the GPU tests, the smoke run, the default bench line
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest.log; cat gpurun_out/pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value","ms_per_step","gpu_launches")}, "e2e", d["e2e"]["value"], "api", d["api_e2e"]["value"], d["api_e2e"]["warm"]["seconds"], d["api_e2e"]["cold"]["seconds"], d["api_e2e"]["warm"]["pngs"], d["api_e2e"]["warm"]["errors"], "png", d["png_stage"]["device_figures_per_s"], "parity", d["parity_checked"]["ok"], d["clocks"]["reasons"])
 PY
-done
