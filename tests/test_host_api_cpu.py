@@ -378,3 +378,59 @@ def test_text_sprites_are_composed_from_glyphs_and_survive_an_atlas_reset():
     ATLAS.clear()
     after = build().compose(100)
     assert np.array_equal(before, after)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_content_rows_property_on_random_figures(seed):
+    """K4's host half on random layouts (grid, size, dpi, panel shapes, log / linear colour bars, markers): a
+    scanline that ``content_rows`` does not list is pixel-identical to the line above it in the composed
+    image -- the property that lets the device encode the listed lines only -- and Adler-32 partial sums of
+    arbitrary segmentations combine to zlib's checksum."""
+    import zlib
+
+    from configurable_spectrograms_b200 import png
+    from configurable_spectrograms_b200.figure import SpectrogramFigure
+
+    rng = np.random.default_rng(seed)
+    n_rows, n_cols = int(rng.integers(1, 4)), int(rng.integers(1, 3))
+    fig = SpectrogramFigure(figsize=(float(rng.uniform(4, 13)) * n_cols, float(rng.uniform(1.5, 3.5)) * n_rows))
+    if seed % 2:
+        fig.suptitle(f"Orbit {13000 + seed} - random layout\nline two")
+    for cell in range(1, n_rows * n_cols + 1):
+        if rng.random() < 0.15:
+            continue  # an empty cell
+        ne, nt = int(rng.integers(1, 90)), int(rng.integers(1, 700))
+        ax = fig.add_subplot(n_rows, n_cols, cell)
+        x0 = 10957.0 + float(rng.random())
+        x1 = x0 + float(rng.uniform(1e-4, 0.03))
+        log = bool(rng.random() < 0.5)
+        im = ax.imshow(rng.integers(0, 255, (ne, nt, 4), dtype=np.uint8), extent=(x0, x1, 4.0, 4000.0), cmap="viridis",
+                       norm="log" if log else None, vmin=1.0 if log else 0.0, vmax=float(rng.uniform(20, 5000)))
+        ax.set_xlim(x0, x1)
+        ax.xaxis.set_major_formatter("%H:%M:%S" if x1 - x0 < 120 / 86400 else "%H:%M")
+        ax.set_ylabel("Energy (eV)")
+        ax.set_title(f"panel {cell} of seed {seed}")
+        if rng.random() < 0.7:
+            fig.colorbar(im, ax=ax, label="Counts")
+        if rng.random() < 0.6:
+            ax.axvline(x0 + 0.4 * (x1 - x0), color="red", linewidth=float(rng.uniform(0.5, 4)))
+    dpi = float(rng.choice([37, 72, 100, 150]))
+    tiles = fig.tiles(dpi)
+    img = fig.compose(dpi)
+    assert img.shape == (tiles.H, tiles.W, 4)
+    rows = tiles.content_rows()
+    assert rows[0] == 0 and np.all(np.diff(rows) > 0) and rows[-1] < tiles.H
+    listed = np.zeros(tiles.H, dtype=bool)
+    listed[rows] = True
+    for line in np.flatnonzero(~listed):
+        assert np.array_equal(img[line], img[line - 1]), (seed, int(line))
+    # Adler-32 from per-segment partial sums, any segmentation
+    raw = rng.integers(0, 256, int(rng.integers(1, 40_000)), dtype=np.uint8)
+    cuts = np.unique(np.concatenate([[0, len(raw)], rng.integers(0, len(raw) + 1, 12)]))
+    sa, sb, ln = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        seg = raw[a:b].astype(np.int64)
+        sa.append(int(seg.sum() % 65521))
+        sb.append(int((seg * (len(seg) - np.arange(len(seg)))).sum() % 65521))
+        ln.append(len(seg))
+    assert png.adler32_of_segments(np.array(sa), np.array(sb), np.array(ln)) == zlib.adler32(raw.tobytes())
