@@ -28,6 +28,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -252,7 +254,8 @@ int parse_image(csg_cdf* f) {
     st = rec_header(f, cpr, 11, &cpr_size);
     if (st != CSG_OK) return st;
     if (be32(f->base + cpr + 12) != 5) return cdf_fail("whole-file compression type %d is not gzip", be32(f->base + cpr + 12));
-    if (usize < 0 || usize > ((int64_t)1 << 36)) return cdf_fail("implausible uncompressed size");
+    if (usize < 0 || usize > ((int64_t)1 << 36) || (double)usize > 1100.0 * (double)size + 65536.0)
+      return cdf_fail("implausible uncompressed size");
     std::vector<uint8_t> image((size_t)usize + 8);
     memcpy(image.data(), f->base, 4);
     const uint32_t plain = 0x0000FFFFu;
@@ -333,6 +336,9 @@ int read_extent(csg_cdf* f, const VarIndex& v, const VarIndex::Extent& ex, int32
     const int64_t csize = be64(f->base + ex.offset + 16);
     if (csize < 0 || 24 + csize > size) return cdf_fail("CVVR of %s is malformed", v.name.c_str());
     const size_t full = (size_t)(ex.last - ex.first + 1) * rec_bytes;
+    // DEFLATE cannot expand more than ~1032 : 1: an index entry that claims more is damaged
+    if (ex.last < ex.first || (double)full > 1100.0 * (double)csize + 65536.0)
+      return cdf_fail("CVVR of %s cannot hold records %d..%d", v.name.c_str(), ex.first, ex.last);
     if (skip == 0 && want == full && !f->swap) {  // inflate straight into the destination
       size_t produced = 0;
       st = inflate_into(f->base + ex.offset + 24, (size_t)csize, dst, want, &produced);
@@ -374,10 +380,19 @@ int csg_cdf_open(const char* path, csg_cdf** out) {
   close(fd);
   if (map == MAP_FAILED) return cdf_fail("mmap of %s failed: %s", path, strerror(errno));
   madvise(map, (size_t)sb.st_size, MADV_SEQUENTIAL);
-  csg_cdf* f = new csg_cdf();
+  csg_cdf* f = new (std::nothrow) csg_cdf();
+  if (!f) {
+    munmap(map, (size_t)sb.st_size);
+    return cdf_fail("out of memory");
+  }
   f->map = map, f->map_size = (size_t)sb.st_size;
   f->base = (const uint8_t*)map, f->size = (size_t)sb.st_size;
-  const int st = parse_image(f);
+  int st;
+  try {  // a damaged size field must come back as an error, never as an exception across the C boundary
+    st = parse_image(f);
+  } catch (const std::exception& e) {
+    st = cdf_fail("%s is damaged (%s)", path, e.what());
+  }
   if (st != CSG_OK) {
     csg_cdf_close(f);
     return st;
@@ -413,7 +428,17 @@ int csg_cdf_var_info(csg_cdf* f, const char* name, int index, csg_cdf_var* info)
   return CSG_OK;
 }
 
+static int cdf_read_checked(csg_cdf* f, const char* name, int64_t rec0, int64_t n_rec, void* dst, size_t dst_bytes);
+
 int csg_cdf_read(csg_cdf* f, const char* name, int64_t rec0, int64_t n_rec, void* dst, size_t dst_bytes) {
+  try {
+    return cdf_read_checked(f, name, rec0, n_rec, dst, dst_bytes);
+  } catch (const std::exception& e) {
+    return cdf_fail("reading %s failed (%s): the file is damaged", name ? name : "?", e.what());
+  }
+}
+
+static int cdf_read_checked(csg_cdf* f, const char* name, int64_t rec0, int64_t n_rec, void* dst, size_t dst_bytes) {
   if (!f || !name || (!dst && n_rec > 0)) return cdf_fail("csg_cdf_read: NULL argument");
   VarIndex* v = find_var(f, name);
   if (!v) return cdf_fail("variable %s not found", name);

@@ -140,3 +140,70 @@ def test_reader_against_cdflib_when_it_is_installed(tmp_path, gzip):
     with CdfFile(str(theirs)) as cdf:  # cdflib's writer -> the native reader
         for v in variables:
             assert np.array_equal(cdf.read(v["name"]), v["data"]), v["name"]
+
+
+_FUZZ = r'''
+import os, sys, tempfile
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tests import cdf_writer as W
+from configurable_spectrograms_b200.cdf_reader import CdfFile
+
+seed = int(sys.argv[2])
+rng = np.random.default_rng(seed)
+variables = [
+    {"name": "time_unix", "data": 946684800.0 + 2.5 * np.arange(37), "gzip": 6 if seed % 3 == 0 else None, "records_per_block": 5},
+    {"name": "data", "data": rng.gamma(2.0, 3.0, (37, 5, 7)).astype(np.float32), "gzip": 6 if seed % 2 else None,
+     "records_per_block": 4, "two_level": seed % 4 == 0, "sparse": {3, 4, 20} if seed % 5 == 0 else None,
+     "pad": -1.0 if seed % 5 == 0 else None},
+    {"name": "counts", "data": rng.integers(-5, 1000, (37, 3), dtype=np.int32)},
+]
+tmp = tempfile.mkdtemp()
+good = os.path.join(tmp, "good.cdf")
+W.write_cdf(good, variables, encoding=W.NETWORK if seed % 2 else W.IBMPC, file_gzip=seed % 7 == 0)
+blob = bytearray(open(good, "rb").read())
+clean = errors = 0
+for trial in range(int(sys.argv[3])):
+    b = bytearray(blob)
+    mode = trial % 4
+    if mode == 0:
+        b = b[: int(rng.integers(0, len(b)))]
+    elif mode == 1:
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(8, len(b)))] = int(rng.integers(0, 256))
+    elif mode == 2:
+        at = int(rng.integers(8, len(b) - 8))
+        b[at : at + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+    else:
+        at = int(rng.integers(8, min(len(b) - 8, 900)))
+        b[at : at + 4] = int(rng.integers(0, 1 << 31)).to_bytes(4, "big")
+    path = os.path.join(tmp, "damaged.cdf")
+    open(path, "wb").write(bytes(b))
+    try:
+        with CdfFile(path) as cdf:
+            for name in cdf.variables():
+                if np.prod(cdf.shape(name), dtype=np.float64) > 1e8:
+                    raise MemoryError("implausible shape")
+                cdf.read(name)
+        clean += 1
+    except Exception:
+        errors += 1
+print("FUZZ_DONE", clean, errors)
+'''
+
+
+@pytest.mark.parametrize("seed", [2, 5, 7, 12])
+def test_reader_survives_damaged_files(seed):
+    """Truncated files, flipped bytes, overwritten offsets and sizes: the reader answers with an error (or
+    with data, when the damage missed what it reads) -- never with a crash, an exception across the C boundary
+    (a damaged size once ended in ``std::bad_alloc`` -> abort) or an unbounded allocation.  Run in a child
+    process so that a crash is a failed test."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FUZZ, root, str(seed), "240"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "FUZZ_DONE" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+    clean, errors = (int(x) for x in r.stdout.split("FUZZ_DONE")[1].split()[:2])
+    assert clean + errors == 240 and errors > 0
