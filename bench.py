@@ -890,15 +890,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = (cube_bytes + sums_bytes) / (k1_ms / 1e3) / 1e9
-    # DRAM bytes of one K1 launch from the committed `ncu --set full` capture of this same
-    # workload (profiles/r1_k1_traffic.json, written by scripts/ncu_summary.py --traffic)
+    # DRAM bytes of one K1 launch from the committed `ncu --set full` capture of this same workload
+    # (profiles/r2_k1_traffic.json -- the round-1 capture as a fallback -- written by scripts/ncu_summary.py --traffic)
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
-        if tr.get("orbits_per_gpu") == n_local and tr.get("algorithmic_bytes") == int(cube_bytes + sums_bytes):
-            traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
-    except (OSError, ValueError, KeyError):
-        pass
+    for name in ("r2_k1_traffic.json", "r1_k1_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if tr.get("orbits_per_gpu") == n_local and tr.get("algorithmic_bytes") == int(cube_bytes + sums_bytes):
+                traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+                break
+        except (OSError, ValueError, KeyError):
+            pass
     # the whole step against the same roofline: SURVEY.md section 8(d)'s B_orbit, i.e. cube read +
     # (G+1) sums written + one pass over the total for the pooled extrema + per panel pixel
     # (stats read + raster read + RGBA write)
