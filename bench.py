@@ -304,7 +304,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "orbits/s", "cores": cores, "kind": kind, "sample": sample, "sample_orbits": n, **extra},
         "e2e": {"value": value, "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -1014,12 +1014,29 @@ def main():
                          "rasterise": raster_ms, "host_enqueue_per_step": host_enqueue_ms, "first_step_with_planning": t_plan * 1e3,
                          "percentile_regions_needing_radix_fallback": fallbacks},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         if exchange is not None and hasattr(exchange, "close"):
             exchange.close()  # collective: unmap the peers' mailboxes, barrier, free the own one
         torch.distributed.destroy_process_group()
 
 
+_JSON_FD = None  # the real stdout while everything else is diverted to stderr (see the bottom of the file)
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout."""
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    fd = 1 if _JSON_FD is None else _JSON_FD
+    while data:
+        data = data[os.write(fd, data):]
+
+
 if __name__ == "__main__":
+    # stdout carries the JSON line and nothing else: what this process, its worker processes (the reference's
+    # fork pool logs to stdout) or a library print meanwhile goes to stderr
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     main()
