@@ -78,3 +78,25 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M):
                     offenders.append(os.path.join(dirpath, name))
     assert offenders == []
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """``bench.py --impl reference`` (CPU only: the unmodified reference from ``oracle/_ref`` on the host cores)
+    on a one-orbit sample: exit 0, stdout = the ONE JSON line of the contract with the reference arm's keys --
+    the reference's own log lines (it prints ``[ERROR] Failed to load progress JSON`` to stdout) go to stderr."""
+    import json
+    import subprocess
+    import sys
+
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")):
+        pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()')")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-orbits", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "orbits/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["vs_baseline"] is None
